@@ -1,0 +1,100 @@
+/* capi_host.cpp — the host-only entry points of include/simmr_b200.h: genome
+ * ingest (genome.rs, main.rs:117-162), genome file and metadata (files.rs),
+ * abundance counts (abundance_profiles/), profile scalars (error_profiles/)
+ * and the table introspection the parity tests use.  No CUDA calls here. */
+#include "host_model.hpp"
+
+#include <cstring>
+#include <fstream>
+
+using namespace simmr;
+
+namespace { thread_local std::string g_err; int flunk(int code, const std::string &m) { g_err = m; return code; } }
+
+struct simmr_genome_builder { GenomeStore store; };
+
+extern "C" {
+
+int simmr_builder_create(simmr_genome_builder **out) { if (!out) return SIMMR_E_INVALID; *out = new simmr_genome_builder; return SIMMR_OK; }
+void simmr_builder_destroy(simmr_genome_builder *b) { delete b; }
+const char *simmr_builder_error(const simmr_genome_builder *b) { return b ? b->store.err.c_str() : ""; }
+int simmr_builder_add_fasta(simmr_genome_builder *b, const char *path, const char *uuid, int contiguous) {
+    if (!b || !path) return SIMMR_E_INVALID;
+    return b->store.add_fasta(path, uuid, contiguous != 0);
+}
+int simmr_builder_filter(simmr_genome_builder *b, uint16_t min_size, uint8_t *kept) {
+    if (!b) return SIMMR_E_INVALID;
+    b->store.filter(min_size, kept);
+    return SIMMR_OK;
+}
+int simmr_builder_view(const simmr_genome_builder *b, simmr_genome_set *out) {
+    if (!b || !out) return SIMMR_E_INVALID;
+    b->store.view(*out);
+    return SIMMR_OK;
+}
+uint64_t simmr_builder_genome_size(const simmr_genome_builder *b, uint32_t g) { return b && g < b->store.genome_size.size() ? b->store.genome_size[g] : 0; }
+
+int64_t simmr_parse_genome_file(const char *path, char *out, uint64_t cap) {
+    std::string text, err;
+    const int64_t n = parse_genome_file(path, text, err);
+    if (n < 0) return flunk(int(n), err);
+    if (text.size() + 1 > cap) return flunk(SIMMR_E_INVALID, "buffer too small");
+    memcpy(out, text.c_str(), text.size() + 1);
+    return n;
+}
+int simmr_write_metadata(const char *output, uint32_t n, const char *const *uuid, const char *const *path,
+                         const uint64_t *num_reads, const double *abundance) {
+    std::remove(output);                                          /* files.rs:106-108 */
+    std::ofstream f(output, std::ios::binary);
+    if (!f) return flunk(SIMMR_E_IO, std::string("cannot write ") + output);
+    f << metadata_tsv(n, uuid, path, num_reads, abundance);
+    return f.good() ? SIMMR_OK : flunk(SIMMR_E_IO, std::string("write failed: ") + output);
+}
+
+int simmr_abundance_counts(const simmr_aprofile_desc *d, uint64_t total_reads, uint32_t n, const uint64_t *sizes,
+                           uint64_t *out_reads, double *out_abund) {
+    if (!d || !out_reads || !out_abund) return flunk(SIMMR_E_INVALID, "null argument");
+    std::string err;
+    const int rc = abundance_counts(d, total_reads, n, sizes, out_reads, out_abund, err);
+    return rc ? flunk(rc, err) : rc;
+}
+
+int simmr_eprofile_minimum_genome_size(const simmr_eprofile_desc *d, uint16_t *out) {
+    ProfileModel m; std::string err;
+    const int rc = build_profile(d, m, err);
+    if (rc) return flunk(rc, err);
+    *out = m.min_size; return SIMMR_OK;
+}
+int simmr_eprofile_is_long_read(const simmr_eprofile_desc *d, int *out) {
+    ProfileModel m; std::string err;
+    const int rc = build_profile(d, m, err);
+    if (rc) return flunk(rc, err);
+    *out = m.is_long; return SIMMR_OK;
+}
+
+int simmr_debug_phred_table(const simmr_eprofile_desc *d, uint32_t *cb, uint32_t *npos, uint32_t *qlo, uint32_t *mshift, uint32_t *entries, uint64_t cap) {
+    ProfileModel m; std::string err;
+    const int rc = build_profile(d, m, err);
+    if (rc) return flunk(rc, err);
+    if (m.phred_const) { *cb = 0; *npos = 0; *qlo = m.const_q; *mshift = 0; return 0; }
+    *cb = m.cb; *npos = m.npos; *qlo = m.qlo; *mshift = m.mshift;
+    if (m.phred_entries.size() > cap) return flunk(SIMMR_E_INVALID, "buffer too small");
+    memcpy(entries, m.phred_entries.data(), m.phred_entries.size() * 4);
+    return int(m.phred_entries.size());
+}
+int simmr_debug_len_table(const simmr_eprofile_desc *d, int which, uint32_t *kind, uint32_t *cb, uint32_t *entries, uint32_t *lo, uint32_t *hi, uint64_t cap) {
+    ProfileModel m; std::string err;
+    const int rc = build_profile(d, m, err);
+    if (rc) return flunk(rc, err);
+    const LenModel &t = which ? m.is : m.rl;
+    *kind = t.kind; *cb = t.cb;
+    if (t.kind == LEN_CONST) { lo[0] = hi[0] = t.value; return 0; }
+    if (t.kind == LEN_GAMMA) return 0;
+    if (t.entries.size() > cap) return flunk(SIMMR_E_INVALID, "buffer too small");
+    memcpy(entries, t.entries.data(), t.entries.size() * 4);
+    memcpy(lo, t.lo.data(), t.lo.size() * 4); memcpy(hi, t.hi.data(), t.hi.size() * 4);
+    return int(t.entries.size());
+}
+void simmr_debug_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_10(ctr, key, out); }
+
+}  // extern "C"

@@ -1,0 +1,476 @@
+/* engine.cu — context, device residency and the batch pipeline behind the
+ * compute entry points of include/simmr_b200.h.
+ *
+ * Replaces the simulate + write phase of the reference's run_main
+ * (simmr/src/main.rs:180-206): simulate::simulate_pe_reads /
+ * simulate_long_reads (simulate.rs:110-150, 323-406) and
+ * fastq::write_to_fastq (fastq.rs:14-124).  There is no CPU fallback. */
+#include "device_code.cuh"
+#include "host_model.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+using namespace simmr;
+
+namespace {
+thread_local std::string g_last_error;
+
+struct DevMem {    /* owning device allocation */
+    void *p = nullptr; size_t bytes = 0;
+    DevMem() = default;
+    DevMem(const DevMem &) = delete;
+    DevMem &operator=(const DevMem &) = delete;
+    ~DevMem() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    cudaError_t reserve(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, n ? n : 1);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <class T> cudaError_t upload(const T *src, size_t count, cudaStream_t s) {
+        cudaError_t e = reserve(count * sizeof(T) + 16);
+        if (e != cudaSuccess) return e;
+        return count ? cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s) : cudaSuccess;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+struct PinnedMem {
+    void *p = nullptr; size_t bytes = 0;
+    ~PinnedMem() { if (p) cudaFreeHost(p); }
+    cudaError_t reserve(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocDefault);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+};
+}  // namespace
+
+struct simmr_ctx {
+    int device = 0;
+    cudaDeviceProp prop{};
+    cudaStream_t compute = nullptr, copy = nullptr;
+    std::string err;
+    /* genomes */
+    bool have_genomes = false;
+    simmr_genome_set host_view{};                 /* host copies of the small tables */
+    std::vector<uint64_t> h_contig_off, h_contig_size;
+    std::vector<uint32_t> h_genome_contig, h_contig_id_off, h_genome_id_off;
+    std::string h_contig_ids, h_genome_ids;
+    DevMem d_bases, d_contig_off, d_contig_size, d_genome_contig;
+    /* headers */
+    std::string header_fmt; bool have_headers = false;
+    HeaderPlan plan;
+    DevMem d_chdr, d_toks, d_pool;
+    /* profile */
+    bool have_profile = false;
+    ProfileModel model;
+    DevMem d_phred, d_rl_e, d_rl_lo, d_rl_hi, d_is_e, d_is_lo, d_is_hi;
+    DevMem d_acc, d_plthr, d_rodds, d_ralias, d_roff, d_rlo, d_rhi;
+    /* run scratch */
+    DevMem d_unit_start, d_sizes, d_offsets, d_block_sums, d_counters, d_out[2];
+    PinnedMem h_out[2], h_total;
+    DevMem d_draw[13];
+    simmr_stats stats{};
+};
+
+namespace {
+
+int fail(simmr_ctx *c, int code, const std::string &m) {
+    g_last_error = m;
+    if (c) c->err = m;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+size_t tile_smem(const ProfileModel &m, uint32_t upt, uint32_t stage_cap) {
+    const size_t tab = m.phred_const ? 0 : (size_t(m.npos) << m.cb) * 4;
+    return ((tab + 15) & ~size_t(15)) + size_t(upt) * sizeof(TileUnit) + stage_cap + 48;
+}
+
+struct Plan {      /* launch geometry for one run */
+    bool tiles = false;
+    uint32_t upt = 0, stage_cap = 0, max_unit_bytes = 0;
+    size_t smem = 0;
+    int grid = 0;
+};
+
+int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
+    const ProfileModel &m = ctx->model;
+    const uint64_t per_rec = uint64_t(ctx->plan.hdr_cap) + 2ull * m.max_read_len + 5;
+    const uint64_t unit_bytes = per_rec * (m.is_long ? 1 : 2);
+    if (unit_bytes > 0xfff00000ull) return fail(ctx, SIMMR_E_LIMIT, "a unit's FASTQ bytes exceed 4 GiB");
+    pl.max_unit_bytes = uint32_t(unit_bytes);
+    const size_t tab = m.phred_const ? 0 : (size_t(m.npos) << m.cb) * 4;
+    const size_t smem_max = ctx->prop.sharedMemPerBlockOptin;
+    if (tab + 1024 > smem_max) return fail(ctx, SIMMR_E_LIMIT, "quality tables do not fit in shared memory");
+    pl.tiles = !m.is_long;
+    if (pl.tiles) {
+        /* stage sized for the worst case of every unit in the tile; aim at ~48 KiB */
+        uint32_t upt = uint32_t(std::min<uint64_t>(64, std::max<uint64_t>(1, (48 * 1024) / unit_bytes)));
+        while (upt > 1 && tile_smem(m, upt, uint32_t(upt * unit_bytes + 32)) > smem_max) --upt;
+        const uint32_t cap = uint32_t(upt * unit_bytes + 32);
+        if (tile_smem(m, upt, cap) > smem_max) pl.tiles = false;   /* headers too long for a tile: direct path */
+        else { pl.upt = upt; pl.stage_cap = cap; pl.smem = tile_smem(m, upt, cap); }
+    }
+    if (!pl.tiles) pl.smem = tab;
+    int occ = 0;
+    cudaError_t e;
+    if (pl.tiles) {
+        auto k = replay ? k_format_tiles<true> : k_format_tiles<false>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, FORMAT_THREADS, pl.smem);
+    } else {
+        auto k = replay ? k_format_direct<true> : k_format_direct<false>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, FORMAT_THREADS, pl.smem);
+    }
+    CU(e);
+    if (occ < 1) return fail(ctx, SIMMR_E_LIMIT, "format kernel does not fit on an SM");
+    pl.grid = occ * ctx->prop.multiProcessorCount;
+    return SIMMR_OK;
+}
+
+int ensure_headers(simmr_ctx *ctx, const char *fmt) {
+    const std::string f = fmt ? fmt : DEFAULT_HEADER_FORMAT;
+    if (ctx->have_headers && f == ctx->header_fmt) return SIMMR_OK;
+    std::string err;
+    int rc = compile_headers(ctx->host_view, f.c_str(), ctx->plan, err);
+    if (rc) return fail(ctx, rc, err);
+    CU(ctx->d_chdr.upload(ctx->plan.contigs.data(), ctx->plan.contigs.size(), ctx->compute));
+    CU(ctx->d_toks.upload(ctx->plan.toks.data(), ctx->plan.toks.size(), ctx->compute));
+    CU(ctx->d_pool.upload(ctx->plan.pool.data(), ctx->plan.pool.size(), ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    ctx->header_fmt = f; ctx->have_headers = true;
+    return SIMMR_OK;
+}
+
+void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base, const Plan &pl) {
+    const ProfileModel &m = ctx->model;
+    memset(&rp, 0, sizeof rp);
+    rp.bases = ctx->d_bases.as<uint8_t>(); rp.contig_off = ctx->d_contig_off.as<uint64_t>();
+    rp.contig_size = ctx->d_contig_size.as<uint64_t>(); rp.genome_contig = ctx->d_genome_contig.as<uint32_t>();
+    rp.chdr = ctx->d_chdr.as<ContigHdr>(); rp.toks = ctx->d_toks.as<HdrTok>(); rp.pool = ctx->d_pool.as<uint8_t>();
+    rp.n_genomes = ctx->host_view.n_genomes; rp.n_contigs = ctx->host_view.n_contigs;
+    rp.unit_start = ctx->d_unit_start.as<uint64_t>();
+    rp.read_id_base = id_base;
+    rp.phred = PhredTab{m.phred_const ? 1u : 0u, m.const_q, m.cb, m.npos, m.qlo, m.mshift, ctx->d_phred.as<uint32_t>()};
+    rp.rl = LenTab{m.rl.kind, m.rl.value, m.rl.cb, 0, ctx->d_rl_e.as<uint32_t>(), ctx->d_rl_lo.as<uint32_t>(), ctx->d_rl_hi.as<uint32_t>()};
+    rp.is = LenTab{m.is.kind, m.is.value, m.is.cb, 0, ctx->d_is_e.as<uint32_t>(), ctx->d_is_lo.as<uint32_t>(), ctx->d_is_hi.as<uint32_t>()};
+    rp.gamma = m.gamma;
+    rp.min_size = m.min_size; rp.is_long = m.is_long; rp.flags = m.flags; rp.mutates = m.mutates;
+    rp.key0 = uint32_t(seed); rp.key1 = uint32_t(seed >> 32);
+    rp.sizes = ctx->d_sizes.as<uint32_t>(); rp.offsets = ctx->d_offsets.as<uint64_t>();
+    rp.block_sums = ctx->d_block_sums.as<uint64_t>(); rp.counters = ctx->d_counters.as<unsigned long long>();
+    rp.upt = pl.upt; rp.stage_cap = pl.stage_cap;
+}
+
+/* The batch pipeline shared by simulate and replay. */
+int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uint64_t ue, uint64_t seed,
+              const simmr_run_opts *opts, simmr_sink_fn sink, void *user) {
+    Plan pl;
+    int rc = make_plan(ctx, replay, pl);
+    if (rc) return rc;
+    const uint64_t target_bytes = sink ? (256ull << 20) : (2048ull << 20);
+    uint64_t batch = opts && opts->batch_units ? opts->batch_units : std::max<uint64_t>(1, target_bytes / pl.max_unit_bytes);
+    batch = std::min<uint64_t>(batch, std::max<uint64_t>(1, ue - ub));
+    batch = std::min<uint64_t>(batch, 0x7fffffffull);
+    if (batch * pl.max_unit_bytes > (64ull << 30)) batch = std::max<uint64_t>(1, (64ull << 30) / pl.max_unit_bytes);
+    const uint64_t out_cap = batch * pl.max_unit_bytes + 64;
+    const uint32_t max_blocks = uint32_t((batch + SIZES_THREADS - 1) / SIZES_THREADS);
+    CU(ctx->d_sizes.reserve(batch * 4)); CU(ctx->d_offsets.reserve((batch + 1) * 8)); CU(ctx->d_block_sums.reserve(size_t(max_blocks) * 8));
+    CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
+    const int nbuf = sink ? 2 : 1;
+    for (int b = 0; b < nbuf; ++b) CU(ctx->d_out[b].reserve(out_cap));
+    if (sink) { for (int b = 0; b < 2; ++b) CU(ctx->h_out[b].reserve(out_cap)); }
+    CU(ctx->h_total.reserve(2 * sizeof(uint64_t)));
+
+    RunParams rp; fill_params(ctx, rp, seed, opts ? opts->read_id_base : 0, pl);
+    cudaEvent_t ev_start, ev_stop, ev_f0, ev_f1, ev_total[2], ev_fmt[2], ev_copy[2];
+    CU(cudaEventCreate(&ev_start)); CU(cudaEventCreate(&ev_stop)); CU(cudaEventCreate(&ev_f0)); CU(cudaEventCreate(&ev_f1));
+    for (int b = 0; b < 2; ++b) { CU(cudaEventCreate(&ev_total[b])); CU(cudaEventCreate(&ev_fmt[b])); CU(cudaEventCreate(&ev_copy[b])); }
+    simmr_stats st{};
+    double format_ms = 0.0;
+    struct Pending { bool live = false; uint64_t first = 0, units = 0; } pend[2];
+    auto drain = [&](int slot) -> int {      /* hand a finished batch to the sink */
+        if (!pend[slot].live) return SIMMR_OK;
+        CU(cudaEventSynchronize(ev_copy[slot]));
+        const uint64_t total = static_cast<uint64_t *>(ctx->h_total.p)[slot];
+        pend[slot].live = false;
+        if (sink(user, static_cast<const uint8_t *>(ctx->h_out[slot].p), total, pend[slot].first, pend[slot].units)) return fail(ctx, SIMMR_E_SINK, "sink callback failed");
+        return SIMMR_OK;
+    };
+    CU(cudaEventRecord(ev_start, ctx->compute));
+    int slot = 0; uint64_t nbatch = 0;
+    for (uint64_t u = ub; u < ue; u += batch, ++nbatch) {
+        const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
+        if (sink) { rc = drain(slot); if (rc) return rc; }       /* slot's buffers are about to be reused */
+        rp.batch_begin = u; rp.batch_units = n; rp.out = ctx->d_out[slot].as<uint8_t>();
+        const uint32_t nblk = (n + SIZES_THREADS - 1) / SIZES_THREADS;
+        if (replay) k_unit_sizes<true><<<nblk, SIZES_THREADS, 0, ctx->compute>>>(rp, rd);
+        else k_unit_sizes<false><<<nblk, SIZES_THREADS, 0, ctx->compute>>>(rp, rd);
+        k_scan_blocks<<<1, 1024, 0, ctx->compute>>>(rp, nblk);
+        k_unit_offsets<<<nblk, SIZES_THREADS, 0, ctx->compute>>>(rp);
+        if (sink) {
+            CU(cudaMemcpyAsync(static_cast<uint64_t *>(ctx->h_total.p) + slot, rp.offsets + n, 8, cudaMemcpyDeviceToHost, ctx->compute));
+            CU(cudaEventRecord(ev_total[slot], ctx->compute));
+        }
+        CU(cudaEventRecord(ev_f0, ctx->compute));
+        if (pl.tiles) {
+            const uint32_t ntiles = (n + pl.upt - 1) / pl.upt;
+            const int grid = int(std::min<uint32_t>(ntiles, uint32_t(pl.grid)));
+            if (replay) k_format_tiles<true><<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
+            else k_format_tiles<false><<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
+        } else {
+            const int grid = int(std::min<uint32_t>(n, uint32_t(pl.grid)));
+            if (replay) k_format_direct<true><<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
+            else k_format_direct<false><<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
+        }
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ev_f1, ctx->compute));
+        st.kernel_launches += 4;
+        if (sink) {
+            CU(cudaEventRecord(ev_fmt[slot], ctx->compute));
+            CU(cudaEventSynchronize(ev_total[slot]));            /* byte count known while the format kernel runs */
+            const uint64_t total = static_cast<uint64_t *>(ctx->h_total.p)[slot];
+            if (total > out_cap) return fail(ctx, SIMMR_E_LIMIT, "batch overflowed its staging buffer");
+            CU(cudaStreamWaitEvent(ctx->copy, ev_fmt[slot], 0));
+            CU(cudaMemcpyAsync(ctx->h_out[slot].p, ctx->d_out[slot].p, total, cudaMemcpyDeviceToHost, ctx->copy));
+            CU(cudaEventRecord(ev_copy[slot], ctx->copy));
+            pend[slot] = Pending{true, u, n};
+            st.d2h_bytes += total + 8;
+            slot ^= 1;
+        }
+        /* per-batch format time: costs one sync per batch, only taken when it cannot hide copies */
+        if (!sink) { CU(cudaEventSynchronize(ev_f1)); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_f0, ev_f1)); format_ms += ms; }
+    }
+    CU(cudaEventRecord(ev_stop, ctx->compute));
+    if (sink) { rc = drain(slot); if (rc) return rc; rc = drain(slot ^ 1); if (rc) return rc; }
+    CU(cudaEventSynchronize(ev_stop));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ev_start, ev_stop));
+    unsigned long long ctr[8];
+    CU(cudaMemcpy(ctr, ctx->d_counters.p, sizeof ctr, cudaMemcpyDeviceToHost));
+    st.units = ue - ub; st.clamped = ctr[0]; st.algorithmic_bytes = ctr[1]; st.bases = ctr[2]; st.records = ctr[3];
+    st.bytes = ctr[1] - ctr[2];                                   /* (3L+H+5) - L */
+    st.device_ms = ms; st.format_ms = format_ms;
+    cudaEventDestroy(ev_start); cudaEventDestroy(ev_stop); cudaEventDestroy(ev_f0); cudaEventDestroy(ev_f1);
+    for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_total[b]); cudaEventDestroy(ev_fmt[b]); cudaEventDestroy(ev_copy[b]); }
+    ctx->stats = st;
+    return SIMMR_OK;
+}
+
+int check_ready(simmr_ctx *ctx) {
+    if (!ctx) return fail(nullptr, SIMMR_E_INVALID, "null context");
+    if (!ctx->have_genomes) return fail(ctx, SIMMR_E_STATE, "no genomes loaded");
+    if (!ctx->have_profile) return fail(ctx, SIMMR_E_STATE, "no error profile set");
+    /* simulate.rs:220-225 / main.rs:124: every contig must exceed the minimum size */
+    const ProfileModel &m = ctx->model;
+    for (uint32_t c = 0; c < ctx->host_view.n_contigs; ++c)
+        if (ctx->h_contig_size[c] <= m.min_size)
+            return fail(ctx, SIMMR_E_TOO_SMALL, "contig " + std::to_string(c) + " (" + std::to_string(ctx->h_contig_size[c]) +
+                        " nt) does not exceed the profile's minimum size " + std::to_string(m.min_size));
+    for (uint32_t g = 0; g < ctx->host_view.n_genomes; ++g)
+        if (ctx->h_genome_contig[g + 1] == ctx->h_genome_contig[g]) return fail(ctx, SIMMR_E_TOO_SMALL, "genome " + std::to_string(g) + " has no usable contigs");
+    return SIMMR_OK;
+}
+
+std::vector<uint64_t> unit_prefix(const simmr_ctx *ctx, const uint64_t *reads) {
+    const uint32_t n = ctx->host_view.n_genomes;
+    std::vector<uint64_t> s(n + 1, 0);
+    for (uint32_t g = 0; g < n; ++g) s[g + 1] = s[g] + (ctx->model.is_long ? reads[g] : reads[g] / 2);   /* simulate.rs:179 / :356 */
+    return s;
+}
+}  // namespace
+
+extern "C" {
+
+const char *simmr_last_error(const simmr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+const char *simmr_version(void) { return "simmr_b200 0.1 (sm_100a)"; }
+
+int simmr_ctx_create(int device, simmr_ctx **out) {
+    simmr_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, SIMMR_E_INVALID, "null out pointer");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(nullptr, SIMMR_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, SIMMR_E_INVALID, "device index out of range");
+    ctx = new simmr_ctx; ctx->device = device;
+    auto bail = [&](const std::string &m) { delete ctx; return fail(nullptr, SIMMR_E_CUDA, m); };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if (ctx->prop.major != 10) return bail("device is sm_" + std::to_string(ctx->prop.major * 10 + ctx->prop.minor) + "; this library carries sm_100a code only");
+    if ((e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    *out = ctx;
+    return SIMMR_OK;
+}
+
+void simmr_ctx_destroy(simmr_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    if (ctx->copy) cudaStreamDestroy(ctx->copy);
+    delete ctx;
+}
+
+int simmr_device_info(const simmr_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, uint64_t *hbm_bytes) {
+    if (!ctx) return fail(nullptr, SIMMR_E_INVALID, "null context");
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = ctx->prop.major;
+    if (cc_minor) *cc_minor = ctx->prop.minor;
+    if (hbm_bytes) *hbm_bytes = ctx->prop.totalGlobalMem;
+    return SIMMR_OK;
+}
+
+int simmr_genomes_load(simmr_ctx *ctx, const simmr_genome_set *s) {
+    if (!ctx || !s) return fail(ctx, SIMMR_E_INVALID, "null argument");
+    if (!s->n_genomes || !s->n_contigs) return fail(ctx, SIMMR_E_INVALID, "empty genome set");
+    CU(cudaSetDevice(ctx->device));
+    ctx->h_contig_off.assign(s->contig_off, s->contig_off + s->n_contigs + 1);
+    ctx->h_contig_size.assign(s->contig_size, s->contig_size + s->n_contigs);
+    ctx->h_genome_contig.assign(s->genome_contig, s->genome_contig + s->n_genomes + 1);
+    ctx->h_contig_id_off.assign(s->contig_id_off, s->contig_id_off + s->n_contigs + 1);
+    ctx->h_genome_id_off.assign(s->genome_id_off, s->genome_id_off + s->n_genomes + 1);
+    ctx->h_contig_ids.assign(s->contig_ids, ctx->h_contig_id_off.back());
+    ctx->h_genome_ids.assign(s->genome_ids, ctx->h_genome_id_off.back());
+    for (uint32_t c = 0; c < s->n_contigs; ++c)
+        if (ctx->h_contig_off[c + 1] < ctx->h_contig_off[c]) return fail(ctx, SIMMR_E_INVALID, "contig offsets must be non-decreasing");
+    if (ctx->h_genome_contig.back() != s->n_contigs) return fail(ctx, SIMMR_E_INVALID, "genome_contig does not cover all contigs");
+    simmr_genome_set &v = ctx->host_view;
+    v = *s; v.bases = nullptr;
+    v.contig_off = ctx->h_contig_off.data(); v.contig_size = ctx->h_contig_size.data(); v.genome_contig = ctx->h_genome_contig.data();
+    v.contig_ids = ctx->h_contig_ids.data(); v.contig_id_off = ctx->h_contig_id_off.data();
+    v.genome_ids = ctx->h_genome_ids.data(); v.genome_id_off = ctx->h_genome_id_off.data();
+    const uint64_t nbytes = ctx->h_contig_off.back();
+    /* one resident copy of every contig; the reference clones sequences per read (simulate.rs:362-367) */
+    CU(ctx->d_bases.reserve(nbytes + 64));
+    CU(cudaMemcpy(ctx->d_bases.p, s->bases, nbytes, cudaMemcpyHostToDevice));
+    CU(cudaMemset(static_cast<uint8_t *>(ctx->d_bases.p) + nbytes, 'N', 64));
+    CU(ctx->d_contig_off.upload(ctx->h_contig_off.data(), ctx->h_contig_off.size(), ctx->compute));
+    CU(ctx->d_contig_size.upload(ctx->h_contig_size.data(), ctx->h_contig_size.size(), ctx->compute));
+    CU(ctx->d_genome_contig.upload(ctx->h_genome_contig.data(), ctx->h_genome_contig.size(), ctx->compute));
+    CU(cudaStreamSynchronize(ctx->compute));
+    ctx->stats.h2d_bytes = nbytes;
+    ctx->have_genomes = true; ctx->have_headers = false;
+    return SIMMR_OK;
+}
+
+int simmr_error_profile_set(simmr_ctx *ctx, const simmr_eprofile_desc *d) {
+    if (!ctx || !d) return fail(ctx, SIMMR_E_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    std::string err;
+    int rc = build_profile(d, ctx->model, err);
+    if (rc) return fail(ctx, rc, err);
+    const ProfileModel &m = ctx->model;
+    cudaStream_t s = ctx->compute;
+    CU(ctx->d_phred.upload(m.phred_entries.data(), m.phred_entries.size(), s));
+    CU(ctx->d_rl_e.upload(m.rl.entries.data(), m.rl.entries.size(), s)); CU(ctx->d_rl_lo.upload(m.rl.lo.data(), m.rl.lo.size(), s)); CU(ctx->d_rl_hi.upload(m.rl.hi.data(), m.rl.hi.size(), s));
+    CU(ctx->d_is_e.upload(m.is.entries.data(), m.is.entries.size(), s)); CU(ctx->d_is_lo.upload(m.is.lo.data(), m.is.lo.size(), s)); CU(ctx->d_is_hi.upload(m.is.hi.data(), m.is.hi.size(), s));
+    CU(ctx->d_acc.upload(m.acc_lut, 256, s)); CU(ctx->d_plthr.upload(m.pl_thr, 64, s));
+    CU(ctx->d_rodds.upload(m.r_odds.data(), m.r_odds.size(), s)); CU(ctx->d_ralias.upload(m.r_alias.data(), m.r_alias.size(), s));
+    CU(ctx->d_roff.upload(m.r_off.data(), m.r_off.size(), s)); CU(ctx->d_rlo.upload(m.r_lo.data(), m.r_lo.size(), s)); CU(ctx->d_rhi.upload(m.r_hi.data(), m.r_hi.size(), s));
+    CU(cudaStreamSynchronize(s));
+    ctx->have_profile = true;
+    return SIMMR_OK;
+}
+
+uint64_t simmr_total_units(const simmr_ctx *ctx, const uint64_t *reads) {
+    if (!ctx || !reads || !ctx->have_genomes || !ctx->have_profile) return 0;
+    return unit_prefix(ctx, reads).back();
+}
+
+int simmr_simulate(simmr_ctx *ctx, const uint64_t *reads, const simmr_run_opts *opts, simmr_sink_fn sink, void *user) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!reads) return fail(ctx, SIMMR_E_INVALID, "null reads_per_genome");
+    CU(cudaSetDevice(ctx->device));
+    rc = ensure_headers(ctx, opts ? opts->header_format : nullptr);
+    if (rc) return rc;
+    const std::vector<uint64_t> us = unit_prefix(ctx, reads);
+    CU(ctx->d_unit_start.upload(us.data(), us.size(), ctx->compute));
+    uint64_t ub = opts ? opts->unit_begin : 0, ue = opts ? opts->unit_end : 0;
+    if (ub == 0 && ue == 0) ue = us.back();
+    if (ub > ue || ue > us.back()) return fail(ctx, SIMMR_E_INVALID, "unit range outside the run");
+    uint64_t seed;
+    if (opts && opts->has_seed) seed = opts->seed;
+    else { std::random_device rd; seed = (uint64_t(rd()) << 32) | rd(); }      /* StdRng::from_entropy(), simulate.rs:174 */
+    ctx->stats = simmr_stats{};
+    if (ub == ue) return SIMMR_OK;
+    ReplayDev rd{};
+    return run_units(ctx, false, rd, ub, ue, seed, opts, sink, user);
+}
+
+int simmr_replay(simmr_ctx *ctx, const simmr_draws *d, const simmr_run_opts *opts, simmr_sink_fn sink, void *user) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!d) return fail(ctx, SIMMR_E_INVALID, "null draws");
+    CU(cudaSetDevice(ctx->device));
+    rc = ensure_headers(ctx, opts ? opts->header_format : nullptr);
+    if (rc) return rc;
+    const ProfileModel &m = ctx->model;
+    const uint64_t n = d->n_units;
+    if (!d->genome || !d->contig || !d->read_length || !d->start || !d->base_off) return fail(ctx, SIMMR_E_INVALID, "replay needs genome, contig, read_length, start and base_off");
+    if (!m.is_long && !d->insert_size) return fail(ctx, SIMMR_E_INVALID, "paired-end replay needs insert_size");
+    for (uint64_t u = 0; u < n; ++u) {
+        if (d->genome[u] >= ctx->host_view.n_genomes) return fail(ctx, SIMMR_E_INVALID, "replay: genome index out of range");
+        const uint32_t g = d->genome[u];
+        if (d->contig[u] >= ctx->h_genome_contig[g + 1] - ctx->h_genome_contig[g]) return fail(ctx, SIMMR_E_INVALID, "replay: contig index out of range");
+    }
+    const uint64_t nslots = d->base_off[n];
+    if (m.replay_kind == RP_NORMAL_FLOOR || m.replay_kind == RP_ACCURACY) { if (!d->phred_z) return fail(ctx, SIMMR_E_INVALID, "replay needs phred_z for this profile"); }
+    if (m.replay_kind == RP_ALIAS && (!d->phred_cand || !d->phred_u || !d->phred_inbin)) return fail(ctx, SIMMR_E_INVALID, "replay needs phred_cand/phred_u/phred_inbin for custom profiles");
+    if (m.mutates && (!d->mut_u || !d->mut_k)) return fail(ctx, SIMMR_E_INVALID, "replay needs mut_u/mut_k for this profile");
+    cudaStream_t s = ctx->compute;
+    std::vector<uint64_t> zero64(n + 1, 0); std::vector<uint16_t> zero16(n, 0);
+    ReplayDev rd{};
+    CU(ctx->d_draw[0].upload(d->genome, n, s)); rd.genome = ctx->d_draw[0].as<uint32_t>();
+    CU(ctx->d_draw[1].upload(d->contig, n, s)); rd.contig = ctx->d_draw[1].as<uint32_t>();
+    CU(ctx->d_draw[2].upload(d->read_length, n, s)); rd.read_length = ctx->d_draw[2].as<uint16_t>();
+    CU(ctx->d_draw[3].upload(d->insert_size ? d->insert_size : zero16.data(), n, s)); rd.insert_size = ctx->d_draw[3].as<uint16_t>();
+    CU(ctx->d_draw[4].upload(d->start, n, s)); rd.start = ctx->d_draw[4].as<uint64_t>();
+    CU(ctx->d_draw[5].upload(d->redraw ? d->redraw : zero64.data(), n, s)); rd.redraw = ctx->d_draw[5].as<uint64_t>();
+    CU(ctx->d_draw[6].upload(d->base_off, n + 1, s)); rd.base_off = ctx->d_draw[6].as<uint64_t>();
+    if (d->phred_z) { CU(ctx->d_draw[7].upload(d->phred_z, nslots, s)); rd.phred_z = ctx->d_draw[7].as<float>(); }
+    if (d->phred_cand) { CU(ctx->d_draw[8].upload(d->phred_cand, nslots, s)); rd.phred_cand = ctx->d_draw[8].as<uint32_t>(); }
+    if (d->phred_u) { CU(ctx->d_draw[9].upload(d->phred_u, nslots, s)); rd.phred_u = ctx->d_draw[9].as<double>(); }
+    if (d->phred_inbin) { CU(ctx->d_draw[10].upload(d->phred_inbin, nslots, s)); rd.phred_inbin = ctx->d_draw[10].as<uint32_t>(); }
+    if (d->mut_u) { CU(ctx->d_draw[11].upload(d->mut_u, nslots, s)); rd.mut_u = ctx->d_draw[11].as<float>(); }
+    if (d->mut_k) { CU(ctx->d_draw[12].upload(d->mut_k, nslots, s)); rd.mut_k = ctx->d_draw[12].as<uint8_t>(); }
+    rd.acc_lut = ctx->d_acc.as<float>(); rd.pl_thr = ctx->d_plthr.as<float>();
+    rd.r_odds = ctx->d_rodds.as<double>(); rd.r_alias = ctx->d_ralias.as<uint32_t>(); rd.r_off = ctx->d_roff.as<uint32_t>();
+    rd.r_lo = ctx->d_rlo.as<uint32_t>(); rd.r_hi = ctx->d_rhi.as<uint32_t>();
+    rd.r_npos = m.r_off.empty() ? 0 : uint32_t(m.r_off.size() - 1); rd.pl_qmax = m.pl_qmax; rd.kind = m.replay_kind;
+    rd.mean_phred = m.mean_phred_f; rd.acc20 = m.acc20;
+    /* unit_start is unused in replay but the parameter block wants a valid pointer */
+    std::vector<uint64_t> us(ctx->host_view.n_genomes + 1, 0);
+    CU(ctx->d_unit_start.upload(us.data(), us.size(), s));
+    CU(cudaStreamSynchronize(s));
+    uint64_t ub = opts ? opts->unit_begin : 0, ue = opts ? opts->unit_end : 0;
+    if (ub == 0 && ue == 0) ue = n;
+    if (ub > ue || ue > n) return fail(ctx, SIMMR_E_INVALID, "unit range outside the draws");
+    ctx->stats = simmr_stats{};
+    if (ub == ue) return SIMMR_OK;
+    return run_units(ctx, true, rd, ub, ue, 0, opts, sink, user);
+}
+
+int simmr_stats_get(const simmr_ctx *ctx, simmr_stats *out) {
+    if (!ctx || !out) return fail(nullptr, SIMMR_E_INVALID, "null argument");
+    *out = ctx->stats;
+    return SIMMR_OK;
+}
+
+}  // extern "C"
