@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the simmr read-simulation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1], "C2"): minimal-short PE 150 bp, 100 M reads from
+a 100-genome synthetic metagenome (2-8 Mbp each, 1-20 contigs), uniform abundance.
+A step is one pass of the whole hot path (sizes -> scan -> fused gather / RC / Phred
+/ substitution / FASTQ format) over one 100 M-read job per GPU.  With N GPUs the job
+is N x 100 M reads sharded by global unit (pair) index, genomes replicated, no
+data-path collective ("weak" scaling).
+
+value : device-side Gbases/s, genomes resident in HBM, FASTQ bytes left in HBM staging.
+e2e   : the same job through simmr_genomes_load + simmr_simulate with HOST buffers:
+        genomes copied host->device and every FASTQ byte copied device->pinned host
+        inside the timed region.
+roofline : algorithmic bytes (sum of 3L+H+5 per record) of the format
+        kernel / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline : the CPU oracle (C++ restatement of the reference; the Rust reference
+        cannot be built in this image) on a bounded sample of the same job.
+--impl reference : that same oracle, all host threads, printed as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "simulated_bases_per_second"
+UNIT = "Gbases/s"
+N_GENOMES = 100
+READS_PER_GPU = 100_000_000
+SEED = 42
+
+
+def c2_genomes():
+    """100 genomes, sizes uniform in [2, 8] Mbp, 1-20 contigs each >= 50 kbp, i.i.d. ACGT,
+    ids g{genome:04}_c{contig:03}, uuids %016x of splitmix64(genome)."""
+    import simmr_b200 as S
+    from helpers import splitmix64
+    rng = np.random.default_rng(0x5EED0000)
+    sizes = rng.integers(2_000_000, 8_000_001, N_GENOMES)
+    total = int(sizes.sum())
+    bases = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, total, dtype=np.uint8)]
+    coff, csize, gcon, cids, cidoff, gids, gidoff = [0], [], [0], b"", [0], b"", [0]
+    for g in range(N_GENOMES):
+        nc = int(rng.integers(1, 21))
+        cuts = np.sort(rng.integers(0, int(sizes[g]) - nc * 50_000 + 1, nc - 1)) if nc > 1 else np.zeros(0, np.int64)
+        lens = np.diff(np.concatenate([[0], cuts, [int(sizes[g]) - nc * 50_000]])) + 50_000
+        for c, ln in enumerate(lens):
+            coff.append(coff[-1] + int(ln))
+            csize.append(int(ln))
+            cids += f"g{g:04d}_c{c:03d}".encode()
+            cidoff.append(len(cids))
+        gcon.append(len(csize))
+        gids += f"{splitmix64(g):016x}".encode()
+        gidoff.append(len(gids))
+    assert coff[-1] == total
+    return S.GenomeSet(bases, coff, csize, gcon, cids, cidoff, gids, gidoff)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        try:
+            p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        while not self.stop_flag.is_set():
+            line = p.stdout.readline()
+            if not line:
+                break
+            self.rows.append([c.strip() for c in line.split(",")])
+        p.terminate()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = []
+        for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+            if any(len(r) >= 8 and r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def oracle_rate(gs, reads, unit_begin, n_units, threads):
+    """Gbases/s of the CPU oracle over n_units units split across `threads` host threads."""
+    from oracle import pyoracle as po
+    import simmr_b200 as S
+    from helpers import oracle_profile
+    og = po.Genomes.from_set(gs)
+    prof = oracle_profile(S.MinimalShortErrorProfile(150, 150, 30))
+    per = (n_units + threads - 1) // threads
+    bases = [0] * threads
+
+    def work(t):
+        a = unit_begin + t * per
+        b = min(unit_begin + n_units, a + per)
+        if b > a:
+            _, st = po.simulate(og, prof, reads, SEED, unit_begin=a, unit_end=b, cap=(b - a) * 1400, want_stats=True)
+            bases[t] = st.bases
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    dt = time.perf_counter() - t0
+    return sum(bases) / dt / 1e9, sum(bases), dt
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path.  The reference is Rust
+    and cannot be compiled in this image, so the C++ oracle (kind "port") stands in."""
+    if rank != 0:
+        return
+    gs = c2_genomes()
+    reads = np.full(N_GENOMES, READS_PER_GPU * world // N_GENOMES, np.uint64)
+    cores = os.cpu_count() or 1
+    rate, _, _ = oracle_rate(gs, reads, 0, 20_000, cores)                  # calibration
+    sample = int(max(20_000, min(2_000_000, rate * 1e9 / 300 * 8)))       # ~8 s of work per step
+    vals, times = [], []
+    for it in range(args.warmup + args.steps):
+        r, nb, dt = oracle_rate(gs, reads, it * sample, sample, cores)
+        if it >= args.warmup:
+            vals.append(r)
+            times.append(dt)
+    v = float(np.mean(vals))
+    desc = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample} pairs ({2 * sample} records) per step of the C2 job, oracle native mode, {cores} threads"}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                      "data": "synthetic", "config": workload_config(world), "cpu_baseline": desc,
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(world):
+    return {"workload": "C2: minimal-short PE 150 bp, 100M reads per GPU from a 100-genome synthetic metagenome "
+                        "(2-8 Mbp, 1-20 contigs), uniform abundance, seed 42",
+            "reads_per_gpu": READS_PER_GPU, "genomes": N_GENOMES, "sharding": f"units x{world}, genomes replicated",
+            "l2": "inputs (~500 MB genomes) and outputs (~53 GB FASTQ per step) both exceed the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="simmr_b200")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--reads-per-gpu", type=int, default=READS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import simmr_b200 as S
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rpg = args.reads_per_gpu
+    gs = c2_genomes()
+    reads, _ = S.UniformAbundanceProfile().determine_abundances(rpg * world, N_GENOMES)   # a1: ceil(total/n)
+    eng = S.Engine(local)
+    eng.load_genomes(gs)
+    eng.set_error_profile(S.MinimalShortErrorProfile(150, 150, 30))
+    total_units = eng.total_units(reads)
+    ub, ue = rank * total_units // world, (rank + 1) * total_units // world
+
+    for _ in range(args.warmup):
+        eng.simulate(reads, SEED, unit_begin=ub, unit_end=ue)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    dev_ms = fmt_ms = 0.0
+    bases = records = alg = launches = 0
+    for _ in range(args.steps):
+        st = eng.simulate(reads, SEED, unit_begin=ub, unit_end=ue)
+        dev_ms += st["device_ms"]; fmt_ms += st["format_ms"]
+        bases += st["bases"]; records += st["records"]; alg += st["algorithmic_bytes"]; launches += st["kernel_launches"]
+    barrier()
+    sampler.stop_flag.set()
+    t = torch.tensor([dev_ms, float(bases), float(records)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        max_ms, all_bases, all_records = float(tmax[0]), float(tsum[1]), float(tsum[2])
+    else:
+        max_ms, all_bases, all_records = dev_ms, float(bases), float(records)
+    value = all_bases / (max_ms / 1e3) / 1e9
+
+    # end to end: host genome buffers -> device, FASTQ bytes -> pinned host, inside the timed region
+    e2e_bases = e2e_d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        eng.load_genomes(gs)
+        sunk = [0]
+        st = eng.simulate(reads, SEED, unit_begin=ub, unit_end=ue, sink=lambda a, f, n: sunk.__setitem__(0, sunk[0] + a.shape[0]))
+        assert sunk[0] == st["bytes"]
+        e2e_bases += st["bases"]; e2e_d2h += st["d2h_bytes"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    tb = torch.tensor([float(e2e_bases)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+    e2e_value = float(tb[0]) / float(te[0]) / 1e9
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = alg / (fmt_ms / 1e3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("format_kernel_dram_bytes_per_launch")
+        n_launch = max(1, launches // 4)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u8", "data": "synthetic", "config": workload_config(world),
+               "reads_per_second": all_records / (max_ms / 1e3), "clocks": sampler.summary(), "gpu_launches": launches,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(gs.bases.nbytes),
+                       "d2h_bytes_per_step": int(e2e_d2h // max(1, args.e2e_steps)), "steps": args.e2e_steps},
+               "roofline": {"bound": "hbm", "kernel": "k_format_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": alg / n_launch,
+                            "launch_ms": fmt_ms / n_launch, "launches": n_launch, "kernel_share_of_step": fmt_ms / dev_ms}}
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            r1, _, _ = oracle_rate(gs, reads, 0, 10_000, 1)
+            n1 = int(max(10_000, min(1_000_000, r1 * 1e9 / 300 * 6)))
+            r1, b1, d1 = oracle_rate(gs, reads, 0, n1, 1)
+            rall, ball, dall = oracle_rate(gs, reads, 0, n1 * min(cores, 16), cores)
+            out["cpu_baseline"] = {"value": rall, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"first {n1 * min(cores, 16)} pairs of the C2 job on {cores} threads ({dall:.1f} s); "
+                                             f"1 thread: {r1:.4f} {UNIT} on {n1} pairs ({d1:.1f} s)",
+                                   "single_thread_value": r1}
+        print(json.dumps(out))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -183,8 +183,8 @@ int  simmr_write_metadata(const char *output, uint32_t n, const char *const *uui
                           const char *const *path, const uint64_t *num_reads, const double *abundance);
 
 /* ---- introspection used by the parity tests (host only) ----------------- */
-int  simmr_debug_phred_table(const simmr_eprofile_desc *desc, uint32_t *cb, uint32_t *npos, uint32_t *qlo,
-                             uint32_t *mshift, uint32_t *entries, uint64_t cap);
+int  simmr_debug_phred_table(const simmr_eprofile_desc *desc, uint32_t *kind, uint32_t *cb, uint32_t *npos,
+                             uint32_t *const_q, uint32_t *entries, uint64_t cap);
 int  simmr_debug_len_table(const simmr_eprofile_desc *desc, int which, uint32_t *kind, uint32_t *cb,
                            uint32_t *entries, uint32_t *lo, uint32_t *hi, uint64_t cap);
 void simmr_debug_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

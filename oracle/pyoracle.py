@@ -144,13 +144,13 @@ class Profile:
         return bool(out.value)
 
     def phred_table(self):
-        cb, npos, qlo, ms = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        kind, cb, npos, cq = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
         ent = np.zeros(1 << 20, np.uint32)
-        n = lib().orc_profile_phred_table(C.byref(self.c), C.byref(cb), C.byref(npos), C.byref(qlo),
-                                          C.byref(ms), _p(ent, u32p), C.c_uint64(len(ent)))
+        n = lib().orc_profile_phred_table(C.byref(self.c), C.byref(kind), C.byref(cb), C.byref(npos), C.byref(cq),
+                                          _p(ent, u32p), C.c_uint64(len(ent)))
         if n < 0:
             raise RuntimeError(err())
-        return dict(cb=cb.value, npos=npos.value, qlo=qlo.value, mshift=ms.value, entries=ent[:n].copy())
+        return dict(kind=kind.value, cb=cb.value, npos=npos.value, const_q=cq.value, entries=ent[:n].copy())
 
     def len_table(self, which):
         kind, cb = C.c_uint32(), C.c_uint32()

@@ -342,9 +342,8 @@ struct RustAlias {
 /* ------------------------------------------------------------------ */
 /* native-mode quantised alias tables                    */
 /* ------------------------------------------------------------------ */
-/* Vose alias over N=2^cb columns; entry = thr<<abits | alias, thr has tbits. */
-bool build_qalias(const std::vector<double> &w, uint32_t cb, uint32_t tbits, uint32_t abits,
-                  std::vector<uint32_t> &out) {
+/* Vose alias over N=2^cb columns: keep-probability and alias per column. */
+bool vose(const std::vector<double> &w, uint32_t cb, std::vector<double> &prob, std::vector<uint32_t> &alias) {
     const size_t N = (size_t)1 << cb;
     if (w.size() > N) return false;
     double S = 0.0;
@@ -352,8 +351,8 @@ bool build_qalias(const std::vector<double> &w, uint32_t cb, uint32_t tbits, uin
     if (!(S > 0.0)) return false;
     std::vector<double> p(N, 0.0);
     for (size_t i = 0; i < w.size(); i++) p[i] = w[i] * (double)N / S;
-    std::vector<uint32_t> small, large, alias(N);
-    std::vector<double> prob(N, 1.0);
+    std::vector<uint32_t> small, large;
+    alias.resize(N); prob.assign(N, 1.0);
     for (size_t i = 0; i < N; i++) { alias[i] = (uint32_t)i; if (p[i] < 1.0) small.push_back((uint32_t)i); else large.push_back((uint32_t)i); }
     while (!small.empty() && !large.empty()) {
         uint32_t s = small.back(); small.pop_back();
@@ -362,15 +361,22 @@ bool build_qalias(const std::vector<double> &w, uint32_t cb, uint32_t tbits, uin
         p[l] = (p[l] + p[s]) - 1.0;
         if (p[l] < 1.0) small.push_back(l); else large.push_back(l);
     }
-    out.resize(N);
-    const double scale = (double)((uint64_t)1 << tbits);
-    const uint32_t tmax = (uint32_t)(((uint64_t)1 << tbits) - 1);
-    for (size_t i = 0; i < N; i++) {
-        uint32_t a = alias[i], thr;
-        if (prob[i] >= 1.0) { a = (uint32_t)i; thr = tmax; }
-        else { double t = std::floor(prob[i] * scale); thr = t <= 0.0 ? 0u : (t >= (double)tmax ? tmax : (uint32_t)t); }
-        out[i] = (thr << abits) | a;
-    }
+    for (size_t i = 0; i < N; i++) if (prob[i] >= 1.0) alias[i] = (uint32_t)i;
+    return true;
+}
+/* threshold = floor(prob * 2^bits), saturated to bits; prob>=1 -> all ones */
+inline uint32_t quant_thr(double prob, uint32_t bits) {
+    const uint32_t top = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+    if (prob >= 1.0) return top;
+    double t = std::floor(prob * std::ldexp(1.0, (int)bits));
+    return t <= 0.0 ? 0u : (t >= (double)top ? top : (uint32_t)t);
+}
+/* length tables: entry = thr20<<12 | alias12 */
+bool build_len_alias(const std::vector<double> &w, uint32_t cb, std::vector<uint32_t> &out) {
+    std::vector<double> prob; std::vector<uint32_t> alias;
+    if (!vose(w, cb, prob, alias)) return false;
+    out.resize(prob.size());
+    for (size_t i = 0; i < prob.size(); i++) out[i] = (quant_thr(prob[i], 20) << 12) | alias[i];
     return true;
 }
 inline uint32_t ceil_log2(size_t n) { uint32_t b = 0; while (((size_t)1 << b) < n) b++; return b; }
@@ -399,10 +405,12 @@ inline double mutation_prob(uint8_t q) {
     return (16777215.0 - T) / 16777216.0;
 }
 
-struct PhredTable {      /* per-position alias tables, outcome -> (q, m) */
-    bool constant = false; uint8_t const_q = 0;
-    uint32_t cb = 0, npos = 0, qlo = 0, mshift = 0;
-    std::vector<uint32_t> entries;   /* npos << cb, entry = thr22<<10 | alias10 */
+struct PhredTable {      /* per-position alias tables */
+    uint32_t kind = 0;   /* 0: constant quality; 1: T64 {thr32, q_self|m_self<<8|q_alias<<16|m_alias<<24};
+                            2: T32 thr16<<16 | q_alias<<8 | q_self (no mutation) */
+    uint8_t const_q = 0;
+    uint32_t cb = 0, npos = 0;
+    std::vector<uint32_t> entries;   /* kind 1: 2 words per column, kind 2: 1 word per column */
 };
 struct LenTable {
     uint32_t kind = 0;   /* 0 const, 1 alias over bins, 2 Marsaglia-Tsang gamma */
@@ -436,15 +444,23 @@ std::vector<double> with_mutation(const std::vector<double> &pq, uint32_t qlo) {
     }
     return w;
 }
-bool phred_table_from_pmf(const std::vector<double> &pq, uint32_t qlo, bool mutates, PhredTable &t) {
-    std::vector<double> w = mutates ? with_mutation(pq, qlo) : pq;
-    t.mshift = mutates ? 2 : 0; t.qlo = qlo; t.npos = 1;
-    t.cb = std::max(1u, ceil_log2(w.size()));
+/* mutating profiles: outcome o = (q-qlo)<<2 | m over the joint (quality, mutation) weights */
+bool phred_table_from_pmf(const std::vector<double> &pq, uint32_t qlo, PhredTable &t) {
+    std::vector<double> w = with_mutation(pq, qlo);
+    t.kind = 1; t.npos = 1; t.cb = std::max(1u, ceil_log2(w.size()));
     if (t.cb > 10) return false;
-    return build_qalias(w, t.cb, 22, 10, t.entries);
+    std::vector<double> prob; std::vector<uint32_t> alias;
+    if (!vose(w, t.cb, prob, alias)) return false;
+    auto pay = [&](uint32_t o) { return ((qlo + (o >> 2)) & 0xffu) | ((o & 3u) << 8); };
+    t.entries.resize(prob.size() * 2);
+    for (size_t i = 0; i < prob.size(); i++) {
+        t.entries[2 * i] = quant_thr(prob[i], 32);
+        t.entries[2 * i + 1] = pay((uint32_t)i) | (pay(alias[i]) << 16);
+    }
+    return true;
 }
 /* per-position tables from the blob: alias over densities, uniform in-bin,
- * `as u8` truncation (custom_short.rs:108-129, 328-352) */
+ * `as u8` truncation (custom_short.rs:108-129, 328-352); no mutation */
 bool phred_table_from_blob(const Blob &b, PhredTable &t) {
     size_t np = b.quality.size();
     if (np == 0) return false;
@@ -471,14 +487,15 @@ bool phred_table_from_blob(const Blob &b, PhredTable &t) {
         }
     }
     if (qmin > qmax) return false;
-    t.qlo = qmin; t.mshift = 0; t.npos = (uint32_t)np;
+    t.kind = 2; t.npos = (uint32_t)np;
     t.cb = std::max(1u, ceil_log2(qmax - qmin + 1));
     t.entries.clear();
     for (size_t p = 0; p < np; p++) {
-        std::vector<double> w(pm[p].begin() + qmin, pm[p].begin() + qmax + 1);
-        std::vector<uint32_t> e;
-        if (!build_qalias(w, t.cb, 22, 10, e)) return false;
-        t.entries.insert(t.entries.end(), e.begin(), e.end());
+        std::vector<double> w(pm[p].begin() + qmin, pm[p].begin() + qmax + 1), prob;
+        std::vector<uint32_t> alias;
+        if (!vose(w, t.cb, prob, alias)) return false;
+        for (size_t i = 0; i < prob.size(); i++)
+            t.entries.push_back((quant_thr(prob[i], 16) << 16) | (((qmin + alias[i]) & 0xffu) << 8) | ((qmin + (uint32_t)i) & 0xffu));
     }
     return true;
 }
@@ -488,7 +505,7 @@ bool len_table_from_pmf(const std::vector<double> &pmf, uint32_t vlo, LenTable &
     size_t N = (size_t)1 << t.cb;
     t.lo.assign(N, vlo); t.hi.assign(N, vlo);
     for (size_t i = 0; i < pmf.size(); i++) t.lo[i] = t.hi[i] = vlo + (uint32_t)i;
-    return build_qalias(pmf, t.cb, 20, 12, t.entries);
+    return build_len_alias(pmf, t.cb, t.entries);
 }
 bool len_table_from_bins(const Bins &b, LenTable &t) {
     if (b.density.empty()) return false;
@@ -497,7 +514,7 @@ bool len_table_from_bins(const Bins &b, LenTable &t) {
     size_t N = (size_t)1 << t.cb;
     t.lo.assign(N, 0); t.hi.assign(N, 0);
     for (size_t j = 0; j < b.density.size(); j++) { auto r = bin_range(b, j); t.lo[j] = r.first; t.hi[j] = std::max(r.first, r.second); }
-    return build_qalias(b.density, t.cb, 20, 12, t.entries);
+    return build_len_alias(b.density, t.cb, t.entries);
 }
 
 /* perfect_long.rs:60-78 as a pmf over q: a = N(acc(20),0.05) (f32), min 0.9999,
@@ -525,7 +542,7 @@ bool make_profile(const orc_profile *in, Profile &p) {
     case ORC_PERFECT_SHORT:   /* perfect_short.rs:22-59 */
         p.is_long = false; p.mutates = false;
         p.min_size = (uint16_t)(2 * p.read_length + p.insert_size);
-        p.phred.constant = true; p.phred.const_q = 60;
+        p.phred.kind = 0; p.phred.const_q = 60;
         p.rl.kind = 0; p.rl.value = p.read_length; p.is.kind = 0; p.is.value = p.insert_size;
         break;
     case ORC_MINIMAL_SHORT: { /* minimal_short.rs:33-145; sd 15 / 75 from cli.rs:239-240 */
@@ -533,7 +550,7 @@ bool make_profile(const orc_profile *in, Profile &p) {
         p.min_size = (uint16_t)(2 * p.read_length + p.insert_size);
         uint32_t vlo; std::vector<double> pmf;
         normal_floor_pmf((double)(float)p.mean_phred, 10.0, 255, vlo, pmf);
-        if (!phred_table_from_pmf(pmf, vlo, true, p.phred)) { fail("phred table"); return false; }
+        if (!phred_table_from_pmf(pmf, vlo, p.phred)) { fail("phred table"); return false; }
         normal_floor_pmf((double)p.read_length, 15.0, 65535, vlo, pmf);
         if (!len_table_from_pmf(pmf, vlo, p.rl)) { fail("rl table"); return false; }
         normal_floor_pmf((double)p.insert_size, 75.0, 65535, vlo, pmf);
@@ -542,14 +559,14 @@ bool make_profile(const orc_profile *in, Profile &p) {
     case ORC_PERFECT_LONG: {  /* perfect_long.rs:36-135 */
         p.is_long = true; p.mutates = true; p.min_size = 20000;
         std::vector<double> pq; perfect_long_pmf(pq);
-        if (!phred_table_from_pmf(pq, 0, true, p.phred)) { fail("phred table"); return false; }
+        if (!phred_table_from_pmf(pq, 0, p.phred)) { fail("phred table"); return false; }
         p.rl.kind = 2; p.is.kind = 0; p.is.value = 0;
         break; }
     case ORC_MINIMAL_LONG: {  /* minimal_long.rs:44-158 */
         p.is_long = true; p.mutates = true; p.min_size = 20000;
         uint32_t vlo; std::vector<double> pmf;
         normal_floor_pmf((double)(float)p.mean_phred, 10.0, 255, vlo, pmf);
-        if (!phred_table_from_pmf(pmf, vlo, true, p.phred)) { fail("phred table"); return false; }
+        if (!phred_table_from_pmf(pmf, vlo, p.phred)) { fail("phred table"); return false; }
         p.rl.kind = 2; p.is.kind = 0; p.is.value = 0;
         break; }
     case ORC_CUSTOM_SHORT: {  /* custom_short.rs:155-229, 237-270, 522-542 */
@@ -589,14 +606,18 @@ inline uint32_t sample_len(const LenTable &t, uint32_t w_alias, uint32_t w_inbin
     return lo + (uint32_t)(((uint64_t)w_inbin * span) >> 32);
 }
 inline void sample_phred(const PhredTable &t, uint32_t pos, uint32_t w, uint8_t &q, uint32_t &m) {
-    if (t.constant) { q = t.const_q; m = 0; return; }
+    if (t.kind == 0) { q = t.const_q; m = 0; return; }
     if (pos >= t.npos) pos = t.npos - 1;                       /* custom_short.rs:339-345 */
-    uint32_t idx = w >> (32 - t.cb);
-    uint32_t thr_draw = (uint32_t)(((uint64_t)w << t.cb) & 0xffffffffu) >> 10;
-    uint32_t e = t.entries[((size_t)pos << t.cb) + idx];
-    uint32_t o = (thr_draw < (e >> 10)) ? idx : (e & 0x3ffu);
-    q = (uint8_t)(t.qlo + (o >> t.mshift));
-    m = o & ((1u << t.mshift) - 1u);
+    const uint32_t idx = w >> (32 - t.cb), x = w << t.cb;
+    const size_t col = ((size_t)pos << t.cb) + idx;
+    if (t.kind == 1) {
+        const uint32_t thr = t.entries[2 * col], pay = t.entries[2 * col + 1];
+        const uint32_t sel = x < thr ? (pay & 0xffffu) : (pay >> 16);
+        q = (uint8_t)(sel & 0xffu); m = (sel >> 8) & 0xffu;
+    } else {
+        const uint32_t e = t.entries[col];
+        q = (uint8_t)((x >> 16) < (e >> 16) ? (e & 0xffu) : ((e >> 8) & 0xffu)); m = 0;
+    }
 }
 /* minimal_short.rs:124-131 substitution table */
 inline uint8_t substitute(uint8_t nt, uint32_t k) {
@@ -783,7 +804,7 @@ void native_read(const Profile &p, const Philox &ph, uint64_t u, uint32_t stream
     uint32_t w[4] = {0, 0, 0, 0};
     for (uint64_t i = 0; i < L; i++) {
         uint8_t q; uint32_t m;
-        if (p.phred.constant) { q = p.phred.const_q; m = 0; }
+        if (p.phred.kind == 0) { q = p.phred.const_q; m = 0; }
         else {
             if ((i & 3) == 0) ph.at(u, stream, (uint32_t)(i >> 2), w);
             sample_phred(p.phred, (uint32_t)std::min<uint64_t>(i, 0xffffffffu), w[i & 3], q, m);
@@ -957,12 +978,11 @@ int orc_abundance(int kind, int size_adjusted, uint64_t total_reads, uint32_t n,
 
 int orc_profile_min_genome_size(const orc_profile *pi, uint16_t *out) { Profile p; if (!make_profile(pi, p)) return -1; *out = p.min_size; return 0; }
 int orc_profile_is_long(const orc_profile *pi, int *out) { Profile p; if (!make_profile(pi, p)) return -1; *out = p.is_long; return 0; }
-int orc_profile_phred_table(const orc_profile *pi, uint32_t *cb, uint32_t *npos, uint32_t *qlo, uint32_t *mshift, uint32_t *entries, uint64_t cap) {
+int orc_profile_phred_table(const orc_profile *pi, uint32_t *kind, uint32_t *cb, uint32_t *npos, uint32_t *const_q, uint32_t *entries, uint64_t cap) {
     Profile p; if (!make_profile(pi, p)) return -1;
-    if (p.phred.constant) { *cb = 0; *npos = 0; *qlo = p.phred.const_q; *mshift = 0; return 0; }
-    *cb = p.phred.cb; *npos = p.phred.npos; *qlo = p.phred.qlo; *mshift = p.phred.mshift;
+    *kind = p.phred.kind; *cb = p.phred.cb; *npos = p.phred.npos; *const_q = p.phred.const_q;
     if (p.phred.entries.size() > cap) return fail("table buffer too small");
-    memcpy(entries, p.phred.entries.data(), p.phred.entries.size() * 4);
+    if (!p.phred.entries.empty()) memcpy(entries, p.phred.entries.data(), p.phred.entries.size() * 4);
     return (int)p.phred.entries.size();
 }
 int orc_profile_len_table(const orc_profile *pi, int which, uint32_t *kind, uint32_t *cb, uint32_t *entries, uint32_t *lo, uint32_t *hi, uint64_t cap) {

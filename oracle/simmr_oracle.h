@@ -118,9 +118,8 @@ int      orc_abundance(int kind, int size_adjusted, uint64_t total_reads, uint32
 int      orc_profile_min_genome_size(const orc_profile *p, uint16_t *out);
 int      orc_profile_is_long(const orc_profile *p, int *out);
 /* quantised alias tables the native mode samples from */
-int      orc_profile_phred_table(const orc_profile *p, uint32_t *cb, uint32_t *npos,
-                                 uint32_t *qlo, uint32_t *mshift,
-                                 uint32_t *entries, uint64_t cap);
+int      orc_profile_phred_table(const orc_profile *p, uint32_t *kind, uint32_t *cb, uint32_t *npos,
+                                 uint32_t *const_q, uint32_t *entries, uint64_t cap);
 int      orc_profile_len_table(const orc_profile *p, int which /*0=RL,1=IS*/,
                                uint32_t *kind, uint32_t *cb, uint32_t *entries,
                                uint32_t *lo, uint32_t *hi, uint64_t cap);

@@ -113,7 +113,7 @@ def lib():
         L.simmr_parse_genome_file.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64]
         L.simmr_parse_genome_file.restype = C.c_int64
         L.simmr_write_metadata.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), u64p, f64p]
-        L.simmr_debug_phred_table.argtypes = [C.POINTER(EProfileDesc), u32p, u32p, u32p, u32p, u32p, C.c_uint64]
+        L.simmr_debug_phred_table.argtypes = [C.POINTER(EProfileDesc), u32p, u32p, u32p, u32p, u32p, C.c_uint64]  # kind, cb, npos, const_q
         L.simmr_debug_len_table.argtypes = [C.POINTER(EProfileDesc), C.c_int, u32p, u32p, u32p, u32p, u32p, C.c_uint64]
         L.simmr_debug_philox4x32_10.argtypes = [u32p, u32p, u32p]
         L.simmr_debug_philox4x32_10.restype = None

@@ -72,12 +72,12 @@ class ErrorProfile:
         return bool(out.value)
 
     def phred_table(self):
-        cb, npos, qlo, ms = (C.c_uint32() for _ in range(4))
+        kind, cb, npos, cq = (C.c_uint32() for _ in range(4))
         ent = np.zeros(1 << 20, np.uint32)
         d = self.desc()
-        n = _check(N.lib().simmr_debug_phred_table(C.byref(d), C.byref(cb), C.byref(npos), C.byref(qlo), C.byref(ms),
+        n = _check(N.lib().simmr_debug_phred_table(C.byref(d), C.byref(kind), C.byref(cb), C.byref(npos), C.byref(cq),
                                                    _p(ent, N.u32p), len(ent)))
-        return dict(cb=cb.value, npos=npos.value, qlo=qlo.value, mshift=ms.value, entries=ent[:n].copy())
+        return dict(kind=kind.value, cb=cb.value, npos=npos.value, const_q=cq.value, entries=ent[:n].copy())
 
     def len_table(self, which):
         kind, cb = C.c_uint32(), C.c_uint32()

@@ -72,14 +72,13 @@ int simmr_eprofile_is_long_read(const simmr_eprofile_desc *d, int *out) {
     *out = m.is_long; return SIMMR_OK;
 }
 
-int simmr_debug_phred_table(const simmr_eprofile_desc *d, uint32_t *cb, uint32_t *npos, uint32_t *qlo, uint32_t *mshift, uint32_t *entries, uint64_t cap) {
+int simmr_debug_phred_table(const simmr_eprofile_desc *d, uint32_t *kind, uint32_t *cb, uint32_t *npos, uint32_t *const_q, uint32_t *entries, uint64_t cap) {
     ProfileModel m; std::string err;
     const int rc = build_profile(d, m, err);
     if (rc) return flunk(rc, err);
-    if (m.phred_const) { *cb = 0; *npos = 0; *qlo = m.const_q; *mshift = 0; return 0; }
-    *cb = m.cb; *npos = m.npos; *qlo = m.qlo; *mshift = m.mshift;
+    *kind = m.phred_kind; *cb = m.cb; *npos = m.npos; *const_q = m.const_q;
     if (m.phred_entries.size() > cap) return flunk(SIMMR_E_INVALID, "buffer too small");
-    memcpy(entries, m.phred_entries.data(), m.phred_entries.size() * 4);
+    if (!m.phred_entries.empty()) memcpy(entries, m.phred_entries.data(), m.phred_entries.size() * 4);
     return int(m.phred_entries.size());
 }
 int simmr_debug_len_table(const simmr_eprofile_desc *d, int which, uint32_t *kind, uint32_t *cb, uint32_t *entries, uint32_t *lo, uint32_t *hi, uint64_t cap) {

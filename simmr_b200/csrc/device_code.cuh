@@ -6,6 +6,7 @@
  *   (no reference equivalent: byte offsets of the FASTQ stream)   -> k_scan_blocks, k_unit_offsets
  *   simulate.rs:261-286 + error_profiles/ *.rs phreds/mutation +
  *   util.rs:15-57 RC / +33 + fastq.rs:61-69 record layout         -> k_format_tiles, k_format_direct
+ *   (load-time) which 32-byte blocks hold only A,C,G,T           -> k_purity
  *
  * Draw schedule, table formats and the tile layout are specified in DESIGN.md.
  * Compile with -fmad=false: the replay arithmetic (minimal_short.rs:90-100) and
@@ -37,12 +38,13 @@ struct ReplayDev {                 /* device copies of simmr_draws + replay LUTs
 struct RunParams {
     /* genomes (device resident) */
     const uint8_t *bases; const uint64_t *contig_off, *contig_size; const uint32_t *genome_contig;
+    const uint32_t *impure;        /* 1 bit per 32-byte block of `bases`: holds a byte other than A,C,G,T */
     const ContigHdr *chdr; const HdrTok *toks; const uint8_t *pool;
     uint32_t n_genomes, n_contigs;
     /* unit space */
     const uint64_t *unit_start;    /* [n_genomes+1] first global unit of each genome */
     uint64_t batch_begin; uint32_t batch_units; uint32_t read_id_base;
-    /* profile */
+    /* profile (phred.entries: device layout, quality bytes already +33) */
     PhredTab phred; LenTab rl, is; GammaConst gamma;
     uint32_t min_size, is_long, flags, mutates;
     uint32_t key0, key1;           /* Philox key = seed                          */
@@ -55,6 +57,15 @@ struct RunParams {
 
 constexpr int SIZES_THREADS = 256;
 constexpr int FORMAT_THREADS = 256;
+constexpr int SUB = 8;             /* lanes that share one record in the tile kernel */
+
+/* ---------------------------------------------------------------------- */
+/* small PTX helpers                                                        */
+/* ---------------------------------------------------------------------- */
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
 
 /* ---------------------------------------------------------------------- */
 /* Philox4x32-10                                                            */
@@ -63,9 +74,8 @@ struct Philox4 { uint32_t x, y, z, w; };
 __device__ __forceinline__ Philox4 philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        const uint64_t p0 = uint64_t(0xD2511F53u) * c0, p1 = uint64_t(0xCD9E8D57u) * c2;
+        c0 = uint32_t(p1 >> 32) ^ c1 ^ k0; c1 = uint32_t(p1); c2 = uint32_t(p0 >> 32) ^ c3 ^ k1; c3 = uint32_t(p0);
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return Philox4{c0, c1, c2, c3};
@@ -216,6 +226,19 @@ __device__ void unit_geometry(const RunParams &rp, const ReplayDev &rd, uint64_t
     }
 }
 
+/* does [a, a+L) touch a 32-byte block flagged as holding anything but A,C,G,T? */
+__device__ __forceinline__ bool window_impure(const RunParams &rp, uint64_t a, uint32_t L) {
+    if (!L) return false;
+    const uint64_t b0 = a >> 5, b1 = (a + L - 1) >> 5;
+    for (uint64_t w = b0 >> 5; w <= (b1 >> 5); ++w) {
+        uint32_t bits = __ldg(rp.impure + w);
+        if (w == (b0 >> 5)) bits &= 0xffffffffu << (b0 & 31);
+        if (w == (b1 >> 5)) bits &= 0xffffffffu >> (31 - (b1 & 31));
+        if (bits) return true;
+    }
+    return false;
+}
+
 /* ---------------------------------------------------------------------- */
 /* headers — fastq.rs:34-57                                                 */
 /* ---------------------------------------------------------------------- */
@@ -250,7 +273,7 @@ __device__ uint32_t emit_header(uint8_t *dst, const RunParams &rp, const ContigH
 }
 
 /* ---------------------------------------------------------------------- */
-/* per-base work                                                            */
+/* per-base work, generic (any byte values, replay, long reads)             */
 /* ---------------------------------------------------------------------- */
 /* util.rs:15-27 */
 __device__ __forceinline__ uint8_t complement(uint8_t b) {
@@ -291,47 +314,202 @@ __device__ __forceinline__ void replay_base(const RunParams &rp, const ReplayDev
     if (rp.mutates && rd.mut_u[slot] > rd.acc_lut[q]) m = 1 + rd.mut_k[slot] % 3;   /* minimal_short.rs:123-125 */
 }
 
-/* Writes one record body (everything after the header) for bases handled by
- * the calling group of `nthr` threads; `dst` may be shared or global memory.
- * Base i of the window gets quality slot i; for mate 2 the (mutated) base is
- * complemented and lands at L-1-i, the quality stays at i (simulate.rs:283-285). */
+/* (quality byte as printed, mutation code) of base i from its Philox word */
+__device__ __forceinline__ void native_base(const RunParams &rp, const uint32_t *tab, uint32_t r, uint32_t i, uint32_t &qc, uint32_t &m) {
+    const uint32_t cb = rp.phred.cb, idx = r >> (32 - cb), x = r << cb;
+    const uint32_t pos = i < rp.phred.npos ? i : rp.phred.npos - 1;               /* custom_short.rs:339-345 */
+    const uint32_t col = (pos << cb) + idx;
+    if (rp.phred.kind == PT_T64) {
+        const uint32_t thr = tab[2 * col], pay = tab[2 * col + 1];
+        const uint32_t s = x < thr ? pay : pay >> 16;
+        qc = s & 0xffu; m = (s >> 8) & 0xffu;
+    } else {
+        const uint32_t e = tab[col];
+        qc = ((x >> 16) < (e >> 16) ? e : e >> 8) & 0xffu; m = 0;
+    }
+}
+
+/* Writes one record body (everything after the header) with byte stores; `dst`
+ * may be shared or global memory.  Base i of the window gets quality slot i; for
+ * mate 2 the (mutated) base is complemented and lands at L-1-i, the quality stays
+ * at i (simulate.rs:283-285). */
 template <bool REPLAY>
-__device__ __forceinline__ void emit_body(const RunParams &rp, const ReplayDev &rd, const uint32_t *tab, uint8_t *dst,
-                                          uint64_t unit, uint32_t mate, uint64_t a, uint32_t L, uint64_t slot0, uint32_t thr, uint32_t nthr) {
+__device__ __forceinline__ void emit_body_generic(const RunParams &rp, const ReplayDev &rd, const uint32_t *tab, uint8_t *dst,
+                                                  uint64_t unit, uint32_t mate, uint64_t a, uint32_t L, uint64_t slot0, uint32_t thr, uint32_t nthr) {
     uint8_t *seq = dst + 1, *qual = dst + L + 4;
     if (thr == 0) { dst[0] = '\n'; dst[L + 1] = '\n'; dst[L + 2] = '+'; dst[L + 3] = '\n'; dst[2 * L + 4] = '\n'; }   /* fastq.rs:61-69 */
     const uint8_t *src = rp.bases + a;
     const bool rc = mate != 0;
-    const uint32_t cb = rp.phred.cb, mshift = rp.phred.mshift, mmask = (1u << mshift) - 1u, npos = rp.phred.npos;
     for (uint32_t g = thr; g * 4 < L; g += nthr) {
         Philox4 w{};
-        if (!REPLAY && !rp.phred.constant) w = draw(rp, unit, 1 + mate, g);
+        if (!REPLAY && rp.phred.kind != PT_CONST) w = draw(rp, unit, 1 + mate, g);
         const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) {
             const uint32_t i = 4 * g + j;
             if (i >= L) break;
-            uint32_t q, m;
-            if (REPLAY) replay_base(rp, rd, slot0 + i, i, q, m);
-            else if (rp.phred.constant) { q = rp.phred.const_q; m = 0; }
-            else {
-                const uint32_t r = wv[j], pos = i < npos ? i : npos - 1;
-                const uint32_t idx = r >> (32 - cb), frac = (r << cb) >> 10;
-                const uint32_t e = tab[(pos << cb) + idx];
-                const uint32_t o = frac < (e >> 10) ? idx : (e & 0x3ffu);
-                q = rp.phred.qlo + (o >> mshift); m = o & mmask;
-            }
+            uint32_t qc, m;
+            if (REPLAY) { uint32_t q; replay_base(rp, rd, slot0 + i, i, q, m); qc = (q + 33) & 0xffu; }   /* util.rs:46-50 */
+            else if (rp.phred.kind == PT_CONST) { qc = (rp.phred.const_q + 33) & 0xffu; m = 0; }
+            else native_base(rp, tab, wv[j], i, qc, m);
             uint8_t b = __ldg(src + i);
             if (m) b = substitute(b, m - 1);
-            qual[i] = uint8_t(q + 33);                                            /* util.rs:46-50 */
+            qual[i] = uint8_t(qc);
             if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;
         }
     }
 }
 
 /* ---------------------------------------------------------------------- */
+/* per-base work, fast path: windows of pure A/C/G/T, SWAR on 4 bases/word  */
+/* ---------------------------------------------------------------------- */
+/* One output line written through aligned 32-bit shared-memory stores.  Words
+ * arrive per 4-base group; the line starts at an arbitrary byte address, so two
+ * consecutive group words are funnel-shifted into each aligned word. */
+struct LineW {
+    uint32_t D, E;      /* shared-space byte range of the line                       */
+    uint32_t A0;        /* aligned address of composed word 0                        */
+    uint32_t sh;        /* 8 * (virtual start & 3)                                   */
+    uint32_t first, prev;
+};
+__device__ __forceinline__ void lw_init(LineW &w, uint32_t D, uint32_t L, uint32_t lead) {
+    const uint32_t V = D - lead;           /* `lead` garbage bytes precede the line (reversed lines) */
+    w.D = D; w.E = D + L; w.A0 = V & ~3u; w.sh = 8u * (V & 3u); w.first = w.prev = 0;
+}
+__device__ __forceinline__ void lw_emit(const LineW &w, uint32_t k, uint32_t c) {
+    const uint32_t addr = w.A0 + 4u * k;
+    const uint32_t lo = max(addr, w.D), hi = min(addr + 4u, w.E);
+    if (hi == lo + 4u) sts32(addr, c);
+    else if (hi > lo) for (uint32_t b = lo; b < hi; ++b) sts8(b, c >> (8u * (b - addr)));
+}
+/* ascending: group g's word holds line bytes [4g, 4g+4) */
+__device__ __forceinline__ void lw_step_asc(LineW &w, uint32_t t, uint32_t g, uint32_t x) {
+    if (t == 0) w.first = x; else lw_emit(w, g, __funnelshift_l(w.prev, x, w.sh));
+    w.prev = x;
+}
+__device__ __forceinline__ void lw_finish_asc(LineW &w, uint32_t g0, uint32_t sl, uint32_t mask) {
+    uint32_t left = __shfl_up_sync(mask, w.prev, 1, SUB);
+    if (sl == 0) left = 0;
+    lw_emit(w, g0, __funnelshift_l(left, w.first, w.sh));
+}
+/* descending: group g's word holds line bytes [L-4g-4, L-4g), i.e. composed index NG-1-g */
+__device__ __forceinline__ void lw_step_desc(LineW &w, uint32_t t, uint32_t g, uint32_t NG, uint32_t x) {
+    if (t == 0) w.first = x; else lw_emit(w, NG - g, __funnelshift_l(x, w.prev, w.sh));
+    w.prev = x;
+}
+__device__ __forceinline__ void lw_finish_desc(LineW &w, uint32_t g0, uint32_t NG, uint32_t sl, uint32_t mask) {
+    uint32_t left = __shfl_up_sync(mask, w.prev, 1, SUB);
+    if (sl == 0) left = 0;
+    lw_emit(w, NG - g0, __funnelshift_l(w.first, left, w.sh));
+}
+
+/* complement of four A/C/G/T bytes: A<->T is ^0x15, C<->G is ^0x04; bit 1 tells which */
+__device__ __forceinline__ uint32_t comp4(uint32_t b) {
+    const uint32_t t = (b >> 1) & 0x01010101u;
+    return b ^ 0x15151515u ^ (t * 0x11u);
+}
+/* substitutions on a word of pure A/C/G/T; mw byte j = 0 or choose()+1 */
+__device__ __forceinline__ uint32_t mutate4(uint32_t bw, uint32_t mw) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t m = (mw >> (8 * j)) & 0xffu;
+        if (m) {
+            const uint32_t b = (bw >> (8 * j)) & 0xffu, rank = ((b >> 1) ^ (b >> 2)) & 3u, k = m - 1;
+            const uint32_t nb = (0x54474341u >> (8u * (k + (k >= rank)))) & 0xffu;
+            bw = (bw & ~(0xffu << (8 * j))) | (nb << (8 * j));
+        }
+    }
+    return bw;
+}
+
+/* quality characters and mutation codes of bases 4g..4g+3 */
+template <int TK>
+__device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, Philox4 w, uint32_t g, uint32_t &qw, uint32_t &mw) {
+    const uint32_t cb = rp.phred.cb;
+    const uint32_t r[4] = {w.x, w.y, w.z, w.w};
+    if (TK == PT_T64) {
+        uint32_t p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint2 e = lds64(tab_s + ((r[j] >> (32 - cb)) << 3));
+            p[j] = (r[j] << cb) < e.x ? e.y : e.y >> 16;
+        }
+        const uint32_t p01 = __byte_perm(p[0], p[1], 0x5410), p23 = __byte_perm(p[2], p[3], 0x5410);
+        qw = __byte_perm(p01, p23, 0x6420); mw = __byte_perm(p01, p23, 0x7531);
+    } else {
+        uint32_t v[4];
+        const uint32_t last = rp.phred.npos - 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t pos = min(4 * g + j, last);
+            const uint32_t e = lds32(tab_s + ((((pos << cb) + (r[j] >> (32 - cb)))) << 2));
+            v[j] = ((r[j] << cb) >> 16) < (e >> 16) ? e : e >> 8;
+        }
+        qw = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410); mw = 0;
+    }
+}
+
+/* One record body by a sub-group of SUB lanes: lane `sl` handles the 4-base
+ * groups [sl*T, (sl+1)*T).  body_s = shared-space address of the '\n' that ends
+ * the header. */
+template <int TK>
+__device__ __forceinline__ void emit_body_fast(const RunParams &rp, uint32_t tab_s, uint32_t body_s, uint64_t unit, uint32_t mate,
+                                               uint64_t a, uint32_t L, uint32_t sl, uint32_t mask) {
+    if (sl == 0) { sts8(body_s, '\n'); sts8(body_s + L + 1, '\n'); sts8(body_s + L + 2, '+'); sts8(body_s + L + 3, '\n'); sts8(body_s + 2 * L + 4, '\n'); }
+    const uint32_t NG = (L + 3) >> 2, T = (NG + SUB) / SUB;          /* SUB*T >= NG+1 composed words */
+    const bool rc = mate != 0;
+    LineW ls, lq;
+    lw_init(ls, body_s + 1, L, rc ? ((4u - (L & 3u)) & 3u) : 0u);
+    lw_init(lq, body_s + L + 4, L, 0);
+    const uint32_t al = uint32_t(a & 3u);                               /* rp.bases is 256-byte aligned */
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(rp.bases + (a - al));
+    const uint32_t g0 = sl * T;
+    const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u;
+    for (uint32_t t = 0; t < T; ++t) {
+        const uint32_t g = g0 + t;
+        uint32_t sw = 0, qw = 0;
+        if (g < NG) {
+            const uint32_t w0 = __ldg(src + g), w1 = __ldg(src + g + 1);
+            sw = __funnelshift_r(w0, w1, 8u * al);
+            if (TK == PT_CONST) qw = qconst;
+            else {
+                uint32_t mw;
+                sample4<TK>(rp, tab_s, draw(rp, unit, 1 + mate, g), g, qw, mw);
+                if (TK == PT_T64 && mw) sw = mutate4(sw, mw);
+            }
+            if (rc) sw = __byte_perm(comp4(sw), 0, 0x0123);
+        }
+        if (rc) lw_step_desc(ls, t, g, NG, sw); else lw_step_asc(ls, t, g, sw);
+        lw_step_asc(lq, t, g, qw);
+    }
+    if (rc) lw_finish_desc(ls, g0, NG, sl, mask); else lw_finish_asc(ls, g0, sl, mask);
+    lw_finish_asc(lq, g0, sl, mask);
+}
+
+/* ---------------------------------------------------------------------- */
 /* kernels                                                                  */
 /* ---------------------------------------------------------------------- */
+/* load time: bit per 32-byte block = block holds a byte that is not A,C,G,T */
+__global__ void k_purity(const uint8_t *bases, uint64_t nbytes, uint32_t *impure, uint64_t nwords) {
+    const uint64_t w = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if (w >= nwords) return;
+    uint32_t bits = 0;
+    for (uint32_t b = 0; b < 32; ++b) {
+        const uint64_t off = (w * 32 + b) * 32;
+        bool bad = false;
+        for (uint32_t k = 0; k < 32 && off + k < nbytes; k += 4) {
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(bases + off + k);   /* tail is padded with 'N' */
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t c = (v >> (8 * j)) & 0xffu;
+                if (off + k + j < nbytes) bad |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+            }
+        }
+        bits |= uint32_t(bad) << b;
+    }
+    impure[w] = bits;
+}
+
 __device__ __forceinline__ uint64_t block_sum_u64(uint64_t v, uint64_t *sh) {
     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -422,27 +600,33 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_offsets(RunParams rp) {
 struct TileUnit {      /* geometry of one unit, kept in shared memory for the tile */
     UnitGeo g;
     uint32_t off[2], H[2];
+    uint32_t impure[2], pad_[2];
     uint64_t slot0;
 };
 
 /* Persistent CTAs; each tile = `upt` consecutive units whose FASTQ bytes are
- * composed in shared memory and leave through one bulk async copy (TMA). */
-template <bool REPLAY>
+ * composed in shared memory and leave through one bulk async copy (TMA).
+ * TK = table kind the fast path is specialised for (REPLAY always takes the
+ * generic per-base path). */
+template <bool REPLAY, int TK>
 __global__ void __launch_bounds__(FORMAT_THREADS) k_format_tiles(RunParams rp, ReplayDev rd) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t tab_words = rp.phred.constant ? 0 : (rp.phred.npos << rp.phred.cb);
+    __shared__ uint32_t next_rec;
+    const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u : 1u);
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
     TileUnit *tu = reinterpret_cast<TileUnit *>(smem + ((tab_words * 4 + 15) & ~15u));
     uint8_t *stage = reinterpret_cast<uint8_t *>(tu + rp.upt);
     stage += (16 - (reinterpret_cast<uintptr_t>(stage) & 15)) & 15;
     for (uint32_t i = threadIdx.x; i < tab_words; i += FORMAT_THREADS) tab[i] = rp.phred.entries[i];
+    const uint32_t tab_s = uint32_t(__cvta_generic_to_shared(tab)), stage_s = uint32_t(__cvta_generic_to_shared(stage));
 
     const uint32_t ntiles = (rp.batch_units + rp.upt - 1) / rp.upt;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31, sl = threadIdx.x & (SUB - 1);
+    const uint32_t submask = ((1u << SUB) - 1u) << (lane & ~(SUB - 1));
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t u0 = tile * rp.upt, nu = min(rp.upt, rp.batch_units - u0);
         /* the previous tile's bulk copy must have finished reading the stage */
-        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (threadIdx.x == 0) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); next_rec = 0; }
         __syncthreads();
         const uint64_t tile_base = rp.offsets[u0], tile_end = rp.offsets[u0 + nu];
         const uint32_t pad = uint32_t(tile_base & 15), total = uint32_t(tile_end - tile_base);
@@ -455,30 +639,39 @@ __global__ void __launch_bounds__(FORMAT_THREADS) k_format_tiles(RunParams rp, R
             for (uint32_t r = 0; r < t.g.nrec; ++r) {
                 t.H[r] = header_len(ch, t.g.id, t.g.sp[r], t.g.ep[r]);
                 t.off[r] = off; off += t.H[r] + 2 * t.g.L[r] + 5;
+                t.impure[r] = REPLAY ? 1u : uint32_t(window_impure(rp, t.g.a[r], t.g.L[r]));
             }
             t.slot0 = REPLAY ? rd.base_off[u] : 0;
         }
         __syncthreads();
+        const uint32_t nrec = 2 * nu;
         /* headers: one thread per record */
-        for (uint32_t r = threadIdx.x; r < 2 * nu; r += FORMAT_THREADS) {
+        for (uint32_t r = threadIdx.x; r < nrec; r += FORMAT_THREADS) {
             const TileUnit &t = tu[r >> 1]; const uint32_t mate = r & 1;
             if (mate < t.g.nrec)
                 emit_header(stage + t.off[mate], rp, rp.chdr[t.g.contig], t.g.id, t.g.sp[mate], t.g.ep[mate], mate != 0, mate);
         }
-        /* bodies: one warp per record */
-        for (uint32_t r = warp; r < 2 * nu; r += FORMAT_THREADS / 32) {
+        /* bodies: sub-groups of SUB lanes pull records from a shared counter */
+        for (;;) {
+            uint32_t r = 0;
+            if (sl == 0) r = atomicAdd(&next_rec, 1u);
+            r = __shfl_sync(submask, r, 0, SUB);
+            if (r >= nrec) break;
             const TileUnit &t = tu[r >> 1]; const uint32_t mate = r & 1;
-            if (mate < t.g.nrec)
-                emit_body<REPLAY>(rp, rd, tab, stage + t.off[mate] + t.H[mate], rp.batch_begin + u0 + (r >> 1), mate,
-                                  t.g.a[mate], t.g.L[mate], t.slot0 + (mate ? t.g.rl : 0), lane, 32);
+            if (mate >= t.g.nrec) continue;
+            const uint32_t body = t.off[mate] + t.H[mate];
+            if (!REPLAY && !t.impure[mate])
+                emit_body_fast<TK>(rp, tab_s, stage_s + body, rp.batch_begin + u0 + (r >> 1), mate, t.g.a[mate], t.g.L[mate], sl, submask);
+            else
+                emit_body_generic<REPLAY>(rp, rd, tab, stage + body, rp.batch_begin + u0 + (r >> 1), mate, t.g.a[mate], t.g.L[mate],
+                                          t.slot0 + (mate ? t.g.rl : 0), sl, SUB);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         /* stage[pad, pad+total) -> out[tile_base, tile_end): 16-byte aligned middle by TMA, edges by byte stores */
         const uint32_t head = min(total, (16 - pad) & 15), mid = (total - head) & ~15u, tail = total - head - mid;
         if (threadIdx.x == 0 && mid) {
-            const uint32_t saddr = uint32_t(__cvta_generic_to_shared(stage + pad + head));
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rp.out + tile_base + head), "r"(saddr), "r"(mid) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rp.out + tile_base + head), "r"(stage_s + pad + head), "r"(mid) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (threadIdx.x >= 32 && threadIdx.x < 32 + head) rp.out[tile_base + (threadIdx.x - 32)] = stage[pad + (threadIdx.x - 32)];
@@ -493,7 +686,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS) k_format_tiles(RunParams rp, R
 template <bool REPLAY>
 __global__ void __launch_bounds__(FORMAT_THREADS) k_format_direct(RunParams rp, ReplayDev rd) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t tab_words = rp.phred.constant ? 0 : (rp.phred.npos << rp.phred.cb);
+    const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u : 1u);
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
     __shared__ UnitGeo g;
     __shared__ uint32_t H[2];
@@ -511,7 +704,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS) k_format_direct(RunParams rp, 
         const uint64_t slot0 = REPLAY ? rd.base_off[u] : 0;
         for (uint32_t r = 0; r < g.nrec; ++r) {
             if (threadIdx.x == 0) emit_header(dst, rp, rp.chdr[g.contig], g.id, g.sp[r], g.ep[r], r != 0, int(r));
-            emit_body<REPLAY>(rp, rd, tab, dst + H[r], u, r, g.a[r], g.L[r], slot0 + (r ? g.rl : 0), threadIdx.x, FORMAT_THREADS);
+            emit_body_generic<REPLAY>(rp, rd, tab, dst + H[r], u, r, g.a[r], g.L[r], slot0 + (r ? g.rl : 0), threadIdx.x, FORMAT_THREADS);
             dst += H[r] + 2 * g.L[r] + 5;
         }
     }

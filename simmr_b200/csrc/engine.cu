@@ -66,7 +66,7 @@ struct simmr_ctx {
     std::vector<uint64_t> h_contig_off, h_contig_size;
     std::vector<uint32_t> h_genome_contig, h_contig_id_off, h_genome_id_off;
     std::string h_contig_ids, h_genome_ids;
-    DevMem d_bases, d_contig_off, d_contig_size, d_genome_contig;
+    DevMem d_bases, d_impure, d_contig_off, d_contig_size, d_genome_contig;
     /* headers */
     std::string header_fmt; bool have_headers = false;
     HeaderPlan plan;
@@ -96,10 +96,22 @@ int fail(simmr_ctx *c, int code, const std::string &m) {
         if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+size_t table_bytes(const ProfileModel &m) { return m.phred_entries.size() * 4; }
 size_t tile_smem(const ProfileModel &m, uint32_t upt, uint32_t stage_cap) {
-    const size_t tab = m.phred_const ? 0 : (size_t(m.npos) << m.cb) * 4;
-    return ((tab + 15) & ~size_t(15)) + size_t(upt) * sizeof(TileUnit) + stage_cap + 48;
+    return ((table_bytes(m) + 15) & ~size_t(15)) + size_t(upt) * sizeof(TileUnit) + stage_cap + 48;
 }
+
+/* kernel instantiations: the fast path is specialised per table kind, replay is generic */
+using FormatKernel = void (*)(RunParams, ReplayDev);
+FormatKernel tiles_kernel(bool replay, uint32_t kind) {
+    if (replay) return k_format_tiles<true, PT_CONST>;
+    switch (kind) {
+    case PT_T64: return k_format_tiles<false, PT_T64>;
+    case PT_T32: return k_format_tiles<false, PT_T32>;
+    default: return k_format_tiles<false, PT_CONST>;
+    }
+}
+FormatKernel direct_kernel(bool replay) { return replay ? k_format_direct<true> : k_format_direct<false>; }
 
 struct Plan {      /* launch geometry for one run */
     bool tiles = false;
@@ -114,7 +126,7 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
     const uint64_t unit_bytes = per_rec * (m.is_long ? 1 : 2);
     if (unit_bytes > 0xfff00000ull) return fail(ctx, SIMMR_E_LIMIT, "a unit's FASTQ bytes exceed 4 GiB");
     pl.max_unit_bytes = uint32_t(unit_bytes);
-    const size_t tab = m.phred_const ? 0 : (size_t(m.npos) << m.cb) * 4;
+    const size_t tab = table_bytes(m);
     const size_t smem_max = ctx->prop.sharedMemPerBlockOptin;
     if (tab + 1024 > smem_max) return fail(ctx, SIMMR_E_LIMIT, "quality tables do not fit in shared memory");
     pl.tiles = !m.is_long;
@@ -128,16 +140,9 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
     }
     if (!pl.tiles) pl.smem = tab;
     int occ = 0;
-    cudaError_t e;
-    if (pl.tiles) {
-        auto k = replay ? k_format_tiles<true> : k_format_tiles<false>;
-        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, FORMAT_THREADS, pl.smem);
-    } else {
-        auto k = replay ? k_format_direct<true> : k_format_direct<false>;
-        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, FORMAT_THREADS, pl.smem);
-    }
+    FormatKernel k = pl.tiles ? tiles_kernel(replay, m.phred_kind) : direct_kernel(replay);
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, FORMAT_THREADS, pl.smem);
     CU(e);
     if (occ < 1) return fail(ctx, SIMMR_E_LIMIT, "format kernel does not fit on an SM");
     pl.grid = occ * ctx->prop.multiProcessorCount;
@@ -163,11 +168,12 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     memset(&rp, 0, sizeof rp);
     rp.bases = ctx->d_bases.as<uint8_t>(); rp.contig_off = ctx->d_contig_off.as<uint64_t>();
     rp.contig_size = ctx->d_contig_size.as<uint64_t>(); rp.genome_contig = ctx->d_genome_contig.as<uint32_t>();
+    rp.impure = ctx->d_impure.as<uint32_t>();
     rp.chdr = ctx->d_chdr.as<ContigHdr>(); rp.toks = ctx->d_toks.as<HdrTok>(); rp.pool = ctx->d_pool.as<uint8_t>();
     rp.n_genomes = ctx->host_view.n_genomes; rp.n_contigs = ctx->host_view.n_contigs;
     rp.unit_start = ctx->d_unit_start.as<uint64_t>();
     rp.read_id_base = id_base;
-    rp.phred = PhredTab{m.phred_const ? 1u : 0u, m.const_q, m.cb, m.npos, m.qlo, m.mshift, ctx->d_phred.as<uint32_t>()};
+    rp.phred = PhredTab{m.phred_kind, m.const_q, m.cb, m.npos, ctx->d_phred.as<uint32_t>()};
     rp.rl = LenTab{m.rl.kind, m.rl.value, m.rl.cb, 0, ctx->d_rl_e.as<uint32_t>(), ctx->d_rl_lo.as<uint32_t>(), ctx->d_rl_hi.as<uint32_t>()};
     rp.is = LenTab{m.is.kind, m.is.value, m.is.cb, 0, ctx->d_is_e.as<uint32_t>(), ctx->d_is_lo.as<uint32_t>(), ctx->d_is_hi.as<uint32_t>()};
     rp.gamma = m.gamma;
@@ -232,12 +238,10 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         if (pl.tiles) {
             const uint32_t ntiles = (n + pl.upt - 1) / pl.upt;
             const int grid = int(std::min<uint32_t>(ntiles, uint32_t(pl.grid)));
-            if (replay) k_format_tiles<true><<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
-            else k_format_tiles<false><<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
+            tiles_kernel(replay, ctx->model.phred_kind)<<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
         } else {
             const int grid = int(std::min<uint32_t>(n, uint32_t(pl.grid)));
-            if (replay) k_format_direct<true><<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
-            else k_format_direct<false><<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
+            direct_kernel(replay)<<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
         }
         CU(cudaGetLastError());
         CU(cudaEventRecord(ev_f1, ctx->compute));
@@ -360,6 +364,12 @@ int simmr_genomes_load(simmr_ctx *ctx, const simmr_genome_set *s) {
     CU(ctx->d_bases.reserve(nbytes + 64));
     CU(cudaMemcpy(ctx->d_bases.p, s->bases, nbytes, cudaMemcpyHostToDevice));
     CU(cudaMemset(static_cast<uint8_t *>(ctx->d_bases.p) + nbytes, 'N', 64));
+    {   /* which 32-byte blocks hold only A,C,G,T: lets the format kernel take its branch-free path */
+        const uint64_t nblocks = (nbytes + 31) / 32, nwords = (nblocks + 31) / 32 + 1;
+        CU(ctx->d_impure.reserve(nwords * 4));
+        k_purity<<<unsigned((nwords + 255) / 256), 256, 0, ctx->compute>>>(ctx->d_bases.as<uint8_t>(), nbytes, ctx->d_impure.as<uint32_t>(), nwords);
+        CU(cudaGetLastError());
+    }
     CU(ctx->d_contig_off.upload(ctx->h_contig_off.data(), ctx->h_contig_off.size(), ctx->compute));
     CU(ctx->d_contig_size.upload(ctx->h_contig_size.data(), ctx->h_contig_size.size(), ctx->compute));
     CU(ctx->d_genome_contig.upload(ctx->h_genome_contig.data(), ctx->h_genome_contig.size(), ctx->compute));
@@ -377,7 +387,14 @@ int simmr_error_profile_set(simmr_ctx *ctx, const simmr_eprofile_desc *d) {
     if (rc) return fail(ctx, rc, err);
     const ProfileModel &m = ctx->model;
     cudaStream_t s = ctx->compute;
-    CU(ctx->d_phred.upload(m.phred_entries.data(), m.phred_entries.size(), s));
+    {   /* device layout: quality bytes carry the +33 of util.rs:46-50 already */
+        std::vector<uint32_t> dev = m.phred_entries;
+        auto plus33 = [](uint32_t w, int shift) { return (w & ~(0xffu << shift)) | ((((w >> shift) & 0xffu) + 33u) & 0xffu) << shift; };
+        if (m.phred_kind == PT_T64) for (size_t i = 1; i < dev.size(); i += 2) dev[i] = plus33(plus33(dev[i], 0), 16);
+        if (m.phred_kind == PT_T32) for (uint32_t &w : dev) w = plus33(plus33(w, 0), 8);
+        CU(ctx->d_phred.upload(dev.data(), dev.size(), s));
+        CU(cudaStreamSynchronize(s));
+    }
     CU(ctx->d_rl_e.upload(m.rl.entries.data(), m.rl.entries.size(), s)); CU(ctx->d_rl_lo.upload(m.rl.lo.data(), m.rl.lo.size(), s)); CU(ctx->d_rl_hi.upload(m.rl.hi.data(), m.rl.hi.size(), s));
     CU(ctx->d_is_e.upload(m.is.entries.data(), m.is.entries.size(), s)); CU(ctx->d_is_lo.upload(m.is.lo.data(), m.is.lo.size(), s)); CU(ctx->d_is_hi.upload(m.is.hi.data(), m.is.hi.size(), s));
     CU(ctx->d_acc.upload(m.acc_lut, 256, s)); CU(ctx->d_plthr.upload(m.pl_thr, 64, s));

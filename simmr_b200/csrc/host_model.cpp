@@ -109,18 +109,18 @@ inline uint16_t cast_u16(double x) { return !(x == x) || x <= 0.0 ? 0 : (x >= 65
 
 inline uint32_t bits_for(size_t n) { uint32_t b = 0; while ((size_t(1) << b) < n) ++b; return b ? b : 1; }
 
-/* Vose alias table over 2^cb columns with quantised thresholds.
- * Word layout: threshold (tbits) above alias (abits). */
-bool quant_alias(const std::vector<double> &weight, uint32_t cb, uint32_t tbits, uint32_t abits,
-                 std::vector<uint32_t> &words) {
+/* Vose alias method over 2^cb columns: keep[i] is the probability of
+ * staying in column i, other[i] the column taken otherwise. */
+bool alias_columns(const std::vector<double> &weight, uint32_t cb, std::vector<double> &keep, std::vector<uint32_t> &other) {
     const size_t cols = size_t(1) << cb;
     if (weight.size() > cols) return false;
     double total = 0.0;
     for (double w : weight) total += w;
     if (!(total > 0.0)) return false;
-    std::vector<double> height(cols, 0.0), keep(cols, 1.0);
+    std::vector<double> height(cols, 0.0);
+    keep.assign(cols, 1.0); other.resize(cols);
     for (size_t i = 0; i < weight.size(); ++i) height[i] = weight[i] * double(cols) / total;
-    std::vector<uint32_t> under, over, other(cols);
+    std::vector<uint32_t> under, over;
     for (size_t i = 0; i < cols; ++i) {
         other[i] = uint32_t(i);
         (height[i] < 1.0 ? under : over).push_back(uint32_t(i));
@@ -132,18 +132,21 @@ bool quant_alias(const std::vector<double> &weight, uint32_t cb, uint32_t tbits,
         height[v] = (height[v] + height[u]) - 1.0;
         (height[v] < 1.0 ? under : over).push_back(v);
     }
-    const uint32_t top = uint32_t((uint64_t(1) << tbits) - 1);
-    const double unit = double(uint64_t(1) << tbits);
-    words.resize(cols);
-    for (size_t i = 0; i < cols; ++i) {
-        uint32_t thr = top, al = other[i];
-        if (keep[i] >= 1.0) al = uint32_t(i);
-        else {
-            const double f = std::floor(keep[i] * unit);
-            thr = f <= 0.0 ? 0u : (f >= double(top) ? top : uint32_t(f));
-        }
-        words[i] = (thr << abits) | al;
-    }
+    for (size_t i = 0; i < cols; ++i) if (keep[i] >= 1.0) other[i] = uint32_t(i);
+    return true;
+}
+/* floor(p * 2^bits) saturated to `bits` bits; certain columns get all ones */
+inline uint32_t threshold(double p, uint32_t bits) {
+    const uint32_t ones = bits >= 32 ? 0xffffffffu : (1u << bits) - 1u;
+    if (p >= 1.0) return ones;
+    const double f = std::floor(std::ldexp(p, int(bits)));
+    return f <= 0.0 ? 0u : (f >= double(ones) ? ones : uint32_t(f));
+}
+bool len_words(const std::vector<double> &weight, uint32_t cb, std::vector<uint32_t> &words) {
+    std::vector<double> keep; std::vector<uint32_t> other;
+    if (!alias_columns(weight, cb, keep, other)) return false;
+    words.resize(keep.size());
+    for (size_t i = 0; i < keep.size(); ++i) words[i] = (threshold(keep[i], 20) << 12) | other[i];
     return true;
 }
 
@@ -170,18 +173,26 @@ double flip_probability(uint8_t q) {
     return (16777215.0 - t) / 16777216.0;
 }
 
-bool phred_from_mass(const std::vector<double> &mass, uint32_t first, bool mutates, ProfileModel &m) {
-    std::vector<double> w;
-    if (mutates) {
-        w.resize(mass.size() * 4);
-        for (size_t i = 0; i < mass.size(); ++i) {
-            const double f = flip_probability(uint8_t(first + i));
-            w[4 * i] = mass[i] * (1.0 - f);
-            w[4 * i + 1] = w[4 * i + 2] = w[4 * i + 3] = mass[i] * f / 3.0;
-        }
-    } else w = mass;
-    m.mshift = mutates ? 2 : 0; m.qlo = first; m.npos = 1; m.cb = bits_for(w.size());
-    return m.cb <= 10 && quant_alias(w, m.cb, 22, 10, m.phred_entries);
+/* joint (quality, mutation) table: outcome = (q-first)<<2 | m, m = 0 none, 1..3 = choose() index + 1 */
+bool phred_from_mass(const std::vector<double> &mass, uint32_t first, ProfileModel &m) {
+    std::vector<double> w(mass.size() * 4);
+    for (size_t i = 0; i < mass.size(); ++i) {
+        const double f = flip_probability(uint8_t(first + i));
+        w[4 * i] = mass[i] * (1.0 - f);
+        w[4 * i + 1] = w[4 * i + 2] = w[4 * i + 3] = mass[i] * f / 3.0;
+    }
+    m.phred_kind = PT_T64; m.npos = 1; m.cb = bits_for(w.size());
+    if (m.cb > 10) return false;
+    std::vector<double> keep; std::vector<uint32_t> other;
+    if (!alias_columns(w, m.cb, keep, other)) return false;
+    m.phred_entries.resize(keep.size() * 2);
+    for (size_t i = 0; i < keep.size(); ++i) {
+        const uint32_t self = ((first + (uint32_t(i) >> 2)) & 0xffu) | ((uint32_t(i) & 3u) << 8);
+        const uint32_t alt = ((first + (other[i] >> 2)) & 0xffu) | ((other[i] & 3u) << 8);
+        m.phred_entries[2 * i] = threshold(keep[i], 32);
+        m.phred_entries[2 * i + 1] = self | (alt << 16);
+    }
+    return true;
 }
 
 bool phred_from_blob(const ProfileBlob &b, ProfileModel &m) {
@@ -208,13 +219,14 @@ bool phred_from_blob(const ProfileBlob &b, ProfileModel &m) {
         }
     }
     if (qmin > qmax) return false;
-    m.qlo = qmin; m.mshift = 0; m.npos = uint32_t(np); m.cb = bits_for(qmax - qmin + 1);
+    m.phred_kind = PT_T32; m.npos = uint32_t(np); m.cb = bits_for(qmax - qmin + 1);
     m.phred_entries.clear();
     for (size_t p = 0; p < np; ++p) {
-        std::vector<double> w(mass[p].begin() + qmin, mass[p].begin() + qmax + 1);
-        std::vector<uint32_t> e;
-        if (!quant_alias(w, m.cb, 22, 10, e)) return false;
-        m.phred_entries.insert(m.phred_entries.end(), e.begin(), e.end());
+        std::vector<double> w(mass[p].begin() + qmin, mass[p].begin() + qmax + 1), keep;
+        std::vector<uint32_t> other;
+        if (!alias_columns(w, m.cb, keep, other)) return false;
+        for (size_t i = 0; i < keep.size(); ++i)
+            m.phred_entries.push_back((threshold(keep[i], 16) << 16) | (((qmin + other[i]) & 0xffu) << 8) | ((qmin + uint32_t(i)) & 0xffu));
     }
     return true;
 }
@@ -226,7 +238,7 @@ bool len_from_mass(const std::vector<double> &mass, uint32_t first, LenModel &t)
     t.lo.assign(cols, first); t.hi.assign(cols, first);
     for (size_t i = 0; i < mass.size(); ++i) t.lo[i] = t.hi[i] = first + uint32_t(i);
     t.vmax = first + uint32_t(mass.size()) - 1;
-    return quant_alias(mass, t.cb, 20, 12, t.entries);
+    return len_words(mass, t.cb, t.entries);
 }
 bool len_from_bins(const BinSet &b, LenModel &t) {
     if (b.density.empty()) return false;
@@ -235,7 +247,7 @@ bool len_from_bins(const BinSet &b, LenModel &t) {
     const size_t cols = size_t(1) << t.cb;
     t.lo.assign(cols, 0); t.hi.assign(cols, 0); t.vmax = 0;
     for (size_t j = 0; j < b.density.size(); ++j) { b.range_of(j, t.lo[j], t.hi[j]); t.vmax = std::max(t.vmax, t.hi[j]); }
-    return quant_alias(b.density, t.cb, 20, 12, t.entries);
+    return len_words(b.density, t.cb, t.entries);
 }
 void len_const(LenModel &t, uint32_t v) { t = LenModel(); t.kind = LEN_CONST; t.value = v; t.vmax = v; }
 
@@ -291,14 +303,14 @@ int build_profile(const simmr_eprofile_desc *d, ProfileModel &m, std::string &er
     switch (d->kind) {
     case SIMMR_EP_PERFECT_SHORT:    /* perfect_short.rs:22-63 */
         m.min_size = uint16_t(2 * d->read_length + d->insert_size);
-        m.phred_const = true; m.const_q = 60; m.replay_kind = RP_CONST;
+        m.phred_kind = PT_CONST; m.const_q = 60; m.replay_kind = RP_CONST;
         len_const(m.rl, d->read_length); len_const(m.is, d->insert_size);
         break;
     case SIMMR_EP_MINIMAL_SHORT:    /* minimal_short.rs:33-149; sigmas from cli.rs:239-240 */
         m.min_size = uint16_t(2 * d->read_length + d->insert_size);
         m.mutates = true; m.replay_kind = RP_NORMAL_FLOOR;
         floor_normal(double(m.mean_phred_f), 10.0, 255, first, mass);
-        if (!phred_from_mass(mass, first, true, m)) { err = "phred table"; return SIMMR_E_INVALID; }
+        if (!phred_from_mass(mass, first, m)) { err = "phred table"; return SIMMR_E_INVALID; }
         floor_normal(double(d->read_length), 15.0, 65535, first, mass);
         if (!len_from_mass(mass, first, m.rl)) { err = "read-length table"; return SIMMR_E_INVALID; }
         floor_normal(double(d->insert_size), 75.0, 65535, first, mass);
@@ -312,7 +324,7 @@ int build_profile(const simmr_eprofile_desc *d, ProfileModel &m, std::string &er
         mass.assign(size_t(cap) + 1, 0.0);
         for (int k = 0; k <= cap; ++k)
             mass[k] = (k == cap ? 1.0 : phi(edge(k + 1), mu, sd)) - (k == 0 ? 0.0 : phi(edge(k), mu, sd));
-        if (!phred_from_mass(mass, 0, true, m)) { err = "phred table"; return SIMMR_E_INVALID; }
+        if (!phred_from_mass(mass, 0, m)) { err = "phred table"; return SIMMR_E_INVALID; }
         /* replay: smallest f32 accuracy whose phred is >= k, by bisection on the bit pattern */
         m.pl_qmax = cap;
         for (uint32_t k = 1; k <= cap; ++k) {
@@ -328,7 +340,7 @@ int build_profile(const simmr_eprofile_desc *d, ProfileModel &m, std::string &er
     case SIMMR_EP_MINIMAL_LONG:     /* minimal_long.rs:44-158 */
         long_common(); m.mutates = true; m.replay_kind = RP_NORMAL_FLOOR;
         floor_normal(double(m.mean_phred_f), 10.0, 255, first, mass);
-        if (!phred_from_mass(mass, first, true, m)) { err = "phred table"; return SIMMR_E_INVALID; }
+        if (!phred_from_mass(mass, first, m)) { err = "phred table"; return SIMMR_E_INVALID; }
         break;
     case SIMMR_EP_CUSTOM_SHORT:     /* custom_short.rs:155-229, 237-270, 522-542 */
         m.is_long = blob.is_long; m.replay_kind = RP_ALIAS;

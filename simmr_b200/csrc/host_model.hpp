@@ -41,10 +41,10 @@ struct ProfileModel {
     uint16_t min_size = 0;
     uint32_t flags = 0;
     /* native sampling tables */
-    bool phred_const = false;
+    uint32_t phred_kind = PT_CONST;     /* PT_* */
     uint8_t const_q = 0;
-    uint32_t cb = 0, npos = 0, qlo = 0, mshift = 0;
-    std::vector<uint32_t> phred_entries;
+    uint32_t cb = 0, npos = 0;
+    std::vector<uint32_t> phred_entries;   /* as specified: quality bytes are raw phreds */
     LenModel rl, is;
     GammaConst gamma{};
     uint32_t max_read_len = 0;          /* upper bound on a read's length    */

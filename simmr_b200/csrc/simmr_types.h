@@ -21,15 +21,15 @@ struct ContigHdr {     /* per contig: token span + what is needed for H      */
     uint8_t  n_id, n_sp, n_ep, n_rc, n_pair, pad_[3];
 };
 
-/* per-position quantised alias tables: entry = thr22<<10 | alias10 */
+/* per-position alias tables for (quality, mutation) */
+enum : uint32_t { PT_CONST = 0,   /* every base has quality const_q, nothing to sample            */
+                  PT_T64 = 1,     /* {thr32, q_self | m_self<<8 | q_alias<<16 | m_alias<<24}       */
+                  PT_T32 = 2 };   /* thr16<<16 | q_alias<<8 | q_self  (profiles without mutation) */
 struct PhredTab {
-    uint32_t constant;     /* 1: every base has quality const_q, no table     */
-    uint32_t const_q;
+    uint32_t kind, const_q;
     uint32_t cb;           /* log2(columns)                                   */
     uint32_t npos;         /* positions; base i uses min(i, npos-1)           */
-    uint32_t qlo;          /* quality of outcome 0                            */
-    uint32_t mshift;       /* 2: outcome = q<<2 | mutation, 0: outcome = q    */
-    const uint32_t *entries;   /* device or host pointer, npos<<cb words      */
+    const uint32_t *entries;   /* device or host pointer                      */
 };
 /* length sampler: constant, alias over bins (entry = thr20<<12 | alias12) or
  * Marsaglia-Tsang gamma */

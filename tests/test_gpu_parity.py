@@ -99,3 +99,62 @@ def test_replay_perfect_and_minimal_short(engine):
         want = po.replay(og, H.oracle_profile(prof), po.Draws(**d))
         assert got == want, first_diff(got, want)
         assert engine.replay_bytes(S.Draws(**d), batch_units=37) == want
+
+
+def test_custom_short_novaseq_native_and_replay(engine):
+    """NovaSeq-style empirical profile (simmrd blob layout): per-position alias tables, bins for RL/IS,
+    no substitutions (custom_short.rs:522-529)."""
+    gs = H.synth_genomes(4, (1, 3), (2500, 9000), seed=31, with_n=True)
+    prof = S.CustomShortErrorProfile(H.novaseq_blob())
+    assert prof.minimum_genome_size() == 648 and not prof.is_long_read()
+    check_native(engine, gs, prof, [1500, 900, 2, 1200], 17)
+    og = po.Genomes.from_set(gs)
+    d = H.make_pe_draws(gs, prof, 300, seed=5)
+    d["read_length"] = np.clip(d["read_length"], 100, 151).astype(np.uint16)
+    bo = np.zeros(301, np.uint64)
+    bo[1:] = np.cumsum(2 * d["read_length"].astype(np.int64))
+    d["base_off"] = bo
+    d["phred_u"] = d["phred_u"] * 8.0          # spans [0, weight_sum) of the un-normalised densities
+    got = engine.replay_bytes(S.Draws(**d))
+    want = po.replay(og, H.oracle_profile(prof), po.Draws(**d))
+    assert got == want, first_diff(got, want)
+
+
+@pytest.mark.parametrize("kind", ["minimal", "perfect", "custom"])
+@pytest.mark.parametrize("compat", [False, True])
+def test_long_reads_native(engine, kind, compat):
+    """simulate.rs:323-406, 464-523 with gamma lengths; compat = start drawn in [0, RL) (simulate.rs:484)."""
+    gs = H.synth_genomes(3, (1, 3), (21000, 90000), seed=41, with_n=True)
+    prof = {"minimal": S.MinimalLongErrorProfile(30, compat_start=compat), "perfect": S.PerfectLongErrorProfile(compat_start=compat),
+            "custom": S.CustomLongErrorProfile(H.ont_blob(), compat_start=compat)}[kind]
+    assert prof.is_long_read() and prof.minimum_genome_size() == 20000
+    data = check_native(engine, gs, prof, [40, 25, 31], 1234)
+    recs = H.parse_fastq(data)
+    assert len(recs) == 96 and all(len(s) == len(q) for _, s, q in recs)
+
+
+def test_long_reads_replay(engine):
+    gs = H.synth_genomes(2, (1, 2), (21000, 60000), seed=43)
+    og = po.Genomes.from_set(gs)
+    for prof in (S.MinimalLongErrorProfile(20), S.PerfectLongErrorProfile()):
+        d = H.make_long_draws(gs, prof, 30, seed=9)
+        engine.load_genomes(gs)
+        engine.set_error_profile(prof)
+        got = engine.replay_bytes(S.Draws(**d))
+        want = po.replay(og, H.oracle_profile(prof), po.Draws(**d))
+        assert got == want, first_diff(got, want)
+
+
+def test_too_small_contig_is_an_error(engine):
+    gs = H.synth_genomes(1, (1, 1), (300, 300), seed=1)
+    engine.load_genomes(gs)
+    engine.set_error_profile(S.PerfectShortErrorProfile(150, 150))
+    with pytest.raises(S.SimmrError) as e:
+        engine.simulate_bytes([10], 1)
+    assert e.value.code == S._native.E_TOO_SMALL
+
+
+def test_medium_scale_minimal_short(engine):
+    """~1.2 M records through several batches, compared byte for byte."""
+    gs = H.synth_genomes(6, (1, 6), (20000, 120000), seed=77)
+    check_native(engine, gs, S.MinimalShortErrorProfile(), [200000] * 6, 2024, batch_units=150001)
