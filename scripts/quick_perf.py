@@ -20,14 +20,17 @@ def main():
     with S.Engine(0) as eng:
         print(eng.device_info())
         t = time.time(); eng.load_genomes(gs); print("load s", time.time() - t)
-        for prof in (S.PerfectShortErrorProfile(), S.MinimalShortErrorProfile()):
+        which = os.environ.get('QP_PROF', 'both')
+        profs = [p for n, p in (('perfect', S.PerfectShortErrorProfile()), ('minimal', S.MinimalShortErrorProfile())) if which in ('both', n)]
+        for prof in profs:
             eng.set_error_profile(prof)
             reads, _ = S.UniformAbundanceProfile().determine_abundances(reads_total, ng)
-            for it in range(3):
+            for it in range(int(os.environ.get('QP_ITERS', '3'))):
                 st = eng.simulate(reads, 42)
             gb = st["bases"] / st["device_ms"] / 1e6
             print(f"{type(prof).__name__}: {st['records']} rec {st['bases']} bases device {st['device_ms']:.2f} ms format {st['format_ms']:.2f} ms "
                   f"-> {gb:.1f} Gbases/s, alg {st['algorithmic_bytes'] / st['device_ms'] / 1e6:.0f} GB/s, fmt-only {st['algorithmic_bytes'] / st['format_ms'] / 1e6:.0f} GB/s launches {st['kernel_launches']}")
+            if os.environ.get('QP_NOSINK'): continue
             t = time.time(); n = [0]
             st = eng.simulate(reads, 42, unit_begin=0, unit_end=min(2_000_000, eng.total_units(reads)), sink=lambda a, f, k: n.__setitem__(0, n[0] + len(a)))
             dt = time.time() - t

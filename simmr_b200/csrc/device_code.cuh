@@ -242,26 +242,45 @@ __device__ __forceinline__ bool window_impure(const RunParams &rp, uint64_t a, u
 /* ---------------------------------------------------------------------- */
 /* headers — fastq.rs:34-57                                                 */
 /* ---------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t dec_digits32(uint32_t v) {
+    return 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
+           (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+}
 __device__ __forceinline__ uint32_t dec_digits(uint64_t v) {
+    if (!(v >> 32)) return dec_digits32(uint32_t(v));
     uint32_t d = 1;
     while (v >= 10) { v /= 10; ++d; }
     return d;
 }
 __device__ __forceinline__ uint32_t header_len(const ContigHdr &ch, uint32_t id, uint64_t sp, uint64_t ep) {
-    return ch.lit_bytes + ch.n_id * dec_digits(id) + ch.n_sp * dec_digits(sp) + ch.n_ep * dec_digits(ep) + ch.n_rc + ch.n_pair;
+    return ch.lit_bytes + ch.n_id * dec_digits32(id) + ch.n_sp * dec_digits(sp) + ch.n_ep * dec_digits(ep) + ch.n_rc + ch.n_pair;
 }
 __device__ __forceinline__ uint32_t put_dec(uint8_t *dst, uint64_t v) {
     const uint32_t d = dec_digits(v);
-    for (uint32_t i = d; i-- > 0;) { dst[i] = uint8_t('0' + v % 10); v /= 10; }
+    uint32_t i = d;
+    while (v >> 32) { dst[--i] = uint8_t('0' + v % 10); v /= 10; }
+    uint32_t w = uint32_t(v);
+    while (i) { const uint32_t q = __umulhi(w, 0xCCCCCCCDu) >> 3; dst[--i] = uint8_t('0' + (w - q * 10u)); w = q; }
     return d;
 }
+/* Instantiates the compiled template of a contig (fastq.rs:34-57).  Literals start on
+ * 4-byte boundaries of the pool so they can be fetched a word at a time. */
 __device__ uint32_t emit_header(uint8_t *dst, const RunParams &rp, const ContigHdr &ch, uint32_t id, uint64_t sp, uint64_t ep, bool rc, int mate) {
     uint32_t n = 0;
     const HdrTok *t = rp.toks + ch.tok_off;
     for (uint32_t i = 0; i < ch.ntok; ++i) {
         const HdrTok k = t[i];
         switch (k.type) {
-        case TOK_LIT: { const uint8_t *s = rp.pool + k.off; for (uint32_t j = 0; j < k.len; ++j) dst[n + j] = __ldg(s + j); n += k.len; break; }
+        case TOK_LIT: {
+            const uint32_t *s = reinterpret_cast<const uint32_t *>(rp.pool + k.off);
+            for (uint32_t j = 0; j < k.len; j += 4) {
+                const uint32_t w = __ldg(s + (j >> 2));
+                dst[n + j] = uint8_t(w);
+                if (j + 1 < k.len) dst[n + j + 1] = uint8_t(w >> 8);
+                if (j + 2 < k.len) dst[n + j + 2] = uint8_t(w >> 16);
+                if (j + 3 < k.len) dst[n + j + 3] = uint8_t(w >> 24);
+            }
+            n += k.len; break; }
         case TOK_READ_ID: n += put_dec(dst + n, id); break;
         case TOK_START: n += put_dec(dst + n, sp); break;
         case TOK_END: n += put_dec(dst + n, ep); break;
@@ -367,40 +386,42 @@ __device__ __forceinline__ void emit_body_generic(const RunParams &rp, const Rep
  * arrive per 4-base group; the line starts at an arbitrary byte address, so two
  * consecutive group words are funnel-shifted into each aligned word. */
 struct LineW {
-    uint32_t D, E;      /* shared-space byte range of the line                       */
-    uint32_t A0;        /* aligned address of composed word 0                        */
+    uint32_t D;         /* shared-space address of the first byte of the line        */
+    int32_t L;          /* bytes in the line                                         */
+    int32_t off0;       /* start of composed word 0 relative to D (-6..0)            */
     uint32_t sh;        /* 8 * (virtual start & 3)                                   */
     uint32_t first, prev;
 };
 __device__ __forceinline__ void lw_init(LineW &w, uint32_t D, uint32_t L, uint32_t lead) {
     const uint32_t V = D - lead;           /* `lead` garbage bytes precede the line (reversed lines) */
-    w.D = D; w.E = D + L; w.A0 = V & ~3u; w.sh = 8u * (V & 3u); w.first = w.prev = 0;
+    w.D = D; w.L = int32_t(L); w.off0 = -int32_t(lead + (V & 3u)); w.sh = 8u * (V & 3u); w.first = w.prev = 0;
 }
-__device__ __forceinline__ void lw_emit(const LineW &w, uint32_t k, uint32_t c) {
-    const uint32_t addr = w.A0 + 4u * k;
-    const uint32_t lo = max(addr, w.D), hi = min(addr + 4u, w.E);
-    if (hi == lo + 4u) sts32(addr, c);
-    else if (hi > lo) for (uint32_t b = lo; b < hi; ++b) sts8(b, c >> (8u * (b - addr)));
+/* composed word k (may be far out of range on either side: nothing is written then) */
+__device__ __forceinline__ void lw_emit(const LineW &w, int32_t k, uint32_t c) {
+    const int32_t p = w.off0 + 4 * k;
+    if (p >= 0 && p + 4 <= w.L) sts32(w.D + uint32_t(p), c);
+    else if (p + 4 > 0 && p < w.L)
+        for (int32_t b = max(p, 0); b < min(p + 4, w.L); ++b) sts8(w.D + uint32_t(b), c >> (8 * (b - p)));
 }
 /* ascending: group g's word holds line bytes [4g, 4g+4) */
 __device__ __forceinline__ void lw_step_asc(LineW &w, uint32_t t, uint32_t g, uint32_t x) {
-    if (t == 0) w.first = x; else lw_emit(w, g, __funnelshift_l(w.prev, x, w.sh));
+    if (t == 0) w.first = x; else lw_emit(w, int32_t(g), __funnelshift_l(w.prev, x, w.sh));
     w.prev = x;
 }
-__device__ __forceinline__ void lw_finish_asc(LineW &w, uint32_t g0, uint32_t sl, uint32_t mask) {
-    uint32_t left = __shfl_up_sync(mask, w.prev, 1, SUB);
+__device__ __forceinline__ void lw_finish_asc(LineW &w, uint32_t g0, uint32_t sl) {
+    uint32_t left = __shfl_up_sync(0xffffffffu, w.prev, 1, SUB);
     if (sl == 0) left = 0;
-    lw_emit(w, g0, __funnelshift_l(left, w.first, w.sh));
+    lw_emit(w, int32_t(g0), __funnelshift_l(left, w.first, w.sh));
 }
 /* descending: group g's word holds line bytes [L-4g-4, L-4g), i.e. composed index NG-1-g */
 __device__ __forceinline__ void lw_step_desc(LineW &w, uint32_t t, uint32_t g, uint32_t NG, uint32_t x) {
-    if (t == 0) w.first = x; else lw_emit(w, NG - g, __funnelshift_l(x, w.prev, w.sh));
+    if (t == 0) w.first = x; else lw_emit(w, int32_t(NG) - int32_t(g), __funnelshift_l(x, w.prev, w.sh));
     w.prev = x;
 }
-__device__ __forceinline__ void lw_finish_desc(LineW &w, uint32_t g0, uint32_t NG, uint32_t sl, uint32_t mask) {
-    uint32_t left = __shfl_up_sync(mask, w.prev, 1, SUB);
+__device__ __forceinline__ void lw_finish_desc(LineW &w, uint32_t g0, uint32_t NG, uint32_t sl) {
+    uint32_t left = __shfl_up_sync(0xffffffffu, w.prev, 1, SUB);
     if (sl == 0) left = 0;
-    lw_emit(w, NG - g0, __funnelshift_l(w.first, left, w.sh));
+    lw_emit(w, int32_t(NG) - int32_t(g0), __funnelshift_l(w.first, left, w.sh));
 }
 
 /* complement of four A/C/G/T bytes: A<->T is ^0x15, C<->G is ^0x04; bit 1 tells which */
@@ -449,14 +470,17 @@ __device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, Phi
     }
 }
 
-/* One record body by a sub-group of SUB lanes: lane `sl` handles the 4-base
- * groups [sl*T, (sl+1)*T).  body_s = shared-space address of the '\n' that ends
- * the header. */
+/* Record bodies by a whole warp: each sub-group of SUB lanes owns one record (`on` =
+ * this sub-group has one), lane `sl` handles the 4-base groups [sl*T, (sl+1)*T) with T
+ * common to the warp so that all 32 lanes stay converged.  body_s = shared-space
+ * address of the '\n' that ends the header. */
 template <int TK>
-__device__ __forceinline__ void emit_body_fast(const RunParams &rp, uint32_t tab_s, uint32_t body_s, uint64_t unit, uint32_t mate,
-                                               uint64_t a, uint32_t L, uint32_t sl, uint32_t mask) {
-    if (sl == 0) { sts8(body_s, '\n'); sts8(body_s + L + 1, '\n'); sts8(body_s + L + 2, '+'); sts8(body_s + L + 3, '\n'); sts8(body_s + 2 * L + 4, '\n'); }
-    const uint32_t NG = (L + 3) >> 2, T = (NG + SUB) / SUB;          /* SUB*T >= NG+1 composed words */
+__device__ __forceinline__ void emit_body_fast(const RunParams &rp, uint32_t tab_s, bool on, uint32_t body_s, uint64_t unit, uint32_t mate,
+                                               uint64_t a, uint32_t L, uint32_t sl) {
+    if (!on) { L = 0; body_s = 0; a = 0; }
+    if (on && sl == 0) { sts8(body_s, '\n'); sts8(body_s + L + 1, '\n'); sts8(body_s + L + 2, '+'); sts8(body_s + L + 3, '\n'); sts8(body_s + 2 * L + 4, '\n'); }
+    const uint32_t NG = (L + 3) >> 2;
+    const uint32_t T = __reduce_max_sync(0xffffffffu, (NG + SUB) / SUB);   /* SUB*T >= NG+1 composed words */
     const bool rc = mate != 0;
     LineW ls, lq;
     lw_init(ls, body_s + 1, L, rc ? ((4u - (L & 3u)) & 3u) : 0u);
@@ -482,8 +506,8 @@ __device__ __forceinline__ void emit_body_fast(const RunParams &rp, uint32_t tab
         if (rc) lw_step_desc(ls, t, g, NG, sw); else lw_step_asc(ls, t, g, sw);
         lw_step_asc(lq, t, g, qw);
     }
-    if (rc) lw_finish_desc(ls, g0, NG, sl, mask); else lw_finish_asc(ls, g0, sl, mask);
-    lw_finish_asc(lq, g0, sl, mask);
+    if (rc) lw_finish_desc(ls, g0, NG, sl); else lw_finish_asc(ls, g0, sl);
+    lw_finish_asc(lq, g0, sl);
 }
 
 /* ---------------------------------------------------------------------- */
@@ -622,7 +646,6 @@ __global__ void __launch_bounds__(FORMAT_THREADS) k_format_tiles(RunParams rp, R
 
     const uint32_t ntiles = (rp.batch_units + rp.upt - 1) / rp.upt;
     const uint32_t lane = threadIdx.x & 31, sl = threadIdx.x & (SUB - 1);
-    const uint32_t submask = ((1u << SUB) - 1u) << (lane & ~(SUB - 1));
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t u0 = tile * rp.upt, nu = min(rp.upt, rp.batch_units - u0);
         /* the previous tile's bulk copy must have finished reading the stage */
@@ -651,20 +674,24 @@ __global__ void __launch_bounds__(FORMAT_THREADS) k_format_tiles(RunParams rp, R
             if (mate < t.g.nrec)
                 emit_header(stage + t.off[mate], rp, rp.chdr[t.g.contig], t.g.id, t.g.sp[mate], t.g.ep[mate], mate != 0, mate);
         }
-        /* bodies: sub-groups of SUB lanes pull records from a shared counter */
+        /* bodies: each warp pulls 32/SUB units at a time from a shared counter; its sub-groups
+         * of SUB lanes take one unit each and run converged, mate 1 of all of them, then mate 2 */
         for (;;) {
-            uint32_t r = 0;
-            if (sl == 0) r = atomicAdd(&next_rec, 1u);
-            r = __shfl_sync(submask, r, 0, SUB);
-            if (r >= nrec) break;
-            const TileUnit &t = tu[r >> 1]; const uint32_t mate = r & 1;
-            if (mate >= t.g.nrec) continue;
-            const uint32_t body = t.off[mate] + t.H[mate];
-            if (!REPLAY && !t.impure[mate])
-                emit_body_fast<TK>(rp, tab_s, stage_s + body, rp.batch_begin + u0 + (r >> 1), mate, t.g.a[mate], t.g.L[mate], sl, submask);
-            else
-                emit_body_generic<REPLAY>(rp, rd, tab, stage + body, rp.batch_begin + u0 + (r >> 1), mate, t.g.a[mate], t.g.L[mate],
-                                          t.slot0 + (mate ? t.g.rl : 0), sl, SUB);
+            uint32_t ul = 0;
+            if (lane == 0) ul = atomicAdd(&next_rec, 32u / SUB);
+            ul = __shfl_sync(0xffffffffu, ul, 0);
+            if (ul >= nu) break;
+            ul += lane / SUB;
+            const TileUnit &t = tu[min(ul, nu - 1)];
+            for (uint32_t mate = 0; mate < 2; ++mate) {
+                const bool have = ul < nu && mate < t.g.nrec;
+                const bool fast = have && !REPLAY && !t.impure[mate];
+                const uint32_t body = t.off[mate] + t.H[mate];
+                emit_body_fast<TK>(rp, tab_s, fast, stage_s + body, rp.batch_begin + u0 + ul, mate, t.g.a[mate], t.g.L[mate], sl);
+                if (have && !fast)
+                    emit_body_generic<REPLAY>(rp, rd, tab, stage + body, rp.batch_begin + u0 + ul, mate, t.g.a[mate], t.g.L[mate],
+                                              t.slot0 + (mate ? t.g.rl : 0), sl, SUB);
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();

@@ -157,6 +157,7 @@ int ensure_headers(simmr_ctx *ctx, const char *fmt) {
     if (rc) return fail(ctx, rc, err);
     CU(ctx->d_chdr.upload(ctx->plan.contigs.data(), ctx->plan.contigs.size(), ctx->compute));
     CU(ctx->d_toks.upload(ctx->plan.toks.data(), ctx->plan.toks.size(), ctx->compute));
+    ctx->plan.pool.resize((ctx->plan.pool.size() + 7) & ~size_t(3), '\0');
     CU(ctx->d_pool.upload(ctx->plan.pool.data(), ctx->plan.pool.size(), ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
     ctx->header_fmt = f; ctx->have_headers = true;

@@ -637,6 +637,7 @@ int compile_headers(const simmr_genome_set &g, const char *fmt, HeaderPlan &plan
             auto lit = [&](const std::string &t) {
                 for (size_t at = 0; at < t.size(); at += 65535) {
                     const size_t len = std::min<size_t>(65535, t.size() - at);
+                    plan.pool.resize((plan.pool.size() + 3) & ~size_t(3), '\0');   /* the kernel fetches literals by words */
                     plan.toks.push_back(HdrTok{uint32_t(plan.pool.size()), uint16_t(len), TOK_LIT, 0});
                     plan.pool.append(t, at, len);
                 }
