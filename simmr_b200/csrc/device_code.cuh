@@ -35,6 +35,7 @@ struct ReplayDev {                 /* device copies of simmr_draws + replay LUTs
     uint32_t r_npos, pl_qmax, kind; float mean_phred, acc20;
 };
 
+struct UnitDesc;
 struct RunParams {
     /* genomes (device resident) */
     const uint8_t *bases; const uint64_t *contig_off, *contig_size; const uint32_t *genome_contig;
@@ -47,16 +48,19 @@ struct RunParams {
     /* profile (phred.entries: device layout, quality bytes already +33) */
     PhredTab phred; LenTab rl, is; GammaConst gamma;
     uint32_t min_size, is_long, flags, mutates;
-    uint32_t key0, key1;           /* Philox key = seed                          */
+    uint32_t rk[20];               /* Philox round keys: seed + r * Weyl constants, r = 0..9 */
     /* per-batch scratch + output */
     uint32_t *sizes; uint64_t *offsets, *block_sums; uint8_t *out;
+    struct UnitDesc *desc;         /* per-unit geometry written by k_unit_sizes, read by the format kernels */
     unsigned long long *counters;  /* [0] clamped [1] algorithmic bytes [2] bases [3] records */
     /* tile geometry of k_format_tiles */
     uint32_t upt, stage_cap;
 };
 
 constexpr int SIZES_THREADS = 256;
-constexpr int FORMAT_THREADS = 256;
+constexpr int FORMAT_THREADS = 128;   /* threads of a tile CTA                          */
+constexpr int FORMAT_MIN_CTAS = 8;    /* occupancy target -> register cap of 64          */
+constexpr int DIRECT_THREADS = 256;
 constexpr int SUB = 8;             /* lanes that share one record in the tile kernel */
 
 /* ---------------------------------------------------------------------- */
@@ -71,18 +75,18 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("l
 /* Philox4x32-10                                                            */
 /* ---------------------------------------------------------------------- */
 struct Philox4 { uint32_t x, y, z, w; };
-__device__ __forceinline__ Philox4 philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+/* round keys come from the kernel parameter block (constant bank): no per-call key schedule */
+__device__ __forceinline__ Philox4 philox(const uint32_t *rk, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint64_t p0 = uint64_t(0xD2511F53u) * c0, p1 = uint64_t(0xCD9E8D57u) * c2;
-        c0 = uint32_t(p1 >> 32) ^ c1 ^ k0; c1 = uint32_t(p1); c2 = uint32_t(p0 >> 32) ^ c3 ^ k1; c3 = uint32_t(p0);
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        c0 = uint32_t(p1 >> 32) ^ c1 ^ rk[2 * r]; c1 = uint32_t(p1); c2 = uint32_t(p0 >> 32) ^ c3 ^ rk[2 * r + 1]; c3 = uint32_t(p0);
     }
     return Philox4{c0, c1, c2, c3};
 }
 /* draw-schedule addressing: counter = (block, stream, unit) */
 __device__ __forceinline__ Philox4 draw(const RunParams &rp, uint64_t unit, uint32_t stream, uint32_t blk) {
-    return philox(rp.key0, rp.key1, blk, stream, uint32_t(unit), uint32_t(unit >> 32));
+    return philox(rp.rk, blk, stream, uint32_t(unit), uint32_t(unit >> 32));
 }
 __device__ __forceinline__ uint64_t pair64(uint32_t lo, uint32_t hi) { return uint64_t(lo) | (uint64_t(hi) << 32); }
 
@@ -143,6 +147,16 @@ struct UnitGeo {
     uint32_t contig, id, nrec, clamped;
     uint32_t rl, pad_;    /* drawn read length (replay slots of mate 2 start rl after mate 1) */
 };
+
+/* what the format kernels need of a unit: 48 bytes written once by k_unit_sizes */
+struct __align__(16) UnitDesc {
+    uint64_t a0, a1;       /* window offsets in `bases`                                     */
+    uint64_t p0, p1;       /* PE: fwd_start, rev_end (simulate.rs:233,241-258); long: start, end */
+    uint32_t contig;
+    uint16_t rl, L0, L1, H0, H1;
+    uint16_t flags;        /* 1: window 0 impure, 2: window 1 impure, 4: two records        */
+};
+static_assert(sizeof(UnitDesc) == 48, "UnitDesc layout");
 
 __device__ __forceinline__ uint32_t genome_of(const RunParams &rp, uint64_t u) {
     uint32_t lo = 0, hi = rp.n_genomes;            /* last g with unit_start[g] <= u */
@@ -429,18 +443,17 @@ __device__ __forceinline__ uint32_t comp4(uint32_t b) {
     const uint32_t t = (b >> 1) & 0x01010101u;
     return b ^ 0x15151515u ^ (t * 0x11u);
 }
-/* substitutions on a word of pure A/C/G/T; mw byte j = 0 or choose()+1 */
+/* substitutions on a word of pure A/C/G/T, branch-free; mw byte j = 0 or choose()+1.
+ * With rank(A,C,G,T) = 0..3 the replacement has rank (m-1) + [m > rank]: the m-th of the
+ * other three bases in alphabetical order (minimal_short.rs:124-131). */
 __device__ __forceinline__ uint32_t mutate4(uint32_t bw, uint32_t mw) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t m = (mw >> (8 * j)) & 0xffu;
-        if (m) {
-            const uint32_t b = (bw >> (8 * j)) & 0xffu, rank = ((b >> 1) ^ (b >> 2)) & 3u, k = m - 1;
-            const uint32_t nb = (0x54474341u >> (8u * (k + (k >= rank)))) & 0xffu;
-            bw = (bw & ~(0xffu << (8 * j))) | (nb << (8 * j));
-        }
-    }
-    return bw;
+    const uint32_t rank = ((bw >> 1) ^ (bw >> 2)) & 0x03030303u;
+    const uint32_t gt = ((mw + (rank ^ 0x03030303u)) >> 2) & 0x01010101u;     /* m > rank, per byte */
+    const uint32_t pick = (mw | 0x04040404u) + gt - 0x01010101u;               /* low 2 bits; garbage where m == 0 */
+    const uint32_t sel = (pick & 0x0003u) | ((pick >> 4) & 0x0030u) | ((pick >> 8) & 0x0300u) | ((pick >> 12) & 0x3000u);
+    const uint32_t nb = __byte_perm(0x54474341u, 0, sel);                      /* "ACGT"[pick] per byte */
+    const uint32_t hit = (((mw + 0x7f7f7f7fu) & 0x80808080u) >> 7) * 0xffu;    /* 0xff where m != 0 */
+    return (bw & ~hit) | (nb & hit);
 }
 
 /* quality characters and mutation codes of bases 4g..4g+3 */
@@ -499,7 +512,7 @@ __device__ __forceinline__ void emit_body_fast(const RunParams &rp, uint32_t tab
             else {
                 uint32_t mw;
                 sample4<TK>(rp, tab_s, draw(rp, unit, 1 + mate, g), g, qw, mw);
-                if (TK == PT_T64 && mw) sw = mutate4(sw, mw);
+                if (TK == PT_T64) sw = mutate4(sw, mw);
             }
             if (rc) sw = __byte_perm(comp4(sw), 0, 0x0123);
         }
@@ -548,7 +561,7 @@ __device__ __forceinline__ uint64_t block_sum_u64(uint64_t v, uint64_t *sh) {
     return r;   /* valid in thread 0 */
 }
 
-/* one thread per unit: FASTQ bytes of the unit, block totals, run statistics */
+/* one thread per unit: geometry -> descriptor, FASTQ bytes of the unit, block totals, run statistics */
 template <bool REPLAY>
 __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, ReplayDev rd) {
     __shared__ uint64_t sh[32];
@@ -557,14 +570,23 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, Repl
     if (i < rp.batch_units) {
         UnitGeo g; unit_geometry<REPLAY>(rp, rd, rp.batch_begin + i, g);
         const ContigHdr ch = rp.chdr[g.contig];
+        uint32_t H[2] = {0, 0};
         for (uint32_t r = 0; r < g.nrec; ++r) {
-            const uint32_t H = header_len(ch, g.id, g.sp[r], g.ep[r]);
-            bytes += H + 2ull * g.L[r] + 5;
-            alg += H + 3ull * g.L[r] + 5;                        /* BASELINE.md §3 */
+            H[r] = header_len(ch, g.id, g.sp[r], g.ep[r]);
+            bytes += H[r] + 2ull * g.L[r] + 5;
+            alg += H[r] + 3ull * g.L[r] + 5;                     /* BASELINE.md §3 */
             bases += g.L[r];
         }
         clamped = g.clamped; recs = g.nrec;
         rp.sizes[i] = uint32_t(bytes);
+        UnitDesc d;
+        d.a0 = g.a[0]; d.a1 = g.a[1];
+        d.p0 = g.sp[0]; d.p1 = g.nrec == 2 ? g.ep[1] : g.ep[0];
+        d.contig = g.contig; d.rl = uint16_t(g.rl); d.L0 = uint16_t(g.L[0]); d.L1 = uint16_t(g.L[1]);
+        d.H0 = uint16_t(H[0]); d.H1 = uint16_t(H[1]);
+        d.flags = uint16_t((REPLAY || window_impure(rp, g.a[0], g.L[0]) ? 1u : 0u) |
+                           (REPLAY || window_impure(rp, g.a[1], g.L[1]) ? 2u : 0u) | (g.nrec == 2 ? 4u : 0u));
+        rp.desc[i] = d;
     }
     const uint64_t tb = block_sum_u64(bytes, sh), ta = block_sum_u64(alg, sh), tn = block_sum_u64(bases, sh),
                    tc = block_sum_u64(clamped, sh), tr = block_sum_u64(recs, sh);
@@ -621,88 +643,99 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_offsets(RunParams rp) {
     if (i < rp.batch_units) rp.offsets[i] = rp.block_sums[blockIdx.x] + before + x - v;
 }
 
-struct TileUnit {      /* geometry of one unit, kept in shared memory for the tile */
-    UnitGeo g;
-    uint32_t off[2], H[2];
-    uint32_t impure[2], pad_[2];
-    uint64_t slot0;
+struct TileUnit {      /* one unit of the current tile, in shared memory */
+    UnitDesc d;
+    uint32_t off[2];   /* stage offsets of its records */
+    uint32_t pad_[2];
 };
+/* header fields of record r of a unit (simulate.rs:287-298, :513-518) */
+__device__ __forceinline__ void record_positions(const UnitDesc &d, uint32_t r, uint64_t &sp, uint64_t &ep) {
+    if (!(d.flags & 4u)) { sp = d.p0; ep = d.p1; }
+    else if (r == 0) { sp = d.p0; ep = d.p0 + d.rl; }
+    else { sp = d.p1 + d.rl; ep = d.p1; }
+}
 
-/* Persistent CTAs; each tile = `upt` consecutive units whose FASTQ bytes are
- * composed in shared memory and leave through one bulk async copy (TMA).
- * TK = table kind the fast path is specialised for (REPLAY always takes the
- * generic per-base path). */
+/* Persistent CTAs; each tile = up to `upt` consecutive units whose FASTQ bytes are
+ * composed in shared memory and leave through one bulk async copy (TMA).  A tile whose
+ * bytes exceed the stage is cut into sub-tiles.  TK = table kind the fast path is
+ * specialised for (REPLAY always takes the generic per-base path). */
 template <bool REPLAY, int TK>
-__global__ void __launch_bounds__(FORMAT_THREADS) k_format_tiles(RunParams rp, ReplayDev rd) {
+__global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tiles(RunParams rp, ReplayDev rd) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint32_t next_rec;
+    __shared__ uint32_t next_unit;
     const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u : 1u);
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
     TileUnit *tu = reinterpret_cast<TileUnit *>(smem + ((tab_words * 4 + 15) & ~15u));
     uint8_t *stage = reinterpret_cast<uint8_t *>(tu + rp.upt);
-    stage += (16 - (reinterpret_cast<uintptr_t>(stage) & 15)) & 15;
     for (uint32_t i = threadIdx.x; i < tab_words; i += FORMAT_THREADS) tab[i] = rp.phred.entries[i];
     const uint32_t tab_s = uint32_t(__cvta_generic_to_shared(tab)), stage_s = uint32_t(__cvta_generic_to_shared(stage));
 
     const uint32_t ntiles = (rp.batch_units + rp.upt - 1) / rp.upt;
     const uint32_t lane = threadIdx.x & 31, sl = threadIdx.x & (SUB - 1);
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t u0 = tile * rp.upt, nu = min(rp.upt, rp.batch_units - u0);
-        /* the previous tile's bulk copy must have finished reading the stage */
-        if (threadIdx.x == 0) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); next_rec = 0; }
-        __syncthreads();
-        const uint64_t tile_base = rp.offsets[u0], tile_end = rp.offsets[u0 + nu];
-        const uint32_t pad = uint32_t(tile_base & 15), total = uint32_t(tile_end - tile_base);
-        if (threadIdx.x < nu) {
-            TileUnit &t = tu[threadIdx.x];
-            const uint64_t u = rp.batch_begin + u0 + threadIdx.x;
-            unit_geometry<REPLAY>(rp, rd, u, t.g);
-            const ContigHdr ch = rp.chdr[t.g.contig];
-            uint32_t off = pad + uint32_t(rp.offsets[u0 + threadIdx.x] - tile_base);
-            for (uint32_t r = 0; r < t.g.nrec; ++r) {
-                t.H[r] = header_len(ch, t.g.id, t.g.sp[r], t.g.ep[r]);
-                t.off[r] = off; off += t.H[r] + 2 * t.g.L[r] + 5;
-                t.impure[r] = REPLAY ? 1u : uint32_t(window_impure(rp, t.g.a[r], t.g.L[r]));
+        const uint32_t t0 = tile * rp.upt, tn = min(rp.upt, rp.batch_units - t0);
+        for (uint32_t s0 = 0; s0 < tn;) {
+            /* sub-tile = longest run of units from s0 that fits the stage */
+            const uint32_t u0 = t0 + s0;
+            const uint64_t tile_base = rp.offsets[u0];
+            const uint32_t pad = uint32_t(tile_base & 15);
+            const bool fits = threadIdx.x < tn - s0 && rp.offsets[u0 + threadIdx.x + 1] - tile_base + pad <= rp.stage_cap;
+            /* the previous bulk copy must have finished reading the stage before it is rewritten */
+            if (threadIdx.x == 0) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); next_unit = 0; }
+            const uint32_t nu = __syncthreads_count(fits);
+            const uint32_t total = uint32_t(rp.offsets[u0 + nu] - tile_base);
+            if (threadIdx.x < nu) {
+                TileUnit &t = tu[threadIdx.x];
+                t.d = rp.desc[u0 + threadIdx.x];
+                t.off[0] = pad + uint32_t(rp.offsets[u0 + threadIdx.x] - tile_base);
+                t.off[1] = t.off[0] + t.d.H0 + 2u * t.d.L0 + 5u;
             }
-            t.slot0 = REPLAY ? rd.base_off[u] : 0;
-        }
-        __syncthreads();
-        const uint32_t nrec = 2 * nu;
-        /* headers: one thread per record */
-        for (uint32_t r = threadIdx.x; r < nrec; r += FORMAT_THREADS) {
-            const TileUnit &t = tu[r >> 1]; const uint32_t mate = r & 1;
-            if (mate < t.g.nrec)
-                emit_header(stage + t.off[mate], rp, rp.chdr[t.g.contig], t.g.id, t.g.sp[mate], t.g.ep[mate], mate != 0, mate);
-        }
-        /* bodies: each warp pulls 32/SUB units at a time from a shared counter; its sub-groups
-         * of SUB lanes take one unit each and run converged, mate 1 of all of them, then mate 2 */
-        for (;;) {
-            uint32_t ul = 0;
-            if (lane == 0) ul = atomicAdd(&next_rec, 32u / SUB);
-            ul = __shfl_sync(0xffffffffu, ul, 0);
-            if (ul >= nu) break;
-            ul += lane / SUB;
-            const TileUnit &t = tu[min(ul, nu - 1)];
-            for (uint32_t mate = 0; mate < 2; ++mate) {
-                const bool have = ul < nu && mate < t.g.nrec;
-                const bool fast = have && !REPLAY && !t.impure[mate];
-                const uint32_t body = t.off[mate] + t.H[mate];
-                emit_body_fast<TK>(rp, tab_s, fast, stage_s + body, rp.batch_begin + u0 + ul, mate, t.g.a[mate], t.g.L[mate], sl);
-                if (have && !fast)
-                    emit_body_generic<REPLAY>(rp, rd, tab, stage + body, rp.batch_begin + u0 + ul, mate, t.g.a[mate], t.g.L[mate],
-                                              t.slot0 + (mate ? t.g.rl : 0), sl, SUB);
+            __syncthreads();
+            const uint32_t nrec = 2 * nu;
+            /* headers: one thread per record */
+            for (uint32_t r = threadIdx.x; r < nrec && !(rp.flags & 0x200u); r += FORMAT_THREADS) {
+                const TileUnit &t = tu[r >> 1]; const uint32_t mate = r & 1;
+                if (mate == 0 || (t.d.flags & 4u)) {
+                    uint64_t sp, ep; record_positions(t.d, mate, sp, ep);
+                    emit_header(stage + t.off[mate], rp, rp.chdr[t.d.contig], rp.read_id_base + uint32_t(rp.batch_begin + u0 + (r >> 1)),
+                                sp, ep, mate != 0, mate);
+                }
             }
+            /* bodies: each warp pulls 32/SUB units at a time from a shared counter; its sub-groups
+             * of SUB lanes take one unit each and run converged, mate 1 of all of them, then mate 2 */
+            for (;;) {
+                uint32_t ul = 0;
+                if (lane == 0) ul = atomicAdd(&next_unit, 32u / SUB);
+                ul = __shfl_sync(0xffffffffu, ul, 0);
+                if (ul >= nu || (rp.flags & 0x400u)) break;
+                ul += lane / SUB;
+                const TileUnit &t = tu[min(ul, nu - 1)];
+                const uint64_t unit = rp.batch_begin + u0 + ul;
+#pragma unroll 1
+                for (uint32_t mate = 0; mate < 2; ++mate) {
+                    const bool have = ul < nu && (mate == 0 || (t.d.flags & 4u));
+                    const bool fast = have && !REPLAY && !(t.d.flags & (1u << mate));
+                    const uint32_t L = mate ? t.d.L1 : t.d.L0, body = t.off[mate] + (mate ? t.d.H1 : t.d.H0);
+                    const uint64_t a = mate ? t.d.a1 : t.d.a0;
+                    emit_body_fast<TK>(rp, tab_s, fast, stage_s + body, unit, mate, a, L, sl);
+                    if (have && !fast)
+                        emit_body_generic<REPLAY>(rp, rd, tab, stage + body, unit, mate, a, L,
+                                                  (REPLAY ? rd.base_off[unit] : 0) + (mate ? t.d.rl : 0), sl, SUB);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            /* stage[pad, pad+total) -> out[tile_base, +total): 16-byte aligned middle by TMA, edges by byte stores */
+            const uint32_t head = min(total, (16 - pad) & 15), mid = (total - head) & ~15u, tail = total - head - mid;
+            if (rp.flags & 0x100u) { for (uint32_t b = threadIdx.x; b < mid; b += FORMAT_THREADS) rp.out[tile_base + head + b] = stage[pad + head + b]; }
+            else if (threadIdx.x == 0 && mid) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rp.out + tile_base + head), "r"(stage_s + pad + head), "r"(mid) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (threadIdx.x >= 32 && threadIdx.x < 32 + head) rp.out[tile_base + (threadIdx.x - 32)] = stage[pad + (threadIdx.x - 32)];
+            if (threadIdx.x >= 64 && threadIdx.x < 64 + tail) rp.out[tile_base + head + mid + (threadIdx.x - 64)] = stage[pad + head + mid + (threadIdx.x - 64)];
+            s0 += nu;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        /* stage[pad, pad+total) -> out[tile_base, tile_end): 16-byte aligned middle by TMA, edges by byte stores */
-        const uint32_t head = min(total, (16 - pad) & 15), mid = (total - head) & ~15u, tail = total - head - mid;
-        if (threadIdx.x == 0 && mid) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rp.out + tile_base + head), "r"(stage_s + pad + head), "r"(mid) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        if (threadIdx.x >= 32 && threadIdx.x < 32 + head) rp.out[tile_base + (threadIdx.x - 32)] = stage[pad + (threadIdx.x - 32)];
-        if (threadIdx.x >= 64 && threadIdx.x < 64 + tail) rp.out[tile_base + head + mid + (threadIdx.x - 64)] = stage[pad + head + mid + (threadIdx.x - 64)];
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -711,28 +744,26 @@ __global__ void __launch_bounds__(FORMAT_THREADS) k_format_tiles(RunParams rp, R
  * reads (records far larger than a tile) and as the fallback when a unit does
  * not fit the shared-memory stage. */
 template <bool REPLAY>
-__global__ void __launch_bounds__(FORMAT_THREADS) k_format_direct(RunParams rp, ReplayDev rd) {
+__global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, ReplayDev rd) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u : 1u);
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
-    __shared__ UnitGeo g;
-    __shared__ uint32_t H[2];
-    for (uint32_t i = threadIdx.x; i < tab_words; i += FORMAT_THREADS) tab[i] = rp.phred.entries[i];
+    for (uint32_t i = threadIdx.x; i < tab_words; i += DIRECT_THREADS) tab[i] = rp.phred.entries[i];
+    __syncthreads();
     for (uint32_t i = blockIdx.x; i < rp.batch_units; i += gridDim.x) {
-        __syncthreads();
         const uint64_t u = rp.batch_begin + i;
-        if (threadIdx.x == 0) {
-            unit_geometry<REPLAY>(rp, rd, u, g);
-            const ContigHdr ch = rp.chdr[g.contig];
-            for (uint32_t r = 0; r < g.nrec; ++r) H[r] = header_len(ch, g.id, g.sp[r], g.ep[r]);
-        }
-        __syncthreads();
+        const UnitDesc d = rp.desc[i];
         uint8_t *dst = rp.out + rp.offsets[i];
         const uint64_t slot0 = REPLAY ? rd.base_off[u] : 0;
-        for (uint32_t r = 0; r < g.nrec; ++r) {
-            if (threadIdx.x == 0) emit_header(dst, rp, rp.chdr[g.contig], g.id, g.sp[r], g.ep[r], r != 0, int(r));
-            emit_body_generic<REPLAY>(rp, rd, tab, dst + H[r], u, r, g.a[r], g.L[r], slot0 + (r ? g.rl : 0), threadIdx.x, FORMAT_THREADS);
-            dst += H[r] + 2 * g.L[r] + 5;
+        const uint32_t nrec = (d.flags & 4u) ? 2 : 1;
+        for (uint32_t r = 0; r < nrec; ++r) {
+            const uint32_t H = r ? d.H1 : d.H0, L = r ? d.L1 : d.L0;
+            if (threadIdx.x == 0) {
+                uint64_t sp, ep; record_positions(d, r, sp, ep);
+                emit_header(dst, rp, rp.chdr[d.contig], rp.read_id_base + uint32_t(u), sp, ep, r != 0, int(r));
+            }
+            emit_body_generic<REPLAY>(rp, rd, tab, dst + H, u, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
+            dst += H + 2 * L + 5;
         }
     }
 }

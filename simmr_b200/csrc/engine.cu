@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
@@ -77,7 +78,7 @@ struct simmr_ctx {
     DevMem d_phred, d_rl_e, d_rl_lo, d_rl_hi, d_is_e, d_is_lo, d_is_hi;
     DevMem d_acc, d_plthr, d_rodds, d_ralias, d_roff, d_rlo, d_rhi;
     /* run scratch */
-    DevMem d_unit_start, d_sizes, d_offsets, d_block_sums, d_counters, d_out[2];
+    DevMem d_unit_start, d_sizes, d_offsets, d_block_sums, d_counters, d_desc, d_out[2];
     PinnedMem h_out[2], h_total;
     DevMem d_draw[13];
     simmr_stats stats{};
@@ -131,21 +132,28 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
     if (tab + 1024 > smem_max) return fail(ctx, SIMMR_E_LIMIT, "quality tables do not fit in shared memory");
     pl.tiles = !m.is_long;
     if (pl.tiles) {
-        /* stage sized for the worst case of every unit in the tile; aim at ~48 KiB */
-        uint32_t upt = uint32_t(std::min<uint64_t>(64, std::max<uint64_t>(1, (48 * 1024) / unit_bytes)));
-        while (upt > 1 && tile_smem(m, upt, uint32_t(upt * unit_bytes + 32)) > smem_max) --upt;
-        const uint32_t cap = uint32_t(upt * unit_bytes + 32);
-        if (tile_smem(m, upt, cap) > smem_max) pl.tiles = false;   /* headers too long for a tile: direct path */
+        /* The stage holds the typical bytes of `upt` units plus a margin; a tile that draws
+         * longer reads than that is cut into sub-tiles by the kernel.  It must hold the
+         * largest possible single unit. */
+        uint32_t upt = 32;
+        if (const char *e = getenv("SIMMR_UPT")) upt = uint32_t(std::max(1, std::min(128, atoi(e))));
+        const uint64_t typical = 2ull * (ctx->plan.hdr_cap + 2ull * m.nominal_read_len + 5);
+        auto cap_for = [&](uint32_t n) { return uint32_t(std::max<uint64_t>(unit_bytes + 32, n * typical * 27 / 25 + 64)); };
+        while (upt > 1 && tile_smem(m, upt, cap_for(upt)) > smem_max) upt /= 2;
+        const uint32_t cap = cap_for(upt);
+        if (tile_smem(m, upt, cap) > smem_max) pl.tiles = false;   /* a single unit does not fit: direct path */
         else { pl.upt = upt; pl.stage_cap = cap; pl.smem = tile_smem(m, upt, cap); }
     }
     if (!pl.tiles) pl.smem = tab;
     int occ = 0;
     FormatKernel k = pl.tiles ? tiles_kernel(replay, m.phred_kind) : direct_kernel(replay);
     CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, FORMAT_THREADS, pl.smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, pl.tiles ? FORMAT_THREADS : DIRECT_THREADS, pl.smem);
     CU(e);
     if (occ < 1) return fail(ctx, SIMMR_E_LIMIT, "format kernel does not fit on an SM");
     pl.grid = occ * ctx->prop.multiProcessorCount;
+    if (const char *e = getenv("SIMMR_GRID")) pl.grid = std::max(1, atoi(e));
+    if (getenv("SIMMR_DEBUG_SYNC")) fprintf(stderr, "[simmr] tiles=%d upt=%u cap=%u smem=%zu occ=%d grid=%d\n", int(pl.tiles), pl.upt, pl.stage_cap, pl.smem, occ, pl.grid);
     return SIMMR_OK;
 }
 
@@ -178,9 +186,11 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.rl = LenTab{m.rl.kind, m.rl.value, m.rl.cb, 0, ctx->d_rl_e.as<uint32_t>(), ctx->d_rl_lo.as<uint32_t>(), ctx->d_rl_hi.as<uint32_t>()};
     rp.is = LenTab{m.is.kind, m.is.value, m.is.cb, 0, ctx->d_is_e.as<uint32_t>(), ctx->d_is_lo.as<uint32_t>(), ctx->d_is_hi.as<uint32_t>()};
     rp.gamma = m.gamma;
-    rp.min_size = m.min_size; rp.is_long = m.is_long; rp.flags = m.flags; rp.mutates = m.mutates;
-    rp.key0 = uint32_t(seed); rp.key1 = uint32_t(seed >> 32);
+    rp.min_size = m.min_size; rp.is_long = m.is_long; rp.flags = m.flags;
+    if (const char *e = getenv("SIMMR_DBG")) rp.flags |= uint32_t(atoi(e)) << 8; rp.mutates = m.mutates;
+    for (uint32_t r = 0; r < 10; ++r) { rp.rk[2 * r] = uint32_t(seed) + r * 0x9E3779B9u; rp.rk[2 * r + 1] = uint32_t(seed >> 32) + r * 0xBB67AE85u; }
     rp.sizes = ctx->d_sizes.as<uint32_t>(); rp.offsets = ctx->d_offsets.as<uint64_t>();
+    rp.desc = ctx->d_desc.as<UnitDesc>();
     rp.block_sums = ctx->d_block_sums.as<uint64_t>(); rp.counters = ctx->d_counters.as<unsigned long long>();
     rp.upt = pl.upt; rp.stage_cap = pl.stage_cap;
 }
@@ -198,7 +208,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     if (batch * pl.max_unit_bytes > (64ull << 30)) batch = std::max<uint64_t>(1, (64ull << 30) / pl.max_unit_bytes);
     const uint64_t out_cap = batch * pl.max_unit_bytes + 64;
     const uint32_t max_blocks = uint32_t((batch + SIZES_THREADS - 1) / SIZES_THREADS);
-    CU(ctx->d_sizes.reserve(batch * 4)); CU(ctx->d_offsets.reserve((batch + 1) * 8)); CU(ctx->d_block_sums.reserve(size_t(max_blocks) * 8));
+    CU(ctx->d_sizes.reserve(batch * 4)); CU(ctx->d_desc.reserve(batch * sizeof(UnitDesc))); CU(ctx->d_offsets.reserve((batch + 1) * 8)); CU(ctx->d_block_sums.reserve(size_t(max_blocks) * 8));
     CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
     const int nbuf = sink ? 2 : 1;
     for (int b = 0; b < nbuf; ++b) CU(ctx->d_out[b].reserve(out_cap));
@@ -229,12 +239,14 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         const uint32_t nblk = (n + SIZES_THREADS - 1) / SIZES_THREADS;
         if (replay) k_unit_sizes<true><<<nblk, SIZES_THREADS, 0, ctx->compute>>>(rp, rd);
         else k_unit_sizes<false><<<nblk, SIZES_THREADS, 0, ctx->compute>>>(rp, rd);
+        if (getenv("SIMMR_DEBUG_SYNC")) { cudaError_t e_ = cudaStreamSynchronize(ctx->compute); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("k_unit_sizes: ") + cudaGetErrorString(e_)); }
         k_scan_blocks<<<1, 1024, 0, ctx->compute>>>(rp, nblk);
         k_unit_offsets<<<nblk, SIZES_THREADS, 0, ctx->compute>>>(rp);
         if (sink) {
             CU(cudaMemcpyAsync(static_cast<uint64_t *>(ctx->h_total.p) + slot, rp.offsets + n, 8, cudaMemcpyDeviceToHost, ctx->compute));
             CU(cudaEventRecord(ev_total[slot], ctx->compute));
         }
+        if (getenv("SIMMR_DEBUG_SYNC")) { cudaError_t e_ = cudaStreamSynchronize(ctx->compute); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("scan kernels: ") + cudaGetErrorString(e_)); }
         CU(cudaEventRecord(ev_f0, ctx->compute));
         if (pl.tiles) {
             const uint32_t ntiles = (n + pl.upt - 1) / pl.upt;
@@ -242,7 +254,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
             tiles_kernel(replay, ctx->model.phred_kind)<<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
         } else {
             const int grid = int(std::min<uint32_t>(n, uint32_t(pl.grid)));
-            direct_kernel(replay)<<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
+            direct_kernel(replay)<<<grid, DIRECT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
         }
         CU(cudaGetLastError());
         CU(cudaEventRecord(ev_f1, ctx->compute));

@@ -357,6 +357,8 @@ int build_profile(const simmr_eprofile_desc *d, ProfileModel &m, std::string &er
     default: err = "unknown error profile kind"; return SIMMR_E_INVALID;
     }
     m.max_read_len = m.is_long ? 65535u : std::min<uint32_t>(m.rl.vmax, 65535u);   /* `as u16` */
+    m.nominal_read_len = m.is_long ? 20000u : (custom ? uint32_t(std::min(65535.0, std::max(1.0, blob.length_mean))) : d->read_length);
+    m.nominal_read_len = std::min(m.nominal_read_len, m.max_read_len);
     if (custom) {
         m.r_off.assign(1, 0);
         for (const BinSet &bs : blob.quality) {

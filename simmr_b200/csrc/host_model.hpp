@@ -48,6 +48,7 @@ struct ProfileModel {
     LenModel rl, is;
     GammaConst gamma{};
     uint32_t max_read_len = 0;          /* upper bound on a read's length    */
+    uint32_t nominal_read_len = 0;      /* typical length (sizes the shared-memory stage) */
     /* replay arithmetic */
     uint32_t replay_kind = RP_CONST;
     float mean_phred_f = 0.f, acc20 = 0.f;
