@@ -629,6 +629,14 @@ inline uint8_t substitute(uint8_t nt, uint32_t k) {
     default: return nt;
     }
 }
+/* native mode: the table's mutation code m in 1..3 picks the substituted base as
+ * rank(nt) ^ m with A,C,G,T = 0..3 — choose()'s index (minimal_short.rs:125) relabelled, still
+ * uniform over the three other bases; replay applies substitute() to the recorded index */
+inline uint8_t substitute_native(uint8_t nt, uint32_t m) {
+    uint32_t rank;
+    switch (nt) { case 'A': rank = 0; break; case 'C': rank = 1; break; case 'G': rank = 2; break; case 'T': rank = 3; break; default: return nt; }
+    return (uint8_t)"ACGT"[rank ^ (m & 3u)];
+}
 inline double u01_open(uint32_t w) { return ((double)w + 0.5) * (1.0 / 4294967296.0); }
 
 /* Marsaglia-Tsang gamma (rand_distr gamma.rs GammaLargeShape), shape and scale
@@ -811,7 +819,7 @@ void native_read(const Profile &p, const Philox &ph, uint64_t u, uint32_t stream
         }
         qual[i] = q;
         uint8_t b = src[i];
-        if (m) { uint8_t nb = substitute(b, m - 1); if (nb != b) st.mutated++; b = nb; }
+        if (m) { uint8_t nb = substitute_native(b, m); if (nb != b) st.mutated++; b = nb; }
         seq[i] = b;
     }
 }

@@ -2,11 +2,12 @@
  *
  * Path (reference file:line -> kernel):
  *   simulate.rs:165-190, 205-262, 353-375, 464-491  geometry      -> unit_geometry()
- *   fastq.rs:34-57 header interpolation, record size             -> k_unit_sizes, emit_header()
+ *   fastq.rs:34-57 header interpolation, record size             -> k_unit_sizes, header_fast(), emit_header()
  *   (no reference equivalent: byte offsets of the FASTQ stream)   -> k_scan_blocks, k_unit_offsets
  *   simulate.rs:261-286 + error_profiles/ *.rs phreds/mutation +
  *   util.rs:15-57 RC / +33 + fastq.rs:61-69 record layout         -> k_format_tiles, k_format_direct
- *   (load-time) which 32-byte blocks hold only A,C,G,T           -> k_purity
+ *   (load-time) 2-bit copy of the contigs + which 32-byte blocks
+ *   hold only A,C,G,T                                            -> k_pack
  *
  * Draw schedule, table formats and the tile layout are specified in DESIGN.md.
  * Compile with -fmad=false: the replay arithmetic (minimal_short.rs:90-100) and
@@ -40,6 +41,7 @@ struct RunParams {
     /* genomes (device resident) */
     const uint8_t *bases; const uint64_t *contig_off, *contig_size; const uint32_t *genome_contig;
     const uint32_t *impure;        /* 1 bit per 32-byte block of `bases`: holds a byte other than A,C,G,T */
+    const uint32_t *packed;        /* 2 bits per base (A,C,G,T = 0..3), 16 bases per word, same indexing as `bases` */
     const ContigHdr *chdr; const HdrTok *toks; const uint8_t *pool;
     uint32_t n_genomes, n_contigs;
     /* unit space */
@@ -55,13 +57,21 @@ struct RunParams {
     unsigned long long *counters;  /* [0] clamped [1] algorithmic bytes [2] bases [3] records */
     /* tile geometry of k_format_tiles */
     uint32_t upt, stage_cap;
+    /* header template shared by every contig (token kinds, fastq.rs:34-57); hdr_ntok == 0: per-contig lists only */
+    uint32_t hdr_ntok;
+    uint64_t hdr_kinds[2];         /* 4 bits per token, token i in bits 4*(i&15) of word i>>4 */
 };
+constexpr uint32_t HDR_MAX_TOK = 32;
 
 constexpr int SIZES_THREADS = 256;
 constexpr int FORMAT_THREADS = 128;   /* threads of a tile CTA                          */
-constexpr int FORMAT_MIN_CTAS = 8;    /* occupancy target -> register cap of 64          */
+constexpr int FORMAT_MIN_CTAS = 4;    /* occupancy target -> register cap of 128         */
 constexpr int DIRECT_THREADS = 256;
-constexpr int SUB = 8;             /* lanes that share one record in the tile kernel */
+constexpr int SUB = 8;                /* lanes that share one record in the tile kernel  */
+constexpr uint32_t PACK_PAD_WORDS = 1024; /* readable words past the end of `packed`     */
+/* shared-memory layout of a tile CTA (byte offsets from the 1024-aligned base) */
+constexpr uint32_t SM_LUT_FWD = 0, SM_LUT_RC = 1024, SM_DEC2 = 2048, SM_TAB = 2304;
+constexpr uint32_t STAGE_FRONT = 16;  /* slack before the tile image (a header's leading newline may land there) */
 
 /* ---------------------------------------------------------------------- */
 /* small PTX helpers                                                        */
@@ -322,6 +332,13 @@ __device__ __forceinline__ uint8_t substitute(uint8_t b, uint32_t k) {
     const uint32_t pick = k + (k >= rank);
     return uint8_t(0x54474341u >> (8 * pick));                    /* "ACGT" */
 }
+/* native mode: m in 1..3 picks the substituted base as rank(b) ^ m (A,C,G,T = 0..3) — a relabelling of
+ * choose()'s index (minimal_short.rs:125) that keeps it uniform over the three other bases */
+__device__ __forceinline__ uint8_t substitute_native(uint8_t b, uint32_t m) {
+    uint32_t rank;
+    switch (b) { case 'A': rank = 0; break; case 'C': rank = 1; break; case 'G': rank = 2; break; case 'T': rank = 3; break; default: return b; }
+    return uint8_t(0x54474341u >> (8 * (rank ^ m)));
+}
 __device__ __forceinline__ uint32_t sat_u8f(float x) { return !(x == x) || x <= 0.f ? 0u : (x >= 255.f ? 255u : uint32_t(x)); }
 
 /* replay: the reference's arithmetic on one recorded draw slot */
@@ -362,15 +379,15 @@ __device__ __forceinline__ void native_base(const RunParams &rp, const uint32_t 
     }
 }
 
-/* Writes one record body (everything after the header) with byte stores; `dst`
- * may be shared or global memory.  Base i of the window gets quality slot i; for
- * mate 2 the (mutated) base is complemented and lands at L-1-i, the quality stays
- * at i (simulate.rs:283-285). */
-template <bool REPLAY>
+/* Writes the sequence and quality lines of one record with byte stores (and, when PUNCT, the
+ * five fixed bytes around them); `dst` = the byte after the header, in shared or global
+ * memory.  Base i of the window gets quality slot i; for mate 2 the (mutated) base is
+ * complemented and lands at L-1-i, the quality stays at i (simulate.rs:283-285). */
+template <bool REPLAY, bool PUNCT>
 __device__ __forceinline__ void emit_body_generic(const RunParams &rp, const ReplayDev &rd, const uint32_t *tab, uint8_t *dst,
                                                   uint64_t unit, uint32_t mate, uint64_t a, uint32_t L, uint64_t slot0, uint32_t thr, uint32_t nthr) {
     uint8_t *seq = dst + 1, *qual = dst + L + 4;
-    if (thr == 0) { dst[0] = '\n'; dst[L + 1] = '\n'; dst[L + 2] = '+'; dst[L + 3] = '\n'; dst[2 * L + 4] = '\n'; }   /* fastq.rs:61-69 */
+    if (PUNCT && thr == 0) { dst[0] = '\n'; dst[L + 1] = '\n'; dst[L + 2] = '+'; dst[L + 3] = '\n'; dst[2 * L + 4] = '\n'; }   /* fastq.rs:61-69 */
     const uint8_t *src = rp.bases + a;
     const bool rc = mate != 0;
     for (uint32_t g = thr; g * 4 < L; g += nthr) {
@@ -386,7 +403,7 @@ __device__ __forceinline__ void emit_body_generic(const RunParams &rp, const Rep
             else if (rp.phred.kind == PT_CONST) { qc = (rp.phred.const_q + 33) & 0xffu; m = 0; }
             else native_base(rp, tab, wv[j], i, qc, m);
             uint8_t b = __ldg(src + i);
-            if (m) b = substitute(b, m - 1);
+            if (m) b = REPLAY ? substitute(b, m - 1) : substitute_native(b, m);
             qual[i] = uint8_t(qc);
             if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;
         }
@@ -394,157 +411,212 @@ __device__ __forceinline__ void emit_body_generic(const RunParams &rp, const Rep
 }
 
 /* ---------------------------------------------------------------------- */
-/* per-base work, fast path: windows of pure A/C/G/T, SWAR on 4 bases/word  */
+/* per-base work, fast path: windows of pure A/C/G/T                        */
 /* ---------------------------------------------------------------------- */
-/* One output line written through aligned 32-bit shared-memory stores.  Words
- * arrive per 4-base group; the line starts at an arbitrary byte address, so two
- * consecutive group words are funnel-shifted into each aligned word. */
-struct LineW {
-    uint32_t D;         /* shared-space address of the first byte of the line        */
-    int32_t L;          /* bytes in the line                                         */
-    int32_t off0;       /* start of composed word 0 relative to D (-6..0)            */
-    uint32_t sh;        /* 8 * (virtual start & 3)                                   */
-    uint32_t first, prev;
-};
-__device__ __forceinline__ void lw_init(LineW &w, uint32_t D, uint32_t L, uint32_t lead) {
-    const uint32_t V = D - lead;           /* `lead` garbage bytes precede the line (reversed lines) */
-    w.D = D; w.L = int32_t(L); w.off0 = -int32_t(lead + (V & 3u)); w.sh = 8u * (V & 3u); w.first = w.prev = 0;
-}
-/* composed word k (may be far out of range on either side: nothing is written then) */
-__device__ __forceinline__ void lw_emit(const LineW &w, int32_t k, uint32_t c) {
-    const int32_t p = w.off0 + 4 * k;
-    if (p >= 0 && p + 4 <= w.L) sts32(w.D + uint32_t(p), c);
-    else if (p + 4 > 0 && p < w.L)
-        for (int32_t b = max(p, 0); b < min(p + 4, w.L); ++b) sts8(w.D + uint32_t(b), c >> (8 * (b - p)));
-}
-/* ascending: group g's word holds line bytes [4g, 4g+4) */
-__device__ __forceinline__ void lw_step_asc(LineW &w, uint32_t t, uint32_t g, uint32_t x) {
-    if (t == 0) w.first = x; else lw_emit(w, int32_t(g), __funnelshift_l(w.prev, x, w.sh));
-    w.prev = x;
-}
-__device__ __forceinline__ void lw_finish_asc(LineW &w, uint32_t g0, uint32_t sl) {
-    uint32_t left = __shfl_up_sync(0xffffffffu, w.prev, 1, SUB);
-    if (sl == 0) left = 0;
-    lw_emit(w, int32_t(g0), __funnelshift_l(left, w.first, w.sh));
-}
-/* descending: group g's word holds line bytes [L-4g-4, L-4g), i.e. composed index NG-1-g */
-__device__ __forceinline__ void lw_step_desc(LineW &w, uint32_t t, uint32_t g, uint32_t NG, uint32_t x) {
-    if (t == 0) w.first = x; else lw_emit(w, int32_t(NG) - int32_t(g), __funnelshift_l(x, w.prev, w.sh));
-    w.prev = x;
-}
-__device__ __forceinline__ void lw_finish_desc(LineW &w, uint32_t g0, uint32_t NG, uint32_t sl) {
-    uint32_t left = __shfl_up_sync(0xffffffffu, w.prev, 1, SUB);
-    if (sl == 0) left = 0;
-    lw_emit(w, int32_t(NG) - int32_t(g0), __funnelshift_l(w.first, left, w.sh));
-}
+/* A record body is "\nSEQ\n+\nQUAL\n".  SUB lanes share one record; lane sl owns the T
+ * consecutive 4-base groups g0 = sl*T .. g0+T-1 (T is common to the warp).  Per group it
+ *   - runs one Philox4x32-10 block (4 words, one per base),
+ *   - turns each word into (quality char, mutation code) through the alias table in
+ *     shared memory,
+ *   - takes the group's 4 bases as one byte of the 2-bit genome copy, XORs the packed
+ *     mutation codes into it and maps the byte to 4 ASCII letters through a 256-entry
+ *     table in shared memory (a second table gives the reverse complement for mate 2),
+ *   - funnel-shifts its word against the previous group's into the 4-byte aligned words
+ *     of the stage and stores them with 32-bit shared-memory stores.
+ * The first and last aligned word of a line also cover up to 3 bytes outside the line;
+ * those always belong to a header or to the fixed "\n", "\n+\n", "\n" bytes, which are
+ * written after a CTA barrier (phase 2 of the tile), so the spill is harmless. */
 
-/* complement of four A/C/G/T bytes: A<->T is ^0x15, C<->G is ^0x04; bit 1 tells which */
-__device__ __forceinline__ uint32_t comp4(uint32_t b) {
-    const uint32_t t = (b >> 1) & 0x01010101u;
-    return b ^ 0x15151515u ^ (t * 0x11u);
-}
-/* substitutions on a word of pure A/C/G/T, branch-free; mw byte j = 0 or choose()+1.
- * With rank(A,C,G,T) = 0..3 the replacement has rank (m-1) + [m > rank]: the m-th of the
- * other three bases in alphabetical order (minimal_short.rs:124-131). */
-__device__ __forceinline__ uint32_t mutate4(uint32_t bw, uint32_t mw) {
-    const uint32_t rank = ((bw >> 1) ^ (bw >> 2)) & 0x03030303u;
-    const uint32_t gt = ((mw + (rank ^ 0x03030303u)) >> 2) & 0x01010101u;     /* m > rank, per byte */
-    const uint32_t pick = (mw | 0x04040404u) + gt - 0x01010101u;               /* low 2 bits; garbage where m == 0 */
-    const uint32_t sel = (pick & 0x0003u) | ((pick >> 4) & 0x0030u) | ((pick >> 8) & 0x0300u) | ((pick >> 12) & 0x3000u);
-    const uint32_t nb = __byte_perm(0x54474341u, 0, sel);                      /* "ACGT"[pick] per byte */
-    const uint32_t hit = (((mw + 0x7f7f7f7fu) & 0x80808080u) >> 7) * 0xffu;    /* 0xff where m != 0 */
-    return (bw & ~hit) | (nb & hit);
-}
+__device__ __forceinline__ uint32_t lds32m(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint32_t mulhi_lo(uint32_t a, uint32_t b, uint32_t &lo) { const uint64_t p = uint64_t(a) * b; lo = uint32_t(p); return uint32_t(p >> 32); }
 
-/* quality characters and mutation codes of bases 4g..4g+3 */
+/* quality characters (+33 applied) and mutation codes of bases 4g..4g+3 from one Philox block */
 template <int TK>
-__device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, Philox4 w, uint32_t g, uint32_t &qw, uint32_t &mw) {
-    const uint32_t cb = rp.phred.cb;
+__device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, const Philox4 &w, uint32_t g, uint32_t &qw, uint32_t &mw) {
+    const uint32_t mult = 1u << rp.phred.cb;       /* r * 2^cb: high word = column, low word = threshold draw */
     const uint32_t r[4] = {w.x, w.y, w.z, w.w};
     if (TK == PT_T64) {
-        uint32_t p[4];
+        uint2 e[4]; uint32_t x[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint2 e = lds64(tab_s + ((r[j] >> (32 - cb)) << 3));
-            p[j] = (r[j] << cb) < e.x ? e.y : e.y >> 16;
-        }
-        const uint32_t p01 = __byte_perm(p[0], p[1], 0x5410), p23 = __byte_perm(p[2], p[3], 0x5410);
-        qw = __byte_perm(p01, p23, 0x6420); mw = __byte_perm(p01, p23, 0x7531);
+        for (int j = 0; j < 4; ++j) { const uint32_t col = mulhi_lo(r[j], mult, x[j]); e[j] = lds64(tab_s + (col << 3)); }
+        /* byte selectors: self = payload bytes 0 (quality) and 1 (mutation), alias = bytes 2 and 3 */
+        const uint32_t s01 = (x[0] < e[0].x ? 0x5140u : 0x5342u) + (x[1] < e[1].x ? 0u : 0x2020u);
+        const uint32_t s23 = (x[2] < e[2].x ? 0x5140u : 0x5342u) + (x[3] < e[3].x ? 0u : 0x2020u);
+        const uint32_t a = __byte_perm(e[0].y, e[1].y, s01), b = __byte_perm(e[2].y, e[3].y, s23);   /* q0 q1 m0 m1 | q2 q3 m2 m3 */
+        qw = __byte_perm(a, b, 0x5410); mw = __byte_perm(a, b, 0x7632);
     } else {
-        uint32_t v[4];
-        const uint32_t last = rp.phred.npos - 1;
+        const uint32_t last = rp.phred.npos - 1, cb = rp.phred.cb;
+        uint32_t e[4], x[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t pos = min(4 * g + j, last);
-            const uint32_t e = lds32(tab_s + ((((pos << cb) + (r[j] >> (32 - cb)))) << 2));
-            v[j] = ((r[j] << cb) >> 16) < (e >> 16) ? e : e >> 8;
+            const uint32_t col = mulhi_lo(r[j], mult, x[j]), pos = min(4 * g + j, last);      /* custom_short.rs:339-345 */
+            e[j] = lds32(tab_s + (((pos << cb) + col) << 2));
         }
-        qw = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410); mw = 0;
+        /* entry = thr16<<16 | q_alias<<8 | q_self; keep self when (x >> 16) < thr16 */
+        const uint32_t s01 = (x[0] < (e[0] & 0xffff0000u) ? 0x40u : 0x41u) + (x[1] < (e[1] & 0xffff0000u) ? 0u : 0x10u);
+        const uint32_t s23 = (x[2] < (e[2] & 0xffff0000u) ? 0x40u : 0x41u) + (x[3] < (e[3] & 0xffff0000u) ? 0u : 0x10u);
+        qw = __byte_perm(__byte_perm(e[0], e[1], s01), __byte_perm(e[2], e[3], s23), 0x5410); mw = 0;
     }
 }
 
-/* Record bodies by a whole warp: each sub-group of SUB lanes owns one record (`on` =
- * this sub-group has one), lane `sl` handles the 4-base groups [sl*T, (sl+1)*T) with T
- * common to the warp so that all 32 lanes stay converged.  body_s = shared-space
- * address of the '\n' that ends the header. */
-template <int TK>
-__device__ __forceinline__ void emit_body_fast(const RunParams &rp, uint32_t tab_s, bool on, uint32_t body_s, uint64_t unit, uint32_t mate,
-                                               uint64_t a, uint32_t L, uint32_t sl) {
-    if (!on) { L = 0; body_s = 0; a = 0; }
-    if (on && sl == 0) { sts8(body_s, '\n'); sts8(body_s + L + 1, '\n'); sts8(body_s + L + 2, '+'); sts8(body_s + L + 3, '\n'); sts8(body_s + 2 * L + 4, '\n'); }
-    const uint32_t NG = (L + 3) >> 2;
-    const uint32_t T = __reduce_max_sync(0xffffffffu, (NG + SUB) / SUB);   /* SUB*T >= NG+1 composed words */
-    const bool rc = mate != 0;
-    LineW ls, lq;
-    lw_init(ls, body_s + 1, L, rc ? ((4u - (L & 3u)) & 3u) : 0u);
-    lw_init(lq, body_s + L + 4, L, 0);
-    const uint32_t al = uint32_t(a & 3u);                               /* rp.bases is 256-byte aligned */
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(rp.bases + (a - al));
+/* Sequence and quality lines of one record by the SUB lanes of a sub-group, all 32 lanes of
+ * the warp converged (lanes whose sub-group has no fast record run with on = false and store
+ * nothing).  RC: mate 2 — bases complemented and written back to front (util.rs:31-37); the
+ * quality line is never reversed (simulate.rs:283-285).  body_s = shared-space address of the
+ * '\n' that ends the header; lut_s = ASCII table for this strand. */
+template <int TK, bool RC>
+__device__ __forceinline__ void body_fast(const RunParams &rp, uint32_t tab_s, uint32_t lut_s, bool on, uint32_t body_s,
+                                          uint32_t ulo, uint32_t uhi, uint32_t stream, uint64_t a, uint32_t L, uint32_t sl, uint32_t T) {
+    if (!on) { L = 0; a = 0; body_s = 0; }
     const uint32_t g0 = sl * T;
+    /* aligned words of the two lines: slot k of the sequence line sits at ps + 4k (ps - 4k when RC), of the quality line at pq + 4k */
+    const uint32_t Ds = body_s + 1, Dq = body_s + L + 4;
+    uint32_t sh_s, kw_s, ps;
+    if (!RC) { const uint32_t o = Ds & 3u; sh_s = 8u * o; kw_s = (L + o + 3u) >> 2; ps = (Ds - o) + 4u * g0; }
+    else { const uint32_t E = Ds + L, c = ((E - 1u) & 3u) + 1u; sh_s = 8u * c; kw_s = ((L + 3u - c) >> 2) + 1u; ps = (E - c) - 4u * g0; }
+    const uint32_t oq = Dq & 3u, sh_q = 8u * oq;
+    uint32_t kw_q = (L + oq + 3u) >> 2, pq = (Dq - oq) + 4u * g0;
+    if (!on) kw_s = kw_q = 0;
+    const uint32_t ps0 = ps, pq0 = pq;
+    /* 16 bases per word of the 2-bit copy; this lane's run starts at base a + 4*g0 */
+    const uint64_t b0 = a + 4ull * g0;
+    const uint32_t *pw = rp.packed + (b0 >> 4);
+    const uint32_t s2 = 2u * (uint32_t(b0) & 15u);
+    uint32_t w0 = __ldg(pw), w1 = __ldg(pw + 1);
     const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u;
-    for (uint32_t t = 0; t < T; ++t) {
-        const uint32_t g = g0 + t;
-        uint32_t sw = 0, qw = 0;
-        if (g < NG) {
-            const uint32_t w0 = __ldg(src + g), w1 = __ldg(src + g + 1);
-            sw = __funnelshift_r(w0, w1, 8u * al);
+    uint32_t first_s = 0, first_q = 0, prev_s = 0, prev_q = 0;
+    for (uint32_t tb = 0; tb < T; tb += 4) {
+        const uint32_t X = __funnelshift_r(w0, w1, s2);
+        w0 = w1; w1 = __ldg(pw + 2 + (tb >> 2));
+#pragma unroll
+        for (uint32_t tt = 0; tt < 4; ++tt) {
+            const uint32_t t = tb + tt, g = g0 + t;
+            if (t >= T) break;
+            uint32_t qw, mw = 0;
             if (TK == PT_CONST) qw = qconst;
+            else sample4<TK>(rp, tab_s, philox(rp.rk, g, stream, ulo, uhi), g, qw, mw);
+            /* byte tt of X = the group's four 2-bit codes; XOR with the packed mutation codes, then ASCII by table */
+            uint32_t at = (tt == 0 ? X << 2 : X >> (8 * tt - 2)) & 0x3fcu;
+            if (TK == PT_T64) at ^= ((mw * 0x01041040u) >> 22) & 0x3fcu;
+            const uint32_t sw = lds32(lut_s + at);
+            if (t == 0) { first_s = sw; first_q = qw; }
             else {
-                uint32_t mw;
-                sample4<TK>(rp, tab_s, draw(rp, unit, 1 + mate, g), g, qw, mw);
-                if (TK == PT_T64) sw = mutate4(sw, mw);
+                const uint32_t as = RC ? __funnelshift_lc(sw, prev_s, sh_s) : __funnelshift_l(prev_s, sw, sh_s);
+                if (g < kw_s) sts32(ps, as);
+                if (TK != PT_CONST) { const uint32_t aq = __funnelshift_l(prev_q, qw, sh_q); if (g < kw_q) sts32(pq, aq); }
+                else if (g < kw_q) sts32(pq, qconst);
             }
-            if (rc) sw = __byte_perm(comp4(sw), 0, 0x0123);
+            prev_s = sw; prev_q = qw;
+            ps += RC ? uint32_t(-4) : 4u; pq += 4u;
         }
-        if (rc) lw_step_desc(ls, t, g, NG, sw); else lw_step_asc(ls, t, g, sw);
-        lw_step_asc(lq, t, g, qw);
     }
-    if (rc) lw_finish_desc(ls, g0, NG, sl); else lw_finish_asc(ls, g0, sl);
-    lw_finish_asc(lq, g0, sl);
+    /* slot g0 needs the last word of the lane to the left (lane 0: bytes before the line, repaired in phase 2) */
+    const uint32_t left_s = __shfl_up_sync(0xffffffffu, prev_s, 1, SUB), left_q = __shfl_up_sync(0xffffffffu, prev_q, 1, SUB);
+    if (g0 < kw_s) sts32(ps0, RC ? __funnelshift_lc(first_s, left_s, sh_s) : __funnelshift_l(left_s, first_s, sh_s));
+    if (g0 < kw_q) sts32(pq0, TK == PT_CONST ? qconst : __funnelshift_l(left_q, first_q, sh_q));
+}
+
+/* ---------------------------------------------------------------------- */
+/* headers, fast path: one thread per record, aligned word stores           */
+/* ---------------------------------------------------------------------- */
+/* Byte stream writer into shared memory.  `carry` holds the `fill` (0..3) bytes not yet
+ * stored, top-aligned; every append funnel-shifts them in front of the new bytes. */
+struct ByteStream { uint32_t addr, carry, fill; };
+__device__ __forceinline__ void bs_open(ByteStream &b, uint32_t at) {        /* first byte goes to shared address `at` */
+    b.addr = at & ~3u; b.fill = at & 3u;
+    b.carry = b.fill ? lds32m(b.addr) << (32u - 8u * b.fill) : 0u;           /* keep the bytes already in that word */
+}
+__device__ __forceinline__ void bs_word(ByteStream &b, uint32_t v) {         /* 4 bytes */
+    sts32(b.addr, __funnelshift_l(b.carry, v, 8u * b.fill)); b.addr += 4u; b.carry = v;
+}
+__device__ __forceinline__ void bs_put(ByteStream &b, uint32_t v, uint32_t n) {   /* low n (1..4) bytes of v */
+    const uint32_t out = __funnelshift_l(b.carry, v, 8u * b.fill), nf = b.fill + n;
+    if (nf >= 4u) { sts32(b.addr, out); b.addr += 4u; }
+    b.carry = __funnelshift_l(b.carry, v, 32u - 8u * n); b.fill = nf & 3u;
+}
+__device__ __forceinline__ void bs_close(ByteStream &b) {                     /* the rest of the last word keeps its bytes */
+    if (b.fill) { const uint32_t keep = 0xffffffffu << (8u * b.fill); sts32(b.addr, (lds32m(b.addr) & keep) | (b.carry >> (32u - 8u * b.fill))); }
+}
+/* four decimal digits of c < 10000 as ASCII, most significant in the low byte */
+__device__ __forceinline__ uint32_t four_digits(uint32_t dec2_s, uint32_t c) {
+    const uint32_t hi = (c * 5243u) >> 19, lo = c - hi * 100u;              /* c / 100 for c < 43699 */
+    return lds16(dec2_s + 2u * hi) | (lds16(dec2_s + 2u * lo) << 16);
+}
+__device__ __forceinline__ void bs_decimal(ByteStream &b, uint32_t dec2_s, uint32_t v) {
+    const uint32_t d = dec_digits32(v);
+    const uint32_t top = __umulhi(v, 0xABCC7712u) >> 26;                     /* v / 10^8 */
+    const uint32_t r8 = v - top * 100000000u, m4 = __umulhi(r8, 0xD1B71759u) >> 13, l4 = r8 - m4 * 10000u;   /* r8 / 10^4 */
+    const uint32_t r2 = four_digits(dec2_s, l4);
+    if (d <= 4) { bs_put(b, r2 >> (8u * (4u - d)), d); return; }
+    const uint32_t r1 = four_digits(dec2_s, m4);
+    if (d <= 8) { const uint32_t s = 8u * (8u - d); bs_word(b, __funnelshift_r(r1, r2, s)); if (d > 4) bs_put(b, r2 >> s, d - 4u); return; }
+    const uint32_t r0 = lds16(dec2_s + 2u * top) << 16, s = 8u * (12u - d);  /* 12 right-aligned characters r0 r1 r2 */
+    bs_word(b, __funnelshift_r(r0, r1, s));
+    bs_word(b, __funnelshift_r(r1, r2, s));
+    bs_put(b, r2 >> s, d - 8u);
+}
+
+/* Header of one record + the newline before it (the previous record's last byte) + the
+ * newline after it, for templates whose token kinds are the same for every contig.
+ * rec_s = shared-space address of the record's first byte. */
+__device__ __forceinline__ void header_fast(const RunParams &rp, uint32_t dec2_s, uint32_t rec_s, const ContigHdr &ch,
+                                            uint32_t id, uint32_t sp, uint32_t ep, bool rc, uint32_t mate) {
+    ByteStream b; bs_open(b, rec_s - 1u);
+    bs_put(b, '\n', 1);
+    const HdrTok *tk = rp.toks + ch.tok_off;
+    for (uint32_t i = 0; i < rp.hdr_ntok; ++i) {
+        switch (uint32_t(rp.hdr_kinds[i >> 4] >> (4 * (i & 15))) & 15u) {
+        case TOK_LIT: {
+            const uint2 k = __ldg(reinterpret_cast<const uint2 *>(tk + i));       /* {off, len | type << 16} */
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(rp.pool + k.x);
+            const uint32_t len = k.y & 0xffffu, nw = len >> 2;
+            for (uint32_t j = 0; j < nw; ++j) bs_word(b, __ldg(src + j));
+            if (len & 3u) bs_put(b, __ldg(src + nw), len & 3u);
+            break; }
+        case TOK_READ_ID: bs_decimal(b, dec2_s, id); break;
+        case TOK_START: bs_decimal(b, dec2_s, sp); break;
+        case TOK_END: bs_decimal(b, dec2_s, ep); break;
+        case TOK_RC: bs_put(b, rc ? 't' : 'f', 1); break;
+        default: bs_put(b, mate ? '2' : '1', 1); break;                           /* fastq.rs:57, :106 */
+        }
+    }
+    bs_put(b, '\n', 1);
+    bs_close(b);
 }
 
 /* ---------------------------------------------------------------------- */
 /* kernels                                                                  */
 /* ---------------------------------------------------------------------- */
-/* load time: bit per 32-byte block = block holds a byte that is not A,C,G,T */
-__global__ void k_purity(const uint8_t *bases, uint64_t nbytes, uint32_t *impure, uint64_t nwords) {
-    const uint64_t w = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if (w >= nwords) return;
-    uint32_t bits = 0;
-    for (uint32_t b = 0; b < 32; ++b) {
-        const uint64_t off = (w * 32 + b) * 32;
-        bool bad = false;
-        for (uint32_t k = 0; k < 32 && off + k < nbytes; k += 4) {
-            const uint32_t v = *reinterpret_cast<const uint32_t *>(bases + off + k);   /* tail is padded with 'N' */
+/* load time, one thread per 32-byte block of `bases`: two words of the 2-bit copy and, by
+ * ballot, one bit = the block holds a byte that is not A,C,G,T */
+__global__ void __launch_bounds__(256) k_pack(const uint8_t *bases, uint64_t nbytes, uint32_t *packed, uint32_t *impure, uint64_t nblocks, uint64_t nimpure) {
+    const uint64_t blk = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;      /* grid covers a multiple of 32 blocks */
+    bool bad = false;
+    if (blk < nblocks) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(bases + blk * 32);   /* the tail is padded with 'N' */
+        uint32_t out[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t c = (v >> (8 * j)) & 0xffu;
-                if (off + k + j < nbytes) bad |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+        for (int h = 0; h < 2; ++h) {
+            const uint4 v = src[h];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t code = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t c = (w[k] >> (8 * j)) & 0xffu;
+                    const uint32_t r = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+                    if (blk * 32 + h * 16 + k * 4 + j < nbytes) bad |= r == 4u;
+                    code |= (r & 3u) << (2 * (4 * k + j));
+                }
             }
+            out[h] = code;
         }
-        bits |= uint32_t(bad) << b;
+        packed[2 * blk] = out[0]; packed[2 * blk + 1] = out[1];
     }
-    impure[w] = bits;
+    const uint32_t bits = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && (blk >> 5) < nimpure) impure[blk >> 5] = bits;
 }
 
 __device__ __forceinline__ uint64_t block_sum_u64(uint64_t v, uint64_t *sh) {
@@ -571,11 +643,13 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, Repl
         UnitGeo g; unit_geometry<REPLAY>(rp, rd, rp.batch_begin + i, g);
         const ContigHdr ch = rp.chdr[g.contig];
         uint32_t H[2] = {0, 0};
+        uint64_t big = 0;
         for (uint32_t r = 0; r < g.nrec; ++r) {
             H[r] = header_len(ch, g.id, g.sp[r], g.ep[r]);
             bytes += H[r] + 2ull * g.L[r] + 5;
             alg += H[r] + 3ull * g.L[r] + 5;                     /* BASELINE.md §3 */
             bases += g.L[r];
+            big |= g.sp[r] | g.ep[r];
         }
         clamped = g.clamped; recs = g.nrec;
         rp.sizes[i] = uint32_t(bytes);
@@ -585,7 +659,8 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, Repl
         d.contig = g.contig; d.rl = uint16_t(g.rl); d.L0 = uint16_t(g.L[0]); d.L1 = uint16_t(g.L[1]);
         d.H0 = uint16_t(H[0]); d.H1 = uint16_t(H[1]);
         d.flags = uint16_t((REPLAY || window_impure(rp, g.a[0], g.L[0]) ? 1u : 0u) |
-                           (REPLAY || window_impure(rp, g.a[1], g.L[1]) ? 2u : 0u) | (g.nrec == 2 ? 4u : 0u));
+                           (REPLAY || window_impure(rp, g.a[1], g.L[1]) ? 2u : 0u) | (g.nrec == 2 ? 4u : 0u) |
+                           ((big >> 32) ? 8u : 0u));             /* 8: a position needs more than 32 bits */
         rp.desc[i] = d;
     }
     const uint64_t tb = block_sum_u64(bytes, sh), ta = block_sum_u64(alg, sh), tn = block_sum_u64(bases, sh),
@@ -655,23 +730,37 @@ __device__ __forceinline__ void record_positions(const UnitDesc &d, uint32_t r, 
     else { sp = d.p1 + d.rl; ep = d.p1; }
 }
 
-/* Persistent CTAs; each tile = up to `upt` consecutive units whose FASTQ bytes are
- * composed in shared memory and leave through one bulk async copy (TMA).  A tile whose
- * bytes exceed the stage is cut into sub-tiles.  TK = table kind the fast path is
- * specialised for (REPLAY always takes the generic per-base path). */
+/* Persistent CTAs; each tile = up to `upt` consecutive units whose FASTQ bytes are composed
+ * in shared memory and leave through one bulk async copy (TMA).  A tile whose bytes exceed
+ * the stage is cut into sub-tiles.  Phase 1: sequence and quality lines (body_fast, or byte
+ * stores for windows holding anything but A,C,G,T and for replay).  Phase 2, after a CTA
+ * barrier: headers and the fixed newline / '+' bytes, one thread per record.  TK = table kind
+ * the fast path is specialised for. */
 template <bool REPLAY, int TK>
 __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tiles(RunParams rp, ReplayDev rd) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint32_t next_unit;
+    extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u : 1u);
-    uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
-    TileUnit *tu = reinterpret_cast<TileUnit *>(smem + ((tab_words * 4 + 15) & ~15u));
-    uint8_t *stage = reinterpret_cast<uint8_t *>(tu + rp.upt);
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem + SM_TAB);
+    TileUnit *tu = reinterpret_cast<TileUnit *>(smem + SM_TAB + ((tab_words * 4 + 15) & ~15u));
+    uint8_t *stage = reinterpret_cast<uint8_t *>(tu + rp.upt) + STAGE_FRONT;
+    const uint32_t base_s = uint32_t(__cvta_generic_to_shared(smem));
+    const uint32_t tab_s = base_s + SM_TAB, dec2_s = base_s + SM_DEC2, stage_s = uint32_t(__cvta_generic_to_shared(stage));
     for (uint32_t i = threadIdx.x; i < tab_words; i += FORMAT_THREADS) tab[i] = rp.phred.entries[i];
-    const uint32_t tab_s = uint32_t(__cvta_generic_to_shared(tab)), stage_s = uint32_t(__cvta_generic_to_shared(stage));
+    for (uint32_t b = threadIdx.x; b < 256; b += FORMAT_THREADS) {          /* 4 bases per byte -> ASCII, both strands */
+        uint32_t f = 0, r = 0;
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t c = (b >> (2 * j)) & 3u;
+            f |= ((0x54474341u >> (8 * c)) & 0xffu) << (8 * j);              /* "ACGT"[c] at byte j */
+            r |= ((0x41434754u >> (8 * c)) & 0xffu) << (8 * (3 - j));        /* "TGCA"[c] at byte 3-j (util.rs:15-37) */
+        }
+        reinterpret_cast<uint32_t *>(smem + SM_LUT_FWD)[b] = f;
+        reinterpret_cast<uint32_t *>(smem + SM_LUT_RC)[b] = r;
+        if (b < 100) reinterpret_cast<uint16_t *>(smem + SM_DEC2)[b] = uint16_t(('0' + b / 10) | (('0' + b % 10) << 8));
+    }
 
     const uint32_t ntiles = (rp.batch_units + rp.upt - 1) / rp.upt;
-    const uint32_t lane = threadIdx.x & 31, sl = threadIdx.x & (SUB - 1);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sl = lane & (SUB - 1), sg = lane / SUB;
+    constexpr uint32_t UPW = 32 / SUB, NWARPS = FORMAT_THREADS / 32;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t t0 = tile * rp.upt, tn = min(rp.upt, rp.batch_units - t0);
         for (uint32_t s0 = 0; s0 < tn;) {
@@ -681,54 +770,67 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tile
             const uint32_t pad = uint32_t(tile_base & 15);
             const bool fits = threadIdx.x < tn - s0 && rp.offsets[u0 + threadIdx.x + 1] - tile_base + pad <= rp.stage_cap;
             /* the previous bulk copy must have finished reading the stage before it is rewritten */
-            if (threadIdx.x == 0) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); next_unit = 0; }
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             const uint32_t nu = __syncthreads_count(fits);
             const uint32_t total = uint32_t(rp.offsets[u0 + nu] - tile_base);
+            bool odd = false;                 /* this unit rules out the word-store paths for the sub-tile */
             if (threadIdx.x < nu) {
                 TileUnit &t = tu[threadIdx.x];
                 t.d = rp.desc[u0 + threadIdx.x];
                 t.off[0] = pad + uint32_t(rp.offsets[u0 + threadIdx.x] - tile_base);
                 t.off[1] = t.off[0] + t.d.H0 + 2u * t.d.L0 + 5u;
+                const bool two = t.d.flags & 4u;
+                odd = (t.d.flags & 8u) || t.d.H0 < 2u || t.d.L0 < 4u || (two && (t.d.H1 < 2u || t.d.L1 < 4u));
             }
-            __syncthreads();
-            const uint32_t nrec = 2 * nu;
-            /* headers: one thread per record */
-            for (uint32_t r = threadIdx.x; r < nrec && !(rp.flags & 0x200u); r += FORMAT_THREADS) {
-                const TileUnit &t = tu[r >> 1]; const uint32_t mate = r & 1;
-                if (mate == 0 || (t.d.flags & 4u)) {
-                    uint64_t sp, ep; record_positions(t.d, mate, sp, ep);
-                    emit_header(stage + t.off[mate], rp, rp.chdr[t.d.contig], rp.read_id_base + uint32_t(rp.batch_begin + u0 + (r >> 1)),
-                                sp, ep, mate != 0, mate);
-                }
-            }
-            /* bodies: each warp pulls 32/SUB units at a time from a shared counter; its sub-groups
-             * of SUB lanes take one unit each and run converged, mate 1 of all of them, then mate 2 */
-            for (;;) {
-                uint32_t ul = 0;
-                if (lane == 0) ul = atomicAdd(&next_unit, 32u / SUB);
-                ul = __shfl_sync(0xffffffffu, ul, 0);
-                if (ul >= nu || (rp.flags & 0x400u)) break;
-                ul += lane / SUB;
+            const bool words_ok = !__syncthreads_or(odd) && !REPLAY;
+            const bool hdr_fast = words_ok && rp.hdr_ntok != 0;
+
+            /* ---- phase 1: sequence and quality lines ---- */
+            for (uint32_t ul0 = warp * UPW; ul0 < nu; ul0 += NWARPS * UPW) {
+                const uint32_t ul = ul0 + sg;
                 const TileUnit &t = tu[min(ul, nu - 1)];
                 const uint64_t unit = rp.batch_begin + u0 + ul;
-#pragma unroll 1
+                const uint32_t ulo = uint32_t(unit), uhi = uint32_t(unit >> 32);
+#pragma unroll
                 for (uint32_t mate = 0; mate < 2; ++mate) {
                     const bool have = ul < nu && (mate == 0 || (t.d.flags & 4u));
-                    const bool fast = have && !REPLAY && !(t.d.flags & (1u << mate));
+                    const bool fast = have && words_ok && !(t.d.flags & (1u << mate));
                     const uint32_t L = mate ? t.d.L1 : t.d.L0, body = t.off[mate] + (mate ? t.d.H1 : t.d.H0);
                     const uint64_t a = mate ? t.d.a1 : t.d.a0;
-                    emit_body_fast<TK>(rp, tab_s, fast, stage_s + body, unit, mate, a, L, sl);
+                    const uint32_t T = __reduce_max_sync(0xffffffffu, fast ? (((L + 3u) >> 2) + SUB) / SUB : 0u);   /* SUB*T > groups */
+                    if (T) {
+                        if (mate == 0) body_fast<TK, false>(rp, tab_s, base_s + SM_LUT_FWD, fast, stage_s + body, ulo, uhi, 1, a, L, sl, T);
+                        else body_fast<TK, true>(rp, tab_s, base_s + SM_LUT_RC, fast, stage_s + body, ulo, uhi, 2, a, L, sl, T);
+                    }
                     if (have && !fast)
-                        emit_body_generic<REPLAY>(rp, rd, tab, stage + body, unit, mate, a, L,
-                                                  (REPLAY ? rd.base_off[unit] : 0) + (mate ? t.d.rl : 0), sl, SUB);
+                        emit_body_generic<REPLAY, false>(rp, rd, tab, stage + body, unit, mate, a, L,
+                                                         (REPLAY ? rd.base_off[unit] : 0) + (mate ? t.d.rl : 0), sl, SUB);
                 }
             }
+            __syncthreads();
+
+            /* ---- phase 2: headers and the fixed bytes, one thread per record ---- */
+            for (uint32_t r = threadIdx.x; r < 2 * nu; r += FORMAT_THREADS) {
+                const TileUnit &t = tu[r >> 1]; const uint32_t mate = r & 1;
+                if (mate && !(t.d.flags & 4u)) continue;
+                uint64_t sp, ep; record_positions(t.d, mate, sp, ep);
+                const uint32_t id = rp.read_id_base + uint32_t(rp.batch_begin + u0 + (r >> 1));
+                const uint32_t H = mate ? t.d.H1 : t.d.H0, L = mate ? t.d.L1 : t.d.L0, rec_s = stage_s + t.off[mate];
+                if (hdr_fast) header_fast(rp, dec2_s, rec_s, rp.chdr[t.d.contig], id, uint32_t(sp), uint32_t(ep), mate != 0, mate);
+                else {
+                    emit_header(stage + t.off[mate], rp, rp.chdr[t.d.contig], id, sp, ep, mate != 0, mate);
+                    sts8(rec_s + H, '\n');
+                    if (t.off[mate] > pad) sts8(rec_s - 1u, '\n');             /* ends the previous record */
+                }
+                const uint32_t mid = rec_s + H + L + 1u;                       /* fastq.rs:61-69 */
+                sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n');
+            }
+            if (threadIdx.x == FORMAT_THREADS - 1 && total) sts8(stage_s + pad + total - 1u, '\n');
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
             /* stage[pad, pad+total) -> out[tile_base, +total): 16-byte aligned middle by TMA, edges by byte stores */
             const uint32_t head = min(total, (16 - pad) & 15), mid = (total - head) & ~15u, tail = total - head - mid;
-            if (rp.flags & 0x100u) { for (uint32_t b = threadIdx.x; b < mid; b += FORMAT_THREADS) rp.out[tile_base + head + b] = stage[pad + head + b]; }
-            else if (threadIdx.x == 0 && mid) {
+            if (threadIdx.x == 0 && mid) {
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rp.out + tile_base + head), "r"(stage_s + pad + head), "r"(mid) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -762,7 +864,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, 
                 uint64_t sp, ep; record_positions(d, r, sp, ep);
                 emit_header(dst, rp, rp.chdr[d.contig], rp.read_id_base + uint32_t(u), sp, ep, r != 0, int(r));
             }
-            emit_body_generic<REPLAY>(rp, rd, tab, dst + H, u, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
+            emit_body_generic<REPLAY, true>(rp, rd, tab, dst + H, u, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
             dst += H + 2 * L + 5;
         }
     }

@@ -67,10 +67,11 @@ struct simmr_ctx {
     std::vector<uint64_t> h_contig_off, h_contig_size;
     std::vector<uint32_t> h_genome_contig, h_contig_id_off, h_genome_id_off;
     std::string h_contig_ids, h_genome_ids;
-    DevMem d_bases, d_impure, d_contig_off, d_contig_size, d_genome_contig;
+    DevMem d_bases, d_impure, d_packed, d_contig_off, d_contig_size, d_genome_contig;
     /* headers */
     std::string header_fmt; bool have_headers = false;
     HeaderPlan plan;
+    uint32_t hdr_ntok = 0; uint64_t hdr_kinds[2] = {0, 0};    /* token kinds when every contig shares them */
     DevMem d_chdr, d_toks, d_pool;
     /* profile */
     bool have_profile = false;
@@ -99,7 +100,7 @@ int fail(simmr_ctx *c, int code, const std::string &m) {
 
 size_t table_bytes(const ProfileModel &m) { return m.phred_entries.size() * 4; }
 size_t tile_smem(const ProfileModel &m, uint32_t upt, uint32_t stage_cap) {
-    return ((table_bytes(m) + 15) & ~size_t(15)) + size_t(upt) * sizeof(TileUnit) + stage_cap + 48;
+    return SM_TAB + ((table_bytes(m) + 15) & ~size_t(15)) + size_t(upt) * sizeof(TileUnit) + STAGE_FRONT + stage_cap + 48;
 }
 
 /* kernel instantiations: the fast path is specialised per table kind, replay is generic */
@@ -135,7 +136,7 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
         /* The stage holds the typical bytes of `upt` units plus a margin; a tile that draws
          * longer reads than that is cut into sub-tiles by the kernel.  It must hold the
          * largest possible single unit. */
-        uint32_t upt = 32;
+        uint32_t upt = 64;
         if (const char *e = getenv("SIMMR_UPT")) upt = uint32_t(std::max(1, std::min(128, atoi(e))));
         const uint64_t typical = 2ull * (ctx->plan.hdr_cap + 2ull * m.nominal_read_len + 5);
         auto cap_for = [&](uint32_t n) { return uint32_t(std::max<uint64_t>(unit_bytes + 32, n * typical * 27 / 25 + 64)); };
@@ -168,6 +169,17 @@ int ensure_headers(simmr_ctx *ctx, const char *fmt) {
     ctx->plan.pool.resize((ctx->plan.pool.size() + 7) & ~size_t(3), '\0');
     CU(ctx->d_pool.upload(ctx->plan.pool.data(), ctx->plan.pool.size(), ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
+    {   /* one token-kind list for all contigs lets the kernel run the template without per-token loads */
+        const HeaderPlan &hp = ctx->plan;
+        const uint32_t n = hp.contigs.empty() ? 0 : hp.contigs[0].ntok;
+        bool same = n > 0 && n <= HDR_MAX_TOK;
+        for (size_t c = 0; same && c < hp.contigs.size(); ++c) {
+            same = hp.contigs[c].ntok == n;
+            for (uint32_t i = 0; same && i < n; ++i) same = hp.toks[hp.contigs[c].tok_off + i].type == hp.toks[hp.contigs[0].tok_off + i].type;
+        }
+        ctx->hdr_ntok = same ? n : 0; ctx->hdr_kinds[0] = ctx->hdr_kinds[1] = 0;
+        for (uint32_t i = 0; same && i < n; ++i) ctx->hdr_kinds[i >> 4] |= uint64_t(hp.toks[hp.contigs[0].tok_off + i].type) << (4 * (i & 15));
+    }
     ctx->header_fmt = f; ctx->have_headers = true;
     return SIMMR_OK;
 }
@@ -177,7 +189,8 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     memset(&rp, 0, sizeof rp);
     rp.bases = ctx->d_bases.as<uint8_t>(); rp.contig_off = ctx->d_contig_off.as<uint64_t>();
     rp.contig_size = ctx->d_contig_size.as<uint64_t>(); rp.genome_contig = ctx->d_genome_contig.as<uint32_t>();
-    rp.impure = ctx->d_impure.as<uint32_t>();
+    rp.impure = ctx->d_impure.as<uint32_t>(); rp.packed = ctx->d_packed.as<uint32_t>();
+    rp.hdr_ntok = ctx->hdr_ntok; rp.hdr_kinds[0] = ctx->hdr_kinds[0]; rp.hdr_kinds[1] = ctx->hdr_kinds[1];
     rp.chdr = ctx->d_chdr.as<ContigHdr>(); rp.toks = ctx->d_toks.as<HdrTok>(); rp.pool = ctx->d_pool.as<uint8_t>();
     rp.n_genomes = ctx->host_view.n_genomes; rp.n_contigs = ctx->host_view.n_contigs;
     rp.unit_start = ctx->d_unit_start.as<uint64_t>();
@@ -377,10 +390,14 @@ int simmr_genomes_load(simmr_ctx *ctx, const simmr_genome_set *s) {
     CU(ctx->d_bases.reserve(nbytes + 64));
     CU(cudaMemcpy(ctx->d_bases.p, s->bases, nbytes, cudaMemcpyHostToDevice));
     CU(cudaMemset(static_cast<uint8_t *>(ctx->d_bases.p) + nbytes, 'N', 64));
-    {   /* which 32-byte blocks hold only A,C,G,T: lets the format kernel take its branch-free path */
-        const uint64_t nblocks = (nbytes + 31) / 32, nwords = (nblocks + 31) / 32 + 1;
-        CU(ctx->d_impure.reserve(nwords * 4));
-        k_purity<<<unsigned((nwords + 255) / 256), 256, 0, ctx->compute>>>(ctx->d_bases.as<uint8_t>(), nbytes, ctx->d_impure.as<uint32_t>(), nwords);
+    {   /* 2-bit copy for the fast path + which 32-byte blocks hold only A,C,G,T (anything else takes the byte path) */
+        const uint64_t nblocks = (nbytes + 31) / 32, nimpure = (nblocks + 31) / 32 + 1;
+        CU(ctx->d_impure.reserve(nimpure * 4));
+        CU(ctx->d_packed.reserve((2 * nblocks + PACK_PAD_WORDS) * 4));
+        CU(cudaMemsetAsync(ctx->d_impure.p, 0, nimpure * 4, ctx->compute));
+        CU(cudaMemsetAsync(ctx->d_packed.as<uint32_t>() + 2 * nblocks, 0, PACK_PAD_WORDS * 4, ctx->compute));
+        k_pack<<<unsigned((nblocks + 255) / 256), 256, 0, ctx->compute>>>(ctx->d_bases.as<uint8_t>(), nbytes, ctx->d_packed.as<uint32_t>(),
+                                                                        ctx->d_impure.as<uint32_t>(), nblocks, nimpure);
         CU(cudaGetLastError());
     }
     CU(ctx->d_contig_off.upload(ctx->h_contig_off.data(), ctx->h_contig_off.size(), ctx->compute));
