@@ -50,6 +50,7 @@ struct RunParams {
     /* profile (phred.entries: device layout, quality bytes already +33) */
     PhredTab phred; LenTab rl, is; GammaConst gamma;
     uint32_t min_size, is_long, flags, mutates;
+    uint32_t phred_mult;           /* 1 << phred.cb */
     uint32_t rk[20];               /* Philox round keys: seed + r * Weyl constants, r = 0..9 */
     /* per-batch scratch + output */
     uint32_t *sizes; uint64_t *offsets, *block_sums; uint8_t *out;
@@ -67,10 +68,11 @@ constexpr int SIZES_THREADS = 256;
 constexpr int FORMAT_THREADS = 128;   /* threads of a tile CTA                          */
 constexpr int FORMAT_MIN_CTAS = 4;    /* occupancy target -> register cap of 128         */
 constexpr int DIRECT_THREADS = 256;
-constexpr int SUB = 8;                /* lanes that share one record in the tile kernel  */
+constexpr int SUB = 4;                /* lanes that share one record in the tile kernel  */
 constexpr uint32_t PACK_PAD_WORDS = 1024; /* readable words past the end of `packed`     */
 /* shared-memory layout of a tile CTA (byte offsets from the 1024-aligned base) */
-constexpr uint32_t SM_LUT_FWD = 0, SM_LUT_RC = 1024, SM_DEC2 = 2048, SM_TAB = 2304;
+constexpr uint32_t SM_LUT_FWD = 0, SM_LUT_RC = 1024, SM_DEC2 = 2048, SM_HIST = 2304, SM_TAB = 2560;
+constexpr uint32_t N_CLASS = 64;      /* work classes of a tile's units (pairs of groups per lane, clipped) */
 constexpr uint32_t STAGE_FRONT = 16;  /* slack before the tile image (a header's leading newline may land there) */
 
 /* ---------------------------------------------------------------------- */
@@ -277,7 +279,7 @@ __device__ __forceinline__ uint32_t dec_digits(uint64_t v) {
     return d;
 }
 __device__ __forceinline__ uint32_t header_len(const ContigHdr &ch, uint32_t id, uint64_t sp, uint64_t ep) {
-    return ch.lit_bytes + ch.n_id * dec_digits32(id) + ch.n_sp * dec_digits(sp) + ch.n_ep * dec_digits(ep) + ch.n_rc + ch.n_pair;
+    return ch.lit_bytes + ch.n_id * dec_digits32(id) + ch.n_sp * dec_digits(sp) + ch.n_ep * dec_digits(ep);
 }
 __device__ __forceinline__ uint32_t put_dec(uint8_t *dst, uint64_t v) {
     const uint32_t d = dec_digits(v);
@@ -289,7 +291,7 @@ __device__ __forceinline__ uint32_t put_dec(uint8_t *dst, uint64_t v) {
 }
 /* Instantiates the compiled template of a contig (fastq.rs:34-57).  Literals start on
  * 4-byte boundaries of the pool so they can be fetched a word at a time. */
-__device__ uint32_t emit_header(uint8_t *dst, const RunParams &rp, const ContigHdr &ch, uint32_t id, uint64_t sp, uint64_t ep, bool rc, int mate) {
+__device__ uint32_t emit_header(uint8_t *dst, const RunParams &rp, const ContigHdr &ch, uint32_t id, uint64_t sp, uint64_t ep) {
     uint32_t n = 0;
     const HdrTok *t = rp.toks + ch.tok_off;
     for (uint32_t i = 0; i < ch.ntok; ++i) {
@@ -307,9 +309,7 @@ __device__ uint32_t emit_header(uint8_t *dst, const RunParams &rp, const ContigH
             n += k.len; break; }
         case TOK_READ_ID: n += put_dec(dst + n, id); break;
         case TOK_START: n += put_dec(dst + n, sp); break;
-        case TOK_END: n += put_dec(dst + n, ep); break;
-        case TOK_RC: dst[n++] = rc ? 't' : 'f'; break;
-        default: dst[n++] = mate ? '2' : '1'; break;              /* fastq.rs:57, :106 */
+        default: n += put_dec(dst + n, ep); break;                /* TOK_END; rc and pair are part of the literals */
         }
     }
     return n;
@@ -434,12 +434,17 @@ __device__ __forceinline__ uint32_t mulhi_lo(uint32_t a, uint32_t b, uint32_t &l
 /* quality characters (+33 applied) and mutation codes of bases 4g..4g+3 from one Philox block */
 template <int TK>
 __device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, const Philox4 &w, uint32_t g, uint32_t &qw, uint32_t &mw) {
-    const uint32_t mult = 1u << rp.phred.cb;       /* r * 2^cb: high word = column, low word = threshold draw */
     const uint32_t r[4] = {w.x, w.y, w.z, w.w};
-    if (TK == PT_T64) {
-        uint2 e[4]; uint32_t x[4];
+    uint32_t col[4], x[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const uint32_t col = mulhi_lo(r[j], mult, x[j]); e[j] = lds64(tab_s + (col << 3)); }
+    for (int j = 0; j < 4; ++j) {                 /* r * 2^cb as one wide multiply: high word = column, low word = threshold draw */
+        uint64_t p; asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(r[j]), "r"(rp.phred_mult));
+        col[j] = uint32_t(p >> 32); x[j] = uint32_t(p);
+    }
+    if (TK == PT_T64) {
+        uint2 e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e[j] = lds64(tab_s + col[j] * 8u);
         /* byte selectors: self = payload bytes 0 (quality) and 1 (mutation), alias = bytes 2 and 3 */
         const uint32_t s01 = (x[0] < e[0].x ? 0x5140u : 0x5342u) + (x[1] < e[1].x ? 0u : 0x2020u);
         const uint32_t s23 = (x[2] < e[2].x ? 0x5140u : 0x5342u) + (x[3] < e[3].x ? 0u : 0x2020u);
@@ -447,11 +452,11 @@ __device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, con
         qw = __byte_perm(a, b, 0x5410); mw = __byte_perm(a, b, 0x7632);
     } else {
         const uint32_t last = rp.phred.npos - 1, cb = rp.phred.cb;
-        uint32_t e[4], x[4];
+        uint32_t e[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t col = mulhi_lo(r[j], mult, x[j]), pos = min(4 * g + j, last);      /* custom_short.rs:339-345 */
-            e[j] = lds32(tab_s + (((pos << cb) + col) << 2));
+            const uint32_t pos = min(4 * g + j, last);                                          /* custom_short.rs:339-345 */
+            e[j] = lds32(tab_s + (((pos << cb) + col[j]) << 2));
         }
         /* entry = thr16<<16 | q_alias<<8 | q_self; keep self when (x >> 16) < thr16 */
         const uint32_t s01 = (x[0] < (e[0] & 0xffff0000u) ? 0x40u : 0x41u) + (x[1] < (e[1] & 0xffff0000u) ? 0u : 0x10u);
@@ -460,16 +465,30 @@ __device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, con
     }
 }
 
+/* one 4-base group: byte `bi` of X holds its four 2-bit codes.  Returns the ASCII word of the
+ * (substituted) bases in `sw` and the quality characters in `qw`. */
+template <int TK>
+__device__ __forceinline__ void group4(const RunParams &rp, uint32_t tab_s, uint32_t lut_s, uint32_t qconst, uint32_t X, uint32_t bi,
+                                       uint32_t g, uint32_t stream, uint32_t ulo, uint32_t uhi, uint32_t &sw, uint32_t &qw) {
+    uint32_t mw = 0;
+    if (TK == PT_CONST) qw = qconst;
+    else sample4<TK>(rp, tab_s, philox(rp.rk, g, stream, ulo, uhi), g, qw, mw);
+    uint32_t at = (bi == 0 ? X << 2 : X >> (8 * bi - 2)) & 0x3fcu;
+    if (TK == PT_T64) at ^= ((mw * 0x01041040u) >> 22) & 0x3fcu;     /* XOR the four 2-bit substitution codes into the byte */
+    sw = lds32(lut_s + at);
+}
+
 /* Sequence and quality lines of one record by the SUB lanes of a sub-group, all 32 lanes of
  * the warp converged (lanes whose sub-group has no fast record run with on = false and store
- * nothing).  RC: mate 2 — bases complemented and written back to front (util.rs:31-37); the
- * quality line is never reversed (simulate.rs:283-285).  body_s = shared-space address of the
- * '\n' that ends the header; lut_s = ASCII table for this strand. */
+ * nothing).  Each lane owns 2*T2 consecutive groups and works on them two at a time (two
+ * independent Philox chains in flight).  RC: mate 2 — bases complemented and written back to
+ * front (util.rs:31-37); the quality line is never reversed (simulate.rs:283-285).  body_s =
+ * shared-space address of the '\n' that ends the header; lut_s = ASCII table of this strand. */
 template <int TK, bool RC>
 __device__ __forceinline__ void body_fast(const RunParams &rp, uint32_t tab_s, uint32_t lut_s, bool on, uint32_t body_s,
-                                          uint32_t ulo, uint32_t uhi, uint32_t stream, uint64_t a, uint32_t L, uint32_t sl, uint32_t T) {
+                                          uint32_t ulo, uint32_t uhi, uint32_t stream, uint64_t a, uint32_t L, uint32_t sl, uint32_t T2) {
     if (!on) { L = 0; a = 0; body_s = 0; }
-    const uint32_t g0 = sl * T;
+    const uint32_t g0 = sl * 2u * T2;
     /* aligned words of the two lines: slot k of the sequence line sits at ps + 4k (ps - 4k when RC), of the quality line at pq + 4k */
     const uint32_t Ds = body_s + 1, Dq = body_s + L + 4;
     uint32_t sh_s, kw_s, ps;
@@ -478,43 +497,43 @@ __device__ __forceinline__ void body_fast(const RunParams &rp, uint32_t tab_s, u
     const uint32_t oq = Dq & 3u, sh_q = 8u * oq;
     uint32_t kw_q = (L + oq + 3u) >> 2, pq = (Dq - oq) + 4u * g0;
     if (!on) kw_s = kw_q = 0;
+    /* slots this lane may store, per line (the rest of its 2*T2 lie past the end of the line) */
+    int32_t ns = int32_t(kw_s) - int32_t(g0), nq = int32_t(kw_q) - int32_t(g0);
     const uint32_t ps0 = ps, pq0 = pq;
+    const bool st0s = ns > 0, st0q = nq > 0;
     /* 16 bases per word of the 2-bit copy; this lane's run starts at base a + 4*g0 */
     const uint64_t b0 = a + 4ull * g0;
     const uint32_t *pw = rp.packed + (b0 >> 4);
     const uint32_t s2 = 2u * (uint32_t(b0) & 15u);
     uint32_t w0 = __ldg(pw), w1 = __ldg(pw + 1);
     const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u;
-    uint32_t first_s = 0, first_q = 0, prev_s = 0, prev_q = 0;
-    for (uint32_t tb = 0; tb < T; tb += 4) {
+    uint32_t first_s = 0, first_q = 0, prev_s = 0, prev_q = 0, g = g0;
+    auto compose_s = [&](uint32_t older, uint32_t newer) { return RC ? __funnelshift_lc(newer, older, sh_s) : __funnelshift_l(older, newer, sh_s); };
+    auto compose_q = [&](uint32_t older, uint32_t newer) { return TK == PT_CONST ? qconst : __funnelshift_l(older, newer, sh_q); };
+    for (uint32_t p = 0; p < T2; p += 2) {           /* one word of the 2-bit copy = 4 groups = 2 pairs */
         const uint32_t X = __funnelshift_r(w0, w1, s2);
-        w0 = w1; w1 = __ldg(pw + 2 + (tb >> 2));
+        w0 = w1; w1 = __ldg(pw + 2 + (p >> 1));
 #pragma unroll
-        for (uint32_t tt = 0; tt < 4; ++tt) {
-            const uint32_t t = tb + tt, g = g0 + t;
-            if (t >= T) break;
-            uint32_t qw, mw = 0;
-            if (TK == PT_CONST) qw = qconst;
-            else sample4<TK>(rp, tab_s, philox(rp.rk, g, stream, ulo, uhi), g, qw, mw);
-            /* byte tt of X = the group's four 2-bit codes; XOR with the packed mutation codes, then ASCII by table */
-            uint32_t at = (tt == 0 ? X << 2 : X >> (8 * tt - 2)) & 0x3fcu;
-            if (TK == PT_T64) at ^= ((mw * 0x01041040u) >> 22) & 0x3fcu;
-            const uint32_t sw = lds32(lut_s + at);
-            if (t == 0) { first_s = sw; first_q = qw; }
+        for (uint32_t h = 0; h < 2; ++h) {
+            if (h == 1 && p + 1 >= T2) break;
+            uint32_t sa, qa, sb, qb;
+            group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h, g, stream, ulo, uhi, sa, qa);
+            group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h + 1, g + 1, stream, ulo, uhi, sb, qb);
+            if (h == 0 && p == 0) { first_s = sa; first_q = qa; }
             else {
-                const uint32_t as = RC ? __funnelshift_lc(sw, prev_s, sh_s) : __funnelshift_l(prev_s, sw, sh_s);
-                if (g < kw_s) sts32(ps, as);
-                if (TK != PT_CONST) { const uint32_t aq = __funnelshift_l(prev_q, qw, sh_q); if (g < kw_q) sts32(pq, aq); }
-                else if (g < kw_q) sts32(pq, qconst);
+                if (ns > 0) sts32(ps, compose_s(prev_s, sa));
+                if (nq > 0) sts32(pq, compose_q(prev_q, qa));
             }
-            prev_s = sw; prev_q = qw;
-            ps += RC ? uint32_t(-4) : 4u; pq += 4u;
+            if (ns > 1) sts32(RC ? ps - 4u : ps + 4u, compose_s(sa, sb));
+            if (nq > 1) sts32(pq + 4u, compose_q(qa, qb));
+            prev_s = sb; prev_q = qb;
+            ps += RC ? uint32_t(-8) : 8u; pq += 8u; ns -= 2; nq -= 2; g += 2;
         }
     }
     /* slot g0 needs the last word of the lane to the left (lane 0: bytes before the line, repaired in phase 2) */
     const uint32_t left_s = __shfl_up_sync(0xffffffffu, prev_s, 1, SUB), left_q = __shfl_up_sync(0xffffffffu, prev_q, 1, SUB);
-    if (g0 < kw_s) sts32(ps0, RC ? __funnelshift_lc(first_s, left_s, sh_s) : __funnelshift_l(left_s, first_s, sh_s));
-    if (g0 < kw_q) sts32(pq0, TK == PT_CONST ? qconst : __funnelshift_l(left_q, first_q, sh_q));
+    if (st0s) sts32(ps0, compose_s(left_s, first_s));
+    if (st0q) sts32(pq0, compose_q(left_q, first_q));
 }
 
 /* ---------------------------------------------------------------------- */
@@ -544,7 +563,9 @@ __device__ __forceinline__ uint32_t four_digits(uint32_t dec2_s, uint32_t c) {
     return lds16(dec2_s + 2u * hi) | (lds16(dec2_s + 2u * lo) << 16);
 }
 __device__ __forceinline__ void bs_decimal(ByteStream &b, uint32_t dec2_s, uint32_t v) {
-    const uint32_t d = dec_digits32(v);
+    /* digits: floor(log10) guessed from the bit length, corrected by one compare */
+    const uint32_t guess = ((32u - __clz(v | 1u)) * 1233u) >> 12;
+    const uint32_t d = guess + ((v | 1u) >= lds32(dec2_s + 200u + 4u * guess) ? 1u : 0u);    /* table of 10^k after the digit pairs */
     const uint32_t top = __umulhi(v, 0xABCC7712u) >> 26;                     /* v / 10^8 */
     const uint32_t r8 = v - top * 100000000u, m4 = __umulhi(r8, 0xD1B71759u) >> 13, l4 = r8 - m4 * 10000u;   /* r8 / 10^4 */
     const uint32_t r2 = four_digits(dec2_s, l4);
@@ -558,28 +579,26 @@ __device__ __forceinline__ void bs_decimal(ByteStream &b, uint32_t dec2_s, uint3
 }
 
 /* Header of one record + the newline before it (the previous record's last byte) + the
- * newline after it, for templates whose token kinds are the same for every contig.
- * rec_s = shared-space address of the record's first byte. */
+ * newline after it, for templates whose token kinds are the same for every contig (at most
+ * 16 tokens).  rec_s = shared-space address of the record's first byte; ch = the token list
+ * of this (contig, mate). */
 __device__ __forceinline__ void header_fast(const RunParams &rp, uint32_t dec2_s, uint32_t rec_s, const ContigHdr &ch,
-                                            uint32_t id, uint32_t sp, uint32_t ep, bool rc, uint32_t mate) {
+                                            uint32_t id, uint32_t sp, uint32_t ep) {
     ByteStream b; bs_open(b, rec_s - 1u);
     bs_put(b, '\n', 1);
-    const HdrTok *tk = rp.toks + ch.tok_off;
-    for (uint32_t i = 0; i < rp.hdr_ntok; ++i) {
-        switch (uint32_t(rp.hdr_kinds[i >> 4] >> (4 * (i & 15))) & 15u) {
-        case TOK_LIT: {
-            const uint2 k = __ldg(reinterpret_cast<const uint2 *>(tk + i));       /* {off, len | type << 16} */
+    const uint2 *tk = reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off);       /* {off, len | type << 16} */
+    uint64_t kinds = rp.hdr_kinds[0];
+#pragma unroll 1
+    for (uint32_t i = 0; i < rp.hdr_ntok; ++i, kinds >>= 4) {
+        const uint32_t kind = uint32_t(kinds) & 15u;                               /* same for every thread */
+        if (kind == TOK_LIT) {
+            const uint2 k = __ldg(tk + i);
             const uint32_t *src = reinterpret_cast<const uint32_t *>(rp.pool + k.x);
             const uint32_t len = k.y & 0xffffu, nw = len >> 2;
+#pragma unroll 4
             for (uint32_t j = 0; j < nw; ++j) bs_word(b, __ldg(src + j));
             if (len & 3u) bs_put(b, __ldg(src + nw), len & 3u);
-            break; }
-        case TOK_READ_ID: bs_decimal(b, dec2_s, id); break;
-        case TOK_START: bs_decimal(b, dec2_s, sp); break;
-        case TOK_END: bs_decimal(b, dec2_s, ep); break;
-        case TOK_RC: bs_put(b, rc ? 't' : 'f', 1); break;
-        default: bs_put(b, mate ? '2' : '1', 1); break;                           /* fastq.rs:57, :106 */
-        }
+        } else bs_decimal(b, dec2_s, kind == TOK_READ_ID ? id : kind == TOK_START ? sp : ep);
     }
     bs_put(b, '\n', 1);
     bs_close(b);
@@ -641,11 +660,10 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, Repl
     uint64_t bytes = 0, alg = 0, bases = 0, clamped = 0, recs = 0;
     if (i < rp.batch_units) {
         UnitGeo g; unit_geometry<REPLAY>(rp, rd, rp.batch_begin + i, g);
-        const ContigHdr ch = rp.chdr[g.contig];
         uint32_t H[2] = {0, 0};
         uint64_t big = 0;
         for (uint32_t r = 0; r < g.nrec; ++r) {
-            H[r] = header_len(ch, g.id, g.sp[r], g.ep[r]);
+            H[r] = header_len(rp.chdr[2 * g.contig + r], g.id, g.sp[r], g.ep[r]);
             bytes += H[r] + 2ull * g.L[r] + 5;
             alg += H[r] + 3ull * g.L[r] + 5;                     /* BASELINE.md §3 */
             bases += g.L[r];
@@ -730,19 +748,25 @@ __device__ __forceinline__ void record_positions(const UnitDesc &d, uint32_t r, 
     else { sp = d.p1 + d.rl; ep = d.p1; }
 }
 
+/* pairs of 4-base groups each of the SUB lanes of a record takes: 2*SUB*T2 slots >= groups + 1 */
+__device__ __forceinline__ uint32_t pairs_per_lane(uint32_t L) { return (((L + 3u) >> 2) + 2u * SUB) / (2u * SUB); }
+
 /* Persistent CTAs; each tile = up to `upt` consecutive units whose FASTQ bytes are composed
  * in shared memory and leave through one bulk async copy (TMA).  A tile whose bytes exceed
  * the stage is cut into sub-tiles.  Phase 1: sequence and quality lines (body_fast, or byte
- * stores for windows holding anything but A,C,G,T and for replay).  Phase 2, after a CTA
- * barrier: headers and the fixed newline / '+' bytes, one thread per record.  TK = table kind
- * the fast path is specialised for. */
+ * stores for windows holding anything but A,C,G,T and for replay); the units are taken in
+ * order of their work class (read length) so that the records a warp handles together need
+ * the same number of steps.  Phase 2, after a CTA barrier: headers and the fixed newline /
+ * '+' bytes, one thread per record.  TK = table kind the fast path is specialised for. */
 template <bool REPLAY, int TK>
 __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tiles(RunParams rp, ReplayDev rd) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u : 1u);
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem + SM_TAB);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem + SM_HIST);
     TileUnit *tu = reinterpret_cast<TileUnit *>(smem + SM_TAB + ((tab_words * 4 + 15) & ~15u));
-    uint8_t *stage = reinterpret_cast<uint8_t *>(tu + rp.upt) + STAGE_FRONT;
+    uint16_t *order = reinterpret_cast<uint16_t *>(tu + rp.upt);
+    uint8_t *stage = reinterpret_cast<uint8_t *>(order) + ((rp.upt * 2u + 15u) & ~15u) + STAGE_FRONT;
     const uint32_t base_s = uint32_t(__cvta_generic_to_shared(smem));
     const uint32_t tab_s = base_s + SM_TAB, dec2_s = base_s + SM_DEC2, stage_s = uint32_t(__cvta_generic_to_shared(stage));
     for (uint32_t i = threadIdx.x; i < tab_words; i += FORMAT_THREADS) tab[i] = rp.phred.entries[i];
@@ -756,6 +780,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tile
         reinterpret_cast<uint32_t *>(smem + SM_LUT_FWD)[b] = f;
         reinterpret_cast<uint32_t *>(smem + SM_LUT_RC)[b] = r;
         if (b < 100) reinterpret_cast<uint16_t *>(smem + SM_DEC2)[b] = uint16_t(('0' + b / 10) | (('0' + b % 10) << 8));
+        if (b < 10) { uint32_t p = 1; for (uint32_t k = 0; k < b; ++k) p *= 10u; reinterpret_cast<uint32_t *>(smem + SM_DEC2 + 200)[b] = p; }
     }
 
     const uint32_t ntiles = (rp.batch_units + rp.upt - 1) / rp.upt;
@@ -769,11 +794,13 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tile
             const uint64_t tile_base = rp.offsets[u0];
             const uint32_t pad = uint32_t(tile_base & 15);
             const bool fits = threadIdx.x < tn - s0 && rp.offsets[u0 + threadIdx.x + 1] - tile_base + pad <= rp.stage_cap;
+            if (threadIdx.x < N_CLASS) hist[threadIdx.x] = 0;
             /* the previous bulk copy must have finished reading the stage before it is rewritten */
             if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             const uint32_t nu = __syncthreads_count(fits);
             const uint32_t total = uint32_t(rp.offsets[u0 + nu] - tile_base);
             bool odd = false;                 /* this unit rules out the word-store paths for the sub-tile */
+            uint32_t cls = 0, rank = 0;
             if (threadIdx.x < nu) {
                 TileUnit &t = tu[threadIdx.x];
                 t.d = rp.desc[u0 + threadIdx.x];
@@ -781,26 +808,34 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tile
                 t.off[1] = t.off[0] + t.d.H0 + 2u * t.d.L0 + 5u;
                 const bool two = t.d.flags & 4u;
                 odd = (t.d.flags & 8u) || t.d.H0 < 2u || t.d.L0 < 4u || (two && (t.d.H1 < 2u || t.d.L1 < 4u));
+                cls = min(pairs_per_lane(max(uint32_t(t.d.L0), two ? uint32_t(t.d.L1) : 0u)), N_CLASS - 1);
+                rank = atomicAdd(hist + cls, 1u);
             }
             const bool words_ok = !__syncthreads_or(odd) && !REPLAY;
             const bool hdr_fast = words_ok && rp.hdr_ntok != 0;
+            if (threadIdx.x < nu) {           /* counting sort by class: position = units of lower classes + rank in own class */
+                for (uint32_t k = 0; k < cls; ++k) rank += hist[k];
+                order[rank] = uint16_t(threadIdx.x);
+            }
+            __syncthreads();
 
             /* ---- phase 1: sequence and quality lines ---- */
-            for (uint32_t ul0 = warp * UPW; ul0 < nu; ul0 += NWARPS * UPW) {
-                const uint32_t ul = ul0 + sg;
-                const TileUnit &t = tu[min(ul, nu - 1)];
+            for (uint32_t c0 = warp * UPW; c0 < nu; c0 += NWARPS * UPW) {
+                const bool mine = c0 + sg < nu;
+                const uint32_t ul = order[min(c0 + sg, nu - 1)];
+                const TileUnit &t = tu[ul];
                 const uint64_t unit = rp.batch_begin + u0 + ul;
                 const uint32_t ulo = uint32_t(unit), uhi = uint32_t(unit >> 32);
 #pragma unroll
                 for (uint32_t mate = 0; mate < 2; ++mate) {
-                    const bool have = ul < nu && (mate == 0 || (t.d.flags & 4u));
+                    const bool have = mine && (mate == 0 || (t.d.flags & 4u));
                     const bool fast = have && words_ok && !(t.d.flags & (1u << mate));
                     const uint32_t L = mate ? t.d.L1 : t.d.L0, body = t.off[mate] + (mate ? t.d.H1 : t.d.H0);
                     const uint64_t a = mate ? t.d.a1 : t.d.a0;
-                    const uint32_t T = __reduce_max_sync(0xffffffffu, fast ? (((L + 3u) >> 2) + SUB) / SUB : 0u);   /* SUB*T > groups */
-                    if (T) {
-                        if (mate == 0) body_fast<TK, false>(rp, tab_s, base_s + SM_LUT_FWD, fast, stage_s + body, ulo, uhi, 1, a, L, sl, T);
-                        else body_fast<TK, true>(rp, tab_s, base_s + SM_LUT_RC, fast, stage_s + body, ulo, uhi, 2, a, L, sl, T);
+                    const uint32_t T2 = __reduce_max_sync(0xffffffffu, fast ? pairs_per_lane(L) : 0u);
+                    if (T2) {
+                        if (mate == 0) body_fast<TK, false>(rp, tab_s, base_s + SM_LUT_FWD, fast, stage_s + body, ulo, uhi, 1, a, L, sl, T2);
+                        else body_fast<TK, true>(rp, tab_s, base_s + SM_LUT_RC, fast, stage_s + body, ulo, uhi, 2, a, L, sl, T2);
                     }
                     if (have && !fast)
                         emit_body_generic<REPLAY, false>(rp, rd, tab, stage + body, unit, mate, a, L,
@@ -816,9 +851,10 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tile
                 uint64_t sp, ep; record_positions(t.d, mate, sp, ep);
                 const uint32_t id = rp.read_id_base + uint32_t(rp.batch_begin + u0 + (r >> 1));
                 const uint32_t H = mate ? t.d.H1 : t.d.H0, L = mate ? t.d.L1 : t.d.L0, rec_s = stage_s + t.off[mate];
-                if (hdr_fast) header_fast(rp, dec2_s, rec_s, rp.chdr[t.d.contig], id, uint32_t(sp), uint32_t(ep), mate != 0, mate);
+                const ContigHdr ch = rp.chdr[2 * t.d.contig + mate];
+                if (hdr_fast) header_fast(rp, dec2_s, rec_s, ch, id, uint32_t(sp), uint32_t(ep));
                 else {
-                    emit_header(stage + t.off[mate], rp, rp.chdr[t.d.contig], id, sp, ep, mate != 0, mate);
+                    emit_header(stage + t.off[mate], rp, ch, id, sp, ep);
                     sts8(rec_s + H, '\n');
                     if (t.off[mate] > pad) sts8(rec_s - 1u, '\n');             /* ends the previous record */
                 }
@@ -862,7 +898,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, 
             const uint32_t H = r ? d.H1 : d.H0, L = r ? d.L1 : d.L0;
             if (threadIdx.x == 0) {
                 uint64_t sp, ep; record_positions(d, r, sp, ep);
-                emit_header(dst, rp, rp.chdr[d.contig], rp.read_id_base + uint32_t(u), sp, ep, r != 0, int(r));
+                emit_header(dst, rp, rp.chdr[2 * d.contig + r], rp.read_id_base + uint32_t(u), sp, ep);
             }
             emit_body_generic<REPLAY, true>(rp, rd, tab, dst + H, u, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
             dst += H + 2 * L + 5;

@@ -100,7 +100,7 @@ int fail(simmr_ctx *c, int code, const std::string &m) {
 
 size_t table_bytes(const ProfileModel &m) { return m.phred_entries.size() * 4; }
 size_t tile_smem(const ProfileModel &m, uint32_t upt, uint32_t stage_cap) {
-    return SM_TAB + ((table_bytes(m) + 15) & ~size_t(15)) + size_t(upt) * sizeof(TileUnit) + STAGE_FRONT + stage_cap + 48;
+    return SM_TAB + ((table_bytes(m) + 15) & ~size_t(15)) + size_t(upt) * sizeof(TileUnit) + ((upt * 2 + 15) & ~size_t(15)) + STAGE_FRONT + stage_cap + 48;
 }
 
 /* kernel instantiations: the fast path is specialised per table kind, replay is generic */
@@ -136,7 +136,7 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
         /* The stage holds the typical bytes of `upt` units plus a margin; a tile that draws
          * longer reads than that is cut into sub-tiles by the kernel.  It must hold the
          * largest possible single unit. */
-        uint32_t upt = 64;
+        uint32_t upt = 32;
         if (const char *e = getenv("SIMMR_UPT")) upt = uint32_t(std::max(1, std::min(128, atoi(e))));
         const uint64_t typical = 2ull * (ctx->plan.hdr_cap + 2ull * m.nominal_read_len + 5);
         auto cap_for = [&](uint32_t n) { return uint32_t(std::max<uint64_t>(unit_bytes + 32, n * typical * 27 / 25 + 64)); };
@@ -172,7 +172,7 @@ int ensure_headers(simmr_ctx *ctx, const char *fmt) {
     {   /* one token-kind list for all contigs lets the kernel run the template without per-token loads */
         const HeaderPlan &hp = ctx->plan;
         const uint32_t n = hp.contigs.empty() ? 0 : hp.contigs[0].ntok;
-        bool same = n > 0 && n <= HDR_MAX_TOK;
+        bool same = n > 0 && n <= 16;
         for (size_t c = 0; same && c < hp.contigs.size(); ++c) {
             same = hp.contigs[c].ntok == n;
             for (uint32_t i = 0; same && i < n; ++i) same = hp.toks[hp.contigs[c].tok_off + i].type == hp.toks[hp.contigs[0].tok_off + i].type;
@@ -199,7 +199,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.rl = LenTab{m.rl.kind, m.rl.value, m.rl.cb, 0, ctx->d_rl_e.as<uint32_t>(), ctx->d_rl_lo.as<uint32_t>(), ctx->d_rl_hi.as<uint32_t>()};
     rp.is = LenTab{m.is.kind, m.is.value, m.is.cb, 0, ctx->d_is_e.as<uint32_t>(), ctx->d_is_lo.as<uint32_t>(), ctx->d_is_hi.as<uint32_t>()};
     rp.gamma = m.gamma;
-    rp.min_size = m.min_size; rp.is_long = m.is_long; rp.flags = m.flags;
+    rp.min_size = m.min_size; rp.is_long = m.is_long; rp.flags = m.flags; rp.phred_mult = 1u << m.cb;
     if (const char *e = getenv("SIMMR_DBG")) rp.flags |= uint32_t(atoi(e)) << 8; rp.mutates = m.mutates;
     for (uint32_t r = 0; r < 10; ++r) { rp.rk[2 * r] = uint32_t(seed) + r * 0x9E3779B9u; rp.rk[2 * r + 1] = uint32_t(seed >> 32) + r * 0xBB67AE85u; }
     rp.sizes = ctx->d_sizes.as<uint32_t>(); rp.offsets = ctx->d_offsets.as<uint64_t>();

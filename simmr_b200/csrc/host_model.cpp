@@ -621,11 +621,16 @@ std::string subst(const std::string &s, const char *what, const std::string &wit
 /* The reference applies seven String::replace calls in a fixed order per record.
  * genome_id and sequence_id are expanded here per contig, honouring that order
  * ({:read_id:} is resolved before {:sequence_id:}, so a placeholder spelled
- * inside a contig id only survives if it is one of the later four); what is
- * left is a token list the kernel instantiates per record. */
+ * inside a contig id only survives if it is one of the later four).  The last
+ * two replacements, {:reverse_complement:} and {:pair:}, take one of two fixed
+ * values per mate (fastq.rs:54-57, :103-106), so each contig gets two token
+ * lists — entry 2c for mate 1 / long reads ("f", "1"), entry 2c+1 for mate 2
+ * ("t", "2") — with those characters folded into the literals.  What is left
+ * per record are the three decimal fields. */
 int compile_headers(const simmr_genome_set &g, const char *fmt, HeaderPlan &plan, std::string &err) {
     static const struct { const char *text; uint8_t tok; } later[] = {
         {"{:start_position:}", TOK_START}, {"{:end_position:}", TOK_END}, {"{:reverse_complement:}", TOK_RC}, {"{:pair:}", TOK_PAIR}};
+    struct Piece { uint8_t kind; std::string text; };
     plan = HeaderPlan();
     const std::string base = fmt ? fmt : DEFAULT_HEADER_FORMAT;
     for (uint32_t gi = 0; gi < g.n_genomes; ++gi) {
@@ -635,22 +640,7 @@ int compile_headers(const simmr_genome_set &g, const char *fmt, HeaderPlan &plan
             const uint8_t *idp = reinterpret_cast<const uint8_t *>(g.contig_ids) + g.contig_id_off[c];
             const size_t idn = g.contig_id_off[c + 1] - g.contig_id_off[c];
             const std::string sid = utf8_ok(idp, idn) ? std::string(reinterpret_cast<const char *>(idp), idn) : std::string();   /* shared/src/util.rs:49-51 */
-            ContigHdr ch{}; ch.tok_off = uint32_t(plan.toks.size());
-            auto lit = [&](const std::string &t) {
-                for (size_t at = 0; at < t.size(); at += 65535) {
-                    const size_t len = std::min<size_t>(65535, t.size() - at);
-                    plan.pool.resize((plan.pool.size() + 3) & ~size_t(3), '\0');   /* the kernel fetches literals by words */
-                    plan.toks.push_back(HdrTok{uint32_t(plan.pool.size()), uint16_t(len), TOK_LIT, 0});
-                    plan.pool.append(t, at, len);
-                }
-            };
-            size_t lit_total = 0;
-            auto field = [&](uint8_t k) {
-                plan.toks.push_back(HdrTok{0, 0, k, 0});
-                uint8_t *ctr = k == TOK_READ_ID ? &ch.n_id : k == TOK_START ? &ch.n_sp : k == TOK_END ? &ch.n_ep : k == TOK_RC ? &ch.n_rc : &ch.n_pair;
-                if (*ctr == 255) return false;
-                ++*ctr; return true;
-            };
+            std::vector<Piece> pieces;
             size_t at = 0;
             for (bool more = true; more;) {
                 const size_t hit = with_gid.find("{:read_id:}", at);
@@ -660,19 +650,46 @@ int compile_headers(const simmr_genome_set &g, const char *fmt, HeaderPlan &plan
                     size_t best = std::string::npos; int which = -1;
                     for (int k = 0; k < 4; ++k) { const size_t h = seg.find(later[k].text, p); if (h < best) { best = h; which = k; } }
                     const std::string piece = seg.substr(p, best == std::string::npos ? best : best - p);
-                    if (!piece.empty()) { lit(piece); lit_total += piece.size(); }
+                    if (!piece.empty()) pieces.push_back(Piece{TOK_LIT, piece});
                     if (which < 0) break;
-                    if (!field(later[which].tok)) { err = "header format repeats a placeholder more than 255 times"; return SIMMR_E_LIMIT; }
+                    pieces.push_back(Piece{later[which].tok, std::string()});
                     p = best + strlen(later[which].text);
                 }
                 if (hit == std::string::npos) more = false;
-                else { if (!field(TOK_READ_ID)) { err = "header format repeats a placeholder more than 255 times"; return SIMMR_E_LIMIT; } at = hit + 11; }
+                else { pieces.push_back(Piece{TOK_READ_ID, std::string()}); at = hit + 11; }
             }
-            if (lit_total > 60000 || plan.toks.size() - ch.tok_off > 60000) { err = "read header too long"; return SIMMR_E_LIMIT; }
-            ch.ntok = uint16_t(plan.toks.size() - ch.tok_off); ch.lit_bytes = uint16_t(lit_total);
-            plan.contigs.push_back(ch);
-            const uint32_t cap = uint32_t(lit_total) + 10u * ch.n_id + 20u * ch.n_sp + 20u * ch.n_ep + ch.n_rc + ch.n_pair;
-            plan.hdr_cap = std::max(plan.hdr_cap, cap);
+            for (int mate = 0; mate < 2; ++mate) {
+                ContigHdr ch{}; ch.tok_off = uint32_t(plan.toks.size());
+                size_t lit_total = 0;
+                std::string run;                           /* literal text gathered up to the next decimal field */
+                auto flush = [&]() {
+                    for (size_t o = 0; o < run.size(); o += 65532) {
+                        const size_t len = std::min<size_t>(65532, run.size() - o);
+                        plan.pool.resize((plan.pool.size() + 3) & ~size_t(3), '\0');   /* the kernel fetches literals by words */
+                        plan.toks.push_back(HdrTok{uint32_t(plan.pool.size()), uint16_t(len), TOK_LIT, 0});
+                        plan.pool.append(run, o, len);
+                    }
+                    lit_total += run.size(); run.clear();
+                };
+                for (const Piece &pc : pieces) {
+                    if (pc.kind == TOK_LIT) run += pc.text;
+                    else if (pc.kind == TOK_RC) run += mate ? 't' : 'f';
+                    else if (pc.kind == TOK_PAIR) run += mate ? '2' : '1';
+                    else {
+                        flush();
+                        plan.toks.push_back(HdrTok{0, 0, pc.kind, 0});
+                        uint8_t *ctr = pc.kind == TOK_READ_ID ? &ch.n_id : pc.kind == TOK_START ? &ch.n_sp : &ch.n_ep;
+                        if (*ctr == 255) { err = "header format repeats a placeholder more than 255 times"; return SIMMR_E_LIMIT; }
+                        ++*ctr;
+                    }
+                }
+                flush();
+                if (lit_total > 60000 || plan.toks.size() - ch.tok_off > 60000) { err = "read header too long"; return SIMMR_E_LIMIT; }
+                ch.ntok = uint16_t(plan.toks.size() - ch.tok_off); ch.lit_bytes = uint16_t(lit_total);
+                plan.contigs.push_back(ch);
+                const uint32_t cap = uint32_t(lit_total) + 10u * ch.n_id + 20u * ch.n_sp + 20u * ch.n_ep;
+                plan.hdr_cap = std::max(plan.hdr_cap, cap);
+            }
         }
     }
     return SIMMR_OK;

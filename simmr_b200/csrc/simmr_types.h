@@ -14,7 +14,7 @@ struct HdrTok {        /* one piece of a compiled per-contig header template */
     uint8_t  type;
     uint8_t  pad_;
 };
-struct ContigHdr {     /* per contig: token span + what is needed for H      */
+struct ContigHdr {     /* per (contig, mate): token span + what is needed for H; index 2*contig + mate */
     uint32_t tok_off;
     uint16_t ntok;
     uint16_t lit_bytes;
