@@ -56,8 +56,8 @@ struct RunParams {
     uint32_t *sizes; uint64_t *offsets, *block_sums; uint8_t *out;
     struct UnitDesc *desc;         /* per-unit geometry written by k_unit_sizes, read by the format kernels */
     unsigned long long *counters;  /* [0] clamped [1] algorithmic bytes [2] bases [3] records */
-    /* tile geometry of k_format_tiles */
-    uint32_t upt, stage_cap;
+    /* per-warp stage of k_format_warps */
+    uint32_t stage_cap;            /* bytes of a warp's stage in k_format_warps */
     /* header template shared by every contig (token kinds, fastq.rs:34-57); hdr_ntok == 0: per-contig lists only */
     uint32_t hdr_ntok;
     uint64_t hdr_kinds[2];         /* 4 bits per token, token i in bits 4*(i&15) of word i>>4 */
@@ -65,14 +65,13 @@ struct RunParams {
 constexpr uint32_t HDR_MAX_TOK = 32;
 
 constexpr int SIZES_THREADS = 256;
-constexpr int FORMAT_THREADS = 128;   /* threads of a tile CTA                          */
-constexpr int FORMAT_MIN_CTAS = 4;    /* occupancy target -> register cap of 128         */
+constexpr int FORMAT_THREADS = 256;   /* threads of a format CTA (8 warps, each with a private stage) */
+constexpr int FORMAT_MIN_CTAS = 3;    /* occupancy target -> register cap of 80          */
 constexpr int DIRECT_THREADS = 256;
 constexpr int SUB = 4;                /* lanes that share one record in the tile kernel  */
 constexpr uint32_t PACK_PAD_WORDS = 1024; /* readable words past the end of `packed`     */
 /* shared-memory layout of a tile CTA (byte offsets from the 1024-aligned base) */
-constexpr uint32_t SM_LUT_FWD = 0, SM_LUT_RC = 1024, SM_DEC2 = 2048, SM_HIST = 2304, SM_TAB = 2560;
-constexpr uint32_t N_CLASS = 64;      /* work classes of a tile's units (pairs of groups per lane, clipped) */
+constexpr uint32_t SM_LUT_FWD = 0, SM_LUT_RC = 1024, SM_DEC2 = 2048, SM_TAB = 2304;
 constexpr uint32_t STAGE_FRONT = 16;  /* slack before the tile image (a header's leading newline may land there) */
 
 /* ---------------------------------------------------------------------- */
@@ -437,14 +436,15 @@ __device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, con
     const uint32_t r[4] = {w.x, w.y, w.z, w.w};
     uint32_t col[4], x[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {                 /* r * 2^cb as one wide multiply: high word = column, low word = threshold draw */
-        uint64_t p; asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(r[j]), "r"(rp.phred_mult));
-        col[j] = uint32_t(p >> 32); x[j] = uint32_t(p);
-    }
+    for (int j = 0; j < 4; ++j)                   /* r * 2^cb as one wide multiply: high word = column, low word = threshold draw */
+        asm("{ .reg .b64 p; mul.wide.u32 p, %2, %3; mov.b64 {%1, %0}, p; }" : "=r"(col[j]), "=r"(x[j]) : "r"(r[j]), "r"(rp.phred_mult));
     if (TK == PT_T64) {
         uint2 e[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) e[j] = lds64(tab_s + col[j] * 8u);
+        for (int j = 0; j < 4; ++j) {             /* entry address by a multiply-add (kept out of the shift unit) */
+            uint32_t at; asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(at) : "r"(col[j]), "r"(tab_s));
+            e[j] = lds64(at);
+        }
         /* byte selectors: self = payload bytes 0 (quality) and 1 (mutation), alias = bytes 2 and 3 */
         const uint32_t s01 = (x[0] < e[0].x ? 0x5140u : 0x5342u) + (x[1] < e[1].x ? 0u : 0x2020u);
         const uint32_t s23 = (x[2] < e[2].x ? 0x5140u : 0x5342u) + (x[3] < e[3].x ? 0u : 0x2020u);
@@ -578,21 +578,19 @@ __device__ __forceinline__ void bs_decimal(ByteStream &b, uint32_t dec2_s, uint3
     bs_put(b, r2 >> s, d - 8u);
 }
 
-/* Header of one record + the newline before it (the previous record's last byte) + the
- * newline after it, for templates whose token kinds are the same for every contig (at most
- * 16 tokens).  rec_s = shared-space address of the record's first byte; ch = the token list
- * of this (contig, mate). */
-__device__ __forceinline__ void header_fast(const RunParams &rp, uint32_t dec2_s, uint32_t rec_s, const ContigHdr &ch,
-                                            uint32_t id, uint32_t sp, uint32_t ep) {
-    ByteStream b; bs_open(b, rec_s - 1u);
-    bs_put(b, '\n', 1);
-    const uint2 *tk = reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off);       /* {off, len | type << 16} */
-    uint64_t kinds = rp.hdr_kinds[0];
+__device__ __forceinline__ void bs_open_blind(ByteStream &b, uint32_t at) {   /* the bytes before `at` in its word are written later by someone else */
+    b.addr = at & ~3u; b.fill = at & 3u; b.carry = 0u;
+}
+
+/* Tokens [i0, i1) of a record's header template into the stream (kinds = the 4-bit token kinds
+ * starting at token i0, the same for every contig; tk = this (contig, mate)'s token list). */
+__device__ __forceinline__ void header_tokens(ByteStream &b, const RunParams &rp, uint32_t dec2_s, const uint2 *tk, uint64_t kinds,
+                                              uint32_t i0, uint32_t i1, uint32_t id, uint32_t sp, uint32_t ep) {
 #pragma unroll 1
-    for (uint32_t i = 0; i < rp.hdr_ntok; ++i, kinds >>= 4) {
+    for (uint32_t i = i0; i < i1; ++i, kinds >>= 4) {
         const uint32_t kind = uint32_t(kinds) & 15u;                               /* same for every thread */
         if (kind == TOK_LIT) {
-            const uint2 k = __ldg(tk + i);
+            const uint2 k = __ldg(tk + i);                                         /* {off, len | type << 16} */
             const uint32_t *src = reinterpret_cast<const uint32_t *>(rp.pool + k.x);
             const uint32_t len = k.y & 0xffffu, nw = len >> 2;
 #pragma unroll 4
@@ -600,8 +598,16 @@ __device__ __forceinline__ void header_fast(const RunParams &rp, uint32_t dec2_s
             if (len & 3u) bs_put(b, __ldg(src + nw), len & 3u);
         } else bs_decimal(b, dec2_s, kind == TOK_READ_ID ? id : kind == TOK_START ? sp : ep);
     }
-    bs_put(b, '\n', 1);
-    bs_close(b);
+}
+/* bytes tokens [0, i1) produce */
+__device__ __forceinline__ uint32_t header_prefix_len(const uint2 *tk, uint64_t kinds, uint32_t i1, uint32_t id, uint32_t sp, uint32_t ep) {
+    uint32_t n = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < i1; ++i, kinds >>= 4) {
+        const uint32_t kind = uint32_t(kinds) & 15u;
+        n += kind == TOK_LIT ? (__ldg(tk + i).y & 0xffffu) : dec_digits32(kind == TOK_READ_ID ? id : kind == TOK_START ? sp : ep);
+    }
+    return n;
 }
 
 /* ---------------------------------------------------------------------- */
@@ -736,6 +742,21 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_offsets(RunParams rp) {
     if (i < rp.batch_units) rp.offsets[i] = rp.block_sums[blockIdx.x] + before + x - v;
 }
 
+
+/* pairs of 4-base groups each of the SUB lanes of a record takes: 2*SUB*T2 slots >= groups + 1 */
+__device__ __forceinline__ uint32_t pairs_per_lane(uint32_t L) { return (((L + 3u) >> 2) + 2u * SUB) / (2u * SUB); }
+
+/* Persistent warps.  A warp owns WARP_UNITS consecutive units at a time: it composes their
+ * FASTQ bytes in its private stage in shared memory and sends them off with one bulk async
+ * copy (TMA); only the sampling tables are shared by the CTA, so there is no CTA barrier in
+ * the loop.  A group of units whose bytes exceed the stage is cut into sub-tiles.
+ *   phase 1  sequence and quality lines: SUB lanes per record, the 8 first mates, then the 8
+ *            second mates (body_fast; byte stores for windows holding anything but A,C,G,T
+ *            and for replay)
+ *   phase 2  headers and the fixed newline / '+' bytes: two lanes per record, each writing
+ *            half of the header's tokens
+ * TK = table kind the fast path is specialised for. */
+constexpr uint32_t WARP_UNITS = 32 / SUB;
 struct TileUnit {      /* one unit of the current tile, in shared memory */
     UnitDesc d;
     uint32_t off[2];   /* stage offsets of its records */
@@ -747,30 +768,23 @@ __device__ __forceinline__ void record_positions(const UnitDesc &d, uint32_t r, 
     else if (r == 0) { sp = d.p0; ep = d.p0 + d.rl; }
     else { sp = d.p1 + d.rl; ep = d.p1; }
 }
+__host__ __device__ constexpr uint32_t warp_region_bytes(uint32_t stage_cap) {
+    return (uint32_t(WARP_UNITS * sizeof(TileUnit)) + STAGE_FRONT + stage_cap + 48u + 15u) & ~15u;
+}
 
-/* pairs of 4-base groups each of the SUB lanes of a record takes: 2*SUB*T2 slots >= groups + 1 */
-__device__ __forceinline__ uint32_t pairs_per_lane(uint32_t L) { return (((L + 3u) >> 2) + 2u * SUB) / (2u * SUB); }
-
-/* Persistent CTAs; each tile = up to `upt` consecutive units whose FASTQ bytes are composed
- * in shared memory and leave through one bulk async copy (TMA).  A tile whose bytes exceed
- * the stage is cut into sub-tiles.  Phase 1: sequence and quality lines (body_fast, or byte
- * stores for windows holding anything but A,C,G,T and for replay); the units are taken in
- * order of their work class (read length) so that the records a warp handles together need
- * the same number of steps.  Phase 2, after a CTA barrier: headers and the fixed newline /
- * '+' bytes, one thread per record.  TK = table kind the fast path is specialised for. */
 template <bool REPLAY, int TK>
-__global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tiles(RunParams rp, ReplayDev rd) {
+__global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_warps(RunParams rp, ReplayDev rd) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u : 1u);
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem + SM_TAB);
-    uint32_t *hist = reinterpret_cast<uint32_t *>(smem + SM_HIST);
-    TileUnit *tu = reinterpret_cast<TileUnit *>(smem + SM_TAB + ((tab_words * 4 + 15) & ~15u));
-    uint16_t *order = reinterpret_cast<uint16_t *>(tu + rp.upt);
-    uint8_t *stage = reinterpret_cast<uint8_t *>(order) + ((rp.upt * 2u + 15u) & ~15u) + STAGE_FRONT;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint8_t *region = smem + SM_TAB + ((tab_words * 4 + 15) & ~15u) + warp * warp_region_bytes(rp.stage_cap);
+    TileUnit *tu = reinterpret_cast<TileUnit *>(region);
+    uint8_t *stage = region + WARP_UNITS * sizeof(TileUnit) + STAGE_FRONT;
     const uint32_t base_s = uint32_t(__cvta_generic_to_shared(smem));
     const uint32_t tab_s = base_s + SM_TAB, dec2_s = base_s + SM_DEC2, stage_s = uint32_t(__cvta_generic_to_shared(stage));
-    for (uint32_t i = threadIdx.x; i < tab_words; i += FORMAT_THREADS) tab[i] = rp.phred.entries[i];
-    for (uint32_t b = threadIdx.x; b < 256; b += FORMAT_THREADS) {          /* 4 bases per byte -> ASCII, both strands */
+    for (uint32_t i = threadIdx.x; i < tab_words; i += blockDim.x) tab[i] = rp.phred.entries[i];
+    for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {               /* 4 bases per byte -> ASCII, both strands */
         uint32_t f = 0, r = 0;
         for (uint32_t j = 0; j < 4; ++j) {
             const uint32_t c = (b >> (2 * j)) & 3u;
@@ -782,49 +796,41 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tile
         if (b < 100) reinterpret_cast<uint16_t *>(smem + SM_DEC2)[b] = uint16_t(('0' + b / 10) | (('0' + b % 10) << 8));
         if (b < 10) { uint32_t p = 1; for (uint32_t k = 0; k < b; ++k) p *= 10u; reinterpret_cast<uint32_t *>(smem + SM_DEC2 + 200)[b] = p; }
     }
+    __syncthreads();
 
-    const uint32_t ntiles = (rp.batch_units + rp.upt - 1) / rp.upt;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sl = lane & (SUB - 1), sg = lane / SUB;
-    constexpr uint32_t UPW = 32 / SUB, NWARPS = FORMAT_THREADS / 32;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t t0 = tile * rp.upt, tn = min(rp.upt, rp.batch_units - t0);
+    const uint32_t sl = lane & (SUB - 1), sg = lane / SUB;
+    const uint32_t ntiles = (rp.batch_units + WARP_UNITS - 1) / WARP_UNITS;
+    for (uint32_t tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) {
+        const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
         for (uint32_t s0 = 0; s0 < tn;) {
             /* sub-tile = longest run of units from s0 that fits the stage */
-            const uint32_t u0 = t0 + s0;
-            const uint64_t tile_base = rp.offsets[u0];
+            const uint32_t u0 = t0 + s0, left = tn - s0;
+            const uint64_t off = lane <= left ? rp.offsets[u0 + lane] : 0;
+            const uint64_t tile_base = __shfl_sync(0xffffffffu, off, 0), next = __shfl_down_sync(0xffffffffu, off, 1);
             const uint32_t pad = uint32_t(tile_base & 15);
-            const bool fits = threadIdx.x < tn - s0 && rp.offsets[u0 + threadIdx.x + 1] - tile_base + pad <= rp.stage_cap;
-            if (threadIdx.x < N_CLASS) hist[threadIdx.x] = 0;
+            const uint32_t nu = __popc(__ballot_sync(0xffffffffu, lane < left && next - tile_base + pad <= rp.stage_cap));
+            const uint32_t total = uint32_t(__shfl_sync(0xffffffffu, off, nu) - tile_base);
             /* the previous bulk copy must have finished reading the stage before it is rewritten */
-            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            const uint32_t nu = __syncthreads_count(fits);
-            const uint32_t total = uint32_t(rp.offsets[u0 + nu] - tile_base);
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
             bool odd = false;                 /* this unit rules out the word-store paths for the sub-tile */
-            uint32_t cls = 0, rank = 0;
-            if (threadIdx.x < nu) {
-                TileUnit &t = tu[threadIdx.x];
-                t.d = rp.desc[u0 + threadIdx.x];
-                t.off[0] = pad + uint32_t(rp.offsets[u0 + threadIdx.x] - tile_base);
+            if (lane < nu) {
+                TileUnit &t = tu[lane];
+                t.d = rp.desc[u0 + lane];
+                t.off[0] = pad + uint32_t(off - tile_base);
                 t.off[1] = t.off[0] + t.d.H0 + 2u * t.d.L0 + 5u;
                 const bool two = t.d.flags & 4u;
                 odd = (t.d.flags & 8u) || t.d.H0 < 2u || t.d.L0 < 4u || (two && (t.d.H1 < 2u || t.d.L1 < 4u));
-                cls = min(pairs_per_lane(max(uint32_t(t.d.L0), two ? uint32_t(t.d.L1) : 0u)), N_CLASS - 1);
-                rank = atomicAdd(hist + cls, 1u);
             }
-            const bool words_ok = !__syncthreads_or(odd) && !REPLAY;
+            const bool words_ok = !__any_sync(0xffffffffu, odd) && !REPLAY;
             const bool hdr_fast = words_ok && rp.hdr_ntok != 0;
-            if (threadIdx.x < nu) {           /* counting sort by class: position = units of lower classes + rank in own class */
-                for (uint32_t k = 0; k < cls; ++k) rank += hist[k];
-                order[rank] = uint16_t(threadIdx.x);
-            }
-            __syncthreads();
+            __syncwarp();
 
-            /* ---- phase 1: sequence and quality lines ---- */
-            for (uint32_t c0 = warp * UPW; c0 < nu; c0 += NWARPS * UPW) {
-                const bool mine = c0 + sg < nu;
-                const uint32_t ul = order[min(c0 + sg, nu - 1)];
-                const TileUnit &t = tu[ul];
-                const uint64_t unit = rp.batch_begin + u0 + ul;
+            /* ---- phase 1: sequence and quality lines, sub-group sg takes unit sg ---- */
+            {
+                const bool mine = sg < nu;
+                const TileUnit &t = tu[min(sg, nu - 1)];
+                const uint64_t unit = rp.batch_begin + u0 + sg;
                 const uint32_t ulo = uint32_t(unit), uhi = uint32_t(unit >> 32);
 #pragma unroll
                 for (uint32_t mate = 0; mate < 2; ++mate) {
@@ -842,40 +848,55 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tile
                                                          (REPLAY ? rd.base_off[unit] : 0) + (mate ? t.d.rl : 0), sl, SUB);
                 }
             }
-            __syncthreads();
+            __syncwarp();
 
-            /* ---- phase 2: headers and the fixed bytes, one thread per record ---- */
-            for (uint32_t r = threadIdx.x; r < 2 * nu; r += FORMAT_THREADS) {
-                const TileUnit &t = tu[r >> 1]; const uint32_t mate = r & 1;
-                if (mate && !(t.d.flags & 4u)) continue;
+            /* ---- phase 2: headers and the fixed bytes; lanes 2r and 2r+1 share record r ---- */
+            {
+                const uint32_t r = lane >> 1, half = lane & 1u;
+                const TileUnit &t = tu[min(r >> 1, nu - 1)]; const uint32_t mate = r & 1u;
+                const bool have = (r >> 1) < nu && (mate == 0 || (t.d.flags & 4u));
                 uint64_t sp, ep; record_positions(t.d, mate, sp, ep);
                 const uint32_t id = rp.read_id_base + uint32_t(rp.batch_begin + u0 + (r >> 1));
                 const uint32_t H = mate ? t.d.H1 : t.d.H0, L = mate ? t.d.L1 : t.d.L0, rec_s = stage_s + t.off[mate];
                 const ContigHdr ch = rp.chdr[2 * t.d.contig + mate];
-                if (hdr_fast) header_fast(rp, dec2_s, rec_s, ch, id, uint32_t(sp), uint32_t(ep));
-                else {
+                ByteStream b{0, 0, 0};
+                if (hdr_fast && have) {
+                    /* first lane: newline that ends the previous record + tokens [0, ka); second lane: the rest + newline */
+                    const uint2 *tk = reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off);
+                    const uint32_t ka = (rp.hdr_ntok + 1u) >> 1;
+                    if (half == 0) {
+                        bs_open(b, rec_s - 1u); bs_put(b, '\n', 1);
+                        header_tokens(b, rp, dec2_s, tk, rp.hdr_kinds[0], 0, ka, id, uint32_t(sp), uint32_t(ep));
+                    } else {
+                        bs_open_blind(b, rec_s + header_prefix_len(tk, rp.hdr_kinds[0], ka, id, uint32_t(sp), uint32_t(ep)));
+                        header_tokens(b, rp, dec2_s, tk, rp.hdr_kinds[0] >> (4u * ka), ka, rp.hdr_ntok, id, uint32_t(sp), uint32_t(ep));
+                        bs_put(b, '\n', 1); bs_close(b);
+                    }
+                } else if (have && half == 0) {
                     emit_header(stage + t.off[mate], rp, ch, id, sp, ep);
                     sts8(rec_s + H, '\n');
                     if (t.off[mate] > pad) sts8(rec_s - 1u, '\n');             /* ends the previous record */
                 }
-                const uint32_t mid = rec_s + H + L + 1u;                       /* fastq.rs:61-69 */
-                sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n');
+                if (have && half == 1) { const uint32_t mid = rec_s + H + L + 1u; sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n'); }   /* fastq.rs:61-69 */
+                if (lane == 31 && total) sts8(stage_s + pad + total - 1u, '\n');
+                __syncwarp();
+                /* the first lane's last partial word shares its word with the second lane's first bytes, already in place */
+                if (hdr_fast && have && half == 0) bs_close(b);
             }
-            if (threadIdx.x == FORMAT_THREADS - 1 && total) sts8(stage_s + pad + total - 1u, '\n');
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
+            __syncwarp();
             /* stage[pad, pad+total) -> out[tile_base, +total): 16-byte aligned middle by TMA, edges by byte stores */
             const uint32_t head = min(total, (16 - pad) & 15), mid = (total - head) & ~15u, tail = total - head - mid;
-            if (threadIdx.x == 0 && mid) {
+            if (lane == 0 && mid) {
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rp.out + tile_base + head), "r"(stage_s + pad + head), "r"(mid) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-            if (threadIdx.x >= 32 && threadIdx.x < 32 + head) rp.out[tile_base + (threadIdx.x - 32)] = stage[pad + (threadIdx.x - 32)];
-            if (threadIdx.x >= 64 && threadIdx.x < 64 + tail) rp.out[tile_base + head + mid + (threadIdx.x - 64)] = stage[pad + head + mid + (threadIdx.x - 64)];
+            if (lane >= 1 && lane < 1 + head) rp.out[tile_base + (lane - 1)] = stage[pad + (lane - 1)];
+            if (lane >= 16 && lane < 16 + tail) rp.out[tile_base + head + mid + (lane - 16)] = stage[pad + head + mid + (lane - 16)];
             s0 += nu;
         }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 /* One CTA per unit, bytes written straight to global memory.  Used for long
@@ -883,7 +904,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_tile
  * not fit the shared-memory stage. */
 template <bool REPLAY>
 __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, ReplayDev rd) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u : 1u);
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
     for (uint32_t i = threadIdx.x; i < tab_words; i += DIRECT_THREADS) tab[i] = rp.phred.entries[i];

@@ -99,25 +99,25 @@ int fail(simmr_ctx *c, int code, const std::string &m) {
     } while (0)
 
 size_t table_bytes(const ProfileModel &m) { return m.phred_entries.size() * 4; }
-size_t tile_smem(const ProfileModel &m, uint32_t upt, uint32_t stage_cap) {
-    return SM_TAB + ((table_bytes(m) + 15) & ~size_t(15)) + size_t(upt) * sizeof(TileUnit) + ((upt * 2 + 15) & ~size_t(15)) + STAGE_FRONT + stage_cap + 48;
+size_t warps_smem(const ProfileModel &m, uint32_t warps, uint32_t stage_cap) {
+    return SM_TAB + ((table_bytes(m) + 15) & ~size_t(15)) + size_t(warps) * warp_region_bytes(stage_cap);
 }
 
 /* kernel instantiations: the fast path is specialised per table kind, replay is generic */
 using FormatKernel = void (*)(RunParams, ReplayDev);
-FormatKernel tiles_kernel(bool replay, uint32_t kind) {
-    if (replay) return k_format_tiles<true, PT_CONST>;
+FormatKernel warps_kernel(bool replay, uint32_t kind) {
+    if (replay) return k_format_warps<true, PT_CONST>;
     switch (kind) {
-    case PT_T64: return k_format_tiles<false, PT_T64>;
-    case PT_T32: return k_format_tiles<false, PT_T32>;
-    default: return k_format_tiles<false, PT_CONST>;
+    case PT_T64: return k_format_warps<false, PT_T64>;
+    case PT_T32: return k_format_warps<false, PT_T32>;
+    default: return k_format_warps<false, PT_CONST>;
     }
 }
 FormatKernel direct_kernel(bool replay) { return replay ? k_format_direct<true> : k_format_direct<false>; }
 
 struct Plan {      /* launch geometry for one run */
-    bool tiles = false;
-    uint32_t upt = 0, stage_cap = 0, max_unit_bytes = 0;
+    bool tiles = false;            /* warp-private stages in shared memory (short reads) vs one CTA per unit */
+    uint32_t stage_cap = 0, max_unit_bytes = 0, threads = 0;
     size_t smem = 0;
     int grid = 0;
 };
@@ -129,32 +129,32 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
     if (unit_bytes > 0xfff00000ull) return fail(ctx, SIMMR_E_LIMIT, "a unit's FASTQ bytes exceed 4 GiB");
     pl.max_unit_bytes = uint32_t(unit_bytes);
     const size_t tab = table_bytes(m);
-    const size_t smem_max = ctx->prop.sharedMemPerBlockOptin;
+    const size_t smem_max = ctx->prop.sharedMemPerBlockOptin, smem_sm = ctx->prop.sharedMemPerMultiprocessor;
     if (tab + 1024 > smem_max) return fail(ctx, SIMMR_E_LIMIT, "quality tables do not fit in shared memory");
     pl.tiles = !m.is_long;
     if (pl.tiles) {
-        /* The stage holds the typical bytes of `upt` units plus a margin; a tile that draws
-         * longer reads than that is cut into sub-tiles by the kernel.  It must hold the
-         * largest possible single unit. */
-        uint32_t upt = 32;
-        if (const char *e = getenv("SIMMR_UPT")) upt = uint32_t(std::max(1, std::min(128, atoi(e))));
+        /* A warp's stage holds the typical bytes of its WARP_UNITS units plus a margin (a group that
+         * draws longer reads is cut into sub-tiles by the kernel) and at least the largest single unit. */
         const uint64_t typical = 2ull * (ctx->plan.hdr_cap + 2ull * m.nominal_read_len + 5);
-        auto cap_for = [&](uint32_t n) { return uint32_t(std::max<uint64_t>(unit_bytes + 32, n * typical * 27 / 25 + 64)); };
-        while (upt > 1 && tile_smem(m, upt, cap_for(upt)) > smem_max) upt /= 2;
-        const uint32_t cap = cap_for(upt);
-        if (tile_smem(m, upt, cap) > smem_max) pl.tiles = false;   /* a single unit does not fit: direct path */
-        else { pl.upt = upt; pl.stage_cap = cap; pl.smem = tile_smem(m, upt, cap); }
+        const uint64_t cap = (std::max<uint64_t>(unit_bytes + 32, WARP_UNITS * typical * 23 / 20 + 64) + 15) & ~15ull;
+        /* warps per CTA: as many as keep three CTAs on an SM, so that the shared tables cost little */
+        uint32_t warps = FORMAT_THREADS / 32;
+        if (const char *e = getenv("SIMMR_WARPS")) warps = uint32_t(std::max(1, std::min(FORMAT_THREADS / 32, atoi(e))));
+        while (warps > 1 && (warps_smem(m, warps, uint32_t(cap)) + 1024) * FORMAT_MIN_CTAS > smem_sm && warps_smem(m, warps / 2, uint32_t(cap)) >= tab + 4096) warps /= 2;
+        while (warps > 1 && warps_smem(m, warps, uint32_t(cap)) > smem_max) warps /= 2;
+        if (cap > 0x7fffffffull || warps_smem(m, warps, uint32_t(cap)) > smem_max) pl.tiles = false;   /* a single unit does not fit: direct path */
+        else { pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.smem = warps_smem(m, warps, uint32_t(cap)); }
     }
-    if (!pl.tiles) pl.smem = tab;
+    if (!pl.tiles) { pl.smem = tab; pl.threads = DIRECT_THREADS; }
     int occ = 0;
-    FormatKernel k = pl.tiles ? tiles_kernel(replay, m.phred_kind) : direct_kernel(replay);
+    FormatKernel k = pl.tiles ? warps_kernel(replay, m.phred_kind) : direct_kernel(replay);
     CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, pl.tiles ? FORMAT_THREADS : DIRECT_THREADS, pl.smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem);
     CU(e);
     if (occ < 1) return fail(ctx, SIMMR_E_LIMIT, "format kernel does not fit on an SM");
     pl.grid = occ * ctx->prop.multiProcessorCount;
     if (const char *e = getenv("SIMMR_GRID")) pl.grid = std::max(1, atoi(e));
-    if (getenv("SIMMR_DEBUG_SYNC")) fprintf(stderr, "[simmr] tiles=%d upt=%u cap=%u smem=%zu occ=%d grid=%d\n", int(pl.tiles), pl.upt, pl.stage_cap, pl.smem, occ, pl.grid);
+    if (getenv("SIMMR_DEBUG_SYNC")) fprintf(stderr, "[simmr] tiles=%d threads=%u cap=%u smem=%zu occ=%d grid=%d\n", int(pl.tiles), pl.threads, pl.stage_cap, pl.smem, occ, pl.grid);
     return SIMMR_OK;
 }
 
@@ -205,7 +205,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.sizes = ctx->d_sizes.as<uint32_t>(); rp.offsets = ctx->d_offsets.as<uint64_t>();
     rp.desc = ctx->d_desc.as<UnitDesc>();
     rp.block_sums = ctx->d_block_sums.as<uint64_t>(); rp.counters = ctx->d_counters.as<unsigned long long>();
-    rp.upt = pl.upt; rp.stage_cap = pl.stage_cap;
+    rp.stage_cap = pl.stage_cap;
 }
 
 /* The batch pipeline shared by simulate and replay. */
@@ -262,12 +262,12 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         if (getenv("SIMMR_DEBUG_SYNC")) { cudaError_t e_ = cudaStreamSynchronize(ctx->compute); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("scan kernels: ") + cudaGetErrorString(e_)); }
         CU(cudaEventRecord(ev_f0, ctx->compute));
         if (pl.tiles) {
-            const uint32_t ntiles = (n + pl.upt - 1) / pl.upt;
-            const int grid = int(std::min<uint32_t>(ntiles, uint32_t(pl.grid)));
-            tiles_kernel(replay, ctx->model.phred_kind)<<<grid, FORMAT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
+            const uint32_t wpc = pl.threads / 32, nctas = ((n + WARP_UNITS - 1) / WARP_UNITS + wpc - 1) / wpc;
+            const int grid = int(std::min<uint32_t>(nctas, uint32_t(pl.grid)));
+            warps_kernel(replay, ctx->model.phred_kind)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
         } else {
             const int grid = int(std::min<uint32_t>(n, uint32_t(pl.grid)));
-            direct_kernel(replay)<<<grid, DIRECT_THREADS, pl.smem, ctx->compute>>>(rp, rd);
+            direct_kernel(replay)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
         }
         CU(cudaGetLastError());
         CU(cudaEventRecord(ev_f1, ctx->compute));
