@@ -160,6 +160,12 @@ int  simmr_simulate(simmr_ctx *ctx, const uint64_t *reads_per_genome, const simm
 int  simmr_replay(simmr_ctx *ctx, const simmr_draws *draws, const simmr_run_opts *opts,
                   simmr_sink_fn sink, void *user);
 uint64_t simmr_total_units(const simmr_ctx *ctx, const uint64_t *reads_per_genome);
+/* FASTQ bytes and records the unit range of `opts` will produce (needs a seed): runs the
+ * geometry kernel only.  This is the per-shard count of the host-side exchange that gives
+ * every GPU its offset in the single output file (the reference appends genome after
+ * genome, main.rs:201-206). */
+int  simmr_measure(simmr_ctx *ctx, const uint64_t *reads_per_genome, const simmr_run_opts *opts,
+                   uint64_t *bytes, uint64_t *records);
 int  simmr_stats_get(const simmr_ctx *ctx, simmr_stats *out);
 
 /* ---- host-side I/O of the same path (genome.rs, files.rs, encoding.rs) -- */

@@ -395,6 +395,14 @@ class Engine:
         self._run(N.lib().simmr_simulate, _p(r, N.u64p), o, sink)
         return self.stats()
 
+    def measure(self, reads_per_genome, seed, header_format=None, unit_begin=0, unit_end=0, read_id_base=0):
+        """simmr_measure: (FASTQ bytes, records) a unit range will produce; geometry kernel only."""
+        r = np.ascontiguousarray(reads_per_genome, np.uint64)
+        o = self._opts(seed, header_format, unit_begin, unit_end, read_id_base, 0)
+        nb, nr = C.c_uint64(), C.c_uint64()
+        _check(N.lib().simmr_measure(self._ctx, _p(r, N.u64p), C.byref(o), C.byref(nb), C.byref(nr)), self._ctx)
+        return nb.value, nr.value
+
     def simulate_bytes(self, reads_per_genome, seed=None, **kw):
         chunks = []
         self.simulate(reads_per_genome, seed, sink=lambda a, f, n: chunks.append(a.tobytes()), **kw)

@@ -9,7 +9,7 @@
 
 using namespace simmr;
 
-namespace { thread_local std::string g_err; int flunk(int code, const std::string &m) { g_err = m; return code; } }
+namespace { int flunk(int code, const std::string &m) { last_error_slot() = m; return code; } }
 
 struct simmr_genome_builder { GenomeStore store; };
 

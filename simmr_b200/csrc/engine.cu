@@ -19,7 +19,6 @@
 using namespace simmr;
 
 namespace {
-thread_local std::string g_last_error;
 
 struct DevMem {    /* owning device allocation */
     void *p = nullptr; size_t bytes = 0;
@@ -88,7 +87,7 @@ struct simmr_ctx {
 namespace {
 
 int fail(simmr_ctx *c, int code, const std::string &m) {
-    g_last_error = m;
+    last_error_slot() = m;
     if (c) c->err = m;
     return code;
 }
@@ -210,10 +209,32 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
 
 /* The batch pipeline shared by simulate and replay. */
 int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uint64_t ue, uint64_t seed,
-              const simmr_run_opts *opts, simmr_sink_fn sink, void *user) {
+              const simmr_run_opts *opts, simmr_sink_fn sink, void *user, bool measure_only = false) {
     Plan pl;
     int rc = make_plan(ctx, replay, pl);
     if (rc) return rc;
+    if (measure_only) {      /* geometry + record sizes only: what the units would occupy in the FASTQ stream */
+        const uint64_t batch = std::min<uint64_t>(ue - ub, 1ull << 24);
+        CU(ctx->d_sizes.reserve(batch * 4)); CU(ctx->d_desc.reserve(batch * sizeof(UnitDesc)));
+        CU(ctx->d_block_sums.reserve(((batch + SIZES_THREADS - 1) / SIZES_THREADS) * 8));
+        CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
+        RunParams rp; fill_params(ctx, rp, seed, opts ? opts->read_id_base : 0, pl);
+        simmr_stats st{};
+        for (uint64_t u = ub; u < ue; u += batch) {
+            const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
+            rp.batch_begin = u; rp.batch_units = n;
+            k_unit_sizes<false><<<(n + SIZES_THREADS - 1) / SIZES_THREADS, SIZES_THREADS, 0, ctx->compute>>>(rp, rd);
+            ++st.kernel_launches;
+        }
+        CU(cudaGetLastError());
+        unsigned long long ctr[8];
+        CU(cudaMemcpyAsync(ctr, ctx->d_counters.p, sizeof ctr, cudaMemcpyDeviceToHost, ctx->compute));
+        CU(cudaStreamSynchronize(ctx->compute));
+        st.units = ue - ub; st.clamped = ctr[0]; st.algorithmic_bytes = ctr[1]; st.bases = ctr[2]; st.records = ctr[3];
+        st.bytes = ctr[1] - ctr[2];
+        ctx->stats = st;
+        return SIMMR_OK;
+    }
     const uint64_t target_bytes = sink ? (256ull << 20) : (2048ull << 20);
     uint64_t batch = opts && opts->batch_units ? opts->batch_units : std::max<uint64_t>(1, target_bytes / pl.max_unit_bytes);
     batch = std::min<uint64_t>(batch, std::max<uint64_t>(1, ue - ub));
@@ -327,7 +348,7 @@ std::vector<uint64_t> unit_prefix(const simmr_ctx *ctx, const uint64_t *reads) {
 
 extern "C" {
 
-const char *simmr_last_error(const simmr_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+const char *simmr_last_error(const simmr_ctx *ctx) { return ctx ? ctx->err.c_str() : last_error_slot().c_str(); }
 const char *simmr_version(void) { return "simmr_b200 0.1 (sm_100a)"; }
 
 int simmr_ctx_create(int device, simmr_ctx **out) {
@@ -459,6 +480,25 @@ int simmr_simulate(simmr_ctx *ctx, const uint64_t *reads, const simmr_run_opts *
     if (ub == ue) return SIMMR_OK;
     ReplayDev rd{};
     return run_units(ctx, false, rd, ub, ue, seed, opts, sink, user);
+}
+
+int simmr_measure(simmr_ctx *ctx, const uint64_t *reads, const simmr_run_opts *opts, uint64_t *bytes, uint64_t *records) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!reads || !opts || !opts->has_seed) return fail(ctx, SIMMR_E_INVALID, "measuring a shard needs reads_per_genome and a seed");
+    CU(cudaSetDevice(ctx->device));
+    rc = ensure_headers(ctx, opts->header_format);
+    if (rc) return rc;
+    const std::vector<uint64_t> us = unit_prefix(ctx, reads);
+    CU(ctx->d_unit_start.upload(us.data(), us.size(), ctx->compute));
+    uint64_t ub = opts->unit_begin, ue = opts->unit_end;
+    if (ub == 0 && ue == 0) ue = us.back();
+    if (ub > ue || ue > us.back()) return fail(ctx, SIMMR_E_INVALID, "unit range outside the run");
+    ctx->stats = simmr_stats{};
+    if (ub < ue) { ReplayDev rd{}; rc = run_units(ctx, false, rd, ub, ue, opts->seed, opts, nullptr, nullptr, true); if (rc) return rc; }
+    if (bytes) *bytes = ctx->stats.bytes;
+    if (records) *records = ctx->stats.records;
+    return SIMMR_OK;
 }
 
 int simmr_replay(simmr_ctx *ctx, const simmr_draws *d, const simmr_run_opts *opts, simmr_sink_fn sink, void *user) {

@@ -15,6 +15,8 @@
 
 namespace simmr {
 
+std::string &last_error_slot() { thread_local std::string slot; return slot; }
+
 const char *const DEFAULT_HEADER_FORMAT =
     "@{:read_id:}|{:genome_id:}/{:pair:} metadata:sid={:sequence_id:}|sp={:start_position:}|ep={:end_position:}|rc={:reverse_complement:}";
 

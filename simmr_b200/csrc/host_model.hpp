@@ -97,4 +97,7 @@ int compile_headers(const simmr_genome_set &g, const char *fmt, HeaderPlan &plan
 
 void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
+/* message behind simmr_last_error(NULL): one slot per host thread, shared by every entry point */
+std::string &last_error_slot();
+
 }  // namespace simmr

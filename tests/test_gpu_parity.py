@@ -158,3 +158,90 @@ def test_medium_scale_minimal_short(engine):
     """~1.2 M records through several batches, compared byte for byte."""
     gs = H.synth_genomes(6, (1, 6), (20000, 120000), seed=77)
     check_native(engine, gs, S.MinimalShortErrorProfile(), [200000] * 6, 2024, batch_units=150001)
+
+
+def test_measure_gives_shard_offsets(engine):
+    """simmr_measure (geometry kernel only) = the per-shard byte/record counts of the host-side exchange."""
+    gs = H.synth_genomes(4, (1, 3), (3000, 8000), seed=9)
+    prof = S.MinimalShortErrorProfile()
+    reads = [1500, 700, 0, 2200]
+    whole = check_native(engine, gs, prof, reads, 5)
+    total = engine.total_units(reads)
+    assert engine.measure(reads, 5) == (len(whole), 2 * total)
+    at = 0
+    from simmr_b200 import sharding
+    for k in range(3):
+        ub, ue = sharding.shard_range(total, k, 3)
+        nb, nr = engine.measure(reads, 5, unit_begin=ub, unit_end=ue)
+        assert nr == 2 * (ue - ub)
+        assert engine.simulate_bytes(reads, 5, unit_begin=ub, unit_end=ue) == whole[at:at + nb]
+        at += nb
+    assert at == len(whole)
+
+
+def _write_fasta(path, contigs):
+    with open(path, "wb") as f:
+        for cid, seq in contigs:
+            f.write(b">" + cid + b"\n")
+            s = bytes(seq)
+            for i in range(0, len(s), 80):
+                f.write(s[i:i + 80] + b"\n")
+
+
+@pytest.mark.parametrize("mode", ["tsv-custom", "list-uniform", "long"])
+def test_cli_binary_end_to_end(engine, tmp_path, mode):
+    """The `simmr` binary (flags of cli.rs:93-220, flow of main.rs:20-266) against the oracle: FASTQ bytes
+    and <output>.tsv, through FASTA files, a genome file, the contig filter and the abundance profile."""
+    import os
+    import subprocess
+    rng = np.random.default_rng(12)
+    n_g = 3
+    lens = (25000, 60000) if mode == "long" else (400, 5000)
+    paths, uuids, ab = [], [], [0.5, 0.3, 0.2]
+    for g in range(n_g):
+        contigs = [(f"g{g}_c{c} some text".encode(), np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(rng.integers(*lens)))])
+                   for c in range(3)]
+        if mode != "long":
+            contigs.append((b"tiny", np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 200)]))      # dropped by the filter (main.rs:124)
+        p = str(tmp_path / f"g{g}.fna")
+        _write_fasta(p, contigs)
+        paths.append(p)
+        uuids.append(f"uuid-{g:02d}")
+    out = str(tmp_path / "reads.fq")
+    exe = os.path.join(os.path.dirname(S._native.LIB_PATH), "simmr")
+    if mode == "tsv-custom":
+        gf = tmp_path / "genomes.tsv"
+        gf.write_text("uuid\tabundance\tpath\n" + "".join(f"{u}\t{a}\t{p}\n" for u, a, p in zip(uuids, ab, paths)))
+        prof, aprof = S.MinimalShortErrorProfile(100, 220, 25), S.CustomAbundanceProfile(ab, size_adjusted=True)
+        cmd = [exe, "--genome-file", str(gf), "--output", out, "--num-reads", "3001", "--seed", "77", "--error-profile", "minimal-short",
+               "--read-length", "100", "--insert-size", "220", "--mean-phred-score", "25", "--abundance-profile", "custom", "--size-adjusted"]
+        fmt = None
+    elif mode == "list-uniform":
+        gf = tmp_path / "genomes.txt"
+        gf.write_text("".join(p + "\n" for p in paths))
+        prof, aprof = S.PerfectShortErrorProfile(150, 150), S.UniformAbundanceProfile()
+        fmt = "@{:read_id:}/{:pair:} {:genome_id:}"
+        cmd = [exe, "--genome-file", str(gf), "--output", out, "--num-reads=2000", "--seed", "5", "--read-header-format", fmt]
+        uuids = None
+    else:
+        prof, aprof = S.MinimalLongErrorProfile(20), S.ExactAbundanceProfile()
+        cmd = [exe] + sum([["--genome", p] for p in paths], []) + ["--output", out, "--num-reads", "25", "--seed", "9", "--error-profile",
+                                                                      "minimal-long", "--mean-phred-score", "20", "--abundance-profile", "exact"]
+        fmt, uuids = None, None
+    open(out, "w").write("stale")                       # existing outputs are replaced (main.rs:191-198)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    tsv = [ln.split("\t") for ln in open(out + ".tsv").read().splitlines()]
+    assert tsv[0] == ["genome_id", "filepath", "num_reads", "abundance"] and [t[1] for t in tsv[1:]] == paths
+    got_ids = [t[0] for t in tsv[1:]]
+    gs, kept = S.GenomeSet.from_fasta(paths, uuids=uuids if uuids else got_ids, min_size=prof.minimum_genome_size())
+    assert kept.all() and (uuids is None or got_ids == uuids)
+    reads, abund = aprof.reads_per_genome({"tsv-custom": 3001, "list-uniform": 2000, "long": 25}[mode], gs.genome_sizes)
+    assert [int(t[2]) for t in tsv[1:]] == reads.tolist()
+    assert [t[3] for t in tsv[1:]] == [po.format_f64(a) for a in abund]
+    seed = {"tsv-custom": 77, "list-uniform": 5, "long": 9}[mode]
+    want = po.simulate(po.Genomes.from_set(gs), H.oracle_profile(prof), reads, seed, header_format=fmt)
+    got = open(out, "rb").read()
+    assert got == want, first_diff(got, want)
+    bad = subprocess.run([exe, "--genome", paths[0], "--output", out, "--error-profile", "nope"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "invalid value" in bad.stderr
