@@ -578,10 +578,6 @@ __device__ __forceinline__ void bs_decimal(ByteStream &b, uint32_t dec2_s, uint3
     bs_put(b, r2 >> s, d - 8u);
 }
 
-__device__ __forceinline__ void bs_open_blind(ByteStream &b, uint32_t at) {   /* the bytes before `at` in its word are written later by someone else */
-    b.addr = at & ~3u; b.fill = at & 3u; b.carry = 0u;
-}
-
 /* Tokens [i0, i1) of a record's header template into the stream (kinds = the 4-bit token kinds
  * starting at token i0, the same for every contig; tk = this (contig, mate)'s token list). */
 __device__ __forceinline__ void header_tokens(ByteStream &b, const RunParams &rp, uint32_t dec2_s, const uint2 *tk, uint64_t kinds,
@@ -599,17 +595,6 @@ __device__ __forceinline__ void header_tokens(ByteStream &b, const RunParams &rp
         } else bs_decimal(b, dec2_s, kind == TOK_READ_ID ? id : kind == TOK_START ? sp : ep);
     }
 }
-/* bytes tokens [0, i1) produce */
-__device__ __forceinline__ uint32_t header_prefix_len(const uint2 *tk, uint64_t kinds, uint32_t i1, uint32_t id, uint32_t sp, uint32_t ep) {
-    uint32_t n = 0;
-#pragma unroll 1
-    for (uint32_t i = 0; i < i1; ++i, kinds >>= 4) {
-        const uint32_t kind = uint32_t(kinds) & 15u;
-        n += kind == TOK_LIT ? (__ldg(tk + i).y & 0xffffu) : dec_digits32(kind == TOK_READ_ID ? id : kind == TOK_START ? sp : ep);
-    }
-    return n;
-}
-
 /* ---------------------------------------------------------------------- */
 /* kernels                                                                  */
 /* ---------------------------------------------------------------------- */
@@ -753,8 +738,7 @@ __device__ __forceinline__ uint32_t pairs_per_lane(uint32_t L) { return (((L + 3
  *   phase 1  sequence and quality lines: SUB lanes per record, the 8 first mates, then the 8
  *            second mates (body_fast; byte stores for windows holding anything but A,C,G,T
  *            and for replay)
- *   phase 2  headers and the fixed newline / '+' bytes: two lanes per record, each writing
- *            half of the header's tokens
+ *   phase 2  headers and the fixed newline / '+' bytes: one lane per record
  * TK = table kind the fast path is specialised for. */
 constexpr uint32_t WARP_UNITS = 32 / SUB;
 struct TileUnit {      /* one unit of the current tile, in shared memory */
@@ -850,39 +834,29 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_warp
             }
             __syncwarp();
 
-            /* ---- phase 2: headers and the fixed bytes; lanes 2r and 2r+1 share record r ---- */
-            {
-                const uint32_t r = lane >> 1, half = lane & 1u;
-                const TileUnit &t = tu[min(r >> 1, nu - 1)]; const uint32_t mate = r & 1u;
-                const bool have = (r >> 1) < nu && (mate == 0 || (t.d.flags & 4u));
-                uint64_t sp, ep; record_positions(t.d, mate, sp, ep);
-                const uint32_t id = rp.read_id_base + uint32_t(rp.batch_begin + u0 + (r >> 1));
-                const uint32_t H = mate ? t.d.H1 : t.d.H0, L = mate ? t.d.L1 : t.d.L0, rec_s = stage_s + t.off[mate];
-                const ContigHdr ch = rp.chdr[2 * t.d.contig + mate];
-                ByteStream b{0, 0, 0};
-                if (hdr_fast && have) {
-                    /* first lane: newline that ends the previous record + tokens [0, ka); second lane: the rest + newline */
-                    const uint2 *tk = reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off);
-                    const uint32_t ka = (rp.hdr_ntok + 1u) >> 1;
-                    if (half == 0) {
-                        bs_open(b, rec_s - 1u); bs_put(b, '\n', 1);
-                        header_tokens(b, rp, dec2_s, tk, rp.hdr_kinds[0], 0, ka, id, uint32_t(sp), uint32_t(ep));
-                    } else {
-                        bs_open_blind(b, rec_s + header_prefix_len(tk, rp.hdr_kinds[0], ka, id, uint32_t(sp), uint32_t(ep)));
-                        header_tokens(b, rp, dec2_s, tk, rp.hdr_kinds[0] >> (4u * ka), ka, rp.hdr_ntok, id, uint32_t(sp), uint32_t(ep));
+            /* ---- phase 2: headers and the fixed bytes, one lane per record ---- */
+            if (lane < 2 * nu) {
+                const TileUnit &t = tu[lane >> 1]; const uint32_t mate = lane & 1u;
+                if (mate == 0 || (t.d.flags & 4u)) {
+                    uint64_t sp, ep; record_positions(t.d, mate, sp, ep);
+                    const uint32_t id = rp.read_id_base + uint32_t(rp.batch_begin + u0 + (lane >> 1));
+                    const uint32_t H = mate ? t.d.H1 : t.d.H0, L = mate ? t.d.L1 : t.d.L0, rec_s = stage_s + t.off[mate];
+                    const ContigHdr ch = rp.chdr[2 * t.d.contig + mate];
+                    if (hdr_fast) {      /* newline that ends the previous record, the tokens, newline */
+                        ByteStream b; bs_open(b, rec_s - 1u); bs_put(b, '\n', 1);
+                        header_tokens(b, rp, dec2_s, reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off), rp.hdr_kinds[0], 0, rp.hdr_ntok,
+                                      id, uint32_t(sp), uint32_t(ep));
                         bs_put(b, '\n', 1); bs_close(b);
+                    } else {
+                        emit_header(stage + t.off[mate], rp, ch, id, sp, ep);
+                        sts8(rec_s + H, '\n');
+                        if (t.off[mate] > pad) sts8(rec_s - 1u, '\n');         /* ends the previous record */
                     }
-                } else if (have && half == 0) {
-                    emit_header(stage + t.off[mate], rp, ch, id, sp, ep);
-                    sts8(rec_s + H, '\n');
-                    if (t.off[mate] > pad) sts8(rec_s - 1u, '\n');             /* ends the previous record */
+                    const uint32_t mid = rec_s + H + L + 1u;                   /* fastq.rs:61-69 */
+                    sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n');
                 }
-                if (have && half == 1) { const uint32_t mid = rec_s + H + L + 1u; sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n'); }   /* fastq.rs:61-69 */
-                if (lane == 31 && total) sts8(stage_s + pad + total - 1u, '\n');
-                __syncwarp();
-                /* the first lane's last partial word shares its word with the second lane's first bytes, already in place */
-                if (hdr_fast && have && half == 0) bs_close(b);
             }
+            if (lane == 31 && total) sts8(stage_s + pad + total - 1u, '\n');
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             /* stage[pad, pad+total) -> out[tile_base, +total): 16-byte aligned middle by TMA, edges by byte stores */
