@@ -193,6 +193,26 @@ struct Philox {
         block(blk, stream, (uint32_t)unit, (uint32_t)(unit >> 32), out);
     }
 };
+/* Per-base words of native mode.  A read's 4-base groups are cut into four runs of
+ * rho = 2*ceil((groups+1)/8) groups.  Inside run j, base i takes the next output of chain (i & 3);
+ * the four chains are MWC64X generators (D. B. Thomas: x' = lo(A*x + c), c' = hi(A*x + c), output
+ * x ^ c, A = 4294883355) seeded from the two Philox blocks (2j, 2j+1) of the read's stream. */
+struct BaseWords {
+    uint32_t x[4], c[4];
+    static uint32_t run_groups(uint64_t L) { const uint64_t ng = (L + 3) >> 2; return (uint32_t)(2 * ((ng + 8) >> 3)); }
+    void seed(const Philox &ph, uint64_t unit, uint32_t stream, uint32_t run) {
+        for (uint32_t h = 0; h < 2; h++) {
+            uint32_t w[4]; ph.at(unit, stream, 2 * run + h, w);
+            x[2 * h] = w[0]; c[2 * h] = (w[1] >> 2) + 1; x[2 * h + 1] = w[2]; c[2 * h + 1] = (w[3] >> 2) + 1;
+        }
+    }
+    uint32_t next(uint32_t j) {
+        const uint32_t r = x[j] ^ c[j];
+        const uint64_t t = (uint64_t)x[j] * 4294883355u + c[j];
+        x[j] = (uint32_t)t; c[j] = (uint32_t)(t >> 32);
+        return r;
+    }
+};
 inline uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
@@ -809,13 +829,14 @@ bool native_geometry(const GenomeView &gv, const Profile &p, const UnitMap &um, 
 void native_read(const Profile &p, const Philox &ph, uint64_t u, uint32_t stream, const uint8_t *src, uint64_t L,
                  std::vector<uint8_t> &seq, std::vector<uint8_t> &qual, orc_stats &st) {
     seq.resize(L); qual.resize(L);
-    uint32_t w[4] = {0, 0, 0, 0};
+    BaseWords bw{};
+    const uint32_t rho = BaseWords::run_groups(L);
     for (uint64_t i = 0; i < L; i++) {
         uint8_t q; uint32_t m;
         if (p.phred.kind == 0) { q = p.phred.const_q; m = 0; }
         else {
-            if ((i & 3) == 0) ph.at(u, stream, (uint32_t)(i >> 2), w);
-            sample_phred(p.phred, (uint32_t)std::min<uint64_t>(i, 0xffffffffu), w[i & 3], q, m);
+            if ((i & 3) == 0 && (i >> 2) % rho == 0) bw.seed(ph, u, stream, (uint32_t)((i >> 2) / rho));
+            sample_phred(p.phred, (uint32_t)std::min<uint64_t>(i, 0xffffffffu), bw.next((uint32_t)(i & 3)), q, m);
         }
         qual[i] = q;
         uint8_t b = src[i];

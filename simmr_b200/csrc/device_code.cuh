@@ -68,7 +68,7 @@ constexpr int SIZES_THREADS = 256;
 constexpr int FORMAT_THREADS = 256;   /* threads of a format CTA (8 warps, each with a private stage) */
 constexpr int FORMAT_MIN_CTAS = 3;    /* occupancy target -> register cap of 80          */
 constexpr int DIRECT_THREADS = 256;
-constexpr int SUB = 4;                /* lanes that share one record in the tile kernel  */
+constexpr int SUB = 4;                /* lanes that share one record = runs of the per-base word schedule */
 constexpr uint32_t PACK_PAD_WORDS = 1024; /* readable words past the end of `packed`     */
 /* shared-memory layout of a tile CTA (byte offsets from the 1024-aligned base) */
 constexpr uint32_t SM_LUT_FWD = 0, SM_LUT_RC = 1024, SM_DEC2 = 2048, SM_TAB = 2304;
@@ -100,6 +100,24 @@ __device__ __forceinline__ Philox4 draw(const RunParams &rp, uint64_t unit, uint
     return philox(rp.rk, blk, stream, uint32_t(unit), uint32_t(unit >> 32));
 }
 __device__ __forceinline__ uint64_t pair64(uint32_t lo, uint32_t hi) { return uint64_t(lo) | (uint64_t(hi) << 32); }
+
+/* Per-base words: a read's 4-base groups are cut into four runs of run_groups(L)
+ * groups; inside run j, base i takes the next output of chain i & 3.  The chains are MWC64X
+ * generators (D. B. Thomas: x' = lo(A*x + c), c' = hi(A*x + c), output x ^ c) seeded from the two
+ * Philox blocks (2j, 2j+1) of the read's stream: one multiply-add per word on the multiply pipe. */
+struct Mwc4 { uint32_t x[4], c[4]; };
+__device__ __forceinline__ uint32_t run_groups(uint32_t L) { return 2u * ((((L + 3u) >> 2) + 8u) >> 3); }
+__device__ __forceinline__ void mwc_seed(const RunParams &rp, Mwc4 &m, uint32_t run, uint32_t stream, uint32_t ulo, uint32_t uhi) {
+    const Philox4 a = philox(rp.rk, 2u * run, stream, ulo, uhi), b = philox(rp.rk, 2u * run + 1u, stream, ulo, uhi);
+    m.x[0] = a.x; m.c[0] = (a.y >> 2) + 1u; m.x[1] = a.z; m.c[1] = (a.w >> 2) + 1u;
+    m.x[2] = b.x; m.c[2] = (b.y >> 2) + 1u; m.x[3] = b.z; m.c[3] = (b.w >> 2) + 1u;
+}
+__device__ __forceinline__ uint32_t mwc_next(uint32_t &x, uint32_t &c) {
+    const uint32_t r = x ^ c;
+    const uint64_t t = uint64_t(x) * 4294883355u + c;
+    x = uint32_t(t); c = uint32_t(t >> 32);
+    return r;
+}
 
 /* ---------------------------------------------------------------------- */
 /* samplers                                                                 */
@@ -389,22 +407,26 @@ __device__ __forceinline__ void emit_body_generic(const RunParams &rp, const Rep
     if (PUNCT && thr == 0) { dst[0] = '\n'; dst[L + 1] = '\n'; dst[L + 2] = '+'; dst[L + 3] = '\n'; dst[2 * L + 4] = '\n'; }   /* fastq.rs:61-69 */
     const uint8_t *src = rp.bases + a;
     const bool rc = mate != 0;
-    for (uint32_t g = thr; g * 4 < L; g += nthr) {
-        Philox4 w{};
-        if (!REPLAY && rp.phred.kind != PT_CONST) w = draw(rp, unit, 1 + mate, g);
-        const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
+    const uint32_t NG = (L + 3u) >> 2;
+    /* replay: groups dealt round-robin; native: one thread per run of the per-base word schedule */
+    const uint32_t rho = REPLAY ? 1u : run_groups(L);
+    for (uint32_t run = thr; run * rho < NG; run += nthr) {
+        Mwc4 w{};
+        if (!REPLAY && rp.phred.kind != PT_CONST) mwc_seed(rp, w, run, 1 + mate, uint32_t(unit), uint32_t(unit >> 32));
+        for (uint32_t g = run * rho; g < min(NG, (run + 1u) * rho); ++g) {
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) {
-            const uint32_t i = 4 * g + j;
-            if (i >= L) break;
-            uint32_t qc, m;
-            if (REPLAY) { uint32_t q; replay_base(rp, rd, slot0 + i, i, q, m); qc = (q + 33) & 0xffu; }   /* util.rs:46-50 */
-            else if (rp.phred.kind == PT_CONST) { qc = (rp.phred.const_q + 33) & 0xffu; m = 0; }
-            else native_base(rp, tab, wv[j], i, qc, m);
-            uint8_t b = __ldg(src + i);
-            if (m) b = REPLAY ? substitute(b, m - 1) : substitute_native(b, m);
-            qual[i] = uint8_t(qc);
-            if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;
+            for (uint32_t j = 0; j < 4; ++j) {
+                const uint32_t i = 4 * g + j;
+                if (i >= L) break;
+                uint32_t qc, m;
+                if (REPLAY) { uint32_t q; replay_base(rp, rd, slot0 + i, i, q, m); qc = (q + 33) & 0xffu; }   /* util.rs:46-50 */
+                else if (rp.phred.kind == PT_CONST) { qc = (rp.phred.const_q + 33) & 0xffu; m = 0; }
+                else native_base(rp, tab, mwc_next(w.x[j], w.c[j]), i, qc, m);
+                uint8_t b = __ldg(src + i);
+                if (m) b = REPLAY ? substitute(b, m - 1) : substitute_native(b, m);
+                qual[i] = uint8_t(qc);
+                if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;
+            }
         }
     }
 }
@@ -430,10 +452,9 @@ __device__ __forceinline__ uint32_t lds32m(uint32_t addr) { uint32_t v; asm vola
 __device__ __forceinline__ uint32_t lds16(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ uint32_t mulhi_lo(uint32_t a, uint32_t b, uint32_t &lo) { const uint64_t p = uint64_t(a) * b; lo = uint32_t(p); return uint32_t(p >> 32); }
 
-/* quality characters (+33 applied) and mutation codes of bases 4g..4g+3 from one Philox block */
+/* quality characters (+33 applied) and mutation codes of bases 4g..4g+3 from their four words */
 template <int TK>
-__device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, const Philox4 &w, uint32_t g, uint32_t &qw, uint32_t &mw) {
-    const uint32_t r[4] = {w.x, w.y, w.z, w.w};
+__device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, const uint32_t (&r)[4], uint32_t g, uint32_t &qw, uint32_t &mw) {
     uint32_t col[4], x[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)                   /* r * 2^cb as one wide multiply: high word = column, low word = threshold draw */
@@ -469,10 +490,13 @@ __device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, con
  * (substituted) bases in `sw` and the quality characters in `qw`. */
 template <int TK>
 __device__ __forceinline__ void group4(const RunParams &rp, uint32_t tab_s, uint32_t lut_s, uint32_t qconst, uint32_t X, uint32_t bi,
-                                       uint32_t g, uint32_t stream, uint32_t ulo, uint32_t uhi, uint32_t &sw, uint32_t &qw) {
+                                       uint32_t g, Mwc4 &rng, uint32_t &sw, uint32_t &qw) {
     uint32_t mw = 0;
     if (TK == PT_CONST) qw = qconst;
-    else sample4<TK>(rp, tab_s, philox(rp.rk, g, stream, ulo, uhi), g, qw, mw);
+    else {
+        const uint32_t r[4] = {mwc_next(rng.x[0], rng.c[0]), mwc_next(rng.x[1], rng.c[1]), mwc_next(rng.x[2], rng.c[2]), mwc_next(rng.x[3], rng.c[3])};
+        sample4<TK>(rp, tab_s, r, g, qw, mw);
+    }
     uint32_t at = (bi == 0 ? X << 2 : X >> (8 * bi - 2)) & 0x3fcu;
     if (TK == PT_T64) at ^= ((mw * 0x01041040u) >> 22) & 0x3fcu;     /* XOR the four 2-bit substitution codes into the byte */
     sw = lds32(lut_s + at);
@@ -480,15 +504,15 @@ __device__ __forceinline__ void group4(const RunParams &rp, uint32_t tab_s, uint
 
 /* Sequence and quality lines of one record by the SUB lanes of a sub-group, all 32 lanes of
  * the warp converged (lanes whose sub-group has no fast record run with on = false and store
- * nothing).  Each lane owns 2*T2 consecutive groups and works on them two at a time (two
- * independent Philox chains in flight).  RC: mate 2 — bases complemented and written back to
+ * nothing).  Lane sl owns run sl of the record's word schedule — run_groups(L) consecutive groups,
+ * taken two at a time — while the warp loops for the longest run among its records (T2 pairs).  RC: mate 2 — bases complemented and written back to
  * front (util.rs:31-37); the quality line is never reversed (simulate.rs:283-285).  body_s =
  * shared-space address of the '\n' that ends the header; lut_s = ASCII table of this strand. */
 template <int TK, bool RC>
 __device__ __forceinline__ void body_fast(const RunParams &rp, uint32_t tab_s, uint32_t lut_s, bool on, uint32_t body_s,
                                           uint32_t ulo, uint32_t uhi, uint32_t stream, uint64_t a, uint32_t L, uint32_t sl, uint32_t T2) {
     if (!on) { L = 0; a = 0; body_s = 0; }
-    const uint32_t g0 = sl * 2u * T2;
+    const uint32_t rho = run_groups(L), g0 = sl * rho;
     /* aligned words of the two lines: slot k of the sequence line sits at ps + 4k (ps - 4k when RC), of the quality line at pq + 4k */
     const uint32_t Ds = body_s + 1, Dq = body_s + L + 4;
     uint32_t sh_s, kw_s, ps;
@@ -498,7 +522,7 @@ __device__ __forceinline__ void body_fast(const RunParams &rp, uint32_t tab_s, u
     uint32_t kw_q = (L + oq + 3u) >> 2, pq = (Dq - oq) + 4u * g0;
     if (!on) kw_s = kw_q = 0;
     /* slots this lane may store, per line (the rest of its 2*T2 lie past the end of the line) */
-    int32_t ns = int32_t(kw_s) - int32_t(g0), nq = int32_t(kw_q) - int32_t(g0);
+    int32_t ns = min(int32_t(kw_s) - int32_t(g0), int32_t(rho)), nq = min(int32_t(kw_q) - int32_t(g0), int32_t(rho));
     const uint32_t ps0 = ps, pq0 = pq;
     const bool st0s = ns > 0, st0q = nq > 0;
     /* 16 bases per word of the 2-bit copy; this lane's run starts at base a + 4*g0 */
@@ -507,7 +531,9 @@ __device__ __forceinline__ void body_fast(const RunParams &rp, uint32_t tab_s, u
     const uint32_t s2 = 2u * (uint32_t(b0) & 15u);
     uint32_t w0 = __ldg(pw), w1 = __ldg(pw + 1);
     const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u;
-    uint32_t first_s = 0, first_q = 0, prev_s = 0, prev_q = 0, g = g0;
+    uint32_t first_s = 0, first_q = 0, prev_s = 0, prev_q = 0, last_s = 0, last_q = 0, g = g0;
+    Mwc4 rng{};
+    if (TK != PT_CONST) mwc_seed(rp, rng, sl, stream, ulo, uhi);
     auto compose_s = [&](uint32_t older, uint32_t newer) { return RC ? __funnelshift_lc(newer, older, sh_s) : __funnelshift_l(older, newer, sh_s); };
     auto compose_q = [&](uint32_t older, uint32_t newer) { return TK == PT_CONST ? qconst : __funnelshift_l(older, newer, sh_q); };
     for (uint32_t p = 0; p < T2; p += 2) {           /* one word of the 2-bit copy = 4 groups = 2 pairs */
@@ -517,8 +543,8 @@ __device__ __forceinline__ void body_fast(const RunParams &rp, uint32_t tab_s, u
         for (uint32_t h = 0; h < 2; ++h) {
             if (h == 1 && p + 1 >= T2) break;
             uint32_t sa, qa, sb, qb;
-            group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h, g, stream, ulo, uhi, sa, qa);
-            group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h + 1, g + 1, stream, ulo, uhi, sb, qb);
+            group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h, g, rng, sa, qa);
+            group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h + 1, g + 1, rng, sb, qb);
             if (h == 0 && p == 0) { first_s = sa; first_q = qa; }
             else {
                 if (ns > 0) sts32(ps, compose_s(prev_s, sa));
@@ -528,10 +554,11 @@ __device__ __forceinline__ void body_fast(const RunParams &rp, uint32_t tab_s, u
             if (nq > 1) sts32(pq + 4u, compose_q(qa, qb));
             prev_s = sb; prev_q = qb;
             ps += RC ? uint32_t(-8) : 8u; pq += 8u; ns -= 2; nq -= 2; g += 2;
+            if (g - g0 == rho) { last_s = sb; last_q = qb; }      /* end of this lane's run: what the next lane's first slot needs */
         }
     }
     /* slot g0 needs the last word of the lane to the left (lane 0: bytes before the line, repaired in phase 2) */
-    const uint32_t left_s = __shfl_up_sync(0xffffffffu, prev_s, 1, SUB), left_q = __shfl_up_sync(0xffffffffu, prev_q, 1, SUB);
+    const uint32_t left_s = __shfl_up_sync(0xffffffffu, last_s, 1, SUB), left_q = __shfl_up_sync(0xffffffffu, last_q, 1, SUB);
     if (st0s) sts32(ps0, compose_s(left_s, first_s));
     if (st0q) sts32(pq0, compose_q(left_q, first_q));
 }
@@ -729,7 +756,8 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_offsets(RunParams rp) {
 
 
 /* pairs of 4-base groups each of the SUB lanes of a record takes: 2*SUB*T2 slots >= groups + 1 */
-__device__ __forceinline__ uint32_t pairs_per_lane(uint32_t L) { return (((L + 3u) >> 2) + 2u * SUB) / (2u * SUB); }
+__device__ __forceinline__ uint32_t pairs_per_lane(uint32_t L) { return run_groups(L) >> 1; }
+static_assert(SUB == 4, "the word schedule cuts every read into four runs");
 
 /* Persistent warps.  A warp owns WARP_UNITS consecutive units at a time: it composes their
  * FASTQ bytes in its private stage in shared memory and sends them off with one bulk async

@@ -213,3 +213,59 @@ def test_native_tables_match_reference_arithmetic(mean_q):
     assert abs(rate - pm.sum()) < 6 * np.sqrt(pm.sum() / n), (rate, pm.sum())
     if mean_q == 30:
         assert abs(pm.sum() - 0.01340) < 2e-4                            # 1.340 %
+
+
+def test_native_stream_statistics():
+    """The per-base word schedule (Philox-seeded MWC64X chains) as it comes out of a native
+    run: Phred histogram against the table's exact distribution (chi-square), substitution rate, no
+    correlation between neighbouring qualities or between the two mates, equal use of the three
+    alternative bases."""
+    import simmr_b200 as S
+    rng = np.random.default_rng(8)
+    seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 400000)]
+    gs = S.GenomeSet.from_contigs([("u", [(b"c", seq)])])
+    og = po.Genomes.from_set(gs)
+    prof = po.Profile(po.MINIMAL_SHORT, 150, 150, 30)
+    t = prof.phred_table()
+    cols = 1 << t["cb"]
+    thr, pay = t["entries"][0::2].astype(np.float64), t["entries"][1::2]
+    pq, pm = np.zeros(256), 0.0
+    for i in range(cols):
+        keep = thr[i] / 2.0 ** 32 if thr[i] < 0xFFFFFFFF else 1.0
+        for w, p in ((keep, pay[i] & 0xFFFF), (1.0 - keep, pay[i] >> 16)):
+            pq[p & 0xFF] += w / cols
+            pm += (w / cols) if (p >> 8) & 0xFF else 0.0
+    recs = H.parse_fastq(po.simulate(og, prof, [30000], 1234))
+    q = np.frombuffer(b"".join(r[2] for r in recs), np.uint8).astype(np.int64) - 33
+    n = len(q)
+    assert n > 4_000_000
+    emp = np.bincount(q, minlength=256) / n
+    sel = pq * n >= 20
+    chi2 = float((((emp - pq) ** 2)[sel] / pq[sel]).sum() * n)
+    assert chi2 < sel.sum() + 6 * np.sqrt(2 * sel.sum()), chi2
+    # substitutions: compare every mate with its source window (mate 2 is reverse-complemented)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    src = seq.tobytes()
+    subs = total = 0
+    alt = np.zeros(4, np.int64)
+    for hdr, s, _ in recs[:20000]:
+        f = dict(kv.split(b"=") for kv in hdr.split(b"metadata:")[1].split(b"|"))
+        sp, ep, rc = int(f[b"sp"]), int(f[b"ep"]), f[b"rc"] == b"t"
+        ref = src[ep:sp].translate(comp)[::-1] if rc else src[sp:ep]
+        a, b = np.frombuffer(s, np.uint8), np.frombuffer(ref, np.uint8)
+        diff = a != b
+        subs += int(diff.sum()); total += len(a)
+        # rank(new) xor rank(old) in 1..3 must be uniform
+        rank = np.zeros(256, np.int64); rank[list(b"ACGT")] = range(4)
+        ra, rb = rank[a[diff]], rank[b[diff]]
+        if rc:
+            ra, rb = 3 - ra, 3 - rb
+        alt += np.bincount(ra ^ rb, minlength=4)
+    assert abs(subs / total - pm) < 6 * np.sqrt(pm / total), (subs / total, pm)
+    assert alt[0] == 0 and np.all(np.abs(alt[1:] - subs / 3) < 6 * np.sqrt(subs / 3)), alt
+    qf = q.astype(np.float64) - q.mean()
+    assert abs(float((qf[:-1] * qf[1:]).mean() / qf.var())) < 5 / np.sqrt(n)         # lag-1 (also across the 4 chains)
+    assert abs(float((qf[:-4] * qf[4:]).mean() / qf.var())) < 5 / np.sqrt(n)         # lag-4: same chain, next step
+    m1 = np.frombuffer(b"".join(r[2][:100] for r in recs[0::2]), np.uint8).astype(np.float64)
+    m2 = np.frombuffer(b"".join(r[2][:100] for r in recs[1::2]), np.uint8).astype(np.float64)
+    assert abs(float(np.corrcoef(m1, m2)[0, 1])) < 5 / np.sqrt(len(m1))
