@@ -51,6 +51,7 @@ struct RunParams {
     PhredTab phred; LenTab rl, is; GammaConst gamma;
     uint32_t min_size, is_long, flags, mutates;
     uint32_t phred_mult;           /* 1 << phred.cb */
+    uint32_t tab_rep;              /* copies of every PT_T64 entry in shared memory, interleaved so that lane l reads copy l % tab_rep */
     uint32_t rk[20];               /* Philox round keys: seed + r * Weyl constants, r = 0..9 */
     /* per-batch scratch + output */
     uint32_t *sizes; uint64_t *offsets, *block_sums; uint8_t *out;
@@ -65,8 +66,8 @@ struct RunParams {
 constexpr uint32_t HDR_MAX_TOK = 32;
 
 constexpr int SIZES_THREADS = 256;
-constexpr int FORMAT_THREADS = 256;   /* threads of a format CTA (8 warps, each with a private stage) */
-constexpr int FORMAT_MIN_CTAS = 3;    /* occupancy target -> register cap of 80          */
+constexpr int FORMAT_THREADS = 768;   /* most threads of a format CTA (each warp has a private stage) -> register cap of 85 */
+constexpr int FORMAT_MIN_CTAS = 1;
 constexpr int DIRECT_THREADS = 256;
 constexpr int SUB = 4;                /* lanes that share one record = runs of the per-base word schedule */
 constexpr uint32_t PACK_PAD_WORDS = 1024; /* readable words past the end of `packed`     */
@@ -382,12 +383,12 @@ __device__ __forceinline__ void replay_base(const RunParams &rp, const ReplayDev
 }
 
 /* (quality byte as printed, mutation code) of base i from its Philox word */
-__device__ __forceinline__ void native_base(const RunParams &rp, const uint32_t *tab, uint32_t r, uint32_t i, uint32_t &qc, uint32_t &m) {
+__device__ __forceinline__ void native_base(const RunParams &rp, const uint32_t *tab, uint32_t tab_rep, uint32_t r, uint32_t i, uint32_t &qc, uint32_t &m) {
     const uint32_t cb = rp.phred.cb, idx = r >> (32 - cb), x = r << cb;
     const uint32_t pos = i < rp.phred.npos ? i : rp.phred.npos - 1;               /* custom_short.rs:339-345 */
     const uint32_t col = (pos << cb) + idx;
     if (rp.phred.kind == PT_T64) {
-        const uint32_t thr = tab[2 * col], pay = tab[2 * col + 1];
+        const uint32_t thr = tab[2 * col * tab_rep], pay = tab[2 * col * tab_rep + 1];
         const uint32_t s = x < thr ? pay : pay >> 16;
         qc = s & 0xffu; m = (s >> 8) & 0xffu;
     } else {
@@ -401,7 +402,7 @@ __device__ __forceinline__ void native_base(const RunParams &rp, const uint32_t 
  * memory.  Base i of the window gets quality slot i; for mate 2 the (mutated) base is
  * complemented and lands at L-1-i, the quality stays at i (simulate.rs:283-285). */
 template <bool REPLAY, bool PUNCT>
-__device__ __forceinline__ void emit_body_generic(const RunParams &rp, const ReplayDev &rd, const uint32_t *tab, uint8_t *dst,
+__device__ __forceinline__ void emit_body_generic(const RunParams &rp, const ReplayDev &rd, const uint32_t *tab, uint32_t tab_rep, uint8_t *dst,
                                                   uint64_t unit, uint32_t mate, uint64_t a, uint32_t L, uint64_t slot0, uint32_t thr, uint32_t nthr) {
     uint8_t *seq = dst + 1, *qual = dst + L + 4;
     if (PUNCT && thr == 0) { dst[0] = '\n'; dst[L + 1] = '\n'; dst[L + 2] = '+'; dst[L + 3] = '\n'; dst[2 * L + 4] = '\n'; }   /* fastq.rs:61-69 */
@@ -421,7 +422,7 @@ __device__ __forceinline__ void emit_body_generic(const RunParams &rp, const Rep
                 uint32_t qc, m;
                 if (REPLAY) { uint32_t q; replay_base(rp, rd, slot0 + i, i, q, m); qc = (q + 33) & 0xffu; }   /* util.rs:46-50 */
                 else if (rp.phred.kind == PT_CONST) { qc = (rp.phred.const_q + 33) & 0xffu; m = 0; }
-                else native_base(rp, tab, mwc_next(w.x[j], w.c[j]), i, qc, m);
+                else native_base(rp, tab, tab_rep, mwc_next(w.x[j], w.c[j]), i, qc, m);
                 uint8_t b = __ldg(src + i);
                 if (m) b = REPLAY ? substitute(b, m - 1) : substitute_native(b, m);
                 qual[i] = uint8_t(qc);
@@ -463,7 +464,7 @@ __device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, con
         uint2 e[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {             /* entry address by a multiply-add (kept out of the shift unit) */
-            uint32_t at; asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(at) : "r"(col[j]), "r"(tab_s));
+            uint32_t at; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(at) : "r"(col[j]), "r"(8u * rp.tab_rep), "r"(tab_s));   /* tab_s: this lane's copy */
             e[j] = lds64(at);
         }
         /* byte selectors: self = payload bytes 0 (quality) and 1 (mutation), alias = bytes 2 and 3 */
@@ -787,15 +788,19 @@ __host__ __device__ constexpr uint32_t warp_region_bytes(uint32_t stage_cap) {
 template <bool REPLAY, int TK>
 __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_warps(RunParams rp, ReplayDev rd) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u : 1u);
+    const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u * rp.tab_rep : 1u);
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem + SM_TAB);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint8_t *region = smem + SM_TAB + ((tab_words * 4 + 15) & ~15u) + warp * warp_region_bytes(rp.stage_cap);
     TileUnit *tu = reinterpret_cast<TileUnit *>(region);
     uint8_t *stage = region + WARP_UNITS * sizeof(TileUnit) + STAGE_FRONT;
     const uint32_t base_s = uint32_t(__cvta_generic_to_shared(smem));
-    const uint32_t tab_s = base_s + SM_TAB, dec2_s = base_s + SM_DEC2, stage_s = uint32_t(__cvta_generic_to_shared(stage));
-    for (uint32_t i = threadIdx.x; i < tab_words; i += blockDim.x) tab[i] = rp.phred.entries[i];
+    /* PT_T64: entry c is stored tab_rep times, copy k at index c * tab_rep + k; a lane reads copy lane % tab_rep, so the
+     * random look-ups of a half-warp fall into different banks */
+    const uint32_t tab_s = base_s + SM_TAB + (rp.phred.kind == PT_T64 ? 8u * (lane & (rp.tab_rep - 1u)) : 0u);
+    const uint32_t dec2_s = base_s + SM_DEC2, stage_s = uint32_t(__cvta_generic_to_shared(stage));
+    if (rp.phred.kind == PT_T64) for (uint32_t i = threadIdx.x; i < tab_words; i += blockDim.x) tab[i] = rp.phred.entries[2u * (i / (2u * rp.tab_rep)) + (i & 1u)];
+    else for (uint32_t i = threadIdx.x; i < tab_words; i += blockDim.x) tab[i] = rp.phred.entries[i];
     for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {               /* 4 bases per byte -> ASCII, both strands */
         uint32_t f = 0, r = 0;
         for (uint32_t j = 0; j < 4; ++j) {
@@ -856,7 +861,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_warp
                         else body_fast<TK, true>(rp, tab_s, base_s + SM_LUT_RC, fast, stage_s + body, ulo, uhi, 2, a, L, sl, T2);
                     }
                     if (have && !fast)
-                        emit_body_generic<REPLAY, false>(rp, rd, tab, stage + body, unit, mate, a, L,
+                        emit_body_generic<REPLAY, false>(rp, rd, tab, rp.tab_rep, stage + body, unit, mate, a, L,
                                                          (REPLAY ? rd.base_off[unit] : 0) + (mate ? t.d.rl : 0), sl, SUB);
                 }
             }
@@ -923,7 +928,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, 
                 uint64_t sp, ep; record_positions(d, r, sp, ep);
                 emit_header(dst, rp, rp.chdr[2 * d.contig + r], rp.read_id_base + uint32_t(u), sp, ep);
             }
-            emit_body_generic<REPLAY, true>(rp, rd, tab, dst + H, u, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
+            emit_body_generic<REPLAY, true>(rp, rd, tab, 1, dst + H, u, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
             dst += H + 2 * L + 5;
         }
     }

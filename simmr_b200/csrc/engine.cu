@@ -98,8 +98,8 @@ int fail(simmr_ctx *c, int code, const std::string &m) {
     } while (0)
 
 size_t table_bytes(const ProfileModel &m) { return m.phred_entries.size() * 4; }
-size_t warps_smem(const ProfileModel &m, uint32_t warps, uint32_t stage_cap) {
-    return SM_TAB + ((table_bytes(m) + 15) & ~size_t(15)) + size_t(warps) * warp_region_bytes(stage_cap);
+size_t warps_smem(const ProfileModel &m, uint32_t rep, uint32_t warps, uint32_t stage_cap) {
+    return SM_TAB + ((table_bytes(m) * rep + 15) & ~size_t(15)) + size_t(warps) * warp_region_bytes(stage_cap);
 }
 
 /* kernel instantiations: the fast path is specialised per table kind, replay is generic */
@@ -116,7 +116,7 @@ FormatKernel direct_kernel(bool replay) { return replay ? k_format_direct<true> 
 
 struct Plan {      /* launch geometry for one run */
     bool tiles = false;            /* warp-private stages in shared memory (short reads) vs one CTA per unit */
-    uint32_t stage_cap = 0, max_unit_bytes = 0, threads = 0;
+    uint32_t stage_cap = 0, max_unit_bytes = 0, threads = 0, tab_rep = 1;
     size_t smem = 0;
     int grid = 0;
 };
@@ -136,13 +136,17 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
          * draws longer reads is cut into sub-tiles by the kernel) and at least the largest single unit. */
         const uint64_t typical = 2ull * (ctx->plan.hdr_cap + 2ull * m.nominal_read_len + 5);
         const uint64_t cap = (std::max<uint64_t>(unit_bytes + 32, WARP_UNITS * typical * 23 / 20 + 64) + 15) & ~15ull;
-        /* warps per CTA: as many as keep three CTAs on an SM, so that the shared tables cost little */
+        /* One CTA per SM with as many warps as fit.  The joint quality/substitution table (4 KB) is stored 8 times,
+         * interleaved, so that the random look-ups of a half-warp spread over the banks instead of colliding
+         * (measured: 8 copies + 24 warps beats 16 copies + 20 warps and 1 copy in 3 CTAs of 8 warps). */
+        uint32_t rep = m.phred_kind == PT_T64 && tab * 8 <= 32768 ? 8u : 1u;
+        if (const char *e = getenv("SIMMR_REP")) { const int r = atoi(e); if (m.phred_kind == PT_T64 && (r == 1 || r == 2 || r == 4 || r == 8 || r == 16)) rep = uint32_t(r); }
         uint32_t warps = FORMAT_THREADS / 32;
         if (const char *e = getenv("SIMMR_WARPS")) warps = uint32_t(std::max(1, std::min(FORMAT_THREADS / 32, atoi(e))));
-        while (warps > 1 && (warps_smem(m, warps, uint32_t(cap)) + 1024) * FORMAT_MIN_CTAS > smem_sm && warps_smem(m, warps / 2, uint32_t(cap)) >= tab + 4096) warps /= 2;
-        while (warps > 1 && warps_smem(m, warps, uint32_t(cap)) > smem_max) warps /= 2;
-        if (cap > 0x7fffffffull || warps_smem(m, warps, uint32_t(cap)) > smem_max) pl.tiles = false;   /* a single unit does not fit: direct path */
-        else { pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.smem = warps_smem(m, warps, uint32_t(cap)); }
+        while (rep > 1 && warps_smem(m, rep, 4, uint32_t(cap)) > smem_max) rep /= 2;
+        while (warps > 1 && warps_smem(m, rep, warps, uint32_t(cap)) > smem_max) --warps;
+        if (cap > 0x7fffffffull || warps_smem(m, rep, warps, uint32_t(cap)) > smem_max) pl.tiles = false;   /* a single unit does not fit: direct path */
+        else { pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.tab_rep = rep; pl.smem = warps_smem(m, rep, warps, uint32_t(cap)); }
     }
     if (!pl.tiles) { pl.smem = tab; pl.threads = DIRECT_THREADS; }
     int occ = 0;
@@ -153,7 +157,7 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
     if (occ < 1) return fail(ctx, SIMMR_E_LIMIT, "format kernel does not fit on an SM");
     pl.grid = occ * ctx->prop.multiProcessorCount;
     if (const char *e = getenv("SIMMR_GRID")) pl.grid = std::max(1, atoi(e));
-    if (getenv("SIMMR_DEBUG_SYNC")) fprintf(stderr, "[simmr] tiles=%d threads=%u cap=%u smem=%zu occ=%d grid=%d\n", int(pl.tiles), pl.threads, pl.stage_cap, pl.smem, occ, pl.grid);
+    if (getenv("SIMMR_DEBUG_SYNC")) fprintf(stderr, "[simmr] tiles=%d threads=%u rep=%u cap=%u smem=%zu occ=%d grid=%d\n", int(pl.tiles), pl.threads, pl.tab_rep, pl.stage_cap, pl.smem, occ, pl.grid);
     return SIMMR_OK;
 }
 
@@ -204,7 +208,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.sizes = ctx->d_sizes.as<uint32_t>(); rp.offsets = ctx->d_offsets.as<uint64_t>();
     rp.desc = ctx->d_desc.as<UnitDesc>();
     rp.block_sums = ctx->d_block_sums.as<uint64_t>(); rp.counters = ctx->d_counters.as<unsigned long long>();
-    rp.stage_cap = pl.stage_cap;
+    rp.stage_cap = pl.stage_cap; rp.tab_rep = pl.tab_rep;
 }
 
 /* The batch pipeline shared by simulate and replay. */
