@@ -934,4 +934,124 @@ __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, 
     }
 }
 
+/* ---------------------------------------------------------------------- */
+/* long reads, native mode                                                  */
+/* ---------------------------------------------------------------------- */
+/* One line (sequence or quality) of one run, written straight to global memory as aligned
+ * 32-bit words: word k of the run = funnel(W[k-1], W[k]) where W[k] is the run's k-th 4-byte
+ * group.  Only whole words inside the run's byte range are stored in the loop; the run's
+ * first and last bytes that share a word with something else go by byte stores, so runs (and
+ * records) never touch each other's bytes. */
+struct RunLine {
+    uint8_t *word0;        /* address of aligned word 0 (holds the run's first byte) */
+    uint32_t o, n;         /* the run's first byte is byte o of word 0; n bytes */
+    uint32_t kend;         /* words [1 or 0, kend) are whole */
+    uint32_t sh;           /* 8 * o */
+    uint32_t first, prev, pp;
+};
+__device__ __forceinline__ void rl_open(RunLine &r, uint8_t *at, uint32_t n) {
+    r.o = uint32_t(reinterpret_cast<uintptr_t>(at)) & 3u; r.word0 = at - r.o; r.n = n; r.sh = 8u * r.o;
+    r.kend = (n + r.o) >> 2; r.first = r.prev = r.pp = 0;
+}
+/* groups k and k+1 of the run (k even) */
+__device__ __forceinline__ void rl_pair(RunLine &r, uint32_t k, uint32_t wa, uint32_t wb) {
+    uint32_t *dst = reinterpret_cast<uint32_t *>(r.word0) + k;
+    if (k == 0) r.first = wa;
+    else if (k < r.kend) dst[0] = __funnelshift_l(r.prev, wa, r.sh);
+    if (k + 1 < r.kend) dst[1] = __funnelshift_l(wa, wb, r.sh);
+    r.pp = r.prev; r.prev = wb; /* after the last pair: prev = W[2T-1], pp = W[2T-3]; W[2T-2] is passed to rl_close */
+}
+/* ng = groups in the run, wa = W[2T-2] of the last pair */
+__device__ __forceinline__ void rl_close(const RunLine &r, uint32_t ng, uint32_t wa) {
+    /* word 0: whole only if the run starts on a word boundary and covers it */
+    const uint32_t a0 = __funnelshift_l(0u, r.first, r.sh);
+    if (r.o == 0 && r.kend >= 1) *reinterpret_cast<uint32_t *>(r.word0) = a0;
+    else for (uint32_t b = r.o; b < min(4u, r.o + r.n); ++b) r.word0[b] = uint8_t(a0 >> (8u * b));
+    /* word kend: the run's last bytes when they do not fill it */
+    const uint32_t rest = (r.n + r.o) & 3u;
+    if (rest && r.kend >= 1) {
+        const uint32_t last = (ng & 1u) ? wa : r.prev, before = (ng & 1u) ? r.pp : wa;      /* W[ng-1], W[ng-2] */
+        const uint32_t ak = r.kend == ng ? __funnelshift_l(last, 0u, r.sh) : __funnelshift_l(before, last, r.sh);
+        for (uint32_t b = 0; b < rest; ++b) r.word0[4u * r.kend + b] = uint8_t(ak >> (8u * b));
+    }
+}
+
+/* Long reads (simulate.rs:323-406, 464-523), native mode.  A record is far larger than a stage
+ * and read lengths vary by an order of magnitude, so every lane works alone: it takes one run
+ * (a quarter of one read) at a time, writes that run's part of the sequence and
+ * quality lines straight to global memory, and fetches the next run when it is done; the lane
+ * that takes a read's first run also writes its header and the fixed bytes.  Reads whose
+ * window holds anything but A,C,G,T take the byte path in that lane. */
+template <int TK>
+__global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u * rp.tab_rep : 1u);
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem + SM_TAB);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t base_s = uint32_t(__cvta_generic_to_shared(smem));
+    const uint32_t tab_s = base_s + SM_TAB + (rp.phred.kind == PT_T64 ? 8u * (lane & (rp.tab_rep - 1u)) : 0u), lut_s = base_s + SM_LUT_FWD;
+    if (rp.phred.kind == PT_T64) for (uint32_t i = threadIdx.x; i < tab_words; i += blockDim.x) tab[i] = rp.phred.entries[2u * (i / (2u * rp.tab_rep)) + (i & 1u)];
+    else for (uint32_t i = threadIdx.x; i < tab_words; i += blockDim.x) tab[i] = rp.phred.entries[i];
+    for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {
+        uint32_t f = 0;
+        for (uint32_t j = 0; j < 4; ++j) f |= ((0x54474341u >> (8 * ((b >> (2 * j)) & 3u))) & 0xffu) << (8 * j);
+        reinterpret_cast<uint32_t *>(smem + SM_LUT_FWD)[b] = f;
+    }
+    __syncthreads();
+
+    const uint32_t total = 4u * rp.batch_units, stride = gridDim.x * blockDim.x;
+    const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u;
+    uint32_t item = blockIdx.x * blockDim.x + threadIdx.x - stride;     /* advanced before first use */
+    uint32_t quads_left = 0, k = 0, ng = 0, wa_s = 0, wa_q = 0, w0 = 0, w1 = 0, s2 = 0, g = 0;
+    const uint32_t *pw = rp.packed;
+    bool busy = false, more = true;
+    RunLine ls{}, lq{};
+    Mwc4 rng{};
+    for (;;) {
+        if (quads_left == 0) {
+            if (busy) { rl_close(ls, ng, wa_s); rl_close(lq, ng, wa_q); busy = false; }
+            while (more && !busy) {                       /* next run that has something to do */
+                item += stride;
+                if (item >= total) { more = false; break; }
+                const uint32_t i = item >> 2, j = item & 3u;
+                const UnitDesc d = rp.desc[i];
+                const uint32_t L = d.L0, H = d.H0;
+                const uint64_t unit = rp.batch_begin + i;
+                uint8_t *rec = rp.out + rp.offsets[i];
+                const bool bytes_path = (d.flags & 9u) || L < 4u;
+                if (j == 0) {                             /* header and the five fixed bytes (fastq.rs:34-69) */
+                    emit_header(rec, rp, rp.chdr[2 * d.contig], rp.read_id_base + uint32_t(unit), d.p0, d.p1);
+                    rec[H] = '\n'; rec[H + L + 1] = '\n'; rec[H + L + 2] = '+'; rec[H + L + 3] = '\n'; rec[H + 2 * L + 4] = '\n';
+                    if (bytes_path) { ReplayDev none{}; emit_body_generic<false, false>(rp, none, tab, rp.tab_rep, rec + H, unit, 0, d.a0, L, 0, 0, 1); }
+                }
+                if (bytes_path) continue;
+                const uint32_t NG = (L + 3u) >> 2, rho = run_groups(L), gb = j * rho;
+                if (gb >= NG) continue;
+                ng = min(rho, NG - gb);
+                const uint32_t b0 = 4u * gb, nb = min(L, 4u * (gb + ng)) - b0;
+                rl_open(ls, rec + H + 1 + b0, nb); rl_open(lq, rec + H + L + 4 + b0, nb);
+                if (TK != PT_CONST) mwc_seed(rp, rng, j, 1, uint32_t(unit), uint32_t(unit >> 32));
+                const uint64_t a = d.a0 + b0;
+                pw = rp.packed + (a >> 4); s2 = 2u * (uint32_t(a) & 15u);
+                w0 = __ldg(pw); w1 = __ldg(pw + 1); pw += 2;
+                quads_left = (ng + 3u) >> 2; k = 0; g = gb; busy = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, busy)) break;
+        if (busy) {                                       /* four groups = one word of the 2-bit copy */
+            const uint32_t X = __funnelshift_r(w0, w1, s2);
+            w0 = w1; w1 = __ldg(pw++);
+#pragma unroll
+            for (uint32_t h = 0; h < 2; ++h) {
+                uint32_t sa, qa, sb, qb;
+                group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h, g, rng, sa, qa);
+                group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h + 1, g + 1, rng, sb, qb);
+                if (k < ng) { rl_pair(ls, k, sa, sb); rl_pair(lq, k, qa, qb); wa_s = sa; wa_q = qa; }
+                k += 2; g += 2;
+            }
+            --quads_left;
+        }
+    }
+}
+
 }  // namespace simmr

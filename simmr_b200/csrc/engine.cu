@@ -113,9 +113,12 @@ FormatKernel warps_kernel(bool replay, uint32_t kind) {
     }
 }
 FormatKernel direct_kernel(bool replay) { return replay ? k_format_direct<true> : k_format_direct<false>; }
+using LongKernel = void (*)(RunParams);
+LongKernel long_kernel(uint32_t kind) { return kind == PT_T64 ? k_format_long<PT_T64> : kind == PT_T32 ? k_format_long<PT_T32> : k_format_long<PT_CONST>; }
 
 struct Plan {      /* launch geometry for one run */
     bool tiles = false;            /* warp-private stages in shared memory (short reads) vs one CTA per unit */
+    bool lanes = false;            /* long reads, native mode: one lane per run (k_format_long) */
     uint32_t stage_cap = 0, max_unit_bytes = 0, threads = 0, tab_rep = 1;
     size_t smem = 0;
     int grid = 0;
@@ -148,12 +151,20 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
         if (cap > 0x7fffffffull || warps_smem(m, rep, warps, uint32_t(cap)) > smem_max) pl.tiles = false;   /* a single unit does not fit: direct path */
         else { pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.tab_rep = rep; pl.smem = warps_smem(m, rep, warps, uint32_t(cap)); }
     }
-    if (!pl.tiles) { pl.smem = tab; pl.threads = DIRECT_THREADS; }
     int occ = 0;
-    FormatKernel k = pl.tiles ? warps_kernel(replay, m.phred_kind) : direct_kernel(replay);
-    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem);
-    CU(e);
+    if (!pl.tiles && !replay && m.is_long && !getenv("SIMMR_NO_LONG_KERNEL")) {
+        pl.lanes = true; pl.threads = DIRECT_THREADS;
+        pl.tab_rep = m.phred_kind == PT_T64 && tab * 8 <= 32768 ? 8u : 1u;
+        pl.smem = SM_TAB + tab * pl.tab_rep;
+        LongKernel k = long_kernel(m.phred_kind);
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
+    } else {
+        if (!pl.tiles) { pl.smem = tab; pl.threads = DIRECT_THREADS; }
+        FormatKernel k = pl.tiles ? warps_kernel(replay, m.phred_kind) : direct_kernel(replay);
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
+    }
     if (occ < 1) return fail(ctx, SIMMR_E_LIMIT, "format kernel does not fit on an SM");
     pl.grid = occ * ctx->prop.multiProcessorCount;
     if (const char *e = getenv("SIMMR_GRID")) pl.grid = std::max(1, atoi(e));
@@ -290,6 +301,9 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
             const uint32_t wpc = pl.threads / 32, nctas = ((n + WARP_UNITS - 1) / WARP_UNITS + wpc - 1) / wpc;
             const int grid = int(std::min<uint32_t>(nctas, uint32_t(pl.grid)));
             warps_kernel(replay, ctx->model.phred_kind)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
+        } else if (pl.lanes) {
+            const int grid = int(std::min<uint32_t>((4 * n + pl.threads - 1) / pl.threads, uint32_t(pl.grid)));
+            long_kernel(ctx->model.phred_kind)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp);
         } else {
             const int grid = int(std::min<uint32_t>(n, uint32_t(pl.grid)));
             direct_kernel(replay)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
