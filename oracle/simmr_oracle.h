@@ -114,7 +114,7 @@ int      orc_abundance(int kind, int size_adjusted, uint64_t total_reads, uint32
                        const double *abund_in, const uint64_t *genome_sizes,
                        uint64_t *out_reads, double *out_abund);
 
-/* -------- profile-level scalars (error_profiles/*.rs) -------- */
+/* -------- profile-level scalars (error_profiles/ *.rs) -------- */
 int      orc_profile_min_genome_size(const orc_profile *p, uint16_t *out);
 int      orc_profile_is_long(const orc_profile *p, int *out);
 /* quantised alias tables the native mode samples from */

@@ -657,24 +657,11 @@ __global__ void __launch_bounds__(256) k_pack(const uint8_t *bases, uint64_t nby
     if ((threadIdx.x & 31) == 0 && (blk >> 5) < nimpure) impure[blk >> 5] = bits;
 }
 
-__device__ __forceinline__ uint64_t block_sum_u64(uint64_t v, uint64_t *sh) {
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) sh[wid] = v;
-    __syncthreads();
-    uint64_t r = 0;
-    if (wid == 0) {
-        r = lane < (blockDim.x >> 5) ? sh[lane] : 0;
-        for (int o = 16; o; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
-    }
-    __syncthreads();
-    return r;   /* valid in thread 0 */
-}
-
 /* one thread per unit: geometry -> descriptor, FASTQ bytes of the unit, block totals, run statistics */
 template <bool REPLAY>
 __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, ReplayDev rd) {
     __shared__ uint64_t sh[32];
+    static_assert(SIZES_THREADS == 256, "block totals assume 8 warps");
     const uint32_t i = blockIdx.x * SIZES_THREADS + threadIdx.x;
     uint64_t bytes = 0, alg = 0, bases = 0, clamped = 0, recs = 0;
     if (i < rp.batch_units) {
@@ -700,14 +687,22 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, Repl
                            ((big >> 32) ? 8u : 0u));             /* 8: a position needs more than 32 bits */
         rp.desc[i] = d;
     }
-    const uint64_t tb = block_sum_u64(bytes, sh), ta = block_sum_u64(alg, sh), tn = block_sum_u64(bases, sh),
-                   tc = block_sum_u64(clamped, sh), tr = block_sum_u64(recs, sh);
-    if (threadIdx.x == 0) {
-        rp.block_sums[blockIdx.x] = tb;
-        if (tc) atomicAdd(rp.counters + 0, (unsigned long long)tc);
-        atomicAdd(rp.counters + 1, (unsigned long long)ta);
-        atomicAdd(rp.counters + 2, (unsigned long long)tn);
-        atomicAdd(rp.counters + 3, (unsigned long long)tr);
+    /* block totals of the five counters: warp sums, one barrier, then five lanes of warp 0 finish (a block's totals fit 32 bits) */
+    uint32_t v[5] = {uint32_t(bytes), uint32_t(alg), uint32_t(bases), uint32_t(clamped), uint32_t(recs)};
+#pragma unroll
+    for (int c = 0; c < 5; ++c) v[c] = __reduce_add_sync(0xffffffffu, v[c]);
+    uint32_t *sh32 = reinterpret_cast<uint32_t *>(sh);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) sh32[c * 8 + wid] = v[c];
+    }
+    __syncthreads();
+    if (wid == 0 && lane < 5) {
+        uint64_t t = 0;
+        for (int w = 0; w < SIZES_THREADS / 32; ++w) t += sh32[lane * 8 + w];
+        if (lane == 0) rp.block_sums[blockIdx.x] = t;
+        else if (t) atomicAdd(rp.counters + (lane == 1 ? 1 : lane == 2 ? 2 : lane == 3 ? 0 : 3), (unsigned long long)t);
     }
 }
 
