@@ -245,3 +245,37 @@ def test_cli_binary_end_to_end(engine, tmp_path, mode):
     assert got == want, first_diff(got, want)
     bad = subprocess.run([exe, "--genome", paths[0], "--output", out, "--error-profile", "nope"], capture_output=True, text=True)
     assert bad.returncode == 1 and "invalid value" in bad.stderr
+
+
+def test_full_size_c2_properties(engine):
+    """BASELINE config C2 at its full size (100 M reads, 100 genomes, ~0.5 GB): size-independent properties of
+    the whole run, and byte parity with the oracle on slices taken far into it (64-bit offsets, batch seams)."""
+    import bench
+    gs = bench.c2_genomes()
+    prof = S.MinimalShortErrorProfile(150, 150, 30)
+    reads, abund = S.UniformAbundanceProfile().determine_abundances(100_000_000, gs.n_genomes)
+    assert reads.tolist() == [1_000_000] * 100 and abund.tolist() == [1.0] * 100        # uniform.rs:28-29
+    engine.load_genomes(gs)
+    engine.set_error_profile(prof)
+    total = engine.total_units(reads)
+    assert total == 50_000_000                                                           # simulate.rs:179: n_reads / 2 pairs
+    st = engine.simulate(reads, 42)                                                      # device-resident run
+    assert st["units"] == total and st["records"] == 2 * total and st["clamped"] == 0
+    mean_len = st["bases"] / st["records"]
+    assert abs(mean_len - 149.5) < 0.02                                                  # floor N(150, 15)
+    assert st["algorithmic_bytes"] == st["bytes"] + st["bases"]                          # (3L+H+5) = (2L+H+5) + L
+    assert engine.measure(reads, 42) == (st["bytes"], st["records"])
+    og = po.Genomes.from_set(gs)
+    oprof = H.oracle_profile(prof)
+    batch = 1_000_003
+    for ub in (0, batch - 3, 17 * batch - 1, total - 400):
+        ue = min(total, ub + 400)
+        got = engine.simulate_bytes(reads, 42, unit_begin=ub, unit_end=ue, batch_units=batch)
+        want = po.simulate(og, oprof, reads, 42, unit_begin=ub, unit_end=ue)
+        assert got == want, first_diff(got, want)
+        recs = H.parse_fastq(got)
+        assert recs[0][0].startswith(f"@{ub}|".encode())                                 # read id = global pair index (simulate.rs:85-89)
+    # a slice that straddles a device batch seam of a longer run
+    got = engine.simulate_bytes(reads, 42, unit_begin=batch - 300, unit_end=batch + 300, batch_units=300)
+    want = po.simulate(og, oprof, reads, 42, unit_begin=batch - 300, unit_end=batch + 300)
+    assert got == want, first_diff(got, want)
