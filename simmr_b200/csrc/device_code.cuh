@@ -59,11 +59,10 @@ struct RunParams {
     unsigned long long *counters;  /* [0] clamped [1] algorithmic bytes [2] bases [3] records */
     /* per-warp stage of k_format_warps */
     uint32_t stage_cap;            /* bytes of a warp's stage in k_format_warps */
-    /* header template shared by every contig (token kinds, fastq.rs:34-57); hdr_ntok == 0: per-contig lists only */
-    uint32_t hdr_ntok;
-    uint64_t hdr_kinds[2];         /* 4 bits per token, token i in bits 4*(i&15) of word i>>4 */
+    /* decimal fields of the header template when every contig has the same ones (fastq.rs:34-57): hdr_fast == 0 means
+     * per-contig lists only; kinds 4 bits each, field i in bits 4*i */
+    uint32_t hdr_fast, hdr_fields, hdr_kinds;
 };
-constexpr uint32_t HDR_MAX_TOK = 32;
 
 constexpr int SIZES_THREADS = 256;
 constexpr int FORMAT_THREADS = 768;   /* most threads of a format CTA (each warp has a private stage) -> register cap of 85 */
@@ -606,23 +605,30 @@ __device__ __forceinline__ void bs_decimal(ByteStream &b, uint32_t dec2_s, uint3
     bs_put(b, r2 >> s, d - 8u);
 }
 
-/* Tokens [i0, i1) of a record's header template into the stream (kinds = the 4-bit token kinds
- * starting at token i0, the same for every contig; tk = this (contig, mate)'s token list). */
-__device__ __forceinline__ void header_tokens(ByteStream &b, const RunParams &rp, uint32_t dec2_s, const uint2 *tk, uint64_t kinds,
-                                              uint32_t i0, uint32_t i1, uint32_t id, uint32_t sp, uint32_t ep) {
-#pragma unroll 1
-    for (uint32_t i = i0; i < i1; ++i, kinds >>= 4) {
-        const uint32_t kind = uint32_t(kinds) & 15u;                               /* same for every thread */
-        if (kind == TOK_LIT) {
-            const uint2 k = __ldg(tk + i);                                         /* {off, len | type << 16} */
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(rp.pool + k.x);
-            const uint32_t len = k.y & 0xffffu, nw = len >> 2;
+/* A record's header template into the stream.  Token lists are canonical (host_model.cpp): literal, field,
+ * literal, ..., field, literal with nf <= HDR_MAX_FIELDS decimal fields whose kinds (4 bits each) are the same
+ * for every contig; tk = this (contig, mate)'s token list. */
+constexpr uint32_t HDR_MAX_FIELDS = 4;
+__device__ __forceinline__ void header_tokens(ByteStream &b, const RunParams &rp, uint32_t dec2_s, const uint2 *tk, uint32_t kinds,
+                                              uint32_t nf, uint32_t id, uint32_t sp, uint32_t ep) {
+    uint2 lit[HDR_MAX_FIELDS + 1];                                               /* {off, len | type << 16}, fetched together */
+#pragma unroll
+    for (uint32_t i = 0; i <= HDR_MAX_FIELDS; ++i) lit[i] = i <= nf ? __ldg(tk + 2 * i) : make_uint2(0u, 0u);
+#pragma unroll
+    for (uint32_t i = 0; i <= HDR_MAX_FIELDS; ++i) {
+        if (i > nf) break;                                                       /* same for every thread */
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(rp.pool + lit[i].x);
+        const uint32_t len = lit[i].y & 0xffffu, nw = len >> 2;
 #pragma unroll 4
-            for (uint32_t j = 0; j < nw; ++j) bs_word(b, __ldg(src + j));
-            if (len & 3u) bs_put(b, __ldg(src + nw), len & 3u);
-        } else bs_decimal(b, dec2_s, kind == TOK_READ_ID ? id : kind == TOK_START ? sp : ep);
+        for (uint32_t j = 0; j < nw; ++j) bs_word(b, __ldg(src + j));
+        if (len & 3u) bs_put(b, __ldg(src + nw), len & 3u);
+        if (i < nf) {
+            const uint32_t kind = (kinds >> (4u * i)) & 15u;
+            bs_decimal(b, dec2_s, kind == TOK_READ_ID ? id : kind == TOK_START ? sp : ep);
+        }
     }
 }
+
 /* ---------------------------------------------------------------------- */
 /* kernels                                                                  */
 /* ---------------------------------------------------------------------- */
@@ -835,7 +841,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_warp
                 odd = (t.d.flags & 8u) || t.d.H0 < 2u || t.d.L0 < 4u || (two && (t.d.H1 < 2u || t.d.L1 < 4u));
             }
             const bool words_ok = !__any_sync(0xffffffffu, odd) && !REPLAY;
-            const bool hdr_fast = words_ok && rp.hdr_ntok != 0;
+            const bool hdr_fast = words_ok && rp.hdr_fast != 0;
             __syncwarp();
 
             /* ---- phase 1: sequence and quality lines, sub-group sg takes unit sg ---- */
@@ -872,7 +878,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_warp
                     const ContigHdr ch = rp.chdr[2 * t.d.contig + mate];
                     if (hdr_fast) {      /* newline that ends the previous record, the tokens, newline */
                         ByteStream b; bs_open(b, rec_s - 1u); bs_put(b, '\n', 1);
-                        header_tokens(b, rp, dec2_s, reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off), rp.hdr_kinds[0], 0, rp.hdr_ntok,
+                        header_tokens(b, rp, dec2_s, reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off), rp.hdr_kinds, rp.hdr_fields,
                                       id, uint32_t(sp), uint32_t(ep));
                         bs_put(b, '\n', 1); bs_close(b);
                     } else {

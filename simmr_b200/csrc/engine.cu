@@ -70,7 +70,7 @@ struct simmr_ctx {
     /* headers */
     std::string header_fmt; bool have_headers = false;
     HeaderPlan plan;
-    uint32_t hdr_ntok = 0; uint64_t hdr_kinds[2] = {0, 0};    /* token kinds when every contig shares them */
+    uint32_t hdr_fast = 0, hdr_fields = 0, hdr_kinds = 0;     /* decimal fields when every contig has the same ones */
     DevMem d_chdr, d_toks, d_pool;
     /* profile */
     bool have_profile = false;
@@ -183,16 +183,20 @@ int ensure_headers(simmr_ctx *ctx, const char *fmt) {
     ctx->plan.pool.resize((ctx->plan.pool.size() + 7) & ~size_t(3), '\0');
     CU(ctx->d_pool.upload(ctx->plan.pool.data(), ctx->plan.pool.size(), ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
-    {   /* one token-kind list for all contigs lets the kernel run the template without per-token loads */
+    {   /* the same decimal fields in every contig (token lists are canonical: literal, field, ..., literal) let the
+         * kernel run the template without per-token dispatch */
         const HeaderPlan &hp = ctx->plan;
         const uint32_t n = hp.contigs.empty() ? 0 : hp.contigs[0].ntok;
-        bool same = n > 0 && n <= 16;
+        bool same = n >= 1 && (n & 1u) && (n >> 1) <= HDR_MAX_FIELDS;
         for (size_t c = 0; same && c < hp.contigs.size(); ++c) {
             same = hp.contigs[c].ntok == n;
-            for (uint32_t i = 0; same && i < n; ++i) same = hp.toks[hp.contigs[c].tok_off + i].type == hp.toks[hp.contigs[0].tok_off + i].type;
+            for (uint32_t i = 0; same && i < n; ++i) {
+                const uint8_t t = hp.toks[hp.contigs[c].tok_off + i].type;
+                same = (i & 1u) ? (t != TOK_LIT && t == hp.toks[hp.contigs[0].tok_off + i].type) : t == TOK_LIT;
+            }
         }
-        ctx->hdr_ntok = same ? n : 0; ctx->hdr_kinds[0] = ctx->hdr_kinds[1] = 0;
-        for (uint32_t i = 0; same && i < n; ++i) ctx->hdr_kinds[i >> 4] |= uint64_t(hp.toks[hp.contigs[0].tok_off + i].type) << (4 * (i & 15));
+        ctx->hdr_fast = same; ctx->hdr_fields = same ? n >> 1 : 0; ctx->hdr_kinds = 0;
+        for (uint32_t i = 0; same && i < (n >> 1); ++i) ctx->hdr_kinds |= uint32_t(hp.toks[hp.contigs[0].tok_off + 2 * i + 1].type) << (4 * i);
     }
     ctx->header_fmt = f; ctx->have_headers = true;
     return SIMMR_OK;
@@ -204,7 +208,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.bases = ctx->d_bases.as<uint8_t>(); rp.contig_off = ctx->d_contig_off.as<uint64_t>();
     rp.contig_size = ctx->d_contig_size.as<uint64_t>(); rp.genome_contig = ctx->d_genome_contig.as<uint32_t>();
     rp.impure = ctx->d_impure.as<uint32_t>(); rp.packed = ctx->d_packed.as<uint32_t>();
-    rp.hdr_ntok = ctx->hdr_ntok; rp.hdr_kinds[0] = ctx->hdr_kinds[0]; rp.hdr_kinds[1] = ctx->hdr_kinds[1];
+    rp.hdr_fast = ctx->hdr_fast; rp.hdr_fields = ctx->hdr_fields; rp.hdr_kinds = ctx->hdr_kinds;
     rp.chdr = ctx->d_chdr.as<ContigHdr>(); rp.toks = ctx->d_toks.as<HdrTok>(); rp.pool = ctx->d_pool.as<uint8_t>();
     rp.n_genomes = ctx->host_view.n_genomes; rp.n_contigs = ctx->host_view.n_contigs;
     rp.unit_start = ctx->d_unit_start.as<uint64_t>();

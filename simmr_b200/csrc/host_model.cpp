@@ -664,29 +664,29 @@ int compile_headers(const simmr_genome_set &g, const char *fmt, HeaderPlan &plan
                 ContigHdr ch{}; ch.tok_off = uint32_t(plan.toks.size());
                 size_t lit_total = 0;
                 std::string run;                           /* literal text gathered up to the next decimal field */
+                /* canonical form: literal, field, literal, ..., field, literal — a literal (possibly empty) on every
+                 * even place, so the kernel needs no per-token dispatch */
                 auto flush = [&]() {
-                    for (size_t o = 0; o < run.size(); o += 65532) {
-                        const size_t len = std::min<size_t>(65532, run.size() - o);
-                        plan.pool.resize((plan.pool.size() + 3) & ~size_t(3), '\0');   /* the kernel fetches literals by words */
-                        plan.toks.push_back(HdrTok{uint32_t(plan.pool.size()), uint16_t(len), TOK_LIT, 0});
-                        plan.pool.append(run, o, len);
-                    }
+                    if (run.size() > 65532) return false;
+                    plan.pool.resize((plan.pool.size() + 3) & ~size_t(3), '\0');   /* the kernel fetches literals by words */
+                    plan.toks.push_back(HdrTok{uint32_t(plan.pool.size()), uint16_t(run.size()), TOK_LIT, 0});
+                    plan.pool.append(run);
                     lit_total += run.size(); run.clear();
+                    return true;
                 };
                 for (const Piece &pc : pieces) {
                     if (pc.kind == TOK_LIT) run += pc.text;
                     else if (pc.kind == TOK_RC) run += mate ? 't' : 'f';
                     else if (pc.kind == TOK_PAIR) run += mate ? '2' : '1';
                     else {
-                        flush();
+                        if (!flush()) { err = "read header too long"; return SIMMR_E_LIMIT; }
                         plan.toks.push_back(HdrTok{0, 0, pc.kind, 0});
                         uint8_t *ctr = pc.kind == TOK_READ_ID ? &ch.n_id : pc.kind == TOK_START ? &ch.n_sp : &ch.n_ep;
                         if (*ctr == 255) { err = "header format repeats a placeholder more than 255 times"; return SIMMR_E_LIMIT; }
                         ++*ctr;
                     }
                 }
-                flush();
-                if (lit_total > 60000 || plan.toks.size() - ch.tok_off > 60000) { err = "read header too long"; return SIMMR_E_LIMIT; }
+                if (!flush() || lit_total > 60000 || plan.toks.size() - ch.tok_off > 60000) { err = "read header too long"; return SIMMR_E_LIMIT; }
                 ch.ntok = uint16_t(plan.toks.size() - ch.tok_off); ch.lit_bytes = uint16_t(lit_total);
                 plan.contigs.push_back(ch);
                 const uint32_t cap = uint32_t(lit_total) + 10u * ch.n_id + 20u * ch.n_sp + 20u * ch.n_ep;
