@@ -279,3 +279,34 @@ def test_full_size_c2_properties(engine):
     got = engine.simulate_bytes(reads, 42, unit_begin=batch - 300, unit_end=batch + 300, batch_units=300)
     want = po.simulate(og, oprof, reads, 42, unit_begin=batch - 300, unit_end=batch + 300)
     assert got == want, first_diff(got, want)
+
+
+def test_edge_cases(engine):
+    """Empty runs, many decimal fields, N-rich genomes, reads too large for a stage, very long reads."""
+    gs = H.synth_genomes(3, (1, 2), (3000, 6000), seed=51)
+    engine.load_genomes(gs)
+    engine.set_error_profile(S.MinimalShortErrorProfile())
+    assert engine.simulate_bytes([0, 0, 0], 1) == b"" and engine.simulate_bytes([1, 1, 1], 1) == b""     # n_reads / 2 pairs
+    assert engine.measure([0, 1, 0], 1) == (0, 0)
+    # five decimal fields: more than the kernel's fixed header program handles, falls back to the token interpreter
+    fmt = "@{:read_id:}_{:start_position:}_{:end_position:}_{:read_id:}{:start_position:} {:sequence_id:}"
+    check_native(engine, gs, S.MinimalShortErrorProfile(), [300, 200, 100], 4, header_format=fmt)
+    check_native(engine, gs, S.MinimalShortErrorProfile(), [300, 200, 100], 4, header_format="{:read_id:}")      # starts and ends with a field
+    check_native(engine, gs, S.PerfectShortErrorProfile(), [300, 200, 100], 4, header_format="@")               # one-byte header: word paths off
+    # every window touches an N: all records take the byte path
+    rng = np.random.default_rng(3)
+    seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 20000)].copy()
+    seq[::97] = ord("N")
+    seq[5000:5100] = np.frombuffer(b"acgtnRYKM-", np.uint8)[rng.integers(0, 10, 100)]
+    gn = S.GenomeSet.from_contigs([("nn", [(b"ncontig", seq)])])
+    check_native(engine, gn, S.MinimalShortErrorProfile(), [2000], 8)
+    check_native(engine, gn, S.CustomShortErrorProfile(H.novaseq_blob()), [2000], 8)
+    # short-read profile whose reads do not fit a warp's stage: one CTA per unit straight to global memory
+    big = H.synth_genomes(2, (1, 1), (70000, 90000), seed=52)
+    check_native(engine, big, S.PerfectShortErrorProfile(20000, 100), [6, 4], 2)
+    check_native(engine, big, S.MinimalShortErrorProfile(9000, 12000, 20), [6, 4], 2)
+    # long reads up to the u16 limit (perfect_long.rs:40-55 saturates at 65535)
+    huge = H.synth_genomes(1, (1, 1), (400000, 400000), seed=53)
+    data = check_native(engine, huge, S.MinimalLongErrorProfile(25), [300], 77)
+    lens = [len(s) for _, s, _ in H.parse_fastq(data)]
+    assert max(lens) == 65535 and min(lens) < 5000
