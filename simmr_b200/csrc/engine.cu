@@ -263,6 +263,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     const uint32_t max_blocks = uint32_t((batch + SIZES_THREADS - 1) / SIZES_THREADS);
     CU(ctx->d_sizes.reserve(batch * 4)); CU(ctx->d_desc.reserve(batch * sizeof(UnitDesc))); CU(ctx->d_offsets.reserve((batch + 1) * 8)); CU(ctx->d_block_sums.reserve(size_t(max_blocks) * 8));
     CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
+    const bool guard = getenv("SIMMR_DEBUG_GUARD") != nullptr;
     const int nbuf = sink ? 2 : 1;
     for (int b = 0; b < nbuf; ++b) CU(ctx->d_out[b].reserve(out_cap));
     if (sink) { for (int b = 0; b < 2; ++b) CU(ctx->h_out[b].reserve(out_cap)); }
@@ -289,6 +290,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
         if (sink) { rc = drain(slot); if (rc) return rc; }       /* slot's buffers are about to be reused */
         rp.batch_begin = u; rp.batch_units = n; rp.out = ctx->d_out[slot].as<uint8_t>();
+        if (guard) CU(cudaMemsetAsync(ctx->d_out[slot].p, 0xA5, out_cap, ctx->compute));
         const uint32_t nblk = (n + SIZES_THREADS - 1) / SIZES_THREADS;
         if (replay) k_unit_sizes<true><<<nblk, SIZES_THREADS, 0, ctx->compute>>>(rp, rd);
         else k_unit_sizes<false><<<nblk, SIZES_THREADS, 0, ctx->compute>>>(rp, rd);
@@ -314,6 +316,14 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         }
         CU(cudaGetLastError());
         CU(cudaEventRecord(ev_f1, ctx->compute));
+        if (guard) {   /* SIMMR_DEBUG_GUARD: nothing may be written past the batch's last byte */
+            uint64_t total = 0; uint8_t tail[64];
+            CU(cudaMemcpyAsync(&total, rp.offsets + n, 8, cudaMemcpyDeviceToHost, ctx->compute));
+            CU(cudaStreamSynchronize(ctx->compute));
+            if (total + 64 > out_cap) return fail(ctx, SIMMR_E_LIMIT, "batch overflowed its staging buffer");
+            CU(cudaMemcpy(tail, rp.out + total, 64, cudaMemcpyDeviceToHost));
+            for (int b = 0; b < 64; ++b) if (tail[b] != 0xA5) return fail(ctx, SIMMR_E_CUDA, "guard bytes after the batch output were overwritten");
+        }
         st.kernel_launches += 4;
         if (sink) {
             CU(cudaEventRecord(ev_fmt[slot], ctx->compute));

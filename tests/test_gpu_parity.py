@@ -310,3 +310,15 @@ def test_edge_cases(engine):
     data = check_native(engine, huge, S.MinimalLongErrorProfile(25), [300], 77)
     lens = [len(s) for _, s, _ in H.parse_fastq(data)]
     assert max(lens) == 65535 and min(lens) < 5000
+
+
+def test_no_write_past_the_batch(engine, monkeypatch):
+    """SIMMR_DEBUG_GUARD fills the staging buffer with a pattern and checks the 64 bytes after every batch's
+    last byte (compute-sanitizer is not available on the GPU pool)."""
+    monkeypatch.setenv("SIMMR_DEBUG_GUARD", "1")
+    gs = H.synth_genomes(5, (1, 4), (2500, 30000), seed=61, with_n=True)
+    for prof, reads in ((S.MinimalShortErrorProfile(), [3001, 7, 1500, 0, 2222]), (S.PerfectShortErrorProfile(151, 149), [999, 1001, 3, 5, 7]),
+                        (S.CustomShortErrorProfile(H.novaseq_blob()), [1200, 800, 400, 200, 100])):
+        check_native(engine, gs, prof, reads, 3, batch_units=997)
+    gl = H.synth_genomes(2, (1, 2), (21000, 70000), seed=62)
+    check_native(engine, gl, S.MinimalLongErrorProfile(20), [33, 21], 5, batch_units=13)
