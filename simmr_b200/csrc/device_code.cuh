@@ -194,7 +194,7 @@ __device__ __forceinline__ uint32_t genome_of(const RunParams &rp, uint64_t u) {
 }
 
 template <bool REPLAY>
-__device__ void unit_geometry(const RunParams &rp, const ReplayDev &rd, uint64_t u, UnitGeo &o) {
+__device__ void unit_geometry(const RunParams &rp, const ReplayDev &rd, uint64_t u, uint32_t g_lo, uint32_t g_hi, UnitGeo &o) {
     o.id = rp.read_id_base + uint32_t(u);                         /* simulate.rs:85-89 */
     o.clamped = 0;
     uint32_t g, c; uint64_t RL, IS = 0, start, redraw = 0;
@@ -204,7 +204,8 @@ __device__ void unit_geometry(const RunParams &rp, const ReplayDev &rd, uint64_t
         RL = rd.read_length[u]; start = rd.start[u]; redraw = rd.redraw[u];
         if (!rp.is_long) IS = rd.insert_size[u];
     } else {
-        g = genome_of(rp, u);
+        g = g_lo;                                   /* the block's units span genomes g_lo..g_hi */
+        while (g < g_hi && __ldg(rp.unit_start + g + 1) <= u) ++g;
         w0 = draw(rp, u, 0, 0);
         const uint32_t c0 = __ldg(rp.genome_contig + g), nseq = __ldg(rp.genome_contig + g + 1) - c0;
         if (!rp.is_long) {
@@ -670,8 +671,15 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, Repl
     static_assert(SIZES_THREADS == 256, "block totals assume 8 warps");
     const uint32_t i = blockIdx.x * SIZES_THREADS + threadIdx.x;
     uint64_t bytes = 0, alg = 0, bases = 0, clamped = 0, recs = 0;
+    /* genome of the block's first and last unit by binary search, once; the threads then walk between the two */
+    __shared__ uint32_t g_span[2];
+    if (!REPLAY && (threadIdx.x == 0 || threadIdx.x == 32)) {
+        const uint32_t first = blockIdx.x * SIZES_THREADS, last = min(first + SIZES_THREADS, rp.batch_units) - 1;
+        g_span[threadIdx.x >> 5] = genome_of(rp, rp.batch_begin + (threadIdx.x ? last : first));
+    }
+    __syncthreads();
     if (i < rp.batch_units) {
-        UnitGeo g; unit_geometry<REPLAY>(rp, rd, rp.batch_begin + i, g);
+        UnitGeo g; unit_geometry<REPLAY>(rp, rd, rp.batch_begin + i, REPLAY ? 0 : g_span[0], REPLAY ? 0 : g_span[1], g);
         uint32_t H[2] = {0, 0};
         uint64_t big = 0;
         for (uint32_t r = 0; r < g.nrec; ++r) {
