@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="simmr_b200")
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--reads-per-gpu", type=int, default=READS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -220,6 +220,8 @@ def main():
 
     # end to end: host genome buffers -> device, FASTQ bytes -> pinned host, inside the timed region
     e2e_bases = e2e_d2h = 0
+    if args.e2e_steps:      # untimed: the pinned output ring is allocated on the first call that has a sink
+        eng.simulate(reads, SEED, unit_begin=ub, unit_end=min(ue, ub + 2_000_000), sink=lambda a, f, n: 0)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
