@@ -946,40 +946,67 @@ __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, 
 /* ---------------------------------------------------------------------- */
 /* long reads, native mode                                                  */
 /* ---------------------------------------------------------------------- */
-/* One line (sequence or quality) of one run, written straight to global memory as aligned
- * 32-bit words: word k of the run = funnel(W[k-1], W[k]) where W[k] is the run's k-th 4-byte
- * group.  Only whole words inside the run's byte range are stored in the loop; the run's
- * first and last bytes that share a word with something else go by byte stores, so runs (and
+/* One line (sequence or quality) of one run, written straight to global memory.  Word k of the
+ * run = funnel(W[k-1], W[k]) where W[k] is the run's k-th 4-byte group and word 0 is the aligned
+ * word holding the run's first byte.  Four groups arrive at a time; the words are regrouped (by
+ * q = the run's phase inside a 16-byte line) so that whole 16-byte lines leave as one vector
+ * store.  Only whole words inside the run's byte range are stored here; the run's first and last
+ * bytes that share a word with something else go by byte stores in rl_close, so runs (and
  * records) never touch each other's bytes. */
 struct RunLine {
-    uint8_t *word0;        /* address of aligned word 0 (holds the run's first byte) */
+    uint8_t *word0;        /* address of aligned word 0 */
     uint32_t o, n;         /* the run's first byte is byte o of word 0; n bytes */
-    uint32_t kend;         /* words [1 or 0, kend) are whole */
-    uint32_t sh;           /* 8 * o */
-    uint32_t first, prev, pp;
+    uint32_t kend;         /* words [1, kend) are whole and stored by rl_quad; word 0 and word kend by rl_close */
+    uint32_t sh, q;        /* 8 * o; (word0 / 4) % 4 */
+    uint32_t c0, c1, c2;   /* words k-3, k-2, k-1 */
+    uint32_t g[5];         /* W[k-1], W[k..k+3] of the last quad */
 };
 __device__ __forceinline__ void rl_open(RunLine &r, uint8_t *at, uint32_t n) {
-    r.o = uint32_t(reinterpret_cast<uintptr_t>(at)) & 3u; r.word0 = at - r.o; r.n = n; r.sh = 8u * r.o;
-    r.kend = (n + r.o) >> 2; r.first = r.prev = r.pp = 0;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(at);
+    r.o = uint32_t(a) & 3u; r.word0 = at - r.o; r.n = n; r.sh = 8u * r.o; r.q = (uint32_t(a) >> 2) & 3u;
+    r.kend = (n + r.o) >> 2; r.c0 = r.c1 = r.c2 = 0;
+    r.g[0] = r.g[1] = r.g[2] = r.g[3] = r.g[4] = 0;
 }
-/* groups k and k+1 of the run (k even) */
-__device__ __forceinline__ void rl_pair(RunLine &r, uint32_t k, uint32_t wa, uint32_t wb) {
-    uint32_t *dst = reinterpret_cast<uint32_t *>(r.word0) + k;
-    if (k == 0) r.first = wa;
-    else if (k < r.kend) dst[0] = __funnelshift_l(r.prev, wa, r.sh);
-    if (k + 1 < r.kend) dst[1] = __funnelshift_l(wa, wb, r.sh);
-    r.pp = r.prev; r.prev = wb; /* after the last pair: prev = W[2T-1], pp = W[2T-3]; W[2T-2] is passed to rl_close */
+/* groups k..k+3 of the run (k a multiple of 4) */
+__device__ __forceinline__ void rl_quad(RunLine &r, uint32_t k, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    const uint32_t a0 = __funnelshift_l(r.g[4], w0, r.sh), a1 = __funnelshift_l(w0, w1, r.sh), a2 = __funnelshift_l(w1, w2, r.sh), a3 = __funnelshift_l(w2, w3, r.sh);
+    r.g[0] = r.g[4]; r.g[1] = w0; r.g[2] = w1; r.g[3] = w2; r.g[4] = w3;
+    /* the 16-byte line that ends inside this quad holds words k-q .. k-q+3 */
+    const bool s1 = r.q & 1u, s2 = r.q & 2u;
+    const uint32_t v0 = s1 ? r.c1 : r.c2, v1 = s1 ? r.c2 : a0, v2 = s1 ? a0 : a1, v3 = s1 ? a1 : a2, v4 = s1 ? a2 : a3;   /* window shifted by q & 1 ... */
+    const uint32_t u0 = s1 ? r.c0 : r.c1;
+    const uint32_t o0 = s2 ? u0 : v1, o1 = s2 ? v0 : v2, o2 = s2 ? v1 : v3, o3 = s2 ? v2 : v4;                           /* ... and by q & 2 */
+    const int32_t cb = int32_t(k) - int32_t(r.q);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(r.word0) + cb;
+    if (cb >= 1 && uint32_t(cb) + 3u < r.kend) *reinterpret_cast<uint4 *>(dst) = make_uint4(o0, o1, o2, o3);
+    else {
+        if (cb >= 1 && uint32_t(cb) < r.kend) dst[0] = o0;
+        if (cb + 1 >= 1 && uint32_t(cb + 1) < r.kend) dst[1] = o1;
+        if (cb + 2 >= 1 && uint32_t(cb + 2) < r.kend) dst[2] = o2;
+        if (cb + 3 >= 1 && uint32_t(cb + 3) < r.kend) dst[3] = o3;
+    }
+    r.c0 = a1; r.c1 = a2; r.c2 = a3;
 }
-/* ng = groups in the run, wa = W[2T-2] of the last pair */
-__device__ __forceinline__ void rl_close(const RunLine &r, uint32_t ng, uint32_t wa) {
-    /* word 0: whole only if the run starts on a word boundary and covers it */
-    const uint32_t a0 = __funnelshift_l(0u, r.first, r.sh);
+/* k = first group of the last quad, ng = groups in the run */
+__device__ __forceinline__ void rl_close(const RunLine &r, uint32_t k, uint32_t ng) {
+    uint32_t *w = reinterpret_cast<uint32_t *>(r.word0);
+    /* the last q words of the last quad have not left yet */
+    if (r.q >= 3 && k + 1 >= 1 && k + 1 < r.kend) w[k + 1] = r.c0;
+    if (r.q >= 2 && k + 2 < r.kend) w[k + 2] = r.c1;
+    if (r.q >= 1 && k + 3 < r.kend) w[k + 3] = r.c2;
+    /* word 0: whole only if the run starts on a word boundary and covers it.  W[0] is g[1] of the first quad; it is
+     * kept by the caller in `first` */
+}
+__device__ __forceinline__ void rl_edges(const RunLine &r, uint32_t k, uint32_t ng, uint32_t first) {
+    const uint32_t a0 = __funnelshift_l(0u, first, r.sh);
     if (r.o == 0 && r.kend >= 1) *reinterpret_cast<uint32_t *>(r.word0) = a0;
     else for (uint32_t b = r.o; b < min(4u, r.o + r.n); ++b) r.word0[b] = uint8_t(a0 >> (8u * b));
-    /* word kend: the run's last bytes when they do not fill it */
+    /* word kend: the run's last bytes when they do not fill it; W[ng-1] and W[ng-2] are among the last quad's groups */
     const uint32_t rest = (r.n + r.o) & 3u;
     if (rest && r.kend >= 1) {
-        const uint32_t last = (ng & 1u) ? wa : r.prev, before = (ng & 1u) ? r.pp : wa;      /* W[ng-1], W[ng-2] */
+        const uint32_t i = ng - 1u - k;                                   /* 0..3: position of W[ng-1] in the last quad */
+        const uint32_t last = i == 0 ? r.g[1] : i == 1 ? r.g[2] : i == 2 ? r.g[3] : r.g[4];
+        const uint32_t before = i == 0 ? r.g[0] : i == 1 ? r.g[1] : i == 2 ? r.g[2] : r.g[3];
         const uint32_t ak = r.kend == ng ? __funnelshift_l(last, 0u, r.sh) : __funnelshift_l(before, last, r.sh);
         for (uint32_t b = 0; b < rest; ++b) r.word0[4u * r.kend + b] = uint8_t(ak >> (8u * b));
     }
@@ -1011,14 +1038,14 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
     const uint32_t total = 4u * rp.batch_units, stride = gridDim.x * blockDim.x;
     const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u;
     uint32_t item = blockIdx.x * blockDim.x + threadIdx.x - stride;     /* advanced before first use */
-    uint32_t quads_left = 0, k = 0, ng = 0, wa_s = 0, wa_q = 0, w0 = 0, w1 = 0, s2 = 0, g = 0;
+    uint32_t quads_left = 0, k = 0, ng = 0, first_s = 0, first_q = 0, w0 = 0, w1 = 0, s2 = 0, g = 0;
     const uint32_t *pw = rp.packed;
     bool busy = false, more = true;
     RunLine ls{}, lq{};
     Mwc4 rng{};
     for (;;) {
         if (quads_left == 0) {
-            if (busy) { rl_close(ls, ng, wa_s); rl_close(lq, ng, wa_q); busy = false; }
+            if (busy) { rl_close(ls, k - 4u, ng); rl_edges(ls, k - 4u, ng, first_s); rl_close(lq, k - 4u, ng); rl_edges(lq, k - 4u, ng, first_q); busy = false; }
             while (more && !busy) {                       /* next run that has something to do */
                 item += stride;
                 if (item >= total) { more = false; break; }
@@ -1050,14 +1077,12 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         if (busy) {                                       /* four groups = one word of the 2-bit copy */
             const uint32_t X = __funnelshift_r(w0, w1, s2);
             w0 = w1; w1 = __ldg(pw++);
+            uint32_t sw[4], qw[4];
 #pragma unroll
-            for (uint32_t h = 0; h < 2; ++h) {
-                uint32_t sa, qa, sb, qb;
-                group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h, g, rng, sa, qa);
-                group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h + 1, g + 1, rng, sb, qb);
-                if (k < ng) { rl_pair(ls, k, sa, sb); rl_pair(lq, k, qa, qb); wa_s = sa; wa_q = qa; }
-                k += 2; g += 2;
-            }
+            for (uint32_t h = 0; h < 4; ++h) group4<TK>(rp, tab_s, lut_s, qconst, X, h, g + h, rng, sw[h], qw[h]);
+            if (k == 0) { first_s = sw[0]; first_q = qw[0]; }
+            rl_quad(ls, k, sw[0], sw[1], sw[2], sw[3]); rl_quad(lq, k, qw[0], qw[1], qw[2], qw[3]);
+            k += 4; g += 4;
             --quads_left;
         }
     }
