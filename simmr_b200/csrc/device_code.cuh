@@ -36,6 +36,8 @@ struct ReplayDev {                 /* device copies of simmr_draws + replay LUTs
     uint32_t r_npos, pl_qmax, kind; float mean_phred, acc20;
 };
 
+/* long reads: a run (quarter of a read, at most 4098 groups) is cut into parts of LONG_PART_GROUPS groups, the unit of work of k_format_long */
+constexpr uint32_t LONG_PART_GROUPS = 256, LONG_PARTS = 17;
 struct UnitDesc;
 struct RunParams {
     /* genomes (device resident) */
@@ -52,6 +54,7 @@ struct RunParams {
     uint32_t min_size, is_long, flags, mutates;
     uint32_t phred_mult;           /* 1 << phred.cb */
     uint32_t tab_rep;              /* copies of every PT_T64 entry in shared memory, interleaved so that lane l reads copy l % tab_rep */
+    uint64_t mwc_skip[LONG_PARTS]; /* A^(LONG_PART_GROUPS * p) mod (A * 2^32 - 1): jumps a per-base word chain to part p of its run */
     uint32_t rk[20];               /* Philox round keys: seed + r * Weyl constants, r = 0..9 */
     /* per-batch scratch + output */
     uint32_t *sizes; uint64_t *offsets, *block_sums; uint8_t *out;
@@ -111,6 +114,12 @@ __device__ __forceinline__ void mwc_seed(const RunParams &rp, Mwc4 &m, uint32_t 
     const Philox4 a = philox(rp.rk, 2u * run, stream, ulo, uhi), b = philox(rp.rk, 2u * run + 1u, stream, ulo, uhi);
     m.x[0] = a.x; m.c[0] = (a.y >> 2) + 1u; m.x[1] = a.z; m.c[1] = (a.w >> 2) + 1u;
     m.x[2] = b.x; m.c[2] = (b.y >> 2) + 1u; m.x[3] = b.z; m.c[3] = (b.w >> 2) + 1u;
+}
+/* the chain's state n steps ahead: as a number t = x + c * 2^32 a step is t -> t * A mod (A * 2^32 - 1); jump = A^n mod m */
+__device__ __forceinline__ void mwc_jump(uint32_t &x, uint32_t &c, uint64_t jump) {
+    const unsigned __int128 m = (unsigned __int128)(4294883355ull * 4294967296ull - 1ull);
+    const uint64_t t = uint64_t(((unsigned __int128)(uint64_t(x) | (uint64_t(c) << 32)) * jump) % m);
+    x = uint32_t(t); c = uint32_t(t >> 32);
 }
 __device__ __forceinline__ uint32_t mwc_next(uint32_t &x, uint32_t &c) {
     const uint32_t r = x ^ c;
@@ -1013,11 +1022,12 @@ __device__ __forceinline__ void rl_edges(const RunLine &r, uint32_t k, uint32_t 
 }
 
 /* Long reads (simulate.rs:323-406, 464-523), native mode.  A record is far larger than a stage
- * and read lengths vary by an order of magnitude, so every lane works alone: it takes one run
- * (a quarter of one read) at a time, writes that run's part of the sequence and
- * quality lines straight to global memory, and fetches the next run when it is done; the lane
- * that takes a read's first run also writes its header and the fixed bytes.  Reads whose
- * window holds anything but A,C,G,T take the byte path in that lane. */
+ * and read lengths vary by an order of magnitude, so every lane works alone on small pieces: a
+ * piece is up to LONG_PART_GROUPS groups (1 KB of bases) of one run (a quarter of one read,
+ * DESIGN.md §4), taken from a shared counter; the lane jumps the run's word chains to the piece
+ * (MWC skip-ahead), writes that part of the sequence and quality lines straight to global memory
+ * and takes the next piece.  The lane that takes a read's first piece also writes its header
+ * and the fixed bytes.  Reads whose window holds anything but A,C,G,T take the byte path there. */
 template <int TK>
 __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -1035,9 +1045,8 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
     }
     __syncthreads();
 
-    const uint32_t total = 4u * rp.batch_units, stride = gridDim.x * blockDim.x;
+    const uint64_t total = uint64_t(4u * LONG_PARTS) * rp.batch_units;   /* pieces, most of them empty for reads shorter than 65535 */
     const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u;
-    uint32_t item = blockIdx.x * blockDim.x + threadIdx.x - stride;     /* advanced before first use */
     uint32_t quads_left = 0, k = 0, ng = 0, first_s = 0, first_q = 0, w0 = 0, w1 = 0, s2 = 0, g = 0;
     const uint32_t *pw = rp.packed;
     bool busy = false, more = true;
@@ -1046,27 +1055,30 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
     for (;;) {
         if (quads_left == 0) {
             if (busy) { rl_close(ls, k - 4u, ng); rl_edges(ls, k - 4u, ng, first_s); rl_close(lq, k - 4u, ng); rl_edges(lq, k - 4u, ng, first_q); busy = false; }
-            while (more && !busy) {                       /* next run that has something to do */
-                item += stride;
+            while (more && !busy) {                       /* next piece that has something to do */
+                const uint64_t item = atomicAdd(rp.counters + 4, 1ull);
                 if (item >= total) { more = false; break; }
-                const uint32_t i = item >> 2, j = item & 3u;
+                const uint32_t i = uint32_t(item / (4u * LONG_PARTS)), jp = uint32_t(item % (4u * LONG_PARTS)), j = jp / LONG_PARTS, p = jp % LONG_PARTS;
                 const UnitDesc d = rp.desc[i];
                 const uint32_t L = d.L0, H = d.H0;
                 const uint64_t unit = rp.batch_begin + i;
                 uint8_t *rec = rp.out + rp.offsets[i];
                 const bool bytes_path = (d.flags & 9u) || L < 4u;
-                if (j == 0) {                             /* header and the five fixed bytes (fastq.rs:34-69) */
+                if (jp == 0) {                            /* header and the five fixed bytes (fastq.rs:34-69) */
                     emit_header(rec, rp, rp.chdr[2 * d.contig], rp.read_id_base + uint32_t(unit), d.p0, d.p1);
                     rec[H] = '\n'; rec[H + L + 1] = '\n'; rec[H + L + 2] = '+'; rec[H + L + 3] = '\n'; rec[H + 2 * L + 4] = '\n';
                     if (bytes_path) { ReplayDev none{}; emit_body_generic<false, false>(rp, none, tab, rp.tab_rep, rec + H, unit, 0, d.a0, L, 0, 0, 1); }
                 }
                 if (bytes_path) continue;
-                const uint32_t NG = (L + 3u) >> 2, rho = run_groups(L), gb = j * rho;
-                if (gb >= NG) continue;
-                ng = min(rho, NG - gb);
+                const uint32_t NG = (L + 3u) >> 2, rho = run_groups(L), run_end = min(NG, (j + 1u) * rho), gb = j * rho + p * LONG_PART_GROUPS;
+                if (gb >= run_end) continue;
+                ng = min(LONG_PART_GROUPS, run_end - gb);
                 const uint32_t b0 = 4u * gb, nb = min(L, 4u * (gb + ng)) - b0;
                 rl_open(ls, rec + H + 1 + b0, nb); rl_open(lq, rec + H + L + 4 + b0, nb);
-                if (TK != PT_CONST) mwc_seed(rp, rng, j, 1, uint32_t(unit), uint32_t(unit >> 32));
+                if (TK != PT_CONST) {
+                    mwc_seed(rp, rng, j, 1, uint32_t(unit), uint32_t(unit >> 32));
+                    if (p) for (uint32_t c = 0; c < 4; ++c) mwc_jump(rng.x[c], rng.c[c], rp.mwc_skip[p]);
+                }
                 const uint64_t a = d.a0 + b0;
                 pw = rp.packed + (a >> 4); s2 = 2u * (uint32_t(a) & 15u);
                 w0 = __ldg(pw); w1 = __ldg(pw + 1); pw += 2;

@@ -224,6 +224,12 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.desc = ctx->d_desc.as<UnitDesc>();
     rp.block_sums = ctx->d_block_sums.as<uint64_t>(); rp.counters = ctx->d_counters.as<unsigned long long>();
     rp.stage_cap = pl.stage_cap; rp.tab_rep = pl.tab_rep;
+    {   /* MWC64X skip-ahead multipliers: A^(LONG_PART_GROUPS * p) mod (A * 2^32 - 1) */
+        const unsigned __int128 mod = (unsigned __int128)(4294883355ull * 4294967296ull - 1ull);
+        unsigned __int128 step = 1, acc = 1;
+        for (uint32_t i = 0; i < LONG_PART_GROUPS; ++i) step = step * 4294883355ull % mod;
+        for (uint32_t p_ = 0; p_ < LONG_PARTS; ++p_) { rp.mwc_skip[p_] = uint64_t(acc); acc = acc * step % mod; }
+    }
 }
 
 /* The batch pipeline shared by simulate and replay. */
@@ -308,8 +314,8 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
             const int grid = int(std::min<uint32_t>(nctas, uint32_t(pl.grid)));
             warps_kernel(replay, ctx->model.phred_kind)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
         } else if (pl.lanes) {
-            const int grid = int(std::min<uint32_t>((4 * n + pl.threads - 1) / pl.threads, uint32_t(pl.grid)));
-            long_kernel(ctx->model.phred_kind)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp);
+            CU(cudaMemsetAsync(rp.counters + 4, 0, 8, ctx->compute));       /* the kernel's piece counter */
+            long_kernel(ctx->model.phred_kind)<<<pl.grid, pl.threads, pl.smem, ctx->compute>>>(rp);
         } else {
             const int grid = int(std::min<uint32_t>(n, uint32_t(pl.grid)));
             direct_kernel(replay)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
