@@ -837,6 +837,14 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_warp
     const uint32_t ntiles = (rp.batch_units + WARP_UNITS - 1) / WARP_UNITS;
     for (uint32_t tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) {
         const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
+        {   /* pull the next tile's offsets and descriptors towards the SM while this one is composed */
+            const uint32_t nt = (tile + gridDim.x * nwarps) * WARP_UNITS + lane;
+            if (lane <= WARP_UNITS && nt <= rp.batch_units) asm volatile("prefetch.global.L1 [%0];" ::"l"(rp.offsets + nt));
+            if (lane < WARP_UNITS && nt < rp.batch_units) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rp.desc + nt));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(rp.desc + nt) + 32));
+            }
+        }
         for (uint32_t s0 = 0; s0 < tn;) {
             /* sub-tile = longest run of units from s0 that fits the stage */
             const uint32_t u0 = t0 + s0, left = tn - s0;
@@ -865,6 +873,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_warp
             {
                 const bool mine = sg < nu;
                 const TileUnit &t = tu[min(sg, nu - 1)];
+
                 const uint64_t unit = rp.batch_begin + u0 + sg;
                 const uint32_t ulo = uint32_t(unit), uhi = uint32_t(unit >> 32);
 #pragma unroll
