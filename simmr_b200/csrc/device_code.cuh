@@ -36,8 +36,9 @@ struct ReplayDev {                 /* device copies of simmr_draws + replay LUTs
     uint32_t r_npos, pl_qmax, kind; float mean_phred, acc20;
 };
 
-/* long reads: a run (quarter of a read, at most 4098 groups) is cut into parts of LONG_PART_GROUPS groups, the unit of work of k_format_long */
-constexpr uint32_t LONG_PART_GROUPS = 256, LONG_PARTS = 17;
+/* long reads: a run (quarter of a read, at most 4098 groups) is cut into LONG_PARTS pieces, the unit of work of k_format_long;
+ * a piece is a multiple of LONG_GRANULE groups so that the word chains can jump to it with one table entry */
+constexpr uint32_t LONG_PARTS = 8, LONG_GRANULE = 32, LONG_JUMPS = 136;
 struct UnitDesc;
 struct RunParams {
     /* genomes (device resident) */
@@ -54,7 +55,7 @@ struct RunParams {
     uint32_t min_size, is_long, flags, mutates;
     uint32_t phred_mult;           /* 1 << phred.cb */
     uint32_t tab_rep;              /* copies of every PT_T64 entry in shared memory, interleaved so that lane l reads copy l % tab_rep */
-    uint64_t mwc_skip[LONG_PARTS]; /* A^(LONG_PART_GROUPS * p) mod (A * 2^32 - 1): jumps a per-base word chain to part p of its run */
+    uint64_t mwc_skip[LONG_JUMPS]; /* A^(LONG_GRANULE * k) mod (A * 2^32 - 1): jumps a per-base word chain k granules into its run */
     uint32_t rk[20];               /* Philox round keys: seed + r * Weyl constants, r = 0..9 */
     /* per-batch scratch + output */
     uint32_t *sizes; uint64_t *offsets, *block_sums; uint8_t *out;
@@ -117,9 +118,20 @@ __device__ __forceinline__ void mwc_seed(const RunParams &rp, Mwc4 &m, uint32_t 
 }
 /* the chain's state n steps ahead: as a number t = x + c * 2^32 a step is t -> t * A mod (A * 2^32 - 1); jump = A^n mod m */
 __device__ __forceinline__ void mwc_jump(uint32_t &x, uint32_t &c, uint64_t jump) {
-    const unsigned __int128 m = (unsigned __int128)(4294883355ull * 4294967296ull - 1ull);
-    const uint64_t t = uint64_t(((unsigned __int128)(uint64_t(x) | (uint64_t(c) << 32)) * jump) % m);
-    x = uint32_t(t); c = uint32_t(t >> 32);
+    /* (t * jump) mod m with m = A * 2^32 - 1: fold the high half down with 2^64 mod m = (2^32 - A) * 2^32 + 1 (49 bits),
+     * five folds bring a 128-bit product below 2^65, then at most two subtractions */
+    constexpr uint64_t M = 4294883355ull * 4294967296ull - 1ull, R = (4294967296ull - 4294883355ull) * 4294967296ull + 1ull;
+    const uint64_t t = uint64_t(x) | (uint64_t(c) << 32);
+    uint64_t lo = t * jump, hi = __umul64hi(t, jump);
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+        const uint64_t pl = hi * R, ph = __umul64hi(hi, R);
+        lo += pl; hi = ph + (lo < pl ? 1ull : 0ull);
+    }
+    /* now hi is 0 or 1 */
+    if (hi) { lo += R; if (lo < R) lo += R; }           /* + 2^64 mod m (the second carry cannot happen twice) */
+    if (lo >= M) lo -= M;
+    x = uint32_t(lo); c = uint32_t(lo >> 32);
 }
 __device__ __forceinline__ uint32_t mwc_next(uint32_t &x, uint32_t &c) {
     const uint32_t r = x ^ c;
@@ -1032,8 +1044,8 @@ __device__ __forceinline__ void rl_edges(const RunLine &r, uint32_t k, uint32_t 
 
 /* Long reads (simulate.rs:323-406, 464-523), native mode.  A record is far larger than a stage
  * and read lengths vary by an order of magnitude, so every lane works alone on small pieces: a
- * piece is up to LONG_PART_GROUPS groups (1 KB of bases) of one run (a quarter of one read,
- * DESIGN.md §4), taken from a shared counter; the lane jumps the run's word chains to the piece
+ * piece is an eighth of one run (a quarter of one read), taken from a shared
+ * counter; the lane jumps the run's word chains to the piece
  * (MWC skip-ahead), writes that part of the sequence and quality lines straight to global memory
  * and takes the next piece.  The lane that takes a read's first piece also writes its header
  * and the fixed bytes.  Reads whose window holds anything but A,C,G,T take the byte path there. */
@@ -1054,57 +1066,59 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
     }
     __syncthreads();
 
-    const uint64_t total = uint64_t(4u * LONG_PARTS) * rp.batch_units;   /* pieces, most of them empty for reads shorter than 65535 */
     const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u;
-    uint32_t quads_left = 0, k = 0, ng = 0, first_s = 0, first_q = 0, w0 = 0, w1 = 0, s2 = 0, g = 0;
-    const uint32_t *pw = rp.packed;
-    bool busy = false, more = true;
-    RunLine ls{}, lq{};
-    Mwc4 rng{};
+    /* a warp takes one read at a time: its 4 runs x LONG_PARTS pieces are the 32 lanes' work, all of (nearly) the same size */
+    const uint32_t j = lane / LONG_PARTS, p = lane % LONG_PARTS;
     for (;;) {
-        if (quads_left == 0) {
-            if (busy) { rl_close(ls, k - 4u, ng); rl_edges(ls, k - 4u, ng, first_s); rl_close(lq, k - 4u, ng); rl_edges(lq, k - 4u, ng, first_q); busy = false; }
-            while (more && !busy) {                       /* next piece that has something to do */
-                const uint64_t item = atomicAdd(rp.counters + 4, 1ull);
-                if (item >= total) { more = false; break; }
-                const uint32_t i = uint32_t(item / (4u * LONG_PARTS)), jp = uint32_t(item % (4u * LONG_PARTS)), j = jp / LONG_PARTS, p = jp % LONG_PARTS;
-                const UnitDesc d = rp.desc[i];
-                const uint32_t L = d.L0, H = d.H0;
-                const uint64_t unit = rp.batch_begin + i;
-                uint8_t *rec = rp.out + rp.offsets[i];
-                const bool bytes_path = (d.flags & 9u) || L < 4u;
-                if (jp == 0) {                            /* header and the five fixed bytes (fastq.rs:34-69) */
-                    emit_header(rec, rp, rp.chdr[2 * d.contig], rp.read_id_base + uint32_t(unit), d.p0, d.p1);
-                    rec[H] = '\n'; rec[H + L + 1] = '\n'; rec[H + L + 2] = '+'; rec[H + L + 3] = '\n'; rec[H + 2 * L + 4] = '\n';
-                    if (bytes_path) { ReplayDev none{}; emit_body_generic<false, false>(rp, none, tab, rp.tab_rep, rec + H, unit, 0, d.a0, L, 0, 0, 1); }
-                }
-                if (bytes_path) continue;
-                const uint32_t NG = (L + 3u) >> 2, rho = run_groups(L), run_end = min(NG, (j + 1u) * rho), gb = j * rho + p * LONG_PART_GROUPS;
-                if (gb >= run_end) continue;
-                ng = min(LONG_PART_GROUPS, run_end - gb);
-                const uint32_t b0 = 4u * gb, nb = min(L, 4u * (gb + ng)) - b0;
-                rl_open(ls, rec + H + 1 + b0, nb); rl_open(lq, rec + H + L + 4 + b0, nb);
-                if (TK != PT_CONST) {
-                    mwc_seed(rp, rng, j, 1, uint32_t(unit), uint32_t(unit >> 32));
-                    if (p) for (uint32_t c = 0; c < 4; ++c) mwc_jump(rng.x[c], rng.c[c], rp.mwc_skip[p]);
-                }
-                const uint64_t a = d.a0 + b0;
-                pw = rp.packed + (a >> 4); s2 = 2u * (uint32_t(a) & 15u);
-                w0 = __ldg(pw); w1 = __ldg(pw + 1); pw += 2;
-                quads_left = (ng + 3u) >> 2; k = 0; g = gb; busy = true;
+        unsigned long long next = 0;
+        if (lane == 0) next = atomicAdd(rp.counters + 4, 1ull);
+        const uint32_t i = uint32_t(__shfl_sync(0xffffffffu, next, 0));
+        if (i >= rp.batch_units) break;
+        const UnitDesc d = rp.desc[i];
+        const uint32_t L = d.L0, H = d.H0;
+        const uint64_t unit = rp.batch_begin + i;
+        uint8_t *rec = rp.out + rp.offsets[i];
+        const bool bytes_path = (d.flags & 9u) || L < 4u;
+        if (lane == 0) {                                  /* header and the five fixed bytes (fastq.rs:34-69) */
+            emit_header(rec, rp, rp.chdr[2 * d.contig], rp.read_id_base + uint32_t(unit), d.p0, d.p1);
+            rec[H] = '\n'; rec[H + L + 1] = '\n'; rec[H + L + 2] = '+'; rec[H + L + 3] = '\n'; rec[H + 2 * L + 4] = '\n';
+            if (bytes_path) { ReplayDev none{}; emit_body_generic<false, false>(rp, none, tab, rp.tab_rep, rec + H, unit, 0, d.a0, L, 0, 0, 1); }
+        }
+        if (bytes_path) { __syncwarp(); continue; }
+        const uint32_t NG = (L + 3u) >> 2, rho = run_groups(L), run_end = min(NG, (j + 1u) * rho);
+        const uint32_t gran = ((rho + LONG_PARTS - 1u) / LONG_PARTS + LONG_GRANULE - 1u) / LONG_GRANULE;      /* granules per piece */
+        const uint32_t gb = j * rho + p * gran * LONG_GRANULE;
+        const uint32_t ng = gb < run_end ? min(gran * LONG_GRANULE, run_end - gb) : 0u;                       /* groups of this lane's piece */
+        const uint32_t b0 = 4u * gb, nb = ng ? min(L, 4u * (gb + ng)) - b0 : 0u;
+        RunLine ls, lq;
+        rl_open(ls, rec + H + 1 + b0, nb); rl_open(lq, rec + H + L + 4 + b0, nb);
+        Mwc4 rng{};
+        if (TK != PT_CONST && ng) {
+            mwc_seed(rp, rng, j, 1, uint32_t(unit), uint32_t(unit >> 32));
+            if (p) for (uint32_t c = 0; c < 4; ++c) mwc_jump(rng.x[c], rng.c[c], rp.mwc_skip[p * gran]);
+        }
+        const uint64_t a = d.a0 + b0;
+        const uint32_t *pw = rp.packed + (a >> 4);
+        const uint32_t s2 = 2u * (uint32_t(a) & 15u);
+        uint32_t w0 = __ldg(pw), w1 = __ldg(pw + 1);
+        pw += 2;
+        const uint32_t quads = (ng + 3u) >> 2, T = __reduce_max_sync(0xffffffffu, quads);
+        uint32_t first_s = 0, first_q = 0, g = gb;
+        for (uint32_t qd = 0; qd < T; ++qd) {             /* four groups = one word of the 2-bit copy */
+            if (qd < quads) {
+                const uint32_t X = __funnelshift_r(w0, w1, s2);
+                w0 = w1; w1 = __ldg(pw++);
+                uint32_t sw[4], qw[4];
+#pragma unroll
+                for (uint32_t h = 0; h < 4; ++h) group4<TK>(rp, tab_s, lut_s, qconst, X, h, g + h, rng, sw[h], qw[h]);
+                if (qd == 0) { first_s = sw[0]; first_q = qw[0]; }
+                rl_quad(ls, 4u * qd, sw[0], sw[1], sw[2], sw[3]); rl_quad(lq, 4u * qd, qw[0], qw[1], qw[2], qw[3]);
+                g += 4;
             }
         }
-        if (!__any_sync(0xffffffffu, busy)) break;
-        if (busy) {                                       /* four groups = one word of the 2-bit copy */
-            const uint32_t X = __funnelshift_r(w0, w1, s2);
-            w0 = w1; w1 = __ldg(pw++);
-            uint32_t sw[4], qw[4];
-#pragma unroll
-            for (uint32_t h = 0; h < 4; ++h) group4<TK>(rp, tab_s, lut_s, qconst, X, h, g + h, rng, sw[h], qw[h]);
-            if (k == 0) { first_s = sw[0]; first_q = qw[0]; }
-            rl_quad(ls, k, sw[0], sw[1], sw[2], sw[3]); rl_quad(lq, k, qw[0], qw[1], qw[2], qw[3]);
-            k += 4; g += 4;
-            --quads_left;
+        if (ng) {
+            const uint32_t kl = 4u * (quads - 1u);
+            rl_close(ls, kl, ng); rl_edges(ls, kl, ng, first_s); rl_close(lq, kl, ng); rl_edges(lq, kl, ng, first_q);
         }
     }
 }

@@ -224,11 +224,11 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.desc = ctx->d_desc.as<UnitDesc>();
     rp.block_sums = ctx->d_block_sums.as<uint64_t>(); rp.counters = ctx->d_counters.as<unsigned long long>();
     rp.stage_cap = pl.stage_cap; rp.tab_rep = pl.tab_rep;
-    {   /* MWC64X skip-ahead multipliers: A^(LONG_PART_GROUPS * p) mod (A * 2^32 - 1) */
+    {   /* MWC64X skip-ahead multipliers: A^(LONG_GRANULE * k) mod (A * 2^32 - 1) */
         const unsigned __int128 mod = (unsigned __int128)(4294883355ull * 4294967296ull - 1ull);
         unsigned __int128 step = 1, acc = 1;
-        for (uint32_t i = 0; i < LONG_PART_GROUPS; ++i) step = step * 4294883355ull % mod;
-        for (uint32_t p_ = 0; p_ < LONG_PARTS; ++p_) { rp.mwc_skip[p_] = uint64_t(acc); acc = acc * step % mod; }
+        for (uint32_t i = 0; i < LONG_GRANULE; ++i) step = step * 4294883355ull % mod;
+        for (uint32_t k = 0; k < LONG_JUMPS; ++k) { rp.mwc_skip[k] = uint64_t(acc); acc = acc * step % mod; }
     }
 }
 
