@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                   "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -87,15 +87,17 @@ class ClockSampler(threading.Thread):
             line = p.stdout.readline()
             if not line:
                 break
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
         p.terminate()
 
-    def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+    def summary(self, t0=None, t1=None):
+        """Samples taken inside [t0, t1] (the timed region); all samples if that leaves none."""
+        rows = [r for t, r in self.rows if t0 is None or t0 <= t <= t1] or [r for _, r in self.rows]
+        sm = [float(r[1]) for r in rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = []
         for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
-            if any(len(r) >= 8 and r[col].lower().startswith("active") for r in self.rows):
+            if any(len(r) >= 8 and r[col].lower().startswith("active") for r in rows):
                 reasons.append(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
@@ -196,11 +198,12 @@ def main():
     total_units = eng.total_units(reads)
     ub, ue = rank * total_units // world, (rank + 1) * total_units // world
 
-    for _ in range(args.warmup):
-        eng.simulate(reads, SEED, unit_begin=ub, unit_end=ue)
     sampler = ClockSampler(local)
     sampler.start()
+    for _ in range(args.warmup):
+        eng.simulate(reads, SEED, unit_begin=ub, unit_end=ue)
     barrier()
+    t_timed0 = time.perf_counter()
     dev_ms = fmt_ms = 0.0
     bases = records = alg = launches = 0
     for _ in range(args.steps):
@@ -208,6 +211,7 @@ def main():
         dev_ms += st["device_ms"]; fmt_ms += st["format_ms"]
         bases += st["bases"]; records += st["records"]; alg += st["algorithmic_bytes"]; launches += st["kernel_launches"]
     barrier()
+    t_timed1 = time.perf_counter()
     sampler.stop_flag.set()
     t = torch.tensor([dev_ms, float(bases), float(records)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -253,7 +257,7 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u8", "data": "synthetic", "config": workload_config(world),
-               "reads_per_second": all_records / (max_ms / 1e3), "clocks": sampler.summary(), "gpu_launches": launches,
+               "reads_per_second": all_records / (max_ms / 1e3), "clocks": sampler.summary(t_timed0, t_timed1), "gpu_launches": launches,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(gs.bases.nbytes),
                        "d2h_bytes_per_step": int(e2e_d2h // max(1, args.e2e_steps)), "steps": args.e2e_steps},
                "roofline": {"bound": "hbm", "kernel": "k_format_warps", "achieved": achieved, "peak": peak, "unit": "GB/s",
