@@ -189,6 +189,8 @@ int  simmr_write_metadata(const char *output, uint32_t n, const char *const *uui
                           const char *const *path, const uint64_t *num_reads, const double *abundance);
 
 /* ---- introspection used by the parity tests (host only) ----------------- */
+/* kind 3 (short reads) of a mutating profile: the (npos << cb) quality words are followed by the 256 words of the
+ * substitution-gap table and the (1 << cb) words of the quality-given-substitution table */
 int  simmr_debug_phred_table(const simmr_eprofile_desc *desc, uint32_t *kind, uint32_t *cb, uint32_t *npos,
                              uint32_t *const_q, uint32_t *entries, uint64_t cap);
 int  simmr_debug_len_table(const simmr_eprofile_desc *desc, int which, uint32_t *kind, uint32_t *cb,

@@ -213,6 +213,18 @@ struct BaseWords {
         return r;
     }
 };
+/* Short reads: one Philox block (0, stream, unit) seeds two MWC64X chains of the record — words 0,1 the
+ * quality chain (base i takes its i-th output), words 2,3 the substitution-event chain. */
+struct Chain {
+    uint32_t x, c;
+    Chain(uint32_t w_even, uint32_t w_odd) : x(w_even), c((w_odd >> 2) + 1) {}
+    uint32_t next() {
+        const uint32_t r = x ^ c;
+        const uint64_t t = (uint64_t)x * 4294883355u + c;
+        x = (uint32_t)t; c = (uint32_t)(t >> 32);
+        return r;
+    }
+};
 inline uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
@@ -430,7 +442,12 @@ struct PhredTable {      /* per-position alias tables */
                             2: T32 thr16<<16 | q_alias<<8 | q_self (no mutation) */
     uint8_t const_q = 0;
     uint32_t cb = 0, npos = 0;
-    std::vector<uint32_t> entries;   /* kind 1: 2 words per column, kind 2: 1 word per column */
+    std::vector<uint32_t> entries;   /* kind 1: 2 words per column, kind 2 and 3: 1 word per column */
+    /* kind 3 (short reads): the kind-2 word, sampled with column = low cb bits of the draw and "self iff draw < word";
+     * a mutating profile adds gap[256] (bases until the next substitution, 255 = none within 255) and
+     * qsub[1 << cb] (quality given a substitution) */
+    bool has_sub = false;
+    std::vector<uint32_t> gap, qsub;
 };
 struct LenTable {
     uint32_t kind = 0;   /* 0 const, 1 alias over bins, 2 Marsaglia-Tsang gamma */
@@ -479,9 +496,50 @@ bool phred_table_from_pmf(const std::vector<double> &pq, uint32_t qlo, PhredTabl
     }
     return true;
 }
+/* kind 3 word: a column whose 16-bit threshold is zero names its alias twice, so that the payload bits of the word
+ * cannot make the sampler keep a column that has no mass */
+inline uint32_t q32_entry(double prob, uint32_t self_v, uint32_t alias_v) {
+    const uint32_t thr = quant_thr(prob, 16);
+    if (thr == 0) self_v = alias_v;
+    return (thr << 16) | ((alias_v & 0xffu) << 8) | (self_v & 0xffu);
+}
+bool q32_table(const std::vector<double> &w, uint32_t vlo, uint32_t cb, std::vector<uint32_t> &out) {
+    std::vector<double> prob; std::vector<uint32_t> alias;
+    if (!vose(w, cb, prob, alias)) return false;
+    out.resize(prob.size());
+    for (size_t i = 0; i < prob.size(); i++) out[i] = q32_entry(prob[i], vlo + (uint32_t)i, vlo + alias[i]);
+    return true;
+}
+/* Short reads of a mutating profile.  minimal_short.rs:83-140 draws q, then substitutes with probability pm(q),
+ * independently per base.  The same joint law, factored the other way: a base is substituted with the marginal
+ * probability s = sum_q P(q) pm(q); a substituted base's quality follows P(q | substituted), any other base's
+ * P(q | kept).  The substituted bases of a record are then found by geometric gaps. */
+bool phred_short_table_from_pmf(const std::vector<double> &pq, uint32_t qlo, PhredTable &t) {
+    const size_t n = pq.size();
+    std::vector<double> kept(n), subst(n);
+    double s = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        const double pm = mutation_prob((uint8_t)(qlo + i));
+        kept[i] = pq[i] * (1.0 - pm); subst[i] = pq[i] * pm;
+        s += subst[i];
+    }
+    t.kind = 3; t.npos = 1; t.cb = std::max(1u, ceil_log2(n));
+    if (t.cb > 8) return false;
+    if (!q32_table(kept, qlo, t.cb, t.entries)) return false;
+    t.has_sub = s > 0.0;
+    if (t.has_sub) {
+        if (!q32_table(subst, qlo, t.cb, t.qsub)) return false;
+        std::vector<double> gap(256);
+        double none = 1.0;
+        for (uint32_t k = 0; k < 255; k++) { gap[k] = s * none; none = none * (1.0 - s); }
+        gap[255] = none;
+        if (!q32_table(gap, 0, 8, t.gap)) return false;
+    }
+    return true;
+}
 /* per-position tables from the blob: alias over densities, uniform in-bin,
  * `as u8` truncation (custom_short.rs:108-129, 328-352); no mutation */
-bool phred_table_from_blob(const Blob &b, PhredTable &t) {
+bool phred_table_from_blob(const Blob &b, bool long_reads, PhredTable &t) {
     size_t np = b.quality.size();
     if (np == 0) return false;
     std::vector<std::vector<double>> pm(np, std::vector<double>(256, 0.0));
@@ -507,7 +565,7 @@ bool phred_table_from_blob(const Blob &b, PhredTable &t) {
         }
     }
     if (qmin > qmax) return false;
-    t.kind = 2; t.npos = (uint32_t)np;
+    t.kind = long_reads ? 2 : 3; t.npos = (uint32_t)np;
     t.cb = std::max(1u, ceil_log2(qmax - qmin + 1));
     t.entries.clear();
     for (size_t p = 0; p < np; p++) {
@@ -515,7 +573,8 @@ bool phred_table_from_blob(const Blob &b, PhredTable &t) {
         std::vector<uint32_t> alias;
         if (!vose(w, t.cb, prob, alias)) return false;
         for (size_t i = 0; i < prob.size(); i++)
-            t.entries.push_back((quant_thr(prob[i], 16) << 16) | (((qmin + alias[i]) & 0xffu) << 8) | ((qmin + (uint32_t)i) & 0xffu));
+            t.entries.push_back(long_reads ? (quant_thr(prob[i], 16) << 16) | (((qmin + alias[i]) & 0xffu) << 8) | ((qmin + (uint32_t)i) & 0xffu)
+                                           : q32_entry(prob[i], qmin + (uint32_t)i, qmin + alias[i]));
     }
     return true;
 }
@@ -570,7 +629,7 @@ bool make_profile(const orc_profile *in, Profile &p) {
         p.min_size = (uint16_t)(2 * p.read_length + p.insert_size);
         uint32_t vlo; std::vector<double> pmf;
         normal_floor_pmf((double)(float)p.mean_phred, 10.0, 255, vlo, pmf);
-        if (!phred_table_from_pmf(pmf, vlo, p.phred)) { fail("phred table"); return false; }
+        if (!phred_short_table_from_pmf(pmf, vlo, p.phred)) { fail("phred table"); return false; }
         normal_floor_pmf((double)p.read_length, 15.0, 65535, vlo, pmf);
         if (!len_table_from_pmf(pmf, vlo, p.rl)) { fail("rl table"); return false; }
         normal_floor_pmf((double)p.insert_size, 75.0, 65535, vlo, pmf);
@@ -592,14 +651,14 @@ bool make_profile(const orc_profile *in, Profile &p) {
     case ORC_CUSTOM_SHORT: {  /* custom_short.rs:155-229, 237-270, 522-542 */
         p.is_long = p.blob.is_long; p.mutates = false;
         p.min_size = sat_u16(2.0 * p.blob.rl_mean + p.blob.is_mean);
-        if (!phred_table_from_blob(p.blob, p.phred)) { fail("custom phred table"); return false; }
+        if (!phred_table_from_blob(p.blob, p.is_long, p.phred)) { fail("custom phred table"); return false; }
         if (!len_table_from_bins(p.blob.rl_bins, p.rl)) { fail("custom rl table"); return false; }
         if (p.blob.has_is_bins) { if (!len_table_from_bins(p.blob.is_bins, p.is)) { fail("custom is table"); return false; } }
         else { p.is.kind = 0; p.is.value = 0; }
         break; }
     case ORC_CUSTOM_LONG: {   /* phreds as custom-short, gamma lengths */
         p.is_long = true; p.mutates = false; p.min_size = 20000;
-        if (!phred_table_from_blob(p.blob, p.phred)) { fail("custom phred table"); return false; }
+        if (!phred_table_from_blob(p.blob, true, p.phred)) { fail("custom phred table"); return false; }
         p.rl.kind = 2; p.is.kind = 0; p.is.value = 0;
         break; }
     default: fail("unknown profile kind"); return false;
@@ -638,6 +697,11 @@ inline void sample_phred(const PhredTable &t, uint32_t pos, uint32_t w, uint8_t 
         const uint32_t e = t.entries[col];
         q = (uint8_t)((x >> 16) < (e >> 16) ? (e & 0xffu) : ((e >> 8) & 0xffu)); m = 0;
     }
+}
+/* kind 3 word against a draw: column = low cb bits, self iff draw < word */
+inline uint32_t sample_q32(const uint32_t *row, uint32_t cb, uint32_t w) {
+    const uint32_t e = row[w & ((1u << cb) - 1u)];
+    return (w < e ? e : e >> 8) & 0xffu;
 }
 /* minimal_short.rs:124-131 substitution table */
 inline uint8_t substitute(uint8_t nt, uint32_t k) {
@@ -845,6 +909,34 @@ void native_read(const Profile &p, const Philox &ph, uint64_t u, uint32_t stream
     }
 }
 
+/* one mate of a short read in native mode: qualities from the record's quality chain, then the
+ * substituted bases by geometric gaps along the window (forward-strand order, simulate.rs:265-270) */
+void native_read_short(const Profile &p, const Philox &ph, uint64_t u, uint32_t stream, const uint8_t *src, uint64_t L,
+                       std::vector<uint8_t> &seq, std::vector<uint8_t> &qual, orc_stats &st) {
+    seq.assign(src, src + L); qual.resize(L);
+    const PhredTable &t = p.phred;
+    if (t.kind == 0) { std::fill(qual.begin(), qual.end(), t.const_q); return; }
+    uint32_t w[4]; ph.at(u, stream, 0, w);
+    Chain qc(w[0], w[1]), ec(w[2], w[3]);
+    for (uint64_t i = 0; i < L; i++) {
+        const uint64_t pos = std::min<uint64_t>(i, t.npos - 1);                 /* custom_short.rs:339-345 */
+        qual[i] = (uint8_t)sample_q32(t.entries.data() + (pos << t.cb), t.cb, qc.next());
+    }
+    if (!t.has_sub) return;
+    for (uint64_t next = 0; next < L;) {               /* every step takes three words of the event chain */
+        const uint32_t r1 = ec.next(), r2 = ec.next(), r3 = ec.next();
+        const uint32_t g = sample_q32(t.gap.data(), 8, r1);
+        if (g == 255) { next += 255; continue; }
+        const uint64_t at = next + g;
+        if (at >= L) break;
+        qual[at] = (uint8_t)sample_q32(t.qsub.data(), t.cb, r2);
+        const uint8_t nb = substitute_native(seq[at], 1u + mulhi32(r3, 3u));
+        if (nb != seq[at]) st.mutated++;
+        seq[at] = nb;
+        next = at + 1;
+    }
+}
+
 int64_t finish(std::vector<uint8_t> &buf, uint8_t *out, uint64_t cap) {
     if (out) { if (buf.size() > cap) return -(int64_t)buf.size(); memcpy(out, buf.data(), buf.size()); }
     return (int64_t)buf.size();
@@ -1010,9 +1102,11 @@ int orc_profile_is_long(const orc_profile *pi, int *out) { Profile p; if (!make_
 int orc_profile_phred_table(const orc_profile *pi, uint32_t *kind, uint32_t *cb, uint32_t *npos, uint32_t *const_q, uint32_t *entries, uint64_t cap) {
     Profile p; if (!make_profile(pi, p)) return -1;
     *kind = p.phred.kind; *cb = p.phred.cb; *npos = p.phred.npos; *const_q = p.phred.const_q;
-    if (p.phred.entries.size() > cap) return fail("table buffer too small");
-    if (!p.phred.entries.empty()) memcpy(entries, p.phred.entries.data(), p.phred.entries.size() * 4);
-    return (int)p.phred.entries.size();
+    std::vector<uint32_t> all = p.phred.entries;      /* kind 3 of a mutating profile: followed by gap[256] and qsub[1 << cb] */
+    if (p.phred.has_sub) { all.insert(all.end(), p.phred.gap.begin(), p.phred.gap.end()); all.insert(all.end(), p.phred.qsub.begin(), p.phred.qsub.end()); }
+    if (all.size() > cap) return fail("table buffer too small");
+    if (!all.empty()) memcpy(entries, all.data(), all.size() * 4);
+    return (int)all.size();
 }
 int orc_profile_len_table(const orc_profile *pi, int which, uint32_t *kind, uint32_t *cb, uint32_t *entries, uint32_t *lo, uint32_t *hi, uint64_t cap) {
     Profile p; if (!make_profile(pi, p)) return -1;
@@ -1129,8 +1223,8 @@ int64_t orc_simulate(const orc_genomes *g, const orc_profile *pi, const uint64_t
         if (!p.is_long) {
             const PeGeom &pg = ng.pe;
             if (pg.clamped) st.clamped++;
-            native_read(p, ph, u, 1, cs + pg.fs, pg.fe - pg.fs, s1, q1, st);           /* :261,265,269 */
-            native_read(p, ph, u, 2, cs + pg.lo, pg.hi - pg.lo, s2, q2, st);           /* :262,266,270 */
+            native_read_short(p, ph, u, 1, cs + pg.fs, pg.fe - pg.fs, s1, q1, st);     /* :261,265,269 */
+            native_read_short(p, ph, u, 2, cs + pg.lo, pg.hi - pg.lo, s2, q2, st);     /* :262,266,270 */
             auto rc = reverse_complement(s2.data(), s2.size());                       /* :283; quality NOT reversed :285 */
             emit_record(buf, fmt, gid, id, sid, pg.fs, ng.start + ng.RL, false, 1, s1, q1);   /* :287-292: end_pos = fwd_end */
             emit_record(buf, fmt, gid, id, sid, pg.lo + (uint64_t)ng.RL, pg.lo, true, 2, rc, q2);   /* :293-298: start=rev_start, end=rev_end */

@@ -77,9 +77,12 @@ int simmr_debug_phred_table(const simmr_eprofile_desc *d, uint32_t *kind, uint32
     const int rc = build_profile(d, m, err);
     if (rc) return flunk(rc, err);
     *kind = m.phred_kind; *cb = m.cb; *npos = m.npos; *const_q = m.const_q;
-    if (m.phred_entries.size() > cap) return flunk(SIMMR_E_INVALID, "buffer too small");
-    if (!m.phred_entries.empty()) memcpy(entries, m.phred_entries.data(), m.phred_entries.size() * 4);
-    return int(m.phred_entries.size());
+    /* PT_Q32 of a mutating profile: the quality table is followed by gap[256] and qsub[1 << cb] */
+    std::vector<uint32_t> all = m.phred_entries;
+    if (m.has_sub) { all.insert(all.end(), m.gap_entries.begin(), m.gap_entries.end()); all.insert(all.end(), m.qsub_entries.begin(), m.qsub_entries.end()); }
+    if (all.size() > cap) return flunk(SIMMR_E_INVALID, "buffer too small");
+    if (!all.empty()) memcpy(entries, all.data(), all.size() * 4);
+    return int(all.size());
 }
 int simmr_debug_len_table(const simmr_eprofile_desc *d, int which, uint32_t *kind, uint32_t *cb, uint32_t *entries, uint32_t *lo, uint32_t *hi, uint64_t cap) {
     ProfileModel m; std::string err;

@@ -5,7 +5,8 @@
  *   fastq.rs:34-57 header interpolation, record size             -> k_unit_sizes, header_fast(), emit_header()
  *   (no reference equivalent: byte offsets of the FASTQ stream)   -> k_scan_blocks, k_unit_offsets
  *   simulate.rs:261-286 + error_profiles/ *.rs phreds/mutation +
- *   util.rs:15-57 RC / +33 + fastq.rs:61-69 record layout         -> k_format_tiles, k_format_direct
+ *   util.rs:15-57 RC / +33 + fastq.rs:61-69 record layout         -> k_format_lanes (short reads), k_format_long,
+ *                                                                    k_format_direct (replay of long reads, oversize records)
  *   (load-time) 2-bit copy of the contigs + which 32-byte blocks
  *   hold only A,C,G,T                                            -> k_pack
  *
@@ -61,22 +62,28 @@ struct RunParams {
     uint32_t *sizes; uint64_t *offsets, *block_sums; uint8_t *out;
     struct UnitDesc *desc;         /* per-unit geometry written by k_unit_sizes, read by the format kernels */
     unsigned long long *counters;  /* [0] clamped [1] algorithmic bytes [2] bases [3] records */
-    /* per-warp stage of k_format_warps */
-    uint32_t stage_cap;            /* bytes of a warp's stage in k_format_warps */
+    /* per-warp stage of k_format_lanes */
+    uint32_t stage_cap;            /* bytes of a warp's stage in k_format_lanes */
     /* decimal fields of the header template when every contig has the same ones (fastq.rs:34-57): hdr_fast == 0 means
      * per-contig lists only; kinds 4 bits each, field i in bits 4*i */
     uint32_t hdr_fast, hdr_fields, hdr_kinds;
 };
 
 constexpr int SIZES_THREADS = 256;
-constexpr int FORMAT_THREADS = 768;   /* most threads of a format CTA (each warp has a private stage) -> register cap of 85 */
+constexpr int FORMAT_THREADS = 512;   /* most threads of a format CTA (each warp has a private stage) -> register cap of 128 */
 constexpr int FORMAT_MIN_CTAS = 1;
 constexpr int DIRECT_THREADS = 256;
-constexpr int SUB = 4;                /* lanes that share one record = runs of the per-base word schedule */
-constexpr uint32_t PACK_PAD_WORDS = 1024; /* readable words past the end of `packed`     */
-/* shared-memory layout of a tile CTA (byte offsets from the 1024-aligned base) */
+constexpr uint32_t PACK_PAD_WORDS = 4104; /* readable words before and after `packed`: a lane keeps fetching (and discarding)
+                                             for as long as the longest record of its warp lasts, at most 65535 / 16 words */
+/* shared-memory layout of a format CTA (byte offsets from the 1024-aligned base); SM_TAB: quality table of the long-read
+ * and direct kernels; the short-read kernel keeps gap / qsub / quality tables at SM_GAP / SM_QSUB / SM_QTAB */
 constexpr uint32_t SM_LUT_FWD = 0, SM_LUT_RC = 1024, SM_DEC2 = 2048, SM_TAB = 2304;
+constexpr uint32_t SM_GAP = 2304, SM_QSUB = 3328, SM_QTAB = 4352;
 constexpr uint32_t STAGE_FRONT = 16;  /* slack before the tile image (a header's leading newline may land there) */
+/* how k_format_lanes samples qualities */
+enum : int { QM_CONST = 0,            /* one quality for every base                                              */
+             QM_LANE = 1,             /* one position, every lane has its own copy of the table (no bank conflicts) */
+             QM_POS = 2 };            /* one table per position, a single copy                                   */
 
 /* ---------------------------------------------------------------------- */
 /* small PTX helpers                                                        */
@@ -139,6 +146,17 @@ __device__ __forceinline__ uint32_t mwc_next(uint32_t &x, uint32_t &c) {
     x = uint32_t(t); c = uint32_t(t >> 32);
     return r;
 }
+
+/* Short reads: one Philox block (0, stream, unit) seeds the two chains of a record — words 0,1 the quality
+ * chain (base i of the window takes its i-th output), words 2,3 the substitution-event chain. */
+struct Mwc1 { uint32_t x, c; };
+__device__ __forceinline__ uint32_t mwc1_next(Mwc1 &m) { return mwc_next(m.x, m.c); }
+__device__ __forceinline__ void mwc1_seed(const RunParams &rp, Mwc1 &qc, Mwc1 &ec, uint32_t stream, uint32_t ulo, uint32_t uhi) {
+    const Philox4 w = philox(rp.rk, 0u, stream, ulo, uhi);
+    qc.x = w.x; qc.c = (w.y >> 2) + 1u; ec.x = w.z; ec.c = (w.w >> 2) + 1u;
+}
+/* PT_Q32 word against a draw whose low cb bits picked the column: self iff draw < word */
+__device__ __forceinline__ uint32_t q32_pick(uint32_t e, uint32_t w) { return (w < e ? e : e >> 8) & 0xffu; }
 
 /* ---------------------------------------------------------------------- */
 /* samplers                                                                 */
@@ -418,6 +436,41 @@ __device__ __forceinline__ void native_base(const RunParams &rp, const uint32_t 
     }
 }
 
+/* Short reads, native mode, one thread and byte stores: the record's quality chain, then its substitution events
+ * (DESIGN.md §4).  Used for windows that hold anything but A,C,G,T and for records that do not fit a stage; same
+ * bytes as the word path of k_format_lanes.  Tables are read from global memory (qualities carry the +33). */
+template <bool PUNCT>
+__device__ void emit_body_short(const RunParams &rp, uint8_t *dst, uint64_t unit, uint32_t mate, uint64_t a, uint32_t L) {
+    uint8_t *seq = dst + 1, *qual = dst + L + 4;
+    if (PUNCT) { dst[0] = '\n'; dst[L + 1] = '\n'; dst[L + 2] = '+'; dst[L + 3] = '\n'; dst[2 * L + 4] = '\n'; }   /* fastq.rs:61-69 */
+    const uint8_t *src = rp.bases + a;
+    const bool rc = mate != 0;
+    Mwc1 qc{}, ec{};
+    const bool sampled = rp.phred.kind != PT_CONST;
+    if (sampled) mwc1_seed(rp, qc, ec, 1 + mate, uint32_t(unit), uint32_t(unit >> 32));
+    const uint32_t mask = rp.phred_mult - 1u, last = rp.phred.npos - 1u;
+    for (uint32_t i = 0; i < L; ++i) {
+        uint32_t qc8 = (rp.phred.const_q + 33u) & 0xffu;
+        if (sampled) { const uint32_t r = mwc1_next(qc); qc8 = q32_pick(__ldg(rp.phred.entries + (min(i, last) << rp.phred.cb) + (r & mask)), r); }
+        qual[i] = uint8_t(qc8);
+        const uint8_t b = __ldg(src + i);
+        if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;               /* util.rs:31-37 */
+    }
+    if (!sampled || !rp.phred.has_sub) return;
+    for (uint32_t next = 0; next < L;) {                                        /* three words of the event chain per step */
+        const uint32_t r1 = mwc1_next(ec), r2 = mwc1_next(ec), r3 = mwc1_next(ec);
+        const uint32_t g = q32_pick(__ldg(rp.phred.gap + (r1 & (GAP_COLS - 1u))), r1);
+        if (g == GAP_NONE) { next += GAP_NONE; continue; }
+        const uint32_t at = next + g;
+        if (at >= L) break;
+        qual[at] = uint8_t(q32_pick(__ldg(rp.phred.qsub + (r2 & mask)), r2));
+        uint8_t *sb = rc ? seq + (L - 1 - at) : seq + at;                      /* mutated before the reverse complement (simulate.rs:269-286) */
+        const uint8_t fwd = rc ? complement(*sb) : *sb, nb = substitute_native(fwd, 1u + __umulhi(r3, 3u));
+        *sb = rc ? complement(nb) : nb;
+        next = at + 1u;
+    }
+}
+
 /* Writes the sequence and quality lines of one record with byte stores (and, when PUNCT, the
  * five fixed bytes around them); `dst` = the byte after the header, in shared or global
  * memory.  Base i of the window gets quality slot i; for mate 2 the (mutated) base is
@@ -456,19 +509,11 @@ __device__ __forceinline__ void emit_body_generic(const RunParams &rp, const Rep
 /* ---------------------------------------------------------------------- */
 /* per-base work, fast path: windows of pure A/C/G/T                        */
 /* ---------------------------------------------------------------------- */
-/* A record body is "\nSEQ\n+\nQUAL\n".  SUB lanes share one record; lane sl owns the T
- * consecutive 4-base groups g0 = sl*T .. g0+T-1 (T is common to the warp).  Per group it
- *   - runs one Philox4x32-10 block (4 words, one per base),
- *   - turns each word into (quality char, mutation code) through the alias table in
- *     shared memory,
- *   - takes the group's 4 bases as one byte of the 2-bit genome copy, XORs the packed
- *     mutation codes into it and maps the byte to 4 ASCII letters through a 256-entry
- *     table in shared memory (a second table gives the reverse complement for mate 2),
- *   - funnel-shifts its word against the previous group's into the 4-byte aligned words
- *     of the stage and stores them with 32-bit shared-memory stores.
- * The first and last aligned word of a line also cover up to 3 bytes outside the line;
- * those always belong to a header or to the fixed "\n", "\n+\n", "\n" bytes, which are
- * written after a CTA barrier (phase 2 of the tile), so the spill is harmless. */
+/* Long reads (k_format_long): per 4-base group
+ *   - four words, one per base, from the run's four MWC64X chains,
+ *   - each word becomes (quality char, mutation code) through the alias table in shared memory,
+ *   - the group's 4 bases are one byte of the 2-bit genome copy: XOR the packed mutation codes into it and map the
+ *     byte to 4 ASCII letters through a 256-entry table in shared memory. */
 
 __device__ __forceinline__ uint32_t lds32m(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ uint32_t lds16(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
@@ -522,67 +567,6 @@ __device__ __forceinline__ void group4(const RunParams &rp, uint32_t tab_s, uint
     uint32_t at = (bi == 0 ? X << 2 : X >> (8 * bi - 2)) & 0x3fcu;
     if (TK == PT_T64) at ^= ((mw * 0x01041040u) >> 22) & 0x3fcu;     /* XOR the four 2-bit substitution codes into the byte */
     sw = lds32(lut_s + at);
-}
-
-/* Sequence and quality lines of one record by the SUB lanes of a sub-group, all 32 lanes of
- * the warp converged (lanes whose sub-group has no fast record run with on = false and store
- * nothing).  Lane sl owns run sl of the record's word schedule — run_groups(L) consecutive groups,
- * taken two at a time — while the warp loops for the longest run among its records (T2 pairs).  RC: mate 2 — bases complemented and written back to
- * front (util.rs:31-37); the quality line is never reversed (simulate.rs:283-285).  body_s =
- * shared-space address of the '\n' that ends the header; lut_s = ASCII table of this strand. */
-template <int TK, bool RC>
-__device__ __forceinline__ void body_fast(const RunParams &rp, uint32_t tab_s, uint32_t lut_s, bool on, uint32_t body_s,
-                                          uint32_t ulo, uint32_t uhi, uint32_t stream, uint64_t a, uint32_t L, uint32_t sl, uint32_t T2) {
-    if (!on) { L = 0; a = 0; body_s = 0; }
-    const uint32_t rho = run_groups(L), g0 = sl * rho;
-    /* aligned words of the two lines: slot k of the sequence line sits at ps + 4k (ps - 4k when RC), of the quality line at pq + 4k */
-    const uint32_t Ds = body_s + 1, Dq = body_s + L + 4;
-    uint32_t sh_s, kw_s, ps;
-    if (!RC) { const uint32_t o = Ds & 3u; sh_s = 8u * o; kw_s = (L + o + 3u) >> 2; ps = (Ds - o) + 4u * g0; }
-    else { const uint32_t E = Ds + L, c = ((E - 1u) & 3u) + 1u; sh_s = 8u * c; kw_s = ((L + 3u - c) >> 2) + 1u; ps = (E - c) - 4u * g0; }
-    const uint32_t oq = Dq & 3u, sh_q = 8u * oq;
-    uint32_t kw_q = (L + oq + 3u) >> 2, pq = (Dq - oq) + 4u * g0;
-    if (!on) kw_s = kw_q = 0;
-    /* slots this lane may store, per line (the rest of its 2*T2 lie past the end of the line) */
-    int32_t ns = min(int32_t(kw_s) - int32_t(g0), int32_t(rho)), nq = min(int32_t(kw_q) - int32_t(g0), int32_t(rho));
-    const uint32_t ps0 = ps, pq0 = pq;
-    const bool st0s = ns > 0, st0q = nq > 0;
-    /* 16 bases per word of the 2-bit copy; this lane's run starts at base a + 4*g0 */
-    const uint64_t b0 = a + 4ull * g0;
-    const uint32_t *pw = rp.packed + (b0 >> 4);
-    const uint32_t s2 = 2u * (uint32_t(b0) & 15u);
-    uint32_t w0 = __ldg(pw), w1 = __ldg(pw + 1);
-    const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u;
-    uint32_t first_s = 0, first_q = 0, prev_s = 0, prev_q = 0, last_s = 0, last_q = 0, g = g0;
-    Mwc4 rng{};
-    if (TK != PT_CONST) mwc_seed(rp, rng, sl, stream, ulo, uhi);
-    auto compose_s = [&](uint32_t older, uint32_t newer) { return RC ? __funnelshift_lc(newer, older, sh_s) : __funnelshift_l(older, newer, sh_s); };
-    auto compose_q = [&](uint32_t older, uint32_t newer) { return TK == PT_CONST ? qconst : __funnelshift_l(older, newer, sh_q); };
-    for (uint32_t p = 0; p < T2; p += 2) {           /* one word of the 2-bit copy = 4 groups = 2 pairs */
-        const uint32_t X = __funnelshift_r(w0, w1, s2);
-        w0 = w1; w1 = __ldg(pw + 2 + (p >> 1));
-#pragma unroll
-        for (uint32_t h = 0; h < 2; ++h) {
-            if (h == 1 && p + 1 >= T2) break;
-            uint32_t sa, qa, sb, qb;
-            group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h, g, rng, sa, qa);
-            group4<TK>(rp, tab_s, lut_s, qconst, X, 2 * h + 1, g + 1, rng, sb, qb);
-            if (h == 0 && p == 0) { first_s = sa; first_q = qa; }
-            else {
-                if (ns > 0) sts32(ps, compose_s(prev_s, sa));
-                if (nq > 0) sts32(pq, compose_q(prev_q, qa));
-            }
-            if (ns > 1) sts32(RC ? ps - 4u : ps + 4u, compose_s(sa, sb));
-            if (nq > 1) sts32(pq + 4u, compose_q(qa, qb));
-            prev_s = sb; prev_q = qb;
-            ps += RC ? uint32_t(-8) : 8u; pq += 8u; ns -= 2; nq -= 2; g += 2;
-            if (g - g0 == rho) { last_s = sb; last_q = qb; }      /* end of this lane's run: what the next lane's first slot needs */
-        }
-    }
-    /* slot g0 needs the last word of the lane to the left (lane 0: bytes before the line, repaired in phase 2) */
-    const uint32_t left_s = __shfl_up_sync(0xffffffffu, last_s, 1, SUB), left_q = __shfl_up_sync(0xffffffffu, last_q, 1, SUB);
-    if (st0s) sts32(ps0, compose_s(left_s, first_s));
-    if (st0q) sts32(pq0, compose_q(left_q, first_q));
 }
 
 /* ---------------------------------------------------------------------- */
@@ -786,66 +770,148 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_offsets(RunParams rp) {
 }
 
 
-/* pairs of 4-base groups each of the SUB lanes of a record takes: 2*SUB*T2 slots >= groups + 1 */
-__device__ __forceinline__ uint32_t pairs_per_lane(uint32_t L) { return run_groups(L) >> 1; }
-static_assert(SUB == 4, "the word schedule cuts every read into four runs");
+/* ---------------------------------------------------------------------- */
+/* short reads, word path: one lane per record                              */
+/* ---------------------------------------------------------------------- */
+/* Quality characters (+33 applied) of four consecutive bases, the first at window index i0 (the same for every lane of
+ * the warp): four steps of the record's quality chain, four look-ups.  QM_LANE: the lane's own copy of the single
+ * position's table (word col * 32 + lane: every lane stays in its bank); QM_POS: row min(i, npos-1) of the one copy. */
+template <int QM>
+__device__ __forceinline__ uint32_t quals4(const RunParams &rp, uint32_t qtab_s, uint32_t mask, Mwc1 &rng, uint32_t i0) {
+    uint32_t qw = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t r = mwc1_next(rng);
+        uint32_t at;
+        if (QM == QM_LANE) at = qtab_s + (r & mask) * 128u;
+        else at = qtab_s + ((min(i0 + j, rp.phred.npos - 1u) << rp.phred.cb) + (r & mask)) * 4u;     /* custom_short.rs:339-345 */
+        const uint32_t e = lds32(at);
+        /* byte j of qw <- byte 0 (self) or 1 (alias) of the entry; bytes below j stay */
+        const uint32_t keep = 0x3210u & ((1u << (4u * j)) - 1u);
+        qw = __byte_perm(qw, e, r < e ? (keep | (4u << (4u * j))) : (keep | (5u << (4u * j))));
+    }
+    return qw;
+}
 
-/* Persistent warps.  A warp owns WARP_UNITS consecutive units at a time: it composes their
- * FASTQ bytes in its private stage in shared memory and sends them off with one bulk async
- * copy (TMA); only the sampling tables are shared by the CTA, so there is no CTA barrier in
- * the loop.  A group of units whose bytes exceed the stage is cut into sub-tiles.
- *   phase 1  sequence and quality lines: SUB lanes per record, the 8 first mates, then the 8
- *            second mates (body_fast; byte stores for windows holding anything but A,C,G,T
- *            and for replay)
- *   phase 2  headers and the fixed newline / '+' bytes: one lane per record
- * TK = table kind the fast path is specialised for. */
-constexpr uint32_t WARP_UNITS = 32 / SUB;
-struct TileUnit {      /* one unit of the current tile, in shared memory */
-    UnitDesc d;
-    uint32_t off[2];   /* stage offsets of its records */
-    uint32_t pad_[2];
-};
+/* Sequence and quality lines of one record by one lane, all 32 lanes of the warp converged (a lane without a record for
+ * this path runs with on = false and stores nothing); the warp loops T16 times, 16 bases of every record per turn.
+ * A record body is "\nSEQ\n+\nQUAL\n"; body_s = shared-space address of the '\n' that ends the header.  Both lines are
+ * written front to back as 4-byte aligned words: a line's group of 4 characters is funnel-shifted against the previous
+ * group onto the word grid of the stage.  The first and last word of a line also cover up to 3 bytes outside it; those
+ * belong to this record's header or fixed bytes or to the next record's header, all written in phase 2.
+ * Mate 2 (rc) reads its window back to front — 16 bases = one 32-bit window of the 2-bit genome copy, byte-reversed,
+ * then the reverse-complement table turns each byte into 4 letters (util.rs:31-37) — while its quality line runs
+ * forward like mate 1's: quality i belongs to window base i, never reversed (simulate.rs:283-285).  Substitutions
+ * are applied afterwards (substitutions_lane), so the two lines are independent here. */
+template <int QM>
+__device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, uint32_t lut_s, bool on, bool rc, uint32_t body_s,
+                                          Mwc1 &rng, uint64_t a, uint32_t L, uint32_t T16) {
+    if (!on) { L = 0; a = 0; }
+    const uint32_t Ds = body_s + 1u, Dq = body_s + L + 4u;
+    const uint32_t os = Ds & 3u, oq = Dq & 3u, sh_s = 8u * os, sh_q = 8u * oq;
+    /* word slots of each line still to store: slot k = characters 4k - o .. 4k - o + 3 of the line */
+    int32_t ns = on ? int32_t((L + os + 3u) >> 2) : 0, nq = on ? int32_t((L + oq + 3u) >> 2) : 0;
+    uint32_t ps = Ds - os, pq = Dq - oq;
+    /* 32-bit windows of the 2-bit copy: mate 1 from the window's first base upwards, mate 2 from its last base downwards */
+    const int64_t bit = rc ? 2 * int64_t(a + L) - 32 : 2 * int64_t(a);
+    const uint32_t *pw = rp.packed + (bit >> 5);
+    const uint32_t s2 = uint32_t(bit) & 31u, rev = rc ? 0x0123u : 0x3210u;
+    const int32_t dw = rc ? -1 : 1;
+    const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u, mask = rp.phred_mult - 1u;
+    uint32_t prev_s = 0, prev_q = 0;
+    for (uint32_t it = 0; it < T16; ++it) {
+        const uint32_t X = __byte_perm(__funnelshift_r(__ldg(pw), __ldg(pw + 1), s2), 0u, rev);
+        pw += dw;
+#pragma unroll
+        for (uint32_t h = 0; h < 4; ++h) {
+            const uint32_t qw = QM == QM_CONST ? qconst : quals4<QM>(rp, qtab_s, mask, rng, 16u * it + 4u * h);
+            const uint32_t sw = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
+            if (ns > int32_t(h)) sts32(ps + 4u * h, __funnelshift_l(prev_s, sw, sh_s));
+            if (nq > int32_t(h)) sts32(pq + 4u * h, QM == QM_CONST ? qconst : __funnelshift_l(prev_q, qw, sh_q));
+            prev_s = sw; prev_q = qw;
+        }
+        ps += 16u; pq += 16u; ns -= 4; nq -= 4;
+    }
+}
+
+/* The substituted bases of one record (minimal_short.rs:104-140 through the factorisation of DESIGN.md §4): geometric
+ * gaps along the window; each event replaces the base (rank ^ m, the same for both strands because complementing is
+ * rank ^ 3) and its quality character.  Byte stores into the lines body_lane wrote. */
+__device__ __forceinline__ void substitutions_lane(const RunParams &rp, uint32_t gap_s, uint32_t qsub_s, bool on, bool rc, uint32_t body_s,
+                                                   Mwc1 &ev, uint32_t L) {
+    const uint32_t Ds = body_s + 1u, Dq = body_s + L + 4u, mask = rp.phred_mult - 1u;
+    uint32_t next = on ? 0u : L;
+    while (next < L) {
+        const uint32_t r1 = mwc1_next(ev), r2 = mwc1_next(ev), r3 = mwc1_next(ev);
+        const uint32_t g = q32_pick(lds32(gap_s + 4u * (r1 & (GAP_COLS - 1u))), r1);
+        if (g == GAP_NONE) { next += GAP_NONE; continue; }
+        const uint32_t at = next + g;
+        if (at >= L) break;
+        sts8(Dq + at, q32_pick(lds32(qsub_s + 4u * (r2 & mask)), r2));
+        const uint32_t sa = Ds + (rc ? L - 1u - at : at);
+        uint32_t b; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(sa) : "memory");
+        uint32_t rank = (b >> 1) & 3u; rank ^= rank >> 1;                       /* A,C,G,T -> 0..3 */
+        sts8(sa, (0x54474341u >> (8u * (rank ^ (1u + __umulhi(r3, 3u))))) & 0xffu);
+        next = at + 1u;
+    }
+}
+
+
+/* Persistent warps, one lane per record.  A warp owns WARP_UNITS consecutive units (32 records) at a time: it composes
+ * their FASTQ bytes in its private stage in shared memory and sends them off with one bulk async copy (TMA); only the
+ * tables are shared by the CTA, so there is no CTA barrier in the loop.  A group of units whose bytes exceed the stage is
+ * cut into sub-tiles.  Lane 2k + m holds mate m of unit k.
+ *   phase 1  sequence and quality lines (body_lane, then substitutions_lane); byte stores for windows holding anything
+ *            but A,C,G,T and for replay
+ *   phase 2  headers and the fixed newline / '+' bytes, by the same lane
+ * QM = how qualities are sampled (QM_*). */
+constexpr uint32_t WARP_UNITS = 16;
 /* header fields of record r of a unit (simulate.rs:287-298, :513-518) */
 __device__ __forceinline__ void record_positions(const UnitDesc &d, uint32_t r, uint64_t &sp, uint64_t &ep) {
     if (!(d.flags & 4u)) { sp = d.p0; ep = d.p1; }
     else if (r == 0) { sp = d.p0; ep = d.p0 + d.rl; }
     else { sp = d.p1 + d.rl; ep = d.p1; }
 }
-__host__ __device__ constexpr uint32_t warp_region_bytes(uint32_t stage_cap) {
-    return (uint32_t(WARP_UNITS * sizeof(TileUnit)) + STAGE_FRONT + stage_cap + 48u + 15u) & ~15u;
+__host__ __device__ constexpr uint32_t warp_region_bytes(uint32_t stage_cap) { return (STAGE_FRONT + stage_cap + 48u + 15u) & ~15u; }
+/* bytes of the quality table in shared memory */
+__host__ __device__ constexpr uint32_t qtab_bytes(int qm, uint32_t cb, uint32_t npos) {
+    return qm == QM_LANE ? (128u << cb) : qm == QM_POS ? ((npos << cb) * 4u + 127u) & ~127u : 0u;
 }
 
-template <bool REPLAY, int TK>
-__global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_warps(RunParams rp, ReplayDev rd) {
+template <bool REPLAY, int QM>
+__global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lanes(RunParams rp, ReplayDev rd) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u * rp.tab_rep : 1u);
-    uint32_t *tab = reinterpret_cast<uint32_t *>(smem + SM_TAB);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    uint8_t *region = smem + SM_TAB + ((tab_words * 4 + 15) & ~15u) + warp * warp_region_bytes(rp.stage_cap);
-    TileUnit *tu = reinterpret_cast<TileUnit *>(region);
-    uint8_t *stage = region + WARP_UNITS * sizeof(TileUnit) + STAGE_FRONT;
     const uint32_t base_s = uint32_t(__cvta_generic_to_shared(smem));
-    /* PT_T64: entry c is stored tab_rep times, copy k at index c * tab_rep + k; a lane reads copy lane % tab_rep, so the
-     * random look-ups of a half-warp fall into different banks */
-    const uint32_t tab_s = base_s + SM_TAB + (rp.phred.kind == PT_T64 ? 8u * (lane & (rp.tab_rep - 1u)) : 0u);
+    const uint32_t qbytes = qtab_bytes(QM, rp.phred.cb, rp.phred.npos);
+    uint8_t *region = smem + SM_QTAB + qbytes + warp * warp_region_bytes(rp.stage_cap);
+    uint8_t *stage = region + STAGE_FRONT;
     const uint32_t dec2_s = base_s + SM_DEC2, stage_s = uint32_t(__cvta_generic_to_shared(stage));
-    if (rp.phred.kind == PT_T64) for (uint32_t i = threadIdx.x; i < tab_words; i += blockDim.x) tab[i] = rp.phred.entries[2u * (i / (2u * rp.tab_rep)) + (i & 1u)];
-    else for (uint32_t i = threadIdx.x; i < tab_words; i += blockDim.x) tab[i] = rp.phred.entries[i];
-    for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {               /* 4 bases per byte -> ASCII, both strands */
-        uint32_t f = 0, r = 0;
-        for (uint32_t j = 0; j < 4; ++j) {
-            const uint32_t c = (b >> (2 * j)) & 3u;
-            f |= ((0x54474341u >> (8 * c)) & 0xffu) << (8 * j);              /* "ACGT"[c] at byte j */
-            r |= ((0x41434754u >> (8 * c)) & 0xffu) << (8 * (3 - j));        /* "TGCA"[c] at byte 3-j (util.rs:15-37) */
+    const uint32_t qtab_s = base_s + SM_QTAB + (QM == QM_LANE ? 4u * lane : 0u);
+    {   /* tables */
+        uint32_t *qt = reinterpret_cast<uint32_t *>(smem + SM_QTAB);
+        if (QM == QM_LANE) for (uint32_t i = threadIdx.x; i < (32u << rp.phred.cb); i += blockDim.x) qt[i] = rp.phred.entries[i >> 5];
+        if (QM == QM_POS) for (uint32_t i = threadIdx.x; i < (rp.phred.npos << rp.phred.cb); i += blockDim.x) qt[i] = rp.phred.entries[i];
+        if (QM != QM_CONST && rp.phred.has_sub) {
+            for (uint32_t i = threadIdx.x; i < GAP_COLS; i += blockDim.x) reinterpret_cast<uint32_t *>(smem + SM_GAP)[i] = rp.phred.gap[i];
+            for (uint32_t i = threadIdx.x; i < rp.phred_mult; i += blockDim.x) reinterpret_cast<uint32_t *>(smem + SM_QSUB)[i] = rp.phred.qsub[i];
         }
-        reinterpret_cast<uint32_t *>(smem + SM_LUT_FWD)[b] = f;
-        reinterpret_cast<uint32_t *>(smem + SM_LUT_RC)[b] = r;
-        if (b < 100) reinterpret_cast<uint16_t *>(smem + SM_DEC2)[b] = uint16_t(('0' + b / 10) | (('0' + b % 10) << 8));
-        if (b < 10) { uint32_t p = 1; for (uint32_t k = 0; k < b; ++k) p *= 10u; reinterpret_cast<uint32_t *>(smem + SM_DEC2 + 200)[b] = p; }
+        for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {           /* 4 bases per byte -> ASCII, both strands */
+            uint32_t f = 0, r = 0;
+            for (uint32_t j = 0; j < 4; ++j) {
+                const uint32_t c = (b >> (2 * j)) & 3u;
+                f |= ((0x54474341u >> (8 * c)) & 0xffu) << (8 * j);          /* "ACGT"[c] at byte j */
+                r |= ((0x41434754u >> (8 * c)) & 0xffu) << (8 * (3 - j));    /* "TGCA"[c] at byte 3-j (util.rs:15-37) */
+            }
+            reinterpret_cast<uint32_t *>(smem + SM_LUT_FWD)[b] = f;
+            reinterpret_cast<uint32_t *>(smem + SM_LUT_RC)[b] = r;
+            if (b < 100) reinterpret_cast<uint16_t *>(smem + SM_DEC2)[b] = uint16_t(('0' + b / 10) | (('0' + b % 10) << 8));
+            if (b < 10) { uint32_t p = 1; for (uint32_t k = 0; k < b; ++k) p *= 10u; reinterpret_cast<uint32_t *>(smem + SM_DEC2 + 200)[b] = p; }
+        }
     }
     __syncthreads();
 
-    const uint32_t sl = lane & (SUB - 1), sg = lane / SUB;
+    const uint32_t mate = lane & 1u, slot = lane >> 1;
     const uint32_t ntiles = (rp.batch_units + WARP_UNITS - 1) / WARP_UNITS;
     for (uint32_t tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) {
         const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
@@ -865,68 +931,60 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_warp
             const uint32_t pad = uint32_t(tile_base & 15);
             const uint32_t nu = __popc(__ballot_sync(0xffffffffu, lane < left && next - tile_base + pad <= rp.stage_cap));
             const uint32_t total = uint32_t(__shfl_sync(0xffffffffu, off, nu) - tile_base);
+            const uint32_t unit_off = pad + uint32_t(__shfl_sync(0xffffffffu, off, slot) - tile_base);
+            /* this lane's record */
+            const bool mine = slot < nu;
+            UnitDesc d{};
+            if (mine) d = rp.desc[u0 + slot];
+            const bool have = mine && (mate == 0 || (d.flags & 4u));
+            const uint32_t L = mate ? d.L1 : d.L0, H = mate ? d.H1 : d.H0;
+            const uint64_t a = mate ? d.a1 : d.a0;
+            const uint32_t rec = unit_off + (mate ? d.H0 + 2u * d.L0 + 5u : 0u);      /* stage offset of the record */
+            const bool odd = have && ((d.flags & 8u) || H < 2u || L < 4u);            /* rules out the word paths for the sub-tile */
+            const bool words_ok = !__any_sync(0xffffffffu, odd) && !REPLAY;
+            const bool hdr_fast = words_ok && rp.hdr_fast != 0;
+            const bool fast = have && words_ok && !(d.flags & (1u << mate));
+            const uint64_t unit = rp.batch_begin + u0 + slot;
             /* the previous bulk copy must have finished reading the stage before it is rewritten */
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
-            bool odd = false;                 /* this unit rules out the word-store paths for the sub-tile */
-            if (lane < nu) {
-                TileUnit &t = tu[lane];
-                t.d = rp.desc[u0 + lane];
-                t.off[0] = pad + uint32_t(off - tile_base);
-                t.off[1] = t.off[0] + t.d.H0 + 2u * t.d.L0 + 5u;
-                const bool two = t.d.flags & 4u;
-                odd = (t.d.flags & 8u) || t.d.H0 < 2u || t.d.L0 < 4u || (two && (t.d.H1 < 2u || t.d.L1 < 4u));
-            }
-            const bool words_ok = !__any_sync(0xffffffffu, odd) && !REPLAY;
-            const bool hdr_fast = words_ok && rp.hdr_fast != 0;
-            __syncwarp();
 
-            /* ---- phase 1: sequence and quality lines, sub-group sg takes unit sg ---- */
+            /* ---- phase 1: sequence and quality lines ---- */
             {
-                const bool mine = sg < nu;
-                const TileUnit &t = tu[min(sg, nu - 1)];
-
-                const uint64_t unit = rp.batch_begin + u0 + sg;
-                const uint32_t ulo = uint32_t(unit), uhi = uint32_t(unit >> 32);
-#pragma unroll
-                for (uint32_t mate = 0; mate < 2; ++mate) {
-                    const bool have = mine && (mate == 0 || (t.d.flags & 4u));
-                    const bool fast = have && words_ok && !(t.d.flags & (1u << mate));
-                    const uint32_t L = mate ? t.d.L1 : t.d.L0, body = t.off[mate] + (mate ? t.d.H1 : t.d.H0);
-                    const uint64_t a = mate ? t.d.a1 : t.d.a0;
-                    const uint32_t T2 = __reduce_max_sync(0xffffffffu, fast ? pairs_per_lane(L) : 0u);
-                    if (T2) {
-                        if (mate == 0) body_fast<TK, false>(rp, tab_s, base_s + SM_LUT_FWD, fast, stage_s + body, ulo, uhi, 1, a, L, sl, T2);
-                        else body_fast<TK, true>(rp, tab_s, base_s + SM_LUT_RC, fast, stage_s + body, ulo, uhi, 2, a, L, sl, T2);
-                    }
-                    if (have && !fast)
-                        emit_body_generic<REPLAY, false>(rp, rd, tab, rp.tab_rep, stage + body, unit, mate, a, L,
-                                                         (REPLAY ? rd.base_off[unit] : 0) + (mate ? t.d.rl : 0), sl, SUB);
+                const uint32_t body_s = stage_s + rec + H;
+                const uint32_t slots = ((L + 3u + 3u) >> 2);                          /* word slots of a line, at most */
+                const uint32_t T16 = __reduce_max_sync(0xffffffffu, fast ? (slots + 3u) >> 2 : 0u);
+                if (T16) {
+                    Mwc1 qc{}, ec{};
+                    if (QM != QM_CONST) mwc1_seed(rp, qc, ec, 1u + mate, uint32_t(unit), uint32_t(unit >> 32));
+                    body_lane<QM>(rp, qtab_s, base_s + (mate ? SM_LUT_RC : SM_LUT_FWD), fast, mate != 0, body_s, qc, a, L, T16);
+                    if (QM != QM_CONST && rp.phred.has_sub) substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
+                }
+                if (have && !fast) {
+                    if (REPLAY) emit_body_generic<true, false>(rp, rd, nullptr, 1, stage + rec + H, unit, mate, a, L, rd.base_off[unit] + (mate ? d.rl : 0), 0, 1);
+                    else emit_body_short<false>(rp, stage + rec + H, unit, mate, a, L);
                 }
             }
             __syncwarp();
 
-            /* ---- phase 2: headers and the fixed bytes, one lane per record ---- */
-            if (lane < 2 * nu) {
-                const TileUnit &t = tu[lane >> 1]; const uint32_t mate = lane & 1u;
-                if (mate == 0 || (t.d.flags & 4u)) {
-                    uint64_t sp, ep; record_positions(t.d, mate, sp, ep);
-                    const uint32_t id = rp.read_id_base + uint32_t(rp.batch_begin + u0 + (lane >> 1));
-                    const uint32_t H = mate ? t.d.H1 : t.d.H0, L = mate ? t.d.L1 : t.d.L0, rec_s = stage_s + t.off[mate];
-                    const ContigHdr ch = rp.chdr[2 * t.d.contig + mate];
-                    if (hdr_fast) {      /* newline that ends the previous record, the tokens, newline */
-                        ByteStream b; bs_open(b, rec_s - 1u); bs_put(b, '\n', 1);
-                        header_tokens(b, rp, dec2_s, reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off), rp.hdr_kinds, rp.hdr_fields,
-                                      id, uint32_t(sp), uint32_t(ep));
-                        bs_put(b, '\n', 1); bs_close(b);
-                    } else {
-                        emit_header(stage + t.off[mate], rp, ch, id, sp, ep);
-                        sts8(rec_s + H, '\n');
-                        if (t.off[mate] > pad) sts8(rec_s - 1u, '\n');         /* ends the previous record */
-                    }
-                    const uint32_t mid = rec_s + H + L + 1u;                   /* fastq.rs:61-69 */
-                    sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n');
+            /* ---- phase 2: header and the fixed bytes ---- */
+            if (have) {
+                uint64_t sp, ep; record_positions(d, mate, sp, ep);
+                const uint32_t id = rp.read_id_base + uint32_t(unit);
+                const uint32_t rec_s = stage_s + rec;
+                const ContigHdr ch = rp.chdr[2 * d.contig + mate];
+                if (hdr_fast) {      /* newline that ends the previous record, the tokens, newline */
+                    ByteStream b; bs_open(b, rec_s - 1u); bs_put(b, '\n', 1);
+                    header_tokens(b, rp, dec2_s, reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off), rp.hdr_kinds, rp.hdr_fields,
+                                  id, uint32_t(sp), uint32_t(ep));
+                    bs_put(b, '\n', 1); bs_close(b);
+                } else {
+                    emit_header(stage + rec, rp, ch, id, sp, ep);
+                    sts8(rec_s + H, '\n');
+                    if (rec > pad) sts8(rec_s - 1u, '\n');                    /* ends the previous record */
                 }
+                const uint32_t mid = rec_s + H + L + 1u;                      /* fastq.rs:61-69 */
+                sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n');
             }
             if (lane == 31 && total) sts8(stage_s + pad + total - 1u, '\n');
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -944,6 +1002,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_warp
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
+
 
 /* One CTA per unit, bytes written straight to global memory.  Used for long
  * reads (records far larger than a tile) and as the fallback when a unit does
@@ -967,7 +1026,8 @@ __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, 
                 uint64_t sp, ep; record_positions(d, r, sp, ep);
                 emit_header(dst, rp, rp.chdr[2 * d.contig + r], rp.read_id_base + uint32_t(u), sp, ep);
             }
-            emit_body_generic<REPLAY, true>(rp, rd, tab, 1, dst + H, u, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
+            if (!REPLAY && !rp.is_long) { if (threadIdx.x == 0) emit_body_short<true>(rp, dst + H, u, r, r ? d.a1 : d.a0, L); }   /* one chain per record */
+            else emit_body_generic<REPLAY, true>(rp, rd, tab, 1, dst + H, u, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
             dst += H + 2 * L + 5;
         }
     }

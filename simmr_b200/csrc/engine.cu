@@ -75,7 +75,7 @@ struct simmr_ctx {
     /* profile */
     bool have_profile = false;
     ProfileModel model;
-    DevMem d_phred, d_rl_e, d_rl_lo, d_rl_hi, d_is_e, d_is_lo, d_is_hi;
+    DevMem d_phred, d_gap, d_qsub, d_rl_e, d_rl_lo, d_rl_hi, d_is_e, d_is_lo, d_is_hi;
     DevMem d_acc, d_plthr, d_rodds, d_ralias, d_roff, d_rlo, d_rhi;
     /* run scratch */
     DevMem d_unit_start, d_sizes, d_offsets, d_block_sums, d_counters, d_desc, d_out[2];
@@ -98,18 +98,23 @@ int fail(simmr_ctx *c, int code, const std::string &m) {
     } while (0)
 
 size_t table_bytes(const ProfileModel &m) { return m.phred_entries.size() * 4; }
-size_t warps_smem(const ProfileModel &m, uint32_t rep, uint32_t warps, uint32_t stage_cap) {
-    return SM_TAB + ((table_bytes(m) * rep + 15) & ~size_t(15)) + size_t(warps) * warp_region_bytes(stage_cap);
+/* how the short-read kernel samples qualities: a single position's table is copied once per lane (no bank conflicts) */
+int quality_mode(const ProfileModel &m) {
+    if (m.phred_kind != PT_Q32) return QM_CONST;
+    return m.npos == 1 && m.cb <= 8 ? QM_LANE : QM_POS;
+}
+size_t lanes_smem(const ProfileModel &m, uint32_t warps, uint32_t stage_cap) {
+    return SM_QTAB + qtab_bytes(quality_mode(m), m.cb, m.npos) + size_t(warps) * warp_region_bytes(stage_cap);
 }
 
-/* kernel instantiations: the fast path is specialised per table kind, replay is generic */
+/* kernel instantiations: the word path is specialised per quality mode, replay is generic */
 using FormatKernel = void (*)(RunParams, ReplayDev);
-FormatKernel warps_kernel(bool replay, uint32_t kind) {
-    if (replay) return k_format_warps<true, PT_CONST>;
-    switch (kind) {
-    case PT_T64: return k_format_warps<false, PT_T64>;
-    case PT_T32: return k_format_warps<false, PT_T32>;
-    default: return k_format_warps<false, PT_CONST>;
+FormatKernel lanes_kernel(bool replay, int qm) {
+    if (replay) return k_format_lanes<true, QM_CONST>;
+    switch (qm) {
+    case QM_LANE: return k_format_lanes<false, QM_LANE>;
+    case QM_POS: return k_format_lanes<false, QM_POS>;
+    default: return k_format_lanes<false, QM_CONST>;
     }
 }
 FormatKernel direct_kernel(bool replay) { return replay ? k_format_direct<true> : k_format_direct<false>; }
@@ -135,21 +140,16 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
     if (tab + 1024 > smem_max) return fail(ctx, SIMMR_E_LIMIT, "quality tables do not fit in shared memory");
     pl.tiles = !m.is_long;
     if (pl.tiles) {
-        /* A warp's stage holds the typical bytes of its WARP_UNITS units plus a margin (a group that
-         * draws longer reads is cut into sub-tiles by the kernel) and at least the largest single unit. */
+        /* A warp's stage holds the typical bytes of its WARP_UNITS units (one record per lane) plus a margin — a group
+         * that draws longer reads is cut into sub-tiles by the kernel — and at least the largest single unit.  One CTA
+         * per SM with as many warps as fit next to the tables. */
         const uint64_t typical = 2ull * (ctx->plan.hdr_cap + 2ull * m.nominal_read_len + 5);
-        const uint64_t cap = (std::max<uint64_t>(unit_bytes + 32, WARP_UNITS * typical * 23 / 20 + 64) + 15) & ~15ull;
-        /* One CTA per SM with as many warps as fit.  The joint quality/substitution table (4 KB) is stored 8 times,
-         * interleaved, so that the random look-ups of a half-warp spread over the banks instead of colliding
-         * (measured: 8 copies + 24 warps beats 16 copies + 20 warps and 1 copy in 3 CTAs of 8 warps). */
-        uint32_t rep = m.phred_kind == PT_T64 && tab * 8 <= 32768 ? 8u : 1u;
-        if (const char *e = getenv("SIMMR_REP")) { const int r = atoi(e); if (m.phred_kind == PT_T64 && (r == 1 || r == 2 || r == 4 || r == 8 || r == 16)) rep = uint32_t(r); }
+        const uint64_t cap = (std::max<uint64_t>(unit_bytes + 32, WARP_UNITS * typical * 21 / 20 + 64) + 15) & ~15ull;
         uint32_t warps = FORMAT_THREADS / 32;
         if (const char *e = getenv("SIMMR_WARPS")) warps = uint32_t(std::max(1, std::min(FORMAT_THREADS / 32, atoi(e))));
-        while (rep > 1 && warps_smem(m, rep, 4, uint32_t(cap)) > smem_max) rep /= 2;
-        while (warps > 1 && warps_smem(m, rep, warps, uint32_t(cap)) > smem_max) --warps;
-        if (cap > 0x7fffffffull || warps_smem(m, rep, warps, uint32_t(cap)) > smem_max) pl.tiles = false;   /* a single unit does not fit: direct path */
-        else { pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.tab_rep = rep; pl.smem = warps_smem(m, rep, warps, uint32_t(cap)); }
+        while (warps > 1 && lanes_smem(m, warps, uint32_t(cap)) > smem_max) --warps;
+        if (cap > 0x7fffffffull || lanes_smem(m, warps, uint32_t(cap)) > smem_max) pl.tiles = false;   /* a single unit does not fit: direct path */
+        else { pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.tab_rep = 1; pl.smem = lanes_smem(m, warps, uint32_t(cap)); }
     }
     int occ = 0;
     if (!pl.tiles && !replay && m.is_long && !getenv("SIMMR_NO_LONG_KERNEL")) {
@@ -161,7 +161,7 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
     } else {
         if (!pl.tiles) { pl.smem = tab; pl.threads = DIRECT_THREADS; }
-        FormatKernel k = pl.tiles ? warps_kernel(replay, m.phred_kind) : direct_kernel(replay);
+        FormatKernel k = pl.tiles ? lanes_kernel(replay, quality_mode(m)) : direct_kernel(replay);
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
     }
@@ -207,13 +207,13 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     memset(&rp, 0, sizeof rp);
     rp.bases = ctx->d_bases.as<uint8_t>(); rp.contig_off = ctx->d_contig_off.as<uint64_t>();
     rp.contig_size = ctx->d_contig_size.as<uint64_t>(); rp.genome_contig = ctx->d_genome_contig.as<uint32_t>();
-    rp.impure = ctx->d_impure.as<uint32_t>(); rp.packed = ctx->d_packed.as<uint32_t>();
+    rp.impure = ctx->d_impure.as<uint32_t>(); rp.packed = ctx->d_packed.as<uint32_t>() + PACK_PAD_WORDS;
     rp.hdr_fast = ctx->hdr_fast; rp.hdr_fields = ctx->hdr_fields; rp.hdr_kinds = ctx->hdr_kinds;
     rp.chdr = ctx->d_chdr.as<ContigHdr>(); rp.toks = ctx->d_toks.as<HdrTok>(); rp.pool = ctx->d_pool.as<uint8_t>();
     rp.n_genomes = ctx->host_view.n_genomes; rp.n_contigs = ctx->host_view.n_contigs;
     rp.unit_start = ctx->d_unit_start.as<uint64_t>();
     rp.read_id_base = id_base;
-    rp.phred = PhredTab{m.phred_kind, m.const_q, m.cb, m.npos, ctx->d_phred.as<uint32_t>()};
+    rp.phred = PhredTab{m.phred_kind, m.const_q, m.cb, m.npos, ctx->d_phred.as<uint32_t>(), ctx->d_gap.as<uint32_t>(), ctx->d_qsub.as<uint32_t>(), m.has_sub ? 1u : 0u, 0u};
     rp.rl = LenTab{m.rl.kind, m.rl.value, m.rl.cb, 0, ctx->d_rl_e.as<uint32_t>(), ctx->d_rl_lo.as<uint32_t>(), ctx->d_rl_hi.as<uint32_t>()};
     rp.is = LenTab{m.is.kind, m.is.value, m.is.cb, 0, ctx->d_is_e.as<uint32_t>(), ctx->d_is_lo.as<uint32_t>(), ctx->d_is_hi.as<uint32_t>()};
     rp.gamma = m.gamma;
@@ -312,7 +312,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         if (pl.tiles) {
             const uint32_t wpc = pl.threads / 32, nctas = ((n + WARP_UNITS - 1) / WARP_UNITS + wpc - 1) / wpc;
             const int grid = int(std::min<uint32_t>(nctas, uint32_t(pl.grid)));
-            warps_kernel(replay, ctx->model.phred_kind)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
+            lanes_kernel(replay, quality_mode(ctx->model))<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
         } else if (pl.lanes) {
             CU(cudaMemsetAsync(rp.counters + 4, 0, 8, ctx->compute));       /* the kernel's piece counter */
             long_kernel(ctx->model.phred_kind)<<<pl.grid, pl.threads, pl.smem, ctx->compute>>>(rp);
@@ -452,10 +452,11 @@ int simmr_genomes_load(simmr_ctx *ctx, const simmr_genome_set *s) {
     {   /* 2-bit copy for the fast path + which 32-byte blocks hold only A,C,G,T (anything else takes the byte path) */
         const uint64_t nblocks = (nbytes + 31) / 32, nimpure = (nblocks + 31) / 32 + 1;
         CU(ctx->d_impure.reserve(nimpure * 4));
-        CU(ctx->d_packed.reserve((2 * nblocks + PACK_PAD_WORDS) * 4));
+        CU(ctx->d_packed.reserve((2 * nblocks + 2 * PACK_PAD_WORDS) * 4));     /* readable words on both sides */
         CU(cudaMemsetAsync(ctx->d_impure.p, 0, nimpure * 4, ctx->compute));
-        CU(cudaMemsetAsync(ctx->d_packed.as<uint32_t>() + 2 * nblocks, 0, PACK_PAD_WORDS * 4, ctx->compute));
-        k_pack<<<unsigned((nblocks + 255) / 256), 256, 0, ctx->compute>>>(ctx->d_bases.as<uint8_t>(), nbytes, ctx->d_packed.as<uint32_t>(),
+        CU(cudaMemsetAsync(ctx->d_packed.p, 0, PACK_PAD_WORDS * 4, ctx->compute));
+        CU(cudaMemsetAsync(ctx->d_packed.as<uint32_t>() + PACK_PAD_WORDS + 2 * nblocks, 0, PACK_PAD_WORDS * 4, ctx->compute));
+        k_pack<<<unsigned((nblocks + 255) / 256), 256, 0, ctx->compute>>>(ctx->d_bases.as<uint8_t>(), nbytes, ctx->d_packed.as<uint32_t>() + PACK_PAD_WORDS,
                                                                         ctx->d_impure.as<uint32_t>(), nblocks, nimpure);
         CU(cudaGetLastError());
     }
@@ -480,8 +481,12 @@ int simmr_error_profile_set(simmr_ctx *ctx, const simmr_eprofile_desc *d) {
         std::vector<uint32_t> dev = m.phred_entries;
         auto plus33 = [](uint32_t w, int shift) { return (w & ~(0xffu << shift)) | ((((w >> shift) & 0xffu) + 33u) & 0xffu) << shift; };
         if (m.phred_kind == PT_T64) for (size_t i = 1; i < dev.size(); i += 2) dev[i] = plus33(plus33(dev[i], 0), 16);
-        if (m.phred_kind == PT_T32) for (uint32_t &w : dev) w = plus33(plus33(w, 0), 8);
+        if (m.phred_kind == PT_T32 || m.phred_kind == PT_Q32) for (uint32_t &w : dev) w = plus33(plus33(w, 0), 8);
         CU(ctx->d_phred.upload(dev.data(), dev.size(), s));
+        std::vector<uint32_t> qsub = m.qsub_entries;
+        for (uint32_t &w : qsub) w = plus33(plus33(w, 0), 8);
+        CU(ctx->d_qsub.upload(qsub.data(), qsub.size(), s));
+        CU(ctx->d_gap.upload(m.gap_entries.data(), m.gap_entries.size(), s));
         CU(cudaStreamSynchronize(s));
     }
     CU(ctx->d_rl_e.upload(m.rl.entries.data(), m.rl.entries.size(), s)); CU(ctx->d_rl_lo.upload(m.rl.lo.data(), m.rl.lo.size(), s)); CU(ctx->d_rl_hi.upload(m.rl.hi.data(), m.rl.hi.size(), s));

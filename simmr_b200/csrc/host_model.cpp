@@ -197,6 +197,47 @@ bool phred_from_mass(const std::vector<double> &mass, uint32_t first, ProfileMod
     return true;
 }
 
+/* PT_Q32 word of a column: thr16<<16 | alias<<8 | self.  The sampler keeps `self` iff word < entry, so a column whose
+ * threshold rounds to zero names its alias twice (the payload bits must not open a window for `self`). */
+inline uint32_t q32_word(double keep, uint32_t self_val, uint32_t alias_val) {
+    const uint32_t thr = threshold(keep, 16);
+    if (thr == 0) self_val = alias_val;
+    return (thr << 16) | ((alias_val & 0xffu) << 8) | (self_val & 0xffu);
+}
+bool q32_words(const std::vector<double> &w, uint32_t first, uint32_t cb, std::vector<uint32_t> &out) {
+    std::vector<double> keep; std::vector<uint32_t> other;
+    if (!alias_columns(w, cb, keep, other)) return false;
+    out.resize(keep.size());
+    for (size_t i = 0; i < keep.size(); ++i) out[i] = q32_word(keep[i], first + uint32_t(i), first + other[i]);
+    return true;
+}
+/* Short reads of a mutating profile (minimal_short.rs:83-140), factored the other way round: a base is substituted with
+ * the marginal probability s = sum_q P(q) flip(q); its quality then follows P(q | substituted), every other base's
+ * P(q | kept).  Bases are independent, so the substituted ones are found by geometric gaps. */
+bool phred_short_from_mass(const std::vector<double> &mass, uint32_t first, ProfileModel &m) {
+    const size_t n = mass.size();
+    std::vector<double> kept(n), subst(n);
+    double s = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        const double f = flip_probability(uint8_t(first + i));
+        kept[i] = mass[i] * (1.0 - f); subst[i] = mass[i] * f;
+        s += subst[i];
+    }
+    m.phred_kind = PT_Q32; m.npos = 1; m.cb = bits_for(n);
+    if (m.cb > 8) return false;
+    if (!q32_words(kept, first, m.cb, m.phred_entries)) return false;
+    m.has_sub = s > 0.0;
+    if (m.has_sub) {
+        if (!q32_words(subst, first, m.cb, m.qsub_entries)) return false;
+        std::vector<double> gap(GAP_COLS);
+        double none = 1.0;                                   /* P(no substitution among the first k bases) */
+        for (uint32_t k = 0; k < GAP_NONE; ++k) { gap[k] = s * none; none = none * (1.0 - s); }
+        gap[GAP_NONE] = none;
+        if (!q32_words(gap, 0, 8, m.gap_entries)) return false;
+    }
+    return true;
+}
+
 bool phred_from_blob(const ProfileBlob &b, ProfileModel &m) {
     const size_t np = b.quality.size();
     if (!np) return false;
@@ -228,8 +269,10 @@ bool phred_from_blob(const ProfileBlob &b, ProfileModel &m) {
         std::vector<uint32_t> other;
         if (!alias_columns(w, m.cb, keep, other)) return false;
         for (size_t i = 0; i < keep.size(); ++i)
-            m.phred_entries.push_back((threshold(keep[i], 16) << 16) | (((qmin + other[i]) & 0xffu) << 8) | ((qmin + uint32_t(i)) & 0xffu));
+            m.phred_entries.push_back(m.is_long ? (threshold(keep[i], 16) << 16) | (((qmin + other[i]) & 0xffu) << 8) | ((qmin + uint32_t(i)) & 0xffu)
+                                                : q32_word(keep[i], qmin + uint32_t(i), qmin + other[i]));
     }
+    if (!m.is_long) m.phred_kind = PT_Q32;                     /* short reads: column from the low bits, direct compare */
     return true;
 }
 
@@ -312,7 +355,7 @@ int build_profile(const simmr_eprofile_desc *d, ProfileModel &m, std::string &er
         m.min_size = uint16_t(2 * d->read_length + d->insert_size);
         m.mutates = true; m.replay_kind = RP_NORMAL_FLOOR;
         floor_normal(double(m.mean_phred_f), 10.0, 255, first, mass);
-        if (!phred_from_mass(mass, first, m)) { err = "phred table"; return SIMMR_E_INVALID; }
+        if (!phred_short_from_mass(mass, first, m)) { err = "phred table"; return SIMMR_E_INVALID; }
         floor_normal(double(d->read_length), 15.0, 65535, first, mass);
         if (!len_from_mass(mass, first, m.rl)) { err = "read-length table"; return SIMMR_E_INVALID; }
         floor_normal(double(d->insert_size), 75.0, 65535, first, mass);

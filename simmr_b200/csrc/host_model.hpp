@@ -45,6 +45,9 @@ struct ProfileModel {
     uint8_t const_q = 0;
     uint32_t cb = 0, npos = 0;
     std::vector<uint32_t> phred_entries;   /* as specified: quality bytes are raw phreds */
+    /* PT_Q32 of a mutating profile: bases until the next substitution, quality given a substitution */
+    bool has_sub = false;
+    std::vector<uint32_t> gap_entries, qsub_entries;
     LenModel rl, is;
     GammaConst gamma{};
     uint32_t max_read_len = 0;          /* upper bound on a read's length    */

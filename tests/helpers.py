@@ -194,3 +194,32 @@ def parse_fastq(data):
         assert lines[i + 2] == b"+"
         out.append((lines[i], lines[i + 1], lines[i + 3]))
     return out
+
+
+def q32_distribution(entries, cb, size=256):
+    """Exact law of the short-read sampler over one row of kind-3 words: a 32-bit draw picks column
+    draw & (2^cb - 1) and keeps the column's own value iff draw < word, else takes its alias."""
+    cols = 1 << cb
+    out = np.zeros(size)
+    for c, e in enumerate(int(v) for v in entries):
+        keep = (max(0, e - c) + cols - 1) // cols / 2.0 ** (32 - cb)      # draws h * cols + c below the word
+        out[e & 0xFF] += keep / cols
+        out[(e >> 8) & 0xFF] += (1.0 - keep) / cols
+    return out
+
+
+def short_read_law(table):
+    """(P(q) over all bases, substitution rate per base) of a kind-3 table: qualities of kept bases from the first
+    (1 << cb) words, then — mutating profiles — the gap table (256 words; 255 = no substitution within 255 bases) and
+    the quality-given-substitution table."""
+    cb, cols = table["cb"], 1 << table["cb"]
+    assert table["kind"] == 3 and table["npos"] == 1
+    kept = q32_distribution(table["entries"][:cols], cb)
+    if len(table["entries"]) == cols:
+        return kept, 0.0
+    gap = q32_distribution(table["entries"][cols:cols + 256], 8)
+    sub = q32_distribution(table["entries"][cols + 256:], cb)
+    # distance between substituted bases: gap + 1, where 255 means "255 bases kept, draw again"
+    mean_d = (float((gap[:255] * (np.arange(255) + 1)).sum()) + 255.0 * gap[255]) / (1.0 - gap[255])
+    rate = 1.0 / mean_d
+    return (1.0 - rate) * kept + rate * sub, rate

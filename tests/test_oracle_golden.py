@@ -186,17 +186,7 @@ def test_native_tables_match_reference_arithmetic(mean_q):
     match draws made with the reference's own arithmetic (minimal_short.rs:83-140: f32
     mean + 10*z, floor, saturating u8; gen::<f32>() > accuracy) within sampling error."""
     prof = po.Profile(po.MINIMAL_SHORT, 150, 150, mean_q)
-    t = prof.phred_table()
-    assert t["kind"] == 1 and t["npos"] == 1
-    cols = 1 << t["cb"]
-    thr, pay = t["entries"][0::2].astype(np.float64), t["entries"][1::2]
-    pq, pm = np.zeros(256), np.zeros(256)
-    for i in range(cols):
-        keep = thr[i] / 2.0 ** 32 if thr[i] < 0xFFFFFFFF else 1.0
-        for w, p in ((keep, pay[i] & 0xFFFF), (1.0 - keep, pay[i] >> 16)):
-            pq[p & 0xFF] += w / cols
-            if (p >> 8) & 0xFF:
-                pm[p & 0xFF] += w / cols
+    pq, rate = H.short_read_law(prof.phred_table())
     n = 2_000_000
     q = np.zeros(n, np.uint8)
     po.lib().orc_ref_minimal_phred(mean_q, C.c_uint64(n), C.c_uint64(7), q.ctypes.data_as(po.u8p))
@@ -209,32 +199,32 @@ def test_native_tables_match_reference_arithmetic(mean_q):
     out = np.zeros(n, np.uint8)
     po.lib().orc_ref_mutate(seq.ctypes.data_as(po.u8p), q.ctypes.data_as(po.u8p), C.c_uint64(n), C.c_uint64(9),
                             out.ctypes.data_as(po.u8p))
-    rate = float((out != seq).mean())
-    assert abs(rate - pm.sum()) < 6 * np.sqrt(pm.sum() / n), (rate, pm.sum())
+    rate_ref = float((out != seq).mean())
+    assert abs(rate_ref - rate) < 6 * np.sqrt(rate / n), (rate_ref, rate)
     if mean_q == 30:
-        assert abs(pm.sum() - 0.01340) < 2e-4                            # 1.340 %
+        assert abs(rate - 0.01340) < 2e-4                                # 1.340 %
+    # quality of the substituted bases (the reference substitutes after drawing q: P(q | substituted))
+    cols = 1 << prof.phred_table()["cb"]
+    sub = H.q32_distribution(prof.phred_table()["entries"][cols + 256:], prof.phred_table()["cb"])
+    qs = q[out != seq]
+    emp_s = np.bincount(qs, minlength=256) / len(qs)
+    sel = sub * len(qs) >= 20
+    chi2 = float((((emp_s - sub) ** 2)[sel] / sub[sel]).sum() * len(qs))
+    assert chi2 < sel.sum() + 6 * np.sqrt(2 * sel.sum()), chi2
 
 
 def test_native_stream_statistics():
-    """The per-base word schedule (Philox-seeded MWC64X chains) as it comes out of a native
-    run: Phred histogram against the table's exact distribution (chi-square), substitution rate, no
-    correlation between neighbouring qualities or between the two mates, equal use of the three
-    alternative bases."""
+    """The short-read draw schedule (a Philox-seeded MWC64X quality chain and an event chain per record,
+    DESIGN.md §4) as it comes out of a native run: Phred histogram against the tables' exact distribution
+    (chi-square), substitution rate, no correlation between neighbouring qualities or between the two
+    mates, equal use of the three alternative bases, substitutions spread evenly along the read."""
     import simmr_b200 as S
     rng = np.random.default_rng(8)
     seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 400000)]
     gs = S.GenomeSet.from_contigs([("u", [(b"c", seq)])])
     og = po.Genomes.from_set(gs)
     prof = po.Profile(po.MINIMAL_SHORT, 150, 150, 30)
-    t = prof.phred_table()
-    cols = 1 << t["cb"]
-    thr, pay = t["entries"][0::2].astype(np.float64), t["entries"][1::2]
-    pq, pm = np.zeros(256), 0.0
-    for i in range(cols):
-        keep = thr[i] / 2.0 ** 32 if thr[i] < 0xFFFFFFFF else 1.0
-        for w, p in ((keep, pay[i] & 0xFFFF), (1.0 - keep, pay[i] >> 16)):
-            pq[p & 0xFF] += w / cols
-            pm += (w / cols) if (p >> 8) & 0xFF else 0.0
+    pq, pm = H.short_read_law(prof.phred_table())
     recs = H.parse_fastq(po.simulate(og, prof, [30000], 1234))
     q = np.frombuffer(b"".join(r[2] for r in recs), np.uint8).astype(np.int64) - 33
     n = len(q)
@@ -248,13 +238,18 @@ def test_native_stream_statistics():
     src = seq.tobytes()
     subs = total = 0
     alt = np.zeros(4, np.int64)
-    for hdr, s, _ in recs[:20000]:
+    where = np.zeros(3, np.int64)                            # substitutions in the thirds of the window (forward-strand order)
+    q_at_sub = []
+    for hdr, s, ql in recs[:20000]:
         f = dict(kv.split(b"=") for kv in hdr.split(b"metadata:")[1].split(b"|"))
         sp, ep, rc = int(f[b"sp"]), int(f[b"ep"]), f[b"rc"] == b"t"
         ref = src[ep:sp].translate(comp)[::-1] if rc else src[sp:ep]
         a, b = np.frombuffer(s, np.uint8), np.frombuffer(ref, np.uint8)
         diff = a != b
         subs += int(diff.sum()); total += len(a)
+        at = np.nonzero(diff)[0]
+        where += np.bincount(((len(a) - 1 - at if rc else at) * 3) // len(a), minlength=3)
+        q_at_sub.append(np.frombuffer(ql, np.uint8)[len(a) - 1 - at if rc else at].astype(np.int64) - 33)   # quality i belongs to window base i
         # rank(new) xor rank(old) in 1..3 must be uniform
         rank = np.zeros(256, np.int64); rank[list(b"ACGT")] = range(4)
         ra, rb = rank[a[diff]], rank[b[diff]]
@@ -263,9 +258,15 @@ def test_native_stream_statistics():
         alt += np.bincount(ra ^ rb, minlength=4)
     assert abs(subs / total - pm) < 6 * np.sqrt(pm / total), (subs / total, pm)
     assert alt[0] == 0 and np.all(np.abs(alt[1:] - subs / 3) < 6 * np.sqrt(subs / 3)), alt
+    assert np.all(np.abs(where - subs / 3) < 6 * np.sqrt(subs / 3)), where
+    # substituted bases carry qualities drawn from P(q | substituted): far below the read's mean
+    t = prof.phred_table(); cols = 1 << t["cb"]
+    sub_law = H.q32_distribution(t["entries"][cols + 256:], t["cb"])
+    qs = np.concatenate(q_at_sub)
+    assert abs(qs.mean() - float((sub_law * np.arange(256)).sum())) < 6 * np.sqrt(float((sub_law * np.arange(256) ** 2).sum()) / len(qs))
     qf = q.astype(np.float64) - q.mean()
-    assert abs(float((qf[:-1] * qf[1:]).mean() / qf.var())) < 5 / np.sqrt(n)         # lag-1 (also across the 4 chains)
-    assert abs(float((qf[:-4] * qf[4:]).mean() / qf.var())) < 5 / np.sqrt(n)         # lag-4: same chain, next step
+    assert abs(float((qf[:-1] * qf[1:]).mean() / qf.var())) < 5 / np.sqrt(n)         # lag-1: next step of the chain
+    assert abs(float((qf[:-4] * qf[4:]).mean() / qf.var())) < 5 / np.sqrt(n)         # lag-4
     m1 = np.frombuffer(b"".join(r[2][:100] for r in recs[0::2]), np.uint8).astype(np.float64)
     m2 = np.frombuffer(b"".join(r[2][:100] for r in recs[1::2]), np.uint8).astype(np.float64)
     assert abs(float(np.corrcoef(m1, m2)[0, 1])) < 5 / np.sqrt(len(m1))
