@@ -525,10 +525,10 @@ bool phred_short_table_from_pmf(const std::vector<double> &pq, uint32_t qlo, Phr
     }
     t.kind = 3; t.npos = 1; t.cb = std::max(1u, ceil_log2(n));
     if (t.cb > 8) return false;
-    if (!q32_table(kept, qlo, t.cb, t.entries)) return false;
+    if (!q32_table(kept, qlo + 33u, t.cb, t.entries)) return false;    /* kind 3 words hold the printed characters (util.rs:46-50) */
     t.has_sub = s > 0.0;
     if (t.has_sub) {
-        if (!q32_table(subst, qlo, t.cb, t.qsub)) return false;
+        if (!q32_table(subst, qlo + 33u, t.cb, t.qsub)) return false;
         std::vector<double> gap(256);
         double none = 1.0;
         for (uint32_t k = 0; k < 255; k++) { gap[k] = s * none; none = none * (1.0 - s); }
@@ -574,7 +574,7 @@ bool phred_table_from_blob(const Blob &b, bool long_reads, PhredTable &t) {
         if (!vose(w, t.cb, prob, alias)) return false;
         for (size_t i = 0; i < prob.size(); i++)
             t.entries.push_back(long_reads ? (quant_thr(prob[i], 16) << 16) | (((qmin + alias[i]) & 0xffu) << 8) | ((qmin + (uint32_t)i) & 0xffu)
-                                           : q32_entry(prob[i], qmin + (uint32_t)i, qmin + alias[i]));
+                                           : q32_entry(prob[i], qmin + (uint32_t)i + 33u, qmin + alias[i] + 33u));
     }
     return true;
 }
@@ -920,7 +920,7 @@ void native_read_short(const Profile &p, const Philox &ph, uint64_t u, uint32_t 
     Chain qc(w[0], w[1]), ec(w[2], w[3]);
     for (uint64_t i = 0; i < L; i++) {
         const uint64_t pos = std::min<uint64_t>(i, t.npos - 1);                 /* custom_short.rs:339-345 */
-        qual[i] = (uint8_t)sample_q32(t.entries.data() + (pos << t.cb), t.cb, qc.next());
+        qual[i] = (uint8_t)(sample_q32(t.entries.data() + (pos << t.cb), t.cb, qc.next()) - 33u);   /* the table holds characters */
     }
     if (!t.has_sub) return;
     for (uint64_t next = 0; next < L;) {               /* every step takes three words of the event chain */
@@ -929,7 +929,7 @@ void native_read_short(const Profile &p, const Philox &ph, uint64_t u, uint32_t 
         if (g == 255) { next += 255; continue; }
         const uint64_t at = next + g;
         if (at >= L) break;
-        qual[at] = (uint8_t)sample_q32(t.qsub.data(), t.cb, r2);
+        qual[at] = (uint8_t)(sample_q32(t.qsub.data(), t.cb, r2) - 33u);
         const uint8_t nb = substitute_native(seq[at], 1u + mulhi32(r3, 3u));
         if (nb != seq[at]) st.mutated++;
         seq[at] = nb;

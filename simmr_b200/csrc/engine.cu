@@ -481,11 +481,9 @@ int simmr_error_profile_set(simmr_ctx *ctx, const simmr_eprofile_desc *d) {
         std::vector<uint32_t> dev = m.phred_entries;
         auto plus33 = [](uint32_t w, int shift) { return (w & ~(0xffu << shift)) | ((((w >> shift) & 0xffu) + 33u) & 0xffu) << shift; };
         if (m.phred_kind == PT_T64) for (size_t i = 1; i < dev.size(); i += 2) dev[i] = plus33(plus33(dev[i], 0), 16);
-        if (m.phred_kind == PT_T32 || m.phred_kind == PT_Q32) for (uint32_t &w : dev) w = plus33(plus33(w, 0), 8);
-        CU(ctx->d_phred.upload(dev.data(), dev.size(), s));
-        std::vector<uint32_t> qsub = m.qsub_entries;
-        for (uint32_t &w : qsub) w = plus33(plus33(w, 0), 8);
-        CU(ctx->d_qsub.upload(qsub.data(), qsub.size(), s));
+        if (m.phred_kind == PT_T32) for (uint32_t &w : dev) w = plus33(plus33(w, 0), 8);
+        CU(ctx->d_phred.upload(dev.data(), dev.size(), s));         /* PT_Q32 words hold the printed characters as built */
+        CU(ctx->d_qsub.upload(m.qsub_entries.data(), m.qsub_entries.size(), s));
         CU(ctx->d_gap.upload(m.gap_entries.data(), m.gap_entries.size(), s));
         CU(cudaStreamSynchronize(s));
     }

@@ -204,6 +204,8 @@ inline uint32_t q32_word(double keep, uint32_t self_val, uint32_t alias_val) {
     if (thr == 0) self_val = alias_val;
     return (thr << 16) | ((alias_val & 0xffu) << 8) | (self_val & 0xffu);
 }
+/* `first` = value of column 0; quality tables pass first = lowest quality + 33: PT_Q32 words hold the characters as
+ * printed (util.rs:46-50), because the whole word is what a draw is compared with */
 bool q32_words(const std::vector<double> &w, uint32_t first, uint32_t cb, std::vector<uint32_t> &out) {
     std::vector<double> keep; std::vector<uint32_t> other;
     if (!alias_columns(w, cb, keep, other)) return false;
@@ -225,10 +227,10 @@ bool phred_short_from_mass(const std::vector<double> &mass, uint32_t first, Prof
     }
     m.phred_kind = PT_Q32; m.npos = 1; m.cb = bits_for(n);
     if (m.cb > 8) return false;
-    if (!q32_words(kept, first, m.cb, m.phred_entries)) return false;
+    if (!q32_words(kept, first + 33u, m.cb, m.phred_entries)) return false;
     m.has_sub = s > 0.0;
     if (m.has_sub) {
-        if (!q32_words(subst, first, m.cb, m.qsub_entries)) return false;
+        if (!q32_words(subst, first + 33u, m.cb, m.qsub_entries)) return false;
         std::vector<double> gap(GAP_COLS);
         double none = 1.0;                                   /* P(no substitution among the first k bases) */
         for (uint32_t k = 0; k < GAP_NONE; ++k) { gap[k] = s * none; none = none * (1.0 - s); }
@@ -270,7 +272,7 @@ bool phred_from_blob(const ProfileBlob &b, ProfileModel &m) {
         if (!alias_columns(w, m.cb, keep, other)) return false;
         for (size_t i = 0; i < keep.size(); ++i)
             m.phred_entries.push_back(m.is_long ? (threshold(keep[i], 16) << 16) | (((qmin + other[i]) & 0xffu) << 8) | ((qmin + uint32_t(i)) & 0xffu)
-                                                : q32_word(keep[i], qmin + uint32_t(i), qmin + other[i]));
+                                                : q32_word(keep[i], qmin + uint32_t(i) + 33u, qmin + other[i] + 33u));
     }
     if (!m.is_long) m.phred_kind = PT_Q32;                     /* short reads: column from the low bits, direct compare */
     return true;

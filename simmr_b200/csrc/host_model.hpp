@@ -44,7 +44,7 @@ struct ProfileModel {
     uint32_t phred_kind = PT_CONST;     /* PT_* */
     uint8_t const_q = 0;
     uint32_t cb = 0, npos = 0;
-    std::vector<uint32_t> phred_entries;   /* as specified: quality bytes are raw phreds */
+    std::vector<uint32_t> phred_entries;   /* PT_T64 / PT_T32: quality bytes are raw phreds; PT_Q32: characters as printed (+33) */
     /* PT_Q32 of a mutating profile: bases until the next substitution, quality given a substitution */
     bool has_sub = false;
     std::vector<uint32_t> gap_entries, qsub_entries;

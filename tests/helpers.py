@@ -196,16 +196,17 @@ def parse_fastq(data):
     return out
 
 
-def q32_distribution(entries, cb, size=256):
+def q32_distribution(entries, cb, size=256, chars=True):
     """Exact law of the short-read sampler over one row of kind-3 words: a 32-bit draw picks column
-    draw & (2^cb - 1) and keeps the column's own value iff draw < word, else takes its alias."""
+    draw & (2^cb - 1) and keeps the column's own value iff draw < word, else takes its alias.  Quality tables hold the
+    characters as printed (chars=True: the law is returned over q = character - 33)."""
     cols = 1 << cb
     out = np.zeros(size)
     for c, e in enumerate(int(v) for v in entries):
         keep = (max(0, e - c) + cols - 1) // cols / 2.0 ** (32 - cb)      # draws h * cols + c below the word
         out[e & 0xFF] += keep / cols
         out[(e >> 8) & 0xFF] += (1.0 - keep) / cols
-    return out
+    return np.roll(out, -33) if chars else out
 
 
 def short_read_law(table):
@@ -217,7 +218,7 @@ def short_read_law(table):
     kept = q32_distribution(table["entries"][:cols], cb)
     if len(table["entries"]) == cols:
         return kept, 0.0
-    gap = q32_distribution(table["entries"][cols:cols + 256], 8)
+    gap = q32_distribution(table["entries"][cols:cols + 256], 8, chars=False)
     sub = q32_distribution(table["entries"][cols + 256:], cb)
     # distance between substituted bases: gap + 1, where 255 means "255 bases kept, draw again"
     mean_d = (float((gap[:255] * (np.arange(255) + 1)).sum()) + 255.0 * gap[255]) / (1.0 - gap[255])
