@@ -812,16 +812,24 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
     /* word slots of each line still to store: slot k = characters 4k - o .. 4k - o + 3 of the line */
     int32_t ns = on ? int32_t((L + os + 3u) >> 2) : 0, nq = on ? int32_t((L + oq + 3u) >> 2) : 0;
     uint32_t ps = Ds - os, pq = Dq - oq;
-    /* 32-bit windows of the 2-bit copy: mate 1 from the window's first base upwards, mate 2 from its last base downwards */
+    /* 32-bit windows of the 2-bit copy: mate 1 from the window's first base upwards, mate 2 from its last base downwards.
+     * The two words under the window slide by one word per turn; the next word is fetched a turn ahead. */
     const int64_t bit = rc ? 2 * int64_t(a + L) - 32 : 2 * int64_t(a);
     const uint32_t *pw = rp.packed + (bit >> 5);
     const uint32_t s2 = uint32_t(bit) & 31u, rev = rc ? 0x0123u : 0x3210u;
+    uint32_t w_lo = __ldg(pw), w_hi = __ldg(pw + 1);
+    pw += rc ? -1 : 2;
     const int32_t dw = rc ? -1 : 1;
     const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u, mask = rp.phred_mult - 1u;
     uint32_t prev_s = 0, prev_q = 0;
     for (uint32_t it = 0; it < T16; ++it) {
-        const uint32_t X = __byte_perm(__funnelshift_r(__ldg(pw), __ldg(pw + 1), s2), 0u, rev);
-        pw += dw;
+        const uint32_t X = __byte_perm(__funnelshift_r(w_lo, w_hi, s2), 0u, rev);
+        {   /* mate 1: (lo, hi) <- (hi, new); mate 2: (lo, hi) <- (new, lo).  The padding around `packed` covers the last fetch. */
+            const uint32_t nw = __ldg(pw);
+            pw += dw;
+            const uint32_t keep = rc ? w_lo : w_hi;
+            w_lo = rc ? nw : keep; w_hi = rc ? keep : nw;
+        }
 #pragma unroll
         for (uint32_t h = 0; h < 4; ++h) {
             const uint32_t qw = QM == QM_CONST ? qconst : quals4<QM>(rp, qtab_s, mask, rng, 16u * it + 4u * h);

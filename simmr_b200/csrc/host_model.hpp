@@ -63,7 +63,7 @@ struct ProfileModel {
 };
 int build_profile(const simmr_eprofile_desc *d, ProfileModel &m, std::string &err);
 
-/* abundance_profiles/*.rs */
+/* abundance_profiles/{uniform,exact,custom}.rs */
 int abundance_counts(const simmr_aprofile_desc *d, uint64_t total_reads, uint32_t n, const uint64_t *sizes,
                      uint64_t *out_reads, double *out_abund, std::string &err);
 
