@@ -260,7 +260,7 @@ def main():
                "reads_per_second": all_records / (max_ms / 1e3), "clocks": sampler.summary(t_timed0, t_timed1), "gpu_launches": launches,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(gs.bases.nbytes),
                        "d2h_bytes_per_step": int(e2e_d2h // max(1, args.e2e_steps)), "steps": args.e2e_steps},
-               "roofline": {"bound": "hbm", "kernel": "k_format_warps", "achieved": achieved, "peak": peak, "unit": "GB/s",
+               "roofline": {"bound": "hbm", "kernel": "k_format_lanes", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": alg / n_launch,
                             "launch_ms": fmt_ms / n_launch, "launches": n_launch, "kernel_share_of_step": fmt_ms / dev_ms}}

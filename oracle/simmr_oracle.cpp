@@ -215,14 +215,15 @@ struct BaseWords {
 };
 /* Short reads: one Philox block (0, stream, unit) seeds two MWC64X chains of the record — words 0,1 the
  * quality chain (base i takes its i-th output), words 2,3 the substitution-event chain. */
+struct Draw { uint32_t word, level; };   /* word = x ^ c (its low bits pick a table column), level = x (compared with the entry) */
 struct Chain {
     uint32_t x, c;
     Chain(uint32_t w_even, uint32_t w_odd) : x(w_even), c((w_odd >> 2) + 1) {}
-    uint32_t next() {
-        const uint32_t r = x ^ c;
+    Draw next() {
+        const Draw d{x ^ c, x};
         const uint64_t t = (uint64_t)x * 4294883355u + c;
         x = (uint32_t)t; c = (uint32_t)(t >> 32);
-        return r;
+        return d;
     }
 };
 inline uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
@@ -698,10 +699,10 @@ inline void sample_phred(const PhredTable &t, uint32_t pos, uint32_t w, uint8_t 
         q = (uint8_t)((x >> 16) < (e >> 16) ? (e & 0xffu) : ((e >> 8) & 0xffu)); m = 0;
     }
 }
-/* kind 3 word against a draw: column = low cb bits, self iff draw < word */
-inline uint32_t sample_q32(const uint32_t *row, uint32_t cb, uint32_t w) {
-    const uint32_t e = row[w & ((1u << cb) - 1u)];
-    return (w < e ? e : e >> 8) & 0xffu;
+/* kind 3 entry against a draw: column = low cb bits of the draw's word, self iff its level < entry */
+inline uint32_t sample_q32(const uint32_t *row, uint32_t cb, Draw d) {
+    const uint32_t e = row[d.word & ((1u << cb) - 1u)];
+    return (d.level < e ? e : e >> 8) & 0xffu;
 }
 /* minimal_short.rs:124-131 substitution table */
 inline uint8_t substitute(uint8_t nt, uint32_t k) {
@@ -924,13 +925,13 @@ void native_read_short(const Profile &p, const Philox &ph, uint64_t u, uint32_t 
     }
     if (!t.has_sub) return;
     for (uint64_t next = 0; next < L;) {               /* every step takes three words of the event chain */
-        const uint32_t r1 = ec.next(), r2 = ec.next(), r3 = ec.next();
+        const Draw r1 = ec.next(), r2 = ec.next(), r3 = ec.next();
         const uint32_t g = sample_q32(t.gap.data(), 8, r1);
         if (g == 255) { next += 255; continue; }
         const uint64_t at = next + g;
         if (at >= L) break;
         qual[at] = (uint8_t)(sample_q32(t.qsub.data(), t.cb, r2) - 33u);
-        const uint8_t nb = substitute_native(seq[at], 1u + mulhi32(r3, 3u));
+        const uint8_t nb = substitute_native(seq[at], 1u + mulhi32(r3.word, 3u));
         if (nb != seq[at]) st.mutated++;
         seq[at] = nb;
         next = at + 1;

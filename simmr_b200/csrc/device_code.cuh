@@ -67,6 +67,7 @@ struct RunParams {
     /* decimal fields of the header template when every contig has the same ones (fastq.rs:34-57): hdr_fast == 0 means
      * per-contig lists only; kinds 4 bits each, field i in bits 4*i */
     uint32_t hdr_fast, hdr_fields, hdr_kinds;
+    uint32_t one;                  /* always 1: a multiplier the compiler cannot fold (mwc1_draw) */
 };
 
 constexpr int SIZES_THREADS = 256;
@@ -90,8 +91,9 @@ enum : int { QM_CONST = 0,            /* one quality for every base             
 /* ---------------------------------------------------------------------- */
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
+/* loads from the read-only tables in shared memory: not volatile, the compiler may move them */
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
 
 /* ---------------------------------------------------------------------- */
 /* Philox4x32-10                                                            */
@@ -150,13 +152,21 @@ __device__ __forceinline__ uint32_t mwc_next(uint32_t &x, uint32_t &c) {
 /* Short reads: one Philox block (0, stream, unit) seeds the two chains of a record — words 0,1 the quality
  * chain (base i of the window takes its i-th output), words 2,3 the substitution-event chain. */
 struct Mwc1 { uint32_t x, c; };
-__device__ __forceinline__ uint32_t mwc1_next(Mwc1 &m) { return mwc_next(m.x, m.c); }
+/* one draw = (word, level): word = x ^ c picks a table column with its low bits, level = x is compared with the entry;
+ * then the chain steps.  The 64-bit addend {c, 0} is made by a widening multiply by `one` (a kernel parameter that is
+ * always 1, so the compiler keeps it): both instructions of a step go to the multiply pipe instead of the ALU. */
+__device__ __forceinline__ uint32_t mwc1_draw(Mwc1 &m, uint32_t one, uint32_t &level) {
+    level = m.x;
+    const uint32_t r = m.x ^ m.c;
+    asm("{ .reg .b64 cc, t; mul.wide.u32 cc, %1, %2; mad.wide.u32 t, %0, %3, cc; mov.b64 {%0, %1}, t; }" : "+r"(m.x), "+r"(m.c) : "r"(one), "r"(4294883355u));
+    return r;
+}
 __device__ __forceinline__ void mwc1_seed(const RunParams &rp, Mwc1 &qc, Mwc1 &ec, uint32_t stream, uint32_t ulo, uint32_t uhi) {
     const Philox4 w = philox(rp.rk, 0u, stream, ulo, uhi);
     qc.x = w.x; qc.c = (w.y >> 2) + 1u; ec.x = w.z; ec.c = (w.w >> 2) + 1u;
 }
-/* PT_Q32 word against a draw whose low cb bits picked the column: self iff draw < word */
-__device__ __forceinline__ uint32_t q32_pick(uint32_t e, uint32_t w) { return (w < e ? e : e >> 8) & 0xffu; }
+/* PT_Q32 entry of the column the draw's word picked: self iff level < entry */
+__device__ __forceinline__ uint32_t q32_pick(uint32_t e, uint32_t level) { return (level < e ? e : e >> 8) & 0xffu; }
 
 /* ---------------------------------------------------------------------- */
 /* samplers                                                                 */
@@ -451,19 +461,20 @@ __device__ void emit_body_short(const RunParams &rp, uint8_t *dst, uint64_t unit
     const uint32_t mask = rp.phred_mult - 1u, last = rp.phred.npos - 1u;
     for (uint32_t i = 0; i < L; ++i) {
         uint32_t qc8 = (rp.phred.const_q + 33u) & 0xffu;
-        if (sampled) { const uint32_t r = mwc1_next(qc); qc8 = q32_pick(__ldg(rp.phred.entries + (min(i, last) << rp.phred.cb) + (r & mask)), r); }
+        if (sampled) { uint32_t lv; const uint32_t r = mwc1_draw(qc, rp.one, lv); qc8 = q32_pick(__ldg(rp.phred.entries + (min(i, last) << rp.phred.cb) + (r & mask)), lv); }
         qual[i] = uint8_t(qc8);
         const uint8_t b = __ldg(src + i);
         if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;               /* util.rs:31-37 */
     }
     if (!sampled || !rp.phred.has_sub) return;
     for (uint32_t next = 0; next < L;) {                                        /* three words of the event chain per step */
-        const uint32_t r1 = mwc1_next(ec), r2 = mwc1_next(ec), r3 = mwc1_next(ec);
-        const uint32_t g = q32_pick(__ldg(rp.phred.gap + (r1 & (GAP_COLS - 1u))), r1);
+        uint32_t l1, l2, l3;
+        const uint32_t r1 = mwc1_draw(ec, rp.one, l1), r2 = mwc1_draw(ec, rp.one, l2), r3 = mwc1_draw(ec, rp.one, l3);
+        const uint32_t g = q32_pick(__ldg(rp.phred.gap + (r1 & (GAP_COLS - 1u))), l1);
         if (g == GAP_NONE) { next += GAP_NONE; continue; }
         const uint32_t at = next + g;
         if (at >= L) break;
-        qual[at] = uint8_t(q32_pick(__ldg(rp.phred.qsub + (r2 & mask)), r2));
+        qual[at] = uint8_t(q32_pick(__ldg(rp.phred.qsub + (r2 & mask)), l2));
         uint8_t *sb = rc ? seq + (L - 1 - at) : seq + at;                      /* mutated before the reverse complement (simulate.rs:269-286) */
         const uint8_t fwd = rc ? complement(*sb) : *sb, nb = substitute_native(fwd, 1u + __umulhi(r3, 3u));
         *sb = rc ? complement(nb) : nb;
@@ -516,7 +527,7 @@ __device__ __forceinline__ void emit_body_generic(const RunParams &rp, const Rep
  *     byte to 4 ASCII letters through a 256-entry table in shared memory. */
 
 __device__ __forceinline__ uint32_t lds32m(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
-__device__ __forceinline__ uint32_t lds16(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ uint32_t mulhi_lo(uint32_t a, uint32_t b, uint32_t &lo) { const uint64_t p = uint64_t(a) * b; lo = uint32_t(p); return uint32_t(p >> 32); }
 
 /* quality characters (+33 applied) and mutation codes of bases 4g..4g+3 from their four words */
@@ -781,14 +792,15 @@ __device__ __forceinline__ uint32_t quals4(const RunParams &rp, uint32_t qtab_s,
     uint32_t qw = 0;
 #pragma unroll
     for (uint32_t j = 0; j < 4; ++j) {
-        const uint32_t r = mwc1_next(rng);
+        uint32_t lv;
+        const uint32_t r = mwc1_draw(rng, rp.one, lv);
         uint32_t at;
         if (QM == QM_LANE) at = qtab_s + (r & mask) * 128u;
         else at = qtab_s + ((min(i0 + j, rp.phred.npos - 1u) << rp.phred.cb) + (r & mask)) * 4u;     /* custom_short.rs:339-345 */
         const uint32_t e = lds32(at);
         /* byte j of qw <- byte 0 (self) or 1 (alias) of the entry; bytes below j stay */
         const uint32_t keep = 0x3210u & ((1u << (4u * j)) - 1u);
-        qw = __byte_perm(qw, e, r < e ? (keep | (4u << (4u * j))) : (keep | (5u << (4u * j))));
+        qw = __byte_perm(qw, e, lv < e ? (keep | (4u << (4u * j))) : (keep | (5u << (4u * j))));
     }
     return qw;
 }
@@ -830,13 +842,23 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
             const uint32_t keep = rc ? w_lo : w_hi;
             w_lo = rc ? nw : keep; w_hi = rc ? keep : nw;
         }
+        uint32_t cs[4], cq[4];                         /* the turn's four words of each line, on the stage's word grid */
 #pragma unroll
         for (uint32_t h = 0; h < 4; ++h) {
             const uint32_t qw = QM == QM_CONST ? qconst : quals4<QM>(rp, qtab_s, mask, rng, 16u * it + 4u * h);
             const uint32_t sw = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
-            if (ns > int32_t(h)) sts32(ps + 4u * h, __funnelshift_l(prev_s, sw, sh_s));
-            if (nq > int32_t(h)) sts32(pq + 4u * h, QM == QM_CONST ? qconst : __funnelshift_l(prev_q, qw, sh_q));
+            cs[h] = __funnelshift_l(prev_s, sw, sh_s); cq[h] = QM == QM_CONST ? qconst : __funnelshift_l(prev_q, qw, sh_q);
             prev_s = sw; prev_q = qw;
+        }
+        if (__all_sync(0xffffffffu, ns >= 4 && nq >= 4)) {      /* every lane is inside both lines: no per-word tests */
+#pragma unroll
+            for (uint32_t h = 0; h < 4; ++h) { sts32(ps + 4u * h, cs[h]); sts32(pq + 4u * h, cq[h]); }
+        } else {
+#pragma unroll
+            for (uint32_t h = 0; h < 4; ++h) {
+                if (ns > int32_t(h)) sts32(ps + 4u * h, cs[h]);
+                if (nq > int32_t(h)) sts32(pq + 4u * h, cq[h]);
+            }
         }
         ps += 16u; pq += 16u; ns -= 4; nq -= 4;
     }
@@ -850,12 +872,13 @@ __device__ __forceinline__ void substitutions_lane(const RunParams &rp, uint32_t
     const uint32_t Ds = body_s + 1u, Dq = body_s + L + 4u, mask = rp.phred_mult - 1u;
     uint32_t next = on ? 0u : L;
     while (next < L) {
-        const uint32_t r1 = mwc1_next(ev), r2 = mwc1_next(ev), r3 = mwc1_next(ev);
-        const uint32_t g = q32_pick(lds32(gap_s + 4u * (r1 & (GAP_COLS - 1u))), r1);
+        uint32_t l1, l2, l3;
+        const uint32_t r1 = mwc1_draw(ev, rp.one, l1), r2 = mwc1_draw(ev, rp.one, l2), r3 = mwc1_draw(ev, rp.one, l3);
+        const uint32_t g = q32_pick(lds32(gap_s + 4u * (r1 & (GAP_COLS - 1u))), l1);
         if (g == GAP_NONE) { next += GAP_NONE; continue; }
         const uint32_t at = next + g;
         if (at >= L) break;
-        sts8(Dq + at, q32_pick(lds32(qsub_s + 4u * (r2 & mask)), r2));
+        sts8(Dq + at, q32_pick(lds32(qsub_s + 4u * (r2 & mask)), l2));
         const uint32_t sa = Ds + (rc ? L - 1u - at : at);
         uint32_t b; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(sa) : "memory");
         uint32_t rank = (b >> 1) & 3u; rank ^= rank >> 1;                       /* A,C,G,T -> 0..3 */

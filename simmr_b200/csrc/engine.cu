@@ -223,7 +223,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.sizes = ctx->d_sizes.as<uint32_t>(); rp.offsets = ctx->d_offsets.as<uint64_t>();
     rp.desc = ctx->d_desc.as<UnitDesc>();
     rp.block_sums = ctx->d_block_sums.as<uint64_t>(); rp.counters = ctx->d_counters.as<unsigned long long>();
-    rp.stage_cap = pl.stage_cap; rp.tab_rep = pl.tab_rep;
+    rp.stage_cap = pl.stage_cap; rp.tab_rep = pl.tab_rep; rp.one = 1;
     {   /* MWC64X skip-ahead multipliers: A^(LONG_GRANULE * k) mod (A * 2^32 - 1) */
         const unsigned __int128 mod = (unsigned __int128)(4294883355ull * 4294967296ull - 1ull);
         unsigned __int128 step = 1, acc = 1;

@@ -197,13 +197,13 @@ def parse_fastq(data):
 
 
 def q32_distribution(entries, cb, size=256, chars=True):
-    """Exact law of the short-read sampler over one row of kind-3 words: a 32-bit draw picks column
-    draw & (2^cb - 1) and keeps the column's own value iff draw < word, else takes its alias.  Quality tables hold the
-    characters as printed (chars=True: the law is returned over q = character - 33)."""
+    """Law of the short-read sampler over one row of kind-3 words for a uniform draw: the low cb bits of
+    the draw's word pick a column, the column's own value is kept iff the draw's 32-bit level < entry, else its alias is
+    taken.  Quality tables hold the characters as printed (chars=True: the law is returned over q = character - 33)."""
     cols = 1 << cb
     out = np.zeros(size)
     for c, e in enumerate(int(v) for v in entries):
-        keep = (max(0, e - c) + cols - 1) // cols / 2.0 ** (32 - cb)      # draws h * cols + c below the word
+        keep = e / 2.0 ** 32
         out[e & 0xFF] += keep / cols
         out[(e >> 8) & 0xFF] += (1.0 - keep) / cols
     return np.roll(out, -33) if chars else out
