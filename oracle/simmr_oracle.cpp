@@ -215,12 +215,14 @@ struct BaseWords {
 };
 /* Short reads: one Philox block (0, stream, unit) seeds two MWC64X chains of the record — words 0,1 the
  * quality chain (base i takes its i-th output), words 2,3 the substitution-event chain. */
-struct Draw { uint32_t word, level; };   /* word = x ^ c (its low bits pick a table column), level = x (compared with the entry) */
+/* word = x ^ c (its low bits pick a table column), level = x (compared with the entry); the quality chain serves a second
+ * base from the same step: column from the next cb bits of the word, level2 = c */
+struct Draw { uint32_t word, level, level2; };
 struct Chain {
     uint32_t x, c;
     Chain(uint32_t w_even, uint32_t w_odd) : x(w_even), c((w_odd >> 2) + 1) {}
     Draw next() {
-        const Draw d{x ^ c, x};
+        const Draw d{x ^ c, x, c};
         const uint64_t t = (uint64_t)x * 4294883355u + c;
         x = (uint32_t)t; c = (uint32_t)(t >> 32);
         return d;
@@ -919,9 +921,11 @@ void native_read_short(const Profile &p, const Philox &ph, uint64_t u, uint32_t 
     if (t.kind == 0) { std::fill(qual.begin(), qual.end(), t.const_q); return; }
     uint32_t w[4]; ph.at(u, stream, 0, w);
     Chain qc(w[0], w[1]), ec(w[2], w[3]);
-    for (uint64_t i = 0; i < L; i++) {
+    Draw d{};
+    for (uint64_t i = 0; i < L; i++) {                 /* one step of the quality chain per two bases */
         const uint64_t pos = std::min<uint64_t>(i, t.npos - 1);                 /* custom_short.rs:339-345 */
-        qual[i] = (uint8_t)(sample_q32(t.entries.data() + (pos << t.cb), t.cb, qc.next()) - 33u);   /* the table holds characters */
+        if (!(i & 1)) d = qc.next(); else d = Draw{d.word >> t.cb, d.level2, 0};
+        qual[i] = (uint8_t)(sample_q32(t.entries.data() + (pos << t.cb), t.cb, d) - 33u);   /* the table holds characters */
     }
     if (!t.has_sub) return;
     for (uint64_t next = 0; next < L;) {               /* every step takes three words of the event chain */

@@ -459,9 +459,14 @@ __device__ void emit_body_short(const RunParams &rp, uint8_t *dst, uint64_t unit
     const bool sampled = rp.phred.kind != PT_CONST;
     if (sampled) mwc1_seed(rp, qc, ec, 1 + mate, uint32_t(unit), uint32_t(unit >> 32));
     const uint32_t mask = rp.phred_mult - 1u, last = rp.phred.npos - 1u;
+    uint32_t word = 0, lv_odd = 0;                           /* one step of the quality chain serves two bases (quals4) */
     for (uint32_t i = 0; i < L; ++i) {
         uint32_t qc8 = (rp.phred.const_q + 33u) & 0xffu;
-        if (sampled) { uint32_t lv; const uint32_t r = mwc1_draw(qc, rp.one, lv); qc8 = q32_pick(__ldg(rp.phred.entries + (min(i, last) << rp.phred.cb) + (r & mask)), lv); }
+        if (sampled) {
+            uint32_t lv = lv_odd, col = (word >> rp.phred.cb) & mask;
+            if (!(i & 1u)) { lv_odd = qc.c; word = mwc1_draw(qc, rp.one, lv); col = word & mask; }
+            qc8 = q32_pick(__ldg(rp.phred.entries + (min(i, last) << rp.phred.cb) + col), lv);
+        }
         qual[i] = uint8_t(qc8);
         const uint8_t b = __ldg(src + i);
         if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;               /* util.rs:31-37 */
@@ -784,23 +789,33 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_offsets(RunParams rp) {
 /* ---------------------------------------------------------------------- */
 /* short reads, word path: one lane per record                              */
 /* ---------------------------------------------------------------------- */
-/* Quality characters (+33 applied) of four consecutive bases, the first at window index i0 (the same for every lane of
- * the warp): four steps of the record's quality chain, four look-ups.  QM_LANE: the lane's own copy of the single
- * position's table (word col * 32 + lane: every lane stays in its bank); QM_POS: row min(i, npos-1) of the one copy. */
-template <int QM>
+/* Quality characters (as printed) of four consecutive bases, the first at window index i0 (the same for every lane of
+ * the warp).  One step of the record's quality chain serves two bases: the word x ^ c picks base 2n's column with bits
+ * 0..cb-1 and base 2n+1's with bits cb..2cb-1; their levels are x and c.  QM_LANE: the lane's own copy of the single
+ * position's table (word col * 32 + lane: every lane stays in its bank; CB7: cb == 7, the second column's byte offset is a
+ * plain mask of the word); QM_POS: row min(i, npos-1) of the one copy. */
+template <int QM, bool CB7>
 __device__ __forceinline__ uint32_t quals4(const RunParams &rp, uint32_t qtab_s, uint32_t mask, Mwc1 &rng, uint32_t i0) {
     uint32_t qw = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < 4; ++j) {
-        uint32_t lv;
-        const uint32_t r = mwc1_draw(rng, rp.one, lv);
-        uint32_t at;
-        if (QM == QM_LANE) at = qtab_s + (r & mask) * 128u;
-        else at = qtab_s + ((min(i0 + j, rp.phred.npos - 1u) << rp.phred.cb) + (r & mask)) * 4u;     /* custom_short.rs:339-345 */
-        const uint32_t e = lds32(at);
+    for (uint32_t j = 0; j < 4; j += 2) {
+        const uint32_t lv0 = rng.x, lv1 = rng.c;
+        uint32_t unused;
+        const uint32_t r = mwc1_draw(rng, rp.one, unused);
+        uint32_t at0, at1;
+        if (QM == QM_LANE) {
+            at0 = qtab_s + (r & mask) * 128u;
+            at1 = CB7 ? qtab_s + (r & 0x3f80u) : qtab_s + ((r >> rp.phred.cb) & mask) * 128u;
+        } else {
+            const uint32_t last = rp.phred.npos - 1u, cb = rp.phred.cb;                              /* custom_short.rs:339-345 */
+            at0 = qtab_s + ((min(i0 + j, last) << cb) + (r & mask)) * 4u;
+            at1 = qtab_s + ((min(i0 + j + 1u, last) << cb) + ((r >> cb) & mask)) * 4u;
+        }
+        const uint32_t e0 = lds32(at0), e1 = lds32(at1);
         /* byte j of qw <- byte 0 (self) or 1 (alias) of the entry; bytes below j stay */
-        const uint32_t keep = 0x3210u & ((1u << (4u * j)) - 1u);
-        qw = __byte_perm(qw, e, lv < e ? (keep | (4u << (4u * j))) : (keep | (5u << (4u * j))));
+        const uint32_t keep0 = 0x3210u & ((1u << (4u * j)) - 1u), keep1 = 0x3210u & ((1u << (4u * j + 4u)) - 1u);
+        qw = __byte_perm(qw, e0, lv0 < e0 ? (keep0 | (4u << (4u * j))) : (keep0 | (5u << (4u * j))));
+        qw = __byte_perm(qw, e1, lv1 < e1 ? (keep1 | (4u << (4u * j + 4u))) : (keep1 | (5u << (4u * j + 4u))));
     }
     return qw;
 }
@@ -815,7 +830,7 @@ __device__ __forceinline__ uint32_t quals4(const RunParams &rp, uint32_t qtab_s,
  * then the reverse-complement table turns each byte into 4 letters (util.rs:31-37) — while its quality line runs
  * forward like mate 1's: quality i belongs to window base i, never reversed (simulate.rs:283-285).  Substitutions
  * are applied afterwards (substitutions_lane), so the two lines are independent here. */
-template <int QM>
+template <int QM, bool CB7>
 __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, uint32_t lut_s, bool on, bool rc, uint32_t body_s,
                                           Mwc1 &rng, uint64_t a, uint32_t L, uint32_t T16) {
     if (!on) { L = 0; a = 0; }
@@ -845,7 +860,7 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
         uint32_t cs[4], cq[4];                         /* the turn's four words of each line, on the stage's word grid */
 #pragma unroll
         for (uint32_t h = 0; h < 4; ++h) {
-            const uint32_t qw = QM == QM_CONST ? qconst : quals4<QM>(rp, qtab_s, mask, rng, 16u * it + 4u * h);
+            const uint32_t qw = QM == QM_CONST ? qconst : quals4<QM, CB7>(rp, qtab_s, mask, rng, 16u * it + 4u * h);
             const uint32_t sw = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
             cs[h] = __funnelshift_l(prev_s, sw, sh_s); cq[h] = QM == QM_CONST ? qconst : __funnelshift_l(prev_q, qw, sh_q);
             prev_s = sw; prev_q = qw;
@@ -944,20 +959,25 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
 
     const uint32_t mate = lane & 1u, slot = lane >> 1;
     const uint32_t ntiles = (rp.batch_units + WARP_UNITS - 1) / WARP_UNITS;
+    /* a tile's offsets (lane k: unit k, lane WARP_UNITS: the end) and descriptors are fetched one tile ahead, into registers */
+    auto fetch_tile = [&](uint32_t tile, uint64_t &off, UnitDesc &d) {
+        off = 0; d = UnitDesc{};
+        if (tile < ntiles) {
+            const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
+            if (lane <= tn) off = rp.offsets[t0 + lane];
+            if (slot < tn) d = rp.desc[t0 + slot];
+        }
+    };
+    uint64_t off_next; UnitDesc d_next;
+    fetch_tile(blockIdx.x * nwarps + warp, off_next, d_next);
     for (uint32_t tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) {
         const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
-        {   /* pull the next tile's offsets and descriptors towards the SM while this one is composed */
-            const uint32_t nt = (tile + gridDim.x * nwarps) * WARP_UNITS + lane;
-            if (lane <= WARP_UNITS && nt <= rp.batch_units) asm volatile("prefetch.global.L1 [%0];" ::"l"(rp.offsets + nt));
-            if (lane < WARP_UNITS && nt < rp.batch_units) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(rp.desc + nt));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(rp.desc + nt) + 32));
-            }
-        }
+        const uint64_t off_tile = off_next; const UnitDesc d_tile = d_next;
+        fetch_tile(tile + gridDim.x * nwarps, off_next, d_next);
         for (uint32_t s0 = 0; s0 < tn;) {
             /* sub-tile = longest run of units from s0 that fits the stage */
             const uint32_t u0 = t0 + s0, left = tn - s0;
-            const uint64_t off = lane <= left ? rp.offsets[u0 + lane] : 0;
+            const uint64_t off = s0 == 0 ? off_tile : (lane <= left ? rp.offsets[u0 + lane] : 0);
             const uint64_t tile_base = __shfl_sync(0xffffffffu, off, 0), next = __shfl_down_sync(0xffffffffu, off, 1);
             const uint32_t pad = uint32_t(tile_base & 15);
             const uint32_t nu = __popc(__ballot_sync(0xffffffffu, lane < left && next - tile_base + pad <= rp.stage_cap));
@@ -965,8 +985,8 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
             const uint32_t unit_off = pad + uint32_t(__shfl_sync(0xffffffffu, off, slot) - tile_base);
             /* this lane's record */
             const bool mine = slot < nu;
-            UnitDesc d{};
-            if (mine) d = rp.desc[u0 + slot];
+            UnitDesc d = d_tile;
+            if (s0 != 0) { d = UnitDesc{}; if (mine) d = rp.desc[u0 + slot]; }
             const bool have = mine && (mate == 0 || (d.flags & 4u));
             const uint32_t L = mate ? d.L1 : d.L0, H = mate ? d.H1 : d.H0;
             const uint64_t a = mate ? d.a1 : d.a0;
@@ -988,7 +1008,9 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
                 if (T16) {
                     Mwc1 qc{}, ec{};
                     if (QM != QM_CONST) mwc1_seed(rp, qc, ec, 1u + mate, uint32_t(unit), uint32_t(unit >> 32));
-                    body_lane<QM>(rp, qtab_s, base_s + (mate ? SM_LUT_RC : SM_LUT_FWD), fast, mate != 0, body_s, qc, a, L, T16);
+                    const uint32_t lut_s = base_s + (mate ? SM_LUT_RC : SM_LUT_FWD);
+                    if (QM == QM_LANE && rp.phred.cb == 7u) body_lane<QM, true>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T16);
+                    else body_lane<QM, false>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T16);
                     if (QM != QM_CONST && rp.phred.has_sub) substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
                 }
                 if (have && !fast) {
