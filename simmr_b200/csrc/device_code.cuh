@@ -1018,6 +1018,13 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
                     else emit_body_short<false>(rp, stage + rec + H, unit, mate, a, L);
                 }
             }
+            if (s0 == 0) {   /* the next tile's windows of the 2-bit genome copy: towards L2 while this tile's headers are written */
+                const uint64_t an = mate ? d_next.a1 : d_next.a0;
+                const uint32_t Ln = mate ? d_next.L1 : d_next.L0;
+                const uint8_t *pn = reinterpret_cast<const uint8_t *>(rp.packed) + (an >> 2);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pn));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + (Ln >> 2)));
+            }
             __syncwarp();
 
             /* ---- phase 2: header and the fixed bytes ---- */

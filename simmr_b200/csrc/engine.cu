@@ -58,7 +58,7 @@ struct PinnedMem {
 struct simmr_ctx {
     int device = 0;
     cudaDeviceProp prop{};
-    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaStream_t compute = nullptr, copy = nullptr, prep = nullptr;   /* format kernels; D2H of finished batches; geometry + offsets of the next batch */
     std::string err;
     /* genomes */
     bool have_genomes = false;
@@ -78,7 +78,8 @@ struct simmr_ctx {
     DevMem d_phred, d_gap, d_qsub, d_rl_e, d_rl_lo, d_rl_hi, d_is_e, d_is_lo, d_is_hi;
     DevMem d_acc, d_plthr, d_rodds, d_ralias, d_roff, d_rlo, d_rhi;
     /* run scratch */
-    DevMem d_unit_start, d_sizes, d_offsets, d_block_sums, d_counters, d_desc, d_out[2];
+    DevMem d_unit_start, d_counters, d_out[2];
+    DevMem d_sizes[2], d_offsets[2], d_block_sums[2], d_desc[2];   /* per-batch scratch, two sets: batch b+1 is prepared while batch b is formatted */
     PinnedMem h_out[2], h_total;
     DevMem d_draw[13];
     simmr_stats stats{};
@@ -220,9 +221,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.min_size = m.min_size; rp.is_long = m.is_long; rp.flags = m.flags; rp.phred_mult = 1u << m.cb;
     if (const char *e = getenv("SIMMR_DBG")) rp.flags |= uint32_t(atoi(e)) << 8; rp.mutates = m.mutates;
     for (uint32_t r = 0; r < 10; ++r) { rp.rk[2 * r] = uint32_t(seed) + r * 0x9E3779B9u; rp.rk[2 * r + 1] = uint32_t(seed >> 32) + r * 0xBB67AE85u; }
-    rp.sizes = ctx->d_sizes.as<uint32_t>(); rp.offsets = ctx->d_offsets.as<uint64_t>();
-    rp.desc = ctx->d_desc.as<UnitDesc>();
-    rp.block_sums = ctx->d_block_sums.as<uint64_t>(); rp.counters = ctx->d_counters.as<unsigned long long>();
+    rp.counters = ctx->d_counters.as<unsigned long long>();
     rp.stage_cap = pl.stage_cap; rp.tab_rep = pl.tab_rep; rp.one = 1;
     {   /* MWC64X skip-ahead multipliers: A^(LONG_GRANULE * k) mod (A * 2^32 - 1) */
         const unsigned __int128 mod = (unsigned __int128)(4294883355ull * 4294967296ull - 1ull);
@@ -240,10 +239,11 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     if (rc) return rc;
     if (measure_only) {      /* geometry + record sizes only: what the units would occupy in the FASTQ stream */
         const uint64_t batch = std::min<uint64_t>(ue - ub, 1ull << 24);
-        CU(ctx->d_sizes.reserve(batch * 4)); CU(ctx->d_desc.reserve(batch * sizeof(UnitDesc)));
-        CU(ctx->d_block_sums.reserve(((batch + SIZES_THREADS - 1) / SIZES_THREADS) * 8));
+        CU(ctx->d_sizes[0].reserve(batch * 4)); CU(ctx->d_desc[0].reserve(batch * sizeof(UnitDesc)));
+        CU(ctx->d_block_sums[0].reserve(((batch + SIZES_THREADS - 1) / SIZES_THREADS) * 8));
         CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
         RunParams rp; fill_params(ctx, rp, seed, opts ? opts->read_id_base : 0, pl);
+        rp.sizes = ctx->d_sizes[0].as<uint32_t>(); rp.desc = ctx->d_desc[0].as<UnitDesc>(); rp.block_sums = ctx->d_block_sums[0].as<uint64_t>();
         simmr_stats st{};
         for (uint64_t u = ub; u < ue; u += batch) {
             const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
@@ -267,18 +267,28 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     if (batch * pl.max_unit_bytes > (64ull << 30)) batch = std::max<uint64_t>(1, (64ull << 30) / pl.max_unit_bytes);
     const uint64_t out_cap = batch * pl.max_unit_bytes + 64;
     const uint32_t max_blocks = uint32_t((batch + SIZES_THREADS - 1) / SIZES_THREADS);
-    CU(ctx->d_sizes.reserve(batch * 4)); CU(ctx->d_desc.reserve(batch * sizeof(UnitDesc))); CU(ctx->d_offsets.reserve((batch + 1) * 8)); CU(ctx->d_block_sums.reserve(size_t(max_blocks) * 8));
+    for (int k = 0; k < 2; ++k) {
+        CU(ctx->d_sizes[k].reserve(batch * 4)); CU(ctx->d_desc[k].reserve(batch * sizeof(UnitDesc)));
+        CU(ctx->d_offsets[k].reserve((batch + 1) * 8)); CU(ctx->d_block_sums[k].reserve(size_t(max_blocks) * 8));
+    }
     CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
-    const bool guard = getenv("SIMMR_DEBUG_GUARD") != nullptr;
+    const bool guard = getenv("SIMMR_DEBUG_GUARD") != nullptr, dbg_sync = getenv("SIMMR_DEBUG_SYNC") != nullptr;
     const int nbuf = sink ? 2 : 1;
     for (int b = 0; b < nbuf; ++b) CU(ctx->d_out[b].reserve(out_cap));
     if (sink) { for (int b = 0; b < 2; ++b) CU(ctx->h_out[b].reserve(out_cap)); }
     CU(ctx->h_total.reserve(2 * sizeof(uint64_t)));
 
     RunParams rp; fill_params(ctx, rp, seed, opts ? opts->read_id_base : 0, pl);
-    cudaEvent_t ev_start, ev_stop, ev_f0, ev_f1, ev_total[2], ev_fmt[2], ev_copy[2];
+    auto scratch = [&](RunParams &r, int k) {
+        r.sizes = ctx->d_sizes[k].as<uint32_t>(); r.offsets = ctx->d_offsets[k].as<uint64_t>();
+        r.desc = ctx->d_desc[k].as<UnitDesc>(); r.block_sums = ctx->d_block_sums[k].as<uint64_t>();
+    };
+    cudaEvent_t ev_start, ev_stop, ev_f0, ev_f1, ev_total[2], ev_fmt[2], ev_copy[2], ev_prep[2], ev_done[2];
     CU(cudaEventCreate(&ev_start)); CU(cudaEventCreate(&ev_stop)); CU(cudaEventCreate(&ev_f0)); CU(cudaEventCreate(&ev_f1));
-    for (int b = 0; b < 2; ++b) { CU(cudaEventCreate(&ev_total[b])); CU(cudaEventCreate(&ev_fmt[b])); CU(cudaEventCreate(&ev_copy[b])); }
+    for (int b = 0; b < 2; ++b) {
+        CU(cudaEventCreate(&ev_total[b])); CU(cudaEventCreate(&ev_fmt[b])); CU(cudaEventCreate(&ev_copy[b]));
+        CU(cudaEventCreateWithFlags(&ev_prep[b], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
+    }
     simmr_stats st{};
     double format_ms = 0.0;
     struct Pending { bool live = false; uint64_t first = 0, units = 0; } pend[2];
@@ -290,24 +300,43 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         if (sink(user, static_cast<const uint8_t *>(ctx->h_out[slot].p), total, pend[slot].first, pend[slot].units)) return fail(ctx, SIMMR_E_SINK, "sink callback failed");
         return SIMMR_OK;
     };
+    /* geometry, sizes and byte offsets of batch number `nb` on the prep stream, into scratch set nb & 1: the small kernels
+     * need no shared memory and share the SMs with the format kernel of the batch before */
+    bool done_live[2] = {false, false};
+    auto prepare = [&](uint64_t u, uint64_t nb) -> int {
+        const int k = int(nb & 1);
+        const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
+        RunParams r = rp; scratch(r, k);
+        r.batch_begin = u; r.batch_units = n;
+        if (done_live[k]) CU(cudaStreamWaitEvent(ctx->prep, ev_done[k], 0));     /* the format kernel that read this set has finished */
+        const uint32_t nblk = (n + SIZES_THREADS - 1) / SIZES_THREADS;
+        if (replay) k_unit_sizes<true><<<nblk, SIZES_THREADS, 0, ctx->prep>>>(r, rd);
+        else k_unit_sizes<false><<<nblk, SIZES_THREADS, 0, ctx->prep>>>(r, rd);
+        if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(ctx->prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("k_unit_sizes: ") + cudaGetErrorString(e_)); }
+        k_scan_blocks<<<1, 1024, 0, ctx->prep>>>(r, nblk);
+        k_unit_offsets<<<nblk, SIZES_THREADS, 0, ctx->prep>>>(r);
+        CU(cudaGetLastError());
+        if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(ctx->prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("scan kernels: ") + cudaGetErrorString(e_)); }
+        CU(cudaEventRecord(ev_prep[k], ctx->prep));
+        return SIMMR_OK;
+    };
     CU(cudaEventRecord(ev_start, ctx->compute));
+    CU(cudaStreamWaitEvent(ctx->prep, ev_start, 0));
+    rc = prepare(ub, 0); if (rc) return rc;
     int slot = 0; uint64_t nbatch = 0;
     for (uint64_t u = ub; u < ue; u += batch, ++nbatch) {
         const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
+        const int k = int(nbatch & 1);
         if (sink) { rc = drain(slot); if (rc) return rc; }       /* slot's buffers are about to be reused */
+        if (u + batch < ue) { rc = prepare(u + batch, nbatch + 1); if (rc) return rc; }
+        scratch(rp, k);
         rp.batch_begin = u; rp.batch_units = n; rp.out = ctx->d_out[slot].as<uint8_t>();
         if (guard) CU(cudaMemsetAsync(ctx->d_out[slot].p, 0xA5, out_cap, ctx->compute));
-        const uint32_t nblk = (n + SIZES_THREADS - 1) / SIZES_THREADS;
-        if (replay) k_unit_sizes<true><<<nblk, SIZES_THREADS, 0, ctx->compute>>>(rp, rd);
-        else k_unit_sizes<false><<<nblk, SIZES_THREADS, 0, ctx->compute>>>(rp, rd);
-        if (getenv("SIMMR_DEBUG_SYNC")) { cudaError_t e_ = cudaStreamSynchronize(ctx->compute); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("k_unit_sizes: ") + cudaGetErrorString(e_)); }
-        k_scan_blocks<<<1, 1024, 0, ctx->compute>>>(rp, nblk);
-        k_unit_offsets<<<nblk, SIZES_THREADS, 0, ctx->compute>>>(rp);
+        CU(cudaStreamWaitEvent(ctx->compute, ev_prep[k], 0));
         if (sink) {
             CU(cudaMemcpyAsync(static_cast<uint64_t *>(ctx->h_total.p) + slot, rp.offsets + n, 8, cudaMemcpyDeviceToHost, ctx->compute));
             CU(cudaEventRecord(ev_total[slot], ctx->compute));
         }
-        if (getenv("SIMMR_DEBUG_SYNC")) { cudaError_t e_ = cudaStreamSynchronize(ctx->compute); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("scan kernels: ") + cudaGetErrorString(e_)); }
         CU(cudaEventRecord(ev_f0, ctx->compute));
         if (pl.tiles) {
             const uint32_t wpc = pl.threads / 32, nctas = ((n + WARP_UNITS - 1) / WARP_UNITS + wpc - 1) / wpc;
@@ -322,6 +351,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         }
         CU(cudaGetLastError());
         CU(cudaEventRecord(ev_f1, ctx->compute));
+        CU(cudaEventRecord(ev_done[k], ctx->compute)); done_live[k] = true;
         if (guard) {   /* SIMMR_DEBUG_GUARD: nothing may be written past the batch's last byte */
             uint64_t total = 0; uint8_t tail[64];
             CU(cudaMemcpyAsync(&total, rp.offsets + n, 8, cudaMemcpyDeviceToHost, ctx->compute));
@@ -356,7 +386,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     st.bytes = ctr[1] - ctr[2];                                   /* (3L+H+5) - L */
     st.device_ms = ms; st.format_ms = format_ms;
     cudaEventDestroy(ev_start); cudaEventDestroy(ev_stop); cudaEventDestroy(ev_f0); cudaEventDestroy(ev_f1);
-    for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_total[b]); cudaEventDestroy(ev_fmt[b]); cudaEventDestroy(ev_copy[b]); }
+    for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_total[b]); cudaEventDestroy(ev_fmt[b]); cudaEventDestroy(ev_copy[b]); cudaEventDestroy(ev_prep[b]); cudaEventDestroy(ev_done[b]); }
     ctx->stats = st;
     return SIMMR_OK;
 }
@@ -403,6 +433,7 @@ int simmr_ctx_create(int device, simmr_ctx **out) {
     if (ctx->prop.major != 10) return bail("device is sm_" + std::to_string(ctx->prop.major * 10 + ctx->prop.minor) + "; this library carries sm_100a code only");
     if ((e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = cudaStreamCreateWithFlags(&ctx->prep, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
     *out = ctx;
     return SIMMR_OK;
 }
@@ -413,6 +444,7 @@ void simmr_ctx_destroy(simmr_ctx *ctx) {
     cudaDeviceSynchronize();
     if (ctx->compute) cudaStreamDestroy(ctx->compute);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
+    if (ctx->prep) cudaStreamDestroy(ctx->prep);
     delete ctx;
 }
 
