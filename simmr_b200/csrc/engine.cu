@@ -303,25 +303,26 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     /* geometry, sizes and byte offsets of batch number `nb` on the prep stream, into scratch set nb & 1: the small kernels
      * need no shared memory and share the SMs with the format kernel of the batch before */
     bool done_live[2] = {false, false};
+    cudaStream_t prep = getenv("SIMMR_PREP_SERIAL") ? ctx->compute : ctx->prep;     /* SIMMR_PREP_SERIAL: everything on one stream (kernel timings without co-runners) */
     auto prepare = [&](uint64_t u, uint64_t nb) -> int {
         const int k = int(nb & 1);
         const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
         RunParams r = rp; scratch(r, k);
         r.batch_begin = u; r.batch_units = n;
-        if (done_live[k]) CU(cudaStreamWaitEvent(ctx->prep, ev_done[k], 0));     /* the format kernel that read this set has finished */
+        if (done_live[k]) CU(cudaStreamWaitEvent(prep, ev_done[k], 0));     /* the format kernel that read this set has finished */
         const uint32_t nblk = (n + SIZES_THREADS - 1) / SIZES_THREADS;
-        if (replay) k_unit_sizes<true><<<nblk, SIZES_THREADS, 0, ctx->prep>>>(r, rd);
-        else k_unit_sizes<false><<<nblk, SIZES_THREADS, 0, ctx->prep>>>(r, rd);
-        if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(ctx->prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("k_unit_sizes: ") + cudaGetErrorString(e_)); }
-        k_scan_blocks<<<1, 1024, 0, ctx->prep>>>(r, nblk);
-        k_unit_offsets<<<nblk, SIZES_THREADS, 0, ctx->prep>>>(r);
+        if (replay) k_unit_sizes<true><<<nblk, SIZES_THREADS, 0, prep>>>(r, rd);
+        else k_unit_sizes<false><<<nblk, SIZES_THREADS, 0, prep>>>(r, rd);
+        if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("k_unit_sizes: ") + cudaGetErrorString(e_)); }
+        k_scan_blocks<<<1, 1024, 0, prep>>>(r, nblk);
+        k_unit_offsets<<<nblk, SIZES_THREADS, 0, prep>>>(r);
         CU(cudaGetLastError());
-        if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(ctx->prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("scan kernels: ") + cudaGetErrorString(e_)); }
-        CU(cudaEventRecord(ev_prep[k], ctx->prep));
+        if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("scan kernels: ") + cudaGetErrorString(e_)); }
+        CU(cudaEventRecord(ev_prep[k], prep));
         return SIMMR_OK;
     };
     CU(cudaEventRecord(ev_start, ctx->compute));
-    CU(cudaStreamWaitEvent(ctx->prep, ev_start, 0));
+    CU(cudaStreamWaitEvent(prep, ev_start, 0));
     rc = prepare(ub, 0); if (rc) return rc;
     int slot = 0; uint64_t nbatch = 0;
     for (uint64_t u = ub; u < ue; u += batch, ++nbatch) {
