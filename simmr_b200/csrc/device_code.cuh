@@ -631,19 +631,48 @@ __device__ __forceinline__ void bs_decimal(ByteStream &b, uint32_t dec2_s, uint3
  * literal, ..., field, literal with nf <= HDR_MAX_FIELDS decimal fields whose kinds (4 bits each) are the same
  * for every contig; tk = this (contig, mate)'s token list. */
 constexpr uint32_t HDR_MAX_FIELDS = 4;
+/* up to four whole words of a literal from one 16-byte fetch: `whole` = whole words of the literal not yet written */
+__device__ __forceinline__ void bs_words16(ByteStream &b, const uint4 v, int32_t whole) {
+    if (whole > 0) bs_word(b, v.x);
+    if (whole > 1) bs_word(b, v.y);
+    if (whole > 2) bs_word(b, v.z);
+    if (whole > 3) bs_word(b, v.w);
+}
 __device__ __forceinline__ void header_tokens(ByteStream &b, const RunParams &rp, uint32_t dec2_s, const uint2 *tk, uint32_t kinds,
                                               uint32_t nf, uint32_t id, uint32_t sp, uint32_t ep) {
-    uint2 lit[HDR_MAX_FIELDS + 1];                                               /* {off, len | type << 16}, fetched together */
+    /* three rounds of loads instead of one per literal word (there is next to no L1 beside the stages): the token
+     * descriptors {off, len | type << 16}; then every literal's first 16 bytes and its last, partial word; then what is
+     * left of a literal longer than 16 bytes, 48 bytes at a time.  Literals start on 16-byte boundaries of the pool. */
+    uint2 lit[HDR_MAX_FIELDS + 1];
 #pragma unroll
     for (uint32_t i = 0; i <= HDR_MAX_FIELDS; ++i) lit[i] = i <= nf ? __ldg(tk + 2 * i) : make_uint2(0u, 0u);
+    uint4 first[HDR_MAX_FIELDS + 1]; uint32_t tail[HDR_MAX_FIELDS + 1];
+#pragma unroll
+    for (uint32_t i = 0; i <= HDR_MAX_FIELDS; ++i) {
+        const uint32_t len = lit[i].y & 0xffffu;
+        first[i] = make_uint4(0u, 0u, 0u, 0u); tail[i] = 0u;
+        if (i <= nf && len) first[i] = __ldg(reinterpret_cast<const uint4 *>(rp.pool + lit[i].x));
+        if (i <= nf && len > 16u && (len & 3u)) tail[i] = __ldg(reinterpret_cast<const uint32_t *>(rp.pool + lit[i].x + (len & ~3u)));
+    }
 #pragma unroll
     for (uint32_t i = 0; i <= HDR_MAX_FIELDS; ++i) {
         if (i > nf) break;                                                       /* same for every thread */
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(rp.pool + lit[i].x);
         const uint32_t len = lit[i].y & 0xffffu, nw = len >> 2;
-#pragma unroll 4
-        for (uint32_t j = 0; j < nw; ++j) bs_word(b, __ldg(src + j));
-        if (len & 3u) bs_put(b, __ldg(src + nw), len & 3u);
+        bs_words16(b, first[i], int32_t(nw));
+        if (len > 16u) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(rp.pool + lit[i].x);
+            for (uint32_t q = 1; 4u * q < nw; q += 3) {                          /* 16-byte pieces q, q+1, q+2 */
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                const uint4 v0 = __ldg(src + q), v1 = 4u * (q + 1u) < nw ? __ldg(src + q + 1) : z, v2 = 4u * (q + 2u) < nw ? __ldg(src + q + 2) : z;
+                bs_words16(b, v0, int32_t(nw) - int32_t(4u * q));
+                bs_words16(b, v1, int32_t(nw) - int32_t(4u * q + 4u));
+                bs_words16(b, v2, int32_t(nw) - int32_t(4u * q + 8u));
+            }
+            if (len & 3u) bs_put(b, tail[i], len & 3u);
+        } else if (len & 3u) {                                                   /* the partial word is one of the first four */
+            const uint32_t w = nw == 0 ? first[i].x : nw == 1 ? first[i].y : nw == 2 ? first[i].z : first[i].w;
+            bs_put(b, w, len & 3u);
+        }
         if (i < nf) {
             const uint32_t kind = (kinds >> (4u * i)) & 15u;
             bs_decimal(b, dec2_s, kind == TOK_READ_ID ? id : kind == TOK_START ? sp : ep);
@@ -886,22 +915,25 @@ __device__ __forceinline__ void substitutions_lane(const RunParams &rp, uint32_t
                                                    Mwc1 &ev, uint32_t L) {
     const uint32_t Ds = body_s + 1u, Dq = body_s + L + 4u, mask = rp.phred_mult - 1u;
     uint32_t next = on ? 0u : L;
+    /* a step's three draws and two table entries are fetched one step ahead of their use */
+    uint32_t l1, l2, l3;
+    uint32_t r1 = mwc1_draw(ev, rp.one, l1), r2 = mwc1_draw(ev, rp.one, l2), r3 = mwc1_draw(ev, rp.one, l3);
+    uint32_t eg = lds32(gap_s + 4u * (r1 & (GAP_COLS - 1u))), eq = lds32(qsub_s + 4u * (r2 & mask));
     while (next < L) {
-        uint32_t l1, l2, l3;
-        const uint32_t r1 = mwc1_draw(ev, rp.one, l1), r2 = mwc1_draw(ev, rp.one, l2), r3 = mwc1_draw(ev, rp.one, l3);
-        const uint32_t g = q32_pick(lds32(gap_s + 4u * (r1 & (GAP_COLS - 1u))), l1);
+        const uint32_t g = q32_pick(eg, l1), qn = q32_pick(eq, l2), m = 1u + __umulhi(r3, 3u);
+        r1 = mwc1_draw(ev, rp.one, l1); r2 = mwc1_draw(ev, rp.one, l2); r3 = mwc1_draw(ev, rp.one, l3);
+        eg = lds32(gap_s + 4u * (r1 & (GAP_COLS - 1u))); eq = lds32(qsub_s + 4u * (r2 & mask));
         if (g == GAP_NONE) { next += GAP_NONE; continue; }
         const uint32_t at = next + g;
         if (at >= L) break;
-        sts8(Dq + at, q32_pick(lds32(qsub_s + 4u * (r2 & mask)), l2));
+        sts8(Dq + at, qn);
         const uint32_t sa = Ds + (rc ? L - 1u - at : at);
         uint32_t b; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(sa) : "memory");
         uint32_t rank = (b >> 1) & 3u; rank ^= rank >> 1;                       /* A,C,G,T -> 0..3 */
-        sts8(sa, (0x54474341u >> (8u * (rank ^ (1u + __umulhi(r3, 3u))))) & 0xffu);
+        sts8(sa, (0x54474341u >> (8u * (rank ^ m))) & 0xffu);
         next = at + 1u;
     }
 }
-
 
 /* Persistent warps, one lane per record.  A warp owns WARP_UNITS consecutive units (32 records) at a time: it composes
  * their FASTQ bytes in its private stage in shared memory and sends them off with one bulk async copy (TMA); only the
