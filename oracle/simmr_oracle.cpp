@@ -193,28 +193,10 @@ struct Philox {
         block(blk, stream, (uint32_t)unit, (uint32_t)(unit >> 32), out);
     }
 };
-/* Per-base words of native mode.  A read's 4-base groups are cut into four runs of
- * rho = 2*ceil((groups+1)/8) groups.  Inside run j, base i takes the next output of chain (i & 3);
- * the four chains are MWC64X generators (D. B. Thomas: x' = lo(A*x + c), c' = hi(A*x + c), output
- * x ^ c, A = 4294883355) seeded from the two Philox blocks (2j, 2j+1) of the read's stream. */
-struct BaseWords {
-    uint32_t x[4], c[4];
-    static uint32_t run_groups(uint64_t L) { const uint64_t ng = (L + 3) >> 2; return (uint32_t)(2 * ((ng + 8) >> 3)); }
-    void seed(const Philox &ph, uint64_t unit, uint32_t stream, uint32_t run) {
-        for (uint32_t h = 0; h < 2; h++) {
-            uint32_t w[4]; ph.at(unit, stream, 2 * run + h, w);
-            x[2 * h] = w[0]; c[2 * h] = (w[1] >> 2) + 1; x[2 * h + 1] = w[2]; c[2 * h + 1] = (w[3] >> 2) + 1;
-        }
-    }
-    uint32_t next(uint32_t j) {
-        const uint32_t r = x[j] ^ c[j];
-        const uint64_t t = (uint64_t)x[j] * 4294883355u + c[j];
-        x[j] = (uint32_t)t; c[j] = (uint32_t)(t >> 32);
-        return r;
-    }
-};
-/* Short reads: one Philox block (0, stream, unit) seeds two MWC64X chains of the record — words 0,1 the
- * quality chain (base i takes its i-th output), words 2,3 the substitution-event chain. */
+/* Per-base draws of native mode.  A read is cut into pieces (short reads: one piece; long reads: 32 pieces
+ * of 16 * ceil(L / 512) bases); Philox block (piece, stream, unit) seeds the piece's two MWC64X chains (D. B. Thomas:
+ * x' = lo(A*x + c), c' = hi(A*x + c), A = 4294883355) — words 0,1 the quality chain (one step per two bases), words 2,3
+ * the substitution-event chain. */
 /* word = x ^ c (its low bits pick a table column), level = x (compared with the entry); the quality chain serves a second
  * base from the same step: column from the next cb bits of the word, level2 = c */
 struct Draw { uint32_t word, level, level2; };
@@ -441,12 +423,11 @@ inline double mutation_prob(uint8_t q) {
 }
 
 struct PhredTable {      /* per-position alias tables */
-    uint32_t kind = 0;   /* 0: constant quality; 1: T64 {thr32, q_self|m_self<<8|q_alias<<16|m_alias<<24};
-                            2: T32 thr16<<16 | q_alias<<8 | q_self (no mutation) */
+    uint32_t kind = 0;   /* 0: constant quality; 3: thr16<<16 | alias<<8 | self per column (kinds 1 and 2 are retired) */
     uint8_t const_q = 0;
     uint32_t cb = 0, npos = 0;
-    std::vector<uint32_t> entries;   /* kind 1: 2 words per column, kind 2 and 3: 1 word per column */
-    /* kind 3 (short reads): the kind-2 word, sampled with column = low cb bits of the draw and "self iff draw < word";
+    std::vector<uint32_t> entries;   /* one word per column, npos rows */
+    /* kind 3: sampled with column = low cb bits of the draw's word and "self iff the draw's level < entry";
      * a mutating profile adds gap[256] (bases until the next substitution, 255 = none within 255) and
      * qsub[1 << cb] (quality given a substitution) */
     bool has_sub = false;
@@ -474,31 +455,6 @@ struct Profile {
     std::vector<RustAlias> q_alias;
 };
 
-/* joint (q, mutation) weights: outcome o = (q-qlo)<<2 | m, m=0 none, 1..3 = choice+1 */
-std::vector<double> with_mutation(const std::vector<double> &pq, uint32_t qlo) {
-    std::vector<double> w(pq.size() * 4);
-    for (size_t i = 0; i < pq.size(); i++) {
-        double pm = mutation_prob((uint8_t)(qlo + i));
-        w[4 * i] = pq[i] * (1.0 - pm);
-        w[4 * i + 1] = w[4 * i + 2] = w[4 * i + 3] = pq[i] * pm / 3.0;
-    }
-    return w;
-}
-/* mutating profiles: outcome o = (q-qlo)<<2 | m over the joint (quality, mutation) weights */
-bool phred_table_from_pmf(const std::vector<double> &pq, uint32_t qlo, PhredTable &t) {
-    std::vector<double> w = with_mutation(pq, qlo);
-    t.kind = 1; t.npos = 1; t.cb = std::max(1u, ceil_log2(w.size()));
-    if (t.cb > 10) return false;
-    std::vector<double> prob; std::vector<uint32_t> alias;
-    if (!vose(w, t.cb, prob, alias)) return false;
-    auto pay = [&](uint32_t o) { return ((qlo + (o >> 2)) & 0xffu) | ((o & 3u) << 8); };
-    t.entries.resize(prob.size() * 2);
-    for (size_t i = 0; i < prob.size(); i++) {
-        t.entries[2 * i] = quant_thr(prob[i], 32);
-        t.entries[2 * i + 1] = pay((uint32_t)i) | (pay(alias[i]) << 16);
-    }
-    return true;
-}
 /* kind 3 word: a column whose 16-bit threshold is zero names its alias twice, so that the payload bits of the word
  * cannot make the sampler keep a column that has no mass */
 inline uint32_t q32_entry(double prob, uint32_t self_v, uint32_t alias_v) {
@@ -513,11 +469,11 @@ bool q32_table(const std::vector<double> &w, uint32_t vlo, uint32_t cb, std::vec
     for (size_t i = 0; i < prob.size(); i++) out[i] = q32_entry(prob[i], vlo + (uint32_t)i, vlo + alias[i]);
     return true;
 }
-/* Short reads of a mutating profile.  minimal_short.rs:83-140 draws q, then substitutes with probability pm(q),
+/* Mutating profiles.  minimal_short.rs:83-140 (and its twins minimal_long.rs:78-140, perfect_long.rs:60-119) draws q, then substitutes with probability pm(q),
  * independently per base.  The same joint law, factored the other way: a base is substituted with the marginal
  * probability s = sum_q P(q) pm(q); a substituted base's quality follows P(q | substituted), any other base's
  * P(q | kept).  The substituted bases of a record are then found by geometric gaps. */
-bool phred_short_table_from_pmf(const std::vector<double> &pq, uint32_t qlo, PhredTable &t) {
+bool phred_table_from_pmf(const std::vector<double> &pq, uint32_t qlo, PhredTable &t) {
     const size_t n = pq.size();
     std::vector<double> kept(n), subst(n);
     double s = 0.0;
@@ -542,7 +498,7 @@ bool phred_short_table_from_pmf(const std::vector<double> &pq, uint32_t qlo, Phr
 }
 /* per-position tables from the blob: alias over densities, uniform in-bin,
  * `as u8` truncation (custom_short.rs:108-129, 328-352); no mutation */
-bool phred_table_from_blob(const Blob &b, bool long_reads, PhredTable &t) {
+bool phred_table_from_blob(const Blob &b, PhredTable &t) {
     size_t np = b.quality.size();
     if (np == 0) return false;
     std::vector<std::vector<double>> pm(np, std::vector<double>(256, 0.0));
@@ -568,7 +524,7 @@ bool phred_table_from_blob(const Blob &b, bool long_reads, PhredTable &t) {
         }
     }
     if (qmin > qmax) return false;
-    t.kind = long_reads ? 2 : 3; t.npos = (uint32_t)np;
+    t.kind = 3; t.npos = (uint32_t)np;
     t.cb = std::max(1u, ceil_log2(qmax - qmin + 1));
     t.entries.clear();
     for (size_t p = 0; p < np; p++) {
@@ -576,8 +532,7 @@ bool phred_table_from_blob(const Blob &b, bool long_reads, PhredTable &t) {
         std::vector<uint32_t> alias;
         if (!vose(w, t.cb, prob, alias)) return false;
         for (size_t i = 0; i < prob.size(); i++)
-            t.entries.push_back(long_reads ? (quant_thr(prob[i], 16) << 16) | (((qmin + alias[i]) & 0xffu) << 8) | ((qmin + (uint32_t)i) & 0xffu)
-                                           : q32_entry(prob[i], qmin + (uint32_t)i + 33u, qmin + alias[i] + 33u));
+            t.entries.push_back(q32_entry(prob[i], qmin + (uint32_t)i + 33u, qmin + alias[i] + 33u));
     }
     return true;
 }
@@ -632,7 +587,7 @@ bool make_profile(const orc_profile *in, Profile &p) {
         p.min_size = (uint16_t)(2 * p.read_length + p.insert_size);
         uint32_t vlo; std::vector<double> pmf;
         normal_floor_pmf((double)(float)p.mean_phred, 10.0, 255, vlo, pmf);
-        if (!phred_short_table_from_pmf(pmf, vlo, p.phred)) { fail("phred table"); return false; }
+        if (!phred_table_from_pmf(pmf, vlo, p.phred)) { fail("phred table"); return false; }
         normal_floor_pmf((double)p.read_length, 15.0, 65535, vlo, pmf);
         if (!len_table_from_pmf(pmf, vlo, p.rl)) { fail("rl table"); return false; }
         normal_floor_pmf((double)p.insert_size, 75.0, 65535, vlo, pmf);
@@ -654,14 +609,14 @@ bool make_profile(const orc_profile *in, Profile &p) {
     case ORC_CUSTOM_SHORT: {  /* custom_short.rs:155-229, 237-270, 522-542 */
         p.is_long = p.blob.is_long; p.mutates = false;
         p.min_size = sat_u16(2.0 * p.blob.rl_mean + p.blob.is_mean);
-        if (!phred_table_from_blob(p.blob, p.is_long, p.phred)) { fail("custom phred table"); return false; }
+        if (!phred_table_from_blob(p.blob, p.phred)) { fail("custom phred table"); return false; }
         if (!len_table_from_bins(p.blob.rl_bins, p.rl)) { fail("custom rl table"); return false; }
         if (p.blob.has_is_bins) { if (!len_table_from_bins(p.blob.is_bins, p.is)) { fail("custom is table"); return false; } }
         else { p.is.kind = 0; p.is.value = 0; }
         break; }
     case ORC_CUSTOM_LONG: {   /* phreds as custom-short, gamma lengths */
         p.is_long = true; p.mutates = false; p.min_size = 20000;
-        if (!phred_table_from_blob(p.blob, true, p.phred)) { fail("custom phred table"); return false; }
+        if (!phred_table_from_blob(p.blob, p.phred)) { fail("custom phred table"); return false; }
         p.rl.kind = 2; p.is.kind = 0; p.is.value = 0;
         break; }
     default: fail("unknown profile kind"); return false;
@@ -686,20 +641,6 @@ inline uint32_t sample_len(const LenTable &t, uint32_t w_alias, uint32_t w_inbin
     uint32_t lo = t.lo[col], hi = t.hi[col];
     uint64_t span = (uint64_t)hi - lo + 1;
     return lo + (uint32_t)(((uint64_t)w_inbin * span) >> 32);
-}
-inline void sample_phred(const PhredTable &t, uint32_t pos, uint32_t w, uint8_t &q, uint32_t &m) {
-    if (t.kind == 0) { q = t.const_q; m = 0; return; }
-    if (pos >= t.npos) pos = t.npos - 1;                       /* custom_short.rs:339-345 */
-    const uint32_t idx = w >> (32 - t.cb), x = w << t.cb;
-    const size_t col = ((size_t)pos << t.cb) + idx;
-    if (t.kind == 1) {
-        const uint32_t thr = t.entries[2 * col], pay = t.entries[2 * col + 1];
-        const uint32_t sel = x < thr ? (pay & 0xffffu) : (pay >> 16);
-        q = (uint8_t)(sel & 0xffu); m = (sel >> 8) & 0xffu;
-    } else {
-        const uint32_t e = t.entries[col];
-        q = (uint8_t)((x >> 16) < (e >> 16) ? (e & 0xffu) : ((e >> 8) & 0xffu)); m = 0;
-    }
 }
 /* kind 3 entry against a draw: column = low cb bits of the draw's word, self iff its level < entry */
 inline uint32_t sample_q32(const uint32_t *row, uint32_t cb, Draw d) {
@@ -891,54 +832,40 @@ bool native_geometry(const GenomeView &gv, const Profile &p, const UnitMap &um, 
     return true;
 }
 
-/* one mate / long read in native mode: phreds, mutation in forward
- * orientation (simulate.rs:265-270 / 497-503) */
+/* pieces of a read and their length: short reads are one piece, long reads 32 pieces of a multiple of 16 bases */
+inline uint64_t piece_len(uint64_t L, bool long_read) { return long_read ? 16 * ((L + 511) / 512) : L; }
+
+/* one mate / long read in native mode: per piece, qualities from the piece's quality chain, then the
+ * substituted bases by geometric gaps along the piece (forward-strand order, simulate.rs:265-270 / 497-503) */
 void native_read(const Profile &p, const Philox &ph, uint64_t u, uint32_t stream, const uint8_t *src, uint64_t L,
                  std::vector<uint8_t> &seq, std::vector<uint8_t> &qual, orc_stats &st) {
-    seq.resize(L); qual.resize(L);
-    BaseWords bw{};
-    const uint32_t rho = BaseWords::run_groups(L);
-    for (uint64_t i = 0; i < L; i++) {
-        uint8_t q; uint32_t m;
-        if (p.phred.kind == 0) { q = p.phred.const_q; m = 0; }
-        else {
-            if ((i & 3) == 0 && (i >> 2) % rho == 0) bw.seed(ph, u, stream, (uint32_t)((i >> 2) / rho));
-            sample_phred(p.phred, (uint32_t)std::min<uint64_t>(i, 0xffffffffu), bw.next((uint32_t)(i & 3)), q, m);
-        }
-        qual[i] = q;
-        uint8_t b = src[i];
-        if (m) { uint8_t nb = substitute_native(b, m); if (nb != b) st.mutated++; b = nb; }
-        seq[i] = b;
-    }
-}
-
-/* one mate of a short read in native mode: qualities from the record's quality chain, then the
- * substituted bases by geometric gaps along the window (forward-strand order, simulate.rs:265-270) */
-void native_read_short(const Profile &p, const Philox &ph, uint64_t u, uint32_t stream, const uint8_t *src, uint64_t L,
-                       std::vector<uint8_t> &seq, std::vector<uint8_t> &qual, orc_stats &st) {
     seq.assign(src, src + L); qual.resize(L);
     const PhredTable &t = p.phred;
     if (t.kind == 0) { std::fill(qual.begin(), qual.end(), t.const_q); return; }
-    uint32_t w[4]; ph.at(u, stream, 0, w);
-    Chain qc(w[0], w[1]), ec(w[2], w[3]);
-    Draw d{};
-    for (uint64_t i = 0; i < L; i++) {                 /* one step of the quality chain per two bases */
-        const uint64_t pos = std::min<uint64_t>(i, t.npos - 1);                 /* custom_short.rs:339-345 */
-        if (!(i & 1)) d = qc.next(); else d = Draw{d.word >> t.cb, d.level2, 0};
-        qual[i] = (uint8_t)(sample_q32(t.entries.data() + (pos << t.cb), t.cb, d) - 33u);   /* the table holds characters */
-    }
-    if (!t.has_sub) return;
-    for (uint64_t next = 0; next < L;) {               /* every step takes three words of the event chain */
-        const Draw r1 = ec.next(), r2 = ec.next(), r3 = ec.next();
-        const uint32_t g = sample_q32(t.gap.data(), 8, r1);
-        if (g == 255) { next += 255; continue; }
-        const uint64_t at = next + g;
-        if (at >= L) break;
-        qual[at] = (uint8_t)(sample_q32(t.qsub.data(), t.cb, r2) - 33u);
-        const uint8_t nb = substitute_native(seq[at], 1u + mulhi32(r3.word, 3u));
-        if (nb != seq[at]) st.mutated++;
-        seq[at] = nb;
-        next = at + 1;
+    const uint64_t S = piece_len(L, p.is_long);
+    for (uint64_t lo = 0, piece = 0; lo < L; lo += S, piece++) {
+        const uint64_t hi = std::min(L, lo + S);
+        uint32_t w[4]; ph.at(u, stream, (uint32_t)piece, w);
+        Chain qc(w[0], w[1]), ec(w[2], w[3]);
+        Draw d{};
+        for (uint64_t i = lo; i < hi; i++) {               /* one step of the quality chain per two bases */
+            const uint64_t pos = std::min<uint64_t>(i, t.npos - 1);             /* custom_short.rs:339-345 */
+            if (!((i - lo) & 1)) d = qc.next(); else d = Draw{d.word >> t.cb, d.level2, 0};
+            qual[i] = (uint8_t)(sample_q32(t.entries.data() + (pos << t.cb), t.cb, d) - 33u);   /* the table holds characters */
+        }
+        if (!t.has_sub) continue;
+        for (uint64_t next = lo; next < hi;) {             /* every step takes three draws of the event chain */
+            const Draw r1 = ec.next(), r2 = ec.next(), r3 = ec.next();
+            const uint32_t g = sample_q32(t.gap.data(), 8, r1);
+            if (g == 255) { next += 255; continue; }
+            const uint64_t at = next + g;
+            if (at >= hi) break;
+            qual[at] = (uint8_t)(sample_q32(t.qsub.data(), t.cb, r2) - 33u);
+            const uint8_t nb = substitute_native(seq[at], 1u + mulhi32(r3.word, 3u));
+            if (nb != seq[at]) st.mutated++;
+            seq[at] = nb;
+            next = at + 1;
+        }
     }
 }
 
@@ -1228,8 +1155,8 @@ int64_t orc_simulate(const orc_genomes *g, const orc_profile *pi, const uint64_t
         if (!p.is_long) {
             const PeGeom &pg = ng.pe;
             if (pg.clamped) st.clamped++;
-            native_read_short(p, ph, u, 1, cs + pg.fs, pg.fe - pg.fs, s1, q1, st);     /* :261,265,269 */
-            native_read_short(p, ph, u, 2, cs + pg.lo, pg.hi - pg.lo, s2, q2, st);     /* :262,266,270 */
+            native_read(p, ph, u, 1, cs + pg.fs, pg.fe - pg.fs, s1, q1, st);     /* :261,265,269 */
+            native_read(p, ph, u, 2, cs + pg.lo, pg.hi - pg.lo, s2, q2, st);     /* :262,266,270 */
             auto rc = reverse_complement(s2.data(), s2.size());                       /* :283; quality NOT reversed :285 */
             emit_record(buf, fmt, gid, id, sid, pg.fs, ng.start + ng.RL, false, 1, s1, q1);   /* :287-292: end_pos = fwd_end */
             emit_record(buf, fmt, gid, id, sid, pg.lo + (uint64_t)ng.RL, pg.lo, true, 2, rc, q2);   /* :293-298: start=rev_start, end=rev_end */

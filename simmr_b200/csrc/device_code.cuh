@@ -37,9 +37,8 @@ struct ReplayDev {                 /* device copies of simmr_draws + replay LUTs
     uint32_t r_npos, pl_qmax, kind; float mean_phred, acc20;
 };
 
-/* long reads: a run (quarter of a read, at most 4098 groups) is cut into LONG_PARTS pieces, the unit of work of k_format_long;
- * a piece is a multiple of LONG_GRANULE groups so that the word chains can jump to it with one table entry */
-constexpr uint32_t LONG_PARTS = 8, LONG_GRANULE = 32, LONG_JUMPS = 136;
+/* long reads are cut into LONG_PIECES pieces of a multiple of 16 bases, each with its own chains: the 32 lanes' work in k_format_long */
+constexpr uint32_t LONG_PIECES = 32;
 struct UnitDesc;
 struct RunParams {
     /* genomes (device resident) */
@@ -55,8 +54,6 @@ struct RunParams {
     PhredTab phred; LenTab rl, is; GammaConst gamma;
     uint32_t min_size, is_long, flags, mutates;
     uint32_t phred_mult;           /* 1 << phred.cb */
-    uint32_t tab_rep;              /* copies of every PT_T64 entry in shared memory, interleaved so that lane l reads copy l % tab_rep */
-    uint64_t mwc_skip[LONG_JUMPS]; /* A^(LONG_GRANULE * k) mod (A * 2^32 - 1): jumps a per-base word chain k granules into its run */
     uint32_t rk[20];               /* Philox round keys: seed + r * Weyl constants, r = 0..9 */
     /* per-batch scratch + output */
     uint32_t *sizes; uint64_t *offsets, *block_sums; uint8_t *out;
@@ -76,10 +73,9 @@ constexpr int FORMAT_MIN_CTAS = 1;
 constexpr int DIRECT_THREADS = 256;
 constexpr uint32_t PACK_PAD_WORDS = 4104; /* readable words before and after `packed`: a lane keeps fetching (and discarding)
                                              for as long as the longest record of its warp lasts, at most 65535 / 16 words */
-/* shared-memory layout of a format CTA (byte offsets from the 1024-aligned base); SM_TAB: quality table of the long-read
- * and direct kernels; the short-read kernel keeps gap / qsub / quality tables at SM_GAP / SM_QSUB / SM_QTAB */
-constexpr uint32_t SM_LUT_FWD = 0, SM_LUT_RC = 1024, SM_DEC2 = 2048, SM_TAB = 2304;
-constexpr uint32_t SM_GAP = 2304, SM_QSUB = 3328, SM_QTAB = 4352;
+/* shared-memory layout of a format CTA (byte offsets from the 1024-aligned base): letter tables, two-digit table, gap and
+ * quality-given-substitution tables, quality table (per-lane copies or one copy per position), then the warps' stages */
+constexpr uint32_t SM_LUT_FWD = 0, SM_LUT_RC = 1024, SM_DEC2 = 2048, SM_GAP = 2304, SM_QSUB = 3328, SM_QTAB = 4352;
 constexpr uint32_t STAGE_FRONT = 16;  /* slack before the tile image (a header's leading newline may land there) */
 /* how k_format_lanes samples qualities */
 enum : int { QM_CONST = 0,            /* one quality for every base                                              */
@@ -114,34 +110,8 @@ __device__ __forceinline__ Philox4 draw(const RunParams &rp, uint64_t unit, uint
 }
 __device__ __forceinline__ uint64_t pair64(uint32_t lo, uint32_t hi) { return uint64_t(lo) | (uint64_t(hi) << 32); }
 
-/* Per-base words: a read's 4-base groups are cut into four runs of run_groups(L)
- * groups; inside run j, base i takes the next output of chain i & 3.  The chains are MWC64X
- * generators (D. B. Thomas: x' = lo(A*x + c), c' = hi(A*x + c), output x ^ c) seeded from the two
- * Philox blocks (2j, 2j+1) of the read's stream: one multiply-add per word on the multiply pipe. */
-struct Mwc4 { uint32_t x[4], c[4]; };
-__device__ __forceinline__ uint32_t run_groups(uint32_t L) { return 2u * ((((L + 3u) >> 2) + 8u) >> 3); }
-__device__ __forceinline__ void mwc_seed(const RunParams &rp, Mwc4 &m, uint32_t run, uint32_t stream, uint32_t ulo, uint32_t uhi) {
-    const Philox4 a = philox(rp.rk, 2u * run, stream, ulo, uhi), b = philox(rp.rk, 2u * run + 1u, stream, ulo, uhi);
-    m.x[0] = a.x; m.c[0] = (a.y >> 2) + 1u; m.x[1] = a.z; m.c[1] = (a.w >> 2) + 1u;
-    m.x[2] = b.x; m.c[2] = (b.y >> 2) + 1u; m.x[3] = b.z; m.c[3] = (b.w >> 2) + 1u;
-}
-/* the chain's state n steps ahead: as a number t = x + c * 2^32 a step is t -> t * A mod (A * 2^32 - 1); jump = A^n mod m */
-__device__ __forceinline__ void mwc_jump(uint32_t &x, uint32_t &c, uint64_t jump) {
-    /* (t * jump) mod m with m = A * 2^32 - 1: fold the high half down with 2^64 mod m = (2^32 - A) * 2^32 + 1 (49 bits),
-     * five folds bring a 128-bit product below 2^65, then at most two subtractions */
-    constexpr uint64_t M = 4294883355ull * 4294967296ull - 1ull, R = (4294967296ull - 4294883355ull) * 4294967296ull + 1ull;
-    const uint64_t t = uint64_t(x) | (uint64_t(c) << 32);
-    uint64_t lo = t * jump, hi = __umul64hi(t, jump);
-#pragma unroll
-    for (int f = 0; f < 5; ++f) {
-        const uint64_t pl = hi * R, ph = __umul64hi(hi, R);
-        lo += pl; hi = ph + (lo < pl ? 1ull : 0ull);
-    }
-    /* now hi is 0 or 1 */
-    if (hi) { lo += R; if (lo < R) lo += R; }           /* + 2^64 mod m (the second carry cannot happen twice) */
-    if (lo >= M) lo -= M;
-    x = uint32_t(lo); c = uint32_t(lo >> 32);
-}
+/* Per-base draws: MWC64X generators (D. B. Thomas: x' = lo(A*x + c), c' = hi(A*x + c), A = 4294883355)
+ * seeded from Philox words. */
 __device__ __forceinline__ uint32_t mwc_next(uint32_t &x, uint32_t &c) {
     const uint32_t r = x ^ c;
     const uint64_t t = uint64_t(x) * 4294883355u + c;
@@ -149,8 +119,8 @@ __device__ __forceinline__ uint32_t mwc_next(uint32_t &x, uint32_t &c) {
     return r;
 }
 
-/* Short reads: one Philox block (0, stream, unit) seeds the two chains of a record — words 0,1 the quality
- * chain (base i of the window takes its i-th output), words 2,3 the substitution-event chain. */
+/* Philox block (piece, stream, unit) seeds the two chains of a piece of a read — words 0,1 the quality chain (one step per
+ * two bases), words 2,3 the substitution-event chain.  Short reads are one piece (block 0), long reads LONG_PIECES. */
 struct Mwc1 { uint32_t x, c; };
 /* one draw = (word, level): word = x ^ c picks a table column with its low bits, level = x is compared with the entry;
  * then the chain steps.  The 64-bit addend {c, 0} is made by a widening multiply by `one` (a kernel parameter that is
@@ -161,12 +131,14 @@ __device__ __forceinline__ uint32_t mwc1_draw(Mwc1 &m, uint32_t one, uint32_t &l
     asm("{ .reg .b64 cc, t; mul.wide.u32 cc, %1, %2; mad.wide.u32 t, %0, %3, cc; mov.b64 {%0, %1}, t; }" : "+r"(m.x), "+r"(m.c) : "r"(one), "r"(4294883355u));
     return r;
 }
-__device__ __forceinline__ void mwc1_seed(const RunParams &rp, Mwc1 &qc, Mwc1 &ec, uint32_t stream, uint32_t ulo, uint32_t uhi) {
-    const Philox4 w = philox(rp.rk, 0u, stream, ulo, uhi);
+__device__ __forceinline__ void mwc1_seed(const RunParams &rp, Mwc1 &qc, Mwc1 &ec, uint32_t piece, uint32_t stream, uint32_t ulo, uint32_t uhi) {
+    const Philox4 w = philox(rp.rk, piece, stream, ulo, uhi);
     qc.x = w.x; qc.c = (w.y >> 2) + 1u; ec.x = w.z; ec.c = (w.w >> 2) + 1u;
 }
 /* PT_Q32 entry of the column the draw's word picked: self iff level < entry */
 __device__ __forceinline__ uint32_t q32_pick(uint32_t e, uint32_t level) { return (level < e ? e : e >> 8) & 0xffu; }
+/* bases per piece of a read of L bases */
+__device__ __forceinline__ uint32_t piece_len(uint32_t L, bool long_read) { return long_read ? 16u * ((L + 511u) >> 9) : L; }
 
 /* ---------------------------------------------------------------------- */
 /* samplers                                                                 */
@@ -431,159 +403,72 @@ __device__ __forceinline__ void replay_base(const RunParams &rp, const ReplayDev
     if (rp.mutates && rd.mut_u[slot] > rd.acc_lut[q]) m = 1 + rd.mut_k[slot] % 3;   /* minimal_short.rs:123-125 */
 }
 
-/* (quality byte as printed, mutation code) of base i from its Philox word */
-__device__ __forceinline__ void native_base(const RunParams &rp, const uint32_t *tab, uint32_t tab_rep, uint32_t r, uint32_t i, uint32_t &qc, uint32_t &m) {
-    const uint32_t cb = rp.phred.cb, idx = r >> (32 - cb), x = r << cb;
-    const uint32_t pos = i < rp.phred.npos ? i : rp.phred.npos - 1;               /* custom_short.rs:339-345 */
-    const uint32_t col = (pos << cb) + idx;
-    if (rp.phred.kind == PT_T64) {
-        const uint32_t thr = tab[2 * col * tab_rep], pay = tab[2 * col * tab_rep + 1];
-        const uint32_t s = x < thr ? pay : pay >> 16;
-        qc = s & 0xffu; m = (s >> 8) & 0xffu;
-    } else {
-        const uint32_t e = tab[col];
-        qc = ((x >> 16) < (e >> 16) ? e : e >> 8) & 0xffu; m = 0;
-    }
-}
-
-/* Short reads, native mode, one thread and byte stores: the record's quality chain, then its substitution events
- * (DESIGN.md §4).  Used for windows that hold anything but A,C,G,T and for records that do not fit a stage; same
- * bytes as the word path of k_format_lanes.  Tables are read from global memory (qualities carry the +33). */
+/* Native mode with byte stores, one thread per piece of the read (thread thr of nthr takes pieces thr, thr + nthr, ...):
+ * the piece's quality chain, then its substitution events.  Used for windows that hold anything but
+ * A,C,G,T, for records that do not fit a stage and behind SIMMR_NO_LONG_KERNEL; same bytes as the word paths of
+ * k_format_lanes and k_format_long.  Tables are read from global memory (entries hold the characters as printed). */
 template <bool PUNCT>
-__device__ void emit_body_short(const RunParams &rp, uint8_t *dst, uint64_t unit, uint32_t mate, uint64_t a, uint32_t L) {
+__device__ void emit_body_pieces(const RunParams &rp, uint8_t *dst, uint64_t unit, uint32_t mate, uint64_t a, uint32_t L, uint32_t thr, uint32_t nthr) {
     uint8_t *seq = dst + 1, *qual = dst + L + 4;
-    if (PUNCT) { dst[0] = '\n'; dst[L + 1] = '\n'; dst[L + 2] = '+'; dst[L + 3] = '\n'; dst[2 * L + 4] = '\n'; }   /* fastq.rs:61-69 */
+    if (PUNCT && thr == 0) { dst[0] = '\n'; dst[L + 1] = '\n'; dst[L + 2] = '+'; dst[L + 3] = '\n'; dst[2 * L + 4] = '\n'; }   /* fastq.rs:61-69 */
     const uint8_t *src = rp.bases + a;
-    const bool rc = mate != 0;
-    Mwc1 qc{}, ec{};
-    const bool sampled = rp.phred.kind != PT_CONST;
-    if (sampled) mwc1_seed(rp, qc, ec, 1 + mate, uint32_t(unit), uint32_t(unit >> 32));
-    const uint32_t mask = rp.phred_mult - 1u, last = rp.phred.npos - 1u;
-    uint32_t word = 0, lv_odd = 0;                           /* one step of the quality chain serves two bases (quals4) */
-    for (uint32_t i = 0; i < L; ++i) {
-        uint32_t qc8 = (rp.phred.const_q + 33u) & 0xffu;
-        if (sampled) {
-            uint32_t lv = lv_odd, col = (word >> rp.phred.cb) & mask;
-            if (!(i & 1u)) { lv_odd = qc.c; word = mwc1_draw(qc, rp.one, lv); col = word & mask; }
-            qc8 = q32_pick(__ldg(rp.phred.entries + (min(i, last) << rp.phred.cb) + col), lv);
+    const bool rc = mate != 0, sampled = rp.phred.kind != PT_CONST;
+    const uint32_t mask = rp.phred_mult - 1u, last = rp.phred.npos - 1u, S = piece_len(L, rp.is_long != 0);
+    for (uint32_t piece = thr; piece * uint64_t(S) < L; piece += nthr) {
+        const uint32_t lo = piece * S, hi = min(L, lo + S);
+        Mwc1 qc{}, ec{};
+        if (sampled) mwc1_seed(rp, qc, ec, piece, 1 + mate, uint32_t(unit), uint32_t(unit >> 32));
+        uint32_t word = 0, lv_odd = 0;                       /* one step of the quality chain serves two bases (quals4) */
+        for (uint32_t i = lo; i < hi; ++i) {
+            uint32_t qc8 = (rp.phred.const_q + 33u) & 0xffu;
+            if (sampled) {
+                uint32_t lv = lv_odd, col = (word >> rp.phred.cb) & mask;
+                if (!((i - lo) & 1u)) { lv_odd = qc.c; word = mwc1_draw(qc, rp.one, lv); col = word & mask; }
+                qc8 = q32_pick(__ldg(rp.phred.entries + (min(i, last) << rp.phred.cb) + col), lv);
+            }
+            qual[i] = uint8_t(qc8);
+            const uint8_t b = __ldg(src + i);
+            if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;           /* util.rs:31-37 */
         }
-        qual[i] = uint8_t(qc8);
-        const uint8_t b = __ldg(src + i);
-        if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;               /* util.rs:31-37 */
-    }
-    if (!sampled || !rp.phred.has_sub) return;
-    for (uint32_t next = 0; next < L;) {                                        /* three words of the event chain per step */
-        uint32_t l1, l2, l3;
-        const uint32_t r1 = mwc1_draw(ec, rp.one, l1), r2 = mwc1_draw(ec, rp.one, l2), r3 = mwc1_draw(ec, rp.one, l3);
-        const uint32_t g = q32_pick(__ldg(rp.phred.gap + (r1 & (GAP_COLS - 1u))), l1);
-        if (g == GAP_NONE) { next += GAP_NONE; continue; }
-        const uint32_t at = next + g;
-        if (at >= L) break;
-        qual[at] = uint8_t(q32_pick(__ldg(rp.phred.qsub + (r2 & mask)), l2));
-        uint8_t *sb = rc ? seq + (L - 1 - at) : seq + at;                      /* mutated before the reverse complement (simulate.rs:269-286) */
-        const uint8_t fwd = rc ? complement(*sb) : *sb, nb = substitute_native(fwd, 1u + __umulhi(r3, 3u));
-        *sb = rc ? complement(nb) : nb;
-        next = at + 1u;
+        if (!sampled || !rp.phred.has_sub) continue;
+        for (uint32_t next = lo; next < hi;) {                                  /* three draws of the event chain per step */
+            uint32_t l1, l2, l3;
+            const uint32_t r1 = mwc1_draw(ec, rp.one, l1), r2 = mwc1_draw(ec, rp.one, l2), r3 = mwc1_draw(ec, rp.one, l3);
+            const uint32_t g = q32_pick(__ldg(rp.phred.gap + (r1 & (GAP_COLS - 1u))), l1);
+            if (g == GAP_NONE) { next += GAP_NONE; continue; }
+            const uint32_t at = next + g;
+            if (at >= hi) break;
+            qual[at] = uint8_t(q32_pick(__ldg(rp.phred.qsub + (r2 & mask)), l2));
+            uint8_t *sb = rc ? seq + (L - 1 - at) : seq + at;                  /* mutated before the reverse complement (simulate.rs:269-286) */
+            const uint8_t fwd = rc ? complement(*sb) : *sb, nb = substitute_native(fwd, 1u + __umulhi(r3, 3u));
+            *sb = rc ? complement(nb) : nb;
+            next = at + 1u;
+        }
     }
 }
 
-/* Writes the sequence and quality lines of one record with byte stores (and, when PUNCT, the
- * five fixed bytes around them); `dst` = the byte after the header, in shared or global
- * memory.  Base i of the window gets quality slot i; for mate 2 the (mutated) base is
- * complemented and lands at L-1-i, the quality stays at i (simulate.rs:283-285). */
-template <bool REPLAY, bool PUNCT>
-__device__ __forceinline__ void emit_body_generic(const RunParams &rp, const ReplayDev &rd, const uint32_t *tab, uint32_t tab_rep, uint8_t *dst,
-                                                  uint64_t unit, uint32_t mate, uint64_t a, uint32_t L, uint64_t slot0, uint32_t thr, uint32_t nthr) {
+/* Replay: the sequence and quality lines of one record from recorded draws, byte stores (and, when PUNCT, the five
+ * fixed bytes around them); `dst` = the byte after the header, in shared or global memory.  Base i of the window
+ * takes draw slot slot0 + i; for mate 2 the (mutated) base is complemented and lands at L-1-i, the quality stays at i
+ * (simulate.rs:283-285).  Thread thr of nthr takes bases thr, thr + nthr, ... */
+template <bool PUNCT>
+__device__ __forceinline__ void emit_body_replay(const RunParams &rp, const ReplayDev &rd, uint8_t *dst, uint32_t mate, uint64_t a, uint32_t L,
+                                                 uint64_t slot0, uint32_t thr, uint32_t nthr) {
     uint8_t *seq = dst + 1, *qual = dst + L + 4;
     if (PUNCT && thr == 0) { dst[0] = '\n'; dst[L + 1] = '\n'; dst[L + 2] = '+'; dst[L + 3] = '\n'; dst[2 * L + 4] = '\n'; }   /* fastq.rs:61-69 */
     const uint8_t *src = rp.bases + a;
     const bool rc = mate != 0;
-    const uint32_t NG = (L + 3u) >> 2;
-    /* replay: groups dealt round-robin; native: one thread per run of the per-base word schedule */
-    const uint32_t rho = REPLAY ? 1u : run_groups(L);
-    for (uint32_t run = thr; run * rho < NG; run += nthr) {
-        Mwc4 w{};
-        if (!REPLAY && rp.phred.kind != PT_CONST) mwc_seed(rp, w, run, 1 + mate, uint32_t(unit), uint32_t(unit >> 32));
-        for (uint32_t g = run * rho; g < min(NG, (run + 1u) * rho); ++g) {
-#pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) {
-                const uint32_t i = 4 * g + j;
-                if (i >= L) break;
-                uint32_t qc, m;
-                if (REPLAY) { uint32_t q; replay_base(rp, rd, slot0 + i, i, q, m); qc = (q + 33) & 0xffu; }   /* util.rs:46-50 */
-                else if (rp.phred.kind == PT_CONST) { qc = (rp.phred.const_q + 33) & 0xffu; m = 0; }
-                else native_base(rp, tab, tab_rep, mwc_next(w.x[j], w.c[j]), i, qc, m);
-                uint8_t b = __ldg(src + i);
-                if (m) b = REPLAY ? substitute(b, m - 1) : substitute_native(b, m);
-                qual[i] = uint8_t(qc);
-                if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;
-            }
-        }
+    for (uint32_t i = thr; i < L; i += nthr) {
+        uint32_t q, m; replay_base(rp, rd, slot0 + i, i, q, m);
+        uint8_t b = __ldg(src + i);
+        if (m) b = substitute(b, m - 1);
+        qual[i] = uint8_t((q + 33) & 0xffu);                                    /* util.rs:46-50 */
+        if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;
     }
 }
-
-/* ---------------------------------------------------------------------- */
-/* per-base work, fast path: windows of pure A/C/G/T                        */
-/* ---------------------------------------------------------------------- */
-/* Long reads (k_format_long): per 4-base group
- *   - four words, one per base, from the run's four MWC64X chains,
- *   - each word becomes (quality char, mutation code) through the alias table in shared memory,
- *   - the group's 4 bases are one byte of the 2-bit genome copy: XOR the packed mutation codes into it and map the
- *     byte to 4 ASCII letters through a 256-entry table in shared memory. */
 
 __device__ __forceinline__ uint32_t lds32m(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ uint32_t lds16(uint32_t addr) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ uint32_t mulhi_lo(uint32_t a, uint32_t b, uint32_t &lo) { const uint64_t p = uint64_t(a) * b; lo = uint32_t(p); return uint32_t(p >> 32); }
-
-/* quality characters (+33 applied) and mutation codes of bases 4g..4g+3 from their four words */
-template <int TK>
-__device__ __forceinline__ void sample4(const RunParams &rp, uint32_t tab_s, const uint32_t (&r)[4], uint32_t g, uint32_t &qw, uint32_t &mw) {
-    uint32_t col[4], x[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)                   /* r * 2^cb as one wide multiply: high word = column, low word = threshold draw */
-        asm("{ .reg .b64 p; mul.wide.u32 p, %2, %3; mov.b64 {%1, %0}, p; }" : "=r"(col[j]), "=r"(x[j]) : "r"(r[j]), "r"(rp.phred_mult));
-    if (TK == PT_T64) {
-        uint2 e[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {             /* entry address by a multiply-add (kept out of the shift unit) */
-            uint32_t at; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(at) : "r"(col[j]), "r"(8u * rp.tab_rep), "r"(tab_s));   /* tab_s: this lane's copy */
-            e[j] = lds64(at);
-        }
-        /* byte selectors: self = payload bytes 0 (quality) and 1 (mutation), alias = bytes 2 and 3 */
-        const uint32_t s01 = (x[0] < e[0].x ? 0x5140u : 0x5342u) + (x[1] < e[1].x ? 0u : 0x2020u);
-        const uint32_t s23 = (x[2] < e[2].x ? 0x5140u : 0x5342u) + (x[3] < e[3].x ? 0u : 0x2020u);
-        const uint32_t a = __byte_perm(e[0].y, e[1].y, s01), b = __byte_perm(e[2].y, e[3].y, s23);   /* q0 q1 m0 m1 | q2 q3 m2 m3 */
-        qw = __byte_perm(a, b, 0x5410); mw = __byte_perm(a, b, 0x7632);
-    } else {
-        const uint32_t last = rp.phred.npos - 1, cb = rp.phred.cb;
-        uint32_t e[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t pos = min(4 * g + j, last);                                          /* custom_short.rs:339-345 */
-            e[j] = lds32(tab_s + (((pos << cb) + col[j]) << 2));
-        }
-        /* entry = thr16<<16 | q_alias<<8 | q_self; keep self when (x >> 16) < thr16 */
-        const uint32_t s01 = (x[0] < (e[0] & 0xffff0000u) ? 0x40u : 0x41u) + (x[1] < (e[1] & 0xffff0000u) ? 0u : 0x10u);
-        const uint32_t s23 = (x[2] < (e[2] & 0xffff0000u) ? 0x40u : 0x41u) + (x[3] < (e[3] & 0xffff0000u) ? 0u : 0x10u);
-        qw = __byte_perm(__byte_perm(e[0], e[1], s01), __byte_perm(e[2], e[3], s23), 0x5410); mw = 0;
-    }
-}
-
-/* one 4-base group: byte `bi` of X holds its four 2-bit codes.  Returns the ASCII word of the
- * (substituted) bases in `sw` and the quality characters in `qw`. */
-template <int TK>
-__device__ __forceinline__ void group4(const RunParams &rp, uint32_t tab_s, uint32_t lut_s, uint32_t qconst, uint32_t X, uint32_t bi,
-                                       uint32_t g, Mwc4 &rng, uint32_t &sw, uint32_t &qw) {
-    uint32_t mw = 0;
-    if (TK == PT_CONST) qw = qconst;
-    else {
-        const uint32_t r[4] = {mwc_next(rng.x[0], rng.c[0]), mwc_next(rng.x[1], rng.c[1]), mwc_next(rng.x[2], rng.c[2]), mwc_next(rng.x[3], rng.c[3])};
-        sample4<TK>(rp, tab_s, r, g, qw, mw);
-    }
-    uint32_t at = (bi == 0 ? X << 2 : X >> (8 * bi - 2)) & 0x3fcu;
-    if (TK == PT_T64) at ^= ((mw * 0x01041040u) >> 22) & 0x3fcu;     /* XOR the four 2-bit substitution codes into the byte */
-    sw = lds32(lut_s + at);
-}
 
 /* ---------------------------------------------------------------------- */
 /* headers, fast path: one thread per record, aligned word stores           */
@@ -1039,15 +924,15 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
                 const uint32_t T16 = __reduce_max_sync(0xffffffffu, fast ? (slots + 3u) >> 2 : 0u);
                 if (T16) {
                     Mwc1 qc{}, ec{};
-                    if (QM != QM_CONST) mwc1_seed(rp, qc, ec, 1u + mate, uint32_t(unit), uint32_t(unit >> 32));
+                    if (QM != QM_CONST) mwc1_seed(rp, qc, ec, 0u, 1u + mate, uint32_t(unit), uint32_t(unit >> 32));
                     const uint32_t lut_s = base_s + (mate ? SM_LUT_RC : SM_LUT_FWD);
                     if (QM == QM_LANE && rp.phred.cb == 7u) body_lane<QM, true>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T16);
                     else body_lane<QM, false>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T16);
                     if (QM != QM_CONST && rp.phred.has_sub) substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
                 }
                 if (have && !fast) {
-                    if (REPLAY) emit_body_generic<true, false>(rp, rd, nullptr, 1, stage + rec + H, unit, mate, a, L, rd.base_off[unit] + (mate ? d.rl : 0), 0, 1);
-                    else emit_body_short<false>(rp, stage + rec + H, unit, mate, a, L);
+                    if (REPLAY) emit_body_replay<false>(rp, rd, stage + rec + H, mate, a, L, rd.base_off[unit] + (mate ? d.rl : 0), 0, 1);
+                    else emit_body_pieces<false>(rp, stage + rec + H, unit, mate, a, L, 0, 1);
                 }
             }
             if (s0 == 0) {   /* the next tile's windows of the 2-bit genome copy: towards L2 while this tile's headers are written */
@@ -1096,16 +981,10 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
 }
 
 
-/* One CTA per unit, bytes written straight to global memory.  Used for long
- * reads (records far larger than a tile) and as the fallback when a unit does
- * not fit the shared-memory stage. */
+/* One CTA per unit, bytes written straight to global memory with byte stores: replay of long reads, records that do not
+ * fit a stage, and native long reads behind SIMMR_NO_LONG_KERNEL.  Not a fast path. */
 template <bool REPLAY>
 __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, ReplayDev rd) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u : 1u);
-    uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
-    for (uint32_t i = threadIdx.x; i < tab_words; i += DIRECT_THREADS) tab[i] = rp.phred.entries[i];
-    __syncthreads();
     for (uint32_t i = blockIdx.x; i < rp.batch_units; i += gridDim.x) {
         const uint64_t u = rp.batch_begin + i;
         const UnitDesc d = rp.desc[i];
@@ -1118,8 +997,8 @@ __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, 
                 uint64_t sp, ep; record_positions(d, r, sp, ep);
                 emit_header(dst, rp, rp.chdr[2 * d.contig + r], rp.read_id_base + uint32_t(u), sp, ep);
             }
-            if (!REPLAY && !rp.is_long) { if (threadIdx.x == 0) emit_body_short<true>(rp, dst + H, u, r, r ? d.a1 : d.a0, L); }   /* one chain per record */
-            else emit_body_generic<REPLAY, true>(rp, rd, tab, 1, dst + H, u, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
+            if (REPLAY) emit_body_replay<true>(rp, rd, dst + H, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
+            else emit_body_pieces<true>(rp, dst + H, u, r, r ? d.a1 : d.a0, L, threadIdx.x, DIRECT_THREADS);   /* a thread per piece */
             dst += H + 2 * L + 5;
         }
     }
@@ -1194,33 +1073,36 @@ __device__ __forceinline__ void rl_edges(const RunLine &r, uint32_t k, uint32_t 
     }
 }
 
-/* Long reads (simulate.rs:323-406, 464-523), native mode.  A record is far larger than a stage
- * and read lengths vary by an order of magnitude, so every lane works alone on small pieces: a
- * piece is an eighth of one run (a quarter of one read), taken from a shared
- * counter; the lane jumps the run's word chains to the piece
- * (MWC skip-ahead), writes that part of the sequence and quality lines straight to global memory
- * and takes the next piece.  The lane that takes a read's first piece also writes its header
- * and the fixed bytes.  Reads whose window holds anything but A,C,G,T take the byte path there. */
-template <int TK>
+/* Long reads (simulate.rs:323-406, 464-523), native mode.  A record is far larger than a stage and read lengths vary by
+ * an order of magnitude (gamma, CV 0.75), so a warp takes one read at a time from a shared counter and its 32 lanes take
+ * the read's LONG_PIECES pieces (16 * ceil(L / 512) bases each): all lanes loop the same number of times
+ * whatever the read's length.  A lane seeds its piece's chains, writes that part of the sequence and quality lines
+ * straight to global memory in 16-byte lines (RunLine), then applies the piece's substitutions to the bytes it wrote.
+ * Lane 0 also writes the header and the fixed bytes.  Reads whose window holds anything but A,C,G,T take the byte
+ * path, a lane per piece.  QM as in k_format_lanes. */
+template <int QM>
 __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t tab_words = rp.phred.kind == PT_CONST ? 0 : (rp.phred.npos << rp.phred.cb) * (rp.phred.kind == PT_T64 ? 2u * rp.tab_rep : 1u);
-    uint32_t *tab = reinterpret_cast<uint32_t *>(smem + SM_TAB);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t base_s = uint32_t(__cvta_generic_to_shared(smem));
-    const uint32_t tab_s = base_s + SM_TAB + (rp.phred.kind == PT_T64 ? 8u * (lane & (rp.tab_rep - 1u)) : 0u), lut_s = base_s + SM_LUT_FWD;
-    if (rp.phred.kind == PT_T64) for (uint32_t i = threadIdx.x; i < tab_words; i += blockDim.x) tab[i] = rp.phred.entries[2u * (i / (2u * rp.tab_rep)) + (i & 1u)];
-    else for (uint32_t i = threadIdx.x; i < tab_words; i += blockDim.x) tab[i] = rp.phred.entries[i];
-    for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {
-        uint32_t f = 0;
-        for (uint32_t j = 0; j < 4; ++j) f |= ((0x54474341u >> (8 * ((b >> (2 * j)) & 3u))) & 0xffu) << (8 * j);
-        reinterpret_cast<uint32_t *>(smem + SM_LUT_FWD)[b] = f;
+    const uint32_t qtab_s = base_s + SM_QTAB + (QM == QM_LANE ? 4u * lane : 0u), lut_s = base_s + SM_LUT_FWD;
+    {
+        uint32_t *qt = reinterpret_cast<uint32_t *>(smem + SM_QTAB);
+        if (QM == QM_LANE) for (uint32_t i = threadIdx.x; i < (32u << rp.phred.cb); i += blockDim.x) qt[i] = rp.phred.entries[i >> 5];
+        if (QM == QM_POS) for (uint32_t i = threadIdx.x; i < (rp.phred.npos << rp.phred.cb); i += blockDim.x) qt[i] = rp.phred.entries[i];
+        if (QM != QM_CONST && rp.phred.has_sub) {
+            for (uint32_t i = threadIdx.x; i < GAP_COLS; i += blockDim.x) reinterpret_cast<uint32_t *>(smem + SM_GAP)[i] = rp.phred.gap[i];
+            for (uint32_t i = threadIdx.x; i < rp.phred_mult; i += blockDim.x) reinterpret_cast<uint32_t *>(smem + SM_QSUB)[i] = rp.phred.qsub[i];
+        }
+        for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {
+            uint32_t f = 0;
+            for (uint32_t j = 0; j < 4; ++j) f |= ((0x54474341u >> (8 * ((b >> (2 * j)) & 3u))) & 0xffu) << (8 * j);
+            reinterpret_cast<uint32_t *>(smem + SM_LUT_FWD)[b] = f;
+        }
     }
     __syncthreads();
 
-    const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u;
-    /* a warp takes one read at a time: its 4 runs x LONG_PARTS pieces are the 32 lanes' work, all of (nearly) the same size */
-    const uint32_t j = lane / LONG_PARTS, p = lane % LONG_PARTS;
+    const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u, mask = rp.phred_mult - 1u;
     for (;;) {
         unsigned long long next = 0;
         if (lane == 0) next = atomicAdd(rp.counters + 4, 1ull);
@@ -1234,43 +1116,55 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         if (lane == 0) {                                  /* header and the five fixed bytes (fastq.rs:34-69) */
             emit_header(rec, rp, rp.chdr[2 * d.contig], rp.read_id_base + uint32_t(unit), d.p0, d.p1);
             rec[H] = '\n'; rec[H + L + 1] = '\n'; rec[H + L + 2] = '+'; rec[H + L + 3] = '\n'; rec[H + 2 * L + 4] = '\n';
-            if (bytes_path) { ReplayDev none{}; emit_body_generic<false, false>(rp, none, tab, rp.tab_rep, rec + H, unit, 0, d.a0, L, 0, 0, 1); }
         }
-        if (bytes_path) { __syncwarp(); continue; }
-        const uint32_t NG = (L + 3u) >> 2, rho = run_groups(L), run_end = min(NG, (j + 1u) * rho);
-        const uint32_t gran = ((rho + LONG_PARTS - 1u) / LONG_PARTS + LONG_GRANULE - 1u) / LONG_GRANULE;      /* granules per piece */
-        const uint32_t gb = j * rho + p * gran * LONG_GRANULE;
-        const uint32_t ng = gb < run_end ? min(gran * LONG_GRANULE, run_end - gb) : 0u;                       /* groups of this lane's piece */
-        const uint32_t b0 = 4u * gb, nb = ng ? min(L, 4u * (gb + ng)) - b0 : 0u;
+        if (bytes_path) { emit_body_pieces<false>(rp, rec + H, unit, 0, d.a0, L, lane, 32); __syncwarp(); continue; }
+        const uint32_t S = piece_len(L, true), lo = lane * S;
+        const uint32_t nb = lo < L ? min(S, L - lo) : 0u, ng = (nb + 3u) >> 2;        /* bases and 4-base groups of this lane's piece */
+        uint8_t *seq = rec + H + 1 + lo, *qual = rec + H + L + 4 + lo;
         RunLine ls, lq;
-        rl_open(ls, rec + H + 1 + b0, nb); rl_open(lq, rec + H + L + 4 + b0, nb);
-        Mwc4 rng{};
-        if (TK != PT_CONST && ng) {
-            mwc_seed(rp, rng, j, 1, uint32_t(unit), uint32_t(unit >> 32));
-            if (p) for (uint32_t c = 0; c < 4; ++c) mwc_jump(rng.x[c], rng.c[c], rp.mwc_skip[p * gran]);
-        }
-        const uint64_t a = d.a0 + b0;
+        rl_open(ls, seq, nb); rl_open(lq, qual, nb);
+        Mwc1 qc{}, ec{};
+        if (QM != QM_CONST && nb) mwc1_seed(rp, qc, ec, lane, 1, uint32_t(unit), uint32_t(unit >> 32));
+        const uint64_t a = d.a0 + lo;
         const uint32_t *pw = rp.packed + (a >> 4);
         const uint32_t s2 = 2u * (uint32_t(a) & 15u);
         uint32_t w0 = __ldg(pw), w1 = __ldg(pw + 1);
         pw += 2;
         const uint32_t quads = (ng + 3u) >> 2, T = __reduce_max_sync(0xffffffffu, quads);
-        uint32_t first_s = 0, first_q = 0, g = gb;
-        for (uint32_t qd = 0; qd < T; ++qd) {             /* four groups = one word of the 2-bit copy */
+        uint32_t first_s = 0, first_q = 0;
+        for (uint32_t qd = 0; qd < T; ++qd) {             /* sixteen bases = one word of the 2-bit copy */
             if (qd < quads) {
                 const uint32_t X = __funnelshift_r(w0, w1, s2);
                 w0 = w1; w1 = __ldg(pw++);
                 uint32_t sw[4], qw[4];
 #pragma unroll
-                for (uint32_t h = 0; h < 4; ++h) group4<TK>(rp, tab_s, lut_s, qconst, X, h, g + h, rng, sw[h], qw[h]);
+                for (uint32_t h = 0; h < 4; ++h) {
+                    qw[h] = QM == QM_CONST ? qconst : quals4<QM, false>(rp, qtab_s, mask, qc, lo + 16u * qd + 4u * h);
+                    sw[h] = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
+                }
                 if (qd == 0) { first_s = sw[0]; first_q = qw[0]; }
                 rl_quad(ls, 4u * qd, sw[0], sw[1], sw[2], sw[3]); rl_quad(lq, 4u * qd, qw[0], qw[1], qw[2], qw[3]);
-                g += 4;
             }
         }
         if (ng) {
             const uint32_t kl = 4u * (quads - 1u);
             rl_close(ls, kl, ng); rl_edges(ls, kl, ng, first_s); rl_close(lq, kl, ng); rl_edges(lq, kl, ng, first_q);
+        }
+        if (QM != QM_CONST && rp.phred.has_sub) {         /* the piece's substituted bases, on the bytes this lane just wrote */
+            const uint32_t gap_s = base_s + SM_GAP, qsub_s = base_s + SM_QSUB;
+            for (uint32_t at0 = 0; at0 < nb;) {
+                uint32_t l1, l2, l3;
+                const uint32_t r1 = mwc1_draw(ec, rp.one, l1), r2 = mwc1_draw(ec, rp.one, l2), r3 = mwc1_draw(ec, rp.one, l3);
+                const uint32_t g = q32_pick(lds32(gap_s + 4u * (r1 & (GAP_COLS - 1u))), l1);
+                if (g == GAP_NONE) { at0 += GAP_NONE; continue; }
+                const uint32_t at = at0 + g;
+                if (at >= nb) break;
+                qual[at] = uint8_t(q32_pick(lds32(qsub_s + 4u * (r2 & mask)), l2));
+                const uint32_t b = seq[at];
+                uint32_t rank = (b >> 1) & 3u; rank ^= rank >> 1;                   /* A,C,G,T -> 0..3 */
+                seq[at] = uint8_t(0x54474341u >> (8u * (rank ^ (1u + __umulhi(r3, 3u)))));
+                at0 = at + 1u;
+            }
         }
     }
 }

@@ -120,12 +120,12 @@ FormatKernel lanes_kernel(bool replay, int qm) {
 }
 FormatKernel direct_kernel(bool replay) { return replay ? k_format_direct<true> : k_format_direct<false>; }
 using LongKernel = void (*)(RunParams);
-LongKernel long_kernel(uint32_t kind) { return kind == PT_T64 ? k_format_long<PT_T64> : kind == PT_T32 ? k_format_long<PT_T32> : k_format_long<PT_CONST>; }
+LongKernel long_kernel(int qm) { return qm == QM_LANE ? k_format_long<QM_LANE> : qm == QM_POS ? k_format_long<QM_POS> : k_format_long<QM_CONST>; }
 
 struct Plan {      /* launch geometry for one run */
     bool tiles = false;            /* warp-private stages in shared memory (short reads) vs one CTA per unit */
     bool lanes = false;            /* long reads, native mode: one lane per run (k_format_long) */
-    uint32_t stage_cap = 0, max_unit_bytes = 0, threads = 0, tab_rep = 1;
+    uint32_t stage_cap = 0, max_unit_bytes = 0, threads = 0;
     size_t smem = 0;
     int grid = 0;
 };
@@ -150,18 +150,17 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
         if (const char *e = getenv("SIMMR_WARPS")) warps = uint32_t(std::max(1, std::min(FORMAT_THREADS / 32, atoi(e))));
         while (warps > 1 && lanes_smem(m, warps, uint32_t(cap)) > smem_max) --warps;
         if (cap > 0x7fffffffull || lanes_smem(m, warps, uint32_t(cap)) > smem_max) pl.tiles = false;   /* a single unit does not fit: direct path */
-        else { pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.tab_rep = 1; pl.smem = lanes_smem(m, warps, uint32_t(cap)); }
+        else { pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.smem = lanes_smem(m, warps, uint32_t(cap)); }
     }
     int occ = 0;
     if (!pl.tiles && !replay && m.is_long && !getenv("SIMMR_NO_LONG_KERNEL")) {
         pl.lanes = true; pl.threads = DIRECT_THREADS;
-        pl.tab_rep = m.phred_kind == PT_T64 && tab * 8 <= 32768 ? 8u : 1u;
-        pl.smem = SM_TAB + tab * pl.tab_rep;
-        LongKernel k = long_kernel(m.phred_kind);
+        pl.smem = SM_QTAB + qtab_bytes(quality_mode(m), m.cb, m.npos);
+        LongKernel k = long_kernel(quality_mode(m));
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
     } else {
-        if (!pl.tiles) { pl.smem = tab; pl.threads = DIRECT_THREADS; }
+        if (!pl.tiles) { pl.smem = 0; pl.threads = DIRECT_THREADS; }
         FormatKernel k = pl.tiles ? lanes_kernel(replay, quality_mode(m)) : direct_kernel(replay);
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
@@ -169,7 +168,7 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
     if (occ < 1) return fail(ctx, SIMMR_E_LIMIT, "format kernel does not fit on an SM");
     pl.grid = occ * ctx->prop.multiProcessorCount;
     if (const char *e = getenv("SIMMR_GRID")) pl.grid = std::max(1, atoi(e));
-    if (getenv("SIMMR_DEBUG_SYNC")) fprintf(stderr, "[simmr] tiles=%d threads=%u rep=%u cap=%u smem=%zu occ=%d grid=%d\n", int(pl.tiles), pl.threads, pl.tab_rep, pl.stage_cap, pl.smem, occ, pl.grid);
+    if (getenv("SIMMR_DEBUG_SYNC")) fprintf(stderr, "[simmr] tiles=%d threads=%u cap=%u smem=%zu occ=%d grid=%d\n", int(pl.tiles), pl.threads, pl.stage_cap, pl.smem, occ, pl.grid);
     return SIMMR_OK;
 }
 
@@ -222,13 +221,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     if (const char *e = getenv("SIMMR_DBG")) rp.flags |= uint32_t(atoi(e)) << 8; rp.mutates = m.mutates;
     for (uint32_t r = 0; r < 10; ++r) { rp.rk[2 * r] = uint32_t(seed) + r * 0x9E3779B9u; rp.rk[2 * r + 1] = uint32_t(seed >> 32) + r * 0xBB67AE85u; }
     rp.counters = ctx->d_counters.as<unsigned long long>();
-    rp.stage_cap = pl.stage_cap; rp.tab_rep = pl.tab_rep; rp.one = 1;
-    {   /* MWC64X skip-ahead multipliers: A^(LONG_GRANULE * k) mod (A * 2^32 - 1) */
-        const unsigned __int128 mod = (unsigned __int128)(4294883355ull * 4294967296ull - 1ull);
-        unsigned __int128 step = 1, acc = 1;
-        for (uint32_t i = 0; i < LONG_GRANULE; ++i) step = step * 4294883355ull % mod;
-        for (uint32_t k = 0; k < LONG_JUMPS; ++k) { rp.mwc_skip[k] = uint64_t(acc); acc = acc * step % mod; }
-    }
+    rp.stage_cap = pl.stage_cap; rp.one = 1;
 }
 
 /* The batch pipeline shared by simulate and replay. */
@@ -345,7 +338,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
             lanes_kernel(replay, quality_mode(ctx->model))<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
         } else if (pl.lanes) {
             CU(cudaMemsetAsync(rp.counters + 4, 0, 8, ctx->compute));       /* the kernel's piece counter */
-            long_kernel(ctx->model.phred_kind)<<<pl.grid, pl.threads, pl.smem, ctx->compute>>>(rp);
+            long_kernel(quality_mode(ctx->model))<<<pl.grid, pl.threads, pl.smem, ctx->compute>>>(rp);
         } else {
             const int grid = int(std::min<uint32_t>(n, uint32_t(pl.grid)));
             direct_kernel(replay)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
@@ -511,11 +504,7 @@ int simmr_error_profile_set(simmr_ctx *ctx, const simmr_eprofile_desc *d) {
     const ProfileModel &m = ctx->model;
     cudaStream_t s = ctx->compute;
     {   /* device layout: quality bytes carry the +33 of util.rs:46-50 already */
-        std::vector<uint32_t> dev = m.phred_entries;
-        auto plus33 = [](uint32_t w, int shift) { return (w & ~(0xffu << shift)) | ((((w >> shift) & 0xffu) + 33u) & 0xffu) << shift; };
-        if (m.phred_kind == PT_T64) for (size_t i = 1; i < dev.size(); i += 2) dev[i] = plus33(plus33(dev[i], 0), 16);
-        if (m.phred_kind == PT_T32) for (uint32_t &w : dev) w = plus33(plus33(w, 0), 8);
-        CU(ctx->d_phred.upload(dev.data(), dev.size(), s));         /* PT_Q32 words hold the printed characters as built */
+        CU(ctx->d_phred.upload(m.phred_entries.data(), m.phred_entries.size(), s));   /* PT_Q32 words hold the printed characters as built */
         CU(ctx->d_qsub.upload(m.qsub_entries.data(), m.qsub_entries.size(), s));
         CU(ctx->d_gap.upload(m.gap_entries.data(), m.gap_entries.size(), s));
         CU(cudaStreamSynchronize(s));

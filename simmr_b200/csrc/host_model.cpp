@@ -175,28 +175,6 @@ double flip_probability(uint8_t q) {
     return (16777215.0 - t) / 16777216.0;
 }
 
-/* joint (quality, mutation) table: outcome = (q-first)<<2 | m, m = 0 none, 1..3 = choose() index + 1 */
-bool phred_from_mass(const std::vector<double> &mass, uint32_t first, ProfileModel &m) {
-    std::vector<double> w(mass.size() * 4);
-    for (size_t i = 0; i < mass.size(); ++i) {
-        const double f = flip_probability(uint8_t(first + i));
-        w[4 * i] = mass[i] * (1.0 - f);
-        w[4 * i + 1] = w[4 * i + 2] = w[4 * i + 3] = mass[i] * f / 3.0;
-    }
-    m.phred_kind = PT_T64; m.npos = 1; m.cb = bits_for(w.size());
-    if (m.cb > 10) return false;
-    std::vector<double> keep; std::vector<uint32_t> other;
-    if (!alias_columns(w, m.cb, keep, other)) return false;
-    m.phred_entries.resize(keep.size() * 2);
-    for (size_t i = 0; i < keep.size(); ++i) {
-        const uint32_t self = ((first + (uint32_t(i) >> 2)) & 0xffu) | ((uint32_t(i) & 3u) << 8);
-        const uint32_t alt = ((first + (other[i] >> 2)) & 0xffu) | ((other[i] & 3u) << 8);
-        m.phred_entries[2 * i] = threshold(keep[i], 32);
-        m.phred_entries[2 * i + 1] = self | (alt << 16);
-    }
-    return true;
-}
-
 /* PT_Q32 word of a column: thr16<<16 | alias<<8 | self.  The sampler keeps `self` iff word < entry, so a column whose
  * threshold rounds to zero names its alias twice (the payload bits must not open a window for `self`). */
 inline uint32_t q32_word(double keep, uint32_t self_val, uint32_t alias_val) {
@@ -213,10 +191,10 @@ bool q32_words(const std::vector<double> &w, uint32_t first, uint32_t cb, std::v
     for (size_t i = 0; i < keep.size(); ++i) out[i] = q32_word(keep[i], first + uint32_t(i), first + other[i]);
     return true;
 }
-/* Short reads of a mutating profile (minimal_short.rs:83-140), factored the other way round: a base is substituted with
+/* Mutating profiles (minimal_short.rs:83-140, minimal_long.rs:78-140, perfect_long.rs:60-119), factored the other way round: a base is substituted with
  * the marginal probability s = sum_q P(q) flip(q); its quality then follows P(q | substituted), every other base's
  * P(q | kept).  Bases are independent, so the substituted ones are found by geometric gaps. */
-bool phred_short_from_mass(const std::vector<double> &mass, uint32_t first, ProfileModel &m) {
+bool phred_from_mass(const std::vector<double> &mass, uint32_t first, ProfileModel &m) {
     const size_t n = mass.size();
     std::vector<double> kept(n), subst(n);
     double s = 0.0;
@@ -264,17 +242,15 @@ bool phred_from_blob(const ProfileBlob &b, ProfileModel &m) {
         }
     }
     if (qmin > qmax) return false;
-    m.phred_kind = PT_T32; m.npos = uint32_t(np); m.cb = bits_for(qmax - qmin + 1);
+    m.phred_kind = PT_Q32; m.npos = uint32_t(np); m.cb = bits_for(qmax - qmin + 1);
     m.phred_entries.clear();
     for (size_t p = 0; p < np; ++p) {
         std::vector<double> w(mass[p].begin() + qmin, mass[p].begin() + qmax + 1), keep;
         std::vector<uint32_t> other;
         if (!alias_columns(w, m.cb, keep, other)) return false;
         for (size_t i = 0; i < keep.size(); ++i)
-            m.phred_entries.push_back(m.is_long ? (threshold(keep[i], 16) << 16) | (((qmin + other[i]) & 0xffu) << 8) | ((qmin + uint32_t(i)) & 0xffu)
-                                                : q32_word(keep[i], qmin + uint32_t(i) + 33u, qmin + other[i] + 33u));
+            m.phred_entries.push_back(q32_word(keep[i], qmin + uint32_t(i) + 33u, qmin + other[i] + 33u));
     }
-    if (!m.is_long) m.phred_kind = PT_Q32;                     /* short reads: column from the low bits, direct compare */
     return true;
 }
 
@@ -357,7 +333,7 @@ int build_profile(const simmr_eprofile_desc *d, ProfileModel &m, std::string &er
         m.min_size = uint16_t(2 * d->read_length + d->insert_size);
         m.mutates = true; m.replay_kind = RP_NORMAL_FLOOR;
         floor_normal(double(m.mean_phred_f), 10.0, 255, first, mass);
-        if (!phred_short_from_mass(mass, first, m)) { err = "phred table"; return SIMMR_E_INVALID; }
+        if (!phred_from_mass(mass, first, m)) { err = "phred table"; return SIMMR_E_INVALID; }
         floor_normal(double(d->read_length), 15.0, 65535, first, mass);
         if (!len_from_mass(mass, first, m.rl)) { err = "read-length table"; return SIMMR_E_INVALID; }
         floor_normal(double(d->insert_size), 75.0, 65535, first, mass);

@@ -21,18 +21,17 @@ struct ContigHdr {     /* per (contig, mate): token span + what is needed for H;
     uint8_t  n_id, n_sp, n_ep, n_rc, n_pair, pad_[3];
 };
 
-/* per-position alias tables for (quality, mutation) */
-enum : uint32_t { PT_CONST = 0,   /* every base has quality const_q, nothing to sample            */
-                  PT_T64 = 1,     /* {thr32, q_self | m_self<<8 | q_alias<<16 | m_alias<<24}       */
-                  PT_T32 = 2,     /* thr16<<16 | q_alias<<8 | q_self  (long reads without mutation; column = top bits of the word) */
-                  PT_Q32 = 3 };   /* short reads: same entry word, column = low cb bits of the word, self iff word < entry;
-                                     substitutions are a separate sparse process (gap / qsub tables) */
+/* per-position alias tables for qualities */
+enum : uint32_t { PT_CONST = 0,   /* every base has quality const_q, nothing to sample */
+                  PT_Q32 = 3 };   /* thr16<<16 | alias<<8 | self per column, characters as printed; the low cb bits of a draw's word
+                                     pick the column, self iff the draw's level < entry; substitutions are a separate sparse
+                                     process (gap / qsub tables).  Kinds 1 and 2 (joint and top-bit tables) are retired. */
 struct PhredTab {
     uint32_t kind, const_q;
     uint32_t cb;           /* log2(columns)                                   */
     uint32_t npos;         /* positions; base i uses min(i, npos-1)           */
     const uint32_t *entries;   /* device or host pointer                      */
-    /* PT_Q32 of a mutating profile: gap[256] = bases until the next substitution (255 = none within 255),
+    /* mutating profile: gap[256] = bases until the next substitution (255 = none within 255),
      * qsub[1 << cb] = quality given a substitution; has_sub == 0 when the profile never substitutes */
     const uint32_t *gap, *qsub;
     uint32_t has_sub, pad_;

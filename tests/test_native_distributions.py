@@ -78,14 +78,7 @@ def test_long_read_lengths_follow_the_reference_gamma():
 def test_perfect_long_phreds():
     """perfect_long.rs:60-78: accuracy ~ N(acc(20), 0.05) capped at 0.9999 -> round(-10 log10(1-a)) in [0, 40]."""
     prof = po.Profile(po.PERFECT_LONG)
-    t = prof.phred_table()
-    cols = 1 << t["cb"]
-    thr, pay = t["entries"][0::2].astype(np.float64), t["entries"][1::2]
-    pq = np.zeros(256)
-    for i in range(cols):
-        keep = thr[i] / 2.0 ** 32 if thr[i] < 0xFFFFFFFF else 1.0
-        pq[pay[i] & 0xFF] += keep / cols
-        pq[(pay[i] >> 16) & 0xFF] += (1.0 - keep) / cols
+    pq, _ = H.short_read_law(prof.phred_table())               # P(q) over all bases: kept and substituted ones
     n = 2_000_000
     q = np.zeros(n, np.uint8)
     po.lib().orc_ref_perfect_long_phred(C.c_uint64(n), C.c_uint64(3), q.ctypes.data_as(po.u8p))
@@ -103,19 +96,12 @@ def test_custom_profile_tables_follow_the_blob(which, blob):
     kind = po.CUSTOM_SHORT if which == "novaseq" else po.CUSTOM_LONG
     prof = po.Profile(kind, blob=blob)
     t = prof.phred_table()
-    assert t["kind"] == (3 if which == "novaseq" else 2)      # short reads: column from the low bits, direct compare
+    assert t["kind"] == 3
     cols, npos = 1 << t["cb"], t["npos"]
     n = 400_000
     for pos in (0, npos // 2, npos - 1):
         e = t["entries"][pos * cols:(pos + 1) * cols]
-        if t["kind"] == 3:
-            pq = H.q32_distribution(e, t["cb"])
-        else:
-            pq = np.zeros(256)
-            keep = (e >> 16).astype(np.float64) / 65536.0
-            keep[(e >> 16) == 0xFFFF] = 1.0
-            np.add.at(pq, e & 0xFF, keep / cols)
-            np.add.at(pq, (e >> 8) & 0xFF, (1.0 - keep) / cols)
+        pq = H.q32_distribution(e, t["cb"])
         q = np.zeros(n, np.uint8)
         assert po.lib().orc_ref_custom_phred(prof._blob.ctypes.data_as(po.u8p), C.c_uint64(len(blob)), pos, C.c_uint64(n), C.c_uint64(5),
                                              q.ctypes.data_as(po.u8p)) == 0
