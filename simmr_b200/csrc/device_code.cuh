@@ -1128,23 +1128,36 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         const uint64_t a = d.a0 + lo;
         const uint32_t *pw = rp.packed + (a >> 4);
         const uint32_t s2 = 2u * (uint32_t(a) & 15u);
-        uint32_t w0 = __ldg(pw), w1 = __ldg(pw + 1);
-        pw += 2;
+        /* Words of the 2-bit copy are fetched a block of four turns ahead of their use (with 32 lanes on 32 different
+         * lines some lane misses L1 nearly every turn); the four turns of a block are unrolled. */
+        uint32_t cur[4], nxt[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) { cur[k] = __ldg(pw + k); nxt[k] = __ldg(pw + 4 + k); }
+        pw += 8;
         const uint32_t quads = (ng + 3u) >> 2, T = __reduce_max_sync(0xffffffffu, quads);
         uint32_t first_s = 0, first_q = 0;
-        for (uint32_t qd = 0; qd < T; ++qd) {             /* sixteen bases = one word of the 2-bit copy */
-            if (qd < quads) {
-                const uint32_t X = __funnelshift_r(w0, w1, s2);
-                w0 = w1; w1 = __ldg(pw++);
-                uint32_t sw[4], qw[4];
+        for (uint32_t q0 = 0; q0 < T; q0 += 4) {
+            uint32_t far[4];
 #pragma unroll
-                for (uint32_t h = 0; h < 4; ++h) {
-                    qw[h] = QM == QM_CONST ? qconst : quals4<QM, false>(rp, qtab_s, mask, qc, lo + 16u * qd + 4u * h);
-                    sw[h] = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
+            for (uint32_t k = 0; k < 4; ++k) far[k] = __ldg(pw + k);
+            pw += 4;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {            /* sixteen bases = one word of the 2-bit copy */
+                const uint32_t qd = q0 + k;
+                if (qd < quads) {
+                    const uint32_t X = __funnelshift_r(cur[k], k < 3 ? cur[(k + 1) & 3] : nxt[0], s2);
+                    uint32_t sw[4], qw[4];
+#pragma unroll
+                    for (uint32_t h = 0; h < 4; ++h) {
+                        qw[h] = QM == QM_CONST ? qconst : quals4<QM, false>(rp, qtab_s, mask, qc, lo + 16u * qd + 4u * h);
+                        sw[h] = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
+                    }
+                    if (qd == 0) { first_s = sw[0]; first_q = qw[0]; }
+                    rl_quad(ls, 4u * qd, sw[0], sw[1], sw[2], sw[3]); rl_quad(lq, 4u * qd, qw[0], qw[1], qw[2], qw[3]);
                 }
-                if (qd == 0) { first_s = sw[0]; first_q = qw[0]; }
-                rl_quad(ls, 4u * qd, sw[0], sw[1], sw[2], sw[3]); rl_quad(lq, 4u * qd, qw[0], qw[1], qw[2], qw[3]);
             }
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) { cur[k] = nxt[k]; nxt[k] = far[k]; }
         }
         if (ng) {
             const uint32_t kl = 4u * (quads - 1u);
