@@ -516,48 +516,19 @@ __device__ __forceinline__ void bs_decimal(ByteStream &b, uint32_t dec2_s, uint3
  * literal, ..., field, literal with nf <= HDR_MAX_FIELDS decimal fields whose kinds (4 bits each) are the same
  * for every contig; tk = this (contig, mate)'s token list. */
 constexpr uint32_t HDR_MAX_FIELDS = 4;
-/* up to four whole words of a literal from one 16-byte fetch: `whole` = whole words of the literal not yet written */
-__device__ __forceinline__ void bs_words16(ByteStream &b, const uint4 v, int32_t whole) {
-    if (whole > 0) bs_word(b, v.x);
-    if (whole > 1) bs_word(b, v.y);
-    if (whole > 2) bs_word(b, v.z);
-    if (whole > 3) bs_word(b, v.w);
-}
 __device__ __forceinline__ void header_tokens(ByteStream &b, const RunParams &rp, uint32_t dec2_s, const uint2 *tk, uint32_t kinds,
                                               uint32_t nf, uint32_t id, uint32_t sp, uint32_t ep) {
-    /* three rounds of loads instead of one per literal word (there is next to no L1 beside the stages): the token
-     * descriptors {off, len | type << 16}; then every literal's first 16 bytes and its last, partial word; then what is
-     * left of a literal longer than 16 bytes, 48 bytes at a time.  Literals start on 16-byte boundaries of the pool. */
-    uint2 lit[HDR_MAX_FIELDS + 1];
+    uint2 lit[HDR_MAX_FIELDS + 1];                                               /* {off, len | type << 16}, fetched together */
 #pragma unroll
     for (uint32_t i = 0; i <= HDR_MAX_FIELDS; ++i) lit[i] = i <= nf ? __ldg(tk + 2 * i) : make_uint2(0u, 0u);
-    uint4 first[HDR_MAX_FIELDS + 1]; uint32_t tail[HDR_MAX_FIELDS + 1];
-#pragma unroll
-    for (uint32_t i = 0; i <= HDR_MAX_FIELDS; ++i) {
-        const uint32_t len = lit[i].y & 0xffffu;
-        first[i] = make_uint4(0u, 0u, 0u, 0u); tail[i] = 0u;
-        if (i <= nf && len) first[i] = __ldg(reinterpret_cast<const uint4 *>(rp.pool + lit[i].x));
-        if (i <= nf && len > 16u && (len & 3u)) tail[i] = __ldg(reinterpret_cast<const uint32_t *>(rp.pool + lit[i].x + (len & ~3u)));
-    }
 #pragma unroll
     for (uint32_t i = 0; i <= HDR_MAX_FIELDS; ++i) {
         if (i > nf) break;                                                       /* same for every thread */
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(rp.pool + lit[i].x);
         const uint32_t len = lit[i].y & 0xffffu, nw = len >> 2;
-        bs_words16(b, first[i], int32_t(nw));
-        if (len > 16u) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(rp.pool + lit[i].x);
-            for (uint32_t q = 1; 4u * q < nw; q += 3) {                          /* 16-byte pieces q, q+1, q+2 */
-                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                const uint4 v0 = __ldg(src + q), v1 = 4u * (q + 1u) < nw ? __ldg(src + q + 1) : z, v2 = 4u * (q + 2u) < nw ? __ldg(src + q + 2) : z;
-                bs_words16(b, v0, int32_t(nw) - int32_t(4u * q));
-                bs_words16(b, v1, int32_t(nw) - int32_t(4u * q + 4u));
-                bs_words16(b, v2, int32_t(nw) - int32_t(4u * q + 8u));
-            }
-            if (len & 3u) bs_put(b, tail[i], len & 3u);
-        } else if (len & 3u) {                                                   /* the partial word is one of the first four */
-            const uint32_t w = nw == 0 ? first[i].x : nw == 1 ? first[i].y : nw == 2 ? first[i].z : first[i].w;
-            bs_put(b, w, len & 3u);
-        }
+#pragma unroll 4
+        for (uint32_t j = 0; j < nw; ++j) bs_word(b, __ldg(src + j));
+        if (len & 3u) bs_put(b, __ldg(src + nw), len & 3u);
         if (i < nf) {
             const uint32_t kind = (kinds >> (4u * i)) & 15u;
             bs_decimal(b, dec2_s, kind == TOK_READ_ID ? id : kind == TOK_START ? sp : ep);

@@ -180,7 +180,7 @@ int ensure_headers(simmr_ctx *ctx, const char *fmt) {
     if (rc) return fail(ctx, rc, err);
     CU(ctx->d_chdr.upload(ctx->plan.contigs.data(), ctx->plan.contigs.size(), ctx->compute));
     CU(ctx->d_toks.upload(ctx->plan.toks.data(), ctx->plan.toks.size(), ctx->compute));
-    ctx->plan.pool.resize((ctx->plan.pool.size() + 79) & ~size_t(15), '\0');   /* a literal's last 16-byte pieces are fetched whole */
+    ctx->plan.pool.resize((ctx->plan.pool.size() + 7) & ~size_t(3), '\0');
     CU(ctx->d_pool.upload(ctx->plan.pool.data(), ctx->plan.pool.size(), ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
     {   /* the same decimal fields in every contig (token lists are canonical: literal, field, ..., literal) let the

@@ -689,7 +689,7 @@ int compile_headers(const simmr_genome_set &g, const char *fmt, HeaderPlan &plan
                  * even place, so the kernel needs no per-token dispatch */
                 auto flush = [&]() {
                     if (run.size() > 65532) return false;
-                    plan.pool.resize((plan.pool.size() + 15) & ~size_t(15), '\0');   /* the kernel fetches literals 16 bytes at a time */
+                    plan.pool.resize((plan.pool.size() + 3) & ~size_t(3), '\0');   /* the kernel fetches literals by words */
                     plan.toks.push_back(HdrTok{uint32_t(plan.pool.size()), uint16_t(run.size()), TOK_LIT, 0});
                     plan.pool.append(run);
                     lit_total += run.size(); run.clear();
