@@ -856,12 +856,10 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
             if (slot < tn) d = rp.desc[t0 + slot];
         }
     };
-    uint64_t off_next; UnitDesc d_next;
-    fetch_tile(blockIdx.x * nwarps + warp, off_next, d_next);
     for (uint32_t tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) {
         const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
-        const uint64_t off_tile = off_next; const UnitDesc d_tile = d_next;
-        fetch_tile(tile + gridDim.x * nwarps, off_next, d_next);
+        uint64_t off_tile; UnitDesc d_tile;
+        fetch_tile(tile, off_tile, d_tile);
         for (uint32_t s0 = 0; s0 < tn;) {
             /* sub-tile = longest run of units from s0 that fits the stage */
             const uint32_t u0 = t0 + s0, left = tn - s0;
@@ -905,13 +903,6 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
                     if (REPLAY) emit_body_replay<false>(rp, rd, stage + rec + H, mate, a, L, rd.base_off[unit] + (mate ? d.rl : 0), 0, 1);
                     else emit_body_pieces<false>(rp, stage + rec + H, unit, mate, a, L, 0, 1);
                 }
-            }
-            if (s0 == 0) {   /* the next tile's windows of the 2-bit genome copy: towards L2 while this tile's headers are written */
-                const uint64_t an = mate ? d_next.a1 : d_next.a0;
-                const uint32_t Ln = mate ? d_next.L1 : d_next.L0;
-                const uint8_t *pn = reinterpret_cast<const uint8_t *>(rp.packed) + (an >> 2);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pn));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + (Ln >> 2)));
             }
             __syncwarp();
 
