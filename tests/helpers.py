@@ -221,6 +221,8 @@ def short_read_law(table):
     gap = q32_distribution(table["entries"][cols:cols + 256], 8, chars=False)
     sub = q32_distribution(table["entries"][cols + 256:], cb)
     # distance between substituted bases: gap + 1, where 255 means "255 bases kept, draw again"
+    if gap[255] >= 1.0:                      # the quantised gap row never ends a gap: no substitutions at all
+        return kept, 0.0
     mean_d = (float((gap[:255] * (np.arange(255) + 1)).sum()) + 255.0 * gap[255]) / (1.0 - gap[255])
     rate = 1.0 / mean_d
     return (1.0 - rate) * kept + rate * sub, rate

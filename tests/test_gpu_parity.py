@@ -57,6 +57,45 @@ def test_minimal_short_other_params(engine):
     check_native(engine, gs, S.MinimalShortErrorProfile(250, 50, 40), [500, 500, 500], 8)
 
 
+@pytest.mark.parametrize("mean_q", [2, 55, 90])
+def test_quality_table_shapes(engine, mean_q):
+    """Mean qualities that change the sampling tables' shape: mean 2 puts a third of the bases on substitution events
+    (dense gap chain, many events per record); mean 55 and 90 need 256 columns (the general column path of the lane
+    kernel instead of the cb == 7 one) and make substitutions rare (long "none within 255" chains)."""
+    gs = H.synth_genomes(3, (1, 3), (3000, 9000), seed=15)
+    prof = S.MinimalShortErrorProfile(150, 150, mean_q)
+    t = prof.phred_table()
+    assert t["kind"] == 3 and t["cb"] == (7 if mean_q == 2 else 8)
+    data = check_native(engine, gs, prof, [1500, 900, 601], 21)
+    _, rate = H.short_read_law(t)
+    # substitution rate of the run against the tables' law (every record against its source window is checked in
+    # test_native_stream_statistics for the oracle; here the two implementations already agree byte for byte)
+    assert (rate > 0.25) if mean_q == 2 else (rate < 1e-3)
+    gl = H.synth_genomes(2, (1, 1), (30000, 70000), seed=16)
+    check_native(engine, gl, S.MinimalLongErrorProfile(mean_q), [12, 9], 22)
+
+
+def test_single_stream_switch_gives_the_same_bytes(engine, monkeypatch):
+    """SIMMR_PREP_SERIAL puts batch preparation and formatting on one stream (bench.py uses it to time the format kernel
+    without co-runners); the two-stream default must produce the same bytes over many small batches."""
+    gs = H.synth_genomes(4, (1, 3), (3000, 8000), seed=19)
+    engine.load_genomes(gs); engine.set_error_profile(S.MinimalShortErrorProfile())
+    reads = [1500, 700, 0, 2200]
+    two = engine.simulate_bytes(reads, 5, batch_units=101)
+    monkeypatch.setenv("SIMMR_PREP_SERIAL", "1")
+    one = engine.simulate_bytes(reads, 5, batch_units=101)
+    assert one == two == po.simulate(po.Genomes.from_set(gs), H.oracle_profile(S.MinimalShortErrorProfile()), reads, 5)
+
+
+def test_long_read_piece_boundaries(engine):
+    """Long reads are cut into 32 pieces of 16 * ceil(L / 512) bases: compat mode (simulate.rs:484-489)
+    produces short and empty long reads, so lanes with empty, partial and full pieces all occur."""
+    gs = H.synth_genomes(2, (1, 2), (21000, 40000), seed=23)
+    data = check_native(engine, gs, S.MinimalLongErrorProfile(25, compat_start=True), [150, 90], 31)
+    lens = sorted(len(s) for _, s, _ in H.parse_fastq(data))
+    assert lens[0] < 1024 and lens[-1] > 16000        # a 518-base read: 17 pieces of 32 bases, 15 lanes without a piece
+
+
 def test_batching_and_sharding_do_not_change_bytes(engine):
     gs = H.synth_genomes(4, (1, 3), (3000, 8000), seed=9)
     prof = S.MinimalShortErrorProfile()
