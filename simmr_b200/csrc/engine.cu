@@ -144,7 +144,7 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
         /* A warp's stage holds the typical bytes of its WARP_UNITS units (one record per lane) plus a margin — a group
          * that draws longer reads is cut into sub-tiles by the kernel — and at least the largest single unit.  One CTA
          * per SM with as many warps as fit next to the tables. */
-        const uint64_t typical = 2ull * (ctx->plan.hdr_cap + 2ull * m.nominal_read_len + 5);
+        const uint64_t typical = 2ull * (ctx->plan.hdr_typ + 2ull * m.nominal_read_len + 5);
         const uint64_t cap = (std::max<uint64_t>(unit_bytes + 32, WARP_UNITS * typical * 21 / 20 + 64) + 15) & ~15ull;
         uint32_t warps = FORMAT_THREADS / 32;
         if (const char *e = getenv("SIMMR_WARPS")) warps = uint32_t(std::max(1, std::min(FORMAT_THREADS / 32, atoi(e))));

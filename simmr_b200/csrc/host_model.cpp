@@ -712,6 +712,9 @@ int compile_headers(const simmr_genome_set &g, const char *fmt, HeaderPlan &plan
                 plan.contigs.push_back(ch);
                 const uint32_t cap = uint32_t(lit_total) + 10u * ch.n_id + 20u * ch.n_sp + 20u * ch.n_ep;
                 plan.hdr_cap = std::max(plan.hdr_cap, cap);
+                uint32_t pos_digits = 1;
+                for (uint64_t v = g.contig_size[c]; v >= 10; v /= 10) ++pos_digits;
+                plan.hdr_typ = std::max(plan.hdr_typ, uint32_t(lit_total) + 10u * ch.n_id + pos_digits * (ch.n_sp + ch.n_ep));
             }
         }
     }

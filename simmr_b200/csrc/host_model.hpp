@@ -94,6 +94,7 @@ struct HeaderPlan {
     std::vector<ContigHdr> contigs;
     std::string pool;
     uint32_t hdr_cap = 0;       /* upper bound on any header's bytes */
+    uint32_t hdr_typ = 0;       /* a header's bytes when positions are printed with the digits of its contig's size (sizes a warp's stage) */
 };
 extern const char *const DEFAULT_HEADER_FORMAT;   /* cli.rs:196 */
 int compile_headers(const simmr_genome_set &g, const char *fmt, HeaderPlan &plan, std::string &err);
