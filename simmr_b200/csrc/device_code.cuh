@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "../../include/simmr_b200.h"
 #include "simmr_types.h"
 
@@ -706,7 +707,7 @@ __device__ __forceinline__ uint32_t quals4(const RunParams &rp, uint32_t qtab_s,
 }
 
 /* Sequence and quality lines of one record by one lane, all 32 lanes of the warp converged (a lane without a record for
- * this path runs with on = false and stores nothing); the warp loops T16 times, 16 bases of every record per turn.
+ * this path runs with on = false and stores nothing); the warp takes T4 groups of 4 bases of every record, 16 bases per turn.
  * A record body is "\nSEQ\n+\nQUAL\n"; body_s = shared-space address of the '\n' that ends the header.  Both lines are
  * written front to back as 4-byte aligned words: a line's group of 4 characters is funnel-shifted against the previous
  * group onto the word grid of the stage.  The first and last word of a line also cover up to 3 bytes outside it; those
@@ -717,7 +718,7 @@ __device__ __forceinline__ uint32_t quals4(const RunParams &rp, uint32_t qtab_s,
  * are applied afterwards (substitutions_lane), so the two lines are independent here. */
 template <int QM, bool CB7>
 __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, uint32_t lut_s, bool on, bool rc, uint32_t body_s,
-                                          Mwc1 &rng, uint64_t a, uint32_t L, uint32_t T16) {
+                                          Mwc1 &rng, uint64_t a, uint32_t L, uint32_t T4) {
     if (!on) { L = 0; a = 0; }
     const uint32_t Ds = body_s + 1u, Dq = body_s + L + 4u;
     const uint32_t os = Ds & 3u, oq = Dq & 3u, sh_s = 8u * os, sh_q = 8u * oq;
@@ -734,33 +735,43 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
     const int32_t dw = rc ? -1 : 1;
     const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u, mask = rp.phred_mult - 1u;
     uint32_t prev_s = 0, prev_q = 0;
-    for (uint32_t it = 0; it < T16; ++it) {
+    /* one turn = G groups of 4 bases of every record: G = 4 but for the warp's last turn, which is as long as its longest record needs */
+    auto turn = [&](auto gc, uint32_t it) {
+        constexpr uint32_t G = decltype(gc)::value;
         const uint32_t X = __byte_perm(__funnelshift_r(w_lo, w_hi, s2), 0u, rev);
-        {   /* mate 1: (lo, hi) <- (hi, new); mate 2: (lo, hi) <- (new, lo).  The padding around `packed` covers the last fetch. */
+        if (G == 4) {   /* mate 1: (lo, hi) <- (hi, new); mate 2: (lo, hi) <- (new, lo).  The padding around `packed` covers the last fetch. */
             const uint32_t nw = __ldg(pw);
             pw += dw;
             const uint32_t keep = rc ? w_lo : w_hi;
             w_lo = rc ? nw : keep; w_hi = rc ? keep : nw;
         }
-        uint32_t cs[4], cq[4];                         /* the turn's four words of each line, on the stage's word grid */
+        uint32_t cs[G], cq[G];                         /* the turn's words of each line, on the stage's word grid */
 #pragma unroll
-        for (uint32_t h = 0; h < 4; ++h) {
+        for (uint32_t h = 0; h < G; ++h) {
             const uint32_t qw = QM == QM_CONST ? qconst : quals4<QM, CB7>(rp, qtab_s, mask, rng, 16u * it + 4u * h);
             const uint32_t sw = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
             cs[h] = __funnelshift_l(prev_s, sw, sh_s); cq[h] = QM == QM_CONST ? qconst : __funnelshift_l(prev_q, qw, sh_q);
             prev_s = sw; prev_q = qw;
         }
-        if (__all_sync(0xffffffffu, ns >= 4 && nq >= 4)) {      /* every lane is inside both lines: no per-word tests */
+        if (G == 4 && __all_sync(0xffffffffu, ns >= 4 && nq >= 4)) {      /* every lane is inside both lines: no per-word tests */
 #pragma unroll
-            for (uint32_t h = 0; h < 4; ++h) { sts32(ps + 4u * h, cs[h]); sts32(pq + 4u * h, cq[h]); }
+            for (uint32_t h = 0; h < G; ++h) { sts32(ps + 4u * h, cs[h]); sts32(pq + 4u * h, cq[h]); }
         } else {
 #pragma unroll
-            for (uint32_t h = 0; h < 4; ++h) {
+            for (uint32_t h = 0; h < G; ++h) {
                 if (ns > int32_t(h)) sts32(ps + 4u * h, cs[h]);
                 if (nq > int32_t(h)) sts32(pq + 4u * h, cq[h]);
             }
         }
-        ps += 16u; pq += 16u; ns -= 4; nq -= 4;
+        ps += 4u * G; pq += 4u * G; ns -= int32_t(G); nq -= int32_t(G);
+    };
+    const uint32_t full = (T4 - 1u) >> 2;              /* T4 >= 1 */
+    for (uint32_t it = 0; it < full; ++it) turn(std::integral_constant<uint32_t, 4>{}, it);
+    switch (T4 - 4u * full) {
+    case 1: turn(std::integral_constant<uint32_t, 1>{}, full); break;
+    case 2: turn(std::integral_constant<uint32_t, 2>{}, full); break;
+    case 3: turn(std::integral_constant<uint32_t, 3>{}, full); break;
+    default: turn(std::integral_constant<uint32_t, 4>{}, full); break;
     }
 }
 
@@ -890,13 +901,13 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
             {
                 const uint32_t body_s = stage_s + rec + H;
                 const uint32_t slots = ((L + 3u + 3u) >> 2);                          /* word slots of a line, at most */
-                const uint32_t T16 = __reduce_max_sync(0xffffffffu, fast ? (slots + 3u) >> 2 : 0u);
-                if (T16) {
+                const uint32_t T4 = __reduce_max_sync(0xffffffffu, fast ? slots : 0u);
+                if (T4) {
                     Mwc1 qc{}, ec{};
                     if (QM != QM_CONST) mwc1_seed(rp, qc, ec, 0u, 1u + mate, uint32_t(unit), uint32_t(unit >> 32));
                     const uint32_t lut_s = base_s + (mate ? SM_LUT_RC : SM_LUT_FWD);
-                    if (QM == QM_LANE && rp.phred.cb == 7u) body_lane<QM, true>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T16);
-                    else body_lane<QM, false>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T16);
+                    if (QM == QM_LANE && rp.phred.cb == 7u) body_lane<QM, true>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4);
+                    else body_lane<QM, false>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4);
                     if (QM != QM_CONST && rp.phred.has_sub) substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
                 }
                 if (have && !fast) {
