@@ -40,6 +40,7 @@ struct ReplayDev {                 /* device copies of simmr_draws + replay LUTs
 
 /* long reads are cut into LONG_PIECES pieces of a multiple of 16 bases, each with its own chains: the 32 lanes' work in k_format_long */
 constexpr uint32_t LONG_PIECES = 32;
+constexpr uint32_t LONG_RING = 16, LONG_AHEAD = 12;   /* k_format_long: words of the 2-bit copy per lane in shared memory, and how far ahead they are fetched */
 struct UnitDesc;
 struct RunParams {
     /* genomes (device resident) */
@@ -72,7 +73,8 @@ constexpr int SIZES_THREADS = 256;
 constexpr int FORMAT_THREADS = 512;   /* most threads of a format CTA (each warp has a private stage) -> register cap of 128 */
 constexpr int FORMAT_MIN_CTAS = 1;
 constexpr int DIRECT_THREADS = 256;
-constexpr uint32_t PACK_PAD_WORDS = 4104; /* readable words before and after `packed`: a lane keeps fetching (and discarding)
+__host__ __device__ constexpr uint32_t long_extra_smem() { return uint32_t(DIRECT_THREADS / 32) * LONG_RING * 128u; }   /* k_format_long: a genome-word ring per warp */
+constexpr uint32_t PACK_PAD_WORDS = 4352; /* readable words before and after `packed`: a lane keeps fetching (and discarding)
                                              for as long as the longest record of its warp lasts, at most 65535 / 16 words */
 /* shared-memory layout of a format CTA (byte offsets from the 1024-aligned base): letter tables, two-digit table, gap and
  * quality-given-substitution tables, quality table (per-lane copies or one copy per position), then the warps' stages */
@@ -1101,37 +1103,39 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         const uint64_t a = d.a0 + lo;
         const uint32_t *pw = rp.packed + (a >> 4);
         const uint32_t s2 = 2u * (uint32_t(a) & 15u);
-        /* Words of the 2-bit copy are fetched a block of four turns ahead of their use (with 32 lanes on 32 different
-         * lines some lane misses L1 nearly every turn); the four turns of a block are unrolled. */
-        uint32_t cur[4], nxt[4];
+        /* Words of the 2-bit copy reach the lane through a ring in shared memory filled by asynchronous copies LONG_AHEAD
+         * turns ahead of their use (with 32 lanes on 32 different lines some lane misses L1 nearly every turn, and a
+         * register loaded that far ahead cannot be kept out of the way of the compiler's moves).  Word k of lane l sits at
+         * ring word (k % LONG_RING) * 32 + l: copies and reads stay in the lane's bank.  One copy group per word. */
+        const uint32_t ring_s = base_s + SM_QTAB + qtab_bytes(QM, rp.phred.cb, rp.phred.npos) + (threadIdx.x >> 5) * (LONG_RING * 128u) + 4u * lane;
 #pragma unroll
-        for (uint32_t k = 0; k < 4; ++k) { cur[k] = __ldg(pw + k); nxt[k] = __ldg(pw + 4 + k); }
-        pw += 8;
+        for (uint32_t k = 0; k <= LONG_AHEAD; ++k) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + (k % LONG_RING) * 128u), "l"(pw + k) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        asm volatile("cp.async.wait_group %0;" ::"n"(LONG_AHEAD) : "memory");           /* word 0 has landed */
+        uint32_t w_lo = lds32m(ring_s);
         const uint32_t quads = (ng + 3u) >> 2, T = __reduce_max_sync(0xffffffffu, quads);
         uint32_t first_s = 0, first_q = 0;
-        for (uint32_t q0 = 0; q0 < T; q0 += 4) {
-            uint32_t far[4];
+        for (uint32_t qd = 0; qd < T; ++qd) {             /* sixteen bases = one word of the 2-bit copy */
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + ((qd + LONG_AHEAD + 1u) % LONG_RING) * 128u), "l"(pw + qd + LONG_AHEAD + 1u) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(LONG_AHEAD) : "memory");       /* words up to qd + 1 have landed */
+            const uint32_t w_hi = lds32m(ring_s + ((qd + 1u) % LONG_RING) * 128u);
+            if (qd < quads) {
+                const uint32_t X = __funnelshift_r(w_lo, w_hi, s2);
+                uint32_t sw[4], qw[4];
 #pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) far[k] = __ldg(pw + k);
-            pw += 4;
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) {            /* sixteen bases = one word of the 2-bit copy */
-                const uint32_t qd = q0 + k;
-                if (qd < quads) {
-                    const uint32_t X = __funnelshift_r(cur[k], k < 3 ? cur[(k + 1) & 3] : nxt[0], s2);
-                    uint32_t sw[4], qw[4];
-#pragma unroll
-                    for (uint32_t h = 0; h < 4; ++h) {
-                        qw[h] = QM == QM_CONST ? qconst : quals4<QM, false>(rp, qtab_s, mask, qc, lo + 16u * qd + 4u * h);
-                        sw[h] = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
-                    }
-                    if (qd == 0) { first_s = sw[0]; first_q = qw[0]; }
-                    rl_quad(ls, 4u * qd, sw[0], sw[1], sw[2], sw[3]); rl_quad(lq, 4u * qd, qw[0], qw[1], qw[2], qw[3]);
+                for (uint32_t h = 0; h < 4; ++h) {
+                    qw[h] = QM == QM_CONST ? qconst : quals4<QM, false>(rp, qtab_s, mask, qc, lo + 16u * qd + 4u * h);
+                    sw[h] = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
                 }
+                if (qd == 0) { first_s = sw[0]; first_q = qw[0]; }
+                rl_quad(ls, 4u * qd, sw[0], sw[1], sw[2], sw[3]); rl_quad(lq, 4u * qd, qw[0], qw[1], qw[2], qw[3]);
             }
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) { cur[k] = nxt[k]; nxt[k] = far[k]; }
+            w_lo = w_hi;
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      /* nothing of this read's copies may land in the next read's ring */
         if (ng) {
             const uint32_t kl = 4u * (quads - 1u);
             rl_close(ls, kl, ng); rl_edges(ls, kl, ng, first_s); rl_close(lq, kl, ng); rl_edges(lq, kl, ng, first_q);

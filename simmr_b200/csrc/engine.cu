@@ -155,7 +155,7 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
     int occ = 0;
     if (!pl.tiles && !replay && m.is_long && !getenv("SIMMR_NO_LONG_KERNEL")) {
         pl.lanes = true; pl.threads = DIRECT_THREADS;
-        pl.smem = SM_QTAB + qtab_bytes(quality_mode(m), m.cb, m.npos);
+        pl.smem = SM_QTAB + qtab_bytes(quality_mode(m), m.cb, m.npos) + long_extra_smem();   /* tables, a genome-word ring per warp, an event list per lane */
         LongKernel k = long_kernel(quality_mode(m));
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
