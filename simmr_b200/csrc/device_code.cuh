@@ -92,7 +92,6 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile(
 __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 /* loads from the read-only tables in shared memory: not volatile, the compiler may move them */
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ uint2 lds64(uint32_t addr) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr)); return v; }
 
 /* ---------------------------------------------------------------------- */
 /* Philox4x32-10                                                            */
@@ -114,15 +113,7 @@ __device__ __forceinline__ Philox4 draw(const RunParams &rp, uint64_t unit, uint
 __device__ __forceinline__ uint64_t pair64(uint32_t lo, uint32_t hi) { return uint64_t(lo) | (uint64_t(hi) << 32); }
 
 /* Per-base draws: MWC64X generators (D. B. Thomas: x' = lo(A*x + c), c' = hi(A*x + c), A = 4294883355)
- * seeded from Philox words. */
-__device__ __forceinline__ uint32_t mwc_next(uint32_t &x, uint32_t &c) {
-    const uint32_t r = x ^ c;
-    const uint64_t t = uint64_t(x) * 4294883355u + c;
-    x = uint32_t(t); c = uint32_t(t >> 32);
-    return r;
-}
-
-/* Philox block (piece, stream, unit) seeds the two chains of a piece of a read — words 0,1 the quality chain (one step per
+ * seeded from Philox words.  Philox block (piece, stream, unit) seeds the two chains of a piece of a read — words 0,1 the quality chain (one step per
  * two bases), words 2,3 the substitution-event chain.  Short reads are one piece (block 0), long reads LONG_PIECES. */
 struct Mwc1 { uint32_t x, c; };
 /* one draw = (word, level): word = x ^ c picks a table column with its low bits, level = x is compared with the entry;
