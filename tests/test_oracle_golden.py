@@ -267,6 +267,16 @@ def test_native_stream_statistics():
     qf = q.astype(np.float64) - q.mean()
     assert abs(float((qf[:-1] * qf[1:]).mean() / qf.var())) < 5 / np.sqrt(n)         # lag-1: next step of the chain
     assert abs(float((qf[:-4] * qf[4:]).mean() / qf.var())) < 5 / np.sqrt(n)         # lag-4
+    # the two bases served by one chain step (columns from adjacent bit fields of the word, levels x and c) are
+    # independent: joint histogram of (q[2k], q[2k+1]) in quartile bins against the product of its margins
+    L0 = np.array([len(r[2]) for r in recs])
+    starts = np.concatenate([[0], np.cumsum(L0)[:-1]])
+    even = np.concatenate([np.arange(s0, s0 + (l0 & ~1), 2) for s0, l0 in zip(starts[:4000], L0[:4000])])
+    edges = np.quantile(q, [0.25, 0.5, 0.75])
+    a, b = np.digitize(q[even], edges), np.digitize(q[even + 1], edges)
+    joint = np.bincount(4 * a + b, minlength=16).reshape(4, 4).astype(np.float64)
+    expect = joint.sum(1)[:, None] * joint.sum(0)[None, :] / joint.sum()
+    assert float(((joint - expect) ** 2 / expect).sum()) < 9 + 6 * np.sqrt(18), joint       # chi-square, 9 degrees of freedom
     m1 = np.frombuffer(b"".join(r[2][:100] for r in recs[0::2]), np.uint8).astype(np.float64)
     m2 = np.frombuffer(b"".join(r[2][:100] for r in recs[1::2]), np.uint8).astype(np.float64)
     assert abs(float(np.corrcoef(m1, m2)[0, 1])) < 5 / np.sqrt(len(m1))
