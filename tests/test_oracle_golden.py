@@ -280,3 +280,39 @@ def test_native_stream_statistics():
     m1 = np.frombuffer(b"".join(r[2][:100] for r in recs[0::2]), np.uint8).astype(np.float64)
     m2 = np.frombuffer(b"".join(r[2][:100] for r in recs[1::2]), np.uint8).astype(np.float64)
     assert abs(float(np.corrcoef(m1, m2)[0, 1])) < 5 / np.sqrt(len(m1))
+
+
+def test_native_stream_statistics_long_reads():
+    """Long reads are cut into 32 pieces with their own chains: qualities against the tables' law,
+    substitution rate, and no seam between pieces (substitutions as frequent in the 64 bases around piece boundaries
+    as elsewhere)."""
+    import simmr_b200 as S
+    rng = np.random.default_rng(12)
+    seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 300000)]
+    gs = S.GenomeSet.from_contigs([("u", [(b"c", seq)])])
+    og = po.Genomes.from_set(gs)
+    prof = po.Profile(po.MINIMAL_LONG, mean_phred=20)
+    pq, pm = H.short_read_law(prof.phred_table())
+    recs = H.parse_fastq(po.simulate(og, prof, [300], 77))
+    q = np.frombuffer(b"".join(r[2] for r in recs), np.uint8).astype(np.int64) - 33
+    n = len(q)
+    assert n > 3_000_000
+    emp = np.bincount(q, minlength=256) / n
+    sel = pq * n >= 20
+    chi2 = float((((emp - pq) ** 2)[sel] / pq[sel]).sum() * n)
+    assert chi2 < sel.sum() + 6 * np.sqrt(2 * sel.sum()), chi2
+    src = seq.tobytes()
+    subs = total = near = near_total = 0
+    for hdr, s, _ in recs:
+        f = dict(kv.split(b"=") for kv in hdr.split(b"metadata:")[1].split(b"|"))
+        sp, ep = int(f[b"sp"]), int(f[b"ep"])
+        a, b = np.frombuffer(s, np.uint8), np.frombuffer(src[sp:ep], np.uint8)
+        diff = a != b
+        subs += int(diff.sum()); total += len(a)
+        piece = 16 * ((len(a) + 511) // 512)
+        if piece >= 128:
+            pos = np.arange(len(a)) % piece
+            edge = (pos < 32) | (pos >= piece - 32)
+            near += int(diff[edge].sum()); near_total += int(edge.sum())
+    assert abs(subs / total - pm) < 6 * np.sqrt(pm / total), (subs / total, pm)
+    assert abs(near / near_total - pm) < 6 * np.sqrt(pm / near_total), (near / near_total, pm)
