@@ -73,7 +73,9 @@ constexpr int SIZES_THREADS = 256;
 constexpr int FORMAT_THREADS = 512;   /* most threads of a format CTA (each warp has a private stage) -> register cap of 128 */
 constexpr int FORMAT_MIN_CTAS = 1;
 constexpr int DIRECT_THREADS = 256;
-__host__ __device__ constexpr uint32_t long_extra_smem() { return uint32_t(DIRECT_THREADS / 32) * LONG_RING * 128u; }   /* k_format_long: a genome-word ring per warp */
+__host__ __device__ constexpr uint32_t long_extra_smem() {   /* k_format_long: per warp a genome-word ring and two tiles of 8 turns x 32 lines */
+    return uint32_t(DIRECT_THREADS / 32) * (LONG_RING * 128u + 8192u);
+}
 constexpr uint32_t PACK_PAD_WORDS = 4352; /* readable words before and after `packed`: a lane keeps fetching (and discarding)
                                              for as long as the longest record of its warp lasts, at most 65535 / 16 words */
 /* shared-memory layout of a format CTA (byte offsets from the 1024-aligned base): letter tables, two-digit table, gap and
@@ -1014,6 +1016,46 @@ __device__ __forceinline__ void rl_quad(RunLine &r, uint32_t k, uint32_t w0, uin
     }
     r.c0 = a1; r.c1 = a2; r.c2 = a3;
 }
+/* Whole 16-byte lines of eight consecutive turns are collected in shared memory and written out by the warp together, a
+ * lane's eight lines (128 contiguous bytes) by eight neighbouring lanes: 32 lanes on 32 different lines per store
+ * instruction become four full 128-byte rows.  Tile layout: line of turn slot s, lane l at s * 512 + ((l + s) & 31) * 16
+ * (both the lane-wise writes and the row-wise reads are free of bank conflicts). */
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory"); return v; }
+/* rl_quad with the whole-line store going to the tile (slot = turn & 7; `valid` collects the slots that hold a line) */
+__device__ __forceinline__ void rl_quad_staged(RunLine &r, uint32_t k, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+                                               uint32_t tile_s, uint32_t lane, uint32_t slot, uint32_t &valid) {
+    const uint32_t a0 = __funnelshift_l(r.g[4], w0, r.sh), a1 = __funnelshift_l(w0, w1, r.sh), a2 = __funnelshift_l(w1, w2, r.sh), a3 = __funnelshift_l(w2, w3, r.sh);
+    r.g[0] = r.g[4]; r.g[1] = w0; r.g[2] = w1; r.g[3] = w2; r.g[4] = w3;
+    const bool s1 = r.q & 1u, s2 = r.q & 2u;
+    const uint32_t v0 = s1 ? r.c1 : r.c2, v1 = s1 ? r.c2 : a0, v2 = s1 ? a0 : a1, v3 = s1 ? a1 : a2, v4 = s1 ? a2 : a3;
+    const uint32_t u0 = s1 ? r.c0 : r.c1;
+    const uint32_t o0 = s2 ? u0 : v1, o1 = s2 ? v0 : v2, o2 = s2 ? v1 : v3, o3 = s2 ? v2 : v4;
+    const int32_t cb = int32_t(k) - int32_t(r.q);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(r.word0) + cb;
+    if (cb >= 1 && uint32_t(cb) + 3u < r.kend) { sts128(tile_s + slot * 512u + ((lane + slot) & 31u) * 16u, make_uint4(o0, o1, o2, o3)); valid |= 1u << slot; }
+    else {
+        if (cb >= 1 && uint32_t(cb) < r.kend) dst[0] = o0;
+        if (cb + 1 >= 1 && uint32_t(cb + 1) < r.kend) dst[1] = o1;
+        if (cb + 2 >= 1 && uint32_t(cb + 2) < r.kend) dst[2] = o2;
+        if (cb + 3 >= 1 && uint32_t(cb + 3) < r.kend) dst[3] = o3;
+    }
+    r.c0 = a1; r.c1 = a2; r.c2 = a3;
+}
+/* Writes the tile out: `base` = this lane's global address of slot 0's line, `valid` = its slots that hold a line.  All 32 lanes. */
+__device__ __forceinline__ void rl_flush(uint32_t tile_s, uint8_t *base, uint32_t valid, uint32_t lane) {
+    __syncwarp();
+    const uint32_t line = lane & 7u;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+        const uint32_t row = 4u * i + (lane >> 3);
+        const uint64_t rb = __shfl_sync(0xffffffffu, uint64_t(reinterpret_cast<uintptr_t>(base)), row);
+        const uint32_t rv = __shfl_sync(0xffffffffu, valid, row);
+        if ((rv >> line) & 1u)
+            *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(uintptr_t(rb)) + 16u * line) = lds128(tile_s + line * 512u + ((row + line) & 31u) * 16u);
+    }
+    __syncwarp();
+}
 /* k = first group of the last quad, ng = groups in the run */
 __device__ __forceinline__ void rl_close(const RunLine &r, uint32_t k, uint32_t ng) {
     uint32_t *w = reinterpret_cast<uint32_t *>(r.word0);
@@ -1107,7 +1149,8 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         asm volatile("cp.async.wait_group %0;" ::"n"(LONG_AHEAD) : "memory");           /* word 0 has landed */
         uint32_t w_lo = lds32m(ring_s);
         const uint32_t quads = (ng + 3u) >> 2, T = __reduce_max_sync(0xffffffffu, quads);
-        uint32_t first_s = 0, first_q = 0;
+        uint32_t first_s = 0, first_q = 0, vs = 0, vq = 0;
+        const uint32_t tile_s = base_s + SM_QTAB + qtab_bytes(QM, rp.phred.cb, rp.phred.npos) + uint32_t(DIRECT_THREADS / 32) * (LONG_RING * 128u) + (threadIdx.x >> 5) * 8192u;
         for (uint32_t qd = 0; qd < T; ++qd) {             /* sixteen bases = one word of the 2-bit copy */
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ring_s + ((qd + LONG_AHEAD + 1u) % LONG_RING) * 128u), "l"(pw + qd + LONG_AHEAD + 1u) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1122,9 +1165,16 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
                     sw[h] = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
                 }
                 if (qd == 0) { first_s = sw[0]; first_q = qw[0]; }
-                rl_quad(ls, 4u * qd, sw[0], sw[1], sw[2], sw[3]); rl_quad(lq, 4u * qd, qw[0], qw[1], qw[2], qw[3]);
+                rl_quad_staged(ls, 4u * qd, sw[0], sw[1], sw[2], sw[3], tile_s, lane, qd & 7u, vs);
+                rl_quad_staged(lq, 4u * qd, qw[0], qw[1], qw[2], qw[3], tile_s + 4096u, lane, qd & 7u, vq);
             }
             w_lo = w_hi;
+            if ((qd & 7u) == 7u || qd + 1u == T) {        /* eight turns collected (or the read is done): the warp writes the lines out */
+                const int32_t first = int32_t(16u * (qd & ~7u));
+                rl_flush(tile_s, ls.word0 + first - 4 * int32_t(ls.q), vs, lane);
+                rl_flush(tile_s + 4096u, lq.word0 + first - 4 * int32_t(lq.q), vq, lane);
+                vs = vq = 0;
+            }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");      /* nothing of this read's copies may land in the next read's ring */
         if (ng) {
