@@ -40,7 +40,7 @@ struct ReplayDev {                 /* device copies of simmr_draws + replay LUTs
 
 /* long reads are cut into LONG_PIECES pieces of a multiple of 16 bases, each with its own chains: the 32 lanes' work in k_format_long */
 constexpr uint32_t LONG_PIECES = 32;
-constexpr uint32_t LONG_RING = 16, LONG_AHEAD = 12;   /* k_format_long: words of the 2-bit copy per lane in shared memory, and how far ahead they are fetched */
+constexpr uint32_t LONG_RING = 8, LONG_AHEAD = 5;   /* k_format_long: words of the 2-bit copy per lane in shared memory, and how far ahead they are fetched */
 struct UnitDesc;
 struct RunParams {
     /* genomes (device resident) */
@@ -73,8 +73,9 @@ constexpr int SIZES_THREADS = 256;
 constexpr int FORMAT_THREADS = 512;   /* most threads of a format CTA (each warp has a private stage) -> register cap of 128 */
 constexpr int FORMAT_MIN_CTAS = 1;
 constexpr int DIRECT_THREADS = 256;
-__host__ __device__ constexpr uint32_t long_extra_smem() {   /* k_format_long: per warp a genome-word ring and two tiles of 8 turns x 32 lines */
-    return uint32_t(DIRECT_THREADS / 32) * (LONG_RING * 128u + 8192u);
+constexpr uint32_t LONG_EVENTS = 16;      /* k_format_long: substitution events of a piece walked ahead of its lines (more are handled the slow way) */
+__host__ __device__ constexpr uint32_t long_extra_smem() {   /* k_format_long: per warp a genome-word ring and two tiles of 8 turns x 32 lines; per lane an event list */
+    return uint32_t(DIRECT_THREADS / 32) * (LONG_RING * 128u + 8192u) + LONG_EVENTS * uint32_t(DIRECT_THREADS) * 4u;
 }
 constexpr uint32_t PACK_PAD_WORDS = 4352; /* readable words before and after `packed`: a lane keeps fetching (and discarding)
                                              for as long as the longest record of its warp lasts, at most 65535 / 16 words */
@@ -1133,6 +1134,26 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         rl_open(ls, seq, nb); rl_open(lq, qual, nb);
         Mwc1 qc{}, ec{};
         if (QM != QM_CONST && nb) mwc1_seed(rp, qc, ec, lane, 1, uint32_t(unit), uint32_t(unit >> 32));
+        /* The piece's first LONG_EVENTS substitution events are walked now (position | new quality << 16 | m << 24, a list
+         * per lane in shared memory): the turn that reaches a position XORs m into the base's 2-bit code before the
+         * letters are looked up, and the new qualities are plain byte stores after the lines are out — no base is read
+         * back from memory.  What a longer chain holds beyond the list is applied the slow way at the end. */
+        const uint32_t ev_s = base_s + SM_QTAB + qtab_bytes(QM, rp.phred.cb, rp.phred.npos) + uint32_t(DIRECT_THREADS / 32) * (LONG_RING * 128u + 8192u) + 4u * threadIdx.x;
+        uint32_t nev = 0, ev_at0 = 0;
+        if (QM != QM_CONST && rp.phred.has_sub) {
+            const uint32_t gap_s = base_s + SM_GAP, qsub_s = base_s + SM_QSUB;
+            while (ev_at0 < nb && nev < LONG_EVENTS) {
+                uint32_t l1, l2, l3;
+                const uint32_t r1 = mwc1_draw(ec, rp.one, l1), r2 = mwc1_draw(ec, rp.one, l2), r3 = mwc1_draw(ec, rp.one, l3);
+                const uint32_t g = q32_pick(lds32(gap_s + 4u * (r1 & (GAP_COLS - 1u))), l1);
+                if (g == GAP_NONE) { ev_at0 += GAP_NONE; continue; }
+                const uint32_t at = ev_at0 + g;
+                if (at >= nb) { ev_at0 = nb; break; }
+                sts32(ev_s + nev * (DIRECT_THREADS * 4u), at | (q32_pick(lds32(qsub_s + 4u * (r2 & mask)), l2) << 16) | ((1u + __umulhi(r3, 3u)) << 24));
+                ++nev; ev_at0 = at + 1u;
+            }
+        }
+        uint32_t ev_i = 0, ev_cur = nev ? lds32m(ev_s) : 0xffffffffu;
         const uint64_t a = d.a0 + lo;
         const uint32_t *pw = rp.packed + (a >> 4);
         const uint32_t s2 = 2u * (uint32_t(a) & 15u);
@@ -1157,7 +1178,11 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
             asm volatile("cp.async.wait_group %0;" ::"n"(LONG_AHEAD) : "memory");       /* words up to qd + 1 have landed */
             const uint32_t w_hi = lds32m(ring_s + ((qd + 1u) % LONG_RING) * 128u);
             if (qd < quads) {
-                const uint32_t X = __funnelshift_r(w_lo, w_hi, s2);
+                uint32_t X = __funnelshift_r(w_lo, w_hi, s2);
+                while (((ev_cur & 0xffffu) >> 4) == qd) {         /* substitutions among this turn's 16 bases: rank ^ m */
+                    X ^= (ev_cur >> 24) << (2u * (ev_cur & 15u));
+                    ++ev_i; ev_cur = ev_i < nev ? lds32m(ev_s + ev_i * (DIRECT_THREADS * 4u)) : 0xffffffffu;
+                }
                 uint32_t sw[4], qw[4];
 #pragma unroll
                 for (uint32_t h = 0; h < 4; ++h) {
@@ -1181,9 +1206,13 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
             const uint32_t kl = 4u * (quads - 1u);
             rl_close(ls, kl, ng); rl_edges(ls, kl, ng, first_s); rl_close(lq, kl, ng); rl_edges(lq, kl, ng, first_q);
         }
-        if (QM != QM_CONST && rp.phred.has_sub) {         /* the piece's substituted bases, on the bytes this lane just wrote */
+        if (QM != QM_CONST && rp.phred.has_sub) {
+            for (uint32_t k = 0; k < nev; ++k) {          /* the listed events' qualities */
+                const uint32_t e = lds32m(ev_s + k * (DIRECT_THREADS * 4u));
+                qual[e & 0xffffu] = uint8_t(e >> 16);
+            }
             const uint32_t gap_s = base_s + SM_GAP, qsub_s = base_s + SM_QSUB;
-            for (uint32_t at0 = 0; at0 < nb;) {
+            for (uint32_t at0 = ev_at0; at0 < nb;) {      /* events past the list: the base is read back from the line */
                 uint32_t l1, l2, l3;
                 const uint32_t r1 = mwc1_draw(ec, rp.one, l1), r2 = mwc1_draw(ec, rp.one, l2), r3 = mwc1_draw(ec, rp.one, l3);
                 const uint32_t g = q32_pick(lds32(gap_s + 4u * (r1 & (GAP_COLS - 1u))), l1);
