@@ -253,7 +253,16 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         ctx->stats = st;
         return SIMMR_OK;
     }
-    const uint64_t target_bytes = sink ? (256ull << 20) : (2048ull << 20);
+    /* Staging per batch.  A long read is budgeted at its largest possible size (131 KB) although it averages 40 KB, and a
+     * warp takes whole reads: 2 GiB would be 16 K reads per launch, 7 per warp, and the last warps' long reads would
+     * leave the GPU half idle.  16 GiB (of 180) gives 55 reads per warp; less when the device is short of memory. */
+    uint64_t target_bytes = sink ? (256ull << 20) : ctx->model.is_long ? (16384ull << 20) : (2048ull << 20);
+    if (!sink) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        free_b += ctx->d_out[0].bytes;                    /* what this context already holds for staging can be reused */
+        while (target_bytes > (256ull << 20) && target_bytes > free_b / 3) target_bytes /= 2;
+    }
     uint64_t batch = opts && opts->batch_units ? opts->batch_units : std::max<uint64_t>(1, target_bytes / pl.max_unit_bytes);
     batch = std::min<uint64_t>(batch, std::max<uint64_t>(1, ue - ub));
     batch = std::min<uint64_t>(batch, 0x7fffffffull);
