@@ -253,10 +253,12 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         ctx->stats = st;
         return SIMMR_OK;
     }
-    /* Staging per batch.  A long read is budgeted at its largest possible size (131 KB) although it averages 40 KB, and a
-     * warp takes whole reads: 2 GiB would be 16 K reads per launch, 7 per warp, and the last warps' long reads would
-     * leave the GPU half idle.  16 GiB (of 180) gives 55 reads per warp; less when the device is short of memory. */
-    uint64_t target_bytes = sink ? (256ull << 20) : ctx->model.is_long ? (16384ull << 20) : (2048ull << 20);
+    /* Staging per batch: 16 GiB (of 180) when nothing has to cross PCIe, less when the device is short of memory.  Few
+     * large launches beat many small ones twice: every launch fills the tables of 148 CTAs and ends with a partly idle
+     * GPU (short reads: 2 -> 16 GiB is +7 %), and a long read is budgeted at its largest possible size (131 KB) although
+     * it averages 40 KB — 2 GiB were 16 K reads per launch, 7 per warp, and the last warps' long reads left the GPU half
+     * idle (+22 %). */
+    uint64_t target_bytes = sink ? (256ull << 20) : (16384ull << 20);
     if (!sink) {
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
