@@ -585,7 +585,9 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, Repl
         UnitGeo g; unit_geometry<REPLAY>(rp, rd, rp.batch_begin + i, REPLAY ? 0 : g_span[0], REPLAY ? 0 : g_span[1], g);
         uint32_t H[2] = {0, 0};
         uint64_t big = 0;
-        for (uint32_t r = 0; r < g.nrec; ++r) {
+#pragma unroll
+        for (uint32_t r = 0; r < 2; ++r) {                       /* unrolled: the arrays stay in registers */
+            if (r >= g.nrec) break;
             H[r] = header_len(rp.chdr[2 * g.contig + r], g.id, g.sp[r], g.ep[r]);
             bytes += H[r] + 2ull * g.L[r] + 5;
             alg += H[r] + 3ull * g.L[r] + 5;                     /* BASELINE.md §3 */
