@@ -205,12 +205,6 @@ struct __align__(16) UnitDesc {
 };
 static_assert(sizeof(UnitDesc) == 48, "UnitDesc layout");
 
-__device__ __forceinline__ uint32_t genome_of(const RunParams &rp, uint64_t u) {
-    uint32_t lo = 0, hi = rp.n_genomes;            /* last g with unit_start[g] <= u */
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(rp.unit_start + mid) <= u) lo = mid; else hi = mid; }
-    return lo;
-}
-
 template <bool REPLAY>
 __device__ void unit_geometry(const RunParams &rp, const ReplayDev &rd, uint64_t u, uint32_t g_lo, uint32_t g_hi, UnitGeo &o) {
     o.id = rp.read_id_base + uint32_t(u);                         /* simulate.rs:85-89 */
@@ -304,9 +298,11 @@ __device__ __forceinline__ bool window_impure(const RunParams &rp, uint64_t a, u
 /* ---------------------------------------------------------------------- */
 /* headers — fastq.rs:34-57                                                 */
 /* ---------------------------------------------------------------------- */
+__constant__ uint32_t POW10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
+/* decimal digits of v: floor(log10) guessed from the bit length (1233 / 4096 ~ log10 2), corrected by one compare */
 __device__ __forceinline__ uint32_t dec_digits32(uint32_t v) {
-    return 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
-           (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+    const uint32_t guess = ((32u - __clz(v | 1u)) * 1233u) >> 12;      /* 0..9: digits - 1 or digits */
+    return guess + ((v | 1u) >= POW10[guess] ? 1u : 0u);
 }
 __device__ __forceinline__ uint32_t dec_digits(uint64_t v) {
     if (!(v >> 32)) return dec_digits32(uint32_t(v));
@@ -576,9 +572,13 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, Repl
     uint64_t bytes = 0, alg = 0, bases = 0, clamped = 0, recs = 0;
     /* genome of the block's first and last unit by binary search, once; the threads then walk between the two */
     __shared__ uint32_t g_span[2];
-    if (!REPLAY && (threadIdx.x == 0 || threadIdx.x == 32)) {
+    if (!REPLAY && threadIdx.x < 64) {      /* warp 0: the first unit's genome, warp 1: the last one's — genomes whose first unit is <= u, counted by 32 lanes */
         const uint32_t first = blockIdx.x * SIZES_THREADS, last = min(first + SIZES_THREADS, rp.batch_units) - 1;
-        g_span[threadIdx.x >> 5] = genome_of(rp, rp.batch_begin + (threadIdx.x ? last : first));
+        const uint64_t u = rp.batch_begin + (threadIdx.x >> 5 ? last : first);
+        uint32_t below = 0;
+        for (uint32_t g = threadIdx.x & 31; g < rp.n_genomes; g += 32) below += __ldg(rp.unit_start + g) <= u ? 1u : 0u;
+        below = __reduce_add_sync(0xffffffffu, below);
+        if ((threadIdx.x & 31) == 0) g_span[threadIdx.x >> 5] = below ? below - 1u : 0u;
     }
     __syncthreads();
     if (i < rp.batch_units) {
