@@ -286,6 +286,11 @@ __device__ void unit_geometry(const RunParams &rp, const ReplayDev &rd, uint64_t
 __device__ __forceinline__ bool window_impure(const RunParams &rp, uint64_t a, uint32_t L) {
     if (!L) return false;
     const uint64_t b0 = a >> 5, b1 = (a + L - 1) >> 5;
+    if (b1 - b0 < 32) {                          /* up to 1024 bases: the window's bits sit in two words (the map has a spare word at its end) */
+        const uint32_t nbits = uint32_t(b1 - b0) + 1u;
+        const uint32_t bits = __funnelshift_r(__ldg(rp.impure + (b0 >> 5)), __ldg(rp.impure + (b0 >> 5) + 1), uint32_t(b0) & 31u);
+        return (bits & (0xffffffffu >> (32u - nbits))) != 0u;
+    }
     for (uint64_t w = b0 >> 5; w <= (b1 >> 5); ++w) {
         uint32_t bits = __ldg(rp.impure + w);
         if (w == (b0 >> 5)) bits &= 0xffffffffu << (b0 & 31);
