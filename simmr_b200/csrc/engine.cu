@@ -98,7 +98,6 @@ int fail(simmr_ctx *c, int code, const std::string &m) {
         if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-size_t table_bytes(const ProfileModel &m) { return m.phred_entries.size() * 4; }
 /* how the short-read kernel samples qualities: a single position's table is copied once per lane (no bank conflicts) */
 int quality_mode(const ProfileModel &m) {
     if (m.phred_kind != PT_Q32) return QM_CONST;
@@ -136,9 +135,7 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
     const uint64_t unit_bytes = per_rec * (m.is_long ? 1 : 2);
     if (unit_bytes > 0xfff00000ull) return fail(ctx, SIMMR_E_LIMIT, "a unit's FASTQ bytes exceed 4 GiB");
     pl.max_unit_bytes = uint32_t(unit_bytes);
-    const size_t tab = table_bytes(m);
-    const size_t smem_max = ctx->prop.sharedMemPerBlockOptin, smem_sm = ctx->prop.sharedMemPerMultiprocessor;
-    if (tab + 1024 > smem_max) return fail(ctx, SIMMR_E_LIMIT, "quality tables do not fit in shared memory");
+    const size_t smem_max = ctx->prop.sharedMemPerBlockOptin;
     pl.tiles = !m.is_long;
     if (pl.tiles) {
         /* A warp's stage holds the typical bytes of its WARP_UNITS units (one record per lane) plus a margin — a group
@@ -153,9 +150,10 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
         else { pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.smem = lanes_smem(m, warps, uint32_t(cap)); }
     }
     int occ = 0;
-    if (!pl.tiles && !replay && m.is_long && !getenv("SIMMR_NO_LONG_KERNEL")) {
+    const size_t long_smem = SM_QTAB + qtab_bytes(quality_mode(m), m.cb, m.npos) + long_extra_smem();   /* tables, a genome-word ring and two line tiles per warp, an event list per lane */
+    if (!pl.tiles && !replay && m.is_long && long_smem <= smem_max && !getenv("SIMMR_NO_LONG_KERNEL")) {   /* per-position tables too large for it: byte path */
         pl.lanes = true; pl.threads = DIRECT_THREADS;
-        pl.smem = SM_QTAB + qtab_bytes(quality_mode(m), m.cb, m.npos) + long_extra_smem();   /* tables, a genome-word ring per warp, an event list per lane */
+        pl.smem = long_smem;
         LongKernel k = long_kernel(quality_mode(m));
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));

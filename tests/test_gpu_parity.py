@@ -96,6 +96,13 @@ def test_long_read_piece_boundaries(engine):
     assert lens[0] < 1024 and lens[-1] > 16000        # a 518-base read: 17 pieces of 32 bases, 15 lanes without a piece
 
 
+def test_long_profile_too_large_for_shared_memory(engine):
+    """A long-read profile with 700 quality positions (358 KB of tables) does not fit next to the long kernel's rings and
+    tiles: the run takes the byte path (one CTA per read, a thread per piece) and still matches the oracle."""
+    gs = H.synth_genomes(2, (1, 1), (30000, 60000), seed=29)
+    check_native(engine, gs, S.CustomLongErrorProfile(H.ont_blob(npos=700)), [9, 7], 41)
+
+
 def test_batching_and_sharding_do_not_change_bytes(engine):
     gs = H.synth_genomes(4, (1, 3), (3000, 8000), seed=9)
     prof = S.MinimalShortErrorProfile()
