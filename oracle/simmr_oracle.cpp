@@ -524,15 +524,28 @@ bool phred_table_from_blob(const Blob &b, PhredTable &t) {
         }
     }
     if (qmin > qmax) return false;
+    /* columns of a row = its qualities with mass above 2^-24 of the row (rarer ones would get a zero threshold), ascending;
+     * table width = the richest row */
+    std::vector<double> cut(np);
+    size_t widest = 1;
+    for (size_t p = 0; p < np; p++) {
+        double row = 0.0;
+        for (uint32_t v = qmin; v <= qmax; v++) row += pm[p][v];
+        cut[p] = std::ldexp(row, -24);
+        size_t n = 0;
+        for (uint32_t v = qmin; v <= qmax; v++) if (pm[p][v] > cut[p]) n++;
+        widest = std::max(widest, n);
+    }
     t.kind = 3; t.npos = (uint32_t)np;
-    t.cb = std::max(1u, ceil_log2(qmax - qmin + 1));
+    t.cb = std::max(1u, ceil_log2(widest));
     t.entries.clear();
     for (size_t p = 0; p < np; p++) {
-        std::vector<double> w(pm[p].begin() + qmin, pm[p].begin() + qmax + 1), prob;
-        std::vector<uint32_t> alias;
+        std::vector<double> w, prob; std::vector<uint32_t> val, alias;
+        for (uint32_t v = qmin; v <= qmax; v++) if (pm[p][v] > cut[p]) { w.push_back(pm[p][v]); val.push_back(v); }
         if (!vose(w, t.cb, prob, alias)) return false;
+        val.resize(prob.size(), val.back());               /* empty columns always take their alias */
         for (size_t i = 0; i < prob.size(); i++)
-            t.entries.push_back(q32_entry(prob[i], qmin + (uint32_t)i + 33u, qmin + alias[i] + 33u));
+            t.entries.push_back(q32_entry(prob[i], val[i] + 33u, val[alias[i]] + 33u));
     }
     return true;
 }

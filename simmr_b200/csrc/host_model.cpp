@@ -242,14 +242,28 @@ bool phred_from_blob(const ProfileBlob &b, ProfileModel &m) {
         }
     }
     if (qmin > qmax) return false;
-    m.phred_kind = PT_Q32; m.npos = uint32_t(np); m.cb = bits_for(qmax - qmin + 1);
+    /* A row's columns are its qualities that can occur at all — mass above 2^-24 of the row, anything rarer would get a
+     * zero 16-bit threshold anyway — in increasing order (the words hold the values themselves), so the table is as wide
+     * as the richest position, not as the range of all positions. */
+    std::vector<double> cut(np);
+    size_t widest = 1;
+    for (size_t p = 0; p < np; ++p) {
+        double row = 0.0;
+        for (uint32_t v = qmin; v <= qmax; ++v) row += mass[p][v];
+        cut[p] = std::ldexp(row, -24);
+        size_t n = 0;
+        for (uint32_t v = qmin; v <= qmax; ++v) n += mass[p][v] > cut[p];
+        widest = std::max(widest, n);
+    }
+    m.phred_kind = PT_Q32; m.npos = uint32_t(np); m.cb = bits_for(widest);
     m.phred_entries.clear();
     for (size_t p = 0; p < np; ++p) {
-        std::vector<double> w(mass[p].begin() + qmin, mass[p].begin() + qmax + 1), keep;
-        std::vector<uint32_t> other;
+        std::vector<double> w, keep; std::vector<uint32_t> value, other;
+        for (uint32_t v = qmin; v <= qmax; ++v) if (mass[p][v] > cut[p]) { w.push_back(mass[p][v]); value.push_back(v); }
         if (!alias_columns(w, m.cb, keep, other)) return false;
+        value.resize(keep.size(), value.back());               /* columns without an outcome always take their alias */
         for (size_t i = 0; i < keep.size(); ++i)
-            m.phred_entries.push_back(q32_word(keep[i], qmin + uint32_t(i) + 33u, qmin + other[i] + 33u));
+            m.phred_entries.push_back(q32_word(keep[i], value[i] + 33u, value[other[i]] + 33u));
     }
     return true;
 }
