@@ -1095,8 +1095,8 @@ __device__ __forceinline__ void rl_edges(const RunLine &r, uint32_t k, uint32_t 
  * whatever the read's length.  A lane seeds its piece's chains, writes that part of the sequence and quality lines
  * straight to global memory in 16-byte lines (RunLine), then applies the piece's substitutions to the bytes it wrote.
  * Lane 0 also writes the header and the fixed bytes.  Reads whose window holds anything but A,C,G,T take the byte
- * path, a lane per piece.  QM as in k_format_lanes. */
-template <int QM>
+ * path, a lane per piece.  QM and CB7 as in k_format_lanes / quals4. */
+template <int QM, bool CB7>
 __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31;
@@ -1193,7 +1193,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
                 uint32_t sw[4], qw[4];
 #pragma unroll
                 for (uint32_t h = 0; h < 4; ++h) {
-                    qw[h] = QM == QM_CONST ? qconst : quals4<QM, false>(rp, qtab_s, mask, qc, lo + 16u * qd + 4u * h);
+                    qw[h] = QM == QM_CONST ? qconst : quals4<QM, CB7>(rp, qtab_s, mask, qc, lo + 16u * qd + 4u * h);
                     sw[h] = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
                 }
                 if (qd == 0) { first_s = sw[0]; first_q = qw[0]; }

@@ -119,7 +119,10 @@ FormatKernel lanes_kernel(bool replay, int qm) {
 }
 FormatKernel direct_kernel(bool replay) { return replay ? k_format_direct<true> : k_format_direct<false>; }
 using LongKernel = void (*)(RunParams);
-LongKernel long_kernel(int qm) { return qm == QM_LANE ? k_format_long<QM_LANE> : qm == QM_POS ? k_format_long<QM_POS> : k_format_long<QM_CONST>; }
+LongKernel long_kernel(int qm, uint32_t cb) {
+    if (qm == QM_LANE) return cb == 7 ? k_format_long<QM_LANE, true> : k_format_long<QM_LANE, false>;
+    return qm == QM_POS ? k_format_long<QM_POS, false> : k_format_long<QM_CONST, false>;
+}
 
 struct Plan {      /* launch geometry for one run */
     bool tiles = false;            /* warp-private stages in shared memory (short reads) vs one CTA per unit */
@@ -154,7 +157,7 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
     if (!pl.tiles && !replay && m.is_long && long_smem <= smem_max && !getenv("SIMMR_NO_LONG_KERNEL")) {   /* per-position tables too large for it: byte path */
         pl.lanes = true; pl.threads = DIRECT_THREADS;
         pl.smem = long_smem;
-        LongKernel k = long_kernel(quality_mode(m));
+        LongKernel k = long_kernel(quality_mode(m), m.cb);
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
     } else {
@@ -347,7 +350,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
             lanes_kernel(replay, quality_mode(ctx->model))<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
         } else if (pl.lanes) {
             CU(cudaMemsetAsync(rp.counters + 4, 0, 8, ctx->compute));       /* the kernel's piece counter */
-            long_kernel(quality_mode(ctx->model))<<<pl.grid, pl.threads, pl.smem, ctx->compute>>>(rp);
+            long_kernel(quality_mode(ctx->model), ctx->model.cb)<<<pl.grid, pl.threads, pl.smem, ctx->compute>>>(rp);
         } else {
             const int grid = int(std::min<uint32_t>(n, uint32_t(pl.grid)));
             direct_kernel(replay)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
