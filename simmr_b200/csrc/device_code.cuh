@@ -739,8 +739,9 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
     const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u, mask = rp.phred_mult - 1u;
     uint32_t prev_s = 0, prev_q = 0;
     /* one turn = G groups of 4 bases of every record: G = 4 but for the warp's last turn, which is as long as its longest record needs */
-    auto turn = [&](auto gc, uint32_t it) {
+    auto turn = [&](auto gc, auto whole, uint32_t it) {       /* whole: every lane is inside both lines for all of this turn */
         constexpr uint32_t G = decltype(gc)::value;
+        constexpr bool WHOLE = decltype(whole)::value;
         const uint32_t X = __byte_perm(__funnelshift_r(w_lo, w_hi, s2), 0u, rev);
         if (G == 4) {   /* mate 1: (lo, hi) <- (hi, new); mate 2: (lo, hi) <- (new, lo).  The padding around `packed` covers the last fetch. */
             const uint32_t nw = __ldg(pw);
@@ -756,7 +757,7 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
             cs[h] = __funnelshift_l(prev_s, sw, sh_s); cq[h] = QM == QM_CONST ? qconst : __funnelshift_l(prev_q, qw, sh_q);
             prev_s = sw; prev_q = qw;
         }
-        if (G == 4 && __all_sync(0xffffffffu, ns >= 4 && nq >= 4)) {      /* every lane is inside both lines: no per-word tests */
+        if (WHOLE) {                                   /* no per-word tests */
 #pragma unroll
             for (uint32_t h = 0; h < G; ++h) { sts32(ps + 4u * h, cs[h]); sts32(pq + 4u * h, cq[h]); }
         } else {
@@ -769,12 +770,16 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
         ps += 4u * G; pq += 4u * G; ns -= int32_t(G); nq -= int32_t(G);
     };
     const uint32_t full = (T4 - 1u) >> 2;              /* T4 >= 1 */
-    for (uint32_t it = 0; it < full; ++it) turn(std::integral_constant<uint32_t, 4>{}, it);
+    /* turns during which every lane of the warp stores whole groups in both lines: the shortest record's */
+    const uint32_t whole = min(full, __reduce_min_sync(0xffffffffu, uint32_t(min(ns, nq)) >> 2));
+    uint32_t it = 0;
+    for (; it < whole; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::true_type{}, it);
+    for (; it < full; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, it);
     switch (T4 - 4u * full) {
-    case 1: turn(std::integral_constant<uint32_t, 1>{}, full); break;
-    case 2: turn(std::integral_constant<uint32_t, 2>{}, full); break;
-    case 3: turn(std::integral_constant<uint32_t, 3>{}, full); break;
-    default: turn(std::integral_constant<uint32_t, 4>{}, full); break;
+    case 1: turn(std::integral_constant<uint32_t, 1>{}, std::false_type{}, full); break;
+    case 2: turn(std::integral_constant<uint32_t, 2>{}, std::false_type{}, full); break;
+    case 3: turn(std::integral_constant<uint32_t, 3>{}, std::false_type{}, full); break;
+    default: turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, full); break;
     }
 }
 
