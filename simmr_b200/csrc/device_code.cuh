@@ -2,7 +2,7 @@
  *
  * Path (reference file:line -> kernel):
  *   simulate.rs:165-190, 205-262, 353-375, 464-491  geometry      -> unit_geometry()
- *   fastq.rs:34-57 header interpolation, record size             -> k_unit_sizes, header_fast(), emit_header()
+ *   fastq.rs:34-57 header interpolation, record size             -> k_unit_sizes, header_tokens(), emit_header()
  *   (no reference equivalent: byte offsets of the FASTQ stream)   -> k_scan_blocks, k_unit_offsets
  *   simulate.rs:261-286 + error_profiles/ *.rs phreds/mutation +
  *   util.rs:15-57 RC / +33 + fastq.rs:61-69 record layout         -> k_format_lanes (short reads), k_format_long,
