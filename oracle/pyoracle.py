@@ -52,16 +52,36 @@ class OrcStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("records", "bases", "bytes", "units", "clamped", "mutated")]
 
 
-def build():
+def _cpu_stamp():
+    """The oracle is built -march=native (it is also the timed CPU baseline): a library built on another machine's CPU
+    (this container vs the GPU box) is rebuilt where it runs."""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                import hashlib
+                return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build(force=False):
+    if force:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "clean"])
     subprocess.check_call(["make", "-s", "-C", _HERE])
+    with open(os.path.join(_HERE, ".build_cpu"), "w") as f:
+        f.write(_cpu_stamp())
 
 
 def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, "libsimmr_oracle.so")
+        stamp = os.path.join(_HERE, ".build_cpu")
         if not os.path.exists(path):
             build()
+        elif not os.path.exists(stamp) or open(stamp).read() != _cpu_stamp():
+            build(force=True)
         L = C.CDLL(path)
         L.orc_last_error.restype = C.c_char_p
         L.orc_complement.restype = C.c_uint8
@@ -82,6 +102,7 @@ def lib():
         L.orc_total_units.restype = C.c_uint64
         L.orc_simulate.restype = C.c_int64
         L.orc_replay.restype = C.c_int64
+        L.orc_ref_stream.restype = C.c_int64
         L.orc_fasta_num_seqs.restype = C.c_uint32
         for f in ("orc_fasta_size", "orc_fasta_seq_size", "orc_fasta_seq_len"):
             getattr(L, f).restype = C.c_uint64
@@ -193,6 +214,28 @@ def simulate(genomes, profile, reads_per_genome, seed, header_format=None, unit_
         raise RuntimeError(err() or f"oracle buffer too small ({-n})")
     out = buf[:n].tobytes()
     return (out, st) if want_stats else out
+
+
+def bench_pe(genomes, profile, reads_per_genome, seed, unit_begin, n_units, mode, threads):
+    """orc_bench_pe -> dict(seconds, bases, records, bytes); mode 0 native draw schedule, 1 the reference's stream."""
+    r = np.ascontiguousarray(reads_per_genome, np.uint64)
+    sec, nb, nr, ny = C.c_double(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    if lib().orc_bench_pe(C.byref(genomes.c), C.byref(profile.c), _p(r, u64p), C.c_uint64(seed), C.c_uint64(unit_begin),
+                          C.c_uint64(n_units), int(mode), int(threads), C.byref(sec), C.byref(nb), C.byref(nr), C.byref(ny)) != 0:
+        raise RuntimeError(err())
+    return dict(seconds=sec.value, bases=nb.value, records=nr.value, bytes=ny.value)
+
+
+def ref_stream(genomes, profile, n_pairs, seed):
+    """FASTQ of the first n_pairs pairs of genome 0 through the reference's own stream plumbing (ref_stream.inc)."""
+    cap = int(n_pairs) * 2 * (2 * 70000 // 100 + 2048) + 4096
+    buf = np.empty(cap, np.uint8)
+    st = OrcStats()
+    n = lib().orc_ref_stream(C.byref(genomes.c), C.byref(profile.c), C.c_uint64(n_pairs), C.c_uint64(seed), _p(buf, u8p),
+                             C.c_uint64(cap), C.byref(st))
+    if n < 0:
+        raise RuntimeError(err())
+    return buf[:n].tobytes(), st
 
 
 def native_geometry(genomes, profile, reads_per_genome, seed, unit_begin=0, unit_end=0):

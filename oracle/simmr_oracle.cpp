@@ -26,6 +26,9 @@
 #include <sstream>
 #include <string>
 #include <vector>
+#include <thread>
+#include <atomic>
+#include <chrono>
 
 namespace {
 
@@ -950,6 +953,8 @@ struct Xo {   /* xoshiro256** seeded by splitmix64 */
     uint32_t below(uint32_t n) { return (uint32_t)(((next() >> 32) * (uint64_t)n) >> 32); }
 };
 
+#include "ref_stream.inc"
+
 }  // namespace
 
 /* ==================================================================== */
@@ -1152,17 +1157,13 @@ int orc_native_geometry(const orc_genomes *g, const orc_profile *pi, const uint6
     return 0;
 }
 
-int64_t orc_simulate(const orc_genomes *g, const orc_profile *pi, const uint64_t *reads, const orc_opts *o,
-                     uint8_t *out, uint64_t cap, orc_stats *stp) {
-    Profile p; if (!make_profile(pi, p)) return -1;
-    GenomeView gv{g}; UnitMap um(reads, g->n_genomes, p.is_long); Philox ph(o->seed);
-    std::string fmt = o->header_format ? o->header_format : DEFAULT_HEADER;
-    uint64_t b = o->unit_begin, e = o->unit_end; if (b == 0 && e == 0) e = um.total();
-    if (e > um.total()) return fail("unit range past the end");
-    orc_stats st{}; std::vector<uint8_t> buf, s1, q1, s2, q2;
+/* units [b, e) of a native-mode run appended to `buf` (the body of orc_simulate; also timed by orc_bench_pe) */
+static bool simulate_range(const GenomeView &gv, const Profile &p, const UnitMap &um, const Philox &ph, const std::string &fmt,
+                           uint32_t id_base, uint64_t b, uint64_t e, std::vector<uint8_t> &buf, orc_stats &st) {
+    std::vector<uint8_t> s1, q1, s2, q2;
     for (uint64_t u = b; u < e; u++) {
-        NativeGeom ng{}; if (!native_geometry(gv, p, um, ph, u, ng)) return -1;
-        uint32_t id = o->read_id_base + (uint32_t)u;                                  /* simulate.rs:85-89, one id per unit */
+        NativeGeom ng{}; if (!native_geometry(gv, p, um, ph, u, ng)) return false;
+        uint32_t id = id_base + (uint32_t)u;                                          /* simulate.rs:85-89, one id per unit */
         std::string gid = gv.gid(ng.genome), sid = gv.cid(ng.contig);
         const uint8_t *cs = gv.seq(ng.contig);
         if (!p.is_long) {
@@ -1181,6 +1182,95 @@ int64_t orc_simulate(const orc_genomes *g, const orc_profile *pi, const uint64_t
         }
         st.units++;
     }
+    return true;
+}
+
+int64_t orc_simulate(const orc_genomes *g, const orc_profile *pi, const uint64_t *reads, const orc_opts *o,
+                     uint8_t *out, uint64_t cap, orc_stats *stp) {
+    Profile p; if (!make_profile(pi, p)) return -1;
+    GenomeView gv{g}; UnitMap um(reads, g->n_genomes, p.is_long); Philox ph(o->seed);
+    std::string fmt = o->header_format ? o->header_format : DEFAULT_HEADER;
+    uint64_t b = o->unit_begin, e = o->unit_end; if (b == 0 && e == 0) e = um.total();
+    if (e > um.total()) return fail("unit range past the end");
+    orc_stats st{}; std::vector<uint8_t> buf;
+    if (!simulate_range(gv, p, um, ph, fmt, o->read_id_base, b, e, buf, st)) return -1;
+    st.bytes = buf.size();
+    if (stp) *stp = st;
+    return finish(buf, out, cap);
+}
+
+/* CPU baseline of bench.py: units [unit_begin, unit_begin + n_units) of a paired-end run split evenly over `threads`
+ * std::threads, each writing FASTQ into its own buffer (allocated and touched before the clock starts).
+ *   mode 0  native: this library's restatement of the GPU's draw schedule (tables, MWC chains, sparse substitutions)
+ *   mode 1  reference stream: simmr's own plumbing — ChaCha12 StdRng re-seeded per pair, a ziggurat normal and an f32
+ *           powf per base (ref_stream.inc; minimal-short only).  Every slice seeds its own per-genome generator, as the
+ *           reference does once per genome.
+ * Returns 0 and the wall time between releasing the threads and the last one finishing. */
+int orc_bench_pe(const orc_genomes *g, const orc_profile *pi, const uint64_t *reads, uint64_t seed, uint64_t unit_begin,
+                 uint64_t n_units, int mode, int threads, double *seconds, uint64_t *bases, uint64_t *records, uint64_t *bytes) {
+    Profile p; if (!make_profile(pi, p)) return -1;
+    if (p.is_long) return fail("orc_bench_pe: paired-end profiles only");
+    if (mode == 1 && pi->kind != ORC_MINIMAL_SHORT) return fail("orc_bench_pe: the reference stream is restated for minimal-short");
+    GenomeView gv{g}; UnitMap um(reads, g->n_genomes, false); Philox ph(seed);
+    if (unit_begin + n_units > um.total()) return fail("unit range past the end");
+    if (threads < 1) threads = 1;
+    const std::string fmt = DEFAULT_HEADER;
+    const RefMinimalShort rprof{pi->read_length, pi->insert_size, pi->mean_phred};
+    std::vector<std::vector<uint8_t>> bufs(threads);
+    std::vector<orc_stats> sts(threads);
+    std::vector<int> ok(threads, 1);
+    const uint64_t per = (n_units + threads - 1) / threads;
+    const uint64_t per_unit = 2 * (256 + 2 * (uint64_t)(pi->read_length + 8 * 15) + 5);
+    for (int t = 0; t < threads; t++) { bufs[t].resize(per * per_unit); bufs[t].clear(); }     /* pages mapped before the clock */
+    std::atomic<int> go{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) th.emplace_back([&, t] {
+        while (!go.load(std::memory_order_acquire)) {}
+        const uint64_t a = unit_begin + std::min(n_units, per * t), b = unit_begin + std::min(n_units, per * (t + 1));
+        orc_stats st{};
+        if (mode == 0) ok[t] = simulate_range(gv, p, um, ph, fmt, 0, a, b, bufs[t], st);
+        else {
+            for (uint64_t u = a; u < b && ok[t];) {
+                const uint32_t gi = um.genome_of(u);
+                const uint64_t e = std::min(b, um.start[gi + 1]);
+                ChaCha12Rng rng_g = ChaCha12Rng::seed_from_u64(seed + 0x9E3779B97F4A7C15ull * u);   /* simulate.rs:172-175, per slice */
+                ok[t] = ref_stream_pairs(gv, rprof, gi, e - u, (uint32_t)u, rng_g, fmt, bufs[t], st);
+                u = e;
+            }
+        }
+        st.bytes = bufs[t].size(); sts[t] = st;
+    });
+    const auto t0 = std::chrono::steady_clock::now();
+    go.store(1, std::memory_order_release);
+    for (auto &x : th) x.join();
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    uint64_t nb = 0, nr = 0, ny = 0;
+    for (int t = 0; t < threads; t++) { if (!ok[t]) return -1; nb += sts[t].bases; nr += sts[t].records; ny += sts[t].bytes; }
+    if (seconds) *seconds = dt;
+    if (bases) *bases = nb;
+    if (records) *records = nr;
+    if (bytes) *bytes = ny;
+    return 0;
+}
+/* one ChaCha12 block (rand_chacha layout: 64-bit counter in words 12-13, stream id 0) — known-answer hook for the tests */
+void orc_chacha12_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
+    ChaCha12Rng r; memcpy(r.key, key, sizeof r.key); r.counter = counter; r.refill();
+    memcpy(out, r.buf, 64);
+}
+/* n standard-normal deviates of the restated ziggurat from StdRng::seed_from_u64(seed) */
+void orc_ref_ziggurat(uint64_t seed, uint64_t n, double *out) {
+    ChaCha12Rng r = ChaCha12Rng::seed_from_u64(seed);
+    for (uint64_t i = 0; i < n; i++) out[i] = zig().sample(r);
+}
+/* first `n` bytes of a reference-stream run (pairs [0, n_pairs) of genome 0 seeded with `seed`): lets the tests check the
+ * stream's output as FASTQ and its distributions */
+int64_t orc_ref_stream(const orc_genomes *g, const orc_profile *pi, uint64_t n_pairs, uint64_t seed, uint8_t *out, uint64_t cap, orc_stats *stp) {
+    if (pi->kind != ORC_MINIMAL_SHORT) return fail("orc_ref_stream: minimal-short only");
+    GenomeView gv{g};
+    const RefMinimalShort rprof{pi->read_length, pi->insert_size, pi->mean_phred};
+    ChaCha12Rng rng_g = ChaCha12Rng::seed_from_u64(seed);
+    std::vector<uint8_t> buf; orc_stats st{};
+    if (!ref_stream_pairs(gv, rprof, 0, n_pairs, 0, rng_g, DEFAULT_HEADER, buf, st)) return -1;
     st.bytes = buf.size();
     if (stp) *stp = st;
     return finish(buf, out, cap);

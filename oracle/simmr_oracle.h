@@ -175,6 +175,17 @@ int      orc_ref_custom_phred(const uint8_t *blob, uint64_t blob_len, uint32_t p
 int      orc_ref_custom_len(const uint8_t *blob, uint64_t blob_len, int which,
                             uint64_t n, uint64_t seed, uint16_t *out);
 
+/* CPU baseline of bench.py (paired-end): mode 0 = native draw schedule, mode 1 = the reference's own stream plumbing
+ * (ChaCha12 re-seeded per pair, ziggurat normal + f32 powf per base; ref_stream.inc), `threads` std::threads, buffers
+ * touched before the clock. */
+int      orc_bench_pe(const orc_genomes *g, const orc_profile *p, const uint64_t *reads_per_genome, uint64_t seed,
+                      uint64_t unit_begin, uint64_t n_units, int mode, int threads, double *seconds,
+                      uint64_t *bases, uint64_t *records, uint64_t *bytes);
+void     orc_chacha12_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]);
+void     orc_ref_ziggurat(uint64_t seed, uint64_t n, double *out);
+int64_t  orc_ref_stream(const orc_genomes *g, const orc_profile *p, uint64_t n_pairs, uint64_t seed,
+                        uint8_t *out, uint64_t cap, orc_stats *st);
+
 const char *orc_last_error(void);
 
 #ifdef __cplusplus

@@ -226,3 +226,7 @@ def short_read_law(table):
     mean_d = (float((gap[:255] * (np.arange(255) + 1)).sum()) + 255.0 * gap[255]) / (1.0 - gap[255])
     rate = 1.0 / mean_d
     return (1.0 - rate) * kept + rate * sub, rate
+
+
+
+from simmr_b200.synth import synthetic_genomes as config_genomes, lognormal_abundances    # noqa: E402,F401
