@@ -195,6 +195,8 @@ int  simmr_debug_phred_table(const simmr_eprofile_desc *desc, uint32_t *kind, ui
                              uint32_t *const_q, uint32_t *entries, uint64_t cap);
 int  simmr_debug_len_table(const simmr_eprofile_desc *desc, int which, uint32_t *kind, uint32_t *cb,
                            uint32_t *entries, uint32_t *lo, uint32_t *hi, uint64_t cap);
+/* custom-long alt-k-mer tables, flattened: ref, keep_thr, row, cb (n_ref words each), then entries and alts */
+int  simmr_debug_err_table(const simmr_eprofile_desc *desc, uint32_t *k, uint32_t *n_ref, uint32_t *words, uint64_t cap);
 void simmr_debug_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 const char *simmr_version(void);
 

@@ -103,6 +103,7 @@ def lib():
         L.orc_simulate.restype = C.c_int64
         L.orc_replay.restype = C.c_int64
         L.orc_ref_stream.restype = C.c_int64
+        L.orc_native_errors.restype = C.c_int64
         L.orc_fasta_num_seqs.restype = C.c_uint32
         for f in ("orc_fasta_size", "orc_fasta_seq_size", "orc_fasta_seq_len"):
             getattr(L, f).restype = C.c_uint64
@@ -184,6 +185,15 @@ class Profile:
         return dict(kind=kind.value, cb=cb.value, entries=ent[:n].copy(), lo=lo[:m].copy(), hi=hi[:m].copy())
 
 
+    def err_table(self):
+        k, n = C.c_uint32(), C.c_uint32()
+        words = np.zeros(1 << 24, np.uint32)
+        m = lib().orc_profile_err_table(C.byref(self.c), C.byref(k), C.byref(n), _p(words, u32p), C.c_uint64(len(words)))
+        if m < 0:
+            raise RuntimeError(err())
+        return dict(k=k.value, n_ref=n.value, words=words[:m].copy())
+
+
 def total_units(profile, reads_per_genome):
     r = np.ascontiguousarray(reads_per_genome, np.uint64)
     return lib().orc_total_units(C.byref(profile.c), _p(r, u64p), len(r))
@@ -236,6 +246,46 @@ def ref_stream(genomes, profile, n_pairs, seed):
     if n < 0:
         raise RuntimeError(err())
     return buf[:n].tobytes(), st
+
+
+def native_errors(profile, seed, unit, seq):
+    """k-mer error injection of native mode on `seq` as read `unit` of a run seeded `seed` -> (new sequence, choices):
+    `choices` is what orc_simulate_errors (the reference loop with explicit alias picks) needs to give the same bytes."""
+    a = np.frombuffer(bytes(seq), np.uint8)
+    out = np.empty(len(a) + 16, np.uint8)
+    ch = np.empty(len(a) + 16, np.uint32)
+    nch = C.c_uint64()
+    n = lib().orc_native_errors(C.byref(profile.c), C.c_uint64(seed), C.c_uint64(unit), _p(a, u8p), C.c_uint64(len(a)),
+                                _p(out, u8p), C.c_uint64(len(out)), _p(ch, u32p), C.c_uint64(len(ch)), C.byref(nch))
+    if n < 0:
+        raise RuntimeError(err())
+    return out[:n].tobytes(), ch[:nch.value].copy()
+
+
+def native_error_first_picks(profile, seed, unit0, n_units, seq):
+    """The first pick of each of n_units consecutive reads over the same sequence (for distribution tests)."""
+    a = np.frombuffer(bytes(seq), np.uint8)
+    ch = np.empty(n_units, np.uint32)
+    if lib().orc_native_errors(C.byref(profile.c), C.c_uint64(seed), C.c_uint64(unit0), _p(a, u8p), C.c_uint64(len(a)),
+                               None, C.c_uint64(n_units), _p(ch, u32p), C.c_uint64(n_units), None) < 0:
+        raise RuntimeError(err())
+    return ch
+
+
+def simulate_errors(seq, k, kmers, choices):
+    """orc_simulate_errors: custom_long.rs:187-232 with the alias picks supplied; kmers = [(ref_code, [(alt_code, w)])]."""
+    a = np.frombuffer(bytes(seq), np.uint8)
+    ref = np.array([r for r, _ in kmers], np.uint32)
+    off = np.zeros(len(kmers) + 1, np.uint32)
+    off[1:] = np.cumsum([len(al) for _, al in kmers])
+    alts = np.array([c for _, al in kmers for c, _ in al], np.uint32)
+    ch = np.ascontiguousarray(choices, np.uint32)
+    out = np.empty(len(a) + 16, np.uint8)
+    n = lib().orc_simulate_errors(_p(a, u8p), C.c_uint64(len(a)), int(k), _p(ref, u32p), _p(off, u32p), _p(alts, u32p),
+                                  len(kmers), _p(ch, u32p), C.c_uint64(len(ch)), _p(out, u8p), C.c_uint64(len(out)))
+    if n < 0:
+        raise RuntimeError(err())
+    return out[:n].tobytes()
 
 
 def native_geometry(genomes, profile, reads_per_genome, seed, unit_begin=0, unit_end=0):

@@ -444,6 +444,61 @@ struct LenTable {
     std::vector<uint32_t> lo, hi;    /* per column */
 };
 
+/* k-mer error injection (custom_long.rs:187-232 == custom_short.rs:452-516), native tables: per observed
+ * reference k-mer the chance that the sampled alternate is the k-mer itself, as a 32-bit threshold on a draw's level, and
+ * an alias row (entry = thr20<<12 | alias12, as the length tables) over the other alternates.  Rows are padded to
+ * 1 << cb columns in both `entries` and `alts`, so one offset addresses both. */
+struct ErrTable {
+    bool on = false;
+    uint32_t k = 0;
+    std::vector<uint32_t> ref;        /* distinct reference k-mers (3-bit codes), ascending */
+    std::vector<uint32_t> keep_thr, row, cb;
+    std::vector<uint32_t> entries, alts;
+    /* for the tests: position in the blob's alternate list of (a) the first alternate equal to the k-mer, (b) every other alternate in row order */
+    std::vector<uint32_t> blob_entry, id_choice; std::vector<std::vector<uint32_t>> other_choice;
+    int find(uint32_t code) const { auto it = std::lower_bound(ref.begin(), ref.end(), code); return it != ref.end() && *it == code ? int(it - ref.begin()) : -1; }
+};
+bool build_err_table(const Blob &b, ErrTable &t) {
+    t = ErrTable();
+    if (b.probs.empty()) return true;
+    if (b.bit_encoding != 3 || b.kmer_size < 1 || b.kmer_size > 10) return false;      /* simmrd/src/main.rs:382, cli.rs:146-156 */
+    t.k = (uint32_t)b.kmer_size; t.on = true;
+    const uint32_t mask = t.k == 10 ? 0x3fffffffu : ((1u << (3 * t.k)) - 1u);
+    std::map<uint32_t, uint32_t> last;                       /* HashMap collect(): the last entry of a k-mer wins */
+    for (uint32_t i = 0; i < b.probs.size(); i++) last[b.probs[i].first] = i;
+    for (auto &kv : last) {
+        const auto &alts = b.probs[kv.second].second;
+        double w_id = 0.0, w_all = 0.0; std::vector<double> w_other; std::vector<uint32_t> c_other, ch_other; uint32_t id_at = UINT32_MAX;
+        for (uint32_t j = 0; j < alts.size(); j++) {
+            const uint32_t code = alts[j].first & mask;
+            for (uint32_t d = 0; d < t.k; d++) if (((code >> (3 * d)) & 7u) > 4u) return false;     /* decode_kmer would fail (encoding.rs:205) */
+            const double w = (double)alts[j].second;
+            if (!(w >= 0.0)) return false;
+            w_all += w;
+            if (code == (kv.first & mask)) { w_id += w; if (id_at == UINT32_MAX) id_at = j; }
+            else if (w > 0.0) { w_other.push_back(w); c_other.push_back(code); ch_other.push_back(j); }
+        }
+        if (!(w_all > 0.0)) continue;                        /* WeightedAliasIndex::new would fail: treated as "not observed" */
+        if (w_other.size() > 4096) return false;
+        t.ref.push_back(kv.first); t.blob_entry.push_back(kv.second); t.id_choice.push_back(id_at); t.other_choice.push_back(ch_other);
+        t.row.push_back((uint32_t)t.entries.size());
+        if (w_other.empty()) {                               /* always the k-mer itself */
+            t.keep_thr.push_back(0xffffffffu); t.cb.push_back(0);
+            t.entries.push_back(0xfffff000u); t.alts.push_back(kv.first & mask);
+            continue;
+        }
+        t.keep_thr.push_back(quant_thr(w_id / w_all, 32));
+        const uint32_t cb = ceil_log2(w_other.size());
+        t.cb.push_back(cb);
+        std::vector<uint32_t> e;
+        if (!build_len_alias(w_other, cb, e)) return false;
+        t.entries.insert(t.entries.end(), e.begin(), e.end());
+        for (uint32_t j = 0; j < (1u << cb); j++) t.alts.push_back(j < c_other.size() ? c_other[j] : (kv.first & mask));
+    }
+    if (t.ref.empty()) t.on = false;
+    return true;
+}
+
 struct Profile {
     int kind = 0;
     uint16_t read_length = 150, insert_size = 150;
@@ -454,6 +509,7 @@ struct Profile {
     uint16_t min_size = 0;
     PhredTable phred;
     LenTable rl, is;
+    ErrTable err;                    /* custom-long: k-mer error injection */
     /* replay helpers */
     std::vector<RustAlias> q_alias;
 };
@@ -633,6 +689,7 @@ bool make_profile(const orc_profile *in, Profile &p) {
     case ORC_CUSTOM_LONG: {   /* phreds as custom-short, gamma lengths */
         p.is_long = true; p.mutates = false; p.min_size = 20000;
         if (!phred_table_from_blob(p.blob, p.phred)) { fail("custom phred table"); return false; }
+        if (!build_err_table(p.blob, p.err)) { fail("bad k-mer table in the custom profile"); return false; }
         p.rl.kind = 2; p.is.kind = 0; p.is.value = 0;
         break; }
     default: fail("unknown profile kind"); return false;
@@ -885,6 +942,53 @@ void native_read(const Profile &p, const Philox &ph, uint64_t u, uint32_t stream
     }
 }
 
+/* simulate_errors in native mode (custom_long.rs:187-232).  The reference walks i over the ORIGINAL length, looks at the
+ * k bytes at i of the sequence as edited so far, and splices the sampled alternate in (an alternate's N digits are deleted
+ * bases).  Everything before i is final and everything from i + k on is still the original's tail, so the state is the k
+ * bytes under the window (`win`) and how far into the original they reach (`r`).  One draw of the read's error chain
+ * (Philox block 0 of stream 3) per window, used or not.  Where the reference would index past the shortened sequence
+ * (and panic) the walk stops.  `choices`, when given, receives what orc_simulate_errors' `choice` array must hold to
+ * reproduce the run (the alternate's position in the blob's list, one per window that had alternates). */
+void native_errors(const Profile &p, const Philox &ph, uint64_t u, const std::vector<uint8_t> &orig, std::vector<uint8_t> &out,
+                   std::vector<uint32_t> *choices = nullptr) {
+    const ErrTable &t = p.err;
+    const size_t L = orig.size(), k = t.k;
+    out.clear();
+    uint32_t w[4]; ph.at(u, 3, 0, w);
+    Chain ch(w[0], w[1]);
+    ch.next();                                                                 /* a fresh chain's carry has 30 bits: one step fills it */
+    std::vector<uint8_t> win; size_t r = 0;
+    for (size_t i = 0; i + k <= L; i++) {                                      /* :196-199 */
+        while (win.size() < k && r < L) win.push_back(orig[r++]);
+        if (win.size() < k) break;                                             /* the reference would panic here */
+        const Draw d = ch.next();
+        uint32_t code;
+        if (kmer_encode(win.data(), (uint32_t)k, 3, &code) == 0) {             /* :203-207 */
+            const int row = t.find(code);
+            if (row >= 0) {                                                    /* :210-213 */
+                uint32_t alt = code, choice = t.id_choice[row];
+                if (d.level >= t.keep_thr[row]) {
+                    const uint32_t cb = t.cb[row], wd = d.word;
+                    const uint32_t idx = cb ? wd >> (32 - cb) : 0u, frac = (uint32_t)(((uint64_t)wd << cb) & 0xffffffffu) >> 12;
+                    const uint32_t e = t.entries[t.row[row] + idx], j = frac < (e >> 12) ? idx : (e & 0xfffu);
+                    alt = t.alts[t.row[row] + j];
+                    if (j < t.other_choice[row].size()) choice = t.other_choice[row][j];
+                }
+                if (choices) choices->push_back(choice);
+                if (alt != code) {                                             /* :221-228 decode with the N digits skipped, splice */
+                    uint8_t dec[16]; const int n = kmer_decode(alt, (uint32_t)k, 3, true, dec);
+                    win.assign(dec, dec + n);
+                }
+            }
+        }
+        if (win.empty() && r < L) win.push_back(orig[r++]);
+        if (win.empty()) break;
+        out.push_back(win.front()); win.erase(win.begin());
+    }
+    out.insert(out.end(), win.begin(), win.end());
+    out.insert(out.end(), orig.begin() + r, orig.end());
+}
+
 int64_t finish(std::vector<uint8_t> &buf, uint8_t *out, uint64_t cap) {
     if (out) { if (buf.size() > cap) return -(int64_t)buf.size(); memcpy(out, buf.data(), buf.size()); }
     return (int64_t)buf.size();
@@ -991,7 +1095,7 @@ int64_t orc_simulate_errors(const uint8_t *seq, uint64_t n, uint32_t k, const ui
     uint64_t used = 0;
     for (uint64_t i = 0; i < n; i++) {
         if (i + k > n) break;                                        /* :197-199 */
-        if (i + k > ns.size()) return fail("window past end (reference would panic)");
+        if (i + k > ns.size()) break;                               /* the reference would panic (unguarded slice): the walk stops, as in native mode */
         uint32_t enc;
         if (kmer_encode(ns.data() + i, k, 3, &enc) != 0) continue;   /* :203-207 */
         auto it = idx.find(enc);
@@ -1056,6 +1160,16 @@ int orc_profile_phred_table(const orc_profile *pi, uint32_t *kind, uint32_t *cb,
     if (p.phred.has_sub) { all.insert(all.end(), p.phred.gap.begin(), p.phred.gap.end()); all.insert(all.end(), p.phred.qsub.begin(), p.phred.qsub.end()); }
     if (all.size() > cap) return fail("table buffer too small");
     if (!all.empty()) memcpy(entries, all.data(), all.size() * 4);
+    return (int)all.size();
+}
+int orc_profile_err_table(const orc_profile *pi, uint32_t *k, uint32_t *n_ref, uint32_t *words, uint64_t cap) {
+    Profile p; if (!make_profile(pi, p)) return -1;
+    const ErrTable &e = p.err;
+    *k = e.on ? e.k : 0; *n_ref = (uint32_t)e.ref.size();
+    std::vector<uint32_t> all;
+    for (const std::vector<uint32_t> *v : {&e.ref, &e.keep_thr, &e.row, &e.cb, &e.entries, &e.alts}) all.insert(all.end(), v->begin(), v->end());
+    if (all.size() > cap) return fail("buffer too small");
+    if (!all.empty()) memcpy(words, all.data(), all.size() * 4);
     return (int)all.size();
 }
 int orc_profile_len_table(const orc_profile *pi, int which, uint32_t *kind, uint32_t *cb, uint32_t *entries, uint32_t *lo, uint32_t *hi, uint64_t cap) {
@@ -1177,6 +1291,7 @@ static bool simulate_range(const GenomeView &gv, const Profile &p, const UnitMap
             st.records += 2; st.bases += s1.size() + s2.size();
         } else {
             native_read(p, ph, u, 1, cs + ng.ls, ng.le - ng.ls, s1, q1, st);           /* :494-503 */
+            if (p.err.on) { native_errors(p, ph, u, s1, s2); s1.swap(s2); }            /* :500, before the (identity) point mutations :503 */
             emit_record(buf, fmt, gid, id, sid, ng.ls, ng.le, false, 1, s1, q1);       /* fastq.rs:57: {:pair:} -> 1 */
             st.records += 1; st.bases += s1.size();
         }
@@ -1251,6 +1366,26 @@ int orc_bench_pe(const orc_genomes *g, const orc_profile *pi, const uint64_t *re
     if (records) *records = nr;
     if (bytes) *bytes = ny;
     return 0;
+}
+/* native-mode k-mer error injection of one read (unit `unit` of a run seeded `seed`) on an arbitrary sequence, with the
+ * choices orc_simulate_errors needs to reproduce it */
+int64_t orc_native_errors(const orc_profile *pi, uint64_t seed, uint64_t unit, const uint8_t *seq, uint64_t n,
+                          uint8_t *out, uint64_t cap, uint32_t *choices, uint64_t choice_cap, uint64_t *n_choices) {
+    Profile p; if (!make_profile(pi, p)) return -1;
+    if (!p.err.on) return fail("profile has no k-mer table");
+    Philox ph(seed);
+    std::vector<uint8_t> o; std::vector<uint32_t> ch;
+    const std::vector<uint8_t> src(seq, seq + n);
+    if (!out) {      /* law of the picks: `cap` consecutive units on the same sequence, the first pick of each into choices */
+        for (uint64_t i = 0; i < cap && i < choice_cap; i++) { ch.clear(); native_errors(p, ph, unit + i, src, o, &ch); choices[i] = ch.empty() ? UINT32_MAX : ch[0]; }
+        return 0;
+    }
+    native_errors(p, ph, unit, src, o, &ch);
+    if (o.size() > cap || ch.size() > choice_cap) return fail("orc_native_errors: buffer too small");
+    if (!o.empty()) memcpy(out, o.data(), o.size());
+    if (!ch.empty()) memcpy(choices, ch.data(), ch.size() * 4);
+    if (n_choices) *n_choices = ch.size();
+    return (int64_t)o.size();
 }
 /* one ChaCha12 block (rand_chacha layout: 64-bit counter in words 12-13, stream id 0) — known-answer hook for the tests */
 void orc_chacha12_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {

@@ -120,6 +120,7 @@ int      orc_profile_is_long(const orc_profile *p, int *out);
 /* quantised alias tables the native mode samples from */
 int      orc_profile_phred_table(const orc_profile *p, uint32_t *kind, uint32_t *cb, uint32_t *npos,
                                  uint32_t *const_q, uint32_t *entries, uint64_t cap);
+int      orc_profile_err_table(const orc_profile *p, uint32_t *k, uint32_t *n_ref, uint32_t *words, uint64_t cap);
 int      orc_profile_len_table(const orc_profile *p, int which /*0=RL,1=IS*/,
                                uint32_t *kind, uint32_t *cb, uint32_t *entries,
                                uint32_t *lo, uint32_t *hi, uint64_t cap);
@@ -181,6 +182,8 @@ int      orc_ref_custom_len(const uint8_t *blob, uint64_t blob_len, int which,
 int      orc_bench_pe(const orc_genomes *g, const orc_profile *p, const uint64_t *reads_per_genome, uint64_t seed,
                       uint64_t unit_begin, uint64_t n_units, int mode, int threads, double *seconds,
                       uint64_t *bases, uint64_t *records, uint64_t *bytes);
+int64_t  orc_native_errors(const orc_profile *p, uint64_t seed, uint64_t unit, const uint8_t *seq, uint64_t n,
+                           uint8_t *out, uint64_t cap, uint32_t *choices, uint64_t choice_cap, uint64_t *n_choices);
 void     orc_chacha12_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]);
 void     orc_ref_ziggurat(uint64_t seed, uint64_t n, double *out);
 int64_t  orc_ref_stream(const orc_genomes *g, const orc_profile *p, uint64_t n_pairs, uint64_t seed,

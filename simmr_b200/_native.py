@@ -69,7 +69,7 @@ EXPORTS = [
     "simmr_total_units", "simmr_measure", "simmr_stats_get", "simmr_builder_create", "simmr_builder_destroy",
     "simmr_builder_add_fasta", "simmr_builder_filter", "simmr_builder_view", "simmr_builder_genome_size",
     "simmr_builder_error", "simmr_parse_genome_file", "simmr_write_metadata", "simmr_debug_phred_table",
-    "simmr_debug_len_table", "simmr_debug_philox4x32_10", "simmr_version",
+    "simmr_debug_len_table", "simmr_debug_err_table", "simmr_debug_philox4x32_10", "simmr_version",
 ]
 
 _lib = None
@@ -116,6 +116,7 @@ def lib():
         L.simmr_write_metadata.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), u64p, f64p]
         L.simmr_debug_phred_table.argtypes = [C.POINTER(EProfileDesc), u32p, u32p, u32p, u32p, u32p, C.c_uint64]  # kind, cb, npos, const_q
         L.simmr_debug_len_table.argtypes = [C.POINTER(EProfileDesc), C.c_int, u32p, u32p, u32p, u32p, u32p, C.c_uint64]
+        L.simmr_debug_err_table.argtypes = [C.POINTER(EProfileDesc), u32p, u32p, u32p, C.c_uint64]
         L.simmr_debug_philox4x32_10.argtypes = [u32p, u32p, u32p]
         L.simmr_debug_philox4x32_10.restype = None
         _lib = L

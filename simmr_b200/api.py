@@ -89,6 +89,15 @@ class ErrorProfile:
         return dict(kind=kind.value, cb=cb.value, entries=ent[:n].copy(), lo=lo[:m].copy(), hi=hi[:m].copy())
 
 
+    def err_table(self):
+        """Alt-k-mer sampling tables of a custom-long blob, flattened; k == 0 when the blob has none."""
+        k, n = C.c_uint32(), C.c_uint32()
+        words = np.zeros(1 << 24, np.uint32)
+        d = self.desc()
+        m = _check(N.lib().simmr_debug_err_table(C.byref(d), C.byref(k), C.byref(n), _p(words, N.u32p), len(words)))
+        return dict(k=k.value, n_ref=n.value, words=words[:m].copy())
+
+
 class PerfectShortErrorProfile(ErrorProfile):      # perfect_short.rs
     kind = N.EP_PERFECT_SHORT
 

@@ -97,6 +97,18 @@ int simmr_debug_len_table(const simmr_eprofile_desc *d, int which, uint32_t *kin
     memcpy(lo, t.lo.data(), t.lo.size() * 4); memcpy(hi, t.hi.data(), t.hi.size() * 4);
     return int(t.entries.size());
 }
+int simmr_debug_err_table(const simmr_eprofile_desc *d, uint32_t *k, uint32_t *n_ref, uint32_t *words, uint64_t cap) {
+    ProfileModel m; std::string err;
+    const int rc = build_profile(d, m, err);
+    if (rc) return flunk(rc, err);
+    const ErrModel &e = m.err;
+    *k = e.on ? e.k : 0; *n_ref = uint32_t(e.ref.size());
+    std::vector<uint32_t> all;
+    for (const std::vector<uint32_t> *v : {&e.ref, &e.keep_thr, &e.row, &e.cb, &e.entries, &e.alts}) all.insert(all.end(), v->begin(), v->end());
+    if (all.size() > cap) return flunk(SIMMR_E_INVALID, "buffer too small");
+    if (!all.empty()) memcpy(words, all.data(), all.size() * 4);
+    return int(all.size());
+}
 void simmr_debug_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_10(ctr, key, out); }
 
 }  // extern "C"

@@ -41,7 +41,7 @@ struct ReplayDev {                 /* device copies of simmr_draws + replay LUTs
 /* long reads are cut into LONG_PIECES pieces of a multiple of 16 bases, each with its own chains: the 32 lanes' work in k_format_long */
 constexpr uint32_t LONG_PIECES = 32;
 constexpr uint32_t LONG_RING = 8, LONG_AHEAD = 5;   /* k_format_long: words of the 2-bit copy per lane in shared memory, and how far ahead they are fetched */
-struct UnitDesc;
+struct UnitRec; struct UnitExt;
 struct RunParams {
     /* genomes (device resident) */
     const uint8_t *bases; const uint64_t *contig_off, *contig_size; const uint32_t *genome_contig;
@@ -59,7 +59,10 @@ struct RunParams {
     uint32_t rk[20];               /* Philox round keys: seed + r * Weyl constants, r = 0..9 */
     /* per-batch scratch + output */
     uint32_t *sizes; uint64_t *offsets, *block_sums; uint8_t *out;
-    struct UnitDesc *desc;         /* per-unit geometry written by k_unit_sizes, read by the format kernels */
+    struct UnitRec *desc;          /* per-unit geometry written by k_unit_sizes, read by the format kernels (32 bytes) */
+    struct UnitExt *desc_ext;      /* what does not fit a UnitRec (clamped windows, positions above 2^32): written and read for flagged units only */
+    /* k_format_lanes takes its tiles from segments of SEG_UNITS units whose units k_segment_sort ordered by size */
+    uint16_t *seg_perm, *seg_tiles; uint32_t *seg_ntiles;
     unsigned long long *counters;  /* [0] clamped [1] algorithmic bytes [2] bases [3] records */
     /* per-warp stage of k_format_lanes */
     uint32_t stage_cap;            /* bytes of a warp's stage in k_format_lanes */
@@ -195,15 +198,39 @@ struct UnitGeo {
     uint32_t rl, pad_;    /* drawn read length (replay slots of mate 2 start rl after mate 1) */
 };
 
-/* what the format kernels need of a unit: 48 bytes written once by k_unit_sizes */
-struct __align__(16) UnitDesc {
+/* what the format kernels need of a unit, in registers */
+struct UnitDesc {
     uint64_t a0, a1;       /* window offsets in `bases`                                     */
     uint64_t p0, p1;       /* PE: fwd_start, rev_end (simulate.rs:233,241-258); long: start, end */
     uint32_t contig;
     uint16_t rl, L0, L1, H0, H1;
-    uint16_t flags;        /* 1: window 0 impure, 2: window 1 impure, 4: two records        */
+    uint16_t flags;        /* 1: window 0 impure, 2: window 1 impure, 4: two records, 8: a position needs more than 32 bits, 16: UnitExt holds a1, p0, p1 */
 };
-static_assert(sizeof(UnitDesc) == 48, "UnitDesc layout");
+/* ... and in memory: 32 bytes per unit (one sector), written once by k_unit_sizes.  Window 1 starts at a0 - p0 + p1
+ * unless a window was clamped at its contig's end; such units, and units of contigs beyond 2^32 bases, also have a UnitExt. */
+struct __align__(16) UnitRec {
+    uint64_t a0;
+    uint32_t p0, p1;
+    uint32_t contig;
+    uint16_t rl, L0, L1, H0, H1, flags;
+};
+struct __align__(16) UnitExt { uint64_t a1, p0, p1, pad_; };
+static_assert(sizeof(UnitRec) == 32 && sizeof(UnitExt) == 32, "descriptor layout");
+__device__ __forceinline__ UnitDesc load_unit(const RunParams &rp, uint32_t i) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(rp.desc + i);
+    const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+    UnitDesc d;
+    d.a0 = pair64(v0.x, v0.y); d.p0 = v0.z; d.p1 = v0.w;
+    d.contig = v1.x; d.rl = uint16_t(v1.y); d.L0 = uint16_t(v1.y >> 16); d.L1 = uint16_t(v1.z); d.H0 = uint16_t(v1.z >> 16);
+    d.H1 = uint16_t(v1.w); d.flags = uint16_t(v1.w >> 16);
+    d.a1 = d.a0 - d.p0 + d.p1;
+    if (d.flags & 16u) {
+        const uint4 *e = reinterpret_cast<const uint4 *>(rp.desc_ext + i);
+        const uint4 e0 = __ldg(e), e1 = __ldg(e + 1);
+        d.a1 = pair64(e0.x, e0.y); d.p0 = pair64(e0.z, e0.w); d.p1 = pair64(e1.x, e1.y);
+    }
+    return d;
+}
 
 template <bool REPLAY>
 __device__ void unit_geometry(const RunParams &rp, const ReplayDev &rd, uint64_t u, uint32_t g_lo, uint32_t g_hi, UnitGeo &o) {
@@ -466,6 +493,9 @@ __device__ __forceinline__ void emit_body_replay(const RunParams &rp, const Repl
 }
 
 __device__ __forceinline__ uint32_t lds32m(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds16m(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint2 lds64m(uint32_t addr) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ uint32_t lds16(uint32_t addr) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 
 /* ---------------------------------------------------------------------- */
@@ -601,15 +631,19 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, Repl
         }
         clamped = g.clamped; recs = g.nrec;
         rp.sizes[i] = uint32_t(bytes);
-        UnitDesc d;
-        d.a0 = g.a[0]; d.a1 = g.a[1];
-        d.p0 = g.sp[0]; d.p1 = g.nrec == 2 ? g.ep[1] : g.ep[0];
-        d.contig = g.contig; d.rl = uint16_t(g.rl); d.L0 = uint16_t(g.L[0]); d.L1 = uint16_t(g.L[1]);
-        d.H0 = uint16_t(H[0]); d.H1 = uint16_t(H[1]);
-        d.flags = uint16_t((REPLAY || window_impure(rp, g.a[0], g.L[0]) ? 1u : 0u) |
-                           (REPLAY || window_impure(rp, g.a[1], g.L[1]) ? 2u : 0u) | (g.nrec == 2 ? 4u : 0u) |
-                           ((big >> 32) ? 8u : 0u));             /* 8: a position needs more than 32 bits */
-        rp.desc[i] = d;
+        const uint64_t p0 = g.sp[0], p1 = g.nrec == 2 ? g.ep[1] : g.ep[0];
+        const bool ext = (big >> 32) != 0 || g.clamped != 0;
+        const uint32_t flags = (REPLAY || window_impure(rp, g.a[0], g.L[0]) ? 1u : 0u) |
+                               (REPLAY || window_impure(rp, g.a[1], g.L[1]) ? 2u : 0u) | (g.nrec == 2 ? 4u : 0u) |
+                               ((big >> 32) ? 8u : 0u) | (ext ? 16u : 0u);    /* 8: a position needs more than 32 bits */
+        uint4 *dst = reinterpret_cast<uint4 *>(rp.desc + i);
+        dst[0] = make_uint4(uint32_t(g.a[0]), uint32_t(g.a[0] >> 32), uint32_t(p0), uint32_t(p1));
+        dst[1] = make_uint4(g.contig, (g.rl & 0xffffu) | (g.L[0] << 16), (g.L[1] & 0xffffu) | (H[0] << 16), (H[1] & 0xffffu) | (flags << 16));
+        if (ext) {
+            uint4 *e = reinterpret_cast<uint4 *>(rp.desc_ext + i);
+            e[0] = make_uint4(uint32_t(g.a[1]), uint32_t(g.a[1] >> 32), uint32_t(p0), uint32_t(p0 >> 32));
+            e[1] = make_uint4(uint32_t(p1), uint32_t(p1 >> 32), 0u, 0u);
+        }
     }
     /* block totals of the five counters: warp sums, one barrier, then five lanes of warp 0 finish (a block's totals fit 32 bits) */
     uint32_t v[5] = {uint32_t(bytes), uint32_t(alg), uint32_t(bases), uint32_t(clamped), uint32_t(recs)};
@@ -674,6 +708,113 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_offsets(RunParams rp) {
     if (i < rp.batch_units) rp.offsets[i] = rp.block_sums[blockIdx.x] + before + x - v;
 }
 
+
+/* Short reads: byte offsets of a segment's SEG_UNITS units (what k_unit_offsets does) and the order in which
+ * k_format_lanes takes them.  A warp of the format kernel runs for its longest record, so the units of a tile should be
+ * equally long: the segment's units are counting-sorted by their FASTQ bytes (256 bins over the segment's range) and cut
+ * into tiles of consecutive sorted units — at most WARP_UNITS of them, and no more than fit a warp's stage, where every
+ * unit sits at its global offset modulo 16 (slot = bytes rounded up to the 16-byte grid around it).  Every unit is
+ * stored at its own offset, so the order changes nothing in the output.
+ *   seg_perm[seg * SEG_UNITS + r]   unit (index inside the segment) at sorted rank r
+ *   seg_tiles[seg * SEG_UNITS + k]  rank at which tile k starts; seg_ntiles[seg] tiles */
+constexpr uint32_t SEG_UNITS = 1024, SEG_THREADS = 256, SEG_PER = SEG_UNITS / SEG_THREADS;
+constexpr uint32_t WARP_UNITS = 16;
+static_assert(SEG_PER * SIZES_THREADS == SEG_UNITS && SEG_THREADS == SIZES_THREADS, "a segment is SEG_PER blocks of k_unit_sizes");
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t *warp_tot, uint32_t &total) {   /* SEG_THREADS threads; two barriers */
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    __syncthreads();                                   /* warp_tot may still be read from the previous scan */
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < SEG_THREADS / 32; ++w) { const uint32_t t = warp_tot[w]; all += t; if (w < wid) before += t; }
+    total = all;
+    return before + x - v;
+}
+__global__ void __launch_bounds__(SEG_THREADS) k_segment_sort(RunParams rp) {
+    __shared__ uint32_t warp_tot[SEG_THREADS / 32], hist[256], slot_s[SEG_UNITS], pre_s[SEG_UNITS + 1], red[2][SEG_THREADS / 32];
+    __shared__ uint16_t perm_s[SEG_UNITS], next_s[SEG_UNITS], tile_s[SEG_UNITS];
+    __shared__ uint32_t ntile_s;
+    const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const uint32_t seg0 = blockIdx.x * SEG_UNITS, n = min(SEG_UNITS, rp.batch_units - seg0);
+    /* 1. sizes -> offsets, block by block of k_unit_sizes (thread t takes unit j * 256 + t of the segment) */
+    uint32_t sz[SEG_PER], lead[SEG_PER], mn = 0xffffffffu, mx = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < SEG_PER; ++j) {
+        const uint32_t u = j * SEG_THREADS + t;
+        sz[j] = u < n ? rp.sizes[seg0 + u] : 0u;
+        uint32_t tot;
+        const uint32_t before = block_scan_excl(sz[j], warp_tot, tot);
+        lead[j] = 0;
+        if (u < n) {
+            const uint64_t off = rp.block_sums[blockIdx.x * SEG_PER + j] + before;
+            rp.offsets[seg0 + u] = off;
+            lead[j] = uint32_t(off) & 15u;
+            mn = min(mn, sz[j]); mx = max(mx, sz[j]);
+        }
+    }
+    /* 2. the segment's size range -> 256 bins */
+    mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) { red[0][wid] = mn; red[1][wid] = mx; }
+    hist[t] = 0;
+    __syncthreads();
+#pragma unroll
+    for (uint32_t w = 0; w < SEG_THREADS / 32; ++w) { mn = min(mn, red[0][w]); mx = max(mx, red[1][w]); }
+    const uint32_t span = mx - mn, sh = span < 256u ? 0u : 24u - __clz(span);     /* (span >> sh) <= 255 */
+    uint32_t bin[SEG_PER];
+#pragma unroll
+    for (uint32_t j = 0; j < SEG_PER; ++j) if (j * SEG_THREADS + t < n) {
+        bin[j] = (rp.flags & 0x400u) ? (j * SEG_THREADS + t) >> 2 : (sz[j] - mn) >> sh;      /* SIMMR_DBG=4: the units' own order (experiment) */
+        atomicAdd(&hist[bin[j]], 1u);
+    }
+    __syncthreads();
+    uint32_t tot;
+    const uint32_t mine = hist[t], start = block_scan_excl(mine, warp_tot, tot);
+    __syncthreads();
+    hist[t] = start;
+    __syncthreads();
+    /* 3. rank of every unit (any order inside a bin), its stage slot at that rank */
+#pragma unroll
+    for (uint32_t j = 0; j < SEG_PER; ++j) if (j * SEG_THREADS + t < n) {
+        const uint32_t r = atomicAdd(&hist[bin[j]], 1u);
+        perm_s[r] = uint16_t(j * SEG_THREADS + t);
+        slot_s[r] = (lead[j] + sz[j] + 15u) & ~15u;
+    }
+    __syncthreads();
+    /* 4. prefix of the slots in sorted order (thread t: ranks 4t .. 4t+3) */
+    uint32_t sl[SEG_PER], sum = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < SEG_PER; ++j) { const uint32_t r = SEG_PER * t + j; sl[j] = r < n ? slot_s[r] : 0u; sum += sl[j]; }
+    uint32_t run = block_scan_excl(sum, warp_tot, tot);
+#pragma unroll
+    for (uint32_t j = 0; j < SEG_PER; ++j) { pre_s[SEG_PER * t + j] = run; run += sl[j]; }
+    if (t == SEG_THREADS - 1) pre_s[SEG_UNITS] = run;
+    __syncthreads();
+    /* 5. where the tile that starts at rank r ends: at most WARP_UNITS units, slots within the stage (a single unit always fits) */
+#pragma unroll
+    for (uint32_t j = 0; j < SEG_PER; ++j) {
+        const uint32_t r = SEG_PER * t + j;
+        if (r < n) {
+            uint32_t e = r + 1;
+            const uint32_t base = pre_s[r], last = min(n, r + WARP_UNITS);
+            while (e < last && pre_s[e + 1] - base <= rp.stage_cap) ++e;
+            next_s[r] = uint16_t(e);
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        uint32_t k = 0;
+        for (uint32_t r = 0; r < n; r = next_s[r]) tile_s[k++] = uint16_t(r);
+        ntile_s = k;
+        rp.seg_ntiles[blockIdx.x] = k;
+    }
+    __syncthreads();
+    for (uint32_t r = t; r < n; r += SEG_THREADS) rp.seg_perm[seg0 + r] = perm_s[r];
+    for (uint32_t k = t; k < ntile_s; k += SEG_THREADS) rp.seg_tiles[seg0 + k] = tile_s[k];
+}
 
 /* ---------------------------------------------------------------------- */
 /* short reads, word path: one lane per record                              */
@@ -757,9 +898,11 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
             cs[h] = __funnelshift_l(prev_s, sw, sh_s); cq[h] = QM == QM_CONST ? qconst : __funnelshift_l(prev_q, qw, sh_q);
             prev_s = sw; prev_q = qw;
         }
-        if (WHOLE) {                                   /* no per-word tests */
+        if (WHOLE) {                                   /* no per-word tests (a lane without a record stores nothing at all) */
+            if (on) {
 #pragma unroll
-            for (uint32_t h = 0; h < G; ++h) { sts32(ps + 4u * h, cs[h]); sts32(pq + 4u * h, cq[h]); }
+                for (uint32_t h = 0; h < G; ++h) { sts32(ps + 4u * h, cs[h]); sts32(pq + 4u * h, cq[h]); }
+            }
         } else {
 #pragma unroll
             for (uint32_t h = 0; h < G; ++h) {
@@ -770,8 +913,8 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
         ps += 4u * G; pq += 4u * G; ns -= int32_t(G); nq -= int32_t(G);
     };
     const uint32_t full = (T4 - 1u) >> 2;              /* T4 >= 1 */
-    /* turns during which every lane of the warp stores whole groups in both lines: the shortest record's */
-    const uint32_t whole = min(full, __reduce_min_sync(0xffffffffu, uint32_t(min(ns, nq)) >> 2));
+    /* turns during which every lane that has a record stores whole groups in both lines: the shortest record's */
+    const uint32_t whole = min(full, __reduce_min_sync(0xffffffffu, on ? uint32_t(min(ns, nq)) >> 2 : 0xffffffffu));
     uint32_t it = 0;
     for (; it < whole; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::true_type{}, it);
     for (; it < full; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, it);
@@ -810,15 +953,15 @@ __device__ __forceinline__ void substitutions_lane(const RunParams &rp, uint32_t
     }
 }
 
-/* Persistent warps, one lane per record.  A warp owns WARP_UNITS consecutive units (32 records) at a time: it composes
- * their FASTQ bytes in its private stage in shared memory and sends them off with one bulk async copy (TMA); only the
- * tables are shared by the CTA, so there is no CTA barrier in the loop.  A group of units whose bytes exceed the stage is
- * cut into sub-tiles.  Lane 2k + m holds mate m of unit k.
+/* Persistent warps, one lane per record.  A CTA takes whole segments of SEG_UNITS units; a warp takes one of the segment's
+ * tiles at a time — up to WARP_UNITS units (32 records) of nearly the same size (k_segment_sort), so its lanes run the same
+ * number of turns — composes their FASTQ bytes in its private stage in shared memory and sends every unit to its own place
+ * in the output with a bulk async copy (TMA); only the tables are shared by the CTA, so there is no CTA barrier in the
+ * loop.  Lane 2k + m holds mate m of the tile's k-th unit.
  *   phase 1  sequence and quality lines (body_lane, then substitutions_lane); byte stores for windows holding anything
  *            but A,C,G,T and for replay
  *   phase 2  headers and the fixed newline / '+' bytes, by the same lane
  * QM = how qualities are sampled (QM_*). */
-constexpr uint32_t WARP_UNITS = 16;
 /* header fields of record r of a unit (simulate.rs:287-298, :513-518) */
 __device__ __forceinline__ void record_positions(const UnitDesc &d, uint32_t r, uint64_t &sp, uint64_t &ep) {
     if (!(d.flags & 4u)) { sp = d.p0; ep = d.p1; }
@@ -865,44 +1008,40 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
     __syncthreads();
 
     const uint32_t mate = lane & 1u, slot = lane >> 1;
-    const uint32_t ntiles = (rp.batch_units + WARP_UNITS - 1) / WARP_UNITS;
-    /* a tile's offsets (lane k: unit k, lane WARP_UNITS: the end) and descriptors are fetched one tile ahead, into registers */
-    auto fetch_tile = [&](uint32_t tile, uint64_t &off, UnitDesc &d) {
-        off = 0; d = UnitDesc{};
-        if (tile < ntiles) {
-            const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
-            if (lane <= tn) off = rp.offsets[t0 + lane];
-            if (slot < tn) d = rp.desc[t0 + slot];
-        }
-    };
-    for (uint32_t tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) {
-        const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
-        uint64_t off_tile; UnitDesc d_tile;
-        fetch_tile(tile, off_tile, d_tile);
-        for (uint32_t s0 = 0; s0 < tn;) {
-            /* sub-tile = longest run of units from s0 that fits the stage */
-            const uint32_t u0 = t0 + s0, left = tn - s0;
-            const uint64_t off = s0 == 0 ? off_tile : (lane <= left ? rp.offsets[u0 + lane] : 0);
-            const uint64_t tile_base = __shfl_sync(0xffffffffu, off, 0), next = __shfl_down_sync(0xffffffffu, off, 1);
-            const uint32_t pad = uint32_t(tile_base & 15);
-            const uint32_t nu = __popc(__ballot_sync(0xffffffffu, lane < left && next - tile_base + pad <= rp.stage_cap));
-            const uint32_t total = uint32_t(__shfl_sync(0xffffffffu, off, nu) - tile_base);
-            const uint32_t unit_off = pad + uint32_t(__shfl_sync(0xffffffffu, off, slot) - tile_base);
-            /* this lane's record */
+    const uint32_t nsegs = (rp.batch_units + SEG_UNITS - 1) / SEG_UNITS;
+    /* a CTA takes whole segments; its warps share out the segment's tiles */
+    for (uint32_t seg = blockIdx.x; seg < nsegs; seg += gridDim.x) {
+        const uint32_t seg0 = seg * SEG_UNITS, nseg = min(SEG_UNITS, rp.batch_units - seg0);
+        const uint32_t nt = __ldg(rp.seg_ntiles + seg);
+        for (uint32_t tile = warp; tile < nt; tile += nwarps) {
+            const uint32_t ts = __ldg(rp.seg_tiles + seg0 + tile);
+            const uint32_t te = tile + 1u < nt ? uint32_t(__ldg(rp.seg_tiles + seg0 + tile + 1u)) : nseg;
+            const uint32_t nu = te - ts;                                               /* 1 .. WARP_UNITS units, slots within the stage */
+            /* this lane's unit and record */
             const bool mine = slot < nu;
-            UnitDesc d = d_tile;
-            if (s0 != 0) { d = UnitDesc{}; if (mine) d = rp.desc[u0 + slot]; }
-            const bool have = mine && (mate == 0 || (d.flags & 4u));
+            uint32_t ui = 0; uint64_t goff = 0;
+            UnitDesc d{};
+            if (mine) { ui = seg0 + __ldg(rp.seg_perm + seg0 + ts + slot); d = load_unit(rp, ui); goff = __ldg(rp.offsets + ui); }
+            const bool two = (d.flags & 4u) != 0;
+            const uint32_t rec0 = d.H0 + 2u * d.L0 + 5u;                               /* bytes of the unit's first record */
+            const uint32_t usz = mine ? rec0 + (two ? d.H1 + 2u * d.L1 + 5u : 0u) : 0u;
+            const uint32_t lead = uint32_t(goff) & 15u;                                /* the unit sits in the stage at its global offset modulo 16 */
+            const uint32_t slotb = mine ? (lead + usz + 15u) & ~15u : 0u;
+            uint32_t so = mate == 0 ? slotb : 0u;                                      /* -> start of the unit's slot: slots of the units before it */
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, so, o); if (lane >= uint32_t(o)) so += y; }
+            so -= slotb;
+            const bool have = mine && (mate == 0 || two);
             const uint32_t L = mate ? d.L1 : d.L0, H = mate ? d.H1 : d.H0;
             const uint64_t a = mate ? d.a1 : d.a0;
-            const uint32_t rec = unit_off + (mate ? d.H0 + 2u * d.L0 + 5u : 0u);      /* stage offset of the record */
-            const bool odd = have && ((d.flags & 8u) || H < 2u || L < 4u);            /* rules out the word paths for the sub-tile */
+            const uint32_t rec = so + lead + (mate ? rec0 : 0u);                       /* stage offset of the record */
+            const bool odd = have && ((d.flags & 8u) || H < 2u || L < 4u);             /* rules out the word paths for the tile */
             const bool words_ok = !__any_sync(0xffffffffu, odd) && !REPLAY;
             const bool hdr_fast = words_ok && rp.hdr_fast != 0;
             const bool fast = have && words_ok && !(d.flags & (1u << mate));
-            const uint64_t unit = rp.batch_begin + u0 + slot;
-            /* the previous bulk copy must have finished reading the stage before it is rewritten */
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            const uint64_t unit = rp.batch_begin + ui;
+            /* the bulk copies this lane issued for the previous tile must have finished reading the stage */
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
 
             /* ---- phase 1: sequence and quality lines ---- */
@@ -931,34 +1070,55 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
                 const uint32_t id = rp.read_id_base + uint32_t(unit);
                 const uint32_t rec_s = stage_s + rec;
                 const ContigHdr ch = rp.chdr[2 * d.contig + mate];
-                if (hdr_fast) {      /* newline that ends the previous record, the tokens, newline */
-                    ByteStream b; bs_open(b, rec_s - 1u); bs_put(b, '\n', 1);
+                if (hdr_fast) {      /* the tokens, newline.  Mate 2's stream starts on the newline that ends mate 1's record: the word it
+                                      * opens holds mate 1's last quality characters (phase 1).  A unit's first record must not open a
+                                      * word of the slot before it, whose last bytes another lane is writing now. */
+                    ByteStream b;
+                    if (mate) { bs_open(b, rec_s - 1u); bs_put(b, '\n', 1); } else bs_open(b, rec_s);
                     header_tokens(b, rp, dec2_s, reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off), rp.hdr_kinds, rp.hdr_fields,
                                   id, uint32_t(sp), uint32_t(ep));
                     bs_put(b, '\n', 1); bs_close(b);
                 } else {
                     emit_header(stage + rec, rp, ch, id, sp, ep);
                     sts8(rec_s + H, '\n');
-                    if (rec > pad) sts8(rec_s - 1u, '\n');                    /* ends the previous record */
                 }
                 const uint32_t mid = rec_s + H + L + 1u;                      /* fastq.rs:61-69 */
-                sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n');
+                sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n'); sts8(mid + L + 3u, '\n');
             }
-            if (lane == 31 && total) sts8(stage_s + pad + total - 1u, '\n');
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            /* stage[pad, pad+total) -> out[tile_base, +total): 16-byte aligned middle by TMA, edges by byte stores */
-            const uint32_t head = min(total, (16 - pad) & 15), mid = (total - head) & ~15u, tail = total - head - mid;
-            if (lane == 0 && mid) {
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rp.out + tile_base + head), "r"(stage_s + pad + head), "r"(mid) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            /* ---- the unit's image, stage[so + lead, + usz), to out[goff, + usz): the 16-byte aligned middle by a bulk copy
+             * issued by the unit's first lane, the bytes before it by that lane, the bytes after it by its second lane ---- */
+            if (mine && !(rp.flags & 0x100u)) {                                    /* SIMMR_DBG=1: nothing leaves the stage (experiment) */
+                const uint32_t img_s = stage_s + so + lead, head = (16u - lead) & 15u;
+                uint8_t *g = rp.out + goff;
+                if (usz < head + 16u) {                                        /* no aligned line inside: bytes */
+                    if (mate == 0) for (uint32_t k = 0; k < usz; ++k) g[k] = stage[so + lead + k];
+                } else {
+                    const uint32_t midb = (usz - head) & ~15u, tail = usz - head - midb;
+                    const bool edges = !(rp.flags & 0x200u);                   /* SIMMR_DBG=2: no edge bytes (experiment) */
+                    if (mate == 0) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g + head), "r"(img_s + head), "r"(midb) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        if (edges) {
+                            uint32_t o = 0;                                    /* head ends on a 16-byte line: 1, 2, 4, 8 bytes by its bits */
+                            if (head & 1u) { g[o] = uint8_t(lds8(img_s + o)); o += 1u; }
+                            if (head & 2u) { *reinterpret_cast<uint16_t *>(g + o) = uint16_t(lds16m(img_s + o)); o += 2u; }
+                            if (head & 4u) { *reinterpret_cast<uint32_t *>(g + o) = lds32m(img_s + o); o += 4u; }
+                            if (head & 8u) { *reinterpret_cast<uint2 *>(g + o) = lds64m(img_s + o); }
+                        }
+                    } else if (edges) {
+                        uint32_t o = head + midb;                              /* tail starts on a 16-byte line: 8, 4, 2, 1 */
+                        if (tail & 8u) { *reinterpret_cast<uint2 *>(g + o) = lds64m(img_s + o); o += 8u; }
+                        if (tail & 4u) { *reinterpret_cast<uint32_t *>(g + o) = lds32m(img_s + o); o += 4u; }
+                        if (tail & 2u) { *reinterpret_cast<uint16_t *>(g + o) = uint16_t(lds16m(img_s + o)); o += 2u; }
+                        if (tail & 1u) { g[o] = uint8_t(lds8(img_s + o)); }
+                    }
+                }
             }
-            if (lane >= 1 && lane < 1 + head) rp.out[tile_base + (lane - 1)] = stage[pad + (lane - 1)];
-            if (lane >= 16 && lane < 16 + tail) rp.out[tile_base + head + mid + (lane - 16)] = stage[pad + head + mid + (lane - 16)];
-            s0 += nu;
         }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 
@@ -968,7 +1128,7 @@ template <bool REPLAY>
 __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, ReplayDev rd) {
     for (uint32_t i = blockIdx.x; i < rp.batch_units; i += gridDim.x) {
         const uint64_t u = rp.batch_begin + i;
-        const UnitDesc d = rp.desc[i];
+        const UnitDesc d = load_unit(rp, i);
         uint8_t *dst = rp.out + rp.offsets[i];
         const uint64_t slot0 = REPLAY ? rd.base_off[u] : 0;
         const uint32_t nrec = (d.flags & 4u) ? 2 : 1;
@@ -1129,7 +1289,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         if (lane == 0) next = atomicAdd(rp.counters + 4, 1ull);
         const uint32_t i = uint32_t(__shfl_sync(0xffffffffu, next, 0));
         if (i >= rp.batch_units) break;
-        const UnitDesc d = rp.desc[i];
+        const UnitDesc d = load_unit(rp, i);
         const uint32_t L = d.L0, H = d.H0;
         const uint64_t unit = rp.batch_begin + i;
         uint8_t *rec = rp.out + rp.offsets[i];

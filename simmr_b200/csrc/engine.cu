@@ -79,7 +79,8 @@ struct simmr_ctx {
     DevMem d_acc, d_plthr, d_rodds, d_ralias, d_roff, d_rlo, d_rhi;
     /* run scratch */
     DevMem d_unit_start, d_counters, d_out[2];
-    DevMem d_sizes[2], d_offsets[2], d_block_sums[2], d_desc[2];   /* per-batch scratch, two sets: batch b+1 is prepared while batch b is formatted */
+    DevMem d_sizes[2], d_offsets[2], d_block_sums[2], d_desc[2], d_desc_ext[2];   /* per-batch scratch, two sets: batch b+1 is prepared while batch b is formatted */
+    DevMem d_seg_perm[2], d_seg_tiles[2], d_seg_ntiles[2];        /* short reads: size-sorted order and tiles of every segment (k_segment_sort) */
     PinnedMem h_out[2], h_total;
     DevMem d_draw[13];
     simmr_stats stats{};
@@ -141,16 +142,20 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
     const size_t smem_max = ctx->prop.sharedMemPerBlockOptin;
     pl.tiles = !m.is_long;
     if (pl.tiles) {
-        /* A warp's stage holds the typical bytes of its WARP_UNITS units (one record per lane) plus a margin — a group
-         * that draws longer reads is cut into sub-tiles by the kernel — and at least the largest single unit.  One CTA
-         * per SM with as many warps as fit next to the tables. */
-        const uint64_t typical = 2ull * (ctx->plan.hdr_typ + 2ull * m.nominal_read_len + 5);
-        const uint64_t cap = (std::max<uint64_t>(unit_bytes + 32, WARP_UNITS * typical * 21 / 20 + 64) + 15) & ~15ull;
+        /* One CTA per SM, its warps' stages share what the tables leave of shared memory.  A stage holds up to WARP_UNITS
+         * units, each at its global offset modulo 16 (a slot is at most the unit's bytes + 30); k_segment_sort fills a
+         * tile with as many units as fit.  Fewer warps when a single unit needs more than a sixteenth. */
+        const uint64_t need = (unit_bytes + 30 + 15) & ~15ull;
+        const uint64_t tables = SM_QTAB + qtab_bytes(quality_mode(m), m.cb, m.npos);
+        auto cap_for = [&](uint32_t w) -> int64_t { return tables >= smem_max ? -1 : int64_t(((smem_max - tables) / w) & ~size_t(15)) - 64; };
         uint32_t warps = FORMAT_THREADS / 32;
         if (const char *e = getenv("SIMMR_WARPS")) warps = uint32_t(std::max(1, std::min(FORMAT_THREADS / 32, atoi(e))));
-        while (warps > 1 && lanes_smem(m, warps, uint32_t(cap)) > smem_max) --warps;
-        if (cap > 0x7fffffffull || lanes_smem(m, warps, uint32_t(cap)) > smem_max) pl.tiles = false;   /* a single unit does not fit: direct path */
-        else { pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.smem = lanes_smem(m, warps, uint32_t(cap)); }
+        while (warps > 1 && cap_for(warps) < int64_t(need)) --warps;
+        if (cap_for(warps) < int64_t(need)) pl.tiles = false;   /* a single unit does not fit: direct path */
+        else {
+            const uint64_t cap = std::min<uint64_t>(uint64_t(cap_for(warps)), WARP_UNITS * need);
+            pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.smem = lanes_smem(m, warps, uint32_t(cap));
+        }
     }
     int occ = 0;
     const size_t long_smem = SM_QTAB + qtab_bytes(quality_mode(m), m.cb, m.npos) + long_extra_smem();   /* tables, a genome-word ring and two line tiles per warp, an event list per lane */
@@ -181,6 +186,7 @@ int ensure_headers(simmr_ctx *ctx, const char *fmt) {
     if (rc) return fail(ctx, rc, err);
     CU(ctx->d_chdr.upload(ctx->plan.contigs.data(), ctx->plan.contigs.size(), ctx->compute));
     CU(ctx->d_toks.upload(ctx->plan.toks.data(), ctx->plan.toks.size(), ctx->compute));
+    if (ctx->plan.hdr_cap > 65535u) return fail(ctx, SIMMR_E_LIMIT, "a read header could exceed 65535 bytes");     /* descriptors hold header lengths in 16 bits */
     ctx->plan.pool.resize((ctx->plan.pool.size() + 7) & ~size_t(3), '\0');
     CU(ctx->d_pool.upload(ctx->plan.pool.data(), ctx->plan.pool.size(), ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
@@ -233,11 +239,11 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     if (rc) return rc;
     if (measure_only) {      /* geometry + record sizes only: what the units would occupy in the FASTQ stream */
         const uint64_t batch = std::min<uint64_t>(ue - ub, 1ull << 24);
-        CU(ctx->d_sizes[0].reserve(batch * 4)); CU(ctx->d_desc[0].reserve(batch * sizeof(UnitDesc)));
+        CU(ctx->d_sizes[0].reserve(batch * 4)); CU(ctx->d_desc[0].reserve(batch * sizeof(UnitRec))); CU(ctx->d_desc_ext[0].reserve(batch * sizeof(UnitExt)));
         CU(ctx->d_block_sums[0].reserve(((batch + SIZES_THREADS - 1) / SIZES_THREADS) * 8));
         CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
         RunParams rp; fill_params(ctx, rp, seed, opts ? opts->read_id_base : 0, pl);
-        rp.sizes = ctx->d_sizes[0].as<uint32_t>(); rp.desc = ctx->d_desc[0].as<UnitDesc>(); rp.block_sums = ctx->d_block_sums[0].as<uint64_t>();
+        rp.sizes = ctx->d_sizes[0].as<uint32_t>(); rp.desc = ctx->d_desc[0].as<UnitRec>(); rp.desc_ext = ctx->d_desc_ext[0].as<UnitExt>(); rp.block_sums = ctx->d_block_sums[0].as<uint64_t>();
         simmr_stats st{};
         for (uint64_t u = ub; u < ue; u += batch) {
             const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
@@ -272,9 +278,14 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     if (batch * pl.max_unit_bytes > (64ull << 30)) batch = std::max<uint64_t>(1, (64ull << 30) / pl.max_unit_bytes);
     const uint64_t out_cap = batch * pl.max_unit_bytes + 64;
     const uint32_t max_blocks = uint32_t((batch + SIZES_THREADS - 1) / SIZES_THREADS);
+    const uint64_t max_segs = (batch + SEG_UNITS - 1) / SEG_UNITS;
     for (int k = 0; k < 2; ++k) {
-        CU(ctx->d_sizes[k].reserve(batch * 4)); CU(ctx->d_desc[k].reserve(batch * sizeof(UnitDesc)));
+        CU(ctx->d_sizes[k].reserve(batch * 4)); CU(ctx->d_desc[k].reserve(batch * sizeof(UnitRec))); CU(ctx->d_desc_ext[k].reserve(batch * sizeof(UnitExt)));
         CU(ctx->d_offsets[k].reserve((batch + 1) * 8)); CU(ctx->d_block_sums[k].reserve(size_t(max_blocks) * 8));
+        if (pl.tiles) {
+            CU(ctx->d_seg_perm[k].reserve(max_segs * SEG_UNITS * 2)); CU(ctx->d_seg_tiles[k].reserve(max_segs * SEG_UNITS * 2));
+            CU(ctx->d_seg_ntiles[k].reserve(max_segs * 4));
+        }
     }
     CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
     const bool guard = getenv("SIMMR_DEBUG_GUARD") != nullptr, dbg_sync = getenv("SIMMR_DEBUG_SYNC") != nullptr;
@@ -286,7 +297,8 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     RunParams rp; fill_params(ctx, rp, seed, opts ? opts->read_id_base : 0, pl);
     auto scratch = [&](RunParams &r, int k) {
         r.sizes = ctx->d_sizes[k].as<uint32_t>(); r.offsets = ctx->d_offsets[k].as<uint64_t>();
-        r.desc = ctx->d_desc[k].as<UnitDesc>(); r.block_sums = ctx->d_block_sums[k].as<uint64_t>();
+        r.desc = ctx->d_desc[k].as<UnitRec>(); r.desc_ext = ctx->d_desc_ext[k].as<UnitExt>(); r.block_sums = ctx->d_block_sums[k].as<uint64_t>();
+        r.seg_perm = ctx->d_seg_perm[k].as<uint16_t>(); r.seg_tiles = ctx->d_seg_tiles[k].as<uint16_t>(); r.seg_ntiles = ctx->d_seg_ntiles[k].as<uint32_t>();
     };
     cudaEvent_t ev_start, ev_stop, ev_f0, ev_f1, ev_total[2], ev_fmt[2], ev_copy[2], ev_prep[2], ev_done[2];
     CU(cudaEventCreate(&ev_start)); CU(cudaEventCreate(&ev_stop)); CU(cudaEventCreate(&ev_f0)); CU(cudaEventCreate(&ev_f1));
@@ -320,7 +332,8 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         else k_unit_sizes<false><<<nblk, SIZES_THREADS, 0, prep>>>(r, rd);
         if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("k_unit_sizes: ") + cudaGetErrorString(e_)); }
         k_scan_blocks<<<1, 1024, 0, prep>>>(r, nblk);
-        k_unit_offsets<<<nblk, SIZES_THREADS, 0, prep>>>(r);
+        if (pl.tiles) k_segment_sort<<<(n + SEG_UNITS - 1) / SEG_UNITS, SEG_THREADS, 0, prep>>>(r);     /* offsets + size-sorted tiles */
+        else k_unit_offsets<<<nblk, SIZES_THREADS, 0, prep>>>(r);
         CU(cudaGetLastError());
         if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("scan kernels: ") + cudaGetErrorString(e_)); }
         CU(cudaEventRecord(ev_prep[k], prep));
@@ -345,8 +358,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         }
         CU(cudaEventRecord(ev_f0, ctx->compute));
         if (pl.tiles) {
-            const uint32_t wpc = pl.threads / 32, nctas = ((n + WARP_UNITS - 1) / WARP_UNITS + wpc - 1) / wpc;
-            const int grid = int(std::min<uint32_t>(nctas, uint32_t(pl.grid)));
+            const int grid = int(std::min<uint32_t>((n + SEG_UNITS - 1) / SEG_UNITS, uint32_t(pl.grid)));      /* a CTA takes whole segments */
             lanes_kernel(replay, quality_mode(ctx->model))<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
         } else if (pl.lanes) {
             CU(cudaMemsetAsync(rp.counters + 4, 0, 8, ctx->compute));       /* the kernel's piece counter */

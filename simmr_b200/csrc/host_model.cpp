@@ -318,6 +318,65 @@ bool rust_alias(const std::vector<double> &w, std::vector<double> &odds, std::ve
     for (; big_head != nil; )   { const uint32_t b = big_head;   big_head = alias[b];   odds[b] = sum; }
     return true;
 }
+/* The alt-k-mer table of a blob as sampling tables (ErrModel).  A k-mer listed twice keeps its last entry (the
+ * reference collects the list into a HashMap, custom_short.rs:462-467); an alternate list without weight would make the
+ * reference's WeightedAliasIndex::new fail and is treated as "k-mer not observed"; alternates that cannot be decoded
+ * (a digit above 4, encoding.rs:205) make the profile invalid. */
+bool err_model(const ProfileBlob &b, ErrModel &e) {
+    e = ErrModel();
+    const size_t n = b.ref_kmer.size();
+    if (!n) return true;
+    if (b.bit_encoding != 3 || b.kmer_size < 1 || b.kmer_size > 10) return false;
+    e.k = uint32_t(b.kmer_size);
+    const uint32_t digits = e.k == 10 ? 0x3fffffffu : (1u << (3 * e.k)) - 1u;
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return b.ref_kmer[x] < b.ref_kmer[y]; });
+    for (size_t at = 0; at < n;) {
+        size_t last = at;
+        while (last + 1 < n && b.ref_kmer[order[last + 1]] == b.ref_kmer[order[at]]) ++last;
+        const uint32_t src = order[last], kmer = b.ref_kmer[src];      /* the stable sort keeps the list's order among equals */
+        at = last + 1;
+        double self = 0.0, all = 0.0;
+        std::vector<double> weight; std::vector<uint32_t> code;
+        for (uint32_t j = b.alt_off[src]; j < b.alt_off[src + 1]; ++j) {
+            const uint32_t alt = b.alt_kmer[j] & digits;
+            for (uint32_t d = 0; d < e.k; ++d) if (((alt >> (3 * d)) & 7u) > 4u) return false;
+            const double w = double(b.alt_prob[j]);
+            if (!(w >= 0.0)) return false;
+            all += w;
+            if (alt == (kmer & digits)) self += w;
+            else if (w > 0.0) { weight.push_back(w); code.push_back(alt); }
+        }
+        if (!(all > 0.0)) continue;
+        if (weight.size() > 4096) return false;
+        e.ref.push_back(kmer); e.row.push_back(uint32_t(e.entries.size()));
+        if (weight.empty()) {
+            e.keep_thr.push_back(0xffffffffu); e.cb.push_back(0);
+            e.entries.push_back(0xfffff000u); e.alts.push_back(kmer & digits);
+            continue;
+        }
+        e.keep_thr.push_back(threshold(self / all, 32));
+        uint32_t cb = 0;
+        while ((size_t(1) << cb) < weight.size()) ++cb;
+        e.cb.push_back(cb);
+        std::vector<uint32_t> words;
+        if (!len_words(weight, cb, words)) return false;
+        e.entries.insert(e.entries.end(), words.begin(), words.end());
+        for (uint32_t j = 0; j < (1u << cb); ++j) e.alts.push_back(j < code.size() ? code[j] : (kmer & digits));
+    }
+    e.on = !e.ref.empty();
+    if (e.on) {
+        e.direct.assign(size_t(1) << (2 * e.k), uint2_host{0u, 0u});
+        for (uint32_t r = 0; r < e.ref.size(); ++r) {
+            uint32_t two = 0; bool acgt = true;
+            for (uint32_t d = 0; d < e.k; ++d) { const uint32_t v = (e.ref[r] >> (3 * d)) & 7u; if (v > 3u) acgt = false; two |= (v & 3u) << (2 * d); }
+            if (acgt && !(e.ref[r] & ~digits)) e.direct[two] = uint2_host{e.keep_thr[r], r + 1u};
+        }
+    }
+    return true;
+}
+
 }  // namespace
 
 int build_profile(const simmr_eprofile_desc *d, ProfileModel &m, std::string &err) {
@@ -390,6 +449,7 @@ int build_profile(const simmr_eprofile_desc *d, ProfileModel &m, std::string &er
     case SIMMR_EP_CUSTOM_LONG:      /* SURVEY.md §A.5 */
         long_common(); m.replay_kind = RP_ALIAS;
         if (!phred_from_blob(blob, m)) { err = "custom profile has an empty quality distribution"; return SIMMR_E_PARSE; }
+        if (!err_model(blob, m.err)) { err = "custom profile has a malformed alt-k-mer table"; return SIMMR_E_PARSE; }
         break;
     default: err = "unknown error profile kind"; return SIMMR_E_INVALID;
     }

@@ -30,9 +30,22 @@ struct ProfileBlob {
 };
 bool decode_blob(const uint8_t *p, uint64_t n, ProfileBlob &out);
 
+struct uint2_host { uint32_t x, y; };
+
 struct LenModel {
     uint32_t kind = LEN_CONST, value = 0, cb = 0, vmax = 0;
     std::vector<uint32_t> entries, lo, hi;
+};
+
+/* k-mer error injection of custom-long profiles (custom_long.rs:187-232), DESIGN.md §5.  Per distinct reference k-mer
+ * (3-bit codes, ascending): the chance that the sampled alternate is the k-mer itself as a 32-bit threshold, and an alias row
+ * (thr20<<12 | alias12 per column) over the other alternates; `entries` and `alts` share one row offset. */
+struct ErrModel {
+    bool on = false;
+    uint32_t k = 0;
+    std::vector<uint32_t> ref, keep_thr, row, cb, entries, alts;
+    /* device look-up of windows of A,C,G,T only: 4^k words pairs {keep_thr, row index + 1 (0: k-mer not observed)} by 2-bit code */
+    std::vector<uint2_host> direct;
 };
 
 struct ProfileModel {
@@ -49,6 +62,7 @@ struct ProfileModel {
     bool has_sub = false;
     std::vector<uint32_t> gap_entries, qsub_entries;
     LenModel rl, is;
+    ErrModel err;                        /* custom-long blobs with an alt-k-mer table */
     GammaConst gamma{};
     uint32_t max_read_len = 0;          /* upper bound on a read's length    */
     uint32_t nominal_read_len = 0;      /* typical length (sizes the shared-memory stage) */

@@ -114,6 +114,60 @@ def ont_blob(npos=64):
     return make_blob(quality, rl, None, rl_mean=19800.0, rl_std=15000.0, is_long=True)
 
 
+def kmer_code(s):
+    """3-bit code of shared/src/encoding.rs:149-179: base i at bits [3i, 3i+3), A C G T N = 0..4."""
+    return sum(b"ACGTN".index(c) << (3 * i) for i, c in enumerate(s))
+
+
+def ont_kmers(k=7, n_alts=20, seed=8, keep=0.9):
+    """An alt-k-mer table as simmrd writes it (simmrd/src/main.rs:315-328): every A,C,G,T k-mer with itself (weight `keep`)
+    and n_alts - 1 other k-mers: single substitutions and single / double deletions (N digits, alignment.rs:333-343)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for v in range(4 ** k):
+        digits = [(v >> (2 * i)) & 3 for i in range(k)]
+        ref = sum(d << (3 * i) for i, d in enumerate(digits))
+        alts, seen = [(ref, keep)], {ref}
+        w = rng.random(n_alts - 1)
+        w = (1.0 - keep) * w / w.sum()
+        for j in range(n_alts - 1):
+            for _ in range(8):
+                d = list(digits)
+                kind = rng.integers(0, 3)
+                at = int(rng.integers(0, k))
+                if kind == 0:
+                    d[at] = (d[at] + 1 + int(rng.integers(0, 3))) & 3
+                elif kind == 1:
+                    d[at] = 4
+                else:
+                    d[at] = 4
+                    d[int(rng.integers(0, k))] = 4
+                c = sum(x << (3 * i) for i, x in enumerate(d))
+                if c not in seen:
+                    break
+            seen.add(c)
+            alts.append((c, float(np.float32(w[j]))))
+        out.append((ref, alts))
+    return out
+
+
+_ONT_CACHE = {}
+
+
+def ont_blob_with_kmers(k=5, n_alts=20, npos=64, seed=8):
+    """ont_blob plus an alt-k-mer table (~n_alts alternates per k-mer) -> (blob, kmers)."""
+    key = (k, n_alts, npos, seed)
+    if key not in _ONT_CACHE:
+        kmers = ont_kmers(k, n_alts, seed)
+        quality = []
+        for p in range(npos):
+            mu = 12.0 + 2.0 * math.sin(p / 9.0)
+            quality.append(([math.exp(-0.5 * ((q - mu) / 4.0) ** 2) for q in range(71)], [(i, i) for i in range(70)]))
+        blob = make_blob(quality, ([1.0], [(20000, 20000)]), None, kmers=kmers, kmer_size=k, rl_mean=19800.0, rl_std=15000.0, is_long=True)
+        _ONT_CACHE[key] = (blob, kmers)
+    return _ONT_CACHE[key]
+
+
 # ----------------------------------------------------------------------------
 # replay draws
 # ----------------------------------------------------------------------------

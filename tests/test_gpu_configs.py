@@ -63,7 +63,7 @@ def test_c1_on_the_reference_fixture(engine):
     tests/golden/): loaded through the FASTA path, whole run against the oracle, and the reference's slice / RC
     literals (simulate_tests.rs:36-45) read back out of the records that cover them."""
     path = os.path.join(GOLDEN, "GCF_000005845.2_ASM584v2_genomic.partial.fna")
-    prof = S.PerfectShortErrorProfile(20, 60)
+    prof = S.PerfectShortErrorProfile(60, 100)
     gs, kept = S.GenomeSet.from_fasta([path], uuids=["fixture"], min_size=prof.minimum_genome_size())
     assert kept.all() and gs.n_contigs == 1 and int(gs.contig_size[0]) == 7920
     assert gs.contig_id(0) == b"NC_000913.3 Escherichia coli str. K-12 substr. MG1655, complete genome"
@@ -73,17 +73,21 @@ def test_c1_on_the_reference_fixture(engine):
     seq = gs.bases.tobytes()
     assert seq[38:58] == b"TGTGGATTAAAAAAAGAGTG" and seq[8:28] == b"ATTCTGACTGCAACGGGCAA"
     comp = bytes.maketrans(b"ACGT", b"TGCA")
-    hits = 0
+    fwd_hits = rc_hits = 0
     for hdr, s, _ in H.parse_fastq(data):
         h = hdr.decode()
         sp, ep = int(h.split("|sp=")[1].split("|")[0]), int(h.split("|ep=")[1].split("|")[0])
         if h.endswith("rc=f"):
             assert s == seq[sp:ep]
-            hits += sp == 38
+            if sp <= 38 and ep >= 58:                                                     # the record covers [38, 58)
+                assert s[38 - sp:58 - sp] == b"TGTGGATTAAAAAAAGAGTG"
+                fwd_hits += 1
         else:
             assert s == seq[ep:sp].translate(comp)[::-1]                                  # simulate.rs:283
-            hits += (ep, sp) == (78, 98) and s == b"TTACTCACGGCAGGTAACCA"
-    assert hits > 0
+            if ep <= 78 and sp >= 98:                                                     # covers [78, 98), reverse strand
+                assert s[sp - 98:sp - 78] == b"TTACTCACGGCAGGTAACCA"
+                rc_hits += 1
+    assert fwd_hits > 0 and rc_hits > 0
 
 
 def _write_fasta(path, contigs):
