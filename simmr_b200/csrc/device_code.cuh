@@ -70,6 +70,10 @@ struct RunParams {
      * per-contig lists only; kinds 4 bits each, field i in bits 4*i */
     uint32_t hdr_fast, hdr_fields, hdr_kinds;
     uint32_t one;                  /* always 1: a multiplier the compiler cannot fold (mwc1_draw) */
+    /* k-mer error injection (custom-long profiles with an alt-k-mer table): the tables, and the edited reads — the
+     * format kernel's source instead of the genome — as 2-bit words (reads of A,C,G,T only) or bytes (all others) */
+    ErrTab err;
+    uint32_t *epacked; uint8_t *ebases;
 };
 
 constexpr int SIZES_THREADS = 256;
@@ -432,13 +436,23 @@ __device__ __forceinline__ void replay_base(const RunParams &rp, const ReplayDev
  * the piece's quality chain, then its substitution events.  Used for windows that hold anything but
  * A,C,G,T, for records that do not fit a stage and behind SIMMR_NO_LONG_KERNEL; same bytes as the word paths of
  * k_format_lanes and k_format_long.  Tables are read from global memory (entries hold the characters as printed). */
+/* base j of an edited read (k_kmer_errors): 2-bit scratch for reads of A,C,G,T only, byte scratch for the others */
+__device__ __forceinline__ uint8_t err_base(const RunParams &rp, bool pure, uint64_t sb, uint32_t j) {
+    if (!pure) return rp.ebases[sb + j];
+    const uint64_t at = sb + j;
+    return uint8_t(0x54474341u >> (8u * ((rp.epacked[at >> 4] >> (2u * (uint32_t(at) & 15u))) & 3u)));
+}
 template <bool PUNCT>
-__device__ void emit_body_pieces(const RunParams &rp, uint8_t *dst, uint64_t unit, uint32_t mate, uint64_t a, uint32_t L, uint32_t thr, uint32_t nthr) {
-    uint8_t *seq = dst + 1, *qual = dst + L + 4;
-    if (PUNCT && thr == 0) { dst[0] = '\n'; dst[L + 1] = '\n'; dst[L + 2] = '+'; dst[L + 3] = '\n'; dst[2 * L + 4] = '\n'; }   /* fastq.rs:61-69 */
+__device__ void emit_body_pieces(const RunParams &rp, uint8_t *dst, uint64_t unit, uint32_t mate, uint64_t a, uint32_t L, uint32_t thr, uint32_t nthr,
+                                 uint32_t Ls = 0xffffffffu, bool pure = false) {
+    const bool edited = Ls != 0xffffffffu;            /* long read after k-mer error injection: Ls bases from the scratch copy at a, L qualities */
+    if (!edited) Ls = L;
+    uint8_t *seq = dst + 1, *qual = dst + Ls + 4;
+    if (PUNCT && thr == 0) { dst[0] = '\n'; dst[Ls + 1] = '\n'; dst[Ls + 2] = '+'; dst[Ls + 3] = '\n'; dst[Ls + L + 4] = '\n'; }   /* fastq.rs:61-69 */
     const uint8_t *src = rp.bases + a;
     const bool rc = mate != 0, sampled = rp.phred.kind != PT_CONST;
     const uint32_t mask = rp.phred_mult - 1u, last = rp.phred.npos - 1u, S = piece_len(L, rp.is_long != 0);
+    if (edited) for (uint32_t j = thr; j < Ls; j += nthr) seq[j] = err_base(rp, pure, a, j);
     for (uint32_t piece = thr; piece * uint64_t(S) < L; piece += nthr) {
         const uint32_t lo = piece * S, hi = min(L, lo + S);
         Mwc1 qc{}, ec{};
@@ -452,10 +466,11 @@ __device__ void emit_body_pieces(const RunParams &rp, uint8_t *dst, uint64_t uni
                 qc8 = q32_pick(__ldg(rp.phred.entries + (min(i, last) << rp.phred.cb) + col), lv);
             }
             qual[i] = uint8_t(qc8);
+            if (edited) continue;
             const uint8_t b = __ldg(src + i);
             if (rc) seq[L - 1 - i] = complement(b); else seq[i] = b;           /* util.rs:31-37 */
         }
-        if (!sampled || !rp.phred.has_sub) continue;
+        if (!sampled || !rp.phred.has_sub || edited) continue;                  /* profiles with a k-mer table never substitute (custom_long.rs:238-245) */
         for (uint32_t next = lo; next < hi;) {                                  /* three draws of the event chain per step */
             uint32_t l1, l2, l3;
             const uint32_t r1 = mwc1_draw(ec, rp.one, l1), r2 = mwc1_draw(ec, rp.one, l2), r3 = mwc1_draw(ec, rp.one, l3);
@@ -817,6 +832,130 @@ __global__ void __launch_bounds__(SEG_THREADS) k_segment_sort(RunParams rp) {
 }
 
 /* ---------------------------------------------------------------------- */
+/* k-mer error injection — custom_long.rs:187-232 (== custom_short.rs:452-516) */
+/* ---------------------------------------------------------------------- */
+/* Where read i's edited bases go in the scratch buffers (an index in bases): its FASTQ offset before the edit rounded up
+ * to a multiple of 16, plus 16 per read before it — a record holds at least as many bytes as its read has bases, so the
+ * regions never overlap, and every region starts on a word of the 2-bit copy. */
+__device__ __forceinline__ uint64_t err_scratch_base(uint64_t off0, uint32_t i) { return ((off0 + 15u) & ~uint64_t(15)) + 16ull * i; }
+/* one draw of a read's error chain decides window `code` (3-bit digits, row r of the tables): the k-mer itself, or one of the other alternates */
+__device__ __forceinline__ uint32_t err_pick_other(const ErrTab &t, uint32_t r, uint32_t word) {
+    const uint32_t ro = __ldg(t.row + r), cb = __ldg(t.cb + r);
+    const uint32_t idx = cb ? word >> (32u - cb) : 0u, frac = (word << cb) >> 12;
+    const uint32_t e = __ldg(t.entries + ro + idx), j = frac < (e >> 12) ? idx : (e & 0xfffu);
+    return __ldg(t.alts + ro + j);
+}
+/* One thread per read, reads taken in the size-sorted order of their segment (k_segment_sort) so that a warp's 32 reads are
+ * about equally long.  The reference walks i over the original length, looks at the k bytes at i of the sequence as edited
+ * so far and splices the sampled alternate in (N digits of an alternate are deleted bases): everything before i is final,
+ * everything from i + k on is still the original's tail, so the state is the window (`win`, `cnt` bases) and how far into
+ * the original it reaches (`r`).  One draw of the read's chain (Philox block 0 of stream 3, one step discarded) per
+ * window.  Where the reference would slice past the shortened sequence (and panic) the walk stops.
+ * Reads of A,C,G,T only: 2-bit codes in, 2-bit words out (epacked), tables by direct index.  Other reads: bytes in,
+ * bytes out (ebases), k-mers found by binary search (N is a digit; anything else cannot be encoded, :203-207).
+ * Afterwards the unit's descriptor points at the scratch copy (a0), L1 holds the sequence length and sizes[] the
+ * record's new bytes. */
+__global__ void __launch_bounds__(256) k_kmer_errors(RunParams rp) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rp.batch_units) return;
+    const uint32_t seg0 = t & ~(SEG_UNITS - 1u);
+    const uint32_t i = seg0 + __ldg(rp.seg_perm + t);
+    UnitDesc d = load_unit(rp, i);
+    const ErrTab &et = rp.err;
+    const uint32_t L = d.L0, k = et.k;
+    const uint64_t unit = rp.batch_begin + i, sb = err_scratch_base(__ldg(rp.offsets + i), i);
+    Mwc1 ch;
+    { const Philox4 w = philox(rp.rk, 0u, 3u, uint32_t(unit), uint32_t(unit >> 32)); ch.x = w.x; ch.c = (w.y >> 2) + 1u; uint32_t lv; mwc1_draw(ch, rp.one, lv); }
+    uint32_t Ls = 0;
+    if (!(d.flags & 1u)) {
+        /* 2-bit path */
+        const uint32_t *src = rp.packed + (d.a0 >> 4);
+        uint32_t sw = __ldg(src), sleft = 16u - (uint32_t(d.a0) & 15u);           /* bases left in the source word */
+        sw >>= 2u * (uint32_t(d.a0) & 15u);
+        uint32_t *dst = rp.epacked + (sb >> 4);
+        uint32_t ow = 0, ocnt = 0;                                                    /* output word being filled */
+        uint32_t win = 0, cnt = 0, r = 0;
+        const uint32_t kmask = (1u << (2u * k)) - 1u;
+        auto take = [&]() -> uint32_t {                                               /* next base of the original */
+            if (!sleft) { sw = __ldg(++src); sleft = 16u; }
+            const uint32_t b = sw & 3u; sw >>= 2; --sleft; ++r; return b;
+        };
+        auto emit = [&](uint32_t b) {
+            ow |= b << (2u * ocnt);
+            if (++ocnt == 16u) { dst[Ls >> 4] = ow; ow = 0; ocnt = 0; }
+            ++Ls;
+        };
+        for (uint32_t at = 0; at + k <= L; ++at) {                                    /* :196-199 */
+            while (cnt < k && r < L) { win |= take() << (2u * cnt); ++cnt; }
+            if (cnt < k) break;                                                       /* the reference would panic here */
+            uint32_t level; const uint32_t word = mwc1_draw(ch, rp.one, level);
+            const uint2 ent = __ldg(reinterpret_cast<const uint2 *>(et.direct) + (win & kmask));
+            if (ent.y && level >= ent.x) {                                            /* observed k-mer, and the draw leaves it: :216-228 */
+                const uint32_t alt = err_pick_other(et, ent.y - 1u, word);
+                win = 0; cnt = 0;
+                for (uint32_t dg = 0; dg < k; ++dg) { const uint32_t v = (alt >> (3u * dg)) & 7u; if (v != 4u) { win |= v << (2u * cnt); ++cnt; } }
+            }
+            if (!cnt && r < L) { win = take(); cnt = 1; }
+            if (!cnt) break;
+            emit(win & 3u); win >>= 2; --cnt;
+        }
+        for (; cnt; --cnt) { emit(win & 3u); win >>= 2; }
+        while (r < L) emit(take());
+        if (ocnt) dst[Ls >> 4] = ow;
+    } else {
+        /* byte path */
+        const uint8_t *src = rp.bases + d.a0;
+        uint8_t *dst = rp.ebases + sb;
+        uint8_t win[16]; uint32_t cnt = 0, r = 0;
+        for (uint32_t at = 0; at + k <= L; ++at) {
+            while (cnt < k && r < L) win[cnt++] = __ldg(src + r++);
+            if (cnt < k) break;
+            uint32_t level; const uint32_t word = mwc1_draw(ch, rp.one, level);
+            uint32_t code = 0; bool ok = true;
+            for (uint32_t dg = 0; dg < k; ++dg) {                                     /* encoding.rs:149-179 */
+                const uint8_t c = win[dg];
+                const uint32_t v = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : c == 'N' ? 4u : 8u;
+                ok &= v < 8u; code |= (v & 7u) << (3u * dg);
+            }
+            if (ok) {
+                uint32_t lo = 0, hi = et.n_ref;                                       /* the k-mer's row */
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(et.ref + mid) < code) lo = mid + 1u; else hi = mid; }
+                if (lo < et.n_ref && __ldg(et.ref + lo) == code && level >= __ldg(et.keep_thr + lo)) {
+                    const uint32_t alt = err_pick_other(et, lo, word);
+                    cnt = 0;
+                    for (uint32_t dg = 0; dg < k; ++dg) { const uint32_t v = (alt >> (3u * dg)) & 7u; if (v != 4u) win[cnt++] = uint8_t(0x54474341u >> (8u * v)); }
+                }
+            }
+            if (!cnt && r < L) { win[0] = __ldg(src + r++); cnt = 1; }
+            if (!cnt) break;
+            dst[Ls++] = win[0];
+            for (uint32_t j = 1; j < cnt; ++j) win[j - 1] = win[j];
+            --cnt;
+        }
+        for (uint32_t j = 0; j < cnt; ++j) dst[Ls++] = win[j];
+        while (r < L) dst[Ls++] = __ldg(src + r++);
+    }
+    /* the unit now reads from the scratch copy; its record shrinks by the deleted bases */
+    uint4 *rec = reinterpret_cast<uint4 *>(rp.desc + i);
+    uint4 v0 = rec[0], v1 = rec[1];
+    v0.x = uint32_t(sb); v0.y = uint32_t(sb >> 32);
+    v1.z = (v1.z & 0xffff0000u) | (Ls & 0xffffu);                                     /* L1 <- sequence length */
+    rec[0] = v0; rec[1] = v1;
+    rp.sizes[i] -= L - Ls;
+    if (L != Ls) atomicAdd(rp.counters + 5, (unsigned long long)(L - Ls));
+}
+/* per-block byte totals again, after k_kmer_errors changed the sizes */
+__global__ void __launch_bounds__(SIZES_THREADS) k_block_sums(RunParams rp) {
+    __shared__ uint32_t warp_tot[SIZES_THREADS / 32];
+    const uint32_t i = blockIdx.x * SIZES_THREADS + threadIdx.x;
+    uint32_t v = i < rp.batch_units ? rp.sizes[i] : 0u;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint64_t s = 0; for (int w = 0; w < SIZES_THREADS / 32; ++w) s += warp_tot[w]; rp.block_sums[blockIdx.x] = s; }
+}
+
+/* ---------------------------------------------------------------------- */
 /* short reads, word path: one lane per record                              */
 /* ---------------------------------------------------------------------- */
 /* Quality characters (as printed) of four consecutive bases, the first at window index i0 (the same for every lane of
@@ -1139,6 +1278,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, 
                 emit_header(dst, rp, rp.chdr[2 * d.contig + r], rp.read_id_base + uint32_t(u), sp, ep);
             }
             if (REPLAY) emit_body_replay<true>(rp, rd, dst + H, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
+            else if (rp.err.on) emit_body_pieces<true>(rp, dst + H, u, r, d.a0, L, threadIdx.x, DIRECT_THREADS, d.L1, !(d.flags & 1u));   /* edited long read */
             else emit_body_pieces<true>(rp, dst + H, u, r, r ? d.a1 : d.a0, L, threadIdx.x, DIRECT_THREADS);   /* a thread per piece */
             dst += H + 2 * L + 5;
         }
@@ -1291,19 +1431,25 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         if (i >= rp.batch_units) break;
         const UnitDesc d = load_unit(rp, i);
         const uint32_t L = d.L0, H = d.H0;
+        const uint32_t Ls = rp.err.on ? uint32_t(d.L1) : L;            /* bases of the sequence line: fewer than qualities after k-mer errors deleted some (simulate.rs:497-503) */
         const uint64_t unit = rp.batch_begin + i;
         uint8_t *rec = rp.out + rp.offsets[i];
         const bool bytes_path = (d.flags & 9u) || L < 4u;
         if (lane == 0) {                                  /* header and the five fixed bytes (fastq.rs:34-69) */
             emit_header(rec, rp, rp.chdr[2 * d.contig], rp.read_id_base + uint32_t(unit), d.p0, d.p1);
-            rec[H] = '\n'; rec[H + L + 1] = '\n'; rec[H + L + 2] = '+'; rec[H + L + 3] = '\n'; rec[H + 2 * L + 4] = '\n';
+            rec[H] = '\n'; rec[H + Ls + 1] = '\n'; rec[H + Ls + 2] = '+'; rec[H + Ls + 3] = '\n'; rec[H + Ls + L + 4] = '\n';
         }
-        if (bytes_path) { emit_body_pieces<false>(rp, rec + H, unit, 0, d.a0, L, lane, 32); __syncwarp(); continue; }
+        if (bytes_path) {
+            if (rp.err.on) emit_body_pieces<false>(rp, rec + H, unit, 0, d.a0, L, lane, 32, Ls, !(d.flags & 1u));
+            else emit_body_pieces<false>(rp, rec + H, unit, 0, d.a0, L, lane, 32);
+            __syncwarp(); continue;
+        }
         const uint32_t S = piece_len(L, true), lo = lane * S;
-        const uint32_t nb = lo < L ? min(S, L - lo) : 0u, ng = (nb + 3u) >> 2;        /* bases and 4-base groups of this lane's piece */
-        uint8_t *seq = rec + H + 1 + lo, *qual = rec + H + L + 4 + lo;
+        const uint32_t nb = lo < L ? min(S, L - lo) : 0u, ng = (nb + 3u) >> 2;        /* qualities and their 4-base groups in this lane's piece */
+        const uint32_t nbs = lo < Ls ? min(S, Ls - lo) : 0u, ngs = (nbs + 3u) >> 2;   /* ... and bases */
+        uint8_t *seq = rec + H + 1 + lo, *qual = rec + H + Ls + 4 + lo;
         RunLine ls, lq;
-        rl_open(ls, seq, nb); rl_open(lq, qual, nb);
+        rl_open(ls, seq, nbs); rl_open(lq, qual, nb);
         Mwc1 qc{}, ec{};
         if (QM != QM_CONST && nb) mwc1_seed(rp, qc, ec, lane, 1, uint32_t(unit), uint32_t(unit >> 32));
         /* The piece's first LONG_EVENTS substitution events are walked now (position | new quality << 16 | m << 24, a list
@@ -1327,7 +1473,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         }
         uint32_t ev_i = 0, ev_cur = nev ? lds32m(ev_s) : 0xffffffffu;
         const uint64_t a = d.a0 + lo;
-        const uint32_t *pw = rp.packed + (a >> 4);
+        const uint32_t *pw = (rp.err.on ? rp.epacked : rp.packed) + (a >> 4);      /* edited reads come from the scratch copy */
         const uint32_t s2 = 2u * (uint32_t(a) & 15u);
         /* Words of the 2-bit copy reach the lane through a ring in shared memory filled by asynchronous copies LONG_AHEAD
          * turns ahead of their use (with 32 lanes on 32 different lines some lane misses L1 nearly every turn, and a
@@ -1341,7 +1487,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         }
         asm volatile("cp.async.wait_group %0;" ::"n"(LONG_AHEAD) : "memory");           /* word 0 has landed */
         uint32_t w_lo = lds32m(ring_s);
-        const uint32_t quads = (ng + 3u) >> 2, T = __reduce_max_sync(0xffffffffu, quads);
+        const uint32_t quads = (ng + 3u) >> 2, quads_s = (ngs + 3u) >> 2, T = __reduce_max_sync(0xffffffffu, quads);
         uint32_t first_s = 0, first_q = 0, vs = 0, vq = 0;
         const uint32_t tile_s = base_s + SM_QTAB + qtab_bytes(QM, rp.phred.cb, rp.phred.npos) + uint32_t(DIRECT_THREADS / 32) * (LONG_RING * 128u) + (threadIdx.x >> 5) * 8192u;
         for (uint32_t qd = 0; qd < T; ++qd) {             /* sixteen bases = one word of the 2-bit copy */
@@ -1362,7 +1508,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
                     sw[h] = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
                 }
                 if (qd == 0) { first_s = sw[0]; first_q = qw[0]; }
-                rl_quad_staged(ls, 4u * qd, sw[0], sw[1], sw[2], sw[3], tile_s, lane, qd & 7u, vs);
+                if (qd < quads_s) rl_quad_staged(ls, 4u * qd, sw[0], sw[1], sw[2], sw[3], tile_s, lane, qd & 7u, vs);
                 rl_quad_staged(lq, 4u * qd, qw[0], qw[1], qw[2], qw[3], tile_s + 4096u, lane, qd & 7u, vq);
             }
             w_lo = w_hi;
@@ -1374,10 +1520,8 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");      /* nothing of this read's copies may land in the next read's ring */
-        if (ng) {
-            const uint32_t kl = 4u * (quads - 1u);
-            rl_close(ls, kl, ng); rl_edges(ls, kl, ng, first_s); rl_close(lq, kl, ng); rl_edges(lq, kl, ng, first_q);
-        }
+        if (ngs) { const uint32_t kl = 4u * (quads_s - 1u); rl_close(ls, kl, ngs); rl_edges(ls, kl, ngs, first_s); }
+        if (ng) { const uint32_t kl = 4u * (quads - 1u); rl_close(lq, kl, ng); rl_edges(lq, kl, ng, first_q); }
         if (QM != QM_CONST && rp.phred.has_sub) {
             for (uint32_t k = 0; k < nev; ++k) {          /* the listed events' qualities */
                 const uint32_t e = lds32m(ev_s + k * (DIRECT_THREADS * 4u));

@@ -77,6 +77,8 @@ struct simmr_ctx {
     ProfileModel model;
     DevMem d_phred, d_gap, d_qsub, d_rl_e, d_rl_lo, d_rl_hi, d_is_e, d_is_lo, d_is_hi;
     DevMem d_acc, d_plthr, d_rodds, d_ralias, d_roff, d_rlo, d_rhi;
+    DevMem d_err_direct, d_err_ref, d_err_keep, d_err_row, d_err_cb, d_err_entries, d_err_alts;     /* k-mer error tables */
+    DevMem d_epacked, d_ebases;                    /* edited reads of a batch (k_kmer_errors) */
     /* run scratch */
     DevMem d_unit_start, d_counters, d_out[2];
     DevMem d_sizes[2], d_offsets[2], d_block_sums[2], d_desc[2], d_desc_ext[2];   /* per-batch scratch, two sets: batch b+1 is prepared while batch b is formatted */
@@ -229,6 +231,12 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     for (uint32_t r = 0; r < 10; ++r) { rp.rk[2 * r] = uint32_t(seed) + r * 0x9E3779B9u; rp.rk[2 * r + 1] = uint32_t(seed >> 32) + r * 0xBB67AE85u; }
     rp.counters = ctx->d_counters.as<unsigned long long>();
     rp.stage_cap = pl.stage_cap; rp.one = 1;
+    if (m.err.on) {
+        rp.err = ErrTab{1u, m.err.k, uint32_t(m.err.ref.size()), 0u, ctx->d_err_direct.as<uint32_t>(), ctx->d_err_ref.as<uint32_t>(), ctx->d_err_keep.as<uint32_t>(),
+                        ctx->d_err_row.as<uint32_t>(), ctx->d_err_cb.as<uint32_t>(), ctx->d_err_entries.as<uint32_t>(), ctx->d_err_alts.as<uint32_t>()};
+        rp.epacked = ctx->d_epacked.as<uint32_t>(); rp.ebases = ctx->d_ebases.as<uint8_t>();
+        if (!pl.tiles) rp.stage_cap = 0xffffffffu;       /* k_segment_sort only orders the reads here */
+    }
 }
 
 /* The batch pipeline shared by simulate and replay. */
@@ -237,36 +245,15 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     Plan pl;
     int rc = make_plan(ctx, replay, pl);
     if (rc) return rc;
-    if (measure_only) {      /* geometry + record sizes only: what the units would occupy in the FASTQ stream */
-        const uint64_t batch = std::min<uint64_t>(ue - ub, 1ull << 24);
-        CU(ctx->d_sizes[0].reserve(batch * 4)); CU(ctx->d_desc[0].reserve(batch * sizeof(UnitRec))); CU(ctx->d_desc_ext[0].reserve(batch * sizeof(UnitExt)));
-        CU(ctx->d_block_sums[0].reserve(((batch + SIZES_THREADS - 1) / SIZES_THREADS) * 8));
-        CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
-        RunParams rp; fill_params(ctx, rp, seed, opts ? opts->read_id_base : 0, pl);
-        rp.sizes = ctx->d_sizes[0].as<uint32_t>(); rp.desc = ctx->d_desc[0].as<UnitRec>(); rp.desc_ext = ctx->d_desc_ext[0].as<UnitExt>(); rp.block_sums = ctx->d_block_sums[0].as<uint64_t>();
-        simmr_stats st{};
-        for (uint64_t u = ub; u < ue; u += batch) {
-            const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
-            rp.batch_begin = u; rp.batch_units = n;
-            k_unit_sizes<false><<<(n + SIZES_THREADS - 1) / SIZES_THREADS, SIZES_THREADS, 0, ctx->compute>>>(rp, rd);
-            ++st.kernel_launches;
-        }
-        CU(cudaGetLastError());
-        unsigned long long ctr[8];
-        CU(cudaMemcpyAsync(ctr, ctx->d_counters.p, sizeof ctr, cudaMemcpyDeviceToHost, ctx->compute));
-        CU(cudaStreamSynchronize(ctx->compute));
-        st.units = ue - ub; st.clamped = ctr[0]; st.algorithmic_bytes = ctr[1]; st.bases = ctr[2]; st.records = ctr[3];
-        st.bytes = ctr[1] - ctr[2];
-        ctx->stats = st;
-        return SIMMR_OK;
-    }
     /* Staging per batch: 16 GiB (of 180) when nothing has to cross PCIe, less when the device is short of memory.  Few
      * large launches beat many small ones twice: every launch fills the tables of 148 CTAs and ends with a partly idle
      * GPU (short reads: 2 -> 16 GiB is +7 %), and a long read is budgeted at its largest possible size (131 KB) although
      * it averages 40 KB — 2 GiB were 16 K reads per launch, 7 per warp, and the last warps' long reads left the GPU half
      * idle (+22 %). */
-    uint64_t target_bytes = sink ? (256ull << 20) : (16384ull << 20);
-    if (!sink) {
+    const bool errs = ctx->model.err.on && !replay;        /* k-mer error injection between sizing and formatting */
+    uint64_t target_bytes = sink ? (256ull << 20) : errs ? (4096ull << 20) : (16384ull << 20);
+    if (measure_only) target_bytes = errs ? (1024ull << 20) : (uint64_t(pl.max_unit_bytes) << 24);
+    if (!sink && !measure_only) {
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
         free_b += ctx->d_out[0].bytes;                    /* what this context already holds for staging can be reused */
@@ -282,14 +269,18 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     for (int k = 0; k < 2; ++k) {
         CU(ctx->d_sizes[k].reserve(batch * 4)); CU(ctx->d_desc[k].reserve(batch * sizeof(UnitRec))); CU(ctx->d_desc_ext[k].reserve(batch * sizeof(UnitExt)));
         CU(ctx->d_offsets[k].reserve((batch + 1) * 8)); CU(ctx->d_block_sums[k].reserve(size_t(max_blocks) * 8));
-        if (pl.tiles) {
+        if (pl.tiles || errs) {
             CU(ctx->d_seg_perm[k].reserve(max_segs * SEG_UNITS * 2)); CU(ctx->d_seg_tiles[k].reserve(max_segs * SEG_UNITS * 2));
             CU(ctx->d_seg_ntiles[k].reserve(max_segs * 4));
         }
     }
+    if (errs) {      /* scratch for a batch's edited reads: as many bases as the batch has FASTQ bytes, 16 more per read (err_scratch_base) */
+        const uint64_t nb = out_cap + 16 * batch + 64;
+        CU(ctx->d_epacked.reserve(nb / 4 + 4 * PACK_PAD_WORDS)); CU(ctx->d_ebases.reserve(nb));
+    }
     CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
     const bool guard = getenv("SIMMR_DEBUG_GUARD") != nullptr, dbg_sync = getenv("SIMMR_DEBUG_SYNC") != nullptr;
-    const int nbuf = sink ? 2 : 1;
+    const int nbuf = measure_only ? 0 : sink ? 2 : 1;
     for (int b = 0; b < nbuf; ++b) CU(ctx->d_out[b].reserve(out_cap));
     if (sink) { for (int b = 0; b < 2; ++b) CU(ctx->h_out[b].reserve(out_cap)); }
     CU(ctx->h_total.reserve(2 * sizeof(uint64_t)));
@@ -320,7 +311,9 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     /* geometry, sizes and byte offsets of batch number `nb` on the prep stream, into scratch set nb & 1: the small kernels
      * need no shared memory and share the SMs with the format kernel of the batch before */
     bool done_live[2] = {false, false};
-    cudaStream_t prep = getenv("SIMMR_PREP_SERIAL") ? ctx->compute : ctx->prep;     /* SIMMR_PREP_SERIAL: everything on one stream (kernel timings without co-runners) */
+    uint64_t prep_launches = 0;
+    /* error injection reads and writes one scratch set per context: its batches are prepared on the compute stream, one at a time */
+    cudaStream_t prep = (errs || measure_only || getenv("SIMMR_PREP_SERIAL")) ? ctx->compute : ctx->prep;     /* SIMMR_PREP_SERIAL: everything on one stream (kernel timings without co-runners) */
     auto prepare = [&](uint64_t u, uint64_t nb) -> int {
         const int k = int(nb & 1);
         const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
@@ -332,8 +325,15 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         else k_unit_sizes<false><<<nblk, SIZES_THREADS, 0, prep>>>(r, rd);
         if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("k_unit_sizes: ") + cudaGetErrorString(e_)); }
         k_scan_blocks<<<1, 1024, 0, prep>>>(r, nblk);
-        if (pl.tiles) k_segment_sort<<<(n + SEG_UNITS - 1) / SEG_UNITS, SEG_THREADS, 0, prep>>>(r);     /* offsets + size-sorted tiles */
+        if (pl.tiles || errs) k_segment_sort<<<(n + SEG_UNITS - 1) / SEG_UNITS, SEG_THREADS, 0, prep>>>(r);     /* offsets + size-sorted tiles */
         else k_unit_offsets<<<nblk, SIZES_THREADS, 0, prep>>>(r);
+        if (errs) {      /* edit the reads (size-sorted order), then offsets again from the edited sizes */
+            k_kmer_errors<<<(n + 255) / 256, 256, 0, prep>>>(r);
+            k_block_sums<<<nblk, SIZES_THREADS, 0, prep>>>(r);
+            k_scan_blocks<<<1, 1024, 0, prep>>>(r, nblk);
+            k_unit_offsets<<<nblk, SIZES_THREADS, 0, prep>>>(r);
+            prep_launches += 4;
+        }
         CU(cudaGetLastError());
         if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("scan kernels: ") + cudaGetErrorString(e_)); }
         CU(cudaEventRecord(ev_prep[k], prep));
@@ -341,13 +341,16 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     };
     CU(cudaEventRecord(ev_start, ctx->compute));
     CU(cudaStreamWaitEvent(prep, ev_start, 0));
-    rc = prepare(ub, 0); if (rc) return rc;
+    const bool ahead = !errs && !measure_only;               /* batch b + 1 is prepared beside batch b's format kernel */
+    if (ahead) { rc = prepare(ub, 0); if (rc) return rc; }
     int slot = 0; uint64_t nbatch = 0;
     for (uint64_t u = ub; u < ue; u += batch, ++nbatch) {
         const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
         const int k = int(nbatch & 1);
+        if (!ahead) { rc = prepare(u, nbatch); if (rc) return rc; st.kernel_launches += 3; }
+        if (measure_only) continue;                              /* geometry, sizes (and edits) only: what the units occupy in the FASTQ stream */
         if (sink) { rc = drain(slot); if (rc) return rc; }       /* slot's buffers are about to be reused */
-        if (u + batch < ue) { rc = prepare(u + batch, nbatch + 1); if (rc) return rc; }
+        if (ahead && u + batch < ue) { rc = prepare(u + batch, nbatch + 1); if (rc) return rc; }
         scratch(rp, k);
         rp.batch_begin = u; rp.batch_units = n; rp.out = ctx->d_out[slot].as<uint8_t>();
         if (guard) CU(cudaMemsetAsync(ctx->d_out[slot].p, 0xA5, out_cap, ctx->compute));
@@ -378,7 +381,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
             CU(cudaMemcpy(tail, rp.out + total, 64, cudaMemcpyDeviceToHost));
             for (int b = 0; b < 64; ++b) if (tail[b] != 0xA5) return fail(ctx, SIMMR_E_CUDA, "guard bytes after the batch output were overwritten");
         }
-        st.kernel_launches += 4;
+        st.kernel_launches += ahead ? 4 : 1;
         if (sink) {
             CU(cudaEventRecord(ev_fmt[slot], ctx->compute));
             CU(cudaEventSynchronize(ev_total[slot]));            /* byte count known while the format kernel runs */
@@ -400,9 +403,10 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     float ms = 0; CU(cudaEventElapsedTime(&ms, ev_start, ev_stop));
     unsigned long long ctr[8];
     CU(cudaMemcpy(ctr, ctx->d_counters.p, sizeof ctr, cudaMemcpyDeviceToHost));
-    st.units = ue - ub; st.clamped = ctr[0]; st.algorithmic_bytes = ctr[1]; st.bases = ctr[2]; st.records = ctr[3];
-    st.bytes = ctr[1] - ctr[2];                                   /* (3L+H+5) - L */
-    st.device_ms = ms; st.format_ms = format_ms;
+    /* ctr[5]: bases deleted by k-mer error injection — read from the genome, absent from the sequence line */
+    st.units = ue - ub; st.clamped = ctr[0]; st.algorithmic_bytes = ctr[1] - ctr[5]; st.bases = ctr[2] - ctr[5]; st.records = ctr[3];
+    st.bytes = ctr[1] - ctr[2] - ctr[5];                          /* (3L+H+5) - L, less the deleted bases */
+    st.device_ms = ms; st.format_ms = format_ms; st.kernel_launches += prep_launches;
     cudaEventDestroy(ev_start); cudaEventDestroy(ev_stop); cudaEventDestroy(ev_f0); cudaEventDestroy(ev_f1);
     for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_total[b]); cudaEventDestroy(ev_fmt[b]); cudaEventDestroy(ev_copy[b]); cudaEventDestroy(ev_prep[b]); cudaEventDestroy(ev_done[b]); }
     ctx->stats = st;
@@ -538,6 +542,12 @@ int simmr_error_profile_set(simmr_ctx *ctx, const simmr_eprofile_desc *d) {
     CU(ctx->d_acc.upload(m.acc_lut, 256, s)); CU(ctx->d_plthr.upload(m.pl_thr, 64, s));
     CU(ctx->d_rodds.upload(m.r_odds.data(), m.r_odds.size(), s)); CU(ctx->d_ralias.upload(m.r_alias.data(), m.r_alias.size(), s));
     CU(ctx->d_roff.upload(m.r_off.data(), m.r_off.size(), s)); CU(ctx->d_rlo.upload(m.r_lo.data(), m.r_lo.size(), s)); CU(ctx->d_rhi.upload(m.r_hi.data(), m.r_hi.size(), s));
+    if (m.err.on) {
+        CU(ctx->d_err_direct.upload(m.err.direct.data(), m.err.direct.size(), s)); CU(ctx->d_err_ref.upload(m.err.ref.data(), m.err.ref.size(), s));
+        CU(ctx->d_err_keep.upload(m.err.keep_thr.data(), m.err.keep_thr.size(), s)); CU(ctx->d_err_row.upload(m.err.row.data(), m.err.row.size(), s));
+        CU(ctx->d_err_cb.upload(m.err.cb.data(), m.err.cb.size(), s)); CU(ctx->d_err_entries.upload(m.err.entries.data(), m.err.entries.size(), s));
+        CU(ctx->d_err_alts.upload(m.err.alts.data(), m.err.alts.size(), s));
+    }
     CU(cudaStreamSynchronize(s));
     ctx->have_profile = true;
     return SIMMR_OK;

@@ -45,7 +45,14 @@ struct LenTab {
     const uint32_t *entries, *lo, *hi;
 };
 
-struct GammaConst { double d, c, scale; };   /* perfect_long.rs:48-54 via rand_distr gamma.rs */
+struct GammaConst { double d, c, scale; };
+
+/* k-mer error injection tables of a custom-long profile (ErrModel in host_model.hpp), device pointers */
+struct ErrTab {
+    uint32_t on, k, n_ref, pad_;
+    const uint32_t *direct;        /* 2 words per A,C,G,T k-mer (2-bit code): keep threshold, row + 1 (0: not observed) */
+    const uint32_t *ref, *keep_thr, *row, *cb, *entries, *alts;
+};   /* perfect_long.rs:48-54 via rand_distr gamma.rs */
 
 /* which reference arithmetic the replay path applies per base */
 enum : uint32_t { RP_CONST = 0, RP_NORMAL_FLOOR = 1, RP_ACCURACY = 2, RP_ALIAS = 3 };

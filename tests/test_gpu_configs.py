@@ -22,7 +22,10 @@ def full_run(engine, gs, prof, reads, seed=42):
     st = engine.simulate(reads, seed)                         # device-resident: FASTQ bytes stay in HBM staging
     total = engine.total_units(reads)
     assert st["units"] == total
-    assert st["algorithmic_bytes"] == st["bytes"] + st["bases"]          # (3L+H+5) = (2L+H+5) + L, BASELINE.md §3
+    if prof.err_table()["k"] == 0:
+        assert st["algorithmic_bytes"] == st["bytes"] + st["bases"]      # (3L+H+5) = (2L+H+5) + L, BASELINE.md §3
+    else:
+        assert st["algorithmic_bytes"] > st["bytes"] + st["bases"]       # bases deleted by k-mer errors were read, not written
     assert engine.measure(reads, seed) == (st["bytes"], st["records"])    # the geometry-only pass agrees with the run
     return st, total
 
@@ -141,13 +144,15 @@ def test_c4_long_reads_10m(engine, which):
     """C4: 10 M long reads with gamma lengths from 50 genomes — (a) minimal-long, (b) an ONT-style custom-long blob
     (empirical Phreds, k-mer error injection, custom_long.rs:187-232)."""
     gs = H.config_genomes(50, 2_000_000, 6_000_000, (1, 4), seed=4, min_contig=100_000)
-    prof = S.MinimalLongErrorProfile(30) if which == "minimal-long" else S.CustomLongErrorProfile(H.ont_blob())
+    prof = S.MinimalLongErrorProfile(30) if which == "minimal-long" else S.CustomLongErrorProfile(H.ont_blob_with_kmers(k=7, n_alts=20)[0])
     reads, _ = S.UniformAbundanceProfile().determine_abundances(10_000_000, 50)
     assert reads.tolist() == [200_000] * 50
     st, total = full_run(engine, gs, prof, reads)
     assert total == 10_000_000 and st["records"] == total
     mean_len = st["bases"] / st["records"]
-    assert 19_000 < mean_len < 20_500            # Gamma(1.7777779, 11250) floored and saturated at 65 535: E = 19 822 (SURVEY §8d)
+    # Gamma(1.7777779, 11250) floored and saturated at 65 535: E = 19 822 (SURVEY §8d); the synthetic alt-k-mer table
+    # deletes about one base in fourteen
+    assert (19_000 < mean_len < 20_500) if which == "minimal-long" else (17_000 < mean_len < 19_800)
     check_slices(engine, gs, prof, reads, [(0, 24), (4_999_990, 24), (total - 24, 24)], batch_units=7)
 
 

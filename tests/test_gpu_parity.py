@@ -179,6 +179,62 @@ def test_long_reads_native(engine, kind, compat):
     assert len(recs) == 96 and all(len(s) == len(q) for _, s, q in recs)
 
 
+@pytest.mark.parametrize("k,n_alts", [(5, 20), (3, 4), (7, 6)])
+def test_long_reads_kmer_error_injection(engine, k, n_alts):
+    """custom-long blobs with an alt-k-mer table: simulate_errors (custom_long.rs:187-232) on the device, between the
+    qualities and the (identity) point mutations as simulate.rs:497-503 orders them.  Deletions make the sequence line
+    shorter than the quality line.  Genomes with N runs take the byte path (N is a k-mer digit), compat mode adds short
+    and empty reads, small batches put seams between the sizing, editing and formatting passes."""
+    blob, kmers = H.ont_blob_with_kmers(k=k, n_alts=n_alts)
+    prof = S.CustomLongErrorProfile(blob)
+    gs = H.synth_genomes(3, (1, 3), (21000, 90000), seed=41, with_n=True)
+    data = check_native(engine, gs, prof, [40, 25, 31], 1234)
+    recs = H.parse_fastq(data)
+    assert len(recs) == 96 and all(len(s) <= len(q) for _, s, q in recs) and any(len(s) < len(q) for _, s, q in recs)
+    # every record against the reference loop itself: window from the header, the oracle's picks, orc_simulate_errors
+    oprof = H.oracle_profile(prof)
+    coff = {gs.contig_id(c): int(gs.contig_off[c]) for c in range(gs.n_contigs)}
+    seq = gs.bases.tobytes()
+    for u, (h, s, q) in enumerate(recs[:20]):
+        hd = h.decode()
+        o = coff[hd.split("sid=")[1].split("|")[0].encode()]
+        sp, ep = int(hd.split("|sp=")[1].split("|")[0]), int(hd.split("|ep=")[1].split("|")[0])
+        window = seq[o + sp:o + ep]
+        assert len(q) == len(window)
+        edited, picks = po.native_errors(oprof, 1234, u, window)
+        assert s == edited == po.simulate_errors(window, k, kmers, picks)
+    assert engine.simulate_bytes([40, 25, 31], 1234, batch_units=7) == data
+    check_native(engine, gs, S.CustomLongErrorProfile(blob, compat_start=True), [150, 90, 3], 31, batch_units=64)
+
+
+def test_kmer_errors_reference_known_answer_on_the_device(engine):
+    """The reference's own known answer (custom_long.rs:299-343: k = 3, ACC -> CAT, ATC -> ATC, TCG -> TGT turns ACCCG
+    into CATGT) through the device: every listed k-mer has a single alternate, so a native run is deterministic and equals
+    the reference loop; a contig made of ACCCG repeats shows the literal."""
+    kmers = [(H.kmer_code(b"ACC"), [(H.kmer_code(b"CAT"), 1.0)]), (H.kmer_code(b"ATC"), [(H.kmer_code(b"ATC"), 1.0)]),
+             (H.kmer_code(b"TCG"), [(H.kmer_code(b"TGT"), 1.0)])]
+    quality = [([1.0] * 71, [(i, i) for i in range(70)])]
+    blob = H.make_blob(quality, ([1.0], [(20000, 20000)]), None, kmers=kmers, kmer_size=3, rl_mean=19800.0, rl_std=15000.0, is_long=True)
+    prof = S.CustomLongErrorProfile(blob)
+    rng = np.random.default_rng(5)
+    rand = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 30000)]
+    rep = np.frombuffer(b"ACCCG" * 6000, np.uint8)
+    gs = S.GenomeSet.from_contigs([("kat", [(b"random", rand), (b"repeat", rep)])])
+    data = check_native(engine, gs, prof, [60], 3)
+    assert po.simulate_errors(b"ACCCG", 3, kmers, [0, 0, 0]) == b"CATGT"
+    seen = 0
+    for h, s, q in H.parse_fastq(data):
+        hd = h.decode()
+        sp, ep = int(hd.split("|sp=")[1].split("|")[0]), int(hd.split("|ep=")[1].split("|")[0])
+        src = (rep if "sid=repeat" in hd else rand).tobytes()[sp:ep]
+        want = po.simulate_errors(src, 3, kmers, [0] * len(src))
+        assert s == want and len(s) == len(q)
+        if "sid=repeat" in hd and sp % 5 == 0 and len(src) >= 5:
+            assert s[:5] == b"CATGT"
+            seen += 1
+    assert seen > 0
+
+
 def test_long_reads_replay(engine):
     gs = H.synth_genomes(2, (1, 2), (21000, 60000), seed=43)
     og = po.Genomes.from_set(gs)
