@@ -90,15 +90,28 @@ typedef struct {
     int32_t  has_seed;
     uint32_t read_id_base;   /* first read id (simulate.rs:85-89 starts at 0)    */
     const char *header_format;   /* --read-header-format; NULL = cli.rs:196 default */
-    uint64_t unit_begin, unit_end;  /* shard of the global unit index space;
-                                       0,0 = all.  unit = pair (PE) or long read */
+    uint64_t unit_begin, unit_end;  /* shard of the global unit index space (unit = pair (PE) or long read).
+                                       Without SIMMR_RUN_EXPLICIT_RANGE, 0,0 = all; with it the range is taken
+                                       literally, so an empty shard that starts at 0 stays empty */
     uint64_t batch_units;    /* units per device batch; 0 = library default      */
+    uint32_t flags;          /* SIMMR_RUN_*                                      */
+    uint32_t pad_;
 } simmr_run_opts;
+#define SIMMR_RUN_EXPLICIT_RANGE 1u
 
 /* One chunk of FASTQ bytes, in file order.  `data` is pinned host memory owned
- * by the library, valid until the callback returns.  Non-zero return aborts. */
+ * by the library, valid until the callback returns.  Non-zero return aborts.
+ * The callback runs on a writer thread owned by the library (one per run), never
+ * concurrently with itself; the launching thread keeps the GPU busy meanwhile. */
 typedef int (*simmr_sink_fn)(void *user, const uint8_t *data, uint64_t len,
                              uint64_t first_unit, uint64_t n_units);
+/* A sink that returns SIMMR_SINK_RETAINED keeps `data` after it returns (e.g. for an I/O thread of its own) and gives
+ * it back with simmr_chunk_release(data), from any thread.  A context owns SIMMR_RING_BUFFERS pinned buffers; the run
+ * waits while all of them are retained, and every retained chunk must be released before the run's entry point returns
+ * (the entry point waits for that). */
+#define SIMMR_SINK_RETAINED 2
+#define SIMMR_RING_BUFFERS  4
+void simmr_chunk_release(const uint8_t *data);
 
 typedef struct {
     uint64_t units, records, bases, bytes;  /* produced by the last run          */
@@ -167,6 +180,23 @@ uint64_t simmr_total_units(const simmr_ctx *ctx, const uint64_t *reads_per_genom
 int  simmr_measure(simmr_ctx *ctx, const uint64_t *reads_per_genome, const simmr_run_opts *opts,
                    uint64_t *bytes, uint64_t *records);
 int  simmr_stats_get(const simmr_ctx *ctx, simmr_stats *out);
+
+/* ---- the same path over several GPUs of one box ----- */
+/* One context per device, genomes and profile replicated.  A run is cut into batches of consecutive units; batch j is
+ * produced by device j mod n on that device's own launch thread, and ONE writer thread hands the batches to the sink in
+ * file order — the bytes are those of the one-GPU run (the reference appends genome after genome, main.rs:201-206).
+ * No device collective.  devices: CUDA ordinals, n >= 1. */
+typedef struct simmr_multi simmr_multi;
+int  simmr_multi_create(const int *devices, int n_devices, simmr_multi **out);
+void simmr_multi_destroy(simmr_multi *m);
+int  simmr_multi_genomes_load(simmr_multi *m, const simmr_genome_set *set);
+int  simmr_multi_error_profile_set(simmr_multi *m, const simmr_eprofile_desc *desc);
+uint64_t simmr_multi_total_units(const simmr_multi *m, const uint64_t *reads_per_genome);
+int  simmr_multi_simulate(simmr_multi *m, const uint64_t *reads_per_genome, const simmr_run_opts *opts,
+                          simmr_sink_fn sink, void *user);
+/* sums over the devices; device_ms / format_ms are the slowest device's */
+int  simmr_multi_stats_get(const simmr_multi *m, simmr_stats *out);
+const char *simmr_multi_last_error(const simmr_multi *m);
 
 /* ---- host-side I/O of the same path (genome.rs, files.rs, encoding.rs) -- */
 typedef struct simmr_genome_builder simmr_genome_builder;

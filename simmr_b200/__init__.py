@@ -6,7 +6,7 @@ from . import _native
 from .api import (DEFAULT_HEADER_FORMAT, SimmrError, ErrorProfile, PerfectShortErrorProfile,
                   MinimalShortErrorProfile, PerfectLongErrorProfile, MinimalLongErrorProfile,
                   CustomShortErrorProfile, CustomLongErrorProfile, AbundanceProfile, UniformAbundanceProfile,
-                  ExactAbundanceProfile, CustomAbundanceProfile, GenomeSet, Draws, Engine, parse_genome_file,
+                  ExactAbundanceProfile, CustomAbundanceProfile, GenomeSet, Draws, Engine, MultiEngine, parse_genome_file,
                   write_metadata, write_to_fastq)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -42,7 +42,10 @@ class AProfileDesc(C.Structure):
 class RunOpts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("has_seed", C.c_int32), ("read_id_base", C.c_uint32),
                 ("header_format", C.c_char_p), ("unit_begin", C.c_uint64), ("unit_end", C.c_uint64),
-                ("batch_units", C.c_uint64)]
+                ("batch_units", C.c_uint64), ("flags", C.c_uint32), ("pad_", C.c_uint32)]
+
+
+RUN_EXPLICIT_RANGE = 1
 
 
 class Stats(C.Structure):
@@ -70,6 +73,8 @@ EXPORTS = [
     "simmr_builder_add_fasta", "simmr_builder_filter", "simmr_builder_view", "simmr_builder_genome_size",
     "simmr_builder_error", "simmr_parse_genome_file", "simmr_write_metadata", "simmr_debug_phred_table",
     "simmr_debug_len_table", "simmr_debug_err_table", "simmr_debug_philox4x32_10", "simmr_version",
+    "simmr_multi_create", "simmr_multi_destroy", "simmr_multi_genomes_load", "simmr_multi_error_profile_set",
+    "simmr_chunk_release", "simmr_multi_total_units", "simmr_multi_simulate", "simmr_multi_stats_get", "simmr_multi_last_error",
 ]
 
 _lib = None
@@ -101,6 +106,19 @@ def lib():
         L.simmr_total_units.argtypes = [C.c_void_p, u64p]
         L.simmr_total_units.restype = C.c_uint64
         L.simmr_stats_get.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.simmr_chunk_release.argtypes = [C.c_void_p]
+        L.simmr_chunk_release.restype = None
+        L.simmr_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        L.simmr_multi_destroy.argtypes = [C.c_void_p]
+        L.simmr_multi_destroy.restype = None
+        L.simmr_multi_genomes_load.argtypes = [C.c_void_p, C.POINTER(GenomeSetC)]
+        L.simmr_multi_error_profile_set.argtypes = [C.c_void_p, C.POINTER(EProfileDesc)]
+        L.simmr_multi_total_units.argtypes = [C.c_void_p, u64p]
+        L.simmr_multi_total_units.restype = C.c_uint64
+        L.simmr_multi_simulate.argtypes = [C.c_void_p, u64p, C.POINTER(RunOpts), C.c_void_p, C.c_void_p]
+        L.simmr_multi_stats_get.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.simmr_multi_last_error.argtypes = [C.c_void_p]
+        L.simmr_multi_last_error.restype = C.c_char_p
         L.simmr_builder_create.argtypes = [C.POINTER(C.c_void_p)]
         L.simmr_builder_destroy.argtypes = [C.c_void_p]
         L.simmr_builder_destroy.restype = None

@@ -371,8 +371,9 @@ class Engine:
 
     def _opts(self, seed, header_format, unit_begin, unit_end, read_id_base, batch_units):
         hf = header_format.encode() if isinstance(header_format, str) else header_format
-        return N.RunOpts(0 if seed is None else seed, int(seed is not None), read_id_base, hf, unit_begin, unit_end,
-                         batch_units)
+        explicit = unit_end is not None          # (0, 0) is then an empty range, not "everything" (an empty first shard)
+        return N.RunOpts(0 if seed is None else seed, int(seed is not None), read_id_base, hf, unit_begin if explicit else 0,
+                         unit_end if explicit else 0, batch_units, N.RUN_EXPLICIT_RANGE if explicit else 0, 0)
 
     def _run(self, fn, first, opts, sink):
         keep = None
@@ -393,9 +394,12 @@ class Engine:
         rc = fn(self._ctx, first, C.byref(opts), cb, None)
         if sink is not None and keep is not None and tramp.err is not None:
             raise tramp.err
-        _check(rc, self._ctx)
+        self._check_rc(rc)
 
-    def simulate(self, reads_per_genome, seed=None, sink=None, header_format=None, unit_begin=0, unit_end=0,
+    def _check_rc(self, rc):
+        return _check(rc, self._ctx)
+
+    def simulate(self, reads_per_genome, seed=None, sink=None, header_format=None, unit_begin=0, unit_end=None,
                  read_id_base=0, batch_units=0):
         """simmr_simulate: native Philox mode.  sink(chunk ndarray, first_unit, n_units);
         sink=None keeps the FASTQ bytes in device staging (device-side throughput)."""
@@ -404,7 +408,7 @@ class Engine:
         self._run(N.lib().simmr_simulate, _p(r, N.u64p), o, sink)
         return self.stats()
 
-    def measure(self, reads_per_genome, seed, header_format=None, unit_begin=0, unit_end=0, read_id_base=0):
+    def measure(self, reads_per_genome, seed, header_format=None, unit_begin=0, unit_end=None, read_id_base=0):
         """simmr_measure: (FASTQ bytes, records) a unit range will produce; geometry kernel only."""
         r = np.ascontiguousarray(reads_per_genome, np.uint64)
         o = self._opts(seed, header_format, unit_begin, unit_end, read_id_base, 0)
@@ -417,7 +421,7 @@ class Engine:
         self.simulate(reads_per_genome, seed, sink=lambda a, f, n: chunks.append(a.tobytes()), **kw)
         return b"".join(chunks)
 
-    def replay(self, draws, sink=None, header_format=None, unit_begin=0, unit_end=0, read_id_base=0, batch_units=0):
+    def replay(self, draws, sink=None, header_format=None, unit_begin=0, unit_end=None, read_id_base=0, batch_units=0):
         d = draws.as_c()
         o = self._opts(0, header_format, unit_begin, unit_end, read_id_base, batch_units)
         self._run(N.lib().simmr_replay, C.byref(d), o, sink)
@@ -453,6 +457,69 @@ class Engine:
     def simulate_long_reads(self, num_reads, genomes, error_profile, abundance_profile, seed=None, **kw):
         """simulate.rs:323-406."""
         return self._simulate_reads(num_reads, genomes, error_profile, abundance_profile, seed, True, **kw)
+
+
+class MultiEngine(Engine):
+    """simmr_multi: one context per listed device behind one handle.  A run's batches are dealt round-robin to the
+    devices; a single writer thread inside the library hands them to the sink in file order, so the bytes are those of a
+    one-GPU run."""
+
+    def __init__(self, devices):
+        self._ctx = C.c_void_p()
+        self.devices = list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        rc = N.lib().simmr_multi_create(arr, len(self.devices), C.byref(self._ctx))
+        if rc < 0:
+            raise SimmrError(rc, N.lib().simmr_multi_last_error(None).decode(errors="replace"))
+        self.genomes = None
+        self.profile = None
+
+    def _mcheck(self, rc):
+        if rc < 0:
+            raise SimmrError(rc, N.lib().simmr_multi_last_error(self._ctx).decode(errors="replace"))
+        return rc
+
+    _check_rc = _mcheck
+
+    def close(self):
+        if self._ctx:
+            N.lib().simmr_multi_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def load_genomes(self, gs):
+        c = gs.as_c()
+        self._mcheck(N.lib().simmr_multi_genomes_load(self._ctx, C.byref(c)))
+        self.genomes = gs
+
+    def set_error_profile(self, prof):
+        d = prof.desc()
+        self._mcheck(N.lib().simmr_multi_error_profile_set(self._ctx, C.byref(d)))
+        self.profile = prof
+
+    def total_units(self, reads_per_genome):
+        r = np.ascontiguousarray(reads_per_genome, np.uint64)
+        return N.lib().simmr_multi_total_units(self._ctx, _p(r, N.u64p))
+
+    def stats(self):
+        s = N.Stats()
+        self._mcheck(N.lib().simmr_multi_stats_get(self._ctx, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in N.Stats._fields_}
+
+    def simulate(self, reads_per_genome, seed=None, sink=None, header_format=None, unit_begin=0, unit_end=None,
+                 read_id_base=0, batch_units=0):
+        r = np.ascontiguousarray(reads_per_genome, np.uint64)
+        o = self._opts(seed, header_format, unit_begin, unit_end, read_id_base, batch_units)
+        self._run(N.lib().simmr_multi_simulate, _p(r, N.u64p), o, sink)
+        return self.stats()
+
+    def measure(self, *a, **k):
+        raise NotImplementedError("a multi-device run needs no shard offsets: its writer thread emits batches in file order")
+
+    def replay(self, *a, **k):
+        raise NotImplementedError("replay is a single-device (test) path")
+
+    def device_info(self):
+        raise NotImplementedError("per-device information: open an Engine on the device")
 
 
 def write_to_fastq(engine, reads_per_genome, output, seed=None, header_format=None, append=False, **kw):

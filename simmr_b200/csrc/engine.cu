@@ -9,7 +9,13 @@
 #include "host_model.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <random>
@@ -83,8 +89,17 @@ struct simmr_ctx {
     DevMem d_unit_start, d_counters, d_out[2];
     DevMem d_sizes[2], d_offsets[2], d_block_sums[2], d_desc[2], d_desc_ext[2];   /* per-batch scratch, two sets: batch b+1 is prepared while batch b is formatted */
     DevMem d_seg_perm[2], d_seg_tiles[2], d_seg_ntiles[2];        /* short reads: size-sorted order and tiles of every segment (k_segment_sort) */
-    PinnedMem h_out[2], h_total;
+    PinnedMem h_out[4], h_total;                   /* pinned ring: batches wait here for the writer thread */
+    cudaEvent_t ev[24] = {};                       /* created with the context (Events below) */
     DevMem d_draw[13];
+    simmr_stats stats{};
+    bool dbg_guard = false, dbg_sync = false, dbg_serial = false;   /* SIMMR_DEBUG_GUARD / SIMMR_DEBUG_SYNC / SIMMR_PREP_SERIAL, read per run */
+};
+
+struct simmr_multi {
+    std::vector<simmr_ctx *> ctx;
+    std::vector<int> devices;
+    std::string err;
     simmr_stats stats{};
 };
 
@@ -239,87 +254,128 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     }
 }
 
-/* The batch pipeline shared by simulate and replay. */
-int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uint64_t ue, uint64_t seed,
-              const simmr_run_opts *opts, simmr_sink_fn sink, void *user, bool measure_only = false) {
-    Plan pl;
-    int rc = make_plan(ctx, replay, pl);
-    if (rc) return rc;
-    /* Staging per batch: 16 GiB (of 180) when nothing has to cross PCIe, less when the device is short of memory.  Few
-     * large launches beat many small ones twice: every launch fills the tables of 148 CTAs and ends with a partly idle
-     * GPU (short reads: 2 -> 16 GiB is +7 %), and a long read is budgeted at its largest possible size (131 KB) although
-     * it averages 40 KB — 2 GiB were 16 K reads per launch, 7 per warp, and the last warps' long reads left the GPU half
-     * idle (+22 %). */
-    const bool errs = ctx->model.err.on && !replay;        /* k-mer error injection between sizing and formatting */
-    uint64_t target_bytes = sink ? (256ull << 20) : errs ? (4096ull << 20) : (16384ull << 20);
-    if (measure_only) target_bytes = errs ? (1024ull << 20) : (uint64_t(pl.max_unit_bytes) << 24);
-    if (!sink && !measure_only) {
-        size_t free_b = 0, total_b = 0;
-        CU(cudaMemGetInfo(&free_b, &total_b));
-        free_b += ctx->d_out[0].bytes;                    /* what this context already holds for staging can be reused */
-        while (target_bytes > (256ull << 20) && target_bytes > free_b / 3) target_bytes /= 2;
-    }
-    uint64_t batch = opts && opts->batch_units ? opts->batch_units : std::max<uint64_t>(1, target_bytes / pl.max_unit_bytes);
-    batch = std::min<uint64_t>(batch, std::max<uint64_t>(1, ue - ub));
-    batch = std::min<uint64_t>(batch, 0x7fffffffull);
-    if (batch * pl.max_unit_bytes > (64ull << 30)) batch = std::max<uint64_t>(1, (64ull << 30) / pl.max_unit_bytes);
-    const uint64_t out_cap = batch * pl.max_unit_bytes + 64;
-    const uint32_t max_blocks = uint32_t((batch + SIZES_THREADS - 1) / SIZES_THREADS);
-    const uint64_t max_segs = (batch + SEG_UNITS - 1) / SEG_UNITS;
-    for (int k = 0; k < 2; ++k) {
-        CU(ctx->d_sizes[k].reserve(batch * 4)); CU(ctx->d_desc[k].reserve(batch * sizeof(UnitRec))); CU(ctx->d_desc_ext[k].reserve(batch * sizeof(UnitExt)));
-        CU(ctx->d_offsets[k].reserve((batch + 1) * 8)); CU(ctx->d_block_sums[k].reserve(size_t(max_blocks) * 8));
-        if (pl.tiles || errs) {
-            CU(ctx->d_seg_perm[k].reserve(max_segs * SEG_UNITS * 2)); CU(ctx->d_seg_tiles[k].reserve(max_segs * SEG_UNITS * 2));
-            CU(ctx->d_seg_ntiles[k].reserve(max_segs * 4));
-        }
-    }
-    if (errs) {      /* scratch for a batch's edited reads: as many bases as the batch has FASTQ bytes, 16 more per read (err_scratch_base) */
-        const uint64_t nb = out_cap + 16 * batch + 64;
-        CU(ctx->d_epacked.reserve(nb / 4 + 4 * PACK_PAD_WORDS)); CU(ctx->d_ebases.reserve(nb));
-    }
-    CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
-    const bool guard = getenv("SIMMR_DEBUG_GUARD") != nullptr, dbg_sync = getenv("SIMMR_DEBUG_SYNC") != nullptr;
-    const int nbuf = measure_only ? 0 : sink ? 2 : 1;
-    for (int b = 0; b < nbuf; ++b) CU(ctx->d_out[b].reserve(out_cap));
-    if (sink) { for (int b = 0; b < 2; ++b) CU(ctx->h_out[b].reserve(out_cap)); }
-    CU(ctx->h_total.reserve(2 * sizeof(uint64_t)));
+/* ---------------------------------------------------------------------- */
+/* the batch pipeline shared by simulate, replay and measure                 */
+/* ---------------------------------------------------------------------- */
+constexpr int RING = SIMMR_RING_BUFFERS;   /* pinned host buffers per context */
+enum : int { EV_START = 0, EV_STOP, EV_F0, EV_F1, EV_TOTAL /* 2 */ = 4, EV_FMT /* 2 */ = 6, EV_PREP /* 2 */ = 8, EV_DONE /* 2 */ = 10, EV_COPY /* RING */ = 12, EV_COUNT = 16 };
 
-    RunParams rp; fill_params(ctx, rp, seed, opts ? opts->read_id_base : 0, pl);
-    auto scratch = [&](RunParams &r, int k) {
+/* A finished batch on its way from a launch thread to the writer thread. */
+struct Ready { int slot; const uint8_t *data; uint64_t bytes, first, units; cudaEvent_t copied; };
+/* Launch thread -> writer thread hand-off of one context: the RING pinned buffers are used round-robin, so "how many are
+ * free" is all the producer needs to know.  A failing sink makes the writer raise `abort`; it keeps releasing buffers
+ * so that the producer never blocks, and the producer stops at its next batch. */
+struct BatchQueue {
+    std::mutex m; std::condition_variable cv;
+    std::deque<Ready> q;
+    int free_slots = RING; bool closed = false;
+    std::atomic<bool> abort{false};
+    bool acquire() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return free_slots > 0; }); --free_slots; return !abort.load(); }
+    void push(const Ready &r) { { std::lock_guard<std::mutex> l(m); q.push_back(r); } cv.notify_all(); }
+    void close() { { std::lock_guard<std::mutex> l(m); closed = true; } cv.notify_all(); }
+    bool pop(Ready &r) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !q.empty() || closed; }); if (q.empty()) return false; r = q.front(); q.pop_front(); return true; }
+    void release() { { std::lock_guard<std::mutex> l(m); ++free_slots; } cv.notify_all(); }
+    void wait_all_released() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return free_slots == RING; }); }
+};
+/* chunks a sink retained (SIMMR_SINK_RETAINED): pinned buffer -> the queue that gets it back */
+std::mutex g_retained_mu;
+std::map<const void *, BatchQueue *> g_retained;
+/* The writer thread: batches leave in file order — batch j comes from queue j % n — and the sink sees them one at a
+ * time.  Returns false if the sink failed. */
+bool write_batches(const std::vector<BatchQueue *> &qs, const std::vector<int> &devices, simmr_sink_fn sink, void *user) {
+    bool ok = true;
+    std::vector<bool> open(qs.size(), true);
+    size_t live = qs.size();
+    for (size_t j = 0; live; ++j) {
+        const size_t g = j % qs.size();
+        if (!open[g]) continue;
+        Ready r;
+        if (!qs[g]->pop(r)) { open[g] = false; --live; continue; }
+        cudaSetDevice(devices[g]);
+        const bool copied = cudaEventSynchronize(r.copied) == cudaSuccess;
+        int verdict = 1;
+        if (ok && copied) {
+            { std::lock_guard<std::mutex> l(g_retained_mu); g_retained[r.data] = qs[g]; }      /* before the sink can pass it on */
+            verdict = sink(user, r.data, r.bytes, r.first, r.units);
+            if (verdict != SIMMR_SINK_RETAINED) { std::lock_guard<std::mutex> l(g_retained_mu); g_retained.erase(r.data); }
+        }
+        if (ok && verdict != 0 && verdict != SIMMR_SINK_RETAINED) { ok = false; for (BatchQueue *q : qs) q->abort.store(true); }
+        if (verdict != SIMMR_SINK_RETAINED) qs[g]->release();
+    }
+    return ok;
+}
+
+struct Runner {
+    simmr_ctx *ctx; bool replay; ReplayDev rd; Plan pl; RunParams rp;
+    uint64_t ub = 0, ue = 0, batch = 0, out_cap = 0;
+    bool errs = false, measure_only = false, guard = false, dbg_sync = false, done_live[2] = {false, false};
+    cudaStream_t prep = nullptr;
+    uint64_t launches = 0;
+    cudaEvent_t *ev;
+
+    void scratch(RunParams &r, int k) const {
         r.sizes = ctx->d_sizes[k].as<uint32_t>(); r.offsets = ctx->d_offsets[k].as<uint64_t>();
         r.desc = ctx->d_desc[k].as<UnitRec>(); r.desc_ext = ctx->d_desc_ext[k].as<UnitExt>(); r.block_sums = ctx->d_block_sums[k].as<uint64_t>();
         r.seg_perm = ctx->d_seg_perm[k].as<uint16_t>(); r.seg_tiles = ctx->d_seg_tiles[k].as<uint16_t>(); r.seg_ntiles = ctx->d_seg_ntiles[k].as<uint32_t>();
-    };
-    cudaEvent_t ev_start, ev_stop, ev_f0, ev_f1, ev_total[2], ev_fmt[2], ev_copy[2], ev_prep[2], ev_done[2];
-    CU(cudaEventCreate(&ev_start)); CU(cudaEventCreate(&ev_stop)); CU(cudaEventCreate(&ev_f0)); CU(cudaEventCreate(&ev_f1));
-    for (int b = 0; b < 2; ++b) {
-        CU(cudaEventCreate(&ev_total[b])); CU(cudaEventCreate(&ev_fmt[b])); CU(cudaEventCreate(&ev_copy[b]));
-        CU(cudaEventCreateWithFlags(&ev_prep[b], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
     }
-    simmr_stats st{};
-    double format_ms = 0.0;
-    struct Pending { bool live = false; uint64_t first = 0, units = 0; } pend[2];
-    auto drain = [&](int slot) -> int {      /* hand a finished batch to the sink */
-        if (!pend[slot].live) return SIMMR_OK;
-        CU(cudaEventSynchronize(ev_copy[slot]));
-        const uint64_t total = static_cast<uint64_t *>(ctx->h_total.p)[slot];
-        pend[slot].live = false;
-        if (sink(user, static_cast<const uint8_t *>(ctx->h_out[slot].p), total, pend[slot].first, pend[slot].units)) return fail(ctx, SIMMR_E_SINK, "sink callback failed");
+    /* plan, batch size, device and pinned buffers */
+    int init(uint64_t ub_, uint64_t ue_, uint64_t seed, const simmr_run_opts *opts, bool to_host, bool measure) {
+        ub = ub_; ue = ue_; measure_only = measure; ev = ctx->ev;
+        int rc = make_plan(ctx, replay, pl);
+        if (rc) return rc;
+        /* Staging per batch: 16 GiB (of 180) when nothing has to cross PCIe, less when the device is short of memory.  Few
+         * large launches beat many small ones twice: every launch fills the tables of 148 CTAs and ends with a partly idle
+         * GPU (short reads: 2 -> 16 GiB is +7 %), and a long read is budgeted at its largest possible size (131 KB) although
+         * it averages 40 KB — 2 GiB were 16 K reads per launch, 7 per warp, and the last warps' long reads left the GPU half
+         * idle (+22 %). */
+        errs = ctx->model.err.on && !replay;           /* k-mer error injection between sizing and formatting */
+        uint64_t target_bytes = to_host ? (256ull << 20) : errs ? (4096ull << 20) : (16384ull << 20);
+        if (measure_only) target_bytes = errs ? (1024ull << 20) : (uint64_t(pl.max_unit_bytes) << 24);
+        if (!to_host && !measure_only) {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            free_b += ctx->d_out[0].bytes;                /* what this context already holds for staging can be reused */
+            while (target_bytes > (256ull << 20) && target_bytes > free_b / 3) target_bytes /= 2;
+        }
+        batch = opts && opts->batch_units ? opts->batch_units : std::max<uint64_t>(1, target_bytes / pl.max_unit_bytes);
+        batch = std::min<uint64_t>(batch, std::max<uint64_t>(1, ue - ub));
+        batch = std::min<uint64_t>(batch, 0x7fffffffull);
+        if (batch * pl.max_unit_bytes > (64ull << 30)) batch = std::max<uint64_t>(1, (64ull << 30) / pl.max_unit_bytes);
+        out_cap = batch * pl.max_unit_bytes + 64;
+        const uint32_t max_blocks = uint32_t((batch + SIZES_THREADS - 1) / SIZES_THREADS);
+        const uint64_t max_segs = (batch + SEG_UNITS - 1) / SEG_UNITS;
+        for (int k = 0; k < 2; ++k) {
+            CU(ctx->d_sizes[k].reserve(batch * 4)); CU(ctx->d_desc[k].reserve(batch * sizeof(UnitRec))); CU(ctx->d_desc_ext[k].reserve(batch * sizeof(UnitExt)));
+            CU(ctx->d_offsets[k].reserve((batch + 1) * 8)); CU(ctx->d_block_sums[k].reserve(size_t(max_blocks) * 8));
+            if (pl.tiles || errs) {
+                CU(ctx->d_seg_perm[k].reserve(max_segs * SEG_UNITS * 2)); CU(ctx->d_seg_tiles[k].reserve(max_segs * SEG_UNITS * 2));
+                CU(ctx->d_seg_ntiles[k].reserve(max_segs * 4));
+            }
+        }
+        if (errs) {      /* scratch for a batch's edited reads: as many bases as the batch has FASTQ bytes, 16 more per read (err_scratch_base) */
+            const uint64_t nb = out_cap + 16 * batch + 64;
+            CU(ctx->d_epacked.reserve(nb / 4 + 4 * PACK_PAD_WORDS)); CU(ctx->d_ebases.reserve(nb));
+        }
+        CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
+        guard = ctx->dbg_guard; dbg_sync = ctx->dbg_sync;
+        const int nbuf = measure_only ? 0 : to_host ? 2 : 1;
+        for (int b = 0; b < nbuf; ++b) CU(ctx->d_out[b].reserve(out_cap));
+        if (to_host) for (int b = 0; b < RING; ++b) CU(ctx->h_out[b].reserve(out_cap));
+        CU(ctx->h_total.reserve(2 * sizeof(uint64_t)));
+        fill_params(ctx, rp, seed, opts ? opts->read_id_base : 0, pl);
+        /* error injection reads and writes one scratch set per context: its batches are prepared on the compute stream, one
+         * at a time.  dbg_serial: everything on one stream (kernel timings without co-runners). */
+        prep = (errs || measure_only || ctx->dbg_serial) ? ctx->compute : ctx->prep;
         return SIMMR_OK;
-    };
-    /* geometry, sizes and byte offsets of batch number `nb` on the prep stream, into scratch set nb & 1: the small kernels
-     * need no shared memory and share the SMs with the format kernel of the batch before */
-    bool done_live[2] = {false, false};
-    uint64_t prep_launches = 0;
-    /* error injection reads and writes one scratch set per context: its batches are prepared on the compute stream, one at a time */
-    cudaStream_t prep = (errs || measure_only || getenv("SIMMR_PREP_SERIAL")) ? ctx->compute : ctx->prep;     /* SIMMR_PREP_SERIAL: everything on one stream (kernel timings without co-runners) */
-    auto prepare = [&](uint64_t u, uint64_t nb) -> int {
-        const int k = int(nb & 1);
+    }
+    bool ahead() const { return !errs && !measure_only; }   /* batch b + 1 is prepared beside batch b's format kernel */
+    /* geometry, sizes and byte offsets of the batch that starts at unit u into scratch set k: the small kernels need no
+     * shared memory and share the SMs with the format kernel of the batch before */
+    int prepare(uint64_t u, int k) {
         const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
         RunParams r = rp; scratch(r, k);
         r.batch_begin = u; r.batch_units = n;
-        if (done_live[k]) CU(cudaStreamWaitEvent(prep, ev_done[k], 0));     /* the format kernel that read this set has finished */
+        if (done_live[k]) CU(cudaStreamWaitEvent(prep, ev[EV_DONE + k], 0));     /* the format kernel that read this set has finished */
         const uint32_t nblk = (n + SIZES_THREADS - 1) / SIZES_THREADS;
         if (replay) k_unit_sizes<true><<<nblk, SIZES_THREADS, 0, prep>>>(r, rd);
         else k_unit_sizes<false><<<nblk, SIZES_THREADS, 0, prep>>>(r, rd);
@@ -327,39 +383,26 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
         k_scan_blocks<<<1, 1024, 0, prep>>>(r, nblk);
         if (pl.tiles || errs) k_segment_sort<<<(n + SEG_UNITS - 1) / SEG_UNITS, SEG_THREADS, 0, prep>>>(r);     /* offsets + size-sorted tiles */
         else k_unit_offsets<<<nblk, SIZES_THREADS, 0, prep>>>(r);
+        launches += 3;
         if (errs) {      /* edit the reads (size-sorted order), then offsets again from the edited sizes */
             k_kmer_errors<<<(n + 255) / 256, 256, 0, prep>>>(r);
             k_block_sums<<<nblk, SIZES_THREADS, 0, prep>>>(r);
             k_scan_blocks<<<1, 1024, 0, prep>>>(r, nblk);
             k_unit_offsets<<<nblk, SIZES_THREADS, 0, prep>>>(r);
-            prep_launches += 4;
+            launches += 4;
         }
         CU(cudaGetLastError());
         if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("scan kernels: ") + cudaGetErrorString(e_)); }
-        CU(cudaEventRecord(ev_prep[k], prep));
+        CU(cudaEventRecord(ev[EV_PREP + k], prep));
         return SIMMR_OK;
-    };
-    CU(cudaEventRecord(ev_start, ctx->compute));
-    CU(cudaStreamWaitEvent(prep, ev_start, 0));
-    const bool ahead = !errs && !measure_only;               /* batch b + 1 is prepared beside batch b's format kernel */
-    if (ahead) { rc = prepare(ub, 0); if (rc) return rc; }
-    int slot = 0; uint64_t nbatch = 0;
-    for (uint64_t u = ub; u < ue; u += batch, ++nbatch) {
+    }
+    /* the format kernel of the batch prepared in set k, into d_out[dslot]; bracketed by EV_F0 / EV_F1 */
+    int format(uint64_t u, int k, int dslot) {
         const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
-        const int k = int(nbatch & 1);
-        if (!ahead) { rc = prepare(u, nbatch); if (rc) return rc; st.kernel_launches += 3; }
-        if (measure_only) continue;                              /* geometry, sizes (and edits) only: what the units occupy in the FASTQ stream */
-        if (sink) { rc = drain(slot); if (rc) return rc; }       /* slot's buffers are about to be reused */
-        if (ahead && u + batch < ue) { rc = prepare(u + batch, nbatch + 1); if (rc) return rc; }
         scratch(rp, k);
-        rp.batch_begin = u; rp.batch_units = n; rp.out = ctx->d_out[slot].as<uint8_t>();
-        if (guard) CU(cudaMemsetAsync(ctx->d_out[slot].p, 0xA5, out_cap, ctx->compute));
-        CU(cudaStreamWaitEvent(ctx->compute, ev_prep[k], 0));
-        if (sink) {
-            CU(cudaMemcpyAsync(static_cast<uint64_t *>(ctx->h_total.p) + slot, rp.offsets + n, 8, cudaMemcpyDeviceToHost, ctx->compute));
-            CU(cudaEventRecord(ev_total[slot], ctx->compute));
-        }
-        CU(cudaEventRecord(ev_f0, ctx->compute));
+        rp.batch_begin = u; rp.batch_units = n; rp.out = ctx->d_out[dslot].as<uint8_t>();
+        if (guard) CU(cudaMemsetAsync(ctx->d_out[dslot].p, 0xA5, out_cap, ctx->compute));
+        CU(cudaEventRecord(ev[EV_F0], ctx->compute));
         if (pl.tiles) {
             const int grid = int(std::min<uint32_t>((n + SEG_UNITS - 1) / SEG_UNITS, uint32_t(pl.grid)));      /* a CTA takes whole segments */
             lanes_kernel(replay, quality_mode(ctx->model))<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
@@ -370,9 +413,10 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
             const int grid = int(std::min<uint32_t>(n, uint32_t(pl.grid)));
             direct_kernel(replay)<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
         }
+        ++launches;
         CU(cudaGetLastError());
-        CU(cudaEventRecord(ev_f1, ctx->compute));
-        CU(cudaEventRecord(ev_done[k], ctx->compute)); done_live[k] = true;
+        CU(cudaEventRecord(ev[EV_F1], ctx->compute));
+        CU(cudaEventRecord(ev[EV_DONE + k], ctx->compute)); done_live[k] = true;
         if (guard) {   /* SIMMR_DEBUG_GUARD: nothing may be written past the batch's last byte */
             uint64_t total = 0; uint8_t tail[64];
             CU(cudaMemcpyAsync(&total, rp.offsets + n, 8, cudaMemcpyDeviceToHost, ctx->compute));
@@ -381,36 +425,91 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
             CU(cudaMemcpy(tail, rp.out + total, 64, cudaMemcpyDeviceToHost));
             for (int b = 0; b < 64; ++b) if (tail[b] != 0xA5) return fail(ctx, SIMMR_E_CUDA, "guard bytes after the batch output were overwritten");
         }
-        st.kernel_launches += ahead ? 4 : 1;
-        if (sink) {
-            CU(cudaEventRecord(ev_fmt[slot], ctx->compute));
-            CU(cudaEventSynchronize(ev_total[slot]));            /* byte count known while the format kernel runs */
-            const uint64_t total = static_cast<uint64_t *>(ctx->h_total.p)[slot];
-            if (total > out_cap) return fail(ctx, SIMMR_E_LIMIT, "batch overflowed its staging buffer");
-            CU(cudaStreamWaitEvent(ctx->copy, ev_fmt[slot], 0));
-            CU(cudaMemcpyAsync(ctx->h_out[slot].p, ctx->d_out[slot].p, total, cudaMemcpyDeviceToHost, ctx->copy));
-            CU(cudaEventRecord(ev_copy[slot], ctx->copy));
-            pend[slot] = Pending{true, u, n};
-            st.d2h_bytes += total + 8;
-            slot ^= 1;
-        }
-        /* per-batch format time: costs one sync per batch, only taken when it cannot hide copies */
-        if (!sink) { CU(cudaEventSynchronize(ev_f1)); float ms = 0; CU(cudaEventElapsedTime(&ms, ev_f0, ev_f1)); format_ms += ms; }
+        return SIMMR_OK;
     }
-    CU(cudaEventRecord(ev_stop, ctx->compute));
-    if (sink) { rc = drain(slot); if (rc) return rc; rc = drain(slot ^ 1); if (rc) return rc; }
-    CU(cudaEventSynchronize(ev_stop));
-    float ms = 0; CU(cudaEventElapsedTime(&ms, ev_start, ev_stop));
-    unsigned long long ctr[8];
-    CU(cudaMemcpy(ctr, ctx->d_counters.p, sizeof ctr, cudaMemcpyDeviceToHost));
-    /* ctr[5]: bases deleted by k-mer error injection — read from the genome, absent from the sequence line */
-    st.units = ue - ub; st.clamped = ctr[0]; st.algorithmic_bytes = ctr[1] - ctr[5]; st.bases = ctr[2] - ctr[5]; st.records = ctr[3];
-    st.bytes = ctr[1] - ctr[2] - ctr[5];                          /* (3L+H+5) - L, less the deleted bases */
-    st.device_ms = ms; st.format_ms = format_ms; st.kernel_launches += prep_launches;
-    cudaEventDestroy(ev_start); cudaEventDestroy(ev_stop); cudaEventDestroy(ev_f0); cudaEventDestroy(ev_f1);
-    for (int b = 0; b < 2; ++b) { cudaEventDestroy(ev_total[b]); cudaEventDestroy(ev_fmt[b]); cudaEventDestroy(ev_copy[b]); cudaEventDestroy(ev_prep[b]); cudaEventDestroy(ev_done[b]); }
-    ctx->stats = st;
-    return SIMMR_OK;
+    int finish(simmr_stats &st, double format_ms) {
+        CU(cudaEventRecord(ev[EV_STOP], ctx->compute));
+        CU(cudaEventSynchronize(ev[EV_STOP]));
+        float ms = 0; CU(cudaEventElapsedTime(&ms, ev[EV_START], ev[EV_STOP]));
+        unsigned long long ctr[8];
+        CU(cudaMemcpy(ctr, ctx->d_counters.p, sizeof ctr, cudaMemcpyDeviceToHost));
+        /* ctr[5]: bases deleted by k-mer error injection — read from the genome, absent from the sequence line */
+        st.clamped = ctr[0]; st.algorithmic_bytes = ctr[1] - ctr[5]; st.bases = ctr[2] - ctr[5]; st.records = ctr[3];
+        st.bytes = ctr[1] - ctr[2] - ctr[5];                          /* (3L+H+5) - L, less the deleted bases */
+        st.device_ms = ms; st.format_ms = format_ms; st.kernel_launches = launches;
+        return SIMMR_OK;
+    }
+};
+
+/* Batches number j0, j0 + stride, ... of the unit range (batch j starts at unit ub + j * batch) — every batch when the
+ * context runs alone, every n-th when n contexts share a run.  to_host: finished batches go to the pinned ring and into
+ * `q` for the writer thread.  Otherwise (device-resident run, or measure) the bytes stay in HBM staging. */
+int produce(Runner &R, uint64_t j0, uint64_t stride, BatchQueue *q, simmr_stats &st) {
+    simmr_ctx *ctx = R.ctx;
+    cudaEvent_t *ev = R.ev;
+    const uint64_t nbatches = (R.ue - R.ub + R.batch - 1) / R.batch;
+    double format_ms = 0.0;
+    int rc = SIMMR_OK;
+    CU(cudaEventRecord(ev[EV_START], ctx->compute));
+    CU(cudaStreamWaitEvent(R.prep, ev[EV_START], 0));
+    auto start_of = [&](uint64_t j) { return R.ub + j * R.batch; };
+    if (R.ahead() && j0 < nbatches) { rc = R.prepare(start_of(j0), 0); if (rc) return rc; }
+    uint64_t seq = 0;                                          /* this context's own batch count */
+    for (uint64_t j = j0; j < nbatches; j += stride, ++seq) {
+        const uint64_t u = start_of(j);
+        const uint32_t n = uint32_t(std::min<uint64_t>(R.batch, R.ue - u));
+        const int k = int(seq & 1), dslot = q ? int(seq & 1) : 0, slot = int(seq % RING);
+        if (!R.ahead()) { rc = R.prepare(u, k); if (rc) return rc; }
+        if (R.measure_only) continue;                          /* geometry, sizes (and edits) only: what the units occupy in the FASTQ stream */
+        if (q && !q->acquire()) return fail(ctx, SIMMR_E_SINK, "sink callback failed");      /* a pinned buffer is free again */
+        if (R.ahead() && j + stride < nbatches) { rc = R.prepare(start_of(j + stride), k ^ 1); if (rc) return rc; }
+        CU(cudaStreamWaitEvent(ctx->compute, ev[EV_PREP + k], 0));
+        if (q) {
+            if (seq >= 2) CU(cudaStreamWaitEvent(ctx->compute, ev[EV_COPY + int((seq - 2) % RING)], 0));   /* d_out[dslot] has been copied out */
+            R.scratch(R.rp, k);
+            CU(cudaMemcpyAsync(static_cast<uint64_t *>(ctx->h_total.p) + dslot, R.rp.offsets + n, 8, cudaMemcpyDeviceToHost, ctx->compute));
+            CU(cudaEventRecord(ev[EV_TOTAL + dslot], ctx->compute));
+        }
+        rc = R.format(u, k, dslot); if (rc) return rc;
+        if (q) {
+            CU(cudaEventRecord(ev[EV_FMT + dslot], ctx->compute));
+            CU(cudaEventSynchronize(ev[EV_TOTAL + dslot]));            /* byte count known while the format kernel runs */
+            const uint64_t total = static_cast<uint64_t *>(ctx->h_total.p)[dslot];
+            if (total > R.out_cap) return fail(ctx, SIMMR_E_LIMIT, "batch overflowed its staging buffer");
+            CU(cudaStreamWaitEvent(ctx->copy, ev[EV_FMT + dslot], 0));
+            CU(cudaMemcpyAsync(ctx->h_out[slot].p, ctx->d_out[dslot].p, total, cudaMemcpyDeviceToHost, ctx->copy));
+            CU(cudaEventRecord(ev[EV_COPY + slot], ctx->copy));
+            q->push(Ready{slot, static_cast<const uint8_t *>(ctx->h_out[slot].p), total, u, n, ev[EV_COPY + slot]});
+            st.d2h_bytes += total + 8;
+        } else {   /* per-batch format time: costs one sync per batch, only taken when it cannot hide copies */
+            CU(cudaEventSynchronize(ev[EV_F1])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev[EV_F0], ev[EV_F1])); format_ms += ms;
+        }
+    }
+    return R.finish(st, format_ms);
+}
+
+/* A run of one context: the caller's thread launches, a writer thread owned by the library hands the batches to the sink. */
+int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uint64_t ue, uint64_t seed,
+              const simmr_run_opts *opts, simmr_sink_fn sink, void *user, bool measure_only = false) {
+    /* debug switches, read once per run */
+    ctx->dbg_guard = getenv("SIMMR_DEBUG_GUARD") != nullptr; ctx->dbg_sync = getenv("SIMMR_DEBUG_SYNC") != nullptr; ctx->dbg_serial = getenv("SIMMR_PREP_SERIAL") != nullptr;
+    Runner R{ctx, replay, rd};
+    int rc = R.init(ub, ue, seed, opts, sink != nullptr, measure_only);
+    if (rc) return rc;
+    simmr_stats st{};
+    st.units = ue - ub;
+    if (!sink) { rc = produce(R, 0, 1, nullptr, st); if (!rc) ctx->stats = st; return rc; }
+    BatchQueue q;
+    bool sink_ok = true;
+    std::thread writer([&] { sink_ok = write_batches({&q}, {ctx->device}, sink, user); });
+    rc = produce(R, 0, 1, &q, st);
+    q.close();
+    writer.join();
+    q.wait_all_released();                  /* chunks the sink retained come back before the ring can go away */
+    if (rc != SIMMR_OK) { cudaStreamSynchronize(ctx->compute); cudaStreamSynchronize(ctx->copy); cudaStreamSynchronize(ctx->prep); }   /* nothing of the run stays in flight */
+    if (!sink_ok) return fail(ctx, SIMMR_E_SINK, "sink callback failed");
+    if (!rc) ctx->stats = st;
+    return rc;
 }
 
 int check_ready(simmr_ctx *ctx) {
@@ -428,17 +527,38 @@ int check_ready(simmr_ctx *ctx) {
     return SIMMR_OK;
 }
 
+/* the run's unit range: everything, unless opts names one (0,0 counts as a range only with SIMMR_RUN_EXPLICIT_RANGE) */
+void unit_range(const simmr_run_opts *opts, uint64_t total, uint64_t &ub, uint64_t &ue) {
+    ub = opts ? opts->unit_begin : 0; ue = opts ? opts->unit_end : 0;
+    if (ub == 0 && ue == 0 && !(opts && (opts->flags & SIMMR_RUN_EXPLICIT_RANGE))) ue = total;
+}
 std::vector<uint64_t> unit_prefix(const simmr_ctx *ctx, const uint64_t *reads) {
     const uint32_t n = ctx->host_view.n_genomes;
     std::vector<uint64_t> s(n + 1, 0);
     for (uint32_t g = 0; g < n; ++g) s[g + 1] = s[g] + (ctx->model.is_long ? reads[g] : reads[g] / 2);   /* simulate.rs:179 / :356 */
     return s;
 }
+int mfail(simmr_multi *m, int code, const std::string &msg) { last_error_slot() = msg; if (m) m->err = msg; return code; }
+/* fn(g) on one thread per device; the first failure's code (its message is in the context) */
+template <class F> int on_every_device(simmr_multi *m, F fn) {
+    std::vector<int> rc(m->ctx.size(), SIMMR_OK);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < m->ctx.size(); ++g) th.emplace_back([&, g] { cudaSetDevice(m->devices[g]); rc[g] = fn(int(g)); });
+    for (auto &t : th) t.join();
+    for (size_t g = 0; g < rc.size(); ++g) if (rc[g]) return mfail(m, rc[g], "device " + std::to_string(m->devices[g]) + ": " + m->ctx[g]->err);
+    return SIMMR_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
 const char *simmr_last_error(const simmr_ctx *ctx) { return ctx ? ctx->err.c_str() : last_error_slot().c_str(); }
+void simmr_chunk_release(const uint8_t *data) {
+    BatchQueue *q = nullptr;
+    { std::lock_guard<std::mutex> l(g_retained_mu); auto it = g_retained.find(data); if (it != g_retained.end()) { q = it->second; g_retained.erase(it); } }
+    if (q) q->release();
+}
 const char *simmr_version(void) { return "simmr_b200 0.1 (sm_100a)"; }
 
 int simmr_ctx_create(int device, simmr_ctx **out) {
@@ -456,6 +576,10 @@ int simmr_ctx_create(int device, simmr_ctx **out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaStreamCreateWithFlags(&ctx->prep, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    for (int i = 0; i < EV_COUNT; ++i) {      /* the pipeline's events live as long as the context */
+        const bool timed = i < EV_TOTAL;
+        if ((e = cudaEventCreateWithFlags(&ctx->ev[i], timed ? cudaEventDefault : cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    }
     *out = ctx;
     return SIMMR_OK;
 }
@@ -464,6 +588,7 @@ void simmr_ctx_destroy(simmr_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    for (int i = 0; i < EV_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->compute) cudaStreamDestroy(ctx->compute);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
     if (ctx->prep) cudaStreamDestroy(ctx->prep);
@@ -567,8 +692,8 @@ int simmr_simulate(simmr_ctx *ctx, const uint64_t *reads, const simmr_run_opts *
     if (rc) return rc;
     const std::vector<uint64_t> us = unit_prefix(ctx, reads);
     CU(ctx->d_unit_start.upload(us.data(), us.size(), ctx->compute));
-    uint64_t ub = opts ? opts->unit_begin : 0, ue = opts ? opts->unit_end : 0;
-    if (ub == 0 && ue == 0) ue = us.back();
+    uint64_t ub, ue;
+    unit_range(opts, us.back(), ub, ue);
     if (ub > ue || ue > us.back()) return fail(ctx, SIMMR_E_INVALID, "unit range outside the run");
     uint64_t seed;
     if (opts && opts->has_seed) seed = opts->seed;
@@ -588,8 +713,8 @@ int simmr_measure(simmr_ctx *ctx, const uint64_t *reads, const simmr_run_opts *o
     if (rc) return rc;
     const std::vector<uint64_t> us = unit_prefix(ctx, reads);
     CU(ctx->d_unit_start.upload(us.data(), us.size(), ctx->compute));
-    uint64_t ub = opts->unit_begin, ue = opts->unit_end;
-    if (ub == 0 && ue == 0) ue = us.back();
+    uint64_t ub, ue;
+    unit_range(opts, us.back(), ub, ue);
     if (ub > ue || ue > us.back()) return fail(ctx, SIMMR_E_INVALID, "unit range outside the run");
     ctx->stats = simmr_stats{};
     if (ub < ue) { ReplayDev rd{}; rc = run_units(ctx, false, rd, ub, ue, opts->seed, opts, nullptr, nullptr, true); if (rc) return rc; }
@@ -643,12 +768,107 @@ int simmr_replay(simmr_ctx *ctx, const simmr_draws *d, const simmr_run_opts *opt
     std::vector<uint64_t> us(ctx->host_view.n_genomes + 1, 0);
     CU(ctx->d_unit_start.upload(us.data(), us.size(), s));
     CU(cudaStreamSynchronize(s));
-    uint64_t ub = opts ? opts->unit_begin : 0, ue = opts ? opts->unit_end : 0;
-    if (ub == 0 && ue == 0) ue = n;
+    uint64_t ub, ue;
+    unit_range(opts, n, ub, ue);
     if (ub > ue || ue > n) return fail(ctx, SIMMR_E_INVALID, "unit range outside the draws");
     ctx->stats = simmr_stats{};
     if (ub == ue) return SIMMR_OK;
     return run_units(ctx, true, rd, ub, ue, 0, opts, sink, user);
+}
+
+/* ---- several GPUs of one box --------------------------------------------- */
+int simmr_multi_create(const int *devices, int n, simmr_multi **out) {
+    if (!out || !devices || n < 1) return mfail(nullptr, SIMMR_E_INVALID, "simmr_multi_create needs at least one device");
+    for (int a = 0; a < n; ++a) for (int b = 0; b < a; ++b) if (devices[a] == devices[b]) return mfail(nullptr, SIMMR_E_INVALID, "device listed twice");
+    simmr_multi *m = new simmr_multi;
+    for (int g = 0; g < n; ++g) {
+        simmr_ctx *c = nullptr;
+        const int rc = simmr_ctx_create(devices[g], &c);
+        if (rc) { const std::string why = last_error_slot(); simmr_multi_destroy(m); return mfail(nullptr, rc, why); }
+        m->ctx.push_back(c); m->devices.push_back(devices[g]);
+    }
+    *out = m;
+    return SIMMR_OK;
+}
+void simmr_multi_destroy(simmr_multi *m) {
+    if (!m) return;
+    for (simmr_ctx *c : m->ctx) simmr_ctx_destroy(c);
+    delete m;
+}
+const char *simmr_multi_last_error(const simmr_multi *m) { return m ? m->err.c_str() : last_error_slot().c_str(); }
+int simmr_multi_genomes_load(simmr_multi *m, const simmr_genome_set *set) {
+    if (!m) return mfail(nullptr, SIMMR_E_INVALID, "null multi-context");
+    return on_every_device(m, [&](int g) { return simmr_genomes_load(m->ctx[g], set); });
+}
+int simmr_multi_error_profile_set(simmr_multi *m, const simmr_eprofile_desc *d) {
+    if (!m) return mfail(nullptr, SIMMR_E_INVALID, "null multi-context");
+    return on_every_device(m, [&](int g) { return simmr_error_profile_set(m->ctx[g], d); });
+}
+uint64_t simmr_multi_total_units(const simmr_multi *m, const uint64_t *reads) { return m && !m->ctx.empty() ? simmr_total_units(m->ctx[0], reads) : 0; }
+int simmr_multi_stats_get(const simmr_multi *m, simmr_stats *out) {
+    if (!m || !out) return mfail(nullptr, SIMMR_E_INVALID, "null argument");
+    *out = m->stats;
+    return SIMMR_OK;
+}
+
+int simmr_multi_simulate(simmr_multi *m, const uint64_t *reads, const simmr_run_opts *opts, simmr_sink_fn sink, void *user) {
+    if (!m) return mfail(nullptr, SIMMR_E_INVALID, "null multi-context");
+    if (!reads) return mfail(m, SIMMR_E_INVALID, "null reads_per_genome");
+    const size_t G = m->ctx.size();
+    simmr_run_opts o = opts ? *opts : simmr_run_opts{};
+    if (!o.has_seed) { std::random_device rd; o.seed = (uint64_t(rd()) << 32) | rd(); o.has_seed = 1; }   /* one seed for every device */
+    /* per device: headers, unit table */
+    uint64_t ub = 0, ue = 0;
+    int rc = on_every_device(m, [&](int g) {
+        simmr_ctx *ctx = m->ctx[g];
+        int r = check_ready(ctx); if (r) return r;
+        r = ensure_headers(ctx, o.header_format); if (r) return r;
+        const std::vector<uint64_t> us = unit_prefix(ctx, reads);
+        CU(ctx->d_unit_start.upload(us.data(), us.size(), ctx->compute));
+        if (g == 0) unit_range(&o, us.back(), ub, ue);
+        ctx->stats = simmr_stats{};
+        return int(SIMMR_OK);
+    });
+    if (rc) return rc;
+    const uint64_t total = simmr_total_units(m->ctx[0], reads);
+    if (ub > ue || ue > total) return mfail(m, SIMMR_E_INVALID, "unit range outside the run");
+    m->stats = simmr_stats{};
+    if (ub == ue) return SIMMR_OK;
+    /* every device cuts the range into the same batches: the first context's plan decides their size */
+    std::vector<Runner> R;
+    for (size_t g = 0; g < G; ++g) R.push_back(Runner{m->ctx[g], false, ReplayDev{}});
+    cudaSetDevice(m->devices[0]);
+    for (simmr_ctx *c : m->ctx) { c->dbg_guard = getenv("SIMMR_DEBUG_GUARD") != nullptr; c->dbg_sync = getenv("SIMMR_DEBUG_SYNC") != nullptr; c->dbg_serial = getenv("SIMMR_PREP_SERIAL") != nullptr; }
+    rc = R[0].init(ub, ue, o.seed, &o, sink != nullptr, false);
+    if (rc) return mfail(m, rc, m->ctx[0]->err);
+    o.batch_units = R[0].batch;
+    std::vector<BatchQueue> q(G);
+    std::vector<BatchQueue *> qs;
+    for (auto &x : q) qs.push_back(&x);
+    bool sink_ok = true;
+    std::thread writer;
+    if (sink) writer = std::thread([&] { sink_ok = write_batches(qs, m->devices, sink, user); });
+    std::vector<simmr_stats> st(G);
+    rc = on_every_device(m, [&](int g) {
+        int r = g == 0 ? int(SIMMR_OK) : R[g].init(ub, ue, o.seed, &o, sink != nullptr, false);
+        if (!r) r = produce(R[g], uint64_t(g), G, sink ? &q[g] : nullptr, st[g]);
+        q[g].close();
+        if (r) { for (auto &x : q) x.abort.store(true); cudaDeviceSynchronize(); }     /* the other devices stop at their next batch */
+        return r;
+    });
+    if (sink) { writer.join(); for (auto &x : q) x.wait_all_released(); }
+    if (!sink_ok) return mfail(m, SIMMR_E_SINK, "sink callback failed");
+    if (rc) return rc;
+    simmr_stats sum{};
+    sum.units = ue - ub;
+    for (size_t g = 0; g < G; ++g) {
+        sum.records += st[g].records; sum.bases += st[g].bases; sum.bytes += st[g].bytes; sum.clamped += st[g].clamped;
+        sum.algorithmic_bytes += st[g].algorithmic_bytes; sum.kernel_launches += st[g].kernel_launches; sum.d2h_bytes += st[g].d2h_bytes;
+        sum.device_ms = std::max(sum.device_ms, st[g].device_ms); sum.format_ms = std::max(sum.format_ms, st[g].format_ms);
+        m->ctx[g]->stats = st[g];
+    }
+    m->stats = sum;
+    return SIMMR_OK;
 }
 
 int simmr_stats_get(const simmr_ctx *ctx, simmr_stats *out) {

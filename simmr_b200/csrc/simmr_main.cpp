@@ -3,9 +3,11 @@
  * Mirrors the reference binary (simmr/src/main.rs:20-266, flags of cli.rs:93-220): same
  * flag names, defaults and kebab-case enum values, same outputs (<output> and
  * <output>.tsv), errors to stderr and exit code 1.  Everything goes through the C ABI of
- * include/simmr_b200.h; nothing here computes reads.  Added: --gpus N (shards the run over
- * N devices of this box, one host thread each, byte-identical output), --compat-long-start
- * (simulate.rs:484 start draw) and the `custom-long` profile value. */
+ * include/simmr_b200.h; nothing here computes reads.  Added: --gpus N (the run's batches are
+ * dealt to N devices of this box through simmr_multi, byte-identical output), --output-parts P
+ * (P part files <output>.000 ... written by P I/O threads: one file takes about 2.5 GB/s,
+ * whatever feeds it), --compat-long-start (simulate.rs:484 start draw) and the `custom-long`
+ * profile value. */
 #include "../../include/simmr_b200.h"
 
 #include <fcntl.h>
@@ -15,6 +17,7 @@
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
+#include <deque>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -40,7 +43,8 @@ struct Args {
     bool has_seed = false; uint64_t seed = 0;        /* :202-203 */
     bool size_adjusted = false, contiguous = false;  /* :206-219 */
     bool compat_long_start = false;
-    int gpus = 1;
+    int gpus = 1, parts = 1;
+    uint64_t batch_units = 0;                        /* 0: library default (about 256 MiB of FASTQ per chunk) */
 };
 
 [[noreturn]] void die(const std::string &m) { fprintf(stderr, "ERROR %s\n", m.c_str()); exit(1); }
@@ -60,7 +64,10 @@ void usage() {
           "  --abundance-profile <p>    [uniform] exact, uniform, custom\n"
           "  --custom-profile <path>    simmrd profile blob\n  --with-ani <n>             accepted, not implemented (as in the reference)\n"
           "  --read-header-format <s>   placeholders {:read_id:} {:genome_id:} {:sequence_id:} {:start_position:} {:end_position:} {:reverse_complement:} {:pair:}\n"
-          "  --seed <n>\n  --size-adjusted\n  --contiguous\n  --gpus <n>                 [1] devices to shard over\n  --compat-long-start\n", stderr);
+          "  --seed <n>\n  --size-adjusted\n  --contiguous\n  --gpus <n>                 [1] devices to share the run\n"
+          "  --output-parts <n>         [1] write <output>.000 ... <output>.(n-1) instead of <output>: chunk j of the run goes to part j mod n\n"
+          "  --batch-units <n>          units (pairs / long reads) per chunk; default: about 256 MiB of FASTQ\n"
+          "  --compat-long-start\n", stderr);
 }
 
 Args parse(int argc, char **argv) {
@@ -94,6 +101,8 @@ Args parse(int argc, char **argv) {
         else if (f == "--contiguous") a.contiguous = true;
         else if (f == "--compat-long-start") a.compat_long_start = true;
         else if (f == "--gpus") a.gpus = int(num(v(), "--gpus", 1, 64));
+        else if (f == "--output-parts") a.parts = int(num(v(), "--output-parts", 1, 64));
+        else if (f == "--batch-units") a.batch_units = uint64_t(num(v(), "--batch-units", 1, 2147483647));
         else if (f == "-h" || f == "--help") { usage(); exit(0); }
         else die("unexpected argument '" + f + "'");
     }
@@ -103,17 +112,44 @@ Args parse(int argc, char **argv) {
     return a;
 }
 
-struct FileSink {      /* pwrite()s chunks at the shard's place in the shared output file */
-    int fd; uint64_t at; bool failed = false;
+/* The run's chunks arrive in file order on the library's writer thread.  One part: written right there.  Several parts:
+ * chunk j goes to part j mod P, each part has its own I/O thread (a single file takes about 2.5 GB/s whatever feeds it),
+ * and the chunk's pinned buffer is kept (SIMMR_SINK_RETAINED) until that thread has written it. */
+struct PartWriter {
+    struct Part {
+        int fd = -1; std::thread th; std::mutex m; std::condition_variable cv;
+        std::deque<std::pair<const uint8_t *, uint64_t>> q; bool closed = false;
+    };
+    std::vector<Part> parts;
+    std::atomic<bool> failed{false};
+    uint64_t next = 0;
+    static bool write_all(int fd, const uint8_t *p, uint64_t n) {
+        while (n) { const ssize_t w = write(fd, p, n); if (w <= 0) return false; p += w; n -= uint64_t(w); }
+        return true;
+    }
+    explicit PartWriter(size_t n) : parts(n) {}
+    void start() {
+        if (parts.size() < 2) return;
+        for (Part &p : parts) p.th = std::thread([this, &p] {
+            for (;;) {
+                std::pair<const uint8_t *, uint64_t> c;
+                { std::unique_lock<std::mutex> l(p.m); p.cv.wait(l, [&] { return !p.q.empty() || p.closed; }); if (p.q.empty()) return; c = p.q.front(); p.q.pop_front(); }
+                if (!failed && !write_all(p.fd, c.first, c.second)) failed = true;
+                simmr_chunk_release(c.first);
+            }
+        });
+    }
+    void finish() {
+        for (Part &p : parts) { { std::lock_guard<std::mutex> l(p.m); p.closed = true; } p.cv.notify_all(); if (p.th.joinable()) p.th.join(); if (p.fd >= 0) close(p.fd); }
+    }
     static int call(void *user, const uint8_t *data, uint64_t len, uint64_t, uint64_t) {
-        FileSink *s = static_cast<FileSink *>(user);
-        for (uint64_t done = 0; done < len;) {
-            const ssize_t w = pwrite(s->fd, data + done, len - done, off_t(s->at + done));
-            if (w <= 0) { s->failed = true; return 1; }
-            done += uint64_t(w);
-        }
-        s->at += len;
-        return 0;
+        PartWriter *w = static_cast<PartWriter *>(user);
+        if (w->failed) return 1;
+        if (w->parts.size() < 2) { if (!write_all(w->parts[0].fd, data, len)) { w->failed = true; return 1; } return 0; }
+        Part &p = w->parts[w->next++ % w->parts.size()];
+        { std::lock_guard<std::mutex> l(p.m); p.q.emplace_back(data, len); }
+        p.cv.notify_all();
+        return SIMMR_SINK_RETAINED;
     }
 };
 
@@ -197,53 +233,44 @@ int main(int argc, char **argv) {
     std::vector<uint64_t> reads(gs.n_genomes); std::vector<double> ab_out(gs.n_genomes);
     if (simmr_abundance_counts(&ap, args.num_reads, gs.n_genomes, k_sizes.data(), reads.data(), ab_out.data())) die(simmr_last_error(nullptr));
 
+    if (ep.kind == SIMMR_EP_CUSTOM_LONG) {
+        uint32_t ek = 0, en = 0;
+        std::vector<uint32_t> words(size_t(1) << 24);
+        if (simmr_debug_err_table(&ep, &ek, &en, words.data(), words.size()) >= 0 && ek == 0)
+            warn("the custom long-read profile has no alt-k-mer table: reads carry its quality scores but no sequencing errors");
+    }
     info(is_long ? "Simulating long reads" : "Simulating short reads");
     info("Writing simulated reads to " + args.output);
     unlink(args.output.c_str());                        /* main.rs:191-198 */
     unlink((args.output + ".tsv").c_str());
-    const int fd = open(args.output.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0) die("Failed to write reads to the output file: cannot create " + args.output);
+    PartWriter writer{size_t(args.parts)};
+    for (int p = 0; p < args.parts; ++p) {
+        char suffix[16]; snprintf(suffix, sizeof suffix, ".%03d", p);
+        const std::string path = args.parts > 1 ? args.output + suffix : args.output;
+        writer.parts[p].fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (writer.parts[p].fd < 0) die("Failed to write reads to the output file: cannot create " + path);
+    }
 
-    simmr_run_opts base{};
-    base.has_seed = 1;
-    if (args.has_seed) base.seed = args.seed;
-    else { std::ifstream r("/dev/urandom", std::ios::binary); r.read(reinterpret_cast<char *>(&base.seed), 8); }   /* from_entropy, simulate.rs:174 */
-    base.header_format = args.header_format.empty() ? nullptr : args.header_format.c_str();
+    simmr_run_opts opts{};
+    opts.has_seed = 1;
+    if (args.has_seed) opts.seed = args.seed;
+    else { std::ifstream r("/dev/urandom", std::ios::binary); r.read(reinterpret_cast<char *>(&opts.seed), 8); }   /* from_entropy, simulate.rs:174 */
+    opts.header_format = args.header_format.empty() ? nullptr : args.header_format.c_str();
+    opts.batch_units = args.batch_units;
 
-    /* one host thread and one context per GPU; shard = contiguous range of the global unit index */
-    const int G = args.gpus;
-    std::vector<uint64_t> shard_bytes(G, 0);
-    std::vector<std::string> errors(G);
-    std::mutex mu; std::condition_variable cv; int measured = 0; bool abort_run = false;
-    std::atomic<uint64_t> total_units{0};
-    auto worker = [&](int k) {
-        simmr_ctx *ctx = nullptr;
-        auto bail = [&](const std::string &m) { errors[k] = m; { std::lock_guard<std::mutex> l(mu); abort_run = true; ++measured; } cv.notify_all(); if (ctx) simmr_ctx_destroy(ctx); };
-        if (simmr_ctx_create(k, &ctx)) return bail(simmr_last_error(nullptr));
-        if (simmr_genomes_load(ctx, &gs) || simmr_error_profile_set(ctx, &ep)) return bail(simmr_last_error(ctx));
-        const uint64_t N = simmr_total_units(ctx, reads.data());
-        total_units = N;
-        simmr_run_opts o = base;
-        o.unit_begin = N * uint64_t(k) / uint64_t(G); o.unit_end = N * uint64_t(k + 1) / uint64_t(G);
-        uint64_t nb = 0, nr = 0;
-        if (o.unit_end > o.unit_begin && simmr_measure(ctx, reads.data(), &o, &nb, &nr)) return bail(simmr_last_error(ctx));
-        {   /* the host-side count exchange: every shard's bytes -> its offset in the file */
-            std::unique_lock<std::mutex> l(mu);
-            shard_bytes[k] = nb; ++measured; cv.notify_all();
-            cv.wait(l, [&] { return measured == G; });
-            if (abort_run) { l.unlock(); simmr_ctx_destroy(ctx); return; }
-        }
-        FileSink sink{fd, 0};
-        for (int j = 0; j < k; ++j) sink.at += shard_bytes[j];
-        if (o.unit_end > o.unit_begin && simmr_simulate(ctx, reads.data(), &o, &FileSink::call, &sink))
-            errors[k] = sink.failed ? "Failed to write reads to the output file" : simmr_last_error(ctx);
-        simmr_ctx_destroy(ctx);
-    };
-    std::vector<std::thread> th;
-    for (int k = 0; k < G; ++k) th.emplace_back(worker, k);
-    for (auto &t : th) t.join();
-    close(fd);
-    for (const auto &m : errors) if (!m.empty()) die(m);
+    /* one context and launch thread per GPU inside the library, batches dealt round-robin, one writer thread calling
+     * PartWriter::call in file order (genomes replicated, no device collective) */
+    std::vector<int> devices(args.gpus);
+    for (int k = 0; k < args.gpus; ++k) devices[k] = k;
+    simmr_multi *multi = nullptr;
+    if (simmr_multi_create(devices.data(), args.gpus, &multi)) die(simmr_multi_last_error(nullptr));
+    if (simmr_multi_genomes_load(multi, &gs) || simmr_multi_error_profile_set(multi, &ep)) die(simmr_multi_last_error(multi));
+    writer.start();
+    const int run_rc = simmr_multi_simulate(multi, reads.data(), &opts, &PartWriter::call, &writer);
+    writer.finish();
+    if (writer.failed) die("Failed to write reads to the output file");
+    if (run_rc) die(simmr_multi_last_error(multi));
+    simmr_multi_destroy(multi);
 
     info("Writing simulation metadata to " + args.output + ".tsv");
     std::vector<std::string> ids(gs.n_genomes);

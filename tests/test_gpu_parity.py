@@ -112,8 +112,10 @@ def test_batching_and_sharding_do_not_change_bytes(engine):
     assert small == whole
     total = engine.total_units(reads)
     parts = [engine.simulate_bytes(reads, 99, unit_begin=a, unit_end=b) for a, b in
-             [(0, 1), (1, total // 3), (total // 3, total // 3), (total // 3, total - 1), (total - 1, total)] if b > a]
+             [(0, 0), (0, 1), (1, total // 3), (total // 3, total // 3), (total // 3, total - 1), (total - 1, total)]]
+    assert parts[0] == b"" and parts[3] == b""            # an explicit empty range is empty, also at unit 0 (an empty first shard)
     assert b"".join(parts) == whole
+    assert engine.measure(reads, 99, unit_begin=0, unit_end=0) == (0, 0)
 
 
 def test_header_format_and_ids(engine):
@@ -349,6 +351,38 @@ def test_cli_binary_end_to_end(engine, tmp_path, mode):
     assert bad.returncode == 1 and "invalid value" in bad.stderr
 
 
+def test_cli_output_parts(engine, tmp_path):
+    """--output-parts P: chunk j of the run goes to part j mod P, every part written by its own I/O thread from pinned
+    buffers the sink retains (SIMMR_SINK_RETAINED / simmr_chunk_release)."""
+    import os
+    import subprocess
+    rng = np.random.default_rng(8)
+    paths = []
+    for g in range(2):
+        p = str(tmp_path / f"g{g}.fna")
+        _write_fasta(p, [(f"g{g}_c{c}".encode(), np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(rng.integers(3000, 9000)))]) for c in range(2)])
+        paths.append(p)
+    out = str(tmp_path / "reads.fq")
+    exe = os.path.join(os.path.dirname(S._native.LIB_PATH), "simmr")
+    cmd = [exe] + sum([["--genome", p] for p in paths], []) + ["--output", out, "--num-reads", "5000", "--seed", "4", "--error-profile",
+                                                                  "minimal-short", "--output-parts", "3", "--batch-units", "100"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert not os.path.exists(out)
+    ids = [ln.split("\t")[0] for ln in open(out + ".tsv").read().splitlines()[1:]]
+    prof = S.MinimalShortErrorProfile()
+    gs, _ = S.GenomeSet.from_fasta(paths, uuids=ids, min_size=prof.minimum_genome_size())
+    reads, _ = S.UniformAbundanceProfile().determine_abundances(5000, 2)
+    og, oprof = po.Genomes.from_set(gs), H.oracle_profile(prof)
+    total = po.total_units(oprof, reads)
+    want = [b"", b"", b""]
+    for j, ub in enumerate(range(0, total, 100)):
+        want[j % 3] += po.simulate(og, oprof, reads, 4, unit_begin=ub, unit_end=min(total, ub + 100))
+    for p in range(3):
+        got = open(f"{out}.{p:03d}", "rb").read()
+        assert got == want[p], first_diff(got, want[p])
+
+
 def test_full_size_c2_properties(engine):
     """BASELINE config C2 at its full size (100 M reads, 100 genomes, ~0.5 GB): size-independent properties of
     the whole run, and byte parity with the oracle on slices taken far into it (64-bit offsets, batch seams)."""
@@ -424,3 +458,45 @@ def test_no_write_past_the_batch(engine, monkeypatch):
         check_native(engine, gs, prof, reads, 3, batch_units=997)
     gl = H.synth_genomes(2, (1, 2), (21000, 70000), seed=62)
     check_native(engine, gl, S.MinimalLongErrorProfile(20), [33, 21], 5, batch_units=13)
+
+
+def test_multi_device_context_single_gpu_and_more(engine):
+    """simmr_multi: per-device launch threads, one writer thread, batches dealt round-robin and handed to
+    the sink in file order.  With one device it must equal the plain context; with every visible device the bytes must
+    still be the one-GPU bytes, whatever the batch size."""
+    import torch
+    gs = H.synth_genomes(4, (1, 3), (3000, 8000), seed=9)
+    prof = S.MinimalShortErrorProfile()
+    reads = [1500, 700, 0, 2200]
+    whole = check_native(engine, gs, prof, reads, 99)
+    ndev = torch.cuda.device_count()
+    for devices in ([0], list(range(ndev))):
+        with S.MultiEngine(devices) as me:
+            me.load_genomes(gs)
+            me.set_error_profile(prof)
+            assert me.total_units(reads) == engine.total_units(reads)
+            for bu in (0, 97, 1000):
+                order = []
+                got = []
+                st = me.simulate(reads, 99, batch_units=bu, sink=lambda a, f, n: (order.append(f), got.append(a.tobytes())) and 0)
+                assert b"".join(got) == whole and order == sorted(order)
+                assert st["bytes"] == len(whole) and st["records"] == 2 * engine.total_units(reads)
+            part = []
+            me.simulate(reads, 99, unit_begin=100, unit_end=900, batch_units=64, sink=lambda a, f, n: part.append(a.tobytes()) and 0)
+            assert b"".join(part) == engine.simulate_bytes(reads, 99, unit_begin=100, unit_end=900)
+            st = me.simulate(reads, 99)                                   # device-resident on every device
+            assert st["bytes"] == len(whole)
+            with pytest.raises(S.SimmrError):
+                me.simulate(reads, 99, batch_units=50, sink=lambda a, f, n: 1)       # a failing sink stops the run
+            assert b"".join(got) == whole
+    with pytest.raises(S.SimmrError):
+        S.MultiEngine([0, 0])
+
+
+def test_sink_runs_on_the_library_writer_thread(engine):
+    import threading
+    gs = H.synth_genomes(2, (1, 2), (3000, 6000), seed=3)
+    engine.load_genomes(gs); engine.set_error_profile(S.PerfectShortErrorProfile())
+    seen = set()
+    engine.simulate([4000, 4000], 1, batch_units=100, sink=lambda a, f, n: seen.add(threading.get_ident()) and 0)
+    assert len(seen) == 1 and threading.get_ident() not in seen
