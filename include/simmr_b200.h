@@ -204,6 +204,10 @@ int  simmr_builder_create(simmr_genome_builder **out);
 void simmr_builder_destroy(simmr_genome_builder *b);
 /* Genome::from_fasta (genome.rs:89-162): uuid NULL -> random (util.rs:124-129) */
 int  simmr_builder_add_fasta(simmr_genome_builder *b, const char *path, const char *uuid, int contiguous);
+/* the same for n files at once, read, decompressed (gzip, bzip2, xz by their magic bytes, as needletail does) and normalised
+ * in parallel; uuids may be NULL or hold NULL entries; threads <= 0: one per core, at most 32 */
+int  simmr_builder_add_fastas(simmr_genome_builder *b, const char *const *paths, const char *const *uuids, uint32_t n,
+                              int contiguous, int threads);
 /* main.rs:117-162: drop contigs with size <= min_size, then empty genomes.
  * kept[i] (optional, one per genome added) says whether genome i survived. */
 int  simmr_builder_filter(simmr_genome_builder *b, uint16_t min_size, uint8_t *kept);

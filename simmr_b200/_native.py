@@ -70,7 +70,7 @@ EXPORTS = [
     "simmr_genomes_load", "simmr_error_profile_set", "simmr_eprofile_minimum_genome_size",
     "simmr_eprofile_is_long_read", "simmr_abundance_counts", "simmr_simulate", "simmr_replay",
     "simmr_total_units", "simmr_measure", "simmr_stats_get", "simmr_builder_create", "simmr_builder_destroy",
-    "simmr_builder_add_fasta", "simmr_builder_filter", "simmr_builder_view", "simmr_builder_genome_size",
+    "simmr_builder_add_fasta", "simmr_builder_add_fastas", "simmr_builder_filter", "simmr_builder_view", "simmr_builder_genome_size",
     "simmr_builder_error", "simmr_parse_genome_file", "simmr_write_metadata", "simmr_debug_phred_table",
     "simmr_debug_len_table", "simmr_debug_err_table", "simmr_debug_philox4x32_10", "simmr_version",
     "simmr_multi_create", "simmr_multi_destroy", "simmr_multi_genomes_load", "simmr_multi_error_profile_set",
@@ -123,6 +123,7 @@ def lib():
         L.simmr_builder_destroy.argtypes = [C.c_void_p]
         L.simmr_builder_destroy.restype = None
         L.simmr_builder_add_fasta.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+        L.simmr_builder_add_fastas.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_uint32, C.c_int, C.c_int]
         L.simmr_builder_filter.argtypes = [C.c_void_p, C.c_uint16, u8p]
         L.simmr_builder_view.argtypes = [C.c_void_p, C.POINTER(GenomeSetC)]
         L.simmr_builder_genome_size.argtypes = [C.c_void_p, C.c_uint32]

@@ -245,17 +245,19 @@ class GenomeSet:
         return cls(allb, coff, csize, gcon, cids, cidoff, gids, gidoff)
 
     @classmethod
-    def from_fasta(cls, paths, uuids=None, contiguous=False, min_size=None):
+    def from_fasta(cls, paths, uuids=None, contiguous=False, min_size=None, threads=0):
         """Genome::from_fasta per path (genome.rs:89-162) then, when `min_size` is
         given, the contig filter of main.rs:117-162.  Returns (set, kept mask)."""
         L = N.lib()
         b = C.c_void_p()
         _check(L.simmr_builder_create(C.byref(b)))
         try:
-            for i, pth in enumerate(paths):
-                u = None if uuids is None or uuids[i] is None else uuids[i].encode()
-                if L.simmr_builder_add_fasta(b, os.fsencode(pth), u, int(contiguous)) < 0:
-                    raise SimmrError(N.E_PARSE, L.simmr_builder_error(b).decode(errors="replace"))
+            n = len(paths)
+            P = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+            U = (C.c_char_p * n)(*[None if uuids is None or uuids[i] is None else uuids[i].encode() for i in range(n)])
+            rc = L.simmr_builder_add_fastas(b, P, U, n, int(contiguous), int(threads))      # parallel over files and chunks
+            if rc < 0:
+                raise SimmrError(rc, L.simmr_builder_error(b).decode(errors="replace"))
             sizes = [L.simmr_builder_genome_size(b, g) for g in range(len(paths))]
             kept = np.ones(len(paths), np.uint8)
             if min_size is not None and not contiguous:        # main.rs:117 `if !args.contiguous`

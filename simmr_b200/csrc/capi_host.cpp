@@ -22,6 +22,10 @@ int simmr_builder_add_fasta(simmr_genome_builder *b, const char *path, const cha
     if (!b || !path) return SIMMR_E_INVALID;
     return b->store.add_fasta(path, uuid, contiguous != 0);
 }
+int simmr_builder_add_fastas(simmr_genome_builder *b, const char *const *paths, const char *const *uuids, uint32_t n, int contiguous, int threads) {
+    if (!b || (!paths && n)) return SIMMR_E_INVALID;
+    return b->store.add_fastas(paths, uuids, n, contiguous != 0, threads > 0 ? unsigned(threads) : 0u);
+}
 int simmr_builder_filter(simmr_genome_builder *b, uint16_t min_size, uint8_t *kept) {
     if (!b) return SIMMR_E_INVALID;
     b->store.filter(min_size, kept);

@@ -512,125 +512,6 @@ int abundance_counts(const simmr_aprofile_desc *d, uint64_t total_reads, uint32_
 }
 
 /* ====================================================================== */
-/* FASTA ingest — genome.rs:89-162 with needletail 0.4.1 normalize(false)   */
-/* ====================================================================== */
-namespace {
-struct Norm {
-    int8_t map[256];
-    Norm() {
-        for (int i = 0; i < 256; ++i) map[i] = 'N';            /* everything else, IUPAC included */
-        for (char c : {'A', 'C', 'G', 'T', 'N', '-'}) map[uint8_t(c)] = c;
-        map['a'] = 'A'; map['c'] = 'C'; map['g'] = 'G'; map['t'] = 'T'; map['n'] = 'N';
-        map['u'] = map['U'] = 'T'; map['.'] = map['~'] = '-';
-        map[' '] = map['\t'] = map['\r'] = map['\n'] = 0;     /* dropped */
-    }
-};
-const Norm kNorm;
-
-bool slurp(const char *path, std::string &data, std::string &err) {
-    gzFile f = gzopen(path, "rb");                            /* plain files pass through */
-    if (!f) { err = std::string("cannot open ") + path; return false; }
-    gzbuffer(f, 1 << 20);
-    std::vector<char> buf(1 << 22);
-    for (;;) {
-        const int got = gzread(f, buf.data(), unsigned(buf.size()));
-        if (got < 0) { err = std::string("read error in ") + path; gzclose(f); return false; }
-        if (got == 0) break;
-        data.append(buf.data(), size_t(got));
-    }
-    gzclose(f);
-    if (data.size() >= 3 && uint8_t(data[0]) == 'B' && data[1] == 'Z' && data[2] == 'h') { err = "bzip2 input is not supported"; return false; }
-    if (data.size() >= 6 && uint8_t(data[0]) == 0xFD && !memcmp(data.data() + 1, "7zXZ", 4)) { err = "xz input is not supported"; return false; }
-    return true;
-}
-
-std::string random_uuid() {   /* util.rs:124-129: top 64 bits of a v4 UUID, `{:x}` */
-    std::random_device rd;
-    uint64_t v = (uint64_t(rd()) << 32) | rd();
-    v = (v & ~0xF000ull) | 0x4000ull;
-    char b[32]; snprintf(b, sizeof b, "%llx", (unsigned long long)v);
-    return b;
-}
-}  // namespace
-
-int GenomeStore::add_fasta(const char *path, const char *uuid, bool contiguous) {
-    std::string data;
-    if (!slurp(path, data, err)) return SIMMR_E_IO;
-    size_t i = 0; const size_t n = data.size();
-    while (i < n && (data[i] == '\n' || data[i] == '\r')) ++i;
-    if (i < n && data[i] != '>') { err = std::string(path) + ": not FASTA (a record must start with '>')"; return SIMMR_E_PARSE; }
-    struct Rec { std::string id; size_t b, e; };
-    std::vector<Rec> recs;
-    const size_t base0 = bases.size();
-    uint64_t total = 0;
-    while (i < n) {
-        size_t eol = data.find('\n', i);
-        if (eol == std::string::npos) eol = n;
-        size_t idend = eol; if (idend > i && data[idend - 1] == '\r') --idend;
-        Rec r; r.id.assign(data, i + 1, idend - i - 1); r.b = bases.size();
-        i = std::min(n, eol + 1);
-        while (i < n) {
-            /* a line starting with '>' begins the next record */
-            if (data[i] == '>' && data[i - 1] == '\n') break;
-            const int8_t c = kNorm.map[uint8_t(data[i++])];
-            if (c) bases.push_back(uint8_t(c));
-        }
-        r.e = bases.size(); total += r.e - r.b;
-        recs.push_back(std::move(r));
-    }
-    auto push_contig = [&](const std::string &id, uint64_t phys_end, uint64_t logical) {
-        contig_off.push_back(phys_end); contig_size.push_back(logical);
-        contig_ids += id; contig_id_off.push_back(uint32_t(contig_ids.size()));
-    };
-    if (contiguous) {   /* genome.rs:117-136: one Seq, contigs each followed by 'N', size without the Ns */
-        std::vector<uint8_t> joined; joined.reserve(total + recs.size());
-        for (const Rec &r : recs) { joined.insert(joined.end(), bases.begin() + r.b, bases.begin() + r.e); joined.push_back('N'); }
-        bases.resize(base0); bases.insert(bases.end(), joined.begin(), joined.end());
-        push_contig("whole genome", bases.size(), total);
-    } else {
-        for (const Rec &r : recs) push_contig(r.id, r.e, r.e - r.b);
-    }
-    genome_contig.push_back(uint32_t(contig_size.size()));
-    genome_ids += uuid ? std::string(uuid) : random_uuid();
-    genome_id_off.push_back(uint32_t(genome_ids.size()));
-    genome_size.push_back(total);
-    paths.push_back(path);
-    return SIMMR_OK;
-}
-
-/* main.rs:117-162 */
-void GenomeStore::filter(uint16_t min_size, uint8_t *kept) {
-    GenomeStore o;
-    const uint32_t ng = uint32_t(genome_contig.size()) - 1;
-    for (uint32_t g = 0; g < ng; ++g) {
-        const size_t before = o.contig_size.size();
-        for (uint32_t c = genome_contig[g]; c < genome_contig[g + 1]; ++c) {
-            if (contig_size[c] <= min_size) continue;                 /* main.rs:124 */
-            o.bases.insert(o.bases.end(), bases.begin() + contig_off[c], bases.begin() + contig_off[c + 1]);
-            o.contig_off.push_back(o.bases.size()); o.contig_size.push_back(contig_size[c]);
-            o.contig_ids.append(contig_ids, contig_id_off[c], contig_id_off[c + 1] - contig_id_off[c]);
-            o.contig_id_off.push_back(uint32_t(o.contig_ids.size()));
-        }
-        const bool keep = o.contig_size.size() > before;               /* main.rs:144-156 */
-        if (kept) kept[g] = keep;
-        if (!keep) continue;
-        o.genome_contig.push_back(uint32_t(o.contig_size.size()));
-        o.genome_ids.append(genome_ids, genome_id_off[g], genome_id_off[g + 1] - genome_id_off[g]);
-        o.genome_id_off.push_back(uint32_t(o.genome_ids.size()));
-        o.genome_size.push_back(genome_size[g]);
-        o.paths.push_back(paths[g]);
-    }
-    *this = std::move(o);
-}
-
-void GenomeStore::view(simmr_genome_set &v) const {
-    v.n_genomes = uint32_t(genome_contig.size()) - 1; v.n_contigs = uint32_t(contig_size.size());
-    v.bases = bases.data(); v.contig_off = contig_off.data(); v.contig_size = contig_size.data();
-    v.genome_contig = genome_contig.data(); v.contig_ids = contig_ids.data(); v.contig_id_off = contig_id_off.data();
-    v.genome_ids = genome_ids.data(); v.genome_id_off = genome_id_off.data();
-}
-
-/* ====================================================================== */
 /* genome file + metadata — files.rs                                        */
 /* ====================================================================== */
 bool utf8_ok(const uint8_t *s, size_t n) {

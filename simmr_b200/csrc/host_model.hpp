@@ -3,6 +3,8 @@
  * counts, FASTA / genome-file ingest, per-contig header templates.
  * Citations are relative to the reference tree (/root/reference/). */
 #pragma once
+#include <algorithm>
+#include <cstring>
 #include <string>
 #include <vector>
 #include "../../include/simmr_b200.h"
@@ -81,9 +83,32 @@ int build_profile(const simmr_eprofile_desc *d, ProfileModel &m, std::string &er
 int abundance_counts(const simmr_aprofile_desc *d, uint64_t total_reads, uint32_t n, const uint64_t *sizes,
                      uint64_t *out_reads, double *out_abund, std::string &err);
 
+/* growable byte buffer that does not zero what it grows by (a 4 GB genome set is filled by parallel copies) */
+class ByteBuf {
+    uint8_t *p_ = nullptr; size_t n_ = 0, cap_ = 0;
+public:
+    ByteBuf() = default;
+    ByteBuf(const ByteBuf &) = delete;
+    ByteBuf &operator=(const ByteBuf &) = delete;
+    ~ByteBuf() { delete[] p_; }
+    size_t size() const { return n_; }
+    uint8_t *data() { return p_; }
+    const uint8_t *data() const { return p_; }
+    void grow(size_t n) {             /* size becomes n >= size(); new bytes are uninitialised */
+        if (n > cap_) {
+            const size_t cap = std::max(n, cap_ + cap_ / 2);
+            uint8_t *q = new uint8_t[cap];
+            if (n_) memcpy(q, p_, n_);
+            delete[] p_; p_ = q; cap_ = cap;
+        }
+        n_ = n;
+    }
+    void shrink(size_t n) { if (n < n_) n_ = n; }
+};
+
 /* genome.rs:15-41 flattened */
 struct GenomeStore {
-    std::vector<uint8_t> bases;
+    ByteBuf bases;
     std::vector<uint64_t> contig_off{0}, contig_size;
     std::vector<uint32_t> genome_contig{0};
     std::string contig_ids, genome_ids;
@@ -92,6 +117,8 @@ struct GenomeStore {
     std::vector<std::string> paths;
     std::string err;
     int add_fasta(const char *path, const char *uuid, bool contiguous);
+    /* n files at once: read, decompressed and normalised in parallel (threads == 0: one per core, at most 32) */
+    int add_fastas(const char *const *path, const char *const *uuid, uint32_t n, bool contiguous, unsigned threads);
     void filter(uint16_t min_size, uint8_t *kept);
     void view(simmr_genome_set &v) const;
 };

@@ -207,11 +207,14 @@ int main(int argc, char **argv) {
     }
     simmr_genome_builder *gb = nullptr;
     if (simmr_builder_create(&gb)) die("out of memory");
-    for (size_t i = 0; i < paths.size(); ++i) {
-        if (simmr_builder_add_fasta(gb, paths[i].c_str(), has_uuid[i] ? uuids[i].c_str() : nullptr, args.contiguous))
-            die("Failed to parse " + paths[i] + ": " + simmr_builder_error(gb));
+    for (size_t i = 0; i < paths.size(); ++i)
         if (ap_kind == SIMMR_AP_CUSTOM && std::isnan(abund[i]))    /* main.rs:80-86 */
             die("You used a custom abundance profile but didn't provide abundances for genome " + paths[i]);
+    {   /* every assembly is read, decompressed and normalised in parallel (genome.rs:89-162 does them one by one) */
+        std::vector<const char *> pp(paths.size()), up(paths.size());
+        for (size_t i = 0; i < paths.size(); ++i) { pp[i] = paths[i].c_str(); up[i] = has_uuid[i] ? uuids[i].c_str() : nullptr; }
+        if (simmr_builder_add_fastas(gb, pp.data(), up.data(), uint32_t(paths.size()), args.contiguous, 0))
+            die(std::string("Failed to parse a genome: ") + simmr_builder_error(gb));
     }
     std::vector<uint64_t> all_sizes(paths.size());
     for (size_t i = 0; i < paths.size(); ++i) all_sizes[i] = simmr_builder_genome_size(gb, uint32_t(i));

@@ -155,6 +155,54 @@ def test_fasta_ingest_matches_oracle_and_reference_fixture(tmp_path):
     assert re.fullmatch(r"[0-9a-f]{1,16}", gs.uuid(0))
 
 
+def test_fasta_ingest_compressed_and_parallel(tmp_path, monkeypatch):
+    """needletail reads gzip, bzip2 and xz by their magic bytes (genome.rs:93); several files load in parallel and a large
+    file is cut at line starts into chunks normalised in parallel (SIMMR_FASTA_CHUNK shrinks the chunks for the test)."""
+    import bz2
+    import gzip
+    import lzma
+    rng = np.random.default_rng(4)
+    files, texts = [], []
+    for g in range(5):
+        recs = []
+        for c in range(int(rng.integers(1, 5))):
+            seq = np.frombuffer(b"ACGTacgtNnRY-.", np.uint8)[rng.integers(0, 14, int(rng.integers(0, 30000)))].tobytes()
+            w = int(rng.integers(50, 90))
+            recs.append(b">g%d_c%d description %d\n" % (g, c, c) + b"".join(seq[i:i + w] + (b"\r\n" if c % 2 else b"\n") for i in range(0, len(seq), w)))
+        texts.append(b"".join(recs))
+        files.append(_write(tmp_path, f"g{g}.fna", texts[-1]))
+    plain, _ = S.GenomeSet.from_fasta(files, uuids=[f"u{g}" for g in range(5)], threads=1)
+    for g in range(5):                                        # against the oracle's single-threaded reader
+        og = po.load_fasta(files[g])
+        c0 = int(plain.genome_contig[g])
+        assert int(plain.genome_contig[g + 1]) - c0 == og["num_seqs"] and int(plain.genome_sizes[g]) == og["size"]
+        for c in range(og["num_seqs"]):
+            assert plain.contig_id(c0 + c) == og["seqs"][c]["id"] and plain.contig(c0 + c).tobytes() == og["seqs"][c]["seq"]
+    same = lambda a, b: (np.array_equal(a.bases, b.bases) and np.array_equal(a.contig_off, b.contig_off) and a.contig_ids == b.contig_ids
+                         and np.array_equal(a.genome_contig, b.genome_contig) and np.array_equal(a.genome_sizes, b.genome_sizes))
+    monkeypatch.setenv("SIMMR_FASTA_CHUNK", "3000")
+    for threads in (2, 8, 0):
+        chunked, _ = S.GenomeSet.from_fasta(files, uuids=[f"u{g}" for g in range(5)], threads=threads)
+        assert same(plain, chunked)
+        cont, _ = S.GenomeSet.from_fasta(files, uuids=None, contiguous=True, threads=threads)
+        for g in range(5):
+            oc = po.load_fasta(files[g], contiguous=True)
+            assert cont.contig(g).tobytes() == oc["seqs"][0]["seq"] and int(cont.contig_size[g]) == oc["seqs"][0]["size"]
+    monkeypatch.delenv("SIMMR_FASTA_CHUNK")
+    packed = []
+    for g, t in enumerate(texts):
+        half = len(t) // 2
+        data = [gzip.compress(t), gzip.compress(t[:half]) + gzip.compress(t[half:]), bz2.compress(t), bz2.compress(t[:half]) + bz2.compress(t[half:]),
+                lzma.compress(t, format=lzma.FORMAT_XZ)][g]
+        packed.append(_write(tmp_path, f"p{g}.fna.{'gz gz bz2 bz2 xz'.split()[g]}", data))
+    comp, _ = S.GenomeSet.from_fasta(packed, uuids=[f"u{g}" for g in range(5)])
+    assert same(plain, comp)
+    with pytest.raises(S.SimmrError):
+        S.GenomeSet.from_fasta([_write(tmp_path, "cut.fna.gz", gzip.compress(texts[0])[:-20])])
+    with pytest.raises(S.SimmrError):
+        S.GenomeSet.from_fasta([_write(tmp_path, "cut.fna.bz2", bz2.compress(texts[0])[:-20])])
+
+
 def test_contig_filter(tmp_path):
     """main.rs:117-162: contigs with size <= minimum are dropped, then empty genomes; Genome.size keeps
     its pre-filter value (main.rs:158-161)."""
