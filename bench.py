@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--reads-per-gpu", type=int, default=READS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-to-file", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,21 +233,40 @@ def main():
     total_units = eng.total_units(reads)
     ub, ue = rank * total_units // world, (rank + 1) * total_units // world
 
+    # `value`: the device-resident run through simmr_simulate_device — every batch is handed to a consumer on the device
+    # (here: it reads the batch's first and last byte back, '@' and '\n'), FASTQ bytes never leave HBM
+    from cuda.bindings import runtime as cudart
+    probe = np.zeros(2, np.uint8)
+    seen = [0, 0]
+
+    def consumer(ptr, n, first, units):
+        if n:
+            cudart.cudaMemcpy(probe.ctypes.data, ptr, 1, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+            cudart.cudaMemcpy(probe.ctypes.data + 1, ptr + n - 1, 1, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+            if probe[0] != ord("@") or probe[1] != ord("\n"):
+                return 1
+        seen[0] += n
+        seen[1] += 1
+        return 0
+
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(args.warmup):
-        eng.simulate(reads, SEED, unit_begin=ub, unit_end=ue)
+        eng.simulate_device(reads, SEED, consumer, unit_begin=ub, unit_end=ue)
     barrier()
     t_timed0 = time.perf_counter()
     dev_ms = fmt_ms = 0.0
-    bases = records = alg = launches = 0
+    bases = records = alg = launches = nbytes = 0
+    seen[:] = [0, 0]
     for _ in range(args.steps):
-        st = eng.simulate(reads, SEED, unit_begin=ub, unit_end=ue)
+        st = eng.simulate_device(reads, SEED, consumer, unit_begin=ub, unit_end=ue)
         dev_ms += st["device_ms"]; fmt_ms += st["format_ms"]
-        bases += st["bases"]; records += st["records"]; alg += st["algorithmic_bytes"]; launches += st["kernel_launches"]
+        bases += st["bases"]; records += st["records"]; alg += st["algorithmic_bytes"]; launches += st["kernel_launches"]; nbytes += st["bytes"]
     barrier()
     t_timed1 = time.perf_counter()
     sampler.stop_flag.set()
+    assert seen[0] == nbytes                     # the consumer was shown every byte of every step
+    n_format_launches = seen[1]
     t = torch.tensor([dev_ms, float(bases), float(records)], dtype=torch.float64, device="cuda")
     if dist is not None:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -255,15 +276,16 @@ def main():
         max_ms, all_bases, all_records = dev_ms, float(bases), float(records)
     value = all_bases / (max_ms / 1e3) / 1e9
 
-    # the format kernel by itself: the library normally prepares batch b+1 (geometry, sizes, offsets) on a second stream
-    # beside batch b's format kernel, which shares the SMs; one extra untimed step with everything on one stream gives
-    # the kernel's duration without co-runners (reported next to the figure of the timed region)
+    # the format kernel by itself: the library normally prepares batch b+1 (geometry, sizes, offsets, size-sorted tiles) on a
+    # second stream beside batch b's format kernel, which shares the SMs; one extra untimed step with everything on one
+    # stream gives the kernel's duration without co-runners (reported next to the figure of the timed region)
     os.environ["SIMMR_PREP_SERIAL"] = "1"
     st = eng.simulate(reads, SEED, unit_begin=ub, unit_end=ue)
     del os.environ["SIMMR_PREP_SERIAL"]
-    alone_ms, alone_alg, alone_launches = st["format_ms"], st["algorithmic_bytes"], max(1, st["kernel_launches"] // 4)
+    alone_ms, alone_alg = st["format_ms"], st["algorithmic_bytes"]
+    alone_launches = max(1, n_format_launches // max(1, args.steps))
 
-    # end to end: host genome buffers -> device, FASTQ bytes -> pinned host, inside the timed region
+    # end to end: host genome buffers -> device, FASTQ bytes -> pinned host -> the sink (library writer thread), inside the timed region
     e2e_bases = e2e_d2h = 0
     if args.e2e_steps:      # untimed: the pinned output ring is allocated on the first call that has a sink
         eng.simulate(reads, SEED, unit_begin=ub, unit_end=min(ue, ub + 2_000_000), sink=lambda a, f, n: 0)
@@ -281,7 +303,10 @@ def main():
     tb = torch.tensor([float(e2e_bases)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(tb, op=dist.ReduceOp.SUM)
-    e2e_value = float(tb[0]) / float(te[0]) / 1e9
+    e2e_value = float(tb[0]) / float(te[0]) / 1e9 if args.e2e_steps else None
+
+    strong = strong_scaling(S, eng, torch, dist, barrier, rank, world) if not args.no_strong else None
+    to_file = fastq_to_file(S, gs, local) if (rank == 0 and not args.no_to_file) else None
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -290,31 +315,128 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = alg / (fmt_ms / 1e3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("format_kernel_dram_bytes_per_launch")
-        n_launch = max(1, launches // 4)
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get("format_kernel_dram_bytes_per_launch"), tj.get("source")
+        n_launch = max(1, n_format_launches)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u8", "data": "synthetic", "config": workload_config(world),
                "reads_per_second": all_records / (max_ms / 1e3), "clocks": sampler.summary(t_timed0, t_timed1), "gpu_launches": launches,
+               "value_note": "device-resident: every batch's FASTQ bytes are handed to a consumer on the device (simmr_simulate_device); e2e is the same job with host buffers",
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(gs.bases.nbytes),
                        "d2h_bytes_per_step": int(e2e_d2h // max(1, args.e2e_steps)), "steps": args.e2e_steps},
                "roofline": {"bound": "hbm", "kernel": "k_format_lanes", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                            "bytes": "algorithmic: sum over records of 3L + H + 5 (L source bases at one byte each, H + 2L + 5 written; SURVEY.md §8d) — the kernel "
+                                     "reads the 2-bit genome copy, so its real DRAM traffic (`traffic`, an offline ncu capture) is lower",
                             "algorithmic_bytes_per_launch": alg / n_launch,
                             "launch_ms": fmt_ms / n_launch, "launches": n_launch, "kernel_share_of_step": fmt_ms / dev_ms,
+                            "whole_step_frac": (alg / (dev_ms / 1e3) / 1e9) / peak,
                             "note": "timed region: the next batch's small kernels run beside this kernel on a second stream",
                             "alone": {"achieved": alone_alg / (alone_ms / 1e3) / 1e9, "frac": alone_alg / (alone_ms / 1e3) / 1e9 / peak,
                                       "launch_ms": alone_ms / alone_launches, "launches": alone_launches,
                                       "note": "one extra untimed step with every kernel on one stream"}}}
+        if strong is not None:
+            out["strong"] = strong
+        if to_file is not None:
+            out["to_file"] = to_file
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(gs, reads)
         print(json.dumps(out))
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def strong_scaling(S, eng, torch, dist, barrier, rank, world):
+    """BASELINE config 5 as a fixed job: exact abundance, 1000 synthetic genomes (4.4 GB), 1 M reads each = 1 B reads,
+    sharded by unit index over the ranks (genomes replicated, no data-path collective); device time = max over ranks.
+    Rank 0 then runs the whole job alone, which gives the efficiency T1 / (N * TN) inside one bench run."""
+    from simmr_b200.synth import synthetic_genomes
+    try:
+        g5 = synthetic_genomes(1000, 4_000_000, 4_800_000, (1, 6), seed=5)
+        reads, _ = S.ExactAbundanceProfile().determine_abundances(1_000_000, 1000)
+        eng.load_genomes(g5)
+        eng.set_error_profile(S.MinimalShortErrorProfile(150, 150, 30))
+        total = eng.total_units(reads)
+        ub, ue = rank * total // world, (rank + 1) * total // world
+        eng.simulate(reads, SEED, unit_begin=ub, unit_end=ue)              # warm-up
+        barrier()
+        st = eng.simulate(reads, SEED, unit_begin=ub, unit_end=ue)
+        barrier()
+        t = torch.tensor([st["device_ms"], float(st["bases"])], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            ms_n, bases = float(tm[0]), float(ts[1])
+        else:
+            ms_n, bases = float(t[0]), float(t[1])
+        ms_1 = ms_n
+        if world > 1 and rank == 0:
+            ms_1 = eng.simulate(reads, SEED)["device_ms"]
+        barrier()
+        return {"workload": "C5: exact abundance, 1000 synthetic genomes (4.4 GB), 1 M reads per genome = 1 B reads (500 M pairs), minimal-short, fixed job sharded over the ranks",
+                "scaling": "strong", "n_gpus": world, "device_ms": ms_n, "value": bases / (ms_n / 1e3) / 1e9, "unit": UNIT,
+                "device_ms_one_gpu": ms_1, "efficiency_vs_one_gpu": ms_1 / (world * ms_n), "genome_bytes": int(g5.bases.nbytes)}
+    except Exception as e:                                                  # the headline must not die with the sub-record
+        return {"error": repr(e)}
+
+
+def fastq_to_file(S, gs, device):
+    """FASTQ to a file on tmpfs through the `simmr` command (FASTA files in, FASTQ out): 20 M reads of the C2 job, one
+    output file and eight part files; rates are FASTQ bytes over the command's own simulate-and-write phase and over
+    its whole wall time (CUDA context, FASTA ingest and genome upload included)."""
+    import shutil
+    import tempfile
+    exe = os.path.join(ROOT, "simmr_b200", "simmr")
+    root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    d = tempfile.mkdtemp(prefix="simmr_bench_", dir=root)
+    try:
+        lines = []
+        for g in range(gs.n_genomes):
+            p = os.path.join(d, f"g{g:04d}.fna")
+            with open(p, "wb") as f:
+                for c in range(int(gs.genome_contig[g]), int(gs.genome_contig[g + 1])):
+                    seq = gs.contig(c)
+                    n = len(seq) // 80 * 80
+                    body = np.empty((n // 80, 81), np.uint8)
+                    body[:, :80] = seq[:n].reshape(-1, 80)
+                    body[:, 80] = 10
+                    f.write(b">" + gs.contig_id(c) + b"\n")
+                    body.tofile(f)
+                    if n < len(seq):
+                        f.write(seq[n:].tobytes() + b"\n")
+            lines.append(f"{p}\t{gs.uuid(g)}\n")
+        open(os.path.join(d, "genomes.tsv"), "w").write("path\tuuid\n" + "".join(lines))
+        out = {"filesystem": "tmpfs (/dev/shm)" if root else "default temporary directory", "reads": 20_000_000}
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(device))
+        for name, extra in (("one_file", []), ("eight_parts", ["--output-parts", "8"])):
+            o = os.path.join(d, "reads.fq")
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "--genome-file", os.path.join(d, "genomes.tsv"), "--output", o, "--num-reads", "20000000", "--seed", "42",
+                                "--error-profile", "minimal-short"] + extra, capture_output=True, text=True, env=env)
+            wall = time.perf_counter() - t0
+            if r.returncode != 0:
+                out[name] = {"error": r.stderr[-300:]}
+                continue
+            files = [o] if not extra else [f"{o}.{k:03d}" for k in range(8)]
+            size = sum(os.path.getsize(p) for p in files)
+            phase = [ln for ln in r.stderr.splitlines() if "FASTQ bytes (" in ln]
+            secs = float(phase[0].split(") in ")[1].split(" s")[0]) if phase else None
+            nbases = int(phase[0].split(" records, ")[1].split(" bases")[0]) if phase else None
+            out[name] = {"fastq_bytes": size, "wall_s": round(wall, 3), "gb_per_s_wall": size / wall / 1e9,
+                         "write_phase_s": secs, "gb_per_s_write_phase": size / secs / 1e9 if secs else None,
+                         "gbases_per_s_write_phase": nbases / secs / 1e9 if secs else None}
+            for p in files:
+                os.remove(p)
+        return out
+    except Exception as e:
+        return {"error": repr(e)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 if __name__ == "__main__":

@@ -169,6 +169,13 @@ int  simmr_abundance_counts(const simmr_aprofile_desc *desc, uint64_t total_read
  * sink == NULL: device-resident run (FASTQ bytes stay in HBM staging). */
 int  simmr_simulate(simmr_ctx *ctx, const uint64_t *reads_per_genome, const simmr_run_opts *opts,
                     simmr_sink_fn sink, void *user);
+/* The same run for a consumer on the device: no copy to the host, every batch's FASTQ bytes are handed over where the
+ * format kernel left them in HBM (`device_data`, valid until the callback returns; the kernels of the batch have
+ * completed).  Non-zero return aborts.  The callback runs on the calling thread. */
+typedef int (*simmr_device_sink_fn)(void *user, const uint8_t *device_data, uint64_t len,
+                                    uint64_t first_unit, uint64_t n_units);
+int  simmr_simulate_device(simmr_ctx *ctx, const uint64_t *reads_per_genome, const simmr_run_opts *opts,
+                           simmr_device_sink_fn sink, void *user);
 /* same output path, draws supplied instead of Philox */
 int  simmr_replay(simmr_ctx *ctx, const simmr_draws *draws, const simmr_run_opts *opts,
                   simmr_sink_fn sink, void *user);

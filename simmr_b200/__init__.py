@@ -7,6 +7,6 @@ from .api import (DEFAULT_HEADER_FORMAT, SimmrError, ErrorProfile, PerfectShortE
                   MinimalShortErrorProfile, PerfectLongErrorProfile, MinimalLongErrorProfile,
                   CustomShortErrorProfile, CustomLongErrorProfile, AbundanceProfile, UniformAbundanceProfile,
                   ExactAbundanceProfile, CustomAbundanceProfile, GenomeSet, Draws, Engine, MultiEngine, parse_genome_file,
-                  write_metadata, write_to_fastq)
+                  write_metadata, write_to_fastq, copy_from_device)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -63,12 +63,13 @@ class DrawsC(C.Structure):
 
 
 SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, u8p, C.c_uint64, C.c_uint64, C.c_uint64)
+DEVICE_SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64)
 
 # every symbol include/simmr_b200.h declares
 EXPORTS = [
     "simmr_ctx_create", "simmr_ctx_destroy", "simmr_last_error", "simmr_device_info",
     "simmr_genomes_load", "simmr_error_profile_set", "simmr_eprofile_minimum_genome_size",
-    "simmr_eprofile_is_long_read", "simmr_abundance_counts", "simmr_simulate", "simmr_replay",
+    "simmr_eprofile_is_long_read", "simmr_abundance_counts", "simmr_simulate", "simmr_simulate_device", "simmr_replay",
     "simmr_total_units", "simmr_measure", "simmr_stats_get", "simmr_builder_create", "simmr_builder_destroy",
     "simmr_builder_add_fasta", "simmr_builder_add_fastas", "simmr_builder_filter", "simmr_builder_view", "simmr_builder_genome_size",
     "simmr_builder_error", "simmr_parse_genome_file", "simmr_write_metadata", "simmr_debug_phred_table",
@@ -101,6 +102,7 @@ def lib():
         L.simmr_eprofile_is_long_read.argtypes = [C.POINTER(EProfileDesc), C.POINTER(C.c_int)]
         L.simmr_abundance_counts.argtypes = [C.POINTER(AProfileDesc), C.c_uint64, C.c_uint32, u64p, u64p, f64p]
         L.simmr_simulate.argtypes = [C.c_void_p, u64p, C.POINTER(RunOpts), C.c_void_p, C.c_void_p]
+        L.simmr_simulate_device.argtypes = [C.c_void_p, u64p, C.POINTER(RunOpts), C.c_void_p, C.c_void_p]
         L.simmr_replay.argtypes = [C.c_void_p, C.POINTER(DrawsC), C.POINTER(RunOpts), C.c_void_p, C.c_void_p]
         L.simmr_measure.argtypes = [C.c_void_p, u64p, C.POINTER(RunOpts), u64p, u64p]
         L.simmr_total_units.argtypes = [C.c_void_p, u64p]

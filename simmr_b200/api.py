@@ -410,6 +410,27 @@ class Engine:
         self._run(N.lib().simmr_simulate, _p(r, N.u64p), o, sink)
         return self.stats()
 
+    def simulate_device(self, reads_per_genome, seed, device_sink, header_format=None, unit_begin=0, unit_end=None,
+                        read_id_base=0, batch_units=0):
+        """simmr_simulate_device: device_sink(device_pointer int, n_bytes, first_unit, n_units) sees every batch's FASTQ
+        bytes in HBM (no copy to the host); the pointer is valid until the callback returns."""
+        r = np.ascontiguousarray(reads_per_genome, np.uint64)
+        o = self._opts(seed, header_format, unit_begin, unit_end, read_id_base, batch_units)
+        err = []
+
+        def tramp(_user, ptr, length, first_unit, n_units):
+            try:
+                return int(device_sink(ptr or 0, length, first_unit, n_units) or 0)
+            except Exception as e:
+                err.append(e)
+                return 1
+        cb = N.DEVICE_SINK_FN(tramp)
+        rc = N.lib().simmr_simulate_device(self._ctx, _p(r, N.u64p), C.byref(o), C.cast(cb, C.c_void_p), None)
+        if err:
+            raise err[0]
+        self._check_rc(rc)
+        return self.stats()
+
     def measure(self, reads_per_genome, seed, header_format=None, unit_begin=0, unit_end=None, read_id_base=0):
         """simmr_measure: (FASTQ bytes, records) a unit range will produce; geometry kernel only."""
         r = np.ascontiguousarray(reads_per_genome, np.uint64)
@@ -520,8 +541,22 @@ class MultiEngine(Engine):
     def replay(self, *a, **k):
         raise NotImplementedError("replay is a single-device (test) path")
 
+    def simulate_device(self, *a, **k):
+        raise NotImplementedError("a device consumer binds to one device: open an Engine on it")
+
     def device_info(self):
         raise NotImplementedError("per-device information: open an Engine on the device")
+
+
+def copy_from_device(ptr, nbytes):
+    """The bytes at a device pointer as handed to a device sink (simmr_simulate_device) -> numpy array."""
+    from cuda.bindings import runtime as cudart
+    out = np.empty(nbytes, np.uint8)
+    if nbytes:
+        err, = cudart.cudaMemcpy(out.ctypes.data, ptr, nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+        if int(err) != 0:
+            raise SimmrError(N.E_CUDA, f"cudaMemcpy from the device sink's pointer failed ({err})")
+    return out
 
 
 def write_to_fastq(engine, reads_per_genome, output, seed=None, header_format=None, append=False, **kw):

@@ -444,7 +444,7 @@ struct Runner {
 /* Batches number j0, j0 + stride, ... of the unit range (batch j starts at unit ub + j * batch) — every batch when the
  * context runs alone, every n-th when n contexts share a run.  to_host: finished batches go to the pinned ring and into
  * `q` for the writer thread.  Otherwise (device-resident run, or measure) the bytes stay in HBM staging. */
-int produce(Runner &R, uint64_t j0, uint64_t stride, BatchQueue *q, simmr_stats &st) {
+int produce(Runner &R, uint64_t j0, uint64_t stride, BatchQueue *q, simmr_stats &st, simmr_device_sink_fn dev_sink = nullptr, void *dev_user = nullptr) {
     simmr_ctx *ctx = R.ctx;
     cudaEvent_t *ev = R.ev;
     const uint64_t nbatches = (R.ue - R.ub + R.batch - 1) / R.batch;
@@ -483,6 +483,12 @@ int produce(Runner &R, uint64_t j0, uint64_t stride, BatchQueue *q, simmr_stats 
             st.d2h_bytes += total + 8;
         } else {   /* per-batch format time: costs one sync per batch, only taken when it cannot hide copies */
             CU(cudaEventSynchronize(ev[EV_F1])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev[EV_F0], ev[EV_F1])); format_ms += ms;
+            if (dev_sink) {      /* a consumer on the device: the batch's bytes where the kernel left them */
+                uint64_t total = 0;
+                CU(cudaMemcpyAsync(&total, R.rp.offsets + n, 8, cudaMemcpyDeviceToHost, ctx->compute));
+                CU(cudaStreamSynchronize(ctx->compute));
+                if (dev_sink(dev_user, ctx->d_out[0].as<uint8_t>(), total, u, n)) return fail(ctx, SIMMR_E_SINK, "device sink callback failed");
+            }
         }
     }
     return R.finish(st, format_ms);
@@ -490,7 +496,8 @@ int produce(Runner &R, uint64_t j0, uint64_t stride, BatchQueue *q, simmr_stats 
 
 /* A run of one context: the caller's thread launches, a writer thread owned by the library hands the batches to the sink. */
 int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uint64_t ue, uint64_t seed,
-              const simmr_run_opts *opts, simmr_sink_fn sink, void *user, bool measure_only = false) {
+              const simmr_run_opts *opts, simmr_sink_fn sink, void *user, bool measure_only = false,
+              simmr_device_sink_fn dev_sink = nullptr) {
     /* debug switches, read once per run */
     ctx->dbg_guard = getenv("SIMMR_DEBUG_GUARD") != nullptr; ctx->dbg_sync = getenv("SIMMR_DEBUG_SYNC") != nullptr; ctx->dbg_serial = getenv("SIMMR_PREP_SERIAL") != nullptr;
     Runner R{ctx, replay, rd};
@@ -498,7 +505,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     if (rc) return rc;
     simmr_stats st{};
     st.units = ue - ub;
-    if (!sink) { rc = produce(R, 0, 1, nullptr, st); if (!rc) ctx->stats = st; return rc; }
+    if (!sink) { rc = produce(R, 0, 1, nullptr, st, dev_sink, user); if (!rc) ctx->stats = st; return rc; }
     BatchQueue q;
     bool sink_ok = true;
     std::thread writer([&] { sink_ok = write_batches({&q}, {ctx->device}, sink, user); });
@@ -683,7 +690,7 @@ uint64_t simmr_total_units(const simmr_ctx *ctx, const uint64_t *reads) {
     return unit_prefix(ctx, reads).back();
 }
 
-int simmr_simulate(simmr_ctx *ctx, const uint64_t *reads, const simmr_run_opts *opts, simmr_sink_fn sink, void *user) {
+static int simulate_common(simmr_ctx *ctx, const uint64_t *reads, const simmr_run_opts *opts, simmr_sink_fn sink, simmr_device_sink_fn dev_sink, void *user) {
     int rc = check_ready(ctx);
     if (rc) return rc;
     if (!reads) return fail(ctx, SIMMR_E_INVALID, "null reads_per_genome");
@@ -701,7 +708,13 @@ int simmr_simulate(simmr_ctx *ctx, const uint64_t *reads, const simmr_run_opts *
     ctx->stats = simmr_stats{};
     if (ub == ue) return SIMMR_OK;
     ReplayDev rd{};
-    return run_units(ctx, false, rd, ub, ue, seed, opts, sink, user);
+    return run_units(ctx, false, rd, ub, ue, seed, opts, sink, user, false, dev_sink);
+}
+int simmr_simulate(simmr_ctx *ctx, const uint64_t *reads, const simmr_run_opts *opts, simmr_sink_fn sink, void *user) {
+    return simulate_common(ctx, reads, opts, sink, nullptr, user);
+}
+int simmr_simulate_device(simmr_ctx *ctx, const uint64_t *reads, const simmr_run_opts *opts, simmr_device_sink_fn sink, void *user) {
+    return simulate_common(ctx, reads, opts, nullptr, sink, user);
 }
 
 int simmr_measure(simmr_ctx *ctx, const uint64_t *reads, const simmr_run_opts *opts, uint64_t *bytes, uint64_t *records) {

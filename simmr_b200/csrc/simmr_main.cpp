@@ -15,6 +15,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <deque>
@@ -269,8 +270,18 @@ int main(int argc, char **argv) {
     if (simmr_multi_create(devices.data(), args.gpus, &multi)) die(simmr_multi_last_error(nullptr));
     if (simmr_multi_genomes_load(multi, &gs) || simmr_multi_error_profile_set(multi, &ep)) die(simmr_multi_last_error(multi));
     writer.start();
+    const auto t_run = std::chrono::steady_clock::now();
     const int run_rc = simmr_multi_simulate(multi, reads.data(), &opts, &PartWriter::call, &writer);
     writer.finish();
+    {
+        simmr_stats rs{};
+        if (!run_rc && !simmr_multi_stats_get(multi, &rs)) {
+            const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run).count();
+            char line[200]; snprintf(line, sizeof line, "Wrote %llu FASTQ bytes (%llu records, %llu bases) in %.3f s (%.2f GB/s)", (unsigned long long)rs.bytes,
+                                     (unsigned long long)rs.records, (unsigned long long)rs.bases, secs, double(rs.bytes) / secs / 1e9);
+            info(line);
+        }
+    }
     if (writer.failed) die("Failed to write reads to the output file");
     if (run_rc) die(simmr_multi_last_error(multi));
     simmr_multi_destroy(multi);

@@ -500,3 +500,19 @@ def test_sink_runs_on_the_library_writer_thread(engine):
     seen = set()
     engine.simulate([4000, 4000], 1, batch_units=100, sink=lambda a, f, n: seen.add(threading.get_ident()) and 0)
     assert len(seen) == 1 and threading.get_ident() not in seen
+
+
+def test_device_sink_sees_the_bytes_in_hbm(engine):
+    """simmr_simulate_device: the device-resident run of bench.py's `value`, with a consumer that reads every batch where
+    the format kernel left it."""
+    gs = H.synth_genomes(3, (1, 3), (3000, 9000), seed=12)
+    prof = S.MinimalShortErrorProfile()
+    reads = [3000, 1000, 2000]
+    whole = check_native(engine, gs, prof, reads, 6)
+    got, firsts = [], []
+    st = engine.simulate_device(reads, 6, lambda ptr, n, first, units: (got.append(S.copy_from_device(ptr, n).tobytes()), firsts.append((first, units))) and 0,
+                                batch_units=700)
+    assert b"".join(got) == whole and st["bytes"] == len(whole)
+    assert [f for f, _ in firsts] == list(range(0, 3000, 700)) and sum(u for _, u in firsts) == 3000
+    with pytest.raises(S.SimmrError):
+        engine.simulate_device(reads, 6, lambda *a: 1)
