@@ -1113,7 +1113,7 @@ __host__ __device__ constexpr uint32_t qtab_bytes(int qm, uint32_t cb, uint32_t 
     return qm == QM_LANE ? (128u << cb) : qm == QM_POS ? ((npos << cb) * 4u + 127u) & ~127u : 0u;
 }
 
-template <bool REPLAY, int QM>
+template <bool REPLAY, int QM, bool SORTED>
 __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lanes(RunParams rp, ReplayDev rd) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1147,6 +1147,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
     __syncthreads();
 
     const uint32_t mate = lane & 1u, slot = lane >> 1;
+    if constexpr (SORTED) {
     const uint32_t nsegs = (rp.batch_units + SEG_UNITS - 1) / SEG_UNITS;
     /* a CTA takes whole segments; its warps share out the segment's tiles */
     for (uint32_t seg = blockIdx.x; seg < nsegs; seg += gridDim.x) {
@@ -1256,6 +1257,102 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
                 }
             }
         }
+    }
+    } else {
+    /* SIMMR_TILES=linear: tiles of WARP_UNITS consecutive units, one bulk copy per tile (the round-1 kernel, kept for comparison) */
+    const uint32_t ntiles = (rp.batch_units + WARP_UNITS - 1) / WARP_UNITS;
+    /* a tile's offsets (lane k: unit k, lane WARP_UNITS: the end) and descriptors are fetched one tile ahead, into registers */
+    auto fetch_tile = [&](uint32_t tile, uint64_t &off, UnitDesc &d) {
+        off = 0; d = UnitDesc{};
+        if (tile < ntiles) {
+            const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
+            if (lane <= tn) off = rp.offsets[t0 + lane];
+            if (slot < tn) d = load_unit(rp, t0 + slot);
+        }
+    };
+    for (uint32_t tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) {
+        const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
+        uint64_t off_tile; UnitDesc d_tile;
+        fetch_tile(tile, off_tile, d_tile);
+        for (uint32_t s0 = 0; s0 < tn;) {
+            /* sub-tile = longest run of units from s0 that fits the stage */
+            const uint32_t u0 = t0 + s0, left = tn - s0;
+            const uint64_t off = s0 == 0 ? off_tile : (lane <= left ? rp.offsets[u0 + lane] : 0);
+            const uint64_t tile_base = __shfl_sync(0xffffffffu, off, 0), next = __shfl_down_sync(0xffffffffu, off, 1);
+            const uint32_t pad = uint32_t(tile_base & 15);
+            const uint32_t nu = __popc(__ballot_sync(0xffffffffu, lane < left && next - tile_base + pad <= rp.stage_cap));
+            const uint32_t total = uint32_t(__shfl_sync(0xffffffffu, off, nu) - tile_base);
+            const uint32_t unit_off = pad + uint32_t(__shfl_sync(0xffffffffu, off, slot) - tile_base);
+            /* this lane's record */
+            const bool mine = slot < nu;
+            UnitDesc d = d_tile;
+            if (s0 != 0) { d = UnitDesc{}; if (mine) d = load_unit(rp, u0 + slot); }
+            const bool have = mine && (mate == 0 || (d.flags & 4u));
+            const uint32_t L = mate ? d.L1 : d.L0, H = mate ? d.H1 : d.H0;
+            const uint64_t a = mate ? d.a1 : d.a0;
+            const uint32_t rec = unit_off + (mate ? d.H0 + 2u * d.L0 + 5u : 0u);      /* stage offset of the record */
+            const bool odd = have && ((d.flags & 8u) || H < 2u || L < 4u);            /* rules out the word paths for the sub-tile */
+            const bool words_ok = !__any_sync(0xffffffffu, odd) && !REPLAY;
+            const bool hdr_fast = words_ok && rp.hdr_fast != 0;
+            const bool fast = have && words_ok && !(d.flags & (1u << mate));
+            const uint64_t unit = rp.batch_begin + u0 + slot;
+            /* the previous bulk copy must have finished reading the stage before it is rewritten */
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+
+            /* ---- phase 1: sequence and quality lines ---- */
+            {
+                const uint32_t body_s = stage_s + rec + H;
+                const uint32_t slots = ((L + 3u + 3u) >> 2);                          /* word slots of a line, at most */
+                const uint32_t T4 = __reduce_max_sync(0xffffffffu, fast ? slots : 0u);
+                if (T4) {
+                    Mwc1 qc{}, ec{};
+                    if (QM != QM_CONST) mwc1_seed(rp, qc, ec, 0u, 1u + mate, uint32_t(unit), uint32_t(unit >> 32));
+                    const uint32_t lut_s = base_s + (mate ? SM_LUT_RC : SM_LUT_FWD);
+                    if (QM == QM_LANE && rp.phred.cb == 7u) body_lane<QM, true>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4);
+                    else body_lane<QM, false>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4);
+                    if (QM != QM_CONST && rp.phred.has_sub) substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
+                }
+                if (have && !fast) {
+                    if (REPLAY) emit_body_replay<false>(rp, rd, stage + rec + H, mate, a, L, rd.base_off[unit] + (mate ? d.rl : 0), 0, 1);
+                    else emit_body_pieces<false>(rp, stage + rec + H, unit, mate, a, L, 0, 1);
+                }
+            }
+            __syncwarp();
+
+            /* ---- phase 2: header and the fixed bytes ---- */
+            if (have) {
+                uint64_t sp, ep; record_positions(d, mate, sp, ep);
+                const uint32_t id = rp.read_id_base + uint32_t(unit);
+                const uint32_t rec_s = stage_s + rec;
+                const ContigHdr ch = rp.chdr[2 * d.contig + mate];
+                if (hdr_fast) {      /* newline that ends the previous record, the tokens, newline */
+                    ByteStream b; bs_open(b, rec_s - 1u); bs_put(b, '\n', 1);
+                    header_tokens(b, rp, dec2_s, reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off), rp.hdr_kinds, rp.hdr_fields,
+                                  id, uint32_t(sp), uint32_t(ep));
+                    bs_put(b, '\n', 1); bs_close(b);
+                } else {
+                    emit_header(stage + rec, rp, ch, id, sp, ep);
+                    sts8(rec_s + H, '\n');
+                    if (rec > pad) sts8(rec_s - 1u, '\n');                    /* ends the previous record */
+                }
+                const uint32_t mid = rec_s + H + L + 1u;                      /* fastq.rs:61-69 */
+                sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n');
+            }
+            if (lane == 31 && total) sts8(stage_s + pad + total - 1u, '\n');
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            /* stage[pad, pad+total) -> out[tile_base, +total): 16-byte aligned middle by TMA, edges by byte stores */
+            const uint32_t head = min(total, (16 - pad) & 15), mid = (total - head) & ~15u, tail = total - head - mid;
+            if (lane == 0 && mid) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rp.out + tile_base + head), "r"(stage_s + pad + head), "r"(mid) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (lane >= 1 && lane < 1 + head) rp.out[tile_base + (lane - 1)] = stage[pad + (lane - 1)];
+            if (lane >= 16 && lane < 16 + tail) rp.out[tile_base + head + mid + (lane - 16)] = stage[pad + head + mid + (lane - 16)];
+            s0 += nu;
+        }
+    }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }

@@ -127,12 +127,21 @@ size_t lanes_smem(const ProfileModel &m, uint32_t warps, uint32_t stage_cap) {
 
 /* kernel instantiations: the word path is specialised per quality mode, replay is generic */
 using FormatKernel = void (*)(RunParams, ReplayDev);
+bool sorted_tiles() { const char *e = getenv("SIMMR_TILES"); return !(e && !strcmp(e, "linear")); }      /* experiment switch */
 FormatKernel lanes_kernel(bool replay, int qm) {
-    if (replay) return k_format_lanes<true, QM_CONST>;
+    if (!sorted_tiles()) {
+        if (replay) return k_format_lanes<true, QM_CONST, false>;
+        switch (qm) {
+        case QM_LANE: return k_format_lanes<false, QM_LANE, false>;
+        case QM_POS: return k_format_lanes<false, QM_POS, false>;
+        default: return k_format_lanes<false, QM_CONST, false>;
+        }
+    }
+    if (replay) return k_format_lanes<true, QM_CONST, true>;
     switch (qm) {
-    case QM_LANE: return k_format_lanes<false, QM_LANE>;
-    case QM_POS: return k_format_lanes<false, QM_POS>;
-    default: return k_format_lanes<false, QM_CONST>;
+    case QM_LANE: return k_format_lanes<false, QM_LANE, true>;
+    case QM_POS: return k_format_lanes<false, QM_POS, true>;
+    default: return k_format_lanes<false, QM_CONST, true>;
     }
 }
 FormatKernel direct_kernel(bool replay) { return replay ? k_format_direct<true> : k_format_direct<false>; }
@@ -404,7 +413,8 @@ struct Runner {
         if (guard) CU(cudaMemsetAsync(ctx->d_out[dslot].p, 0xA5, out_cap, ctx->compute));
         CU(cudaEventRecord(ev[EV_F0], ctx->compute));
         if (pl.tiles) {
-            const int grid = int(std::min<uint32_t>((n + SEG_UNITS - 1) / SEG_UNITS, uint32_t(pl.grid)));      /* a CTA takes whole segments */
+            const uint32_t wpc = pl.threads / 32, work = sorted_tiles() ? (n + SEG_UNITS - 1) / SEG_UNITS : ((n + WARP_UNITS - 1) / WARP_UNITS + wpc - 1) / wpc;
+            const int grid = int(std::min<uint32_t>(work, uint32_t(pl.grid)));      /* a CTA takes whole segments */
             lanes_kernel(replay, quality_mode(ctx->model))<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
         } else if (pl.lanes) {
             CU(cudaMemsetAsync(rp.counters + 4, 0, 8, ctx->compute));       /* the kernel's piece counter */
