@@ -8,6 +8,10 @@
 #include "device_code.cuh"
 #include "host_model.hpp"
 
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -47,13 +51,55 @@ struct DevMem {    /* owning device allocation */
     }
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
+/* NUMA placement, best effort (a container may forbid either call; then nothing changes): pinned buffers are allocated
+ * with the calling thread's memory policy preferring the GPU's node, and the threads the library owns run on that node's
+ * cores — eight GPUs copying 50 GB/s each into one socket's memory was the end-to-end limit of round 1. */
+int numa_node_of_device(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return -1;
+    for (char *c = bus; *c; ++c) if (*c >= 'A' && *c <= 'F') *c = char(*c - 'A' + 'a');
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+struct PreferNode {          /* scope: memory of this thread comes from `node` if possible (MPOL_PREFERRED = 1) */
+    bool on = false;
+    explicit PreferNode(int node) {
+        if (node < 0 || node >= 1024) return;
+        unsigned long mask[16] = {0};
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        on = syscall(SYS_set_mempolicy, 1, mask, 1024ul + 1) == 0;
+    }
+    ~PreferNode() { if (on) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul); }
+};
+void run_on_node(int node) {  /* the calling (library-owned) thread onto the cores of `node` */
+    if (node < 0) return;
+    FILE *f = fopen(("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist").c_str(), "r");
+    if (!f) return;
+    cpu_set_t set; CPU_ZERO(&set);
+    int a, b, any = 0;
+    while (fscanf(f, "%d", &a) == 1) {
+        b = a;
+        int c = fgetc(f);
+        if (c == '-') { if (fscanf(f, "%d", &b) != 1) break; c = fgetc(f); }
+        for (int i = a; i <= b && i < CPU_SETSIZE; ++i) { CPU_SET(i, &set); any = 1; }
+        if (c != ',') break;
+    }
+    fclose(f);
+    if (any) sched_setaffinity(0, sizeof set, &set);
+}
 struct PinnedMem {
     void *p = nullptr; size_t bytes = 0;
     ~PinnedMem() { if (p) cudaFreeHost(p); }
-    cudaError_t reserve(size_t n) {
+    cudaError_t reserve(size_t n, int node = -1) {
         if (n <= bytes) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; bytes = 0;
+        PreferNode prefer(node);
         cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocDefault);
         if (e == cudaSuccess) bytes = n;
         return e;
@@ -62,7 +108,7 @@ struct PinnedMem {
 }  // namespace
 
 struct simmr_ctx {
-    int device = 0;
+    int device = 0, numa_node = -1;
     cudaDeviceProp prop{};
     cudaStream_t compute = nullptr, copy = nullptr, prep = nullptr;   /* format kernels; D2H of finished batches; geometry + offsets of the next batch */
     std::string err;
@@ -369,8 +415,8 @@ struct Runner {
         guard = ctx->dbg_guard; dbg_sync = ctx->dbg_sync;
         const int nbuf = measure_only ? 0 : to_host ? 2 : 1;
         for (int b = 0; b < nbuf; ++b) CU(ctx->d_out[b].reserve(out_cap));
-        if (to_host) for (int b = 0; b < RING; ++b) CU(ctx->h_out[b].reserve(out_cap));
-        CU(ctx->h_total.reserve(2 * sizeof(uint64_t)));
+        if (to_host) for (int b = 0; b < RING; ++b) CU(ctx->h_out[b].reserve(out_cap, ctx->numa_node));
+        CU(ctx->h_total.reserve(2 * sizeof(uint64_t), ctx->numa_node));
         fill_params(ctx, rp, seed, opts ? opts->read_id_base : 0, pl);
         /* error injection reads and writes one scratch set per context: its batches are prepared on the compute stream, one
          * at a time.  dbg_serial: everything on one stream (kernel timings without co-runners). */
@@ -518,7 +564,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     if (!sink) { rc = produce(R, 0, 1, nullptr, st, dev_sink, user); if (!rc) ctx->stats = st; return rc; }
     BatchQueue q;
     bool sink_ok = true;
-    std::thread writer([&] { sink_ok = write_batches({&q}, {ctx->device}, sink, user); });
+    std::thread writer([&] { run_on_node(ctx->numa_node); sink_ok = write_batches({&q}, {ctx->device}, sink, user); });
     rc = produce(R, 0, 1, &q, st);
     q.close();
     writer.join();
@@ -560,7 +606,7 @@ int mfail(simmr_multi *m, int code, const std::string &msg) { last_error_slot() 
 template <class F> int on_every_device(simmr_multi *m, F fn) {
     std::vector<int> rc(m->ctx.size(), SIMMR_OK);
     std::vector<std::thread> th;
-    for (size_t g = 0; g < m->ctx.size(); ++g) th.emplace_back([&, g] { cudaSetDevice(m->devices[g]); rc[g] = fn(int(g)); });
+    for (size_t g = 0; g < m->ctx.size(); ++g) th.emplace_back([&, g] { cudaSetDevice(m->devices[g]); run_on_node(m->ctx[g]->numa_node); rc[g] = fn(int(g)); });
     for (auto &t : th) t.join();
     for (size_t g = 0; g < rc.size(); ++g) if (rc[g]) return mfail(m, rc[g], "device " + std::to_string(m->devices[g]) + ": " + m->ctx[g]->err);
     return SIMMR_OK;
@@ -593,6 +639,7 @@ int simmr_ctx_create(int device, simmr_ctx **out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaStreamCreateWithFlags(&ctx->prep, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    ctx->numa_node = numa_node_of_device(device);
     for (int i = 0; i < EV_COUNT; ++i) {      /* the pipeline's events live as long as the context */
         const bool timed = i < EV_TOTAL;
         if ((e = cudaEventCreateWithFlags(&ctx->ev[i], timed ? cudaEventDefault : cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
