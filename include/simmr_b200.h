@@ -110,7 +110,7 @@ typedef int (*simmr_sink_fn)(void *user, const uint8_t *data, uint64_t len,
  * waits while all of them are retained, and every retained chunk must be released before the run's entry point returns
  * (the entry point waits for that). */
 #define SIMMR_SINK_RETAINED 2
-#define SIMMR_RING_BUFFERS  4
+#define SIMMR_RING_BUFFERS  8
 void simmr_chunk_release(const uint8_t *data);
 
 typedef struct {

@@ -47,7 +47,9 @@ struct RunParams {
     const uint8_t *bases; const uint64_t *contig_off, *contig_size; const uint32_t *genome_contig;
     const uint32_t *impure;        /* 1 bit per 32-byte block of `bases`: holds a byte other than A,C,G,T */
     const uint32_t *packed;        /* 2 bits per base (A,C,G,T = 0..3), 16 bases per word, same indexing as `bases` */
-    const ContigHdr *chdr; const HdrTok *toks; const uint8_t *pool;
+    /* compiled header templates: block 2 * contig + mate of hdr_stride bytes = ContigHdr, its tokens, their literals (one or
+     * two cache lines a record's lane can prefetch from the contig number alone); toks and pool address the same buffer */
+    const uint8_t *hdr; uint32_t hdr_stride, hdr_pad_; const HdrTok *toks; const uint8_t *pool;
     uint32_t n_genomes, n_contigs;
     /* unit space */
     const uint64_t *unit_start;    /* [n_genomes+1] first global unit of each genome */
@@ -61,8 +63,8 @@ struct RunParams {
     uint32_t *sizes; uint64_t *offsets, *block_sums; uint8_t *out;
     struct UnitRec *desc;          /* per-unit geometry written by k_unit_sizes, read by the format kernels (32 bytes) */
     struct UnitExt *desc_ext;      /* what does not fit a UnitRec (clamped windows, positions above 2^32): written and read for flagged units only */
-    /* k_format_lanes takes its tiles from segments of SEG_UNITS units whose units k_segment_sort ordered by size */
-    uint16_t *seg_perm, *seg_tiles; uint32_t *seg_ntiles;
+    /* k_kmer_errors takes the reads of every segment of SEG_UNITS units in the order of their sizes (k_segment_sort) */
+    uint16_t *seg_perm;
     unsigned long long *counters;  /* [0] clamped [1] algorithmic bytes [2] bases [3] records */
     /* per-warp stage of k_format_lanes */
     uint32_t stage_cap;            /* bytes of a warp's stage in k_format_lanes */
@@ -102,6 +104,11 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile(
 __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 /* loads from the read-only tables in shared memory: not volatile, the compiler may move them */
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+
+__device__ __forceinline__ const ContigHdr &hdr_at(const RunParams &rp, uint32_t contig, uint32_t mate) {
+    return *reinterpret_cast<const ContigHdr *>(rp.hdr + size_t(2u * contig + mate) * rp.hdr_stride);
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 /* ---------------------------------------------------------------------- */
 /* Philox4x32-10                                                            */
@@ -638,7 +645,7 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_sizes(RunParams rp, Repl
 #pragma unroll
         for (uint32_t r = 0; r < 2; ++r) {                       /* unrolled: the arrays stay in registers */
             if (r >= g.nrec) break;
-            H[r] = header_len(rp.chdr[2 * g.contig + r], g.id, g.sp[r], g.ep[r]);
+            H[r] = header_len(hdr_at(rp, g.contig, r), g.id, g.sp[r], g.ep[r]);
             bytes += H[r] + 2ull * g.L[r] + 5;
             alg += H[r] + 3ull * g.L[r] + 5;                     /* BASELINE.md §3 */
             bases += g.L[r];
@@ -724,14 +731,12 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_unit_offsets(RunParams rp) {
 }
 
 
-/* Short reads: byte offsets of a segment's SEG_UNITS units (what k_unit_offsets does) and the order in which
- * k_format_lanes takes them.  A warp of the format kernel runs for its longest record, so the units of a tile should be
- * equally long: the segment's units are counting-sorted by their FASTQ bytes (256 bins over the segment's range) and cut
- * into tiles of consecutive sorted units — at most WARP_UNITS of them, and no more than fit a warp's stage, where every
- * unit sits at its global offset modulo 16 (slot = bytes rounded up to the 16-byte grid around it).  Every unit is
- * stored at its own offset, so the order changes nothing in the output.
- *   seg_perm[seg * SEG_UNITS + r]   unit (index inside the segment) at sorted rank r
- *   seg_tiles[seg * SEG_UNITS + k]  rank at which tile k starts; seg_ntiles[seg] tiles */
+/* Byte offsets of a segment's SEG_UNITS units (what k_unit_offsets does) and the segment's units in the order of their
+ * FASTQ bytes (a counting sort over 256 bins of the segment's range).  k_kmer_errors gives a read to a thread and takes
+ * the reads in that order, so that the 32 reads of a warp are about equally long (gamma lengths vary by an order of
+ * magnitude).  [A size-ordered variant of the short-read kernel used the same order; it lost more on storing every unit
+ * separately than it gained from equal turns, DESIGN.md §6.1.]
+ *   seg_perm[seg * SEG_UNITS + r]   unit (index inside the segment) at sorted rank r */
 constexpr uint32_t SEG_UNITS = 1024, SEG_THREADS = 256, SEG_PER = SEG_UNITS / SEG_THREADS;
 constexpr uint32_t WARP_UNITS = 16;
 static_assert(SEG_PER * SIZES_THREADS == SEG_UNITS && SEG_THREADS == SIZES_THREADS, "a segment is SEG_PER blocks of k_unit_sizes");
@@ -750,24 +755,19 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t *warp_t
     return before + x - v;
 }
 __global__ void __launch_bounds__(SEG_THREADS) k_segment_sort(RunParams rp) {
-    __shared__ uint32_t warp_tot[SEG_THREADS / 32], hist[256], slot_s[SEG_UNITS], pre_s[SEG_UNITS + 1], red[2][SEG_THREADS / 32];
-    __shared__ uint16_t perm_s[SEG_UNITS], next_s[SEG_UNITS], tile_s[SEG_UNITS];
-    __shared__ uint32_t ntile_s;
+    __shared__ uint32_t warp_tot[SEG_THREADS / 32], hist[256], red[2][SEG_THREADS / 32];
     const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const uint32_t seg0 = blockIdx.x * SEG_UNITS, n = min(SEG_UNITS, rp.batch_units - seg0);
     /* 1. sizes -> offsets, block by block of k_unit_sizes (thread t takes unit j * 256 + t of the segment) */
-    uint32_t sz[SEG_PER], lead[SEG_PER], mn = 0xffffffffu, mx = 0;
+    uint32_t sz[SEG_PER], mn = 0xffffffffu, mx = 0;
 #pragma unroll
     for (uint32_t j = 0; j < SEG_PER; ++j) {
         const uint32_t u = j * SEG_THREADS + t;
         sz[j] = u < n ? rp.sizes[seg0 + u] : 0u;
         uint32_t tot;
         const uint32_t before = block_scan_excl(sz[j], warp_tot, tot);
-        lead[j] = 0;
         if (u < n) {
-            const uint64_t off = rp.block_sums[blockIdx.x * SEG_PER + j] + before;
-            rp.offsets[seg0 + u] = off;
-            lead[j] = uint32_t(off) & 15u;
+            rp.offsets[seg0 + u] = rp.block_sums[blockIdx.x * SEG_PER + j] + before;
             mn = min(mn, sz[j]); mx = max(mx, sz[j]);
         }
     }
@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_segment_sort(RunParams rp) {
     uint32_t bin[SEG_PER];
 #pragma unroll
     for (uint32_t j = 0; j < SEG_PER; ++j) if (j * SEG_THREADS + t < n) {
-        bin[j] = (rp.flags & 0x400u) ? (j * SEG_THREADS + t) >> 2 : (sz[j] - mn) >> sh;      /* SIMMR_DBG=4: the units' own order (experiment) */
+        bin[j] = (sz[j] - mn) >> sh;
         atomicAdd(&hist[bin[j]], 1u);
     }
     __syncthreads();
@@ -791,44 +791,9 @@ __global__ void __launch_bounds__(SEG_THREADS) k_segment_sort(RunParams rp) {
     __syncthreads();
     hist[t] = start;
     __syncthreads();
-    /* 3. rank of every unit (any order inside a bin), its stage slot at that rank */
+    /* 3. rank of every unit (any order inside a bin) */
 #pragma unroll
-    for (uint32_t j = 0; j < SEG_PER; ++j) if (j * SEG_THREADS + t < n) {
-        const uint32_t r = atomicAdd(&hist[bin[j]], 1u);
-        perm_s[r] = uint16_t(j * SEG_THREADS + t);
-        slot_s[r] = (lead[j] + sz[j] + 15u) & ~15u;
-    }
-    __syncthreads();
-    /* 4. prefix of the slots in sorted order (thread t: ranks 4t .. 4t+3) */
-    uint32_t sl[SEG_PER], sum = 0;
-#pragma unroll
-    for (uint32_t j = 0; j < SEG_PER; ++j) { const uint32_t r = SEG_PER * t + j; sl[j] = r < n ? slot_s[r] : 0u; sum += sl[j]; }
-    uint32_t run = block_scan_excl(sum, warp_tot, tot);
-#pragma unroll
-    for (uint32_t j = 0; j < SEG_PER; ++j) { pre_s[SEG_PER * t + j] = run; run += sl[j]; }
-    if (t == SEG_THREADS - 1) pre_s[SEG_UNITS] = run;
-    __syncthreads();
-    /* 5. where the tile that starts at rank r ends: at most WARP_UNITS units, slots within the stage (a single unit always fits) */
-#pragma unroll
-    for (uint32_t j = 0; j < SEG_PER; ++j) {
-        const uint32_t r = SEG_PER * t + j;
-        if (r < n) {
-            uint32_t e = r + 1;
-            const uint32_t base = pre_s[r], last = min(n, r + WARP_UNITS);
-            while (e < last && pre_s[e + 1] - base <= rp.stage_cap) ++e;
-            next_s[r] = uint16_t(e);
-        }
-    }
-    __syncthreads();
-    if (t == 0) {
-        uint32_t k = 0;
-        for (uint32_t r = 0; r < n; r = next_s[r]) tile_s[k++] = uint16_t(r);
-        ntile_s = k;
-        rp.seg_ntiles[blockIdx.x] = k;
-    }
-    __syncthreads();
-    for (uint32_t r = t; r < n; r += SEG_THREADS) rp.seg_perm[seg0 + r] = perm_s[r];
-    for (uint32_t k = t; k < ntile_s; k += SEG_THREADS) rp.seg_tiles[seg0 + k] = tile_s[k];
+    for (uint32_t j = 0; j < SEG_PER; ++j) if (j * SEG_THREADS + t < n) rp.seg_perm[seg0 + atomicAdd(&hist[bin[j]], 1u)] = uint16_t(j * SEG_THREADS + t);
 }
 
 /* ---------------------------------------------------------------------- */
@@ -1092,11 +1057,10 @@ __device__ __forceinline__ void substitutions_lane(const RunParams &rp, uint32_t
     }
 }
 
-/* Persistent warps, one lane per record.  A CTA takes whole segments of SEG_UNITS units; a warp takes one of the segment's
- * tiles at a time — up to WARP_UNITS units (32 records) of nearly the same size (k_segment_sort), so its lanes run the same
- * number of turns — composes their FASTQ bytes in its private stage in shared memory and sends every unit to its own place
- * in the output with a bulk async copy (TMA); only the tables are shared by the CTA, so there is no CTA barrier in the
- * loop.  Lane 2k + m holds mate m of the tile's k-th unit.
+/* Persistent warps, one lane per record.  A warp owns WARP_UNITS consecutive units (32 records) at a time: it composes
+ * their FASTQ bytes in its private stage in shared memory and sends them off with one bulk async copy (TMA); only the
+ * tables are shared by the CTA, so there is no CTA barrier in the loop.  A group of units whose bytes exceed the stage is
+ * cut into sub-tiles.  Lane 2k + m holds mate m of unit k.
  *   phase 1  sequence and quality lines (body_lane, then substitutions_lane); byte stores for windows holding anything
  *            but A,C,G,T and for replay
  *   phase 2  headers and the fixed newline / '+' bytes, by the same lane
@@ -1113,7 +1077,7 @@ __host__ __device__ constexpr uint32_t qtab_bytes(int qm, uint32_t cb, uint32_t 
     return qm == QM_LANE ? (128u << cb) : qm == QM_POS ? ((npos << cb) * 4u + 127u) & ~127u : 0u;
 }
 
-template <bool REPLAY, int QM, bool SORTED>
+template <bool REPLAY, int QM>
 __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lanes(RunParams rp, ReplayDev rd) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1147,119 +1111,6 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
     __syncthreads();
 
     const uint32_t mate = lane & 1u, slot = lane >> 1;
-    if constexpr (SORTED) {
-    const uint32_t nsegs = (rp.batch_units + SEG_UNITS - 1) / SEG_UNITS;
-    /* a CTA takes whole segments; its warps share out the segment's tiles */
-    for (uint32_t seg = blockIdx.x; seg < nsegs; seg += gridDim.x) {
-        const uint32_t seg0 = seg * SEG_UNITS, nseg = min(SEG_UNITS, rp.batch_units - seg0);
-        const uint32_t nt = __ldg(rp.seg_ntiles + seg);
-        for (uint32_t tile = warp; tile < nt; tile += nwarps) {
-            const uint32_t ts = __ldg(rp.seg_tiles + seg0 + tile);
-            const uint32_t te = tile + 1u < nt ? uint32_t(__ldg(rp.seg_tiles + seg0 + tile + 1u)) : nseg;
-            const uint32_t nu = te - ts;                                               /* 1 .. WARP_UNITS units, slots within the stage */
-            /* this lane's unit and record */
-            const bool mine = slot < nu;
-            uint32_t ui = 0; uint64_t goff = 0;
-            UnitDesc d{};
-            if (mine) { ui = seg0 + __ldg(rp.seg_perm + seg0 + ts + slot); d = load_unit(rp, ui); goff = __ldg(rp.offsets + ui); }
-            const bool two = (d.flags & 4u) != 0;
-            const uint32_t rec0 = d.H0 + 2u * d.L0 + 5u;                               /* bytes of the unit's first record */
-            const uint32_t usz = mine ? rec0 + (two ? d.H1 + 2u * d.L1 + 5u : 0u) : 0u;
-            const uint32_t lead = uint32_t(goff) & 15u;                                /* the unit sits in the stage at its global offset modulo 16 */
-            const uint32_t slotb = mine ? (lead + usz + 15u) & ~15u : 0u;
-            uint32_t so = mate == 0 ? slotb : 0u;                                      /* -> start of the unit's slot: slots of the units before it */
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, so, o); if (lane >= uint32_t(o)) so += y; }
-            so -= slotb;
-            const bool have = mine && (mate == 0 || two);
-            const uint32_t L = mate ? d.L1 : d.L0, H = mate ? d.H1 : d.H0;
-            const uint64_t a = mate ? d.a1 : d.a0;
-            const uint32_t rec = so + lead + (mate ? rec0 : 0u);                       /* stage offset of the record */
-            const bool odd = have && ((d.flags & 8u) || H < 2u || L < 4u);             /* rules out the word paths for the tile */
-            const bool words_ok = !__any_sync(0xffffffffu, odd) && !REPLAY;
-            const bool hdr_fast = words_ok && rp.hdr_fast != 0;
-            const bool fast = have && words_ok && !(d.flags & (1u << mate));
-            const uint64_t unit = rp.batch_begin + ui;
-            /* the bulk copies this lane issued for the previous tile must have finished reading the stage */
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
-
-            /* ---- phase 1: sequence and quality lines ---- */
-            {
-                const uint32_t body_s = stage_s + rec + H;
-                const uint32_t slots = ((L + 3u + 3u) >> 2);                          /* word slots of a line, at most */
-                const uint32_t T4 = __reduce_max_sync(0xffffffffu, fast ? slots : 0u);
-                if (T4) {
-                    Mwc1 qc{}, ec{};
-                    if (QM != QM_CONST) mwc1_seed(rp, qc, ec, 0u, 1u + mate, uint32_t(unit), uint32_t(unit >> 32));
-                    const uint32_t lut_s = base_s + (mate ? SM_LUT_RC : SM_LUT_FWD);
-                    if (QM == QM_LANE && rp.phred.cb == 7u) body_lane<QM, true>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4);
-                    else body_lane<QM, false>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4);
-                    if (QM != QM_CONST && rp.phred.has_sub) substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
-                }
-                if (have && !fast) {
-                    if (REPLAY) emit_body_replay<false>(rp, rd, stage + rec + H, mate, a, L, rd.base_off[unit] + (mate ? d.rl : 0), 0, 1);
-                    else emit_body_pieces<false>(rp, stage + rec + H, unit, mate, a, L, 0, 1);
-                }
-            }
-            __syncwarp();
-
-            /* ---- phase 2: header and the fixed bytes ---- */
-            if (have) {
-                uint64_t sp, ep; record_positions(d, mate, sp, ep);
-                const uint32_t id = rp.read_id_base + uint32_t(unit);
-                const uint32_t rec_s = stage_s + rec;
-                const ContigHdr ch = rp.chdr[2 * d.contig + mate];
-                if (hdr_fast) {      /* the tokens, newline.  Mate 2's stream starts on the newline that ends mate 1's record: the word it
-                                      * opens holds mate 1's last quality characters (phase 1).  A unit's first record must not open a
-                                      * word of the slot before it, whose last bytes another lane is writing now. */
-                    ByteStream b;
-                    if (mate) { bs_open(b, rec_s - 1u); bs_put(b, '\n', 1); } else bs_open(b, rec_s);
-                    header_tokens(b, rp, dec2_s, reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off), rp.hdr_kinds, rp.hdr_fields,
-                                  id, uint32_t(sp), uint32_t(ep));
-                    bs_put(b, '\n', 1); bs_close(b);
-                } else {
-                    emit_header(stage + rec, rp, ch, id, sp, ep);
-                    sts8(rec_s + H, '\n');
-                }
-                const uint32_t mid = rec_s + H + L + 1u;                      /* fastq.rs:61-69 */
-                sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n'); sts8(mid + L + 3u, '\n');
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            /* ---- the unit's image, stage[so + lead, + usz), to out[goff, + usz): the 16-byte aligned middle by a bulk copy
-             * issued by the unit's first lane, the bytes before it by that lane, the bytes after it by its second lane ---- */
-            if (mine && !(rp.flags & 0x100u)) {                                    /* SIMMR_DBG=1: nothing leaves the stage (experiment) */
-                const uint32_t img_s = stage_s + so + lead, head = (16u - lead) & 15u;
-                uint8_t *g = rp.out + goff;
-                if (usz < head + 16u) {                                        /* no aligned line inside: bytes */
-                    if (mate == 0) for (uint32_t k = 0; k < usz; ++k) g[k] = stage[so + lead + k];
-                } else {
-                    const uint32_t midb = (usz - head) & ~15u, tail = usz - head - midb;
-                    const bool edges = !(rp.flags & 0x200u);                   /* SIMMR_DBG=2: no edge bytes (experiment) */
-                    if (mate == 0) {
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g + head), "r"(img_s + head), "r"(midb) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        if (edges) {
-                            uint32_t o = 0;                                    /* head ends on a 16-byte line: 1, 2, 4, 8 bytes by its bits */
-                            if (head & 1u) { g[o] = uint8_t(lds8(img_s + o)); o += 1u; }
-                            if (head & 2u) { *reinterpret_cast<uint16_t *>(g + o) = uint16_t(lds16m(img_s + o)); o += 2u; }
-                            if (head & 4u) { *reinterpret_cast<uint32_t *>(g + o) = lds32m(img_s + o); o += 4u; }
-                            if (head & 8u) { *reinterpret_cast<uint2 *>(g + o) = lds64m(img_s + o); }
-                        }
-                    } else if (edges) {
-                        uint32_t o = head + midb;                              /* tail starts on a 16-byte line: 8, 4, 2, 1 */
-                        if (tail & 8u) { *reinterpret_cast<uint2 *>(g + o) = lds64m(img_s + o); o += 8u; }
-                        if (tail & 4u) { *reinterpret_cast<uint32_t *>(g + o) = lds32m(img_s + o); o += 4u; }
-                        if (tail & 2u) { *reinterpret_cast<uint16_t *>(g + o) = uint16_t(lds16m(img_s + o)); o += 2u; }
-                        if (tail & 1u) { g[o] = uint8_t(lds8(img_s + o)); }
-                    }
-                }
-            }
-        }
-    }
-    } else {
-    /* SIMMR_TILES=linear: tiles of WARP_UNITS consecutive units, one bulk copy per tile (the round-1 kernel, kept for comparison) */
     const uint32_t ntiles = (rp.batch_units + WARP_UNITS - 1) / WARP_UNITS;
     /* a tile's offsets (lane k: unit k, lane WARP_UNITS: the end) and descriptors are fetched one tile ahead, into registers */
     auto fetch_tile = [&](uint32_t tile, uint64_t &off, UnitDesc &d) {
@@ -1274,6 +1125,16 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
         const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
         uint64_t off_tile; UnitDesc d_tile;
         fetch_tile(tile, off_tile, d_tile);
+        const uint32_t tile_next = tile + gridDim.x * nwarps;
+        if ((rp.flags & 0x800u) && tile_next < ntiles) {        /* the next tile's offsets (2 lines) and descriptors (4 lines) towards L2 */
+            const uint32_t t1 = tile_next * WARP_UNITS;
+            if (lane < 2) prefetch_l2(rp.offsets + t1 + 16u * lane);
+            else if (lane < 6) prefetch_l2(reinterpret_cast<const uint8_t *>(rp.desc + t1) + 128u * (lane - 2u));
+        }
+        if ((rp.flags & 0x2000u) && slot < tn) {                /* this record's header template */
+            const uint8_t *blk = rp.hdr + size_t(2u * d_tile.contig + mate) * rp.hdr_stride;
+            prefetch_l2(blk); if (rp.hdr_stride > 128u) prefetch_l2(blk + 128);
+        }
         for (uint32_t s0 = 0; s0 < tn;) {
             /* sub-tile = longest run of units from s0 that fits the stage */
             const uint32_t u0 = t0 + s0, left = tn - s0;
@@ -1325,7 +1186,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
                 uint64_t sp, ep; record_positions(d, mate, sp, ep);
                 const uint32_t id = rp.read_id_base + uint32_t(unit);
                 const uint32_t rec_s = stage_s + rec;
-                const ContigHdr ch = rp.chdr[2 * d.contig + mate];
+                const ContigHdr ch = hdr_at(rp, d.contig, mate);
                 if (hdr_fast) {      /* newline that ends the previous record, the tokens, newline */
                     ByteStream b; bs_open(b, rec_s - 1u); bs_put(b, '\n', 1);
                     header_tokens(b, rp, dec2_s, reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off), rp.hdr_kinds, rp.hdr_fields,
@@ -1351,10 +1212,18 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
             if (lane >= 1 && lane < 1 + head) rp.out[tile_base + (lane - 1)] = stage[pad + (lane - 1)];
             if (lane >= 16 && lane < 16 + tail) rp.out[tile_base + head + mid + (lane - 16)] = stage[pad + head + mid + (lane - 16)];
             s0 += nu;
+            if ((rp.flags & 0x1000u) && s0 >= tn && tile_next < ntiles) {     /* the next tile's genome windows towards L2 (its descriptors were prefetched at this tile's start) */
+                const uint32_t t1 = tile_next * WARP_UNITS;
+                if (t1 + slot < rp.batch_units) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rp.desc + t1 + slot));
+                    const uint64_t a1 = pair64(v.x, v.y) + (mate ? uint64_t(v.w) - v.z : 0u);
+                    const uint32_t *w = rp.packed + (a1 >> 4);
+                    prefetch_l2(w); prefetch_l2(w + 8);
+                }
+            }
         }
     }
-    }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 
@@ -1372,7 +1241,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, 
             const uint32_t H = r ? d.H1 : d.H0, L = r ? d.L1 : d.L0;
             if (threadIdx.x == 0) {
                 uint64_t sp, ep; record_positions(d, r, sp, ep);
-                emit_header(dst, rp, rp.chdr[2 * d.contig + r], rp.read_id_base + uint32_t(u), sp, ep);
+                emit_header(dst, rp, hdr_at(rp, d.contig, r), rp.read_id_base + uint32_t(u), sp, ep);
             }
             if (REPLAY) emit_body_replay<true>(rp, rd, dst + H, r, r ? d.a1 : d.a0, L, slot0 + (r ? d.rl : 0), threadIdx.x, DIRECT_THREADS);
             else if (rp.err.on) emit_body_pieces<true>(rp, dst + H, u, r, d.a0, L, threadIdx.x, DIRECT_THREADS, d.L1, !(d.flags & 1u));   /* edited long read */
@@ -1533,7 +1402,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         uint8_t *rec = rp.out + rp.offsets[i];
         const bool bytes_path = (d.flags & 9u) || L < 4u;
         if (lane == 0) {                                  /* header and the five fixed bytes (fastq.rs:34-69) */
-            emit_header(rec, rp, rp.chdr[2 * d.contig], rp.read_id_base + uint32_t(unit), d.p0, d.p1);
+            emit_header(rec, rp, hdr_at(rp, d.contig, 0), rp.read_id_base + uint32_t(unit), d.p0, d.p1);
             rec[H] = '\n'; rec[H + Ls + 1] = '\n'; rec[H + Ls + 2] = '+'; rec[H + Ls + 3] = '\n'; rec[H + Ls + L + 4] = '\n';
         }
         if (bytes_path) {

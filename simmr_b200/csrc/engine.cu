@@ -123,7 +123,8 @@ struct simmr_ctx {
     std::string header_fmt; bool have_headers = false;
     HeaderPlan plan;
     uint32_t hdr_fast = 0, hdr_fields = 0, hdr_kinds = 0;     /* decimal fields when every contig has the same ones */
-    DevMem d_chdr, d_toks, d_pool;
+    DevMem d_hdr;                                  /* header templates, one fixed-stride block per (contig, mate) */
+    uint32_t hdr_stride = 0;
     /* profile */
     bool have_profile = false;
     ProfileModel model;
@@ -134,8 +135,8 @@ struct simmr_ctx {
     /* run scratch */
     DevMem d_unit_start, d_counters, d_out[2];
     DevMem d_sizes[2], d_offsets[2], d_block_sums[2], d_desc[2], d_desc_ext[2];   /* per-batch scratch, two sets: batch b+1 is prepared while batch b is formatted */
-    DevMem d_seg_perm[2], d_seg_tiles[2], d_seg_ntiles[2];        /* short reads: size-sorted order and tiles of every segment (k_segment_sort) */
-    PinnedMem h_out[4], h_total;                   /* pinned ring: batches wait here for the writer thread */
+    DevMem d_seg_perm[2];                          /* k-mer error injection: the reads of every segment ordered by size (k_segment_sort) */
+    PinnedMem h_out[SIMMR_RING_BUFFERS], h_total;                   /* pinned ring: batches wait here for the writer thread */
     cudaEvent_t ev[24] = {};                       /* created with the context (Events below) */
     DevMem d_draw[13];
     simmr_stats stats{};
@@ -173,21 +174,12 @@ size_t lanes_smem(const ProfileModel &m, uint32_t warps, uint32_t stage_cap) {
 
 /* kernel instantiations: the word path is specialised per quality mode, replay is generic */
 using FormatKernel = void (*)(RunParams, ReplayDev);
-bool sorted_tiles() { const char *e = getenv("SIMMR_TILES"); return !(e && !strcmp(e, "linear")); }      /* experiment switch */
 FormatKernel lanes_kernel(bool replay, int qm) {
-    if (!sorted_tiles()) {
-        if (replay) return k_format_lanes<true, QM_CONST, false>;
-        switch (qm) {
-        case QM_LANE: return k_format_lanes<false, QM_LANE, false>;
-        case QM_POS: return k_format_lanes<false, QM_POS, false>;
-        default: return k_format_lanes<false, QM_CONST, false>;
-        }
-    }
-    if (replay) return k_format_lanes<true, QM_CONST, true>;
+    if (replay) return k_format_lanes<true, QM_CONST>;
     switch (qm) {
-    case QM_LANE: return k_format_lanes<false, QM_LANE, true>;
-    case QM_POS: return k_format_lanes<false, QM_POS, true>;
-    default: return k_format_lanes<false, QM_CONST, true>;
+    case QM_LANE: return k_format_lanes<false, QM_LANE>;
+    case QM_POS: return k_format_lanes<false, QM_POS>;
+    default: return k_format_lanes<false, QM_CONST>;
     }
 }
 FormatKernel direct_kernel(bool replay) { return replay ? k_format_direct<true> : k_format_direct<false>; }
@@ -256,11 +248,33 @@ int ensure_headers(simmr_ctx *ctx, const char *fmt) {
     std::string err;
     int rc = compile_headers(ctx->host_view, f.c_str(), ctx->plan, err);
     if (rc) return fail(ctx, rc, err);
-    CU(ctx->d_chdr.upload(ctx->plan.contigs.data(), ctx->plan.contigs.size(), ctx->compute));
-    CU(ctx->d_toks.upload(ctx->plan.toks.data(), ctx->plan.toks.size(), ctx->compute));
-    if (ctx->plan.hdr_cap > 65535u) return fail(ctx, SIMMR_E_LIMIT, "a read header could exceed 65535 bytes");     /* descriptors hold header lengths in 16 bits */
-    ctx->plan.pool.resize((ctx->plan.pool.size() + 7) & ~size_t(3), '\0');
-    CU(ctx->d_pool.upload(ctx->plan.pool.data(), ctx->plan.pool.size(), ctx->compute));
+    {   /* device image: block i = 2 * contig + mate of `stride` bytes holds the ContigHdr, its tokens and their literals
+         * (literals on 4-byte boundaries, the kernel fetches them by words); token offsets become absolute */
+        const HeaderPlan &hp = ctx->plan;
+        size_t stride = 32;
+        for (const ContigHdr &ch : hp.contigs) {
+            size_t need = sizeof(ContigHdr) + size_t(ch.ntok) * sizeof(HdrTok);
+            for (uint32_t i = 0; i < ch.ntok; ++i) need += (size_t(hp.toks[ch.tok_off + i].len) + 3) & ~size_t(3);
+            stride = std::max(stride, (need + 4 + 31) & ~size_t(31));
+        }
+        if (stride * hp.contigs.size() > (size_t(2) << 30)) return fail(ctx, SIMMR_E_LIMIT, "header templates need more than 2 GiB");
+        std::vector<uint8_t> img(stride * hp.contigs.size() + 64, 0);
+        for (size_t i = 0; i < hp.contigs.size(); ++i) {
+            uint8_t *blk = img.data() + i * stride;
+            ContigHdr ch = hp.contigs[i];
+            const uint32_t src_tok = ch.tok_off;
+            ch.tok_off = uint32_t((i * stride + sizeof(ContigHdr)) / sizeof(HdrTok));
+            memcpy(blk, &ch, sizeof ch);
+            size_t lit_at = i * stride + sizeof(ContigHdr) + size_t(ch.ntok) * sizeof(HdrTok);
+            for (uint32_t t = 0; t < ch.ntok; ++t) {
+                HdrTok k = hp.toks[src_tok + t];
+                if (k.type == TOK_LIT) { memcpy(img.data() + lit_at, hp.pool.data() + k.off, k.len); k.off = uint32_t(lit_at); lit_at += (size_t(k.len) + 3) & ~size_t(3); }
+                memcpy(blk + sizeof(ContigHdr) + t * sizeof(HdrTok), &k, sizeof k);
+            }
+        }
+        ctx->hdr_stride = uint32_t(stride);
+        CU(ctx->d_hdr.upload(img.data(), img.size(), ctx->compute));
+    }
     CU(cudaStreamSynchronize(ctx->compute));
     {   /* the same decimal fields in every contig (token lists are canonical: literal, field, ..., literal) let the
          * kernel run the template without per-token dispatch */
@@ -288,7 +302,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.contig_size = ctx->d_contig_size.as<uint64_t>(); rp.genome_contig = ctx->d_genome_contig.as<uint32_t>();
     rp.impure = ctx->d_impure.as<uint32_t>(); rp.packed = ctx->d_packed.as<uint32_t>() + PACK_PAD_WORDS;
     rp.hdr_fast = ctx->hdr_fast; rp.hdr_fields = ctx->hdr_fields; rp.hdr_kinds = ctx->hdr_kinds;
-    rp.chdr = ctx->d_chdr.as<ContigHdr>(); rp.toks = ctx->d_toks.as<HdrTok>(); rp.pool = ctx->d_pool.as<uint8_t>();
+    rp.hdr = ctx->d_hdr.as<uint8_t>(); rp.hdr_stride = ctx->hdr_stride; rp.toks = ctx->d_hdr.as<HdrTok>(); rp.pool = ctx->d_hdr.as<uint8_t>();
     rp.n_genomes = ctx->host_view.n_genomes; rp.n_contigs = ctx->host_view.n_contigs;
     rp.unit_start = ctx->d_unit_start.as<uint64_t>();
     rp.read_id_base = id_base;
@@ -305,7 +319,6 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
         rp.err = ErrTab{1u, m.err.k, uint32_t(m.err.ref.size()), 0u, ctx->d_err_direct.as<uint32_t>(), ctx->d_err_ref.as<uint32_t>(), ctx->d_err_keep.as<uint32_t>(),
                         ctx->d_err_row.as<uint32_t>(), ctx->d_err_cb.as<uint32_t>(), ctx->d_err_entries.as<uint32_t>(), ctx->d_err_alts.as<uint32_t>()};
         rp.epacked = ctx->d_epacked.as<uint32_t>(); rp.ebases = ctx->d_ebases.as<uint8_t>();
-        if (!pl.tiles) rp.stage_cap = 0xffffffffu;       /* k_segment_sort only orders the reads here */
     }
 }
 
@@ -313,7 +326,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
 /* the batch pipeline shared by simulate, replay and measure                 */
 /* ---------------------------------------------------------------------- */
 constexpr int RING = SIMMR_RING_BUFFERS;   /* pinned host buffers per context */
-enum : int { EV_START = 0, EV_STOP, EV_F0, EV_F1, EV_TOTAL /* 2 */ = 4, EV_FMT /* 2 */ = 6, EV_PREP /* 2 */ = 8, EV_DONE /* 2 */ = 10, EV_COPY /* RING */ = 12, EV_COUNT = 16 };
+enum : int { EV_START = 0, EV_STOP, EV_F0, EV_F1, EV_TOTAL /* 2 */ = 4, EV_FMT /* 2 */ = 6, EV_PREP /* 2 */ = 8, EV_DONE /* 2 */ = 10, EV_COPY /* RING */ = 12, EV_COUNT = 12 + SIMMR_RING_BUFFERS };
 
 /* A finished batch on its way from a launch thread to the writer thread. */
 struct Ready { int slot; const uint8_t *data; uint64_t bytes, first, units; cudaEvent_t copied; };
@@ -371,7 +384,7 @@ struct Runner {
     void scratch(RunParams &r, int k) const {
         r.sizes = ctx->d_sizes[k].as<uint32_t>(); r.offsets = ctx->d_offsets[k].as<uint64_t>();
         r.desc = ctx->d_desc[k].as<UnitRec>(); r.desc_ext = ctx->d_desc_ext[k].as<UnitExt>(); r.block_sums = ctx->d_block_sums[k].as<uint64_t>();
-        r.seg_perm = ctx->d_seg_perm[k].as<uint16_t>(); r.seg_tiles = ctx->d_seg_tiles[k].as<uint16_t>(); r.seg_ntiles = ctx->d_seg_ntiles[k].as<uint32_t>();
+        r.seg_perm = ctx->d_seg_perm[k].as<uint16_t>();
     }
     /* plan, batch size, device and pinned buffers */
     int init(uint64_t ub_, uint64_t ue_, uint64_t seed, const simmr_run_opts *opts, bool to_host, bool measure) {
@@ -384,7 +397,7 @@ struct Runner {
          * it averages 40 KB — 2 GiB were 16 K reads per launch, 7 per warp, and the last warps' long reads left the GPU half
          * idle (+22 %). */
         errs = ctx->model.err.on && !replay;           /* k-mer error injection between sizing and formatting */
-        uint64_t target_bytes = to_host ? (256ull << 20) : errs ? (4096ull << 20) : (16384ull << 20);
+        uint64_t target_bytes = to_host ? (128ull << 20) : errs ? (4096ull << 20) : (16384ull << 20);     /* to the host: 8 pinned buffers of 128 MiB */
         if (measure_only) target_bytes = errs ? (1024ull << 20) : (uint64_t(pl.max_unit_bytes) << 24);
         if (!to_host && !measure_only) {
             size_t free_b = 0, total_b = 0;
@@ -402,10 +415,7 @@ struct Runner {
         for (int k = 0; k < 2; ++k) {
             CU(ctx->d_sizes[k].reserve(batch * 4)); CU(ctx->d_desc[k].reserve(batch * sizeof(UnitRec))); CU(ctx->d_desc_ext[k].reserve(batch * sizeof(UnitExt)));
             CU(ctx->d_offsets[k].reserve((batch + 1) * 8)); CU(ctx->d_block_sums[k].reserve(size_t(max_blocks) * 8));
-            if (pl.tiles || errs) {
-                CU(ctx->d_seg_perm[k].reserve(max_segs * SEG_UNITS * 2)); CU(ctx->d_seg_tiles[k].reserve(max_segs * SEG_UNITS * 2));
-                CU(ctx->d_seg_ntiles[k].reserve(max_segs * 4));
-            }
+            if (errs) CU(ctx->d_seg_perm[k].reserve(max_segs * SEG_UNITS * 2));
         }
         if (errs) {      /* scratch for a batch's edited reads: as many bases as the batch has FASTQ bytes, 16 more per read (err_scratch_base) */
             const uint64_t nb = out_cap + 16 * batch + 64;
@@ -436,7 +446,7 @@ struct Runner {
         else k_unit_sizes<false><<<nblk, SIZES_THREADS, 0, prep>>>(r, rd);
         if (dbg_sync) { cudaError_t e_ = cudaStreamSynchronize(prep); if (e_ != cudaSuccess) return fail(ctx, SIMMR_E_CUDA, std::string("k_unit_sizes: ") + cudaGetErrorString(e_)); }
         k_scan_blocks<<<1, 1024, 0, prep>>>(r, nblk);
-        if (pl.tiles || errs) k_segment_sort<<<(n + SEG_UNITS - 1) / SEG_UNITS, SEG_THREADS, 0, prep>>>(r);     /* offsets + size-sorted tiles */
+        if (errs) k_segment_sort<<<(n + SEG_UNITS - 1) / SEG_UNITS, SEG_THREADS, 0, prep>>>(r);     /* offsets + the reads of every segment ordered by size */
         else k_unit_offsets<<<nblk, SIZES_THREADS, 0, prep>>>(r);
         launches += 3;
         if (errs) {      /* edit the reads (size-sorted order), then offsets again from the edited sizes */
@@ -459,8 +469,8 @@ struct Runner {
         if (guard) CU(cudaMemsetAsync(ctx->d_out[dslot].p, 0xA5, out_cap, ctx->compute));
         CU(cudaEventRecord(ev[EV_F0], ctx->compute));
         if (pl.tiles) {
-            const uint32_t wpc = pl.threads / 32, work = sorted_tiles() ? (n + SEG_UNITS - 1) / SEG_UNITS : ((n + WARP_UNITS - 1) / WARP_UNITS + wpc - 1) / wpc;
-            const int grid = int(std::min<uint32_t>(work, uint32_t(pl.grid)));      /* a CTA takes whole segments */
+            const uint32_t wpc = pl.threads / 32, nctas = ((n + WARP_UNITS - 1) / WARP_UNITS + wpc - 1) / wpc;
+            const int grid = int(std::min<uint32_t>(nctas, uint32_t(pl.grid)));
             lanes_kernel(replay, quality_mode(ctx->model))<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
         } else if (pl.lanes) {
             CU(cudaMemsetAsync(rp.counters + 4, 0, 8, ctx->compute));       /* the kernel's piece counter */

@@ -117,7 +117,7 @@ def test_c3_novaseq_500m_reads_tsv_genome_file(engine, tmp_path):
         _write_fasta(p, [(ref.contig_id(c), ref.contig(c)) for c in range(int(ref.genome_contig[g]), int(ref.genome_contig[g + 1]))])
         paths.append(p)
     tsv = tmp_path / "genomes.tsv"
-    tsv.write_text("path\tuuid\tabundance\n" + "".join(f"{p}\t{ref.uuid(g)}\t{ab[g]!r}\n" for g, p in enumerate(paths)))
+    tsv.write_text("path\tuuid\tabundance\n" + "".join(f"{p}\t{ref.uuid(g)}\t{float(ab[g])!r}\n" for g, p in enumerate(paths)))
     recs = S.parse_genome_file(str(tsv))
     assert [r["filepath"] for r in recs] == paths and [r["uuid"] for r in recs] == [ref.uuid(g) for g in range(100)]
     assert [r["abundance"] for r in recs] == ab.tolist()
