@@ -336,14 +336,15 @@ struct Ready { int slot; const uint8_t *data; uint64_t bytes, first, units; cuda
 struct BatchQueue {
     std::mutex m; std::condition_variable cv;
     std::deque<Ready> q;
-    int free_slots = RING; bool closed = false;
+    int free_slots = RING, retained = 0; bool closed = false;      /* retained: chunks a sink kept (SIMMR_SINK_RETAINED) and has not given back */
     std::atomic<bool> abort{false};
     bool acquire() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return free_slots > 0; }); --free_slots; return !abort.load(); }
     void push(const Ready &r) { { std::lock_guard<std::mutex> l(m); q.push_back(r); } cv.notify_all(); }
     void close() { { std::lock_guard<std::mutex> l(m); closed = true; } cv.notify_all(); }
     bool pop(Ready &r) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !q.empty() || closed; }); if (q.empty()) return false; r = q.front(); q.pop_front(); return true; }
-    void release() { { std::lock_guard<std::mutex> l(m); ++free_slots; } cv.notify_all(); }
-    void wait_all_released() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return free_slots == RING; }); }
+    void release(bool was_retained = false) { { std::lock_guard<std::mutex> l(m); ++free_slots; if (was_retained) --retained; } cv.notify_all(); }
+    void retain() { std::lock_guard<std::mutex> l(m); ++retained; }
+    void wait_all_released() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return retained == 0; }); }
 };
 /* chunks a sink retained (SIMMR_SINK_RETAINED): pinned buffer -> the queue that gets it back */
 std::mutex g_retained_mu;
@@ -364,8 +365,13 @@ bool write_batches(const std::vector<BatchQueue *> &qs, const std::vector<int> &
         int verdict = 1;
         if (ok && copied) {
             { std::lock_guard<std::mutex> l(g_retained_mu); g_retained[r.data] = qs[g]; }      /* before the sink can pass it on */
+            qs[g]->retain();                                   /* counted before the sink can release it from another thread */
             verdict = sink(user, r.data, r.bytes, r.first, r.units);
-            if (verdict != SIMMR_SINK_RETAINED) { std::lock_guard<std::mutex> l(g_retained_mu); g_retained.erase(r.data); }
+            if (verdict != SIMMR_SINK_RETAINED) {
+                bool still = false;
+                { std::lock_guard<std::mutex> l(g_retained_mu); still = g_retained.erase(r.data) != 0; }
+                if (still) { std::lock_guard<std::mutex> l(qs[g]->m); --qs[g]->retained; }
+            }
         }
         if (ok && verdict != 0 && verdict != SIMMR_SINK_RETAINED) { ok = false; for (BatchQueue *q : qs) q->abort.store(true); }
         if (verdict != SIMMR_SINK_RETAINED) qs[g]->release();
@@ -630,7 +636,7 @@ const char *simmr_last_error(const simmr_ctx *ctx) { return ctx ? ctx->err.c_str
 void simmr_chunk_release(const uint8_t *data) {
     BatchQueue *q = nullptr;
     { std::lock_guard<std::mutex> l(g_retained_mu); auto it = g_retained.find(data); if (it != g_retained.end()) { q = it->second; g_retained.erase(it); } }
-    if (q) q->release();
+    if (q) q->release(true);
 }
 const char *simmr_version(void) { return "simmr_b200 0.1 (sm_100a)"; }
 
