@@ -326,7 +326,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
 /* the batch pipeline shared by simulate, replay and measure                 */
 /* ---------------------------------------------------------------------- */
 constexpr int RING = SIMMR_RING_BUFFERS;   /* pinned host buffers per context */
-enum : int { EV_START = 0, EV_STOP, EV_F0, EV_F1, EV_TOTAL /* 2 */ = 4, EV_FMT /* 2 */ = 6, EV_PREP /* 2 */ = 8, EV_DONE /* 2 */ = 10, EV_COPY /* RING */ = 12, EV_COUNT = 12 + SIMMR_RING_BUFFERS };
+enum : int { EV_START = 0, EV_STOP = 1, EV_F0 /* 2 */ = 2, EV_F1 /* 2 */ = 4, EV_TOTAL /* 2 */ = 6, EV_FMT /* 2 */ = 8, EV_PREP /* 2 */ = 10, EV_DONE /* 2 */ = 12, EV_COPY /* RING */ = 14, EV_COUNT = 14 + SIMMR_RING_BUFFERS };
 
 /* A finished batch on its way from a launch thread to the writer thread. */
 struct Ready { int slot; const uint8_t *data; uint64_t bytes, first, units; cudaEvent_t copied; };
@@ -393,7 +393,7 @@ struct Runner {
         r.seg_perm = ctx->d_seg_perm[k].as<uint16_t>();
     }
     /* plan, batch size, device and pinned buffers */
-    int init(uint64_t ub_, uint64_t ue_, uint64_t seed, const simmr_run_opts *opts, bool to_host, bool measure) {
+    int init(uint64_t ub_, uint64_t ue_, uint64_t seed, const simmr_run_opts *opts, bool to_host, bool measure, bool dev_sink = false) {
         ub = ub_; ue = ue_; measure_only = measure; ev = ctx->ev;
         int rc = make_plan(ctx, replay, pl);
         if (rc) return rc;
@@ -408,8 +408,8 @@ struct Runner {
         if (!to_host && !measure_only) {
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
-            free_b += ctx->d_out[0].bytes;                /* what this context already holds for staging can be reused */
-            while (target_bytes > (256ull << 20) && target_bytes > free_b / 3) target_bytes /= 2;
+            free_b += ctx->d_out[0].bytes + ctx->d_out[1].bytes;       /* what this context already holds for staging can be reused */
+            while (target_bytes > (256ull << 20) && target_bytes > free_b / (dev_sink ? 5 : 3)) target_bytes /= 2;
         }
         batch = opts && opts->batch_units ? opts->batch_units : std::max<uint64_t>(1, target_bytes / pl.max_unit_bytes);
         batch = std::min<uint64_t>(batch, std::max<uint64_t>(1, ue - ub));
@@ -429,7 +429,7 @@ struct Runner {
         }
         CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
         guard = ctx->dbg_guard; dbg_sync = ctx->dbg_sync;
-        const int nbuf = measure_only ? 0 : to_host ? 2 : 1;
+        const int nbuf = measure_only ? 0 : (to_host || dev_sink) ? 2 : 1;       /* a device consumer reads batch b while batch b + 1 is being formatted */
         for (int b = 0; b < nbuf; ++b) CU(ctx->d_out[b].reserve(out_cap));
         if (to_host) for (int b = 0; b < RING; ++b) CU(ctx->h_out[b].reserve(out_cap, ctx->numa_node));
         CU(ctx->h_total.reserve(2 * sizeof(uint64_t), ctx->numa_node));
@@ -467,13 +467,13 @@ struct Runner {
         CU(cudaEventRecord(ev[EV_PREP + k], prep));
         return SIMMR_OK;
     }
-    /* the format kernel of the batch prepared in set k, into d_out[dslot]; bracketed by EV_F0 / EV_F1 */
+    /* the format kernel of the batch prepared in set k, into d_out[dslot]; bracketed by EV_F0 / EV_F1 of set k */
     int format(uint64_t u, int k, int dslot) {
         const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
         scratch(rp, k);
         rp.batch_begin = u; rp.batch_units = n; rp.out = ctx->d_out[dslot].as<uint8_t>();
         if (guard) CU(cudaMemsetAsync(ctx->d_out[dslot].p, 0xA5, out_cap, ctx->compute));
-        CU(cudaEventRecord(ev[EV_F0], ctx->compute));
+        CU(cudaEventRecord(ev[EV_F0 + k], ctx->compute));
         if (pl.tiles) {
             const uint32_t wpc = pl.threads / 32, nctas = ((n + WARP_UNITS - 1) / WARP_UNITS + wpc - 1) / wpc;
             const int grid = int(std::min<uint32_t>(nctas, uint32_t(pl.grid)));
@@ -487,7 +487,7 @@ struct Runner {
         }
         ++launches;
         CU(cudaGetLastError());
-        CU(cudaEventRecord(ev[EV_F1], ctx->compute));
+        CU(cudaEventRecord(ev[EV_F1 + k], ctx->compute));
         CU(cudaEventRecord(ev[EV_DONE + k], ctx->compute)); done_live[k] = true;
         if (guard) {   /* SIMMR_DEBUG_GUARD: nothing may be written past the batch's last byte */
             uint64_t total = 0; uint8_t tail[64];
@@ -527,17 +527,32 @@ int produce(Runner &R, uint64_t j0, uint64_t stride, BatchQueue *q, simmr_stats 
     auto start_of = [&](uint64_t j) { return R.ub + j * R.batch; };
     if (R.ahead() && j0 < nbatches) { rc = R.prepare(start_of(j0), 0); if (rc) return rc; }
     uint64_t seq = 0;                                          /* this context's own batch count */
+    /* device-resident runs: batch b's kernel time is read, and its bytes are shown to the device consumer, while batch
+     * b + 1 is already running (two staging buffers when there is a consumer) */
+    struct Last { bool live = false; int k = 0, dslot = 0; uint64_t first = 0; uint32_t units = 0; } last;
+    auto settle = [&]() -> int {
+        if (!last.live) return SIMMR_OK;
+        last.live = false;
+        CU(cudaEventSynchronize(ev[EV_F1 + last.k]));
+        float ms = 0; CU(cudaEventElapsedTime(&ms, ev[EV_F0 + last.k], ev[EV_F1 + last.k])); format_ms += ms;
+        if (dev_sink) {
+            const uint64_t total = static_cast<uint64_t *>(ctx->h_total.p)[last.dslot];
+            if (total > R.out_cap) return fail(ctx, SIMMR_E_LIMIT, "batch overflowed its staging buffer");
+            if (dev_sink(dev_user, ctx->d_out[last.dslot].as<uint8_t>(), total, last.first, last.units)) return fail(ctx, SIMMR_E_SINK, "device sink callback failed");
+        }
+        return SIMMR_OK;
+    };
     for (uint64_t j = j0; j < nbatches; j += stride, ++seq) {
         const uint64_t u = start_of(j);
         const uint32_t n = uint32_t(std::min<uint64_t>(R.batch, R.ue - u));
-        const int k = int(seq & 1), dslot = q ? int(seq & 1) : 0, slot = int(seq % RING);
+        const int k = int(seq & 1), dslot = (q || dev_sink) ? int(seq & 1) : 0, slot = int(seq % RING);
         if (!R.ahead()) { rc = R.prepare(u, k); if (rc) return rc; }
         if (R.measure_only) continue;                          /* geometry, sizes (and edits) only: what the units occupy in the FASTQ stream */
         if (q && !q->acquire()) return fail(ctx, SIMMR_E_SINK, "sink callback failed");      /* a pinned buffer is free again */
         if (R.ahead() && j + stride < nbatches) { rc = R.prepare(start_of(j + stride), k ^ 1); if (rc) return rc; }
         CU(cudaStreamWaitEvent(ctx->compute, ev[EV_PREP + k], 0));
-        if (q) {
-            if (seq >= 2) CU(cudaStreamWaitEvent(ctx->compute, ev[EV_COPY + int((seq - 2) % RING)], 0));   /* d_out[dslot] has been copied out */
+        if (q || dev_sink) {      /* the batch's byte count, on its way to the host before the format kernel starts */
+            if (q && seq >= 2) CU(cudaStreamWaitEvent(ctx->compute, ev[EV_COPY + int((seq - 2) % RING)], 0));   /* d_out[dslot] has been copied out */
             R.scratch(R.rp, k);
             CU(cudaMemcpyAsync(static_cast<uint64_t *>(ctx->h_total.p) + dslot, R.rp.offsets + n, 8, cudaMemcpyDeviceToHost, ctx->compute));
             CU(cudaEventRecord(ev[EV_TOTAL + dslot], ctx->compute));
@@ -553,16 +568,12 @@ int produce(Runner &R, uint64_t j0, uint64_t stride, BatchQueue *q, simmr_stats 
             CU(cudaEventRecord(ev[EV_COPY + slot], ctx->copy));
             q->push(Ready{slot, static_cast<const uint8_t *>(ctx->h_out[slot].p), total, u, n, ev[EV_COPY + slot]});
             st.d2h_bytes += total + 8;
-        } else {   /* per-batch format time: costs one sync per batch, only taken when it cannot hide copies */
-            CU(cudaEventSynchronize(ev[EV_F1])); float ms = 0; CU(cudaEventElapsedTime(&ms, ev[EV_F0], ev[EV_F1])); format_ms += ms;
-            if (dev_sink) {      /* a consumer on the device: the batch's bytes where the kernel left them */
-                uint64_t total = 0;
-                CU(cudaMemcpyAsync(&total, R.rp.offsets + n, 8, cudaMemcpyDeviceToHost, ctx->compute));
-                CU(cudaStreamSynchronize(ctx->compute));
-                if (dev_sink(dev_user, ctx->d_out[0].as<uint8_t>(), total, u, n)) return fail(ctx, SIMMR_E_SINK, "device sink callback failed");
-            }
+        } else {
+            rc = settle(); if (rc) return rc;                  /* the batch before this one */
+            last = Last{true, k, dslot, u, n};
         }
     }
+    rc = settle(); if (rc) return rc;
     return R.finish(st, format_ms);
 }
 
@@ -573,7 +584,7 @@ int run_units(simmr_ctx *ctx, bool replay, const ReplayDev &rd, uint64_t ub, uin
     /* debug switches, read once per run */
     ctx->dbg_guard = getenv("SIMMR_DEBUG_GUARD") != nullptr; ctx->dbg_sync = getenv("SIMMR_DEBUG_SYNC") != nullptr; ctx->dbg_serial = getenv("SIMMR_PREP_SERIAL") != nullptr;
     Runner R{ctx, replay, rd};
-    int rc = R.init(ub, ue, seed, opts, sink != nullptr, measure_only);
+    int rc = R.init(ub, ue, seed, opts, sink != nullptr, measure_only, dev_sink != nullptr);
     if (rc) return rc;
     simmr_stats st{};
     st.units = ue - ub;
