@@ -20,21 +20,7 @@ from oracle import pyoracle as po              # noqa: E402
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
 
-def genomes(n, lo, hi, contigs, seed, min_contig=50_000):
-    rng = np.random.default_rng(seed)
-    sizes = rng.integers(lo, hi + 1, n)
-    bases = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(sizes.sum()), dtype=np.uint8)]
-    coff, csize, gcon, cids, cidoff, gids, gidoff = [0], [], [0], b"", [0], b"", [0]
-    for g in range(n):
-        nc = int(rng.integers(contigs[0], contigs[1] + 1))
-        room = int(sizes[g]) - nc * min_contig
-        cuts = np.sort(rng.integers(0, room + 1, nc - 1)) if nc > 1 else np.zeros(0, np.int64)
-        for c, ln in enumerate(np.diff(np.concatenate([[0], cuts, [room]])) + min_contig):
-            coff.append(coff[-1] + int(ln)); csize.append(int(ln))
-            cids += f"g{g:04d}_c{c:03d}".encode(); cidoff.append(len(cids))
-        gcon.append(len(csize))
-        gids += f"{H.splitmix64(g):016x}".encode(); gidoff.append(len(gids))
-    return S.GenomeSet(bases, coff, csize, gcon, cids, cidoff, gids, gidoff)
+genomes = H.config_genomes          # synthetic sets of the named sizes (simmr_b200/synth.py)
 
 
 def run(eng, gs, prof, reads, seed=42, iters=3, slices=((0, 300),)):
@@ -50,7 +36,7 @@ def run(eng, gs, prof, reads, seed=42, iters=3, slices=((0, 300),)):
         ue = min(total, ub + n)
         ok &= eng.simulate_bytes(reads, seed, unit_begin=ub, unit_end=ue) == po.simulate(og, oprof, reads, seed, unit_begin=ub, unit_end=ue)
     ok &= eng.measure(reads, seed) == (st["bytes"], st["records"])
-    return {"records": st["records"], "bases": st["bases"], "fastq_bytes": st["bytes"], "device_ms": round(st["device_ms"], 3),
+    return {"records": st["records"], "bases": st["bases"], "fastq_bytes": st["bytes"], "device_ms": round(st["device_ms"], 3), "format_ms": round(st["format_ms"], 3),
             "gbases_per_s": round(st["bases"] / st["device_ms"] / 1e6, 1), "records_per_s": round(st["records"] / st["device_ms"] * 1e3),
             "format_kernel_alg_gbs": round(st["algorithmic_bytes"] / st["format_ms"] / 1e6, 1),
             "format_kernel_roofline_frac": round(st["algorithmic_bytes"] / st["format_ms"] / 1e6 / PEAK, 3),
@@ -58,11 +44,11 @@ def run(eng, gs, prof, reads, seed=42, iters=3, slices=((0, 300),)):
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     out = {"peak_gbs": PEAK, "note": "one B200, device-side (FASTQ bytes left in HBM staging), seed 42; slices of every run are byte-compared with the CPU oracle"}
     with S.Engine(0) as eng:
         t = time.time()
-        g1 = genomes(1, 5_000_000, 5_000_000, (1, 1), 1)
+        g1 = genomes(1, 5_000_000, 5_000_000, (1, 1), seed=1)
         prof = S.PerfectShortErrorProfile(150, 150)
         reads, _ = S.UniformAbundanceProfile().determine_abundances(5000, 1)
         eng.load_genomes(g1); eng.set_error_profile(prof)
@@ -84,16 +70,19 @@ def main():
         out["C3 NovaSeq custom-short, 500M reads, uuid+abundance genome file (custom abundance)"] = r
         print("C3", r, flush=True)
 
-        g50 = genomes(50, 2_000_000, 6_000_000, (1, 4), 4, min_contig=100_000)
+        g50 = genomes(50, 2_000_000, 6_000_000, (1, 4), seed=4, min_contig=100_000)
         reads, _ = S.UniformAbundanceProfile().determine_abundances(10_000_000, 50)
         r = run(eng, g50, S.MinimalLongErrorProfile(30), reads, iters=2, slices=((0, 20), (5_000_000, 20)))
         out["C4a minimal-long, 10M reads, 50 genomes"] = r
         print("C4a", r, flush=True)
         r = run(eng, g50, S.CustomLongErrorProfile(H.ont_blob()), reads, iters=2, slices=((0, 20), (7_000_000, 20)))
-        out["C4b ONT-style custom-long (empirical Phreds, gamma lengths; k-mer errors not on device yet), 10M reads"] = r
+        out["C4b' ONT-style custom-long without an alt-k-mer table (empirical Phreds, gamma lengths), 10M reads"] = r
+        print("C4b'", r, flush=True)
+        r = run(eng, g50, S.CustomLongErrorProfile(H.ont_blob_with_kmers(k=7, n_alts=20)[0]), reads, iters=2, slices=((0, 20), (7_000_000, 20)))
+        out["C4b ONT-style custom-long with a k = 7 alt-k-mer table of 20 alternates per k-mer (k-mer error injection on device), 10M reads"] = r
         print("C4b", r, flush=True)
 
-        g1000 = genomes(1000, 3_500_000, 4_500_000, (1, 6), 5)
+        g1000 = genomes(1000, 4_000_000, 4_800_000, (1, 6), seed=5)
         reads, _ = S.ExactAbundanceProfile().determine_abundances(1_000_000, 1000)
         r = run(eng, g1000, S.MinimalShortErrorProfile(150, 150, 30), reads, iters=2, slices=((0, 300), (499_999_000, 300)))
         r["genome_bytes"] = int(g1000.bases.nbytes)
