@@ -1243,7 +1243,8 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
-    asm volatile("{ .reg .pred p; W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1; @!p bra W; }" ::"r"(addr), "r"(parity) : "memory");
+    /* the hint lets the hardware park the warp instead of spinning through issue slots */
+    asm volatile("{ .reg .pred p; W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2; @!p bra W; }" ::"r"(addr), "r"(parity), "r"(20000u) : "memory");
 }
 /* bytes [lo, hi) of word v to the word at addr */
 __device__ __forceinline__ void sts_bytes(uint32_t addr, uint32_t v, uint32_t lo, uint32_t hi) {
@@ -1310,12 +1311,7 @@ __device__ __forceinline__ void line_lane(const RunParams &rp, uint32_t tab_s, b
         for (; it < whole; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::true_type{}, it);
         before_tail();
         for (; it < full; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, it);
-        switch (T4 - 4u * full) {
-        case 1: turn(std::integral_constant<uint32_t, 1>{}, std::false_type{}, full); break;
-        case 2: turn(std::integral_constant<uint32_t, 2>{}, std::false_type{}, full); break;
-        case 3: turn(std::integral_constant<uint32_t, 3>{}, std::false_type{}, full); break;
-        default: turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, full); break;
-        }
+        turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, full);     /* four groups whatever the rest is: slots beyond a line's end are not stored */
     } else before_tail();
 }
 
