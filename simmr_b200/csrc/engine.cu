@@ -223,7 +223,7 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
             const uint64_t cap = std::min<uint64_t>(uint64_t(cap_for(warps)), WARP_UNITS * need);
             pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.smem = lanes_smem(m, warps, uint32_t(cap));
             const char *pe = getenv("SIMMR_PAIRS");
-            pl.pairs = !replay && quality_mode(m) != QM_CONST && !(pe && !strcmp(pe, "0"));
+            pl.pairs = !replay && quality_mode(m) != QM_CONST && pe && !strcmp(pe, "1");   /* experiment, slower than one warp per tile (profiles/r02_experiment_warp_pairs_*) */
             if (pl.pairs) pl.threads *= 2;
         }
     }
