@@ -227,9 +227,8 @@ struct __align__(16) UnitRec {
 };
 struct __align__(16) UnitExt { uint64_t a1, p0, p1, pad_; };
 static_assert(sizeof(UnitRec) == 32 && sizeof(UnitExt) == 32, "descriptor layout");
-__device__ __forceinline__ UnitDesc load_unit(const RunParams &rp, uint32_t i) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(rp.desc + i);
-    const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+/* v0, v1 = the UnitRec of unit i of the batch as stored */
+__device__ __forceinline__ UnitDesc unpack_unit(const RunParams &rp, uint4 v0, uint4 v1, uint32_t i) {
     UnitDesc d;
     d.a0 = pair64(v0.x, v0.y); d.p0 = v0.z; d.p1 = v0.w;
     d.contig = v1.x; d.rl = uint16_t(v1.y); d.L0 = uint16_t(v1.y >> 16); d.L1 = uint16_t(v1.z); d.H0 = uint16_t(v1.z >> 16);
@@ -241,6 +240,11 @@ __device__ __forceinline__ UnitDesc load_unit(const RunParams &rp, uint32_t i) {
         d.a1 = pair64(e0.x, e0.y); d.p0 = pair64(e0.z, e0.w); d.p1 = pair64(e1.x, e1.y);
     }
     return d;
+}
+__device__ __forceinline__ UnitDesc load_unit(const RunParams &rp, uint32_t i) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(rp.desc + i);
+    const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+    return unpack_unit(rp, v0, v1, i);
 }
 
 template <bool REPLAY>
@@ -966,7 +970,7 @@ __device__ __forceinline__ uint32_t quals4(const RunParams &rp, uint32_t qtab_s,
  * are applied afterwards (substitutions_lane), so the two lines are independent here. */
 template <int QM, bool CB7>
 __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, uint32_t lut_s, bool on, bool rc, uint32_t body_s,
-                                          Mwc1 &rng, uint64_t a, uint32_t L, uint32_t T4) {
+                                          Mwc1 &rng, uint64_t a, uint32_t L, uint32_t T4, bool pre, uint32_t pre_lo, uint32_t pre_hi) {
     if (!on) { L = 0; a = 0; }
     const uint32_t Ds = body_s + 1u, Dq = body_s + L + 4u;
     const uint32_t os = Ds & 3u, oq = Dq & 3u, sh_s = 8u * os, sh_q = 8u * oq;
@@ -978,7 +982,8 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
     const int64_t bit = rc ? 2 * int64_t(a + L) - 32 : 2 * int64_t(a);
     const uint32_t *pw = rp.packed + (bit >> 5);
     const uint32_t s2 = uint32_t(bit) & 31u, rev = rc ? 0x0123u : 0x3210u;
-    uint32_t w_lo = __ldg(pw), w_hi = __ldg(pw + 1);
+    uint32_t w_lo = pre_lo, w_hi = pre_hi;             /* pre: the window's first two words were fetched while the tile before was composed */
+    if (!pre) { w_lo = __ldg(pw); w_hi = __ldg(pw + 1); }
     pw += rc ? -1 : 2;
     const int32_t dw = rc ? -1 : 1;
     const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u, mask = rp.phred_mult - 1u;
@@ -1112,46 +1117,56 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
 
     const uint32_t mate = lane & 1u, slot = lane >> 1;
     const uint32_t ntiles = (rp.batch_units + WARP_UNITS - 1) / WARP_UNITS;
-    /* a tile's offsets (lane k: unit k, lane WARP_UNITS: the end) and descriptors are fetched one tile ahead, into registers */
-    auto fetch_tile = [&](uint32_t tile, uint64_t &off, UnitDesc &d) {
-        off = 0; d = UnitDesc{};
+    /* What a tile needs from global memory before it can start — this lane's unit descriptor, the tile's first byte in the
+     * batch, the first two words of the 2-bit copy under this lane's window — is fetched into registers while the tile
+     * before it is composed (the descriptors after its lines, the words after its headers): a warp has nothing else to
+     * do during those round trips, and 16 warps per SM do not hide them. */
+    struct TileIn { uint4 r0, r1; uint64_t base; uint32_t w_lo, w_hi; };
+    auto fetch_in = [&](uint32_t tile, TileIn &t) {
+        t.r0 = t.r1 = make_uint4(0u, 0u, 0u, 0u); t.base = 0; t.w_lo = t.w_hi = 0;
         if (tile < ntiles) {
             const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
-            if (lane <= tn) off = rp.offsets[t0 + lane];
-            if (slot < tn) d = load_unit(rp, t0 + slot);
+            if (slot < tn) { const uint4 *src = reinterpret_cast<const uint4 *>(rp.desc + t0 + slot); t.r0 = __ldg(src); t.r1 = __ldg(src + 1); }
+            t.base = __ldg(rp.offsets + t0);
         }
     };
-    for (uint32_t tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += gridDim.x * nwarps) {
+    auto fetch_words = [&](TileIn &t) {      /* same address arithmetic as body_lane; units with a UnitExt (flag 16) fetch theirs there */
+        const uint32_t L = mate ? (t.r1.z & 0xffffu) : (t.r1.y >> 16);
+        const uint64_t a = pair64(t.r0.x, t.r0.y) + (mate ? uint64_t(t.r0.w) - t.r0.z : 0u);
+        const int64_t bit = mate ? 2 * int64_t(a + L) - 32 : 2 * int64_t(a);
+        if (!((t.r1.w >> 16) & 16u)) { const uint32_t *pw = rp.packed + (bit >> 5); t.w_lo = __ldg(pw); t.w_hi = __ldg(pw + 1); }
+    };
+    TileIn nx{}; bool nx_ok = false;
+    const uint32_t tile_step = gridDim.x * nwarps;
+    for (uint32_t tile = blockIdx.x * nwarps + warp; tile < ntiles; tile += tile_step) {
         const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
-        uint64_t off_tile; UnitDesc d_tile;
-        fetch_tile(tile, off_tile, d_tile);
-        const uint32_t tile_next = tile + gridDim.x * nwarps;
-        if ((rp.flags & 0x800u) && tile_next < ntiles) {        /* the next tile's offsets (2 lines) and descriptors (4 lines) towards L2 */
-            const uint32_t t1 = tile_next * WARP_UNITS;
-            if (lane < 2) prefetch_l2(rp.offsets + t1 + 16u * lane);
-            else if (lane < 6) prefetch_l2(reinterpret_cast<const uint8_t *>(rp.desc + t1) + 128u * (lane - 2u));
-        }
-        if ((rp.flags & 0x2000u) && slot < tn) {                /* this record's header template */
-            const uint8_t *blk = rp.hdr + size_t(2u * d_tile.contig + mate) * rp.hdr_stride;
-            prefetch_l2(blk); if (rp.hdr_stride > 128u) prefetch_l2(blk + 128);
-        }
+        TileIn cur = nx;
+        const bool words_ahead = nx_ok;
+        if (!nx_ok) fetch_in(tile, cur);
+        nx_ok = false;
+        const UnitDesc d_tile = slot < tn ? unpack_unit(rp, cur.r0, cur.r1, t0 + slot) : UnitDesc{};
+        const uint32_t tile_next = tile + tile_step;
+        uint64_t tile_base = cur.base;                           /* first byte of the sub-tile in the batch */
         for (uint32_t s0 = 0; s0 < tn;) {
-            /* sub-tile = longest run of units from s0 that fits the stage */
+            /* sub-tile = longest run of units from s0 that fits the stage; a record's place in it by a scan of the records' bytes */
             const uint32_t u0 = t0 + s0, left = tn - s0;
-            const uint64_t off = s0 == 0 ? off_tile : (lane <= left ? rp.offsets[u0 + lane] : 0);
-            const uint64_t tile_base = __shfl_sync(0xffffffffu, off, 0), next = __shfl_down_sync(0xffffffffu, off, 1);
+            UnitDesc d = d_tile;
+            if (s0 != 0) { d = UnitDesc{}; if (slot < left) d = load_unit(rp, u0 + slot); }
+            const bool present = slot < left && (mate == 0 || (d.flags & 4u));
+            const uint32_t L = mate ? d.L1 : d.L0, H = mate ? d.H1 : d.H0;
+            const uint32_t rbytes = present ? H + 2u * L + 5u : 0u;
+            uint32_t rend = rbytes;                                                       /* bytes of the records up to and including this lane's */
+#pragma unroll
+            for (uint32_t o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, rend, o); if (lane >= o) rend += y; }
             const uint32_t pad = uint32_t(tile_base & 15);
-            const uint32_t nu = __popc(__ballot_sync(0xffffffffu, lane < left && next - tile_base + pad <= rp.stage_cap));
-            const uint32_t total = uint32_t(__shfl_sync(0xffffffffu, off, nu) - tile_base);
-            const uint32_t unit_off = pad + uint32_t(__shfl_sync(0xffffffffu, off, slot) - tile_base);
+            const uint32_t nu = __popc(__ballot_sync(0xffffffffu, mate == 1u && slot < left && rend + pad <= rp.stage_cap));
+            const uint32_t total = __shfl_sync(0xffffffffu, rend, 2u * nu - 1u);
+            const bool last_sub = s0 + nu >= tn;
             /* this lane's record */
             const bool mine = slot < nu;
-            UnitDesc d = d_tile;
-            if (s0 != 0) { d = UnitDesc{}; if (mine) d = load_unit(rp, u0 + slot); }
-            const bool have = mine && (mate == 0 || (d.flags & 4u));
-            const uint32_t L = mate ? d.L1 : d.L0, H = mate ? d.H1 : d.H0;
+            const bool have = mine && present;
             const uint64_t a = mate ? d.a1 : d.a0;
-            const uint32_t rec = unit_off + (mate ? d.H0 + 2u * d.L0 + 5u : 0u);      /* stage offset of the record */
+            const uint32_t rec = pad + rend - rbytes;                                 /* stage offset of the record */
             const bool odd = have && ((d.flags & 8u) || H < 2u || L < 4u);            /* rules out the word paths for the sub-tile */
             const bool words_ok = !__any_sync(0xffffffffu, odd) && !REPLAY;
             const bool hdr_fast = words_ok && rp.hdr_fast != 0;
@@ -1166,14 +1181,16 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
                 const uint32_t body_s = stage_s + rec + H;
                 const uint32_t slots = ((L + 3u + 3u) >> 2);                          /* word slots of a line, at most */
                 const uint32_t T4 = __reduce_max_sync(0xffffffffu, fast ? slots : 0u);
+                Mwc1 qc{}, ec{};
                 if (T4) {
-                    Mwc1 qc{}, ec{};
                     if (QM != QM_CONST) mwc1_seed(rp, qc, ec, 0u, 1u + mate, uint32_t(unit), uint32_t(unit >> 32));
                     const uint32_t lut_s = base_s + (mate ? SM_LUT_RC : SM_LUT_FWD);
-                    if (QM == QM_LANE && rp.phred.cb == 7u) body_lane<QM, true>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4);
-                    else body_lane<QM, false>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4);
-                    if (QM != QM_CONST && rp.phred.has_sub) substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
+                    const bool pre = words_ahead && s0 == 0 && !(d.flags & 16u);
+                    if (QM == QM_LANE && rp.phred.cb == 7u) body_lane<QM, true>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4, pre, cur.w_lo, cur.w_hi);
+                    else body_lane<QM, false>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4, pre, cur.w_lo, cur.w_hi);
                 }
+                if (last_sub && tile_next < ntiles) fetch_in(tile_next, nx);           /* on their way during the substitutions and the headers */
+                if (T4 && QM != QM_CONST && rp.phred.has_sub) substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
                 if (have && !fast) {
                     if (REPLAY) emit_body_replay<false>(rp, rd, stage + rec + H, mate, a, L, rd.base_off[unit] + (mate ? d.rl : 0), 0, 1);
                     else emit_body_pieces<false>(rp, stage + rec + H, unit, mate, a, L, 0, 1);
@@ -1201,6 +1218,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
                 sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n');
             }
             if (lane == 31 && total) sts8(stage_s + pad + total - 1u, '\n');
+            if (last_sub && tile_next < ntiles) { fetch_words(nx); nx_ok = true; }   /* the descriptors have arrived by now */
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             /* stage[pad, pad+total) -> out[tile_base, +total): 16-byte aligned middle by TMA, edges by byte stores */
@@ -1211,16 +1229,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
             }
             if (lane >= 1 && lane < 1 + head) rp.out[tile_base + (lane - 1)] = stage[pad + (lane - 1)];
             if (lane >= 16 && lane < 16 + tail) rp.out[tile_base + head + mid + (lane - 16)] = stage[pad + head + mid + (lane - 16)];
-            s0 += nu;
-            if ((rp.flags & 0x1000u) && s0 >= tn && tile_next < ntiles) {     /* the next tile's genome windows towards L2 (its descriptors were prefetched at this tile's start) */
-                const uint32_t t1 = tile_next * WARP_UNITS;
-                if (t1 + slot < rp.batch_units) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(rp.desc + t1 + slot));
-                    const uint64_t a1 = pair64(v.x, v.y) + (mate ? uint64_t(v.w) - v.z : 0u);
-                    const uint32_t *w = rp.packed + (a1 >> 4);
-                    prefetch_l2(w); prefetch_l2(w + 8);
-                }
-            }
+            s0 += nu; tile_base += total;
         }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
