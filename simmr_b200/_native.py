@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsimmr_b200.so")
+LIB_PATH = os.environ.get("SIMMR_B200_LIB") or os.path.join(_HERE, "libsimmr_b200.so")   # the override loads another build of the same library (kernel A/B runs)
 
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)
