@@ -21,6 +21,10 @@
 #include "../../include/simmr_b200.h"
 #include "simmr_types.h"
 
+#ifndef SIMMR_KO
+#define SIMMR_KO 0          /* development builds knock a piece of work out to see what it costs (profiles/r02_experiment_knockouts.txt); 0 = the product */
+#endif
+
 namespace simmr {
 
 /* ---------------------------------------------------------------------- */
@@ -1190,7 +1194,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
                     else body_lane<QM, false>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4, pre, cur.w_lo, cur.w_hi);
                 }
                 if (last_sub && tile_next < ntiles) fetch_in(tile_next, nx);           /* on their way during the substitutions and the headers */
-                if (T4 && QM != QM_CONST && rp.phred.has_sub) substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
+                if (SIMMR_KO != 3 && T4 && QM != QM_CONST && rp.phred.has_sub) substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
                 if (have && !fast) {
                     if (REPLAY) emit_body_replay<false>(rp, rd, stage + rec + H, mate, a, L, rd.base_off[unit] + (mate ? d.rl : 0), 0, 1);
                     else emit_body_pieces<false>(rp, stage + rec + H, unit, mate, a, L, 0, 1);
@@ -1199,7 +1203,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
             __syncwarp();
 
             /* ---- phase 2: header and the fixed bytes ---- */
-            if (have) {
+            if (have && SIMMR_KO != 1) {
                 uint64_t sp, ep; record_positions(d, mate, sp, ep);
                 const uint32_t id = rp.read_id_base + uint32_t(unit);
                 const uint32_t rec_s = stage_s + rec;
@@ -1235,232 +1239,6 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-
-/* ---------------------------------------------------------------------- */
-/* short reads, word path, two warps per tile                               */
-/* ---------------------------------------------------------------------- */
-/* k_format_lanes at 16 warps per SM is bound by latency, not by issue slots (58 % busy): its registers (124) and its
- * stages (13 KB per warp) allow no more warps.  Here a tile is shared by a PAIR of warps with half the registers each:
- * lane l of both warps holds record l of the tile, the "S" warp writes headers, fixed bytes, sequence lines and the
- * substituted bases, the "Q" warp seeds and walks the quality chains and writes the quality lines — 32 warps per SM on the
- * same shared memory.  The two never write the same byte; where they share a WORD only byte stores are used, except for
- * the read-modify-write with which a header's stream opens on the word before it: the Q warp holds back the last words
- * of its lines until the S warp has written its headers.  Three mbarriers per pair, each completing once per tile:
- *   FREE  S -> Q  the previous tile's bulk copy has read the stage: Q may store
- *   HDR   S -> Q  headers written: Q may store the tails of its lines
- *   QUAL  Q -> S  quality lines written: S may apply the substitutions and send the tile off */
-__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
-    /* the hint lets the hardware park the warp instead of spinning through issue slots */
-    asm volatile("{ .reg .pred p; W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2; @!p bra W; }" ::"r"(addr), "r"(parity), "r"(20000u) : "memory");
-}
-/* bytes [lo, hi) of word v to the word at addr */
-__device__ __forceinline__ void sts_bytes(uint32_t addr, uint32_t v, uint32_t lo, uint32_t hi) {
-    for (uint32_t b = lo; b < hi; ++b) sts8(addr + b, (v >> (8u * b)) & 0xffu);
-}
-/* One line of a record by one lane: the sequence line (QUAL = false: tab_s = the letter table of the record's strand) or
- * the quality line (QUAL = true: tab_s = the quality table), exactly its L bytes at D — the first and last word of a line
- * are stored byte by byte where they are partial.  All 32 lanes converged; T4 = groups of 4 bases the warp runs for.
- * `before_tail()` is called once, after the turns in which every lane stores whole words and before the rest. */
-template <bool QUAL, int QM, bool CB7, class F>
-__device__ __forceinline__ void line_lane(const RunParams &rp, uint32_t tab_s, bool on, bool rc, uint32_t D, Mwc1 &rng, uint64_t a, uint32_t L, uint32_t T4, F before_tail) {
-    if (!on) { L = 0; a = 0; }
-    const uint32_t o = D & 3u, sh = 8u * o;
-    const uint32_t n = on ? (L + o + 3u) >> 2 : 0u;                 /* word slots: slot k = characters 4k - o .. 4k - o + 3 */
-    const uint32_t tail = (L + o) & 3u;                              /* bytes in the last slot when it is partial */
-    uint32_t p = D - o, k = 0;                                       /* next slot and its address */
-    const int64_t bit = rc ? 2 * int64_t(a + L) - 32 : 2 * int64_t(a);
-    const uint32_t *pw = rp.packed + (bit >> 5);
-    const uint32_t s2 = uint32_t(bit) & 31u, rev = rc ? 0x0123u : 0x3210u;
-    uint32_t w_lo = 0, w_hi = 0;
-    if (!QUAL) { w_lo = __ldg(pw); w_hi = __ldg(pw + 1); pw += rc ? -1 : 2; }
-    const int32_t dw = rc ? -1 : 1;
-    const uint32_t mask = rp.phred_mult - 1u;
-    uint32_t prev = 0;
-    auto turn = [&](auto gc, auto whole, uint32_t it) {
-        constexpr uint32_t G = decltype(gc)::value;
-        constexpr bool WHOLE = decltype(whole)::value;
-        uint32_t X = 0;
-        if (!QUAL) {
-            X = __byte_perm(__funnelshift_r(w_lo, w_hi, s2), 0u, rev);
-            if (G == 4) { const uint32_t nw = __ldg(pw); pw += dw; const uint32_t keep = rc ? w_lo : w_hi; w_lo = rc ? nw : keep; w_hi = rc ? keep : nw; }
-        }
-        uint32_t c[G];
-#pragma unroll
-        for (uint32_t h = 0; h < G; ++h) {
-            const uint32_t w = QUAL ? quals4<QM, CB7>(rp, tab_s, mask, rng, 16u * it + 4u * h) : lds32(tab_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
-            c[h] = __funnelshift_l(prev, w, sh);
-            prev = w;
-        }
-        if (WHOLE) {
-            if (on) {
-#pragma unroll
-                for (uint32_t h = 0; h < G; ++h) sts32(p + 4u * h, c[h]);
-            }
-        } else {
-#pragma unroll
-            for (uint32_t h = 0; h < G; ++h) {
-                const uint32_t slot = k + h;
-                if (slot < n) {
-                    const uint32_t lo = slot == 0u ? o : 0u, hi = (slot + 1u == n && tail) ? tail : 4u;
-                    if (lo == 0u && hi == 4u) sts32(p + 4u * h, c[h]); else sts_bytes(p + 4u * h, c[h], lo, hi);
-                }
-            }
-        }
-        p += 4u * G; k += G;
-    };
-    const uint32_t full = (T4 - 1u) >> 2;
-    /* turns 1 .. whole - 1 store whole words in every lane that has a record: turn 0 holds slot 0, and a lane's last slot
-     * (partial or not) is left to the tests */
-    const uint32_t whole = min(full, __reduce_min_sync(0xffffffffu, on ? (n - 1u) >> 2 : 0xffffffffu));
-    turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, 0u);       /* T4 < 4: slots beyond n are not stored */
-    uint32_t it = 1;
-    if (full >= 1u) {
-        for (; it < whole; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::true_type{}, it);
-        before_tail();
-        for (; it < full; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, it);
-        turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, full);     /* four groups whatever the rest is: slots beyond a line's end are not stored */
-    } else before_tail();
-}
-
-constexpr int PAIR_THREADS = 1024;
-template <int QM>
-__global__ void __launch_bounds__(PAIR_THREADS, 1) k_format_pairs(RunParams rp) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp >> 1, npairs = blockDim.x >> 6;
-    const bool role_q = warp & 1u;
-    const uint32_t base_s = uint32_t(__cvta_generic_to_shared(smem));
-    const uint32_t qbytes = qtab_bytes(QM, rp.phred.cb, rp.phred.npos);
-    uint8_t *stage = smem + SM_QTAB + qbytes + pair * warp_region_bytes(rp.stage_cap) + STAGE_FRONT;
-    const uint32_t dec2_s = base_s + SM_DEC2, stage_s = uint32_t(__cvta_generic_to_shared(stage));
-    const uint32_t qtab_s = base_s + SM_QTAB + (QM == QM_LANE ? 4u * lane : 0u);
-    /* the pair's three mbarriers sit in the 48 spare bytes behind its stage (this kernel stores nothing outside a tile's image) */
-    const uint32_t mb_free = stage_s + rp.stage_cap + 16u, mb_hdr = mb_free + 8u, mb_qual = mb_free + 16u;
-    {   /* tables, as k_format_lanes */
-        uint32_t *qt = reinterpret_cast<uint32_t *>(smem + SM_QTAB);
-        if (QM == QM_LANE) for (uint32_t i = threadIdx.x; i < (32u << rp.phred.cb); i += blockDim.x) qt[i] = rp.phred.entries[i >> 5];
-        if (QM == QM_POS) for (uint32_t i = threadIdx.x; i < (rp.phred.npos << rp.phred.cb); i += blockDim.x) qt[i] = rp.phred.entries[i];
-        if (rp.phred.has_sub) {
-            for (uint32_t i = threadIdx.x; i < GAP_COLS; i += blockDim.x) reinterpret_cast<uint32_t *>(smem + SM_GAP)[i] = rp.phred.gap[i];
-            for (uint32_t i = threadIdx.x; i < rp.phred_mult; i += blockDim.x) reinterpret_cast<uint32_t *>(smem + SM_QSUB)[i] = rp.phred.qsub[i];
-        }
-        for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) {
-            uint32_t f = 0, r = 0;
-            for (uint32_t j = 0; j < 4; ++j) {
-                const uint32_t c = (b >> (2 * j)) & 3u;
-                f |= ((0x54474341u >> (8 * c)) & 0xffu) << (8 * j);
-                r |= ((0x41434754u >> (8 * c)) & 0xffu) << (8 * (3 - j));
-            }
-            reinterpret_cast<uint32_t *>(smem + SM_LUT_FWD)[b] = f;
-            reinterpret_cast<uint32_t *>(smem + SM_LUT_RC)[b] = r;
-            if (b < 100) reinterpret_cast<uint16_t *>(smem + SM_DEC2)[b] = uint16_t(('0' + b / 10) | (('0' + b % 10) << 8));
-            if (b < 10) { uint32_t p = 1; for (uint32_t k = 0; k < b; ++k) p *= 10u; reinterpret_cast<uint32_t *>(smem + SM_DEC2 + 200)[b] = p; }
-        }
-        if (lane < 3u && !role_q) mbar_init(mb_free + 8u * lane, 1u);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-
-    const uint32_t mate = lane & 1u, slot = lane >> 1;
-    const uint32_t ntiles = (rp.batch_units + WARP_UNITS - 1) / WARP_UNITS;
-    uint32_t round = 0;                                                /* sub-tiles this pair has done: the mbarriers' phase */
-    for (uint32_t tile = blockIdx.x * npairs + pair; tile < ntiles; tile += gridDim.x * npairs) {
-        const uint32_t t0 = tile * WARP_UNITS, tn = min(WARP_UNITS, rp.batch_units - t0);
-        const uint32_t tile_next = tile + gridDim.x * npairs;
-        if (!role_q && tile_next < ntiles) {                           /* the next tile's offsets and descriptors towards L2 */
-            const uint32_t t1 = tile_next * WARP_UNITS;
-            if (lane < 2) prefetch_l2(rp.offsets + t1 + 16u * lane);
-            else if (lane < 6) prefetch_l2(reinterpret_cast<const uint8_t *>(rp.desc + t1) + 128u * (lane - 2u));
-        }
-        for (uint32_t s0 = 0; s0 < tn; ++round) {
-            /* both warps lay the sub-tile out the same way: the longest run of units from s0 that fits the stage */
-            const uint32_t u0 = t0 + s0, left = tn - s0;
-            const uint64_t off = lane <= left ? __ldg(rp.offsets + u0 + lane) : 0;
-            const uint64_t tile_base = __shfl_sync(0xffffffffu, off, 0), next = __shfl_down_sync(0xffffffffu, off, 1);
-            const uint32_t pad = uint32_t(tile_base & 15);
-            const uint32_t nu = __popc(__ballot_sync(0xffffffffu, lane < left && next - tile_base + pad <= rp.stage_cap));
-            const uint32_t total = uint32_t(__shfl_sync(0xffffffffu, off, nu) - tile_base);
-            const uint32_t unit_off = pad + uint32_t(__shfl_sync(0xffffffffu, off, slot) - tile_base);
-            const bool mine = slot < nu;
-            UnitDesc d{};
-            if (mine) d = load_unit(rp, u0 + slot);
-            const bool have = mine && (mate == 0 || (d.flags & 4u));
-            const uint32_t L = mate ? d.L1 : d.L0, H = mate ? d.H1 : d.H0;
-            const uint64_t a = mate ? d.a1 : d.a0;
-            const uint32_t rec = unit_off + (mate ? d.H0 + 2u * d.L0 + 5u : 0u);
-            const bool odd = have && ((d.flags & 8u) || H < 2u || L < 4u);
-            const bool words_ok = !__any_sync(0xffffffffu, odd);
-            const bool hdr_fast = words_ok && rp.hdr_fast != 0;
-            const bool fast = have && words_ok && !(d.flags & (1u << mate));
-            const uint64_t unit = rp.batch_begin + u0 + slot;
-            const uint32_t body_s = stage_s + rec + H;
-            const uint32_t T4 = __reduce_max_sync(0xffffffffu, fast ? (L + 3u + 3u) >> 2 : 0u);
-            const uint32_t phase = round & 1u;
-            if (role_q) {
-                /* ---- Q: the quality lines ---- */
-                Mwc1 qc{}, ec{};
-                if (T4) mwc1_seed(rp, qc, ec, 0u, 1u + mate, uint32_t(unit), uint32_t(unit >> 32));
-                mbar_wait(mb_free, phase);
-                if (T4) {
-                    auto hold = [&]() { mbar_wait(mb_hdr, phase); };
-                    if (QM == QM_LANE && rp.phred.cb == 7u) line_lane<true, QM, true>(rp, qtab_s, fast, mate != 0, body_s + L + 4u, qc, a, L, T4, hold);
-                    else line_lane<true, QM, false>(rp, qtab_s, fast, mate != 0, body_s + L + 4u, qc, a, L, T4, hold);
-                } else mbar_wait(mb_hdr, phase);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(mb_qual);
-            } else {
-                /* ---- S: headers, fixed bytes, sequence lines, substitutions, the tile's way out ---- */
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     /* the previous bulk copy has read the stage */
-                __syncwarp();
-                if (lane == 0) mbar_arrive(mb_free);
-                if (have) {
-                    uint64_t sp, ep; record_positions(d, mate, sp, ep);
-                    const uint32_t id = rp.read_id_base + uint32_t(unit);
-                    const uint32_t rec_s = stage_s + rec;
-                    const ContigHdr ch = hdr_at(rp, d.contig, mate);
-                    if (hdr_fast) {
-                        ByteStream b; bs_open(b, rec_s - 1u); bs_put(b, '\n', 1);
-                        header_tokens(b, rp, dec2_s, reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off), rp.hdr_kinds, rp.hdr_fields, id, uint32_t(sp), uint32_t(ep));
-                        bs_put(b, '\n', 1); bs_close(b);
-                    } else {
-                        emit_header(stage + rec, rp, ch, id, sp, ep);
-                        sts8(rec_s + H, '\n');
-                        if (rec > pad) sts8(rec_s - 1u, '\n');
-                    }
-                    const uint32_t mid = rec_s + H + L + 1u;                      /* fastq.rs:61-69 */
-                    sts8(mid, '\n'); sts8(mid + 1u, '+'); sts8(mid + 2u, '\n');
-                }
-                if (lane == 31 && total) sts8(stage_s + pad + total - 1u, '\n');
-                __syncwarp();
-                if (lane == 0) mbar_arrive(mb_hdr);
-                if (T4) {
-                    Mwc1 none{};
-                    const uint32_t lut_s = base_s + (mate ? SM_LUT_RC : SM_LUT_FWD);
-                    line_lane<false, QM, false>(rp, lut_s, fast, mate != 0, body_s + 1u, none, a, L, T4, [] {});
-                }
-                if (have && !fast) emit_body_pieces<false>(rp, stage + rec + H, unit, mate, a, L, 0, 1);     /* windows holding anything but A,C,G,T: bytes, qualities included */
-                mbar_wait(mb_qual, phase);
-                if (T4 && rp.phred.has_sub) {
-                    Mwc1 qc{}, ec{};
-                    mwc1_seed(rp, qc, ec, 0u, 1u + mate, uint32_t(unit), uint32_t(unit >> 32));
-                    substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                const uint32_t head = min(total, (16 - pad) & 15), mid = (total - head) & ~15u, tail = total - head - mid;
-                if (lane == 0 && mid) {
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rp.out + tile_base + head), "r"(stage_s + pad + head), "r"(mid) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                if (lane >= 1 && lane < 1 + head) rp.out[tile_base + (lane - 1)] = stage[pad + (lane - 1)];
-                if (lane >= 16 && lane < 16 + tail) rp.out[tile_base + head + mid + (lane - 16)] = stage[pad + head + mid + (lane - 16)];
-            }
-            s0 += nu;
-        }
-    }
-    if (!role_q && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
 
 /* One CTA per unit, bytes written straight to global memory with byte stores: replay of long reads, records that do not
  * fit a stage, and native long reads behind SIMMR_NO_LONG_KERNEL.  Not a fast path. */

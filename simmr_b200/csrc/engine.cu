@@ -182,8 +182,6 @@ FormatKernel lanes_kernel(bool replay, int qm) {
     default: return k_format_lanes<false, QM_CONST>;
     }
 }
-using PairKernel = void (*)(RunParams);
-PairKernel pairs_kernel(int qm) { return qm == QM_LANE ? k_format_pairs<QM_LANE> : k_format_pairs<QM_POS>; }
 FormatKernel direct_kernel(bool replay) { return replay ? k_format_direct<true> : k_format_direct<false>; }
 using LongKernel = void (*)(RunParams);
 LongKernel long_kernel(int qm, uint32_t cb) {
@@ -194,7 +192,6 @@ LongKernel long_kernel(int qm, uint32_t cb) {
 struct Plan {      /* launch geometry for one run */
     bool tiles = false;            /* warp-private stages in shared memory (short reads) vs one CTA per unit */
     bool lanes = false;            /* long reads, native mode: one lane per run (k_format_long) */
-    bool pairs = false;            /* short reads, sampled qualities: two warps per tile (k_format_pairs) */
     uint32_t stage_cap = 0, max_unit_bytes = 0, threads = 0;
     size_t smem = 0;
     int grid = 0;
@@ -222,9 +219,6 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
         else {
             const uint64_t cap = std::min<uint64_t>(uint64_t(cap_for(warps)), WARP_UNITS * need);
             pl.stage_cap = uint32_t(cap); pl.threads = warps * 32; pl.smem = lanes_smem(m, warps, uint32_t(cap));
-            const char *pe = getenv("SIMMR_PAIRS");
-            pl.pairs = !replay && quality_mode(m) != QM_CONST && pe && !strcmp(pe, "1");   /* experiment, slower than one warp per tile (profiles/r02_experiment_warp_pairs_*) */
-            if (pl.pairs) pl.threads *= 2;
         }
     }
     int occ = 0;
@@ -237,15 +231,9 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
     } else {
         if (!pl.tiles) { pl.smem = 0; pl.threads = DIRECT_THREADS; }
-        if (pl.pairs) {
-            PairKernel k = pairs_kernel(quality_mode(m));
-            CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
-        } else {
-            FormatKernel k = pl.tiles ? lanes_kernel(replay, quality_mode(m)) : direct_kernel(replay);
-            CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
-        }
+        FormatKernel k = pl.tiles ? lanes_kernel(replay, quality_mode(m)) : direct_kernel(replay);
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, int(pl.threads), pl.smem));
     }
     if (occ < 1) return fail(ctx, SIMMR_E_LIMIT, "format kernel does not fit on an SM");
     pl.grid = occ * ctx->prop.multiProcessorCount;
@@ -487,10 +475,9 @@ struct Runner {
         if (guard) CU(cudaMemsetAsync(ctx->d_out[dslot].p, 0xA5, out_cap, ctx->compute));
         CU(cudaEventRecord(ev[EV_F0 + k], ctx->compute));
         if (pl.tiles) {
-            const uint32_t wpc = pl.threads / (pl.pairs ? 64 : 32), nctas = ((n + WARP_UNITS - 1) / WARP_UNITS + wpc - 1) / wpc;
+            const uint32_t wpc = pl.threads / 32, nctas = ((n + WARP_UNITS - 1) / WARP_UNITS + wpc - 1) / wpc;
             const int grid = int(std::min<uint32_t>(nctas, uint32_t(pl.grid)));
-            if (pl.pairs) pairs_kernel(quality_mode(ctx->model))<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp);
-            else lanes_kernel(replay, quality_mode(ctx->model))<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
+            lanes_kernel(replay, quality_mode(ctx->model))<<<grid, pl.threads, pl.smem, ctx->compute>>>(rp, rd);
         } else if (pl.lanes) {
             CU(cudaMemsetAsync(rp.counters + 4, 0, 8, ctx->compute));       /* the kernel's piece counter */
             long_kernel(quality_mode(ctx->model), ctx->model.cb)<<<pl.grid, pl.threads, pl.smem, ctx->compute>>>(rp);
