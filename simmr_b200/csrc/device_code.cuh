@@ -398,6 +398,38 @@ __device__ uint32_t emit_header(uint8_t *dst, const RunParams &rp, const ContigH
     return n;
 }
 
+/* The same header by a whole warp (k_format_long: one record per warp at a time, and lane 0 writing it byte by byte,
+ * one dependent load after the other, was 15 % of that kernel).  Lane t sizes token t, a scan places the tokens, then every
+ * lane renders bytes lane, lane + 32, ... of the header: a literal's byte from the pool, a field's digit by division.
+ * False (nothing written) for what it does not cover — more than 32 tokens, a position beyond 2^32. */
+__device__ __forceinline__ bool emit_header_warp(uint8_t *dst, const RunParams &rp, const ContigHdr &ch, uint32_t id, uint64_t sp, uint64_t ep, uint32_t lane) {
+    const uint32_t ntok = ch.ntok;
+    if (ntok > 32u || ((sp | ep) >> 32)) return false;
+    uint32_t type = TOK_LIT, off = 0, len = 0, val = 0;
+    if (lane < ntok) {
+        const uint2 k = __ldg(reinterpret_cast<const uint2 *>(rp.toks + ch.tok_off) + lane);      /* {off, len | type << 16} */
+        type = (k.y >> 16) & 0xffu; off = k.x;
+        if (type == TOK_LIT) len = k.y & 0xffffu;
+        else { val = type == TOK_READ_ID ? id : type == TOK_START ? uint32_t(sp) : uint32_t(ep); len = dec_digits32(val); }
+    }
+    uint32_t end = len;
+#pragma unroll
+    for (uint32_t o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, end, o); if (lane >= o) end += y; }
+    const uint32_t start = end - len, H = __shfl_sync(0xffffffffu, end, 31);
+    for (uint32_t p0 = 0; p0 < H; p0 += 32u) {
+        const uint32_t pos = p0 + lane;
+        uint32_t t = 0;                                     /* the token holding byte pos: as many tokens end at or before it */
+        for (uint32_t i = 0; i + 1u < ntok; ++i) t += __shfl_sync(0xffffffffu, end, i) <= pos ? 1u : 0u;
+        const uint32_t ts = __shfl_sync(0xffffffffu, start, t), tl = __shfl_sync(0xffffffffu, len, t), ty = __shfl_sync(0xffffffffu, type, t);
+        const uint32_t to = __shfl_sync(0xffffffffu, off, t), tv = __shfl_sync(0xffffffffu, val, t);
+        if (pos < H) {
+            const uint32_t idx = pos - ts;
+            dst[pos] = ty == TOK_LIT ? __ldg(rp.pool + to + idx) : uint8_t('0' + (tv / POW10[tl - 1u - idx]) % 10u);
+        }
+    }
+    return true;
+}
+
 /* ---------------------------------------------------------------------- */
 /* per-base work, generic (any byte values, replay, long reads)             */
 /* ---------------------------------------------------------------------- */
@@ -1414,9 +1446,13 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
         const uint64_t unit = rp.batch_begin + i;
         uint8_t *rec = rp.out + rp.offsets[i];
         const bool bytes_path = (d.flags & 9u) || L < 4u;
-        if (lane == 0) {                                  /* header and the five fixed bytes (fastq.rs:34-69) */
-            emit_header(rec, rp, hdr_at(rp, d.contig, 0), rp.read_id_base + uint32_t(unit), d.p0, d.p1);
-            rec[H] = '\n'; rec[H + Ls + 1] = '\n'; rec[H + Ls + 2] = '+'; rec[H + Ls + 3] = '\n'; rec[H + Ls + L + 4] = '\n';
+        {                                                 /* header and the five fixed bytes (fastq.rs:34-69) */
+            const ContigHdr &ch = hdr_at(rp, d.contig, 0);
+            const bool done = emit_header_warp(rec, rp, ch, rp.read_id_base + uint32_t(unit), d.p0, d.p1, lane);
+            if (lane == 0) {
+                if (!done) emit_header(rec, rp, ch, rp.read_id_base + uint32_t(unit), d.p0, d.p1);
+                rec[H] = '\n'; rec[H + Ls + 1] = '\n'; rec[H + Ls + 2] = '+'; rec[H + Ls + 3] = '\n'; rec[H + Ls + L + 4] = '\n';
+            }
         }
         if (bytes_path) {
             if (rp.err.on) emit_body_pieces<false>(rp, rec + H, unit, 0, d.a0, L, lane, 32, Ls, !(d.flags & 1u));

@@ -215,6 +215,12 @@ int make_plan(simmr_ctx *ctx, bool replay, Plan &pl) {
         uint32_t warps = FORMAT_THREADS / 32;
         if (const char *e = getenv("SIMMR_WARPS")) warps = uint32_t(std::max(1, std::min(FORMAT_THREADS / 32, atoi(e))));
         while (warps > 1 && cap_for(warps) < int64_t(need)) --warps;
+        /* A stage should hold a whole tile — WARP_UNITS units of typical size (nominal read length, header positions with
+         * the digits of the contigs' sizes) and 5 % more: a tile that does not fit is cut in two, and its second part runs
+         * with most lanes idle.  Large per-position quality tables (NovaSeq: 38 KB) are paid for with warps, not with tiles. */
+        const uint64_t typ_unit = (uint64_t(ctx->plan.hdr_typ) + 2ull * m.nominal_read_len + 5) * 2;
+        const int64_t want = int64_t(std::min<uint64_t>(WARP_UNITS * need, WARP_UNITS * typ_unit * 21 / 20 + 32));
+        while (warps > 8 && cap_for(warps) < want) --warps;
         if (cap_for(warps) < int64_t(need)) pl.tiles = false;   /* a single unit does not fit: direct path */
         else {
             const uint64_t cap = std::min<uint64_t>(uint64_t(cap_for(warps)), WARP_UNITS * need);
