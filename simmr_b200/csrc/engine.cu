@@ -254,6 +254,7 @@ int ensure_headers(simmr_ctx *ctx, const char *fmt) {
     std::string err;
     int rc = compile_headers(ctx->host_view, f.c_str(), ctx->plan, err);
     if (rc) return fail(ctx, rc, err);
+    if (ctx->plan.hdr_cap > 65535u) return fail(ctx, SIMMR_E_LIMIT, "a read header could exceed 65535 bytes");      /* UnitRec keeps header lengths in 16 bits */
     {   /* device image: block i = 2 * contig + mate of `stride` bytes holds the ContigHdr, its tokens and their literals
          * (literals on 4-byte boundaries, the kernel fetches them by words); token offsets become absolute */
         const HeaderPlan &hp = ctx->plan;
@@ -317,7 +318,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.is = LenTab{m.is.kind, m.is.value, m.is.cb, 0, ctx->d_is_e.as<uint32_t>(), ctx->d_is_lo.as<uint32_t>(), ctx->d_is_hi.as<uint32_t>()};
     rp.gamma = m.gamma;
     rp.min_size = m.min_size; rp.is_long = m.is_long; rp.flags = m.flags; rp.phred_mult = 1u << m.cb;
-    if (const char *e = getenv("SIMMR_DBG")) rp.flags |= uint32_t(atoi(e)) << 8; rp.mutates = m.mutates;
+    rp.mutates = m.mutates;
     for (uint32_t r = 0; r < 10; ++r) { rp.rk[2 * r] = uint32_t(seed) + r * 0x9E3779B9u; rp.rk[2 * r + 1] = uint32_t(seed >> 32) + r * 0xBB67AE85u; }
     rp.counters = ctx->d_counters.as<unsigned long long>();
     rp.stage_cap = pl.stage_cap; rp.one = 1;
@@ -715,6 +716,12 @@ int simmr_genomes_load(simmr_ctx *ctx, const simmr_genome_set *s) {
     for (uint32_t c = 0; c < s->n_contigs; ++c)
         if (ctx->h_contig_off[c + 1] < ctx->h_contig_off[c]) return fail(ctx, SIMMR_E_INVALID, "contig offsets must be non-decreasing");
     if (ctx->h_genome_contig.back() != s->n_contigs) return fail(ctx, SIMMR_E_INVALID, "genome_contig does not cover all contigs");
+    /* the kernels index with these tables unchecked */
+    if (ctx->h_genome_contig.front() != 0) return fail(ctx, SIMMR_E_INVALID, "genome_contig must start at 0");
+    for (uint32_t g = 0; g < s->n_genomes; ++g)
+        if (ctx->h_genome_contig[g + 1] < ctx->h_genome_contig[g]) return fail(ctx, SIMMR_E_INVALID, "genome_contig must be non-decreasing");
+    for (uint32_t c = 0; c < s->n_contigs; ++c)
+        if (ctx->h_contig_size[c] > ctx->h_contig_off[c + 1] - ctx->h_contig_off[c]) return fail(ctx, SIMMR_E_INVALID, "a contig's size exceeds its span in bases");
     simmr_genome_set &v = ctx->host_view;
     v = *s; v.bases = nullptr;
     v.contig_off = ctx->h_contig_off.data(); v.contig_size = ctx->h_contig_size.data(); v.genome_contig = ctx->h_genome_contig.data();
@@ -843,6 +850,10 @@ int simmr_replay(simmr_ctx *ctx, const simmr_draws *d, const simmr_run_opts *opt
         if (d->contig[u] >= ctx->h_genome_contig[g + 1] - ctx->h_genome_contig[g]) return fail(ctx, SIMMR_E_INVALID, "replay: contig index out of range");
     }
     const uint64_t nslots = d->base_off[n];
+    for (uint64_t u = 0; u < n; ++u) {      /* a unit reads rl draw slots per record from base_off[u] on */
+        if (d->base_off[u + 1] < d->base_off[u]) return fail(ctx, SIMMR_E_INVALID, "replay: base_off must be non-decreasing");
+        if (d->base_off[u + 1] - d->base_off[u] < uint64_t(d->read_length[u]) * (m.is_long ? 1 : 2)) return fail(ctx, SIMMR_E_INVALID, "replay: a unit has fewer draw slots than bases");
+    }
     if (m.replay_kind == RP_NORMAL_FLOOR || m.replay_kind == RP_ACCURACY) { if (!d->phred_z) return fail(ctx, SIMMR_E_INVALID, "replay needs phred_z for this profile"); }
     if (m.replay_kind == RP_ALIAS && (!d->phred_cand || !d->phred_u || !d->phred_inbin)) return fail(ctx, SIMMR_E_INVALID, "replay needs phred_cand/phred_u/phred_inbin for custom profiles");
     if (m.mutates && (!d->mut_u || !d->mut_k)) return fail(ctx, SIMMR_E_INVALID, "replay needs mut_u/mut_k for this profile");

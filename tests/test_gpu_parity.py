@@ -258,6 +258,29 @@ def test_too_small_contig_is_an_error(engine):
     assert e.value.code == S._native.E_TOO_SMALL
 
 
+def test_malformed_tables_are_refused(engine):
+    """Inputs the kernels would index with unchecked: a genome_contig table that runs backwards, a contig larger than
+    its span, replay draws with fewer slots than bases."""
+    gs = H.synth_genomes(3, (2, 2), (3000, 4000), seed=5)
+    bad = S.GenomeSet(gs.bases, gs.contig_off, gs.contig_size, [0, 4, 2, 6], gs.contig_ids, gs.contig_id_off, gs.genome_ids, gs.genome_id_off)
+    with pytest.raises(S.SimmrError) as e:
+        engine.load_genomes(bad)
+    assert e.value.code == S._native.E_INVALID
+    sizes = gs.contig_size.copy(); sizes[1] += 1
+    bad = S.GenomeSet(gs.bases, gs.contig_off, sizes, gs.genome_contig, gs.contig_ids, gs.contig_id_off, gs.genome_ids, gs.genome_id_off)
+    with pytest.raises(S.SimmrError) as e:
+        engine.load_genomes(bad)
+    assert e.value.code == S._native.E_INVALID
+    prof = S.MinimalShortErrorProfile(150, 150, 30)
+    engine.load_genomes(gs)
+    engine.set_error_profile(prof)
+    d = H.make_pe_draws(gs, prof, 50, seed=3)
+    d["base_off"] = d["base_off"].copy(); d["base_off"][10:] -= 7          # unit 9 is left with too few slots
+    with pytest.raises(S.SimmrError) as e:
+        engine.replay_bytes(S.Draws(**d))
+    assert e.value.code == S._native.E_INVALID
+
+
 def test_medium_scale_minimal_short(engine):
     """~1.2 M records through several batches, compared byte for byte."""
     gs = H.synth_genomes(6, (1, 6), (20000, 120000), seed=77)
