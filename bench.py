@@ -193,6 +193,14 @@ def workload_config(world):
             "l2": "inputs (~500 MB genomes) and outputs (~38 GB FASTQ per step) both exceed the 126 MB L2: no flush needed"}
 
 
+_T0 = time.perf_counter()
+
+
+def note(msg):
+    """progress on stderr (the JSON line on stdout stays alone)"""
+    print(f"[bench {time.perf_counter() - _T0:7.1f} s] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,6 +233,7 @@ def main():
         torch.cuda.synchronize()
 
     rpg = args.reads_per_gpu
+    note("building the C2 genome set")
     gs = c2_genomes()
     reads, _ = S.UniformAbundanceProfile().determine_abundances(rpg * world, N_GENOMES)   # a1: ceil(total/n)
     eng = S.Engine(local)
@@ -249,6 +258,7 @@ def main():
         seen[1] += 1
         return 0
 
+    note("genomes resident; device-resident steps")
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(args.warmup):
@@ -279,6 +289,7 @@ def main():
     # the format kernel by itself: the library normally prepares batch b+1 (geometry, sizes, offsets, size-sorted tiles) on a
     # second stream beside batch b's format kernel, which shares the SMs; one extra untimed step with everything on one
     # stream gives the kernel's duration without co-runners (reported next to the figure of the timed region)
+    note("timed region done; one step with every kernel on one stream")
     os.environ["SIMMR_PREP_SERIAL"] = "1"
     st = eng.simulate(reads, SEED, unit_begin=ub, unit_end=ue)
     del os.environ["SIMMR_PREP_SERIAL"]
@@ -286,6 +297,7 @@ def main():
     alone_launches = max(1, n_format_launches // max(1, args.steps))
 
     # end to end: host genome buffers -> device, FASTQ bytes -> pinned host -> the sink (library writer thread), inside the timed region
+    note("end-to-end steps (host buffers)")
     e2e_bases = e2e_d2h = 0
     if args.e2e_steps:      # untimed: the pinned output ring is allocated on the first call that has a sink
         eng.simulate(reads, SEED, unit_begin=ub, unit_end=min(ue, ub + 2_000_000), sink=lambda a, f, n: 0)
@@ -305,8 +317,11 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX); dist.all_reduce(tb, op=dist.ReduceOp.SUM)
     e2e_value = float(tb[0]) / float(te[0]) / 1e9 if args.e2e_steps else None
 
+    note("strong-scaling record (C5)")
     strong = strong_scaling(S, eng, torch, dist, barrier, rank, world) if not args.no_strong else None
+    note("FASTQ to file")
     to_file = fastq_to_file(S, gs, local) if (rank == 0 and not args.no_to_file) else None
+    note("CPU baseline")
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
