@@ -2,9 +2,11 @@
 # the round's evidence in one GPU call: full GPU test suite, the bench line (both arms), the ncu launch list of the bench
 # command and one `ncu --set full` capture each of the three format kernels (after their commands' own clean runs)
 cd "$(dirname "$0")/.."
+if [ "$1" != "notests" ]; then
 timeout 1700 python -m pytest tests -q -m gpu --timeout 500 -o faulthandler_timeout=450 --durations=8 > gpurun_out/r02_final_tests.log 2>&1
 tail -14 gpurun_out/r02_final_tests.log
-timeout 600 python bench.py > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err || { tail -5 gpurun_out/r02_bench_final.err; exit 1; }
+fi
+timeout 900 python bench.py > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err || { tail -5 gpurun_out/r02_bench_final.err; }
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_final_ref.json 2> gpurun_out/r02_bench_final_ref.err
 ARGS="--steps 2 --warmup 1 --e2e-steps 0 --no-strong --no-to-file --no-cpu-baseline"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv python bench.py $ARGS > gpurun_out/r02_ncu_launches.log 2>&1

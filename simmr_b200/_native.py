@@ -46,6 +46,7 @@ class RunOpts(C.Structure):
 
 
 RUN_EXPLICIT_RANGE = 1
+SINK_RETAINED = 2           # a sink's return value: it keeps the chunk and gives it back with simmr_chunk_release
 
 
 class Stats(C.Structure):

@@ -337,25 +337,26 @@ enum : int { EV_START = 0, EV_STOP = 1, EV_F0 /* 2 */ = 2, EV_F1 /* 2 */ = 4, EV
 
 /* A finished batch on its way from a launch thread to the writer thread. */
 struct Ready { int slot; const uint8_t *data; uint64_t bytes, first, units; cudaEvent_t copied; };
-/* Launch thread -> writer thread hand-off of one context: the RING pinned buffers are used round-robin, so "how many are
- * free" is all the producer needs to know.  A failing sink makes the writer raise `abort`; it keeps releasing buffers
- * so that the producer never blocks, and the producer stops at its next batch. */
+/* Launch thread -> writer thread hand-off of one context: the RING pinned buffers are used round-robin, and a sink that
+ * retains chunks may give them back in any order, so the producer waits for the very buffer it is about to fill.  A
+ * failing sink makes the writer raise `abort`; it keeps releasing buffers so that the producer never blocks, and the
+ * producer stops at its next batch. */
 struct BatchQueue {
     std::mutex m; std::condition_variable cv;
     std::deque<Ready> q;
-    int free_slots = RING, retained = 0; bool closed = false;      /* retained: chunks a sink kept (SIMMR_SINK_RETAINED) and has not given back */
+    bool busy[RING] = {}; int retained = 0; bool closed = false;   /* retained: chunks a sink kept (SIMMR_SINK_RETAINED) and has not given back */
     std::atomic<bool> abort{false};
-    bool acquire() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return free_slots > 0; }); --free_slots; return !abort.load(); }
+    bool acquire(int slot) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !busy[slot]; }); busy[slot] = true; return !abort.load(); }
     void push(const Ready &r) { { std::lock_guard<std::mutex> l(m); q.push_back(r); } cv.notify_all(); }
     void close() { { std::lock_guard<std::mutex> l(m); closed = true; } cv.notify_all(); }
     bool pop(Ready &r) { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return !q.empty() || closed; }); if (q.empty()) return false; r = q.front(); q.pop_front(); return true; }
-    void release(bool was_retained = false) { { std::lock_guard<std::mutex> l(m); ++free_slots; if (was_retained) --retained; } cv.notify_all(); }
+    void release(int slot, bool was_retained = false) { { std::lock_guard<std::mutex> l(m); busy[slot] = false; if (was_retained) --retained; } cv.notify_all(); }
     void retain() { std::lock_guard<std::mutex> l(m); ++retained; }
     void wait_all_released() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return retained == 0; }); }
 };
 /* chunks a sink retained (SIMMR_SINK_RETAINED): pinned buffer -> the queue that gets it back */
 std::mutex g_retained_mu;
-std::map<const void *, BatchQueue *> g_retained;
+std::map<const void *, std::pair<BatchQueue *, int>> g_retained;      /* ... and the buffer's place in that queue's ring */
 /* The writer thread: batches leave in file order — batch j comes from queue j % n — and the sink sees them one at a
  * time.  Returns false if the sink failed. */
 bool write_batches(const std::vector<BatchQueue *> &qs, const std::vector<int> &devices, simmr_sink_fn sink, void *user) {
@@ -371,7 +372,7 @@ bool write_batches(const std::vector<BatchQueue *> &qs, const std::vector<int> &
         const bool copied = cudaEventSynchronize(r.copied) == cudaSuccess;
         int verdict = 1;
         if (ok && copied) {
-            { std::lock_guard<std::mutex> l(g_retained_mu); g_retained[r.data] = qs[g]; }      /* before the sink can pass it on */
+            { std::lock_guard<std::mutex> l(g_retained_mu); g_retained[r.data] = {qs[g], r.slot}; }      /* before the sink can pass it on */
             qs[g]->retain();                                   /* counted before the sink can release it from another thread */
             verdict = sink(user, r.data, r.bytes, r.first, r.units);
             if (verdict != SIMMR_SINK_RETAINED) {
@@ -381,7 +382,7 @@ bool write_batches(const std::vector<BatchQueue *> &qs, const std::vector<int> &
             }
         }
         if (ok && verdict != 0 && verdict != SIMMR_SINK_RETAINED) { ok = false; for (BatchQueue *q : qs) q->abort.store(true); }
-        if (verdict != SIMMR_SINK_RETAINED) qs[g]->release();
+        if (verdict != SIMMR_SINK_RETAINED) qs[g]->release(r.slot);
     }
     return ok;
 }
@@ -555,7 +556,7 @@ int produce(Runner &R, uint64_t j0, uint64_t stride, BatchQueue *q, simmr_stats 
         const int k = int(seq & 1), dslot = (q || dev_sink) ? int(seq & 1) : 0, slot = int(seq % RING);
         if (!R.ahead()) { rc = R.prepare(u, k); if (rc) return rc; }
         if (R.measure_only) continue;                          /* geometry, sizes (and edits) only: what the units occupy in the FASTQ stream */
-        if (q && !q->acquire()) return fail(ctx, SIMMR_E_SINK, "sink callback failed");      /* a pinned buffer is free again */
+        if (q && !q->acquire(slot)) return fail(ctx, SIMMR_E_SINK, "sink callback failed");      /* this batch's pinned buffer is free again */
         if (R.ahead() && j + stride < nbatches) { rc = R.prepare(start_of(j + stride), k ^ 1); if (rc) return rc; }
         CU(cudaStreamWaitEvent(ctx->compute, ev[EV_PREP + k], 0));
         if (q || dev_sink) {      /* the batch's byte count, on its way to the host before the format kernel starts */
@@ -653,8 +654,9 @@ extern "C" {
 const char *simmr_last_error(const simmr_ctx *ctx) { return ctx ? ctx->err.c_str() : last_error_slot().c_str(); }
 void simmr_chunk_release(const uint8_t *data) {
     BatchQueue *q = nullptr;
-    { std::lock_guard<std::mutex> l(g_retained_mu); auto it = g_retained.find(data); if (it != g_retained.end()) { q = it->second; g_retained.erase(it); } }
-    if (q) q->release(true);
+    int slot = 0;
+    { std::lock_guard<std::mutex> l(g_retained_mu); auto it = g_retained.find(data); if (it != g_retained.end()) { q = it->second.first; slot = it->second.second; g_retained.erase(it); } }
+    if (q) q->release(slot, true);
 }
 const char *simmr_version(void) { return "simmr_b200 0.1 (sm_100a)"; }
 

@@ -406,6 +406,52 @@ def test_cli_output_parts(engine, tmp_path):
         assert got == want[p], first_diff(got, want[p])
 
 
+def test_retained_chunks_released_out_of_order(engine):
+    """A sink that keeps its chunks (SIMMR_SINK_RETAINED) may give them back in any order and from any thread — the
+    command line's part files do.  The ring's buffers are filled round-robin, so the launch thread has to wait for the very
+    buffer it is about to fill: with a count of free buffers instead, a run of many chunks overwrote a chunk still in use
+    and then waited for ever."""
+    import ctypes
+    import threading
+    gs = H.synth_genomes(2, (1, 2), (3000, 6000), seed=31)
+    prof = S.MinimalShortErrorProfile(150, 150, 30)
+    engine.load_genomes(gs)
+    engine.set_error_profile(prof)
+    reads = [3000, 3000]
+    lib = S._native.lib()
+    import time
+    got, held, lock, done, last_put = {}, [], threading.Lock(), threading.Event(), [time.time()]
+
+    def releaser():                      # gives back the newest of the chunks it holds, so that the oldest waits longest;
+        while not (done.is_set() and not held):          # when nothing new arrives (the run waits for its chunks) it lets go
+            with lock:
+                ptr = held.pop() if (len(held) >= 3 or (held and time.time() - last_put[0] > 0.05)) else None
+            if ptr is not None:
+                lib.simmr_chunk_release(ctypes.c_void_p(ptr))
+            else:
+                done.wait(0.001)
+
+    def sink(a, first, n):
+        got[first] = a.tobytes()
+        with lock:
+            held.append(a.ctypes.data)
+            last_put[0] = time.time()
+        return S._native.SINK_RETAINED
+
+    th = threading.Thread(target=releaser, daemon=True)
+    th.start()
+    runner = threading.Thread(target=lambda: engine.simulate(reads, 9, sink=sink, batch_units=40), daemon=True)
+    runner.start()
+    runner.join(120)
+    finished = not runner.is_alive()
+    done.set()
+    th.join(10)
+    assert finished, "the run did not return: a retained chunk was lost"
+    want = po.simulate(po.Genomes.from_set(gs), H.oracle_profile(prof), reads, 9)
+    data = b"".join(got[k] for k in sorted(got))
+    assert data == want, first_diff(data, want)
+
+
 def test_full_size_c2_properties(engine):
     """BASELINE config C2 at its full size (100 M reads, 100 genomes, ~0.5 GB): size-independent properties of
     the whole run, and byte parity with the oracle on slices taken far into it (64-bit offsets, batch seams)."""
