@@ -362,6 +362,10 @@ def main():
     watchdog.daemon = True
     watchdog.start()
     note("strong-scaling record (C5)")
+    copy_peak = d2h_copy_rate(torch, dist, barrier) if args.e2e_steps else None
+    if out is not None and copy_peak is not None:      # what the box gives a plain device -> pinned-host copy on all ranks at once
+        out["e2e"]["d2h_copy_gbs_all_ranks"] = copy_peak
+        out["e2e"]["d2h_gbs_achieved"] = out["e2e"]["d2h_bytes_per_step"] * world * args.e2e_steps / (float(te[0]) * 1e9)
     strong = strong_scaling(S, eng, torch, dist, barrier, rank, world) if not args.no_strong else None
     if out is not None and strong is not None:
         out["strong"] = strong
@@ -379,6 +383,30 @@ def main():
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def d2h_copy_rate(torch, dist, barrier):
+    """Aggregate GB/s of plain cudaMemcpyAsync device -> pinned host, 1 GiB buffers, every rank at the same time: the
+    ceiling the end-to-end figure (every FASTQ byte crosses PCIe) can reach on this box."""
+    try:
+        n = 1 << 30
+        dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+        host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        host.copy_(dev, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            host.copy_(dev, non_blocking=True)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        nb = torch.tensor([4.0 * n], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX); dist.all_reduce(nb, op=dist.ReduceOp.SUM)
+        del dev, host
+        return float(nb[0]) / float(dt[0]) / 1e9
+    except Exception as e:
+        note(f"copy-rate probe failed: {e!r}")
+        return None
 
 
 def strong_scaling(S, eng, torch, dist, barrier, rank, world):
@@ -443,7 +471,7 @@ def fastq_to_file(S, gs, device):
         open(os.path.join(d, "genomes.tsv"), "w").write("path\tuuid\n" + "".join(lines))
         out = {"filesystem": "tmpfs (/dev/shm)" if root else "default temporary directory", "reads": 20_000_000}
         env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(device))
-        for name, extra in (("one_file", []), ("eight_parts", ["--output-parts", "8"])):
+        for name, extra in (("one_file", []), ("eight_parts", ["--output-parts", "8"]), ("gzip_split_mates", ["--gzip", "--split-mates"])):
             o = os.path.join(d, "reads.fq")
             t0 = time.perf_counter()
             r = subprocess.run([exe, "--genome-file", os.path.join(d, "genomes.tsv"), "--output", o, "--num-reads", "20000000", "--seed", "42",
@@ -452,12 +480,14 @@ def fastq_to_file(S, gs, device):
             if r.returncode != 0:
                 out[name] = {"error": r.stderr[-300:]}
                 continue
-            files = [o] if not extra else [f"{o}.{k:03d}" for k in range(8)]
-            size = sum(os.path.getsize(p) for p in files)
+            files = ([o] if not extra else [f"{o}.{k:03d}" for k in range(8)] if name == "eight_parts"
+                     else [os.path.join(d, "reads_R1.fq"), os.path.join(d, "reads_R2.fq")])
+            on_disk = sum(os.path.getsize(p) for p in files)
             phase = [ln for ln in r.stderr.splitlines() if "FASTQ bytes (" in ln]
             secs = float(phase[0].split(") in ")[1].split(" s")[0]) if phase else None
             nbases = int(phase[0].split(" records, ")[1].split(" bases")[0]) if phase else None
-            out[name] = {"fastq_bytes": size, "wall_s": round(wall, 3), "gb_per_s_wall": size / wall / 1e9,
+            size = int(phase[0].split("Wrote ")[1].split(" FASTQ")[0]) if phase else on_disk
+            out[name] = {"fastq_bytes": size, "file_bytes": on_disk, "wall_s": round(wall, 3), "gb_per_s_wall": size / wall / 1e9,
                          "write_phase_s": secs, "gb_per_s_write_phase": size / secs / 1e9 if secs else None,
                          "gbases_per_s_write_phase": nbases / secs / 1e9 if secs else None}
             for p in files:

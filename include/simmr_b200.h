@@ -229,6 +229,17 @@ int64_t simmr_parse_genome_file(const char *path, char *out, uint64_t cap);
 int  simmr_write_metadata(const char *output, uint32_t n, const char *const *uuid,
                           const char *const *path, const uint64_t *num_reads, const double *abundance);
 
+/* ---- output side: what the reference's readme lists as to-do (readme.md:209-211) and fastq.rs:14-124 writes as one
+ * plain interleaved file.  Host-side helpers for a sink; the bytes a sink receives stay plain interleaved FASTQ. ---- */
+/* One gzip member (RFC 1952) holding src[0, n): members may be concatenated, so the slices of a chunk can be compressed
+ * on as many threads as the caller has and written in order.  Returns the member's bytes, or a negative SIMMR_E_*
+ * (SIMMR_E_LIMIT: cap too small; simmr_gzip_bound gives a sufficient cap). */
+int64_t  simmr_gzip_member(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, int level);
+uint64_t simmr_gzip_bound(uint64_t n);
+/* Splits interleaved paired-end FASTQ (whole records, mate 1 first) into its two mates: r1 and r2 need n bytes of room
+ * each.  Writes the byte counts; SIMMR_E_PARSE if src does not hold an even number of four-line records. */
+int  simmr_fastq_split_mates(const uint8_t *src, uint64_t n, uint8_t *r1, uint64_t *n1, uint8_t *r2, uint64_t *n2);
+
 /* ---- introspection used by the parity tests (host only) ----------------- */
 /* kind 3 (short reads) of a mutating profile: the (npos << cb) quality words are followed by the 256 words of the
  * substitution-gap table and the (1 << cb) words of the quality-given-substitution table */

@@ -76,6 +76,7 @@ EXPORTS = [
     "simmr_builder_error", "simmr_parse_genome_file", "simmr_write_metadata", "simmr_debug_phred_table",
     "simmr_debug_len_table", "simmr_debug_err_table", "simmr_debug_philox4x32_10", "simmr_version",
     "simmr_multi_create", "simmr_multi_destroy", "simmr_multi_genomes_load", "simmr_multi_error_profile_set",
+    "simmr_gzip_member", "simmr_gzip_bound", "simmr_fastq_split_mates",
     "simmr_chunk_release", "simmr_multi_total_units", "simmr_multi_simulate", "simmr_multi_stats_get", "simmr_multi_last_error",
 ]
 
@@ -109,6 +110,11 @@ def lib():
         L.simmr_total_units.argtypes = [C.c_void_p, u64p]
         L.simmr_total_units.restype = C.c_uint64
         L.simmr_stats_get.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.simmr_gzip_member.argtypes = [u8p, C.c_uint64, u8p, C.c_uint64, C.c_int]
+        L.simmr_gzip_member.restype = C.c_int64
+        L.simmr_gzip_bound.argtypes = [C.c_uint64]
+        L.simmr_gzip_bound.restype = C.c_uint64
+        L.simmr_fastq_split_mates.argtypes = [u8p, C.c_uint64, u8p, u64p, u8p, u64p]
         L.simmr_chunk_release.argtypes = [C.c_void_p]
         L.simmr_chunk_release.restype = None
         L.simmr_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]

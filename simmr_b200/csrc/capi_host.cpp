@@ -4,6 +4,8 @@
  * and the table introspection the parity tests use.  No CUDA calls here. */
 #include "host_model.hpp"
 
+#include <zlib.h>
+
 #include <cstring>
 #include <fstream>
 
@@ -14,6 +16,39 @@ namespace { int flunk(int code, const std::string &m) { last_error_slot() = m; r
 struct simmr_genome_builder { GenomeStore store; };
 
 extern "C" {
+
+/* ---- output side helpers (no reference equivalent: fastq.rs writes one plain file) ---- */
+uint64_t simmr_gzip_bound(uint64_t n) { return n + n / 1000 + 64 + 18; }
+int64_t simmr_gzip_member(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, int level) {
+    if ((!src && n) || !dst) return flunk(SIMMR_E_INVALID, "null buffer");
+    if (n > 0xfffffff0ull) return flunk(SIMMR_E_LIMIT, "a gzip member holds less than 4 GiB here: compress the chunk in slices");
+    z_stream z{};
+    if (deflateInit2(&z, level < 0 ? 1 : level > 9 ? 9 : level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return flunk(SIMMR_E_IO, "zlib: deflateInit2 failed");
+    z.next_in = const_cast<Bytef *>(src); z.avail_in = uInt(n);
+    z.next_out = dst; z.avail_out = uInt(cap > 0xfffffff0ull ? 0xfffffff0ull : cap);
+    const int rc = deflate(&z, Z_FINISH);
+    const uint64_t out = z.total_out;
+    deflateEnd(&z);
+    if (rc != Z_STREAM_END) return flunk(SIMMR_E_LIMIT, "gzip output buffer too small");
+    return int64_t(out);
+}
+int simmr_fastq_split_mates(const uint8_t *src, uint64_t n, uint8_t *r1, uint64_t *n1, uint8_t *r2, uint64_t *n2) {
+    if ((!src && n) || !r1 || !r2 || !n1 || !n2) return flunk(SIMMR_E_INVALID, "null buffer");
+    uint64_t at = 0, a = 0, b = 0, rec = 0;
+    while (at < n) {                                  /* a record is four lines (fastq.rs:61-69) */
+        uint64_t end = at;
+        for (int line = 0; line < 4; ++line) {
+            const void *nl = memchr(src + end, '\n', n - end);
+            if (!nl) return flunk(SIMMR_E_PARSE, "FASTQ chunk ends inside a record");
+            end = uint64_t(static_cast<const uint8_t *>(nl) - src) + 1;
+        }
+        if (rec & 1) { memcpy(r2 + b, src + at, end - at); b += end - at; } else { memcpy(r1 + a, src + at, end - at); a += end - at; }
+        at = end; ++rec;
+    }
+    if (rec & 1) return flunk(SIMMR_E_PARSE, "FASTQ chunk holds an odd number of records");
+    *n1 = a; *n2 = b;
+    return SIMMR_OK;
+}
 
 int simmr_builder_create(simmr_genome_builder **out) { if (!out) return SIMMR_E_INVALID; *out = new simmr_genome_builder; return SIMMR_OK; }
 void simmr_builder_destroy(simmr_genome_builder *b) { delete b; }

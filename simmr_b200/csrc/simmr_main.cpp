@@ -6,7 +6,9 @@
  * include/simmr_b200.h; nothing here computes reads.  Added: --gpus N (the run's batches are
  * dealt to N devices of this box through simmr_multi, byte-identical output), --output-parts P
  * (P part files <output>.000 ... written by P I/O threads: one file takes about 2.5 GB/s,
- * whatever feeds it), --compat-long-start (simulate.rs:484 start draw) and the `custom-long`
+ * whatever feeds it), --gzip [--gzip-level L] (the output as concatenated gzip members, the slices of a chunk compressed
+ * on all host threads), --split-mates (two files, <stem>_R1<ext> and <stem>_R2<ext>, instead of the interleaved one:
+ * readme.md:209-211 lists that as to-do), --compat-long-start (simulate.rs:484 start draw) and the `custom-long`
  * profile value. */
 #include "../../include/simmr_b200.h"
 
@@ -14,6 +16,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -44,7 +47,8 @@ struct Args {
     bool has_seed = false; uint64_t seed = 0;        /* :202-203 */
     bool size_adjusted = false, contiguous = false;  /* :206-219 */
     bool compat_long_start = false;
-    int gpus = 1, parts = 1;
+    int gpus = 1, parts = 1, gzip_level = 1;
+    bool gzip = false, split_mates = false;
     uint64_t batch_units = 0;                        /* 0: library default (about 256 MiB of FASTQ per chunk) */
 };
 
@@ -67,6 +71,8 @@ void usage() {
           "  --read-header-format <s>   placeholders {:read_id:} {:genome_id:} {:sequence_id:} {:start_position:} {:end_position:} {:reverse_complement:} {:pair:}\n"
           "  --seed <n>\n  --size-adjusted\n  --contiguous\n  --gpus <n>                 [1] devices to share the run\n"
           "  --output-parts <n>         [1] write <output>.000 ... <output>.(n-1) instead of <output>: chunk j of the run goes to part j mod n\n"
+          "  --gzip                     write gzip (concatenated members, compressed on all host threads); --gzip-level <1-9> [1]\n"
+          "  --split-mates              paired-end reads into <stem>_R1<ext> and <stem>_R2<ext> instead of one interleaved file\n"
           "  --batch-units <n>          units (pairs / long reads) per chunk; default: about 256 MiB of FASTQ\n"
           "  --compat-long-start\n", stderr);
 }
@@ -103,6 +109,9 @@ Args parse(int argc, char **argv) {
         else if (f == "--compat-long-start") a.compat_long_start = true;
         else if (f == "--gpus") a.gpus = int(num(v(), "--gpus", 1, 64));
         else if (f == "--output-parts") a.parts = int(num(v(), "--output-parts", 1, 64));
+        else if (f == "--gzip") a.gzip = true;
+        else if (f == "--gzip-level") a.gzip_level = int(num(v(), "--gzip-level", 1, 9));
+        else if (f == "--split-mates") a.split_mates = true;
         else if (f == "--batch-units") a.batch_units = uint64_t(num(v(), "--batch-units", 1, 2147483647));
         else if (f == "-h" || f == "--help") { usage(); exit(0); }
         else die("unexpected argument '" + f + "'");
@@ -118,35 +127,62 @@ Args parse(int argc, char **argv) {
  * and the chunk's pinned buffer is kept (SIMMR_SINK_RETAINED) until that thread has written it. */
 struct PartWriter {
     struct Part {
-        int fd = -1; std::thread th; std::mutex m; std::condition_variable cv;
+        int fd = -1, fd2 = -1; std::thread th; std::mutex m; std::condition_variable cv;
         std::deque<std::pair<const uint8_t *, uint64_t>> q; bool closed = false;
     };
     std::vector<Part> parts;
     std::atomic<bool> failed{false};
     uint64_t next = 0;
+    bool gz = false, split = false; int level = 1;
+    unsigned workers = std::max(1u, std::thread::hardware_concurrency());
+    /* [p, p + n) to fd: as it is, or as gzip members — one per slice of about 4 MiB, the slices compressed in parallel */
+    bool emit(int fd, const uint8_t *p, uint64_t n) const {
+        if (!gz) return write_all(fd, p, n);
+        const uint64_t nsl = std::max<uint64_t>(1, std::min<uint64_t>(workers / std::max<size_t>(1, parts.size()) + 1, (n + (4u << 20) - 1) / (4u << 20)));
+        std::vector<std::vector<uint8_t>> out(nsl);
+        std::vector<int64_t> got(nsl, 0);
+        std::vector<std::thread> th;
+        for (uint64_t k = 0; k < nsl; ++k) th.emplace_back([&, k] {
+            const uint64_t lo = n * k / nsl, hi = n * (k + 1) / nsl;
+            out[k].resize(simmr_gzip_bound(hi - lo));
+            got[k] = simmr_gzip_member(p + lo, hi - lo, out[k].data(), out[k].size(), level);
+        });
+        for (auto &t : th) t.join();
+        for (uint64_t k = 0; k < nsl; ++k) if (got[k] < 0 || !write_all(fd, out[k].data(), uint64_t(got[k]))) return false;
+        return true;
+    }
+    /* one chunk of the run to its part: split into mates and / or compressed on the way */
+    bool process(Part &p, const uint8_t *data, uint64_t len) const {
+        if (!split) return emit(p.fd, data, len);
+        std::vector<uint8_t> r1(len), r2(len);
+        uint64_t n1 = 0, n2 = 0;
+        if (simmr_fastq_split_mates(data, len, r1.data(), &n1, r2.data(), &n2)) return false;
+        return emit(p.fd, r1.data(), n1) && emit(p.fd2, r2.data(), n2);
+    }
+    bool threaded() const { return parts.size() > 1 || gz || split; }      /* chunks are kept and handled by the parts' own threads */
     static bool write_all(int fd, const uint8_t *p, uint64_t n) {
         while (n) { const ssize_t w = write(fd, p, n); if (w <= 0) return false; p += w; n -= uint64_t(w); }
         return true;
     }
     explicit PartWriter(size_t n) : parts(n) {}
     void start() {
-        if (parts.size() < 2) return;
+        if (!threaded()) return;
         for (Part &p : parts) p.th = std::thread([this, &p] {
             for (;;) {
                 std::pair<const uint8_t *, uint64_t> c;
                 { std::unique_lock<std::mutex> l(p.m); p.cv.wait(l, [&] { return !p.q.empty() || p.closed; }); if (p.q.empty()) return; c = p.q.front(); p.q.pop_front(); }
-                if (!failed && !write_all(p.fd, c.first, c.second)) failed = true;
+                if (!failed && !process(p, c.first, c.second)) failed = true;
                 simmr_chunk_release(c.first);
             }
         });
     }
     void finish() {
-        for (Part &p : parts) { { std::lock_guard<std::mutex> l(p.m); p.closed = true; } p.cv.notify_all(); if (p.th.joinable()) p.th.join(); if (p.fd >= 0) close(p.fd); }
+        for (Part &p : parts) { { std::lock_guard<std::mutex> l(p.m); p.closed = true; } p.cv.notify_all(); if (p.th.joinable()) p.th.join(); if (p.fd >= 0) close(p.fd); if (p.fd2 >= 0) close(p.fd2); }
     }
     static int call(void *user, const uint8_t *data, uint64_t len, uint64_t, uint64_t) {
         PartWriter *w = static_cast<PartWriter *>(user);
         if (w->failed) return 1;
-        if (w->parts.size() < 2) { if (!write_all(w->parts[0].fd, data, len)) { w->failed = true; return 1; } return 0; }
+        if (!w->threaded()) { if (!write_all(w->parts[0].fd, data, len)) { w->failed = true; return 1; } return 0; }
         Part &p = w->parts[w->next++ % w->parts.size()];
         { std::lock_guard<std::mutex> l(p.m); p.q.emplace_back(data, len); }
         p.cv.notify_all();
@@ -247,12 +283,27 @@ int main(int argc, char **argv) {
     info("Writing simulated reads to " + args.output);
     unlink(args.output.c_str());                        /* main.rs:191-198 */
     unlink((args.output + ".tsv").c_str());
+    if (args.split_mates && is_long) die("--split-mates needs a paired-end error profile");
     PartWriter writer{size_t(args.parts)};
+    writer.gz = args.gzip; writer.level = args.gzip_level; writer.split = args.split_mates;
+    auto mate_path = [&](const std::string &path, const char *tag) {      /* reads.fq.gz -> reads_R1.fq.gz */
+        size_t cut = path.size();
+        for (const char *ext : {".gz", ".fastq", ".fq"}) { const size_t n = strlen(ext); if (cut >= n && path.compare(cut - n, n, ext) == 0) cut -= n; }
+        const size_t slash = path.rfind('/');
+        if (slash != std::string::npos && cut <= slash) cut = path.size();
+        return path.substr(0, cut) + tag + path.substr(cut);
+    };
     for (int p = 0; p < args.parts; ++p) {
         char suffix[16]; snprintf(suffix, sizeof suffix, ".%03d", p);
         const std::string path = args.parts > 1 ? args.output + suffix : args.output;
-        writer.parts[p].fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-        if (writer.parts[p].fd < 0) die("Failed to write reads to the output file: cannot create " + path);
+        const std::string first = args.split_mates ? mate_path(path, "_R1") : path;
+        writer.parts[p].fd = open(first.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (writer.parts[p].fd < 0) die("Failed to write reads to the output file: cannot create " + first);
+        if (args.split_mates) {
+            const std::string second = mate_path(path, "_R2");
+            writer.parts[p].fd2 = open(second.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+            if (writer.parts[p].fd2 < 0) die("Failed to write reads to the output file: cannot create " + second);
+        }
     }
 
     simmr_run_opts opts{};

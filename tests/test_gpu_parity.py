@@ -406,6 +406,43 @@ def test_cli_output_parts(engine, tmp_path):
         assert got == want[p], first_diff(got, want[p])
 
 
+def test_cli_gzip_and_split_mates(engine, tmp_path):
+    """--gzip --split-mates: the two mates as gzip files whose plain bytes are the records of the interleaved output
+    (readme.md:209-211 lists split output as to-do); --gzip alone reads back as the plain file."""
+    import gzip
+    import os
+    import subprocess
+    rng = np.random.default_rng(12)
+    paths = []
+    for g in range(2):
+        p = str(tmp_path / f"g{g}.fna")
+        _write_fasta(p, [(f"g{g}_c{c}".encode(), np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(rng.integers(3000, 9000)))]) for c in range(2)])
+        paths.append(p)
+    exe = os.path.join(os.path.dirname(S._native.LIB_PATH), "simmr")
+    base = [exe] + sum([["--genome", p] for p in paths], []) + ["--num-reads", "6000", "--seed", "4", "--error-profile", "minimal-short", "--batch-units", "700"]
+    out = str(tmp_path / "reads.fq.gz")
+    r = subprocess.run(base + ["--output", out, "--gzip", "--split-mates"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ids = [ln.split("\t")[0] for ln in open(out + ".tsv").read().splitlines()[1:]]
+    prof = S.MinimalShortErrorProfile()
+    gs, _ = S.GenomeSet.from_fasta(paths, uuids=ids, min_size=prof.minimum_genome_size())
+    reads, _ = S.UniformAbundanceProfile().determine_abundances(6000, 2)
+    want = po.simulate(po.Genomes.from_set(gs), H.oracle_profile(prof), reads, 4)
+    lines = want.split(b"\n")[:-1]
+    recs = [b"\n".join(lines[i:i + 4]) + b"\n" for i in range(0, len(lines), 4)]
+    for tag, mate in (("_R1", recs[0::2]), ("_R2", recs[1::2])):
+        got = gzip.decompress(open(str(tmp_path / f"reads{tag}.fq.gz"), "rb").read())
+        assert got == b"".join(mate), first_diff(got, b"".join(mate))
+    assert not os.path.exists(out)
+    r = subprocess.run(base + ["--output", out, "--gzip", "--gzip-level", "6"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ids2 = [ln.split("\t")[0] for ln in open(out + ".tsv").read().splitlines()[1:]]
+    gs2, _ = S.GenomeSet.from_fasta(paths, uuids=ids2, min_size=prof.minimum_genome_size())
+    want2 = po.simulate(po.Genomes.from_set(gs2), H.oracle_profile(prof), reads, 4)
+    got = gzip.decompress(open(out, "rb").read())
+    assert got == want2, first_diff(got, want2)
+
+
 def test_retained_chunks_released_out_of_order(engine):
     """A sink that keeps its chunks (SIMMR_SINK_RETAINED) may give them back in any order and from any thread — the
     command line's part files do.  The ring's buffers are filled round-robin, so the launch thread has to wait for the very

@@ -242,3 +242,38 @@ def test_philox_host_copy():
     o = np.zeros(4, np.uint32)
     N.lib().simmr_debug_philox4x32_10(c.ctypes.data_as(N.u32p), k.ctypes.data_as(N.u32p), o.ctypes.data_as(N.u32p))
     assert o.tolist() == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]             # Random123 kat_vectors
+
+
+def test_output_helpers_gzip_members_and_mate_split():
+    """simmr_gzip_member: concatenated members read back as the plain bytes; simmr_fastq_split_mates: records of an
+    interleaved chunk go alternately to the two mates, malformed chunks are refused."""
+    import ctypes as C
+    import gzip
+    L = N.lib()
+    rng = np.random.default_rng(3)
+    recs = []
+    for i in range(200):
+        n = int(rng.integers(1, 200))
+        seq = bytes(rng.choice(list(b"ACGT"), n).astype(np.uint8))
+        q = bytes((33 + rng.integers(0, 60, n)).astype(np.uint8))          # '@' and '+' occur among the qualities
+        recs.append(b"@r%d|x/%d m:sp=%d\n" % (i // 2, 1 + i % 2, i) + seq + b"\n+\n" + q + b"\n")
+    data = b"".join(recs)
+    src = np.frombuffer(data, np.uint8)
+    out = b""
+    for lo, hi in ((0, 1000), (1000, 1000), (1000, len(data))):             # an empty slice is a member too
+        cap = int(L.simmr_gzip_bound(hi - lo))
+        dst = np.zeros(cap, np.uint8)
+        got = L.simmr_gzip_member(src[lo:].ctypes.data_as(N.u8p), hi - lo, dst.ctypes.data_as(N.u8p), cap, 1)
+        assert got > 0
+        out += dst[:got].tobytes()
+    assert gzip.decompress(out) == data
+    small = np.zeros(8, np.uint8)
+    assert L.simmr_gzip_member(src.ctypes.data_as(N.u8p), len(data), small.ctypes.data_as(N.u8p), 8, 1) == N.E_LIMIT
+    r1, r2 = np.zeros(len(data), np.uint8), np.zeros(len(data), np.uint8)
+    n1, n2 = C.c_uint64(), C.c_uint64()
+    assert L.simmr_fastq_split_mates(src.ctypes.data_as(N.u8p), len(data), r1.ctypes.data_as(N.u8p), C.byref(n1), r2.ctypes.data_as(N.u8p), C.byref(n2)) == 0
+    assert r1[:n1.value].tobytes() == b"".join(recs[0::2]) and r2[:n2.value].tobytes() == b"".join(recs[1::2])
+    odd = np.frombuffer(b"".join(recs[:3]), np.uint8)
+    assert L.simmr_fastq_split_mates(odd.ctypes.data_as(N.u8p), len(odd), r1.ctypes.data_as(N.u8p), C.byref(n1), r2.ctypes.data_as(N.u8p), C.byref(n2)) == N.E_PARSE
+    cut = np.frombuffer(data[:-5], np.uint8)
+    assert L.simmr_fastq_split_mates(cut.ctypes.data_as(N.u8p), len(cut), r1.ctypes.data_as(N.u8p), C.byref(n1), r2.ctypes.data_as(N.u8p), C.byref(n2)) == N.E_PARSE
