@@ -966,11 +966,15 @@ __global__ void __launch_bounds__(SIZES_THREADS) k_block_sums(RunParams rp) {
 /* Quality characters (as printed) of four consecutive bases, the first at window index i0 (the same for every lane of
  * the warp).  One step of the record's quality chain serves two bases: the word x ^ c picks base 2n's column with bits
  * 0..cb-1 and base 2n+1's with bits cb..2cb-1; their levels are x and c.  QM_LANE: the lane's own copy of the single
- * position's table (word col * 32 + lane: every lane stays in its bank; CB7: cb == 7, the second column's byte offset is a
- * plain mask of the word); QM_POS: row min(i, npos-1) of the one copy. */
-template <int QM, bool CB7>
+ * position's table (word col * 32 + lane: every lane stays in its bank); QM_POS: row min(i, npos-1) of the one copy.
+ * CBK = cb when it is known at compile time (7: minimal profiles, where the second column's byte offset is then a plain
+ * mask of the word; 6: NovaSeq-style blobs), 0 = read from the parameters.  FLAT (QM_POS): none of the four bases is past
+ * the table's last row, so their rows follow each other from row i0 on and the address is a column plus a constant —
+ * the row arithmetic (a minimum, a shift and an add per look-up) had made the per-position kernel ALU-bound at 79 %. */
+template <int QM, int CBK, bool FLAT = false>
 __device__ __forceinline__ uint32_t quals4(const RunParams &rp, uint32_t qtab_s, uint32_t mask, Mwc1 &rng, uint32_t i0) {
     uint32_t qw = 0;
+    const uint32_t cb = CBK ? uint32_t(CBK) : rp.phred.cb;
 #pragma unroll
     for (uint32_t j = 0; j < 4; j += 2) {
         const uint32_t lv0 = rng.x, lv1 = rng.c;
@@ -979,9 +983,13 @@ __device__ __forceinline__ uint32_t quals4(const RunParams &rp, uint32_t qtab_s,
         uint32_t at0, at1;
         if (QM == QM_LANE) {
             at0 = qtab_s + (r & mask) * 128u;
-            at1 = CB7 ? qtab_s + (r & 0x3f80u) : qtab_s + ((r >> rp.phred.cb) & mask) * 128u;
+            at1 = CBK == 7 ? qtab_s + (r & 0x3f80u) : qtab_s + ((r >> cb) & mask) * 128u;
+        } else if (FLAT) {
+            const uint32_t row_s = qtab_s + (i0 << (cb + 2u));                                       /* the same for every lane */
+            at0 = row_s + (j << (cb + 2u)) + (r & mask) * 4u;
+            at1 = row_s + ((j + 1u) << (cb + 2u)) + ((r >> cb) & mask) * 4u;
         } else {
-            const uint32_t last = rp.phred.npos - 1u, cb = rp.phred.cb;                              /* custom_short.rs:339-345 */
+            const uint32_t last = rp.phred.npos - 1u;                                                /* custom_short.rs:339-345 */
             at0 = qtab_s + ((min(i0 + j, last) << cb) + (r & mask)) * 4u;
             at1 = qtab_s + ((min(i0 + j + 1u, last) << cb) + ((r >> cb) & mask)) * 4u;
         }
@@ -1004,7 +1012,7 @@ __device__ __forceinline__ uint32_t quals4(const RunParams &rp, uint32_t qtab_s,
  * then the reverse-complement table turns each byte into 4 letters (util.rs:31-37) — while its quality line runs
  * forward like mate 1's: quality i belongs to window base i, never reversed (simulate.rs:283-285).  Substitutions
  * are applied afterwards (substitutions_lane), so the two lines are independent here. */
-template <int QM, bool CB7>
+template <int QM, int CBK>
 __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, uint32_t lut_s, bool on, bool rc, uint32_t body_s,
                                           Mwc1 &rng, uint64_t a, uint32_t L, uint32_t T4, bool pre, uint32_t pre_lo, uint32_t pre_hi) {
     if (!on) { L = 0; a = 0; }
@@ -1025,9 +1033,9 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
     const uint32_t qconst = ((rp.phred.const_q + 33u) & 0xffu) * 0x01010101u, mask = rp.phred_mult - 1u;
     uint32_t prev_s = 0, prev_q = 0;
     /* one turn = G groups of 4 bases of every record: G = 4 but for the warp's last turn, which is as long as its longest record needs */
-    auto turn = [&](auto gc, auto whole, uint32_t it) {       /* whole: every lane is inside both lines for all of this turn */
+    auto turn = [&](auto gc, auto whole, auto flat, uint32_t it) {       /* whole: every lane is inside both lines for all of this turn; flat: quals4 */
         constexpr uint32_t G = decltype(gc)::value;
-        constexpr bool WHOLE = decltype(whole)::value;
+        constexpr bool WHOLE = decltype(whole)::value, FLAT = decltype(flat)::value;
         const uint32_t X = __byte_perm(__funnelshift_r(w_lo, w_hi, s2), 0u, rev);
         if (G == 4) {   /* mate 1: (lo, hi) <- (hi, new); mate 2: (lo, hi) <- (new, lo).  The padding around `packed` covers the last fetch. */
             const uint32_t nw = __ldg(pw);
@@ -1038,7 +1046,7 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
         uint32_t cs[G], cq[G];                         /* the turn's words of each line, on the stage's word grid */
 #pragma unroll
         for (uint32_t h = 0; h < G; ++h) {
-            const uint32_t qw = QM == QM_CONST ? qconst : quals4<QM, CB7>(rp, qtab_s, mask, rng, 16u * it + 4u * h);
+            const uint32_t qw = QM == QM_CONST ? qconst : quals4<QM, CBK, FLAT>(rp, qtab_s, mask, rng, 16u * it + 4u * h);
             const uint32_t sw = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
             cs[h] = __funnelshift_l(prev_s, sw, sh_s); cq[h] = QM == QM_CONST ? qconst : __funnelshift_l(prev_q, qw, sh_q);
             prev_s = sw; prev_q = qw;
@@ -1061,13 +1069,17 @@ __device__ __forceinline__ void body_lane(const RunParams &rp, uint32_t qtab_s, 
     /* turns during which every lane that has a record stores whole groups in both lines: the shortest record's */
     const uint32_t whole = min(full, __reduce_min_sync(0xffffffffu, on ? uint32_t(min(ns, nq)) >> 2 : 0xffffffffu));
     uint32_t it = 0;
-    for (; it < whole; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::true_type{}, it);
-    for (; it < full; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, it);
+    if (QM == QM_POS) {                                /* the turns whose sixteen positions all have a row of their own */
+        const uint32_t nflat = min(whole, rp.phred.npos >> 4);
+        for (; it < nflat; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::true_type{}, std::true_type{}, it);
+    }
+    for (; it < whole; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::true_type{}, std::false_type{}, it);
+    for (; it < full; ++it) turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, std::false_type{}, it);
     switch (T4 - 4u * full) {
-    case 1: turn(std::integral_constant<uint32_t, 1>{}, std::false_type{}, full); break;
-    case 2: turn(std::integral_constant<uint32_t, 2>{}, std::false_type{}, full); break;
-    case 3: turn(std::integral_constant<uint32_t, 3>{}, std::false_type{}, full); break;
-    default: turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, full); break;
+    case 1: turn(std::integral_constant<uint32_t, 1>{}, std::false_type{}, std::false_type{}, full); break;
+    case 2: turn(std::integral_constant<uint32_t, 2>{}, std::false_type{}, std::false_type{}, full); break;
+    case 3: turn(std::integral_constant<uint32_t, 3>{}, std::false_type{}, std::false_type{}, full); break;
+    default: turn(std::integral_constant<uint32_t, 4>{}, std::false_type{}, std::false_type{}, full); break;
     }
 }
 
@@ -1222,8 +1234,9 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
                     if (QM != QM_CONST) mwc1_seed(rp, qc, ec, 0u, 1u + mate, uint32_t(unit), uint32_t(unit >> 32));
                     const uint32_t lut_s = base_s + (mate ? SM_LUT_RC : SM_LUT_FWD);
                     const bool pre = words_ahead && s0 == 0 && !(d.flags & 16u);
-                    if (QM == QM_LANE && rp.phred.cb == 7u) body_lane<QM, true>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4, pre, cur.w_lo, cur.w_hi);
-                    else body_lane<QM, false>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4, pre, cur.w_lo, cur.w_hi);
+                    if (QM == QM_LANE && rp.phred.cb == 7u) body_lane<QM, 7>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4, pre, cur.w_lo, cur.w_hi);
+                    else if (QM == QM_POS && rp.phred.cb == 6u) body_lane<QM, 6>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4, pre, cur.w_lo, cur.w_hi);
+                    else body_lane<QM, 0>(rp, qtab_s, lut_s, fast, mate != 0, body_s, qc, a, L, T4, pre, cur.w_lo, cur.w_hi);
                 }
                 if (last_sub && tile_next < ntiles) fetch_in(tile_next, nx);           /* on their way during the substitutions and the headers */
                 if (SIMMR_KO != 3 && T4 && QM != QM_CONST && rp.phred.has_sub) substitutions_lane(rp, base_s + SM_GAP, base_s + SM_QSUB, fast, mate != 0, body_s, ec, L);
@@ -1411,8 +1424,8 @@ __device__ __forceinline__ void rl_edges(const RunLine &r, uint32_t k, uint32_t 
  * whatever the read's length.  A lane seeds its piece's chains, writes that part of the sequence and quality lines
  * straight to global memory in 16-byte lines (RunLine), then applies the piece's substitutions to the bytes it wrote.
  * Lane 0 also writes the header and the fixed bytes.  Reads whose window holds anything but A,C,G,T take the byte
- * path, a lane per piece.  QM and CB7 as in k_format_lanes / quals4. */
-template <int QM, bool CB7>
+ * path, a lane per piece.  QM and CBK as in k_format_lanes / quals4. */
+template <int QM, int CBK>
 __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31;
@@ -1519,7 +1532,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp)
                 uint32_t sw[4], qw[4];
 #pragma unroll
                 for (uint32_t h = 0; h < 4; ++h) {
-                    qw[h] = QM == QM_CONST ? qconst : quals4<QM, CB7>(rp, qtab_s, mask, qc, lo + 16u * qd + 4u * h);
+                    qw[h] = QM == QM_CONST ? qconst : quals4<QM, CBK>(rp, qtab_s, mask, qc, lo + 16u * qd + 4u * h);
                     sw[h] = lds32(lut_s + ((h == 0 ? X << 2 : X >> (8u * h - 2u)) & 0x3fcu));
                 }
                 if (qd == 0) { first_s = sw[0]; first_q = qw[0]; }

@@ -185,8 +185,8 @@ FormatKernel lanes_kernel(bool replay, int qm) {
 FormatKernel direct_kernel(bool replay) { return replay ? k_format_direct<true> : k_format_direct<false>; }
 using LongKernel = void (*)(RunParams);
 LongKernel long_kernel(int qm, uint32_t cb) {
-    if (qm == QM_LANE) return cb == 7 ? k_format_long<QM_LANE, true> : k_format_long<QM_LANE, false>;
-    return qm == QM_POS ? k_format_long<QM_POS, false> : k_format_long<QM_CONST, false>;
+    if (qm == QM_LANE) return cb == 7 ? k_format_long<QM_LANE, 7> : k_format_long<QM_LANE, 0>;
+    return qm == QM_POS ? k_format_long<QM_POS, 0> : k_format_long<QM_CONST, 0>;
 }
 
 struct Plan {      /* launch geometry for one run */
