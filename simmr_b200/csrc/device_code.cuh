@@ -65,11 +65,12 @@ struct RunParams {
     uint32_t rk[20];               /* Philox round keys: seed + r * Weyl constants, r = 0..9 */
     /* per-batch scratch + output */
     uint32_t *sizes; uint64_t *offsets, *block_sums; uint8_t *out;
+    uint64_t out_cap;              /* bytes of `out`: a batch whose FASTQ bytes (offsets[batch_units]) exceed it is not written at all */
     struct UnitRec *desc;          /* per-unit geometry written by k_unit_sizes, read by the format kernels (32 bytes) */
     struct UnitExt *desc_ext;      /* what does not fit a UnitRec (clamped windows, positions above 2^32): written and read for flagged units only */
     /* k_kmer_errors takes the reads of every segment of SEG_UNITS units in the order of their sizes (k_segment_sort) */
     uint16_t *seg_perm;
-    unsigned long long *counters;  /* [0] clamped [1] algorithmic bytes [2] bases [3] records */
+    unsigned long long *counters;  /* [0] clamped [1] algorithmic bytes [2] bases [3] records [4] k_format_long's read counter [5] bases deleted by k-mer errors [6] a batch overflowed */
     /* per-warp stage of k_format_lanes */
     uint32_t stage_cap;            /* bytes of a warp's stage in k_format_lanes */
     /* decimal fields of the header template when every contig has the same ones (fastq.rs:34-57): hdr_fast == 0 means
@@ -213,6 +214,13 @@ struct UnitGeo {
     uint32_t rl, pad_;    /* drawn read length (replay slots of mate 2 start rl after mate 1) */
 };
 
+/* A batch of long reads is budgeted below its largest possible size (engine.cu): if its bytes exceed the staging buffer
+ * after all, the format kernels write nothing and raise counters[6]; the run then fails with SIMMR_E_LIMIT. */
+__device__ __forceinline__ bool batch_overflows(const RunParams &rp) {
+    if (rp.offsets[rp.batch_units] <= rp.out_cap) return false;
+    if (blockIdx.x == 0 && threadIdx.x == 0) rp.counters[6] = 1ull;
+    return true;
+}
 /* what the format kernels need of a unit, in registers */
 struct UnitDesc {
     uint64_t a0, a1;       /* window offsets in `bases`                                     */
@@ -873,39 +881,50 @@ __global__ void __launch_bounds__(256) k_kmer_errors(RunParams rp) {
     { const Philox4 w = philox(rp.rk, 0u, 3u, uint32_t(unit), uint32_t(unit >> 32)); ch.x = w.x; ch.c = (w.y >> 2) + 1u; uint32_t lv; mwc1_draw(ch, rp.one, lv); }
     uint32_t Ls = 0;
     if (!(d.flags & 1u)) {
-        /* 2-bit path */
+        /* 2-bit path.  A warp's 32 reads walk in lock step, and with an error in one window of thirteen some lane takes
+         * the error branch in nearly every step: the step is kept short — the original's bases wait in a 64-bit buffer
+         * (a window is refilled by one masked shift, not base by base), an alternate comes from the tables with its bases
+         * already packed and counted (ErrTab::alts2). */
         const uint32_t *src = rp.packed + (d.a0 >> 4);
-        uint32_t sw = __ldg(src), sleft = 16u - (uint32_t(d.a0) & 15u);           /* bases left in the source word */
-        sw >>= 2u * (uint32_t(d.a0) & 15u);
+        const uint32_t off0 = uint32_t(d.a0) & 15u;
+        uint64_t sbuf = uint64_t(__ldg(src)) >> (2u * off0);                          /* bases of the original not yet taken, oldest in the low bits */
+        uint32_t sleft = 16u - off0;                                                  /* ... how many of them the buffer holds */
+        ++src;
         uint32_t *dst = rp.epacked + (sb >> 4);
         uint32_t ow = 0, ocnt = 0;                                                    /* output word being filled */
         uint32_t win = 0, cnt = 0, r = 0;
         const uint32_t kmask = (1u << (2u * k)) - 1u;
-        auto take = [&]() -> uint32_t {                                               /* next base of the original */
-            if (!sleft) { sw = __ldg(++src); sleft = 16u; }
-            const uint32_t b = sw & 3u; sw >>= 2; --sleft; ++r; return b;
-        };
         auto emit = [&](uint32_t b) {
             ow |= b << (2u * ocnt);
             if (++ocnt == 16u) { dst[Ls >> 4] = ow; ow = 0; ocnt = 0; }
             ++Ls;
         };
         for (uint32_t at = 0; at + k <= L; ++at) {                                    /* :196-199 */
-            while (cnt < k && r < L) { win |= take() << (2u * cnt); ++cnt; }
+            if (sleft <= 16u) { sbuf |= uint64_t(__ldg(src)) << (2u * sleft); ++src; sleft += 16u; }   /* the padding behind `packed` covers the last fetch */
+            const uint32_t need = min(k - cnt, L - r);                                /* k <= 10 < sleft */
+            win |= (uint32_t(sbuf) & ((1u << (2u * need)) - 1u)) << (2u * cnt);
+            sbuf >>= 2u * need; sleft -= need; cnt += need; r += need;
             if (cnt < k) break;                                                       /* the reference would panic here */
             uint32_t level; const uint32_t word = mwc1_draw(ch, rp.one, level);
             const uint2 ent = __ldg(reinterpret_cast<const uint2 *>(et.direct) + (win & kmask));
             if (ent.y && level >= ent.x) {                                            /* observed k-mer, and the draw leaves it: :216-228 */
-                const uint32_t alt = err_pick_other(et, ent.y - 1u, word);
-                win = 0; cnt = 0;
-                for (uint32_t dg = 0; dg < k; ++dg) { const uint32_t v = (alt >> (3u * dg)) & 7u; if (v != 4u) { win |= v << (2u * cnt); ++cnt; } }
+                const uint32_t ro = __ldg(et.row + ent.y - 1u), cb = __ldg(et.cb + ent.y - 1u);
+                const uint32_t idx = cb ? word >> (32u - cb) : 0u, frac = (word << cb) >> 12;
+                const uint32_t e = __ldg(et.entries + ro + idx), j = frac < (e >> 12) ? idx : (e & 0xfffu);
+                const uint32_t alt = __ldg(et.alts2 + ro + j);
+                win = alt & 0x0fffffffu; cnt = alt >> 28;
             }
-            if (!cnt && r < L) { win = take(); cnt = 1; }
-            if (!cnt) break;
+            if (!cnt) {
+                if (r >= L) break;
+                win = uint32_t(sbuf) & 3u; cnt = 1; sbuf >>= 2; --sleft; ++r;         /* sleft > 16 - 10 here */
+            }
             emit(win & 3u); win >>= 2; --cnt;
         }
         for (; cnt; --cnt) { emit(win & 3u); win >>= 2; }
-        while (r < L) emit(take());
+        while (r < L) {
+            if (!sleft) { sbuf = __ldg(src); ++src; sleft = 16u; }
+            emit(uint32_t(sbuf) & 3u); sbuf >>= 2; --sleft; ++r;
+        }
         if (ocnt) dst[Ls >> 4] = ow;
     } else {
         /* byte path */
@@ -1133,6 +1152,7 @@ __host__ __device__ constexpr uint32_t qtab_bytes(int qm, uint32_t cb, uint32_t 
 template <bool REPLAY, int QM>
 __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lanes(RunParams rp, ReplayDev rd) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    if (batch_overflows(rp)) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t base_s = uint32_t(__cvta_generic_to_shared(smem));
     const uint32_t qbytes = qtab_bytes(QM, rp.phred.cb, rp.phred.npos);
@@ -1289,6 +1309,7 @@ __global__ void __launch_bounds__(FORMAT_THREADS, FORMAT_MIN_CTAS) k_format_lane
  * fit a stage, and native long reads behind SIMMR_NO_LONG_KERNEL.  Not a fast path. */
 template <bool REPLAY>
 __global__ void __launch_bounds__(DIRECT_THREADS) k_format_direct(RunParams rp, ReplayDev rd) {
+    if (batch_overflows(rp)) return;
     for (uint32_t i = blockIdx.x; i < rp.batch_units; i += gridDim.x) {
         const uint64_t u = rp.batch_begin + i;
         const UnitDesc d = load_unit(rp, i);
@@ -1428,6 +1449,7 @@ __device__ __forceinline__ void rl_edges(const RunLine &r, uint32_t k, uint32_t 
 template <int QM, int CBK>
 __global__ void __launch_bounds__(DIRECT_THREADS, 2) k_format_long(RunParams rp) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    if (batch_overflows(rp)) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t base_s = uint32_t(__cvta_generic_to_shared(smem));
     const uint32_t qtab_s = base_s + SM_QTAB + (QM == QM_LANE ? 4u * lane : 0u), lut_s = base_s + SM_LUT_FWD;

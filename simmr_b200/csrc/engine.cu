@@ -130,7 +130,7 @@ struct simmr_ctx {
     ProfileModel model;
     DevMem d_phred, d_gap, d_qsub, d_rl_e, d_rl_lo, d_rl_hi, d_is_e, d_is_lo, d_is_hi;
     DevMem d_acc, d_plthr, d_rodds, d_ralias, d_roff, d_rlo, d_rhi;
-    DevMem d_err_direct, d_err_ref, d_err_keep, d_err_row, d_err_cb, d_err_entries, d_err_alts;     /* k-mer error tables */
+    DevMem d_err_direct, d_err_ref, d_err_keep, d_err_row, d_err_cb, d_err_entries, d_err_alts, d_err_alts2;     /* k-mer error tables */
     DevMem d_epacked, d_ebases;                    /* edited reads of a batch (k_kmer_errors) */
     /* run scratch */
     DevMem d_unit_start, d_counters, d_out[2];
@@ -324,7 +324,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.stage_cap = pl.stage_cap; rp.one = 1;
     if (m.err.on) {
         rp.err = ErrTab{1u, m.err.k, uint32_t(m.err.ref.size()), 0u, ctx->d_err_direct.as<uint32_t>(), ctx->d_err_ref.as<uint32_t>(), ctx->d_err_keep.as<uint32_t>(),
-                        ctx->d_err_row.as<uint32_t>(), ctx->d_err_cb.as<uint32_t>(), ctx->d_err_entries.as<uint32_t>(), ctx->d_err_alts.as<uint32_t>()};
+                        ctx->d_err_row.as<uint32_t>(), ctx->d_err_cb.as<uint32_t>(), ctx->d_err_entries.as<uint32_t>(), ctx->d_err_alts.as<uint32_t>(), ctx->d_err_alts2.as<uint32_t>()};
         rp.epacked = ctx->d_epacked.as<uint32_t>(); rp.ebases = ctx->d_ebases.as<uint8_t>();
     }
 }
@@ -411,19 +411,30 @@ struct Runner {
          * it averages 40 KB — 2 GiB were 16 K reads per launch, 7 per warp, and the last warps' long reads left the GPU half
          * idle (+22 %). */
         errs = ctx->model.err.on && !replay;           /* k-mer error injection between sizing and formatting */
-        uint64_t target_bytes = to_host ? (128ull << 20) : errs ? (4096ull << 20) : (16384ull << 20);     /* to the host: 8 pinned buffers of 128 MiB */
-        if (measure_only) target_bytes = errs ? (1024ull << 20) : (uint64_t(pl.max_unit_bytes) << 24);
+        uint64_t target_bytes = to_host ? (128ull << 20) : (16384ull << 20);     /* to the host: 8 pinned buffers of 128 MiB */
+        if (measure_only) target_bytes = errs ? (4096ull << 20) : (uint64_t(pl.max_unit_bytes) << 24);
         if (!to_host && !measure_only) {
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
-            free_b += ctx->d_out[0].bytes + ctx->d_out[1].bytes;       /* what this context already holds for staging can be reused */
-            while (target_bytes > (256ull << 20) && target_bytes > free_b / (dev_sink ? 5 : 3)) target_bytes /= 2;
+            free_b += ctx->d_out[0].bytes + ctx->d_out[1].bytes + ctx->d_epacked.bytes + ctx->d_ebases.bytes;       /* what this context already holds can be reused */
+            /* error injection keeps a batch's edited reads beside the staging buffer: a byte and two bits per FASTQ byte */
+            while (target_bytes > (256ull << 20) && target_bytes > free_b / ((dev_sink ? 5 : 3) + (errs ? 3 : 0))) target_bytes /= 2;
         }
-        batch = opts && opts->batch_units ? opts->batch_units : std::max<uint64_t>(1, target_bytes / pl.max_unit_bytes);
-        batch = std::min<uint64_t>(batch, std::max<uint64_t>(1, ue - ub));
+        /* Bytes a batch of n units is given.  Short reads: n times the largest unit.  Long reads are 40 KB on average and
+         * 131 KB at most, and a batch budgeted at the maximum holds a third of the reads it could — which left the GPU
+         * mostly idle in the k-mer error walk (a thread per read: 32 K reads per batch, every batch waiting for its longest
+         * read).  They get their typical size and a quarter more, plus sixteen largest units: at least nine standard
+         * deviations of a batch's bytes above their mean for gamma lengths, whatever n.  The format kernels write
+         * nothing when a batch's bytes exceed its buffer (RunParams::out_cap), and the run fails with SIMMR_E_LIMIT. */
+        const uint64_t max_unit = pl.max_unit_bytes, typ_unit = std::min<uint64_t>(max_unit, uint64_t(ctx->plan.hdr_typ) + 2ull * ctx->model.nominal_read_len + 5);
+        auto cap_of = [&](uint64_t n) { return ctx->model.is_long ? std::min(n * max_unit, n * typ_unit * 5 / 4 + 16 * max_unit) : n * max_unit; };
+        if (opts && opts->batch_units) batch = opts->batch_units;
+        else if (ctx->model.is_long && target_bytes > 32 * max_unit) batch = (target_bytes - 16 * max_unit) * 4 / (typ_unit * 5);
+        else batch = target_bytes / max_unit;
+        batch = std::max<uint64_t>(1, std::min<uint64_t>(batch, std::max<uint64_t>(1, ue - ub)));
         batch = std::min<uint64_t>(batch, 0x7fffffffull);
-        if (batch * pl.max_unit_bytes > (64ull << 30)) batch = std::max<uint64_t>(1, (64ull << 30) / pl.max_unit_bytes);
-        out_cap = batch * pl.max_unit_bytes + 64;
+        while (batch > 1 && cap_of(batch) > (64ull << 30)) batch /= 2;
+        out_cap = cap_of(batch) + 64;
         const uint32_t max_blocks = uint32_t((batch + SIZES_THREADS - 1) / SIZES_THREADS);
         const uint64_t max_segs = (batch + SEG_UNITS - 1) / SEG_UNITS;
         for (int k = 0; k < 2; ++k) {
@@ -479,7 +490,7 @@ struct Runner {
     int format(uint64_t u, int k, int dslot) {
         const uint32_t n = uint32_t(std::min<uint64_t>(batch, ue - u));
         scratch(rp, k);
-        rp.batch_begin = u; rp.batch_units = n; rp.out = ctx->d_out[dslot].as<uint8_t>();
+        rp.batch_begin = u; rp.batch_units = n; rp.out = ctx->d_out[dslot].as<uint8_t>(); rp.out_cap = out_cap;
         if (guard) CU(cudaMemsetAsync(ctx->d_out[dslot].p, 0xA5, out_cap, ctx->compute));
         CU(cudaEventRecord(ev[EV_F0 + k], ctx->compute));
         if (pl.tiles) {
@@ -513,6 +524,7 @@ struct Runner {
         float ms = 0; CU(cudaEventElapsedTime(&ms, ev[EV_START], ev[EV_STOP]));
         unsigned long long ctr[8];
         CU(cudaMemcpy(ctr, ctx->d_counters.p, sizeof ctr, cudaMemcpyDeviceToHost));
+        if (ctr[6]) return fail(ctx, SIMMR_E_LIMIT, "a batch overflowed its staging buffer and was not written: set batch_units lower");   /* raised by the format kernels */
         /* ctr[5]: bases deleted by k-mer error injection — read from the genome, absent from the sequence line */
         st.clamped = ctr[0]; st.algorithmic_bytes = ctr[1] - ctr[5]; st.bases = ctr[2] - ctr[5]; st.records = ctr[3];
         st.bytes = ctr[1] - ctr[2] - ctr[5];                          /* (3L+H+5) - L, less the deleted bases */
@@ -543,9 +555,10 @@ int produce(Runner &R, uint64_t j0, uint64_t stride, BatchQueue *q, simmr_stats 
         last.live = false;
         CU(cudaEventSynchronize(ev[EV_F1 + last.k]));
         float ms = 0; CU(cudaEventElapsedTime(&ms, ev[EV_F0 + last.k], ev[EV_F1 + last.k])); format_ms += ms;
+
         if (dev_sink) {
             const uint64_t total = static_cast<uint64_t *>(ctx->h_total.p)[last.dslot];
-            if (total > R.out_cap) return fail(ctx, SIMMR_E_LIMIT, "batch overflowed its staging buffer");
+            if (total > R.out_cap) return fail(ctx, SIMMR_E_LIMIT, "batch overflowed its staging buffer: set batch_units lower");
             if (dev_sink(dev_user, ctx->d_out[last.dslot].as<uint8_t>(), total, last.first, last.units)) return fail(ctx, SIMMR_E_SINK, "device sink callback failed");
         }
         return SIMMR_OK;
@@ -570,7 +583,7 @@ int produce(Runner &R, uint64_t j0, uint64_t stride, BatchQueue *q, simmr_stats 
             CU(cudaEventRecord(ev[EV_FMT + dslot], ctx->compute));
             CU(cudaEventSynchronize(ev[EV_TOTAL + dslot]));            /* byte count known while the format kernel runs */
             const uint64_t total = static_cast<uint64_t *>(ctx->h_total.p)[dslot];
-            if (total > R.out_cap) return fail(ctx, SIMMR_E_LIMIT, "batch overflowed its staging buffer");
+            if (total > R.out_cap) return fail(ctx, SIMMR_E_LIMIT, "batch overflowed its staging buffer: set batch_units lower");
             CU(cudaStreamWaitEvent(ctx->copy, ev[EV_FMT + dslot], 0));
             CU(cudaMemcpyAsync(ctx->h_out[slot].p, ctx->d_out[dslot].p, total, cudaMemcpyDeviceToHost, ctx->copy));
             CU(cudaEventRecord(ev[EV_COPY + slot], ctx->copy));
@@ -778,6 +791,13 @@ int simmr_error_profile_set(simmr_ctx *ctx, const simmr_eprofile_desc *d) {
         CU(ctx->d_err_keep.upload(m.err.keep_thr.data(), m.err.keep_thr.size(), s)); CU(ctx->d_err_row.upload(m.err.row.data(), m.err.row.size(), s));
         CU(ctx->d_err_cb.upload(m.err.cb.data(), m.err.cb.size(), s)); CU(ctx->d_err_entries.upload(m.err.entries.data(), m.err.entries.size(), s));
         CU(ctx->d_err_alts.upload(m.err.alts.data(), m.err.alts.size(), s));
+        std::vector<uint32_t> alts2(m.err.alts.size());          /* the alternates' bases as 2-bit codes and their number (N digits are deleted bases) */
+        for (size_t i = 0; i < alts2.size(); ++i) {
+            uint32_t bases = 0, n = 0;
+            for (uint32_t dg = 0; dg < m.err.k; ++dg) { const uint32_t v = (m.err.alts[i] >> (3u * dg)) & 7u; if (v != 4u) { bases |= (v & 3u) << (2u * n); ++n; } }
+            alts2[i] = bases | (n << 28);
+        }
+        CU(ctx->d_err_alts2.upload(alts2.data(), alts2.size(), s));
     }
     CU(cudaStreamSynchronize(s));
     ctx->have_profile = true;
