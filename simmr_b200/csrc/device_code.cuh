@@ -889,7 +889,7 @@ __global__ void __launch_bounds__(256) k_kmer_errors(RunParams rp) {
         const uint32_t off0 = uint32_t(d.a0) & 15u;
         uint64_t sbuf = uint64_t(__ldg(src)) >> (2u * off0);                          /* bases of the original not yet taken, oldest in the low bits */
         uint32_t sleft = 16u - off0;                                                  /* ... how many of them the buffer holds */
-        ++src;
+        uint32_t nextw = __ldg(++src);                                                /* the word behind the buffer, fetched a refill ahead */
         uint32_t *dst = rp.epacked + (sb >> 4);
         uint32_t ow = 0, ocnt = 0;                                                    /* output word being filled */
         uint32_t win = 0, cnt = 0, r = 0;
@@ -900,18 +900,18 @@ __global__ void __launch_bounds__(256) k_kmer_errors(RunParams rp) {
             ++Ls;
         };
         for (uint32_t at = 0; at + k <= L; ++at) {                                    /* :196-199 */
-            if (sleft <= 16u) { sbuf |= uint64_t(__ldg(src)) << (2u * sleft); ++src; sleft += 16u; }   /* the padding behind `packed` covers the last fetch */
+            if (sleft <= 16u) { sbuf |= uint64_t(nextw) << (2u * sleft); sleft += 16u; nextw = __ldg(++src); }   /* the padding behind `packed` covers the last fetches */
             const uint32_t need = min(k - cnt, L - r);                                /* k <= 10 < sleft */
             win |= (uint32_t(sbuf) & ((1u << (2u * need)) - 1u)) << (2u * cnt);
             sbuf >>= 2u * need; sleft -= need; cnt += need; r += need;
             if (cnt < k) break;                                                       /* the reference would panic here */
             uint32_t level; const uint32_t word = mwc1_draw(ch, rp.one, level);
-            const uint2 ent = __ldg(reinterpret_cast<const uint2 *>(et.direct) + (win & kmask));
+            const uint2 ent = __ldg(reinterpret_cast<const uint2 *>(et.direct2) + (win & kmask));
             if (ent.y && level >= ent.x) {                                            /* observed k-mer, and the draw leaves it: :216-228 */
-                const uint32_t ro = __ldg(et.row + ent.y - 1u), cb = __ldg(et.cb + ent.y - 1u);
+                const uint32_t ro = (ent.y & 0x0fffffffu) - 1u, cb = ent.y >> 28;
                 const uint32_t idx = cb ? word >> (32u - cb) : 0u, frac = (word << cb) >> 12;
-                const uint32_t e = __ldg(et.entries + ro + idx), j = frac < (e >> 12) ? idx : (e & 0xfffu);
-                const uint32_t alt = __ldg(et.alts2 + ro + j);
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(et.ent4) + ro + idx);
+                const uint32_t alt = frac < q.x ? q.y : q.z;                          /* the column's alternate or its alias's */
                 win = alt & 0x0fffffffu; cnt = alt >> 28;
             }
             if (!cnt) {
@@ -922,7 +922,7 @@ __global__ void __launch_bounds__(256) k_kmer_errors(RunParams rp) {
         }
         for (; cnt; --cnt) { emit(win & 3u); win >>= 2; }
         while (r < L) {
-            if (!sleft) { sbuf = __ldg(src); ++src; sleft = 16u; }
+            if (!sleft) { sbuf = nextw; sleft = 16u; nextw = __ldg(++src); }
             emit(uint32_t(sbuf) & 3u); sbuf >>= 2; --sleft; ++r;
         }
         if (ocnt) dst[Ls >> 4] = ow;

@@ -130,7 +130,7 @@ struct simmr_ctx {
     ProfileModel model;
     DevMem d_phred, d_gap, d_qsub, d_rl_e, d_rl_lo, d_rl_hi, d_is_e, d_is_lo, d_is_hi;
     DevMem d_acc, d_plthr, d_rodds, d_ralias, d_roff, d_rlo, d_rhi;
-    DevMem d_err_direct, d_err_ref, d_err_keep, d_err_row, d_err_cb, d_err_entries, d_err_alts, d_err_alts2;     /* k-mer error tables */
+    DevMem d_err_direct, d_err_ref, d_err_keep, d_err_row, d_err_cb, d_err_entries, d_err_alts, d_err_direct2, d_err_ent4;     /* k-mer error tables */
     DevMem d_epacked, d_ebases;                    /* edited reads of a batch (k_kmer_errors) */
     /* run scratch */
     DevMem d_unit_start, d_counters, d_out[2];
@@ -324,7 +324,7 @@ void fill_params(simmr_ctx *ctx, RunParams &rp, uint64_t seed, uint32_t id_base,
     rp.stage_cap = pl.stage_cap; rp.one = 1;
     if (m.err.on) {
         rp.err = ErrTab{1u, m.err.k, uint32_t(m.err.ref.size()), 0u, ctx->d_err_direct.as<uint32_t>(), ctx->d_err_ref.as<uint32_t>(), ctx->d_err_keep.as<uint32_t>(),
-                        ctx->d_err_row.as<uint32_t>(), ctx->d_err_cb.as<uint32_t>(), ctx->d_err_entries.as<uint32_t>(), ctx->d_err_alts.as<uint32_t>(), ctx->d_err_alts2.as<uint32_t>()};
+                        ctx->d_err_row.as<uint32_t>(), ctx->d_err_cb.as<uint32_t>(), ctx->d_err_entries.as<uint32_t>(), ctx->d_err_alts.as<uint32_t>(), ctx->d_err_direct2.as<uint32_t>(), ctx->d_err_ent4.as<uint32_t>()};
         rp.epacked = ctx->d_epacked.as<uint32_t>(); rp.ebases = ctx->d_ebases.as<uint8_t>();
     }
 }
@@ -791,13 +791,26 @@ int simmr_error_profile_set(simmr_ctx *ctx, const simmr_eprofile_desc *d) {
         CU(ctx->d_err_keep.upload(m.err.keep_thr.data(), m.err.keep_thr.size(), s)); CU(ctx->d_err_row.upload(m.err.row.data(), m.err.row.size(), s));
         CU(ctx->d_err_cb.upload(m.err.cb.data(), m.err.cb.size(), s)); CU(ctx->d_err_entries.upload(m.err.entries.data(), m.err.entries.size(), s));
         CU(ctx->d_err_alts.upload(m.err.alts.data(), m.err.alts.size(), s));
-        std::vector<uint32_t> alts2(m.err.alts.size());          /* the alternates' bases as 2-bit codes and their number (N digits are deleted bases) */
-        for (size_t i = 0; i < alts2.size(); ++i) {
+        /* the 2-bit walk's view of the same tables (ErrTab::direct2, ent4) */
+        auto packed_alt = [&](uint32_t alt) {                    /* bases as 2-bit codes and their number (N digits are deleted bases) */
             uint32_t bases = 0, n = 0;
-            for (uint32_t dg = 0; dg < m.err.k; ++dg) { const uint32_t v = (m.err.alts[i] >> (3u * dg)) & 7u; if (v != 4u) { bases |= (v & 3u) << (2u * n); ++n; } }
-            alts2[i] = bases | (n << 28);
+            for (uint32_t dg = 0; dg < m.err.k; ++dg) { const uint32_t v = (alt >> (3u * dg)) & 7u; if (v != 4u) { bases |= (v & 3u) << (2u * n); ++n; } }
+            return bases | (n << 28);
+        };
+        if (m.err.entries.size() >= (1u << 28)) return fail(ctx, SIMMR_E_LIMIT, "alt-k-mer table too large");
+        std::vector<uint32_t> ent4(m.err.entries.size() * 4, 0), direct2(m.err.direct.size() * 2, 0);
+        for (size_t r = 0; r < m.err.row.size(); ++r) {
+            const uint32_t ro = m.err.row[r], n = 1u << m.err.cb[r];
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint32_t e = m.err.entries[ro + i];
+                ent4[4 * size_t(ro + i)] = e >> 12; ent4[4 * size_t(ro + i) + 1] = packed_alt(m.err.alts[ro + i]); ent4[4 * size_t(ro + i) + 2] = packed_alt(m.err.alts[ro + (e & 0xfffu)]);
+            }
         }
-        CU(ctx->d_err_alts2.upload(alts2.data(), alts2.size(), s));
+        for (size_t c = 0; c < m.err.direct.size(); ++c) {
+            direct2[2 * c] = m.err.direct[c].x;
+            if (m.err.direct[c].y) { const uint32_t r = m.err.direct[c].y - 1u; direct2[2 * c + 1] = (m.err.row[r] + 1u) | (m.err.cb[r] << 28); }
+        }
+        CU(ctx->d_err_direct2.upload(direct2.data(), direct2.size(), s)); CU(ctx->d_err_ent4.upload(ent4.data(), ent4.size(), s));
     }
     CU(cudaStreamSynchronize(s));
     ctx->have_profile = true;

@@ -52,7 +52,11 @@ struct ErrTab {
     uint32_t on, k, n_ref, pad_;
     const uint32_t *direct;        /* 2 words per A,C,G,T k-mer (2-bit code): keep threshold, row + 1 (0: not observed) */
     const uint32_t *ref, *keep_thr, *row, *cb, *entries, *alts;
-    const uint32_t *alts2;         /* an alternate as the 2-bit walk wants it: its bases (A,C,G,T = 0..3, N digits dropped) in the low bits, their count << 28 */
+    /* the same tables as the 2-bit walk (reads of A,C,G,T only) wants them — two dependent loads per error instead of five:
+     *   direct2[4^k]  {keep_thr, (first entry of the k-mer's alias row + 1) | cb << 28}, 0 in the second word: k-mer not observed
+     *   ent4[entry]   {thr20, the column's alternate, its alias's alternate, 0}; an alternate = its bases (A,C,G,T = 0..3, N
+     *                 digits dropped) in the low bits, their count << 28 */
+    const uint32_t *direct2, *ent4;
 };   /* perfect_long.rs:48-54 via rand_distr gamma.rs */
 
 /* which reference arithmetic the replay path applies per base */
