@@ -113,7 +113,7 @@ struct simmr_ctx {
     cudaStream_t compute = nullptr, copy = nullptr, prep = nullptr;   /* format kernels; D2H of finished batches; geometry + offsets of the next batch */
     std::string err;
     /* genomes */
-    bool have_genomes = false;
+    bool have_genomes = false, any_impure = true;   /* any_impure: some 32-byte block of `bases` holds a byte other than A,C,G,T */
     simmr_genome_set host_view{};                 /* host copies of the small tables */
     std::vector<uint64_t> h_contig_off, h_contig_size;
     std::vector<uint32_t> h_genome_contig, h_contig_id_off, h_genome_id_off;
@@ -411,14 +411,17 @@ struct Runner {
          * it averages 40 KB — 2 GiB were 16 K reads per launch, 7 per warp, and the last warps' long reads left the GPU half
          * idle (+22 %). */
         errs = ctx->model.err.on && !replay;           /* k-mer error injection between sizing and formatting */
-        uint64_t target_bytes = to_host ? (128ull << 20) : (16384ull << 20);     /* to the host: 8 pinned buffers of 128 MiB */
+        /* to the host: 8 pinned buffers of 128 MiB.  Error injection walks a read per thread, and a batch is as slow as its
+         * longest read: the more reads share a launch the better the GPU is filled (16 GiB = 343 K reads = 1.1 waves of
+         * threads ran at 43 % occupancy), so those batches take up to 64 GiB when the device has the room. */
+        uint64_t target_bytes = to_host ? (128ull << 20) : errs ? (65536ull << 20) : (16384ull << 20);
         if (measure_only) target_bytes = errs ? (4096ull << 20) : (uint64_t(pl.max_unit_bytes) << 24);
         if (!to_host && !measure_only) {
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
             free_b += ctx->d_out[0].bytes + ctx->d_out[1].bytes + ctx->d_epacked.bytes + ctx->d_ebases.bytes;       /* what this context already holds can be reused */
             /* error injection keeps a batch's edited reads beside the staging buffer: a byte and two bits per FASTQ byte */
-            while (target_bytes > (256ull << 20) && target_bytes > free_b / ((dev_sink ? 5 : 3) + (errs ? 3 : 0))) target_bytes /= 2;
+            while (target_bytes > (256ull << 20) && target_bytes > free_b / ((dev_sink ? 5 : 3) + (errs ? (ctx->any_impure ? 3 : 1) : 0))) target_bytes /= 2;
         }
         /* Bytes a batch of n units is given.  Short reads: n times the largest unit.  Long reads are 40 KB on average and
          * 131 KB at most, and a batch budgeted at the maximum holds a third of the reads it could — which left the GPU
@@ -444,7 +447,8 @@ struct Runner {
         }
         if (errs) {      /* scratch for a batch's edited reads: as many bases as the batch has FASTQ bytes, 16 more per read (err_scratch_base) */
             const uint64_t nb = out_cap + 16 * batch + 64;
-            CU(ctx->d_epacked.reserve(nb / 4 + 4 * PACK_PAD_WORDS)); CU(ctx->d_ebases.reserve(nb));
+            CU(ctx->d_epacked.reserve(nb / 4 + 4 * PACK_PAD_WORDS));
+            if (ctx->any_impure) CU(ctx->d_ebases.reserve(nb)); else ctx->d_ebases.release();      /* byte-wise scratch: only reads that hold something else than A,C,G,T use it */
         }
         CU(ctx->d_counters.reserve(64)); CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->compute));
         guard = ctx->dbg_guard; dbg_sync = ctx->dbg_sync;
@@ -762,6 +766,12 @@ int simmr_genomes_load(simmr_ctx *ctx, const simmr_genome_set *s) {
     CU(ctx->d_contig_size.upload(ctx->h_contig_size.data(), ctx->h_contig_size.size(), ctx->compute));
     CU(ctx->d_genome_contig.upload(ctx->h_genome_contig.data(), ctx->h_genome_contig.size(), ctx->compute));
     CU(cudaStreamSynchronize(ctx->compute));
+    {   /* does any window take the byte paths at all?  (error injection keeps a byte-wise scratch copy only then) */
+        const uint64_t nimpure = ((nbytes + 31) / 32 + 31) / 32 + 1;
+        std::vector<uint32_t> map(nimpure);
+        CU(cudaMemcpy(map.data(), ctx->d_impure.p, nimpure * 4, cudaMemcpyDeviceToHost));
+        ctx->any_impure = std::any_of(map.begin(), map.end(), [](uint32_t w) { return w != 0; });
+    }
     ctx->stats.h2d_bytes = nbytes;
     ctx->have_genomes = true; ctx->have_headers = false;
     return SIMMR_OK;
