@@ -414,7 +414,7 @@ struct Runner {
         /* to the host: 8 pinned buffers of 128 MiB.  Error injection walks a read per thread, and a batch is as slow as its
          * longest read: the more reads share a launch the better the GPU is filled (16 GiB = 343 K reads = 1.1 waves of
          * threads ran at 43 % occupancy), so those batches take up to 64 GiB when the device has the room. */
-        uint64_t target_bytes = to_host ? (128ull << 20) : errs ? (65536ull << 20) : (16384ull << 20);
+        uint64_t target_bytes = to_host ? (errs ? (1024ull << 20) : (128ull << 20)) : errs ? (65536ull << 20) : (16384ull << 20);   /* to the host with error injection: 1 GiB buffers, 21 K reads per launch */
         if (measure_only) target_bytes = errs ? (4096ull << 20) : (uint64_t(pl.max_unit_bytes) << 24);
         if (!to_host && !measure_only) {
             size_t free_b = 0, total_b = 0;
