@@ -869,6 +869,7 @@ __device__ __forceinline__ uint32_t err_pick_other(const ErrTab &t, uint32_t r, 
  * Afterwards the unit's descriptor points at the scratch copy (a0), L1 holds the sequence length and sizes[] the
  * record's new bytes. */
 __global__ void __launch_bounds__(256) k_kmer_errors(RunParams rp) {
+    if (batch_overflows(rp)) return;                   /* the scratch copies are as large as the staging buffer */
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= rp.batch_units) return;
     const uint32_t seg0 = t & ~(SEG_UNITS - 1u);

@@ -438,6 +438,7 @@ struct Runner {
         batch = std::min<uint64_t>(batch, 0x7fffffffull);
         while (batch > 1 && cap_of(batch) > (64ull << 30)) batch /= 2;
         out_cap = cap_of(batch) + 64;
+        if (const char *e = getenv("SIMMR_DEBUG_CAP")) out_cap = std::min<uint64_t>(out_cap, strtoull(e, nullptr, 10));   /* tests: a batch that does not fit */
         const uint32_t max_blocks = uint32_t((batch + SIZES_THREADS - 1) / SIZES_THREADS);
         const uint64_t max_segs = (batch + SEG_UNITS - 1) / SEG_UNITS;
         for (int k = 0; k < 2; ++k) {
@@ -457,6 +458,7 @@ struct Runner {
         if (to_host) for (int b = 0; b < RING; ++b) CU(ctx->h_out[b].reserve(out_cap, ctx->numa_node));
         CU(ctx->h_total.reserve(2 * sizeof(uint64_t), ctx->numa_node));
         fill_params(ctx, rp, seed, opts ? opts->read_id_base : 0, pl);
+        rp.out_cap = out_cap;
         /* error injection reads and writes one scratch set per context: its batches are prepared on the compute stream, one
          * at a time.  dbg_serial: everything on one stream (kernel timings without co-runners). */
         prep = (errs || measure_only || ctx->dbg_serial) ? ctx->compute : ctx->prep;

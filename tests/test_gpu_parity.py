@@ -281,6 +281,26 @@ def test_malformed_tables_are_refused(engine):
     assert e.value.code == S._native.E_INVALID
 
 
+def test_a_batch_that_overflows_its_buffer_is_refused(engine, monkeypatch):
+    """Long-read batches are budgeted at the typical read size, not the largest: should a batch's bytes exceed its
+    staging buffer after all, the kernels write nothing and the run fails with SIMMR_E_LIMIT (here the buffer is made
+    too small on purpose), with and without a sink, and for the k-mer error walk's scratch copies too."""
+    gs = H.synth_genomes(2, (1, 2), (80000, 90000), seed=17)
+    engine.load_genomes(gs)
+    monkeypatch.setenv("SIMMR_DEBUG_CAP", "100000")
+    for prof in (S.MinimalLongErrorProfile(30), S.CustomLongErrorProfile(H.ont_blob_with_kmers(k=5, n_alts=6)[0])):
+        engine.set_error_profile(prof)
+        with pytest.raises(S.SimmrError) as e:
+            engine.simulate([40, 40], 3)
+        assert e.value.code == S._native.E_LIMIT
+        with pytest.raises(S.SimmrError) as e:
+            engine.simulate_bytes([40, 40], 3)
+        assert e.value.code == S._native.E_LIMIT
+    monkeypatch.delenv("SIMMR_DEBUG_CAP")
+    engine.set_error_profile(S.MinimalLongErrorProfile(30))
+    assert len(engine.simulate_bytes([40, 40], 3)) > 100000
+
+
 def test_medium_scale_minimal_short(engine):
     """~1.2 M records through several batches, compared byte for byte."""
     gs = H.synth_genomes(6, (1, 6), (20000, 120000), seed=77)
