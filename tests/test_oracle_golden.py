@@ -180,7 +180,7 @@ def test_rust_float_formatting():
     assert po.format_f64(1e-7) == "0.0000001" and po.format_f64(20.0) == "20"
 
 
-@pytest.mark.parametrize("mean_q", [30, 17])
+@pytest.mark.parametrize("mean_q", [30, 17, 90])       # 90: more than 128 outcomes, 256-column tables (cb == 8)
 def test_native_tables_match_reference_arithmetic(mean_q):
     """Native mode samples quantised alias tables.  Their exact distribution must
     match draws made with the reference's own arithmetic (minimal_short.rs:83-140: f32
@@ -200,7 +200,9 @@ def test_native_tables_match_reference_arithmetic(mean_q):
     po.lib().orc_ref_mutate(seq.ctypes.data_as(po.u8p), q.ctypes.data_as(po.u8p), C.c_uint64(n), C.c_uint64(9),
                             out.ctypes.data_as(po.u8p))
     rate_ref = float((out != seq).mean())
-    assert abs(rate_ref - rate) < 6 * np.sqrt(rate / n), (rate_ref, rate)
+    assert abs(rate_ref - rate) <= 6 * np.sqrt(rate / n) + 2.0 / n, (rate_ref, rate)
+    if rate * n < 1000:                                                  # mean 90: a substitution in 10^7 bases, nothing to compare
+        return
     if mean_q == 30:
         assert abs(rate - 0.01340) < 2e-4                                # 1.340 %
     # quality of the substituted bases (the reference substitutes after drawing q: P(q | substituted))
